@@ -1,0 +1,196 @@
+"""ctypes binding of lip2speech_b200/lib/libl2s_b200.so (C ABI: include/l2s_b200.h).
+
+There is no fallback: if the library is missing or fails, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libl2s_b200.so")
+
+PART_VIDEO, PART_SPEAKER, PART_DECODER = 1, 2, 4
+PRECISION_FP32, PRECISION_BF16 = 0, 1
+
+EXPORTS = ("l2s_version", "l2s_create", "l2s_destroy", "l2s_last_error", "l2s_bind_weight", "l2s_commit_weights",
+           "l2s_video_fwd", "l2s_speaker_fwd", "l2s_decoder_infer", "l2s_postnet_fwd", "l2s_infer", "l2s_infer_host",
+           "l2s_launch_count", "l2s_debug_read")
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load() -> C.CDLL:
+    """Load the shared library (no compute, no GPU needed) and declare the prototypes."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} not found: build it with `python -m lip2speech_b200.build` "
+                               "(there is no CPU or PyTorch fallback)")
+        lib = C.CDLL(LIB_PATH)
+        vp, i, i64p, fp = C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.c_void_p
+        lib.l2s_version.restype = i
+        lib.l2s_create.argtypes = [C.POINTER(vp), i]
+        lib.l2s_destroy.argtypes = [vp]; lib.l2s_destroy.restype = None
+        lib.l2s_last_error.argtypes = [vp]; lib.l2s_last_error.restype = C.c_char_p
+        lib.l2s_bind_weight.argtypes = [vp, C.c_char_p, vp, i64p, i, i, i]
+        lib.l2s_commit_weights.argtypes = [vp, i]
+        lib.l2s_video_fwd.argtypes = [vp, fp, i, i, i, i, fp, i, vp]
+        lib.l2s_speaker_fwd.argtypes = [vp, fp, i, i, fp, i, vp]
+        lib.l2s_decoder_infer.argtypes = [vp, fp, fp, fp, i, i, i, fp, vp, fp, vp]
+        lib.l2s_postnet_fwd.argtypes = [vp, fp, i, i, fp, i, vp]
+        lib.l2s_infer.argtypes = [vp, fp, fp, fp, i, i, i, i, i, i, fp, vp, i, vp]
+        lib.l2s_infer_host.argtypes = [vp, fp, fp, fp, i, i, i, i, i, i, fp, vp, i]
+        lib.l2s_launch_count.argtypes = [vp]; lib.l2s_launch_count.restype = C.c_int64
+        lib.l2s_debug_read.argtypes = [vp, C.c_char_p, fp, C.c_int64]; lib.l2s_debug_read.restype = C.c_int64
+        _lib = lib
+        return lib
+
+
+def _f32c(t: torch.Tensor, device) -> torch.Tensor:
+    if t.dtype != torch.float32 or not t.is_contiguous() or t.device != device:
+        t = t.to(device=device, dtype=torch.float32).contiguous()
+    return t
+
+
+class Backend:
+    """One l2s_ctx on one CUDA device."""
+
+    def __init__(self, device: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("lip2speech_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = load()
+        self.device = torch.device("cuda", device)
+        h = C.c_void_p()
+        rc = self.lib.l2s_create(C.byref(h), device)
+        if rc != 0:
+            raise RuntimeError("l2s_create failed: " + self.lib.l2s_last_error(None).decode())
+        self.h = h
+        self._sig = {}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.l2s_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed ({rc}): " + self.lib.l2s_last_error(self.h).decode())
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- weights ---------------------------------------------------------------------------------
+    def bind_state_dict(self, sd, prefix: str, part: int):
+        """Bind every tensor of `sd` under `prefix + key` and commit `part`."""
+        for k, t in sd.items():
+            t = t.detach()
+            if t.dtype == torch.int64:
+                dtype = 1
+            else:
+                dtype = 0
+                if t.dtype != torch.float32:
+                    t = t.float()
+            t = t.contiguous()
+            shape = (C.c_int64 * max(t.dim(), 1))(*t.shape)
+            rc = self.lib.l2s_bind_weight(self.h, (prefix + k).encode(), C.c_void_p(t.data_ptr()), shape, t.dim(), dtype,
+                                          1 if t.is_cuda else 0)
+            self._check(rc, f"l2s_bind_weight({prefix + k})")
+        self._check(self.lib.l2s_commit_weights(self.h, part), "l2s_commit_weights")
+
+    def sync_module(self, module: torch.nn.Module, prefix: str, part: int):
+        """(Re)bind when any parameter/buffer changed (data_ptr or in-place version counter)."""
+        sd = module.state_dict(keep_vars=True)
+        sig = tuple((k, t.data_ptr(), t._version) for k, t in sd.items())
+        if self._sig.get(prefix) != sig:
+            self.bind_state_dict(sd, prefix, part)
+            self._sig[prefix] = sig
+
+    # ---- forward calls ---------------------------------------------------------------------------
+    def video_fwd(self, video: torch.Tensor, precision: int = PRECISION_FP32) -> torch.Tensor:
+        video = _f32c(video, self.device)
+        B, Cc, T, H, W = video.shape
+        assert Cc == 3
+        out = torch.empty(B, T, 768, device=self.device, dtype=torch.float32)
+        self._check(self.lib.l2s_video_fwd(self.h, video.data_ptr(), B, T, H, W, out.data_ptr(), precision, self._stream()), "l2s_video_fwd")
+        return out
+
+    def speaker_fwd(self, wav: torch.Tensor, normalize: bool) -> torch.Tensor:
+        wav = _f32c(wav, self.device)
+        B, S = wav.shape
+        out = torch.empty(B, 256, device=self.device, dtype=torch.float32)
+        self._check(self.lib.l2s_speaker_fwd(self.h, wav.data_ptr(), B, S, out.data_ptr(), int(normalize), self._stream()), "l2s_speaker_fwd")
+        return out
+
+    def decoder_infer(self, visual, spk, gumbel, steps: int = 300, return_attention: bool = False):
+        visual, spk, gumbel = _f32c(visual, self.device), _f32c(spk, self.device), _f32c(gumbel, self.device)
+        B, T, D = visual.shape
+        assert D == 1024 and spk.shape == (B, 256)
+        mel = torch.empty(B, 80, steps, device=self.device, dtype=torch.float32)
+        lengths = torch.empty(B, device=self.device, dtype=torch.int64)
+        attn = torch.empty(B, steps, T, device=self.device, dtype=torch.float32) if return_attention else None
+        self._check(self.lib.l2s_decoder_infer(self.h, visual.data_ptr(), spk.data_ptr(), gumbel.data_ptr(), B, T, steps, mel.data_ptr(),
+                                               C.c_void_p(lengths.data_ptr()), attn.data_ptr() if attn is not None else None,
+                                               self._stream()), "l2s_decoder_infer")
+        return (mel, lengths, attn) if return_attention else (mel, lengths)
+
+    def postnet_fwd(self, x: torch.Tensor, add_residual: bool = False) -> torch.Tensor:
+        x = _f32c(x, self.device)
+        B, Cc, L = x.shape
+        assert Cc == 80
+        out = torch.empty_like(x)
+        self._check(self.lib.l2s_postnet_fwd(self.h, x.data_ptr(), B, L, out.data_ptr(), int(add_residual), self._stream()), "l2s_postnet_fwd")
+        return out
+
+    def infer(self, video, wav, gumbel, steps: int = 300, precision: int = PRECISION_FP32):
+        video, wav, gumbel = _f32c(video, self.device), _f32c(wav, self.device), _f32c(gumbel, self.device)
+        B, _, T, H, W = video.shape
+        mel = torch.empty(B, 80, steps, device=self.device, dtype=torch.float32)
+        lengths = torch.empty(B, device=self.device, dtype=torch.int64)
+        self._check(self.lib.l2s_infer(self.h, video.data_ptr(), wav.data_ptr(), gumbel.data_ptr(), B, T, H, W, wav.shape[1], steps,
+                                       mel.data_ptr(), C.c_void_p(lengths.data_ptr()), precision, self._stream()), "l2s_infer")
+        return mel, lengths
+
+    def infer_host(self, video, wav, gumbel, mel_out, lengths_out, steps: int = 300, precision: int = PRECISION_FP32):
+        """All arguments are HOST tensors (ideally pinned); synchronous."""
+        B, _, T, H, W = video.shape
+        for t in (video, wav, gumbel, mel_out):
+            assert t.device.type == "cpu" and t.dtype == torch.float32 and t.is_contiguous()
+        self._check(self.lib.l2s_infer_host(self.h, video.data_ptr(), wav.data_ptr(), gumbel.data_ptr(), B, T, H, W, wav.shape[1], steps,
+                                            mel_out.data_ptr(), C.c_void_p(lengths_out.data_ptr()), precision), "l2s_infer_host")
+
+    def launch_count(self) -> int:
+        return int(self.lib.l2s_launch_count(self.h))
+
+    def debug_read(self, name: str, shape) -> torch.Tensor:
+        n = 1
+        for s in shape:
+            n *= s
+        out = torch.empty(n, dtype=torch.float32)
+        got = self.lib.l2s_debug_read(self.h, name.encode(), out.data_ptr(), n)
+        if got < 0:
+            raise KeyError(name)
+        assert got == n, (name, got, n)
+        return out.view(*shape)
+
+
+_backends = {}
+
+
+def backend(device: int = 0) -> Backend:
+    """Process-wide context per device."""
+    if device not in _backends:
+        _backends[device] = Backend(device)
+    return _backends[device]

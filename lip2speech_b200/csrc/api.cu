@@ -1,0 +1,565 @@
+// C ABI of lip2speech_b200 (include/l2s_b200.h): context, weight binding, and the orchestration of the
+// CUDA kernels for the three reference modules on the inference hot path.
+#include "../../include/l2s_b200.h"
+
+#include "context.h"
+#include "decode.cuh"
+#include "gemm.cuh"
+#include "lstm.cuh"
+#include "misc.cuh"
+#include "pack.h"
+#include "video.cuh"
+
+using namespace l2s;
+
+struct l2s_ctx {
+    Context c;
+};
+
+static std::string g_create_err;
+
+#define API_BEGIN try {
+#define API_END(ctxp)                                                         \
+    }                                                                         \
+    catch (const L2sError& e) { (ctxp)->c.err = e.what(); return e.code; }    \
+    catch (const std::exception& e) { (ctxp)->c.err = e.what(); return L2S_ERR_INVALID; } \
+    return L2S_OK;
+
+static inline void check_launch(Context& c, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw L2sError(L2S_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    c.launches++;
+}
+
+static inline int ew_grid(size_t total, int threads = 256) {
+    size_t g = (total + threads - 1) / threads;
+    return (int)std::min<size_t>(std::max<size_t>(g, 1), 148 * 16);
+}
+
+static void run_gemm(Context& c, GemmParams p, cudaStream_t s, const char* what) {
+    cudaError_t e = launch_gemm(p, s);
+    if (e != cudaSuccess) throw L2sError(L2S_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    c.launches++;
+}
+
+// plain linear: C[M,N] = act(A[M,K] W[N,K]^T + b)
+static void linear(Context& c, const float* A, int lda, const float* W, const float* b, float* C, int ldc, int M, int N, int K,
+                   int act, const float* act_w, cudaStream_t s, const char* what) {
+    GemmParams p = gemm_defaults();
+    p.A = A; p.lda = lda; p.W = W; p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.Kc = K; p.bias = b; p.act = act; p.act_w = act_w;
+    run_gemm(c, p, s, what);
+}
+
+// ------------------------------------------------------------------------------------------------
+// video frontend
+// ------------------------------------------------------------------------------------------------
+static void video_forward(Context& c, const float* video, int B, int T, int H, int W, float* out_feat, int precision, cudaStream_t s) {
+    if (B <= 0 || T <= 0 || (H & 3) || (W & 3)) throw L2sError(L2S_ERR_INVALID, "video_fwd: bad shape");
+    (void)precision;   // bf16 tensor-core stem is selected here once enabled; fp32 path below
+    const int N = B * T;
+    const int Ho = H / 2, Wo = W / 2;                 // Conv3d stride (1,2,2), pad 3, k 7
+    const int Hp = (Ho - 1) / 2 + 1, Wp = (Wo - 1) / 2 + 1;   // MaxPool 3x3 s2 p1
+    float* stem = c.fbuf("ws.v.stem", (size_t)N * Ho * Wo * 24);
+    {
+        GemmParams p = gemm_defaults();
+        p.stem = 1; p.A = video; p.W = c.dev("v.stem.w"); p.C = stem; p.ldc = 24;
+        p.M = N * Ho * Wo; p.N = 24; p.Kc = 735; p.taps = 1; p.L_out = p.M; p.L_in = p.M;
+        p.bias = c.dev("v.stem.b"); p.act = ACT_PRELU; p.act_w = c.dev("v.stem.prelu");
+        p.T = T; p.H = H; p.Wd = W; p.Ho = Ho; p.Wo = Wo;
+        run_gemm(c, p, s, "stem conv3d");
+    }
+    // activation ping-pong and branch temporaries, sized for the largest stage
+    int h = Hp, w = Wp;
+    const size_t rows0 = (size_t)N * h * w;
+    float* xa = c.fbuf("ws.v.xa", rows0 * 32);     // >= N*24*24*24 and >= N*12*12*120
+    float* xb = c.fbuf("ws.v.xb", rows0 * 32);
+    float* t1 = c.fbuf("ws.v.t1", rows0 * 64);     // dw outputs (quarter resolution) / pw1 outputs (full res, hp<=60 at stage 2)
+    float* t2 = c.fbuf("ws.v.t2", rows0 * 64);
+    {
+        size_t total = rows0 * 6;
+        maxpool3x3s2_kernel<<<ew_grid(total), 256, 0, s>>>(stem, xa, N, Ho, Wo, 24, Hp, Wp);
+        check_launch(c, "maxpool");
+    }
+    float* x = xa; float* y = xb;
+    const int nblk = (int)c.meta.at("v.nblocks");
+    for (int i = 0; i < nblk; ++i) {
+        const std::string n = "v.b" + std::to_string(i) + ".";
+        const int down = (int)c.meta.at(n + "down"), cin_phys = (int)c.meta.at(n + "cin_phys");
+        const int half = (int)c.meta.at(n + "half"), hp = (int)c.meta.at(n + "hp");
+        const int cph = 2 * hp;
+        if (down) {
+            const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
+            const size_t rin = (size_t)N * h * w, rout = (size_t)N * ho * wo;
+            // branch1: dw s2 (all input channels) -> 1x1 -> logical channel 2j
+            dwconv3x3_kernel<<<ew_grid(rout * (cin_phys / 4)), 256, 0, s>>>(x, cin_phys, 0, t1, cin_phys, 0, c.dev(n + "b1dw.w"), c.dev(n + "b1dw.b"),
+                                                                          N, h, w, cin_phys, 2, ho, wo);
+            check_launch(c, "b1 dw");
+            GemmParams p = gemm_defaults();
+            p.A = t1; p.lda = cin_phys; p.W = c.dev(n + "b1pw.w"); p.bias = c.dev(n + "b1pw.b"); p.act = ACT_RELU;
+            p.C = y; p.ldc = cph; p.M = (int)rout; p.N = half; p.Kc = cin_phys; p.cstride = 2; p.coff = 0; p.chalf = half; p.chp = hp;
+            run_gemm(c, p, s, "b1 pw");
+            // branch2: 1x1 (full res) -> dw s2 -> 1x1 -> logical channel 2j+1
+            p = gemm_defaults();
+            p.A = x; p.lda = cin_phys; p.W = c.dev(n + "b2pw1.w"); p.bias = c.dev(n + "b2pw1.b"); p.act = ACT_RELU;
+            p.C = t2; p.ldc = hp; p.M = (int)rin; p.N = half; p.Kc = cin_phys;
+            run_gemm(c, p, s, "b2 pw1");
+            dwconv3x3_kernel<<<ew_grid(rout * (hp / 4)), 256, 0, s>>>(t2, hp, 0, t1, hp, 0, c.dev(n + "b2dw.w"), c.dev(n + "b2dw.b"), N, h, w, hp, 2, ho, wo);
+            check_launch(c, "b2 dw");
+            p = gemm_defaults();
+            p.A = t1; p.lda = hp; p.W = c.dev(n + "b2pw2.w"); p.bias = c.dev(n + "b2pw2.b"); p.act = ACT_RELU;
+            p.C = y; p.ldc = cph; p.M = (int)rout; p.N = half; p.Kc = hp; p.cstride = 2; p.coff = 1; p.chalf = half; p.chp = hp;
+            run_gemm(c, p, s, "b2 pw2");
+            h = ho; w = wo;
+        } else {
+            const size_t rows = (size_t)N * h * w;
+            shuffle_passthrough_kernel<<<ew_grid(rows * half), 256, 0, s>>>(x, y, rows, cph, half, hp);
+            check_launch(c, "passthrough");
+            GemmParams p = gemm_defaults();
+            p.A = x + hp; p.lda = cph; p.W = c.dev(n + "b2pw1.w"); p.bias = c.dev(n + "b2pw1.b"); p.act = ACT_RELU;
+            p.C = t2; p.ldc = hp; p.M = (int)rows; p.N = half; p.Kc = hp;
+            run_gemm(c, p, s, "b2 pw1");
+            dwconv3x3_kernel<<<ew_grid(rows * (hp / 4)), 256, 0, s>>>(t2, hp, 0, t1, hp, 0, c.dev(n + "b2dw.w"), c.dev(n + "b2dw.b"), N, h, w, hp, 1, h, w);
+            check_launch(c, "b2 dw");
+            p = gemm_defaults();
+            p.A = t1; p.lda = hp; p.W = c.dev(n + "b2pw2.w"); p.bias = c.dev(n + "b2pw2.b"); p.act = ACT_RELU;
+            p.C = y; p.ldc = cph; p.M = (int)rows; p.N = half; p.Kc = hp; p.cstride = 2; p.coff = 1; p.chalf = half; p.chp = hp;
+            run_gemm(c, p, s, "b2 pw2");
+        }
+        std::swap(x, y);
+    }
+    if (h != 3 || w != 3) throw L2sError(L2S_ERR_INVALID, "video_fwd: trunk output must be 3x3 (H,W in {88,96}) for AvgPool2d(3)");
+    const int Kl = (int)c.meta.at("v.last.k"), Nl = (int)c.meta.at("v.last.n");
+    float* last = c.fbuf("ws.v.last", (size_t)N * 9 * Nl);
+    linear(c, x, Kl, c.dev("v.last.w"), c.dev("v.last.b"), last, Nl, N * 9, Nl, Kl, ACT_RELU, nullptr, s, "conv_last");
+    avgpool_l2norm_kernel<<<N, 256, Nl * sizeof(float), s>>>(last, out_feat, 9, Nl);
+    check_launch(c, "avgpool_l2norm");
+}
+
+// ------------------------------------------------------------------------------------------------
+// persistent LSTM launch helper
+// ------------------------------------------------------------------------------------------------
+static void launch_lstm(Context& c, LstmParams lp, cudaStream_t s) {
+    unsigned* bar = static_cast<unsigned*>(c.buf("ws.barrier", 256));
+    L2S_CUDA(cudaMemsetAsync(bar, 0, 4, s));
+    lp.barrier = bar;
+    const size_t smem = ((size_t)lp.max_chunks * 16 * 2 * lp.H + MV_WARPS * 16 * MV_CLIPS + 16 * MV_CLIPS) * sizeof(float);
+    L2S_CUDA(cudaFuncSetAttribute(lstm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = std::min(c.num_sms, lp.nchunks);
+    void* args[] = {&lp};
+    L2S_CUDA(cudaLaunchCooperativeKernel((void*)lstm_persistent_kernel, dim3(grid), dim3(MV_THREADS), args, smem, s));
+    c.launches++;
+}
+
+// ------------------------------------------------------------------------------------------------
+// speaker encoder
+// ------------------------------------------------------------------------------------------------
+static void speaker_forward(Context& c, const float* wav, int B, int S, float* emb, int normalize, cudaStream_t s) {
+    if (B <= 0 || S < 401) throw L2sError(L2S_ERR_INVALID, "speaker_fwd: bad shape");
+    const int F = 1 + S / 160, H = 256, L = 3;
+    const int Bpad = round_up(B, 32);
+    float* mel = c.fbuf("ws.s.mel", (size_t)B * F * 40);
+    melspec_kernel<<<B * F, 256, 0, s>>>(wav, c.dev("s.window"), c.dev("s.fb"), mel, S, F);
+    check_launch(c, "melspec");
+    float* xproj = c.fbuf("ws.s.xproj", (size_t)B * F * 4 * H);
+    linear(c, mel, 40, c.dev("s.wih0"), c.dev("s.b0"), xproj, 4 * H, B * F, 4 * H, 40, ACT_NONE, nullptr, s, "speaker xproj");
+    const size_t plane = (size_t)H * Bpad;
+    float* hbuf = c.fbuf("ws.s.h", 2 * L * plane);
+    float* cbuf = c.fbuf("ws.s.c", L * plane);
+    L2S_CUDA(cudaMemsetAsync(hbuf, 0, 2 * L * plane * sizeof(float), s));
+    L2S_CUDA(cudaMemsetAsync(cbuf, 0, L * plane * sizeof(float), s));
+    LstmParams lp{};
+    lp.xproj = xproj; lp.ldx = 4 * H; lp.wpk = c.dev("s.lstm.w");
+    lp.chunks = reinterpret_cast<const LstmChunk*>(c.dev("s.lstm.chunks")); lp.nchunks = (int)c.meta.at("s.lstm.nchunks");
+    lp.hbuf = hbuf; lp.cbuf = cbuf; lp.out = nullptr; lp.ldo = 0;
+    lp.T = F; lp.B = B; lp.Bpad = Bpad; lp.H = H; lp.L = L; lp.dirs = 1; lp.max_chunks = (int)c.meta.at("s.lstm.max_chunks");
+    launch_lstm(c, lp, s);
+    const int nsteps = F + L - 1;
+    const float* hfinal = hbuf + (size_t)(nsteps & 1) * L * plane + (size_t)(L - 1) * plane;
+    speaker_head_kernel<<<B, 256, 0, s>>>(hfinal, Bpad, c.dev("s.lin.w"), c.dev("s.lin.b"), emb, normalize);
+    check_launch(c, "speaker head");
+}
+
+// ------------------------------------------------------------------------------------------------
+// postnet (time-major rows [B*L][C])
+// ------------------------------------------------------------------------------------------------
+static void postnet_rows(Context& c, const float* x_rows /*[B*L][80]*/, int B, int L, float* out_bcl /*[B][80][L]*/, bool add_residual, cudaStream_t s) {
+    const int M = B * L;
+    float* a = c.fbuf("ws.p.a", (size_t)M * 512);
+    float* b = c.fbuf("ws.p.b", (size_t)M * 512);
+    const float* in = x_rows; int cin = 80;
+    float* bufs[2] = {a, b};
+    for (int i = 0; i < 5; ++i) {
+        const std::string n = "d.post" + std::to_string(i);
+        GemmParams p = gemm_defaults();
+        p.A = in; p.lda = cin; p.W = c.dev(n + ".w"); p.bias = c.dev(n + ".b");
+        p.M = M; p.Kc = cin; p.taps = 5; p.pad = 2; p.stride = 1; p.L_out = L; p.L_in = L;
+        if (i < 4) {
+            p.N = 512; p.C = bufs[i & 1]; p.ldc = 512; p.act = ACT_PSINE; p.act_w = c.dev(n + ".psw");
+            if (i != 0) { p.resid = in; p.ldr = 512; }
+        } else {
+            p.N = 80; p.C = out_bcl; p.transposed = 1; p.act = ACT_NONE;
+            if (add_residual) { p.resid = x_rows; p.ldr = 80; }
+        }
+        run_gemm(c, p, s, "postnet conv");
+        in = bufs[i & 1]; cin = 512;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// decoder
+// ------------------------------------------------------------------------------------------------
+static void decoder_infer(Context& c, const float* visual, const float* spk, const float* gumbel, int B, int T, int steps,
+                          float* mel_post, int64_t* lengths, float* attn, cudaStream_t s) {
+    if (B <= 0 || T < 7 || T > 300 || steps <= 0 || steps > 300) throw L2sError(L2S_ERR_INVALID, "decoder_infer: need 7<=T<=300, 1<=steps<=300 (pos_table has 300 rows)");
+    if (!gumbel) throw L2sError(L2S_ERR_INVALID, "decoder_infer: gumbel noise tensor is required");
+    const int M = B * T, Bpad = round_up(B, 32);
+    int minT = T;
+    const int cks[4] = {1, 3, 5, 7};
+    int Lc[4];
+    for (int j = 0; j < 4; ++j) { Lc[j] = (T - cks[j]) / cks[j] + 1; minT = std::min(minT, Lc[j]); }
+    const float* pos = c.dev("d.pos");
+
+    // ---- encoder pre-loop (decoder.py:383-394) --------------------------------------------------
+    float* resid = c.fbuf("ws.d.resid", (size_t)M * 512);
+    linear(c, visual, 1024, c.dev("d.resid.w"), c.dev("d.resid.b"), resid, 512, M, 512, 1024, ACT_NONE, nullptr, s, "residual_bottleneck");
+    float* encsite = c.fbuf("ws.d.encsite", (size_t)B * 512);
+    float* attsite = c.fbuf("ws.d.attsite", (size_t)B * 512);
+    linear(c, spk, 256, c.dev("d.encsite.w"), c.dev("d.encsite.b"), encsite, 512, B, 512, 256, ACT_PSINE, c.dev("d.encsite.psw"), s, "encoder_site");
+    linear(c, spk, 256, c.dev("d.attsite.w"), c.dev("d.attsite.b"), attsite, 512, B, 512, 256, ACT_PSINE, c.dev("d.attsite.psw"), s, "attention_site");
+    float* xproj = c.fbuf("ws.d.xproj", (size_t)M * 4096);
+    linear(c, visual, 1024, c.dev("d.ernn.wih"), c.dev("d.ernn.b"), xproj, 4096, M, 4096, 1024, ACT_NONE, nullptr, s, "encoder_rnn xproj");
+    const size_t plane = (size_t)512 * Bpad;
+    float* eh = c.fbuf("ws.d.eh", 2 * 2 * plane);      // [parity][dir][512][Bpad]
+    float* ec = c.fbuf("ws.d.ec", 2 * plane);
+    for (int i = 0; i < 4; ++i) {
+        rows_to_fm_kernel<<<ew_grid(plane), 256, 0, s>>>(encsite, 512, 0, eh + i * plane, 512, B, Bpad);
+        check_launch(c, "site->fm");
+    }
+    for (int i = 0; i < 2; ++i) {
+        rows_to_fm_kernel<<<ew_grid(plane), 256, 0, s>>>(encsite, 512, 0, ec + i * plane, 512, B, Bpad);
+        check_launch(c, "site->fm");
+    }
+    float* rnn_out = c.fbuf("ws.d.rnnout", (size_t)M * 1024);
+    {
+        LstmParams lp{};
+        lp.xproj = xproj; lp.ldx = 4096; lp.wpk = c.dev("d.ernn.w");
+        lp.chunks = reinterpret_cast<const LstmChunk*>(c.dev("d.ernn.chunks")); lp.nchunks = (int)c.meta.at("d.ernn.nchunks");
+        lp.hbuf = eh; lp.cbuf = ec; lp.out = rnn_out; lp.ldo = 1024;
+        lp.T = T; lp.B = B; lp.Bpad = Bpad; lp.H = 512; lp.L = 1; lp.dirs = 2; lp.max_chunks = (int)c.meta.at("d.ernn.max_chunks");
+        launch_lstm(c, lp, s);
+    }
+    const float* hfinal = eh + (size_t)(T & 1) * 2 * plane;      // feature-major [h_fwd ; h_bwd] = decoder (h0 ; h1)
+    float* ccat = c.fbuf("ws.d.ccat", (size_t)B * 1024);
+    fm_to_rows_kernel<<<ew_grid((size_t)1024 * B), 256, 0, s>>>(ec, Bpad, ccat, 1024, 0, 1024, B);
+    check_launch(c, "c_n -> rows");
+    float* enc_cell = c.fbuf("ws.d.enc_cell", (size_t)B * 512);
+    linear(c, ccat, 1024, c.dev("d.ec.w"), c.dev("d.ec.b"), enc_cell, 512, B, 512, 1024, ACT_NONE, nullptr, s, "E_C");
+    float* enc = c.fbuf("ws.d.enc", (size_t)M * 512);
+    {
+        GemmParams p = gemm_defaults();
+        p.A = rnn_out; p.lda = 1024; p.W = c.dev("d.encproj.w"); p.bias = c.dev("d.encproj.b"); p.C = enc; p.ldc = 512;
+        p.M = M; p.N = 512; p.Kc = 1024; p.L_out = T; p.L_in = T; p.addrow = attsite; p.resid = resid; p.ldr = 512;
+        run_gemm(c, p, s, "encoder_proj");
+    }
+    // ---- K / V (MultiHopConv + PSine + positions, decoder.py:396-399) -----------------------------
+    float* cat = c.fbuf("ws.d.cat", (size_t)M * 2560);
+    float* Kmem = c.fbuf("ws.d.K", (size_t)M * 512);
+    float* Vmem = c.fbuf("ws.d.V", (size_t)M * 512);
+    L2S_CUDA(cudaMemcpy2DAsync(cat, 2560 * sizeof(float), enc, 512 * sizeof(float), 512 * sizeof(float), M, cudaMemcpyDeviceToDevice, s));
+    const int mks[4] = {1, 3, 7, 11};
+    for (int kv = 0; kv < 2; ++kv) {
+        const std::string n = kv == 0 ? "d.K" : "d.V";
+        for (int j = 0; j < 4; ++j) {
+            GemmParams p = gemm_defaults();
+            p.A = enc; p.lda = 512; p.W = c.dev(n + ".c" + std::to_string(j) + ".w"); p.bias = c.dev(n + ".c" + std::to_string(j) + ".b");
+            p.C = cat; p.ldc = 2560; p.coff = 512 * (j + 1); p.M = M; p.N = 512; p.Kc = 512; p.taps = mks[j]; p.pad = mks[j] / 2;
+            p.L_out = T; p.L_in = T; p.act = ACT_SILU;
+            run_gemm(c, p, s, "multihop conv");
+        }
+        GemmParams p = gemm_defaults();
+        p.A = cat; p.lda = 2560; p.W = c.dev(n + ".bn.w"); p.bias = c.dev(n + ".bn.b"); p.C = kv == 0 ? Kmem : Vmem; p.ldc = 512;
+        p.M = M; p.N = 512; p.Kc = 2560; p.L_out = T; p.L_in = T; p.act = ACT_PSINE; p.act_w = c.dev(n + ".psw"); p.addpos = pos; p.ldpos = 512;
+        run_gemm(c, p, s, "multihop bottleneck");
+    }
+    // ---- Content.encode (decoder.py:239-260) -----------------------------------------------------
+    const int Mc = B * minT;
+    float* ccat2 = c.fbuf("ws.d.ccat2", (size_t)Mc * 2560);
+    float* ctmp = c.fbuf("ws.d.ctmp", (size_t)M * 512);
+    adaptive_pool_kernel<<<ew_grid((size_t)Mc * 512), 256, 0, s>>>(enc, 512, T, ccat2, 2560, 0, minT, 512, B);
+    check_launch(c, "adaptive pool");
+    for (int j = 0; j < 4; ++j) {
+        GemmParams p = gemm_defaults();
+        p.A = enc; p.lda = 512; p.W = c.dev("d.cagg" + std::to_string(j) + ".w"); p.bias = c.dev("d.cagg" + std::to_string(j) + ".b");
+        p.C = ctmp; p.ldc = 512; p.M = B * Lc[j]; p.N = 512; p.Kc = 512; p.taps = cks[j]; p.pad = 0; p.stride = cks[j];
+        p.L_out = Lc[j]; p.L_in = T; p.act = ACT_SILU;
+        run_gemm(c, p, s, "content agg conv");
+        adaptive_pool_kernel<<<ew_grid((size_t)Mc * 512), 256, 0, s>>>(ctmp, 512, Lc[j], ccat2, 2560, 512 * (j + 1), minT, 512, B);
+        check_launch(c, "adaptive pool");
+    }
+    float* cw = c.fbuf("ws.d.cw", (size_t)Mc * 256);
+    float* cu = c.fbuf("ws.d.cu", (size_t)Mc * 256);
+    float* cv2 = c.fbuf("ws.d.cv2", (size_t)Mc * 256);
+    float* ckey = c.fbuf("ws.d.ckey", (size_t)Mc * 256);
+    float* cval = c.fbuf("ws.d.cval", (size_t)Mc * 256);
+    float* clog = c.fbuf("ws.d.clog", (size_t)Mc * 501);
+    linear(c, ccat2, 2560, c.dev("d.cbn.w"), c.dev("d.cbn.b"), cw, 256, Mc, 256, 2560, ACT_NONE, nullptr, s, "content bottleneck");
+    linear(c, cw, 256, c.dev("d.ck0.w"), c.dev("d.ck0.b"), cu, 256, Mc, 256, 256, ACT_SILU, nullptr, s, "content K.0");
+    linear(c, cu, 256, c.dev("d.ck2.w"), c.dev("d.ck2.b"), ckey, 256, Mc, 256, 256, ACT_SILU, nullptr, s, "content K.2");
+    linear(c, cw, 256, c.dev("d.cloc0.w"), c.dev("d.cloc0.b"), cu, 256, Mc, 256, 256, ACT_SILU, nullptr, s, "location_fc.0");
+    linear(c, cu, 256, c.dev("d.cloc2.w"), c.dev("d.cloc2.b"), cv2, 256, Mc, 256, 256, ACT_SILU, nullptr, s, "location_fc.2");
+    linear(c, cv2, 256, c.dev("d.cloc4.w"), c.dev("d.cloc4.b"), clog, 501, Mc, 501, 256, ACT_SILU, nullptr, s, "location_fc.4");
+    gumbel_value_kernel<<<Mc, 256, 501 * sizeof(float), s>>>(clog, gumbel, 1.0f / 0.1f, c.dev("d.cemb"), cval, nullptr, 501);
+    check_launch(c, "gumbel value");
+    // ---- stop-token constant, initial state --------------------------------------------------------
+    float* stopc = c.fbuf("ws.d.stopc", (size_t)B);
+    linear(c, enc_cell, 512, c.dev("d.stop.w2"), nullptr, stopc, 1, B, 1, 512, ACT_NONE, nullptr, s, "stop const");
+    float* S = c.fbuf("ws.d.S", 2 * 2 * plane);
+    float* Cst = c.fbuf("ws.d.Cst", 2 * plane);
+    L2S_CUDA(cudaMemcpyAsync(S, hfinal, 2 * plane * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    L2S_CUDA(cudaMemsetAsync(Cst, 0, 2 * plane * sizeof(float), s));           // cell.fill_(0), decoder.py:406
+    float* outputs = c.fbuf("ws.d.outputs", (size_t)B * steps * 80);
+    fill_i64_kernel<<<ceil_div(B, 256), 256, 0, s>>>(reinterpret_cast<long long*>(lengths), (long long)steps, B);
+    check_launch(c, "lengths init");
+
+    // ---- the 300-step loop: one persistent cooperative kernel ------------------------------------
+    {
+        DecodeParams dp{};
+        dp.passes = reinterpret_cast<const DecPass*>(c.dev("d.step.passes"));
+        dp.npasses = reinterpret_cast<const int*>(c.dev("d.step.npasses"));
+        dp.wimg = c.dev("d.step.wimg"); dp.wimg_floats = (int)c.meta.at("d.step.wimg_floats");
+        dp.S = S; dp.Cst = Cst;
+        dp.P1 = c.fbuf("ws.d.P1", (size_t)256 * Bpad); dp.P2 = c.fbuf("ws.d.P2", (size_t)256 * Bpad);
+        dp.Q = c.fbuf("ws.d.Q", (size_t)512 * Bpad); dp.CQ = c.fbuf("ws.d.CQ", (size_t)256 * Bpad);
+        dp.CTX = c.fbuf("ws.d.CTX", (size_t)512 * Bpad); dp.XD = c.fbuf("ws.d.XD", (size_t)512 * Bpad);
+        dp.Kmem = Kmem; dp.Vmem = Vmem; dp.ckey = ckey; dp.cval = cval; dp.stop_const = stopc; dp.pos = pos;
+        dp.temp = c.W("decoder.temperature").f[0]; dp.ctemp = c.W("decoder.content.temperature").f[0];
+        dp.outputs = outputs; dp.lengths = reinterpret_cast<long long*>(lengths); dp.attn = attn;
+        dp.B = B; dp.Bpad = Bpad; dp.T = T; dp.minT = minT; dp.steps = steps;
+        unsigned* bar = static_cast<unsigned*>(c.buf("ws.barrier", 256));
+        L2S_CUDA(cudaMemsetAsync(bar, 0, 4, s));
+        dp.barrier = bar;
+        const size_t smem = (size_t)c.meta.at("d.step.smem");
+        L2S_CUDA(cudaFuncSetAttribute(decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        void* args[] = {&dp};
+        L2S_CUDA(cudaLaunchCooperativeKernel((void*)decode_persistent_kernel, dim3(c.num_sms), dim3(MV_THREADS), args, smem, s));
+        c.launches++;
+    }
+    // ---- postnet + residual (decoder.py:437-439) --------------------------------------------------
+    postnet_rows(c, outputs, B, steps, mel_post, true, s);
+    c.meta["dbg.B"] = B; c.meta["dbg.T"] = T; c.meta["dbg.minT"] = minT; c.meta["dbg.steps"] = steps;
+}
+
+// visual[b,t,:] = [feat[b,t,0:768], emb[b,0:256]]   (model.py:52-55)
+__global__ void concat_visual_kernel(const float* __restrict__ feat, const float* __restrict__ emb, float* __restrict__ visual, int B, int T) {
+    const size_t total = (size_t)B * T * 1024;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int col = i % 1024; size_t r = i / 1024;
+        int b = r / T;
+        visual[i] = col < 768 ? feat[r * 768 + col] : emb[(size_t)b * 256 + col - 768];
+    }
+}
+// x [B][C][L] -> rows [B][L][C]
+__global__ void bcl_to_rows_kernel(const float* __restrict__ x, float* __restrict__ rows, int B, int C, int L) {
+    const size_t total = (size_t)B * C * L;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int ch = i % C; size_t r = i / C;
+        int t = r % L; int b = r / L;
+        rows[i] = x[((size_t)b * C + ch) * L + t];
+    }
+}
+
+static void infer_device(Context& c, const float* video, const float* wav, const float* gumbel, int B, int T, int H, int W, int S,
+                         int steps, float* mel_post, int64_t* lengths, int precision, cudaStream_t s) {
+    float* emb = c.fbuf("ws.i.emb", (size_t)B * 256);
+    float* feat = c.fbuf("ws.i.feat", (size_t)B * T * 768);
+    float* visual = c.fbuf("ws.i.visual", (size_t)B * T * 1024);
+    speaker_forward(c, wav, B, S, emb, 1, s);
+    video_forward(c, video, B, T, H, W, feat, precision, s);
+    concat_visual_kernel<<<ew_grid((size_t)B * T * 1024), 256, 0, s>>>(feat, emb, visual, B, T);
+    check_launch(c, "concat visual");
+    decoder_infer(c, visual, emb, gumbel, B, T, steps, mel_post, lengths, nullptr, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int l2s_version(void) { return 100; }
+
+int l2s_create(l2s_ctx** out, int device) {
+    if (!out) return L2S_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || device < 0 || device >= n) {
+        g_create_err = e != cudaSuccess ? std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e) : "no such CUDA device";
+        return L2S_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        g_create_err = cudaGetErrorString(e);
+        return L2S_ERR_CUDA;
+    }
+    if (prop.major != 10) {
+        g_create_err = "lip2speech_b200 is built for sm_100a (B200) only; found sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
+        return L2S_ERR_CUDA;
+    }
+    l2s_ctx* ctx = new l2s_ctx();
+    ctx->c.device = device;
+    ctx->c.num_sms = prop.multiProcessorCount;
+    ctx->c.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    *out = ctx;
+    return L2S_OK;
+}
+
+void l2s_destroy(l2s_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->c.device);
+    cudaDeviceSynchronize();
+    ctx->c.free_all();
+    delete ctx;
+}
+
+const char* l2s_last_error(const l2s_ctx* ctx) { return ctx ? ctx->c.err.c_str() : g_create_err.c_str(); }
+
+int l2s_bind_weight(l2s_ctx* ctx, const char* key, const void* ptr, const int64_t* shape, int ndim, int dtype, int on_device) {
+    if (!ctx) return L2S_ERR_INVALID;
+    API_BEGIN
+    if (!key || !ptr || ndim < 0 || ndim > 8) throw L2sError(L2S_ERR_INVALID, "bind_weight: bad arguments");
+    L2S_CUDA(cudaSetDevice(ctx->c.device));
+    HostTensor t;
+    t.shape.assign(shape, shape + ndim);
+    const int64_t n = t.numel();
+    t.f.resize((size_t)n);
+    if (dtype == L2S_DTYPE_F32) {
+        if (on_device) L2S_CUDA(cudaMemcpy(t.f.data(), ptr, n * sizeof(float), cudaMemcpyDeviceToHost));
+        else std::memcpy(t.f.data(), ptr, n * sizeof(float));
+    } else if (dtype == L2S_DTYPE_I64) {
+        std::vector<int64_t> tmp((size_t)n);
+        if (on_device) L2S_CUDA(cudaMemcpy(tmp.data(), ptr, n * sizeof(int64_t), cudaMemcpyDeviceToHost));
+        else std::memcpy(tmp.data(), ptr, n * sizeof(int64_t));
+        for (int64_t i = 0; i < n; ++i) t.f[i] = (float)tmp[i];
+    } else {
+        throw L2sError(L2S_ERR_INVALID, std::string("bind_weight: unsupported dtype for ") + key);
+    }
+    ctx->c.w[key] = std::move(t);
+    API_END(ctx)
+}
+
+int l2s_commit_weights(l2s_ctx* ctx, int parts) {
+    if (!ctx) return L2S_ERR_INVALID;
+    API_BEGIN
+    L2S_CUDA(cudaSetDevice(ctx->c.device));
+    L2S_CUDA(cudaDeviceSynchronize());
+    if (parts & L2S_PART_VIDEO) pack_video(ctx->c);
+    if (parts & L2S_PART_SPEAKER) pack_speaker(ctx->c);
+    if (parts & L2S_PART_DECODER) pack_decoder(ctx->c);
+    ctx->c.committed |= parts;
+    L2S_CUDA(cudaDeviceSynchronize());
+    API_END(ctx)
+}
+
+static void need(l2s_ctx* ctx, int part, const char* what) {
+    if (!(ctx->c.committed & part)) throw L2sError(L2S_ERR_MISSING_WEIGHT, std::string(what) + ": weights not committed (l2s_commit_weights)");
+    L2S_CUDA(cudaSetDevice(ctx->c.device));
+}
+
+int l2s_video_fwd(l2s_ctx* ctx, const float* video, int B, int T, int H, int W, float* out_feat, int precision, void* stream) {
+    if (!ctx) return L2S_ERR_INVALID;
+    API_BEGIN
+    need(ctx, L2S_PART_VIDEO, "video_fwd");
+    video_forward(ctx->c, video, B, T, H, W, out_feat, precision, (cudaStream_t)stream);
+    API_END(ctx)
+}
+
+int l2s_speaker_fwd(l2s_ctx* ctx, const float* wav, int B, int S, float* emb, int normalize, void* stream) {
+    if (!ctx) return L2S_ERR_INVALID;
+    API_BEGIN
+    need(ctx, L2S_PART_SPEAKER, "speaker_fwd");
+    speaker_forward(ctx->c, wav, B, S, emb, normalize, (cudaStream_t)stream);
+    API_END(ctx)
+}
+
+int l2s_decoder_infer(l2s_ctx* ctx, const float* visual, const float* spk, const float* gumbel, int B, int T, int steps,
+                      float* mel_post, int64_t* lengths, float* attn, void* stream) {
+    if (!ctx) return L2S_ERR_INVALID;
+    API_BEGIN
+    need(ctx, L2S_PART_DECODER, "decoder_infer");
+    decoder_infer(ctx->c, visual, spk, gumbel, B, T, steps, mel_post, lengths, attn, (cudaStream_t)stream);
+    API_END(ctx)
+}
+
+int l2s_postnet_fwd(l2s_ctx* ctx, const float* x, int B, int L, float* out, int add_residual, void* stream) {
+    if (!ctx) return L2S_ERR_INVALID;
+    API_BEGIN
+    need(ctx, L2S_PART_DECODER, "postnet_fwd");
+    if (B <= 0 || L <= 0) throw L2sError(L2S_ERR_INVALID, "postnet_fwd: bad shape");
+    cudaStream_t s = (cudaStream_t)stream;
+    float* rows = ctx->c.fbuf("ws.p.rows", (size_t)B * L * 80);
+    bcl_to_rows_kernel<<<ew_grid((size_t)B * L * 80), 256, 0, s>>>(x, rows, B, 80, L);
+    check_launch(ctx->c, "bcl->rows");
+    postnet_rows(ctx->c, rows, B, L, out, add_residual != 0, s);
+    API_END(ctx)
+}
+
+int l2s_infer(l2s_ctx* ctx, const float* video, const float* wav, const float* gumbel, int B, int T, int H, int W, int S, int steps,
+              float* mel_post, int64_t* lengths, int precision, void* stream) {
+    if (!ctx) return L2S_ERR_INVALID;
+    API_BEGIN
+    need(ctx, L2S_PART_VIDEO | L2S_PART_SPEAKER | L2S_PART_DECODER, "infer");
+    infer_device(ctx->c, video, wav, gumbel, B, T, H, W, S, steps, mel_post, lengths, precision, (cudaStream_t)stream);
+    API_END(ctx)
+}
+
+int l2s_infer_host(l2s_ctx* ctx, const float* video, const float* wav, const float* gumbel, int B, int T, int H, int W, int S, int steps,
+                   float* mel_post, int64_t* lengths, int precision) {
+    if (!ctx) return L2S_ERR_INVALID;
+    API_BEGIN
+    need(ctx, L2S_PART_VIDEO | L2S_PART_SPEAKER | L2S_PART_DECODER, "infer_host");
+    Context& c = ctx->c;
+    int minT = T;
+    for (int k : {1, 3, 5, 7}) minT = std::min(minT, (T - k) / k + 1);
+    const size_t nv = (size_t)B * 3 * T * H * W, nw = (size_t)B * S, ng = (size_t)B * minT * 501, nm = (size_t)B * 80 * steps;
+    float* dv = c.fbuf("ws.h.video", nv); float* dw = c.fbuf("ws.h.wav", nw); float* dg = c.fbuf("ws.h.gumbel", ng);
+    float* dm = c.fbuf("ws.h.mel", nm);
+    int64_t* dl = static_cast<int64_t*>(c.buf("ws.h.len", (size_t)B * sizeof(int64_t)));
+    cudaStream_t s = 0;
+    L2S_CUDA(cudaMemcpyAsync(dv, video, nv * sizeof(float), cudaMemcpyHostToDevice, s));
+    L2S_CUDA(cudaMemcpyAsync(dw, wav, nw * sizeof(float), cudaMemcpyHostToDevice, s));
+    L2S_CUDA(cudaMemcpyAsync(dg, gumbel, ng * sizeof(float), cudaMemcpyHostToDevice, s));
+    infer_device(c, dv, dw, dg, B, T, H, W, S, steps, dm, dl, precision, s);
+    L2S_CUDA(cudaMemcpyAsync(mel_post, dm, nm * sizeof(float), cudaMemcpyDeviceToHost, s));
+    L2S_CUDA(cudaMemcpyAsync(lengths, dl, (size_t)B * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    L2S_CUDA(cudaStreamSynchronize(s));
+    API_END(ctx)
+}
+
+int64_t l2s_launch_count(const l2s_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
+
+int64_t l2s_debug_read(l2s_ctx* ctx, const char* name, float* out, int64_t n) {
+    if (!ctx || !name) return -1;
+    Context& c = ctx->c;
+    auto get = [&](const char* k) { auto it = c.meta.find(k); return it == c.meta.end() ? (int64_t)0 : it->second; };
+    const int64_t B = get("dbg.B"), T = get("dbg.T"), minT = get("dbg.minT"), steps = get("dbg.steps");
+    struct { const char* name; const char* buf; int64_t count; } tab[] = {
+        {"dec.K", "ws.d.K", B * T * 512}, {"dec.V", "ws.d.V", B * T * 512}, {"dec.enc_cell", "ws.d.enc_cell", B * 512},
+        {"dec.enc", "ws.d.enc", B * T * 512}, {"dec.rnn_out", "ws.d.rnnout", B * T * 1024},
+        {"dec.ckey", "ws.d.ckey", B * minT * 256}, {"dec.cval", "ws.d.cval", B * minT * 256},
+        {"dec.outputs", "ws.d.outputs", B * steps * 80}, {"dec.clog", "ws.d.clog", B * minT * 501},
+    };
+    for (auto& t : tab) {
+        if (std::strcmp(t.name, name) == 0) {
+            auto it = c.bufs.find(t.buf);
+            if (it == c.bufs.end() || !it->second.p) return -1;
+            cudaSetDevice(c.device);
+            cudaDeviceSynchronize();
+            int64_t k = std::min<int64_t>(n, t.count);
+            if (out && k > 0) cudaMemcpy(out, it->second.p, (size_t)k * sizeof(float), cudaMemcpyDeviceToHost);
+            return t.count;
+        }
+    }
+    return -1;
+}
+
+}  // extern "C"

@@ -1,0 +1,67 @@
+// Shared helpers for the lip2speech_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cmath>
+
+namespace l2s {
+
+constexpr int ACT_NONE = 0;
+constexpr int ACT_RELU = 1;
+constexpr int ACT_SILU = 2;
+constexpr int ACT_PSINE = 3;   // sin(x) * w[channel]   (reference decoder.py:43-70)
+constexpr int ACT_PRELU = 4;   // x>=0 ? x : w[channel]*x (reference video.py:66)
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float siluf_acc(float x) { return x / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float apply_act(float v, int act, float w) {
+    switch (act) {
+        case ACT_RELU: return v > 0.f ? v : 0.f;
+        case ACT_SILU: return siluf_acc(v);
+        case ACT_PSINE: return sinf(v) * w;
+        case ACT_PRELU: return v >= 0.f ? v : w * v;
+        default: return v;
+    }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// L2-only loads for data produced by other CTAs of the same persistent kernel (L1 is not coherent).
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float ldcg1(const float* p) { return __ldcg(p); }
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Grid-wide barrier for cooperative (co-resident) launches.  `counter` is zeroed by the host before
+// the launch and only ever grows; `target` is the per-thread running expected value.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target, unsigned nblocks) {
+    target += nblocks;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        red_release_add_u32(counter, 1u);             // release: orders this CTA's prior global writes
+        while (ld_acquire_u32(counter) < target) {}
+    }
+    __syncthreads();
+}
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace l2s

@@ -1,0 +1,92 @@
+// Host-side context: raw weight store, device buffer registry, error plumbing.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace l2s {
+
+struct HostTensor {
+    std::vector<float> f;          // fp32 payload (int64 tensors are stored converted; only num_batches_tracked)
+    std::vector<int64_t> shape;
+    int64_t numel() const { int64_t n = 1; for (auto s : shape) n *= s; return n; }
+};
+
+struct L2sError : std::runtime_error {
+    int code;
+    L2sError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define L2S_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            throw ::l2s::L2sError(2, std::string(#expr) + ": " + cudaGetErrorString(_e));           \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+struct Context {
+    int device = 0;
+    int num_sms = 0;
+    int max_smem_optin = 0;
+    std::string err;
+    std::map<std::string, HostTensor> w;
+    std::map<std::string, DevBuf> bufs;       // named device allocations (packed weights + workspaces)
+    std::map<std::string, int64_t> meta;      // small integers produced by packing (sizes, counts)
+    int64_t launches = 0;
+    int committed = 0;
+
+    const HostTensor& W(const std::string& key) const {
+        auto it = w.find(key);
+        if (it == w.end()) throw L2sError(3, "missing weight: " + key);
+        return it->second;
+    }
+    bool has(const std::string& key) const { return w.count(key) != 0; }
+
+    // (Re)allocate a named device buffer of at least `bytes`; contents are zeroed on (re)allocation.
+    void* buf(const std::string& name, size_t bytes) {
+        DevBuf& b = bufs[name];
+        if (b.bytes < bytes) {
+            if (b.p) L2S_CUDA(cudaFree(b.p));
+            b.p = nullptr; b.bytes = 0;
+            size_t alloc = (bytes + 255) & ~size_t(255);
+            L2S_CUDA(cudaMalloc(&b.p, alloc));
+            L2S_CUDA(cudaMemset(b.p, 0, alloc));
+            b.bytes = alloc;
+        }
+        return b.p;
+    }
+    float* fbuf(const std::string& name, size_t floats) { return static_cast<float*>(buf(name, floats * sizeof(float))); }
+    float* upload(const std::string& name, const std::vector<float>& v) {
+        float* d = fbuf(name, v.size());
+        L2S_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+        return d;
+    }
+    template <typename T>
+    T* upload_raw(const std::string& name, const T* src, size_t count) {
+        T* d = static_cast<T*>(buf(name, count * sizeof(T)));
+        L2S_CUDA(cudaMemcpy(d, src, count * sizeof(T), cudaMemcpyHostToDevice));
+        return d;
+    }
+    float* dev(const std::string& name) const {
+        auto it = bufs.find(name);
+        if (it == bufs.end() || !it->second.p) throw L2sError(1, "internal: buffer not packed: " + name + " (call l2s_commit_weights)");
+        return static_cast<float*>(it->second.p);
+    }
+    void free_all() {
+        for (auto& kv : bufs)
+            if (kv.second.p) cudaFree(kv.second.p);
+        bufs.clear();
+    }
+};
+
+}  // namespace l2s

@@ -1,0 +1,421 @@
+// Host-side weight packing: eval-BatchNorm folding, layout changes, per-SM row partition of the decode
+// step.  Runs once per l2s_commit_weights on the CPU in plain C++ (38 M parameters, ~100 ms).
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+#include "context.h"
+#include "decode.cuh"
+#include "lstm.cuh"
+
+namespace l2s {
+
+constexpr float BN_EPS = 1e-5f;
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// scale/shift of an eval BatchNorm: y = x*scale + shift  (reference: nn.BatchNorm*, eps=1e-5)
+inline void bn_affine(const Context& c, const std::string& bn, std::vector<float>& scale, std::vector<float>& shift) {
+    const auto& g = c.W(bn + ".weight").f; const auto& b = c.W(bn + ".bias").f;
+    const auto& m = c.W(bn + ".running_mean").f; const auto& v = c.W(bn + ".running_var").f;
+    scale.resize(g.size()); shift.resize(g.size());
+    for (size_t i = 0; i < g.size(); ++i) {
+        float s = g[i] / std::sqrt(v[i] + BN_EPS);
+        scale[i] = s; shift[i] = b[i] - m[i] * s;
+    }
+}
+
+// Conv1d weight [co][ci][k] (+bias) followed by BN -> [co][k*ci_n + ci] with BN folded; bias out.
+inline void pack_conv1d(const Context& c, const std::string& conv, const std::string& bn /* "" = none */,
+                        std::vector<float>& w, std::vector<float>& bias) {
+    const HostTensor& W = c.W(conv + ".weight");
+    const int co = (int)W.shape[0], ci = (int)W.shape[1], k = (int)W.shape[2];
+    const auto& b = c.W(conv + ".bias").f;
+    std::vector<float> scale(co, 1.f), shift(co, 0.f);
+    if (!bn.empty()) bn_affine(c, bn, scale, shift);
+    w.assign((size_t)co * k * ci, 0.f); bias.assign(co, 0.f);
+    for (int o = 0; o < co; ++o) {
+        for (int i = 0; i < ci; ++i)
+            for (int t = 0; t < k; ++t) w[(size_t)o * k * ci + (size_t)t * ci + i] = W.f[((size_t)o * ci + i) * k + t] * scale[o];
+        bias[o] = b[o] * scale[o] + shift[o];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// video frontend
+// ------------------------------------------------------------------------------------------------
+struct TrunkBlockMeta { int down, cin_phys, half, hp, in_half, in_hp; };
+
+inline int phys_ch(int l, int half, int hp) { return (half > 0 && l >= half) ? l - half + hp : l; }
+
+inline void pack_video(Context& c) {
+    const std::string p = "encoder.";
+    {   // stem: Conv3d weight [24][3*5*7*7] * bn scale, bias = shift, PReLU slopes
+        const HostTensor& W = c.W(p + "frontend3D.0.weight");
+        std::vector<float> scale, shift; bn_affine(c, p + "frontend3D.1", scale, shift);
+        std::vector<float> w(W.f.size());
+        const int K = 735;
+        for (int o = 0; o < 24; ++o) for (int k = 0; k < K; ++k) w[(size_t)o * K + k] = W.f[(size_t)o * K + k] * scale[o];
+        c.upload("v.stem.w", w); c.upload("v.stem.b", shift); c.upload("v.stem.prelu", c.W(p + "frontend3D.2.weight").f);
+    }
+    int blk = 0;
+    int in_half = 0, in_hp = 0, cin = 24, cin_phys = 24;       // stem output: identity layout
+    std::vector<TrunkBlockMeta> metas;
+    while (c.has(p + "trunk.0." + std::to_string(blk) + ".banch2.0.weight")) {
+        const std::string q = p + "trunk.0." + std::to_string(blk) + ".";
+        const std::string n = "v.b" + std::to_string(blk) + ".";
+        const bool down = c.has(q + "banch1.0.weight");
+        const int half = (int)c.W(q + "banch2.5.weight").shape[0];
+        const int hp = round_up(half, 4);
+        std::vector<float> scale, shift;
+        auto pack_pw = [&](const std::string& conv, const std::string& bn, int K_phys, bool map_in, const std::string& name) {
+            // 1x1 conv [co][ci] -> [co][K_phys] over PHYSICAL input channels, BN folded
+            const HostTensor& W = c.W(conv + ".weight");
+            const int co = (int)W.shape[0], ci = (int)W.shape[1];
+            bn_affine(c, bn, scale, shift);
+            std::vector<float> w((size_t)co * K_phys, 0.f);
+            for (int o = 0; o < co; ++o)
+                for (int i = 0; i < ci; ++i) {
+                    int pi = map_in ? phys_ch(i, in_half, in_hp) : i;
+                    w[(size_t)o * K_phys + pi] = W.f[(size_t)o * ci + i] * scale[o];
+                }
+            c.upload(name + ".w", w); c.upload(name + ".b", shift);
+        };
+        auto pack_dw = [&](const std::string& conv, const std::string& bn, int C_phys, bool map_in, const std::string& name) {
+            const HostTensor& W = c.W(conv + ".weight");            // [C][1][3][3]
+            const int C = (int)W.shape[0];
+            bn_affine(c, bn, scale, shift);
+            std::vector<float> w((size_t)9 * C_phys, 0.f), b(C_phys, 0.f);
+            for (int ch = 0; ch < C; ++ch) {
+                int pc = map_in ? phys_ch(ch, in_half, in_hp) : ch;
+                for (int k = 0; k < 9; ++k) w[(size_t)k * C_phys + pc] = W.f[(size_t)ch * 9 + k] * scale[ch];
+                b[pc] = shift[ch];
+            }
+            c.upload(name + ".w", w); c.upload(name + ".b", b);
+        };
+        if (down) {
+            pack_dw(q + "banch1.0", q + "banch1.1", cin_phys, true, n + "b1dw");
+            pack_pw(q + "banch1.2", q + "banch1.3", cin_phys, true, n + "b1pw");
+            pack_pw(q + "banch2.0", q + "banch2.1", cin_phys, true, n + "b2pw1");
+        } else {
+            pack_pw(q + "banch2.0", q + "banch2.1", hp, false, n + "b2pw1");
+        }
+        pack_dw(q + "banch2.3", q + "banch2.4", hp, false, n + "b2dw");
+        pack_pw(q + "banch2.5", q + "banch2.6", hp, false, n + "b2pw2");
+        metas.push_back({down ? 1 : 0, cin_phys, half, hp, in_half, in_hp});
+        cin = 2 * half; cin_phys = 2 * hp; in_half = half; in_hp = hp;
+        ++blk;
+    }
+    {   // conv_last 1x1 cin->768 over physical channels
+        const HostTensor& W = c.W(p + "trunk.1.0.weight");
+        const int co = (int)W.shape[0], ci = (int)W.shape[1];
+        std::vector<float> scale, shift; bn_affine(c, p + "trunk.1.1", scale, shift);
+        std::vector<float> w((size_t)co * cin_phys, 0.f);
+        for (int o = 0; o < co; ++o)
+            for (int i = 0; i < ci; ++i) w[(size_t)o * cin_phys + phys_ch(i, in_half, in_hp)] = W.f[(size_t)o * ci + i] * scale[o];
+        c.upload("v.last.w", w); c.upload("v.last.b", shift);
+        c.meta["v.last.k"] = cin_phys; c.meta["v.last.n"] = co;
+    }
+    c.meta["v.nblocks"] = blk;
+    for (int i = 0; i < blk; ++i) {
+        const std::string n = "v.b" + std::to_string(i) + ".";
+        c.meta[n + "down"] = metas[i].down; c.meta[n + "cin_phys"] = metas[i].cin_phys;
+        c.meta[n + "half"] = metas[i].half; c.meta[n + "hp"] = metas[i].hp;
+    }
+    (void)cin;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LSTM chunking shared by the decoder's encoder_rnn and the speaker encoder
+// ------------------------------------------------------------------------------------------------
+struct LstmPack { std::vector<LstmChunk> chunks; std::vector<float> w; int max_chunks = 0; };
+
+// layers x dirs x H units in chunks of <=4 units.  get_w(layer, dir, which /*0 ih, 1 hh*/) returns the
+// torch-layout [4H][in] matrix, get_b(layer, dir) the summed bias.
+template <typename GW, typename GB>
+inline LstmPack pack_lstm(int L, int dirs, int H, int num_ctas, GW get_w, GB get_b) {
+    LstmPack pk;
+    for (int l = 0; l < L; ++l)
+        for (int d = 0; d < dirs; ++d)
+            for (int u0 = 0; u0 < H; u0 += 4) {
+                LstmChunk ck{};
+                ck.layer = l; ck.dir = d; ck.u0 = u0; ck.nu = std::min(4, H - u0);
+                ck.K0 = H; ck.K1 = (l == 0) ? 0 : H;
+                ck.w_off = (int)pk.w.size();
+                const int K = ck.K0 + ck.K1;
+                pk.w.resize(pk.w.size() + (size_t)16 * K, 0.f);
+                const std::vector<float>* wih = (l == 0) ? nullptr : get_w(l, d, 0);
+                const std::vector<float>* whh = get_w(l, d, 1);
+                const std::vector<float> bsum = get_b(l, d);
+                for (int ul = 0; ul < ck.nu; ++ul)
+                    for (int g = 0; g < 4; ++g) {
+                        const int r = 4 * ul + g, row = g * H + u0 + ul;
+                        float* dst = pk.w.data() + ck.w_off + (size_t)r * K;
+                        if (l == 0) {
+                            std::copy(whh->begin() + (size_t)row * H, whh->begin() + (size_t)(row + 1) * H, dst);
+                        } else {
+                            std::copy(wih->begin() + (size_t)row * H, wih->begin() + (size_t)(row + 1) * H, dst);
+                            std::copy(whh->begin() + (size_t)row * H, whh->begin() + (size_t)(row + 1) * H, dst + H);
+                        }
+                        ck.bias[r] = (l == 0) ? 0.f : bsum[row];
+                    }
+                pk.chunks.push_back(ck);
+            }
+    pk.max_chunks = ((int)pk.chunks.size() + num_ctas - 1) / num_ctas;
+    return pk;
+}
+
+inline std::vector<float> vadd(const std::vector<float>& a, const std::vector<float>& b) {
+    std::vector<float> r(a.size());
+    for (size_t i = 0; i < a.size(); ++i) r[i] = a[i] + b[i];
+    return r;
+}
+
+inline void pack_speaker(Context& c) {
+    const std::string p = "speaker_encoder.";
+    c.upload("s.window", c.W(p + "mel_spec.spectrogram.window").f);
+    c.upload("s.fb", c.W(p + "mel_spec.mel_scale.fb").f);
+    c.upload("s.wih0", c.W(p + "lstm.weight_ih_l0").f);
+    c.upload("s.b0", vadd(c.W(p + "lstm.bias_ih_l0").f, c.W(p + "lstm.bias_hh_l0").f));
+    c.upload("s.lin.w", c.W(p + "linear.weight").f);
+    c.upload("s.lin.b", c.W(p + "linear.bias").f);
+    auto gw = [&](int l, int, int which) { return &c.W(p + "lstm.weight_" + (which ? "hh" : "ih") + "_l" + std::to_string(l)).f; };
+    auto gb = [&](int l, int) { return vadd(c.W(p + "lstm.bias_ih_l" + std::to_string(l)).f, c.W(p + "lstm.bias_hh_l" + std::to_string(l)).f); };
+    LstmPack pk = pack_lstm(3, 1, 256, c.num_sms, gw, gb);
+    if (pk.max_chunks > LSTM_MAX_CHUNKS) throw L2sError(1, "speaker LSTM does not fit this SM count");
+    c.upload("s.lstm.w", pk.w);
+    c.upload_raw("s.lstm.chunks", pk.chunks.data(), pk.chunks.size());
+    c.meta["s.lstm.nchunks"] = (int64_t)pk.chunks.size(); c.meta["s.lstm.max_chunks"] = pk.max_chunks;
+}
+
+// ------------------------------------------------------------------------------------------------
+// decoder: pre-loop, postnet, decode-step program
+// ------------------------------------------------------------------------------------------------
+struct PassBuild {
+    int stage, R, K0, K1, src0, src1;
+    struct Row { int op, idx; float bias, aux, aux2; const float* w0; const float* w1; };
+    std::vector<Row> rows;
+    double cost() const { return (double)R * (K0 + K1); }
+    size_t floats() const { return (size_t)R * (K0 + K1); }
+};
+
+inline void pack_decode_program(Context& c) {
+    const std::string p = "decoder.";
+    const int nC = c.num_sms;
+    const auto& Wfc = c.W(p + "fc_out.linear_layer.weight").f;   const auto& bfc = c.W(p + "fc_out.linear_layer.bias").f;
+    const auto& Wp1 = c.W(p + "prenet.0.linear_layer.weight").f; const auto& bp1 = c.W(p + "prenet.0.linear_layer.bias").f;
+    const auto& ps1 = c.W(p + "prenet.1.w").f;
+    const auto& Wp2 = c.W(p + "prenet.3.linear_layer.weight").f; const auto& bp2 = c.W(p + "prenet.3.linear_layer.bias").f;
+    const auto& ps2 = c.W(p + "prenet.4.w").f;
+    const auto& Wq = c.W(p + "Q.0.linear_layer.weight").f;       const auto& bq = c.W(p + "Q.0.linear_layer.bias").f;
+    const auto& psq = c.W(p + "Q.1.w").f;
+    const auto& Wcq = c.W(p + "content.Q.0.weight").f;           const auto& bcq = c.W(p + "content.Q.0.bias").f;
+    const auto& Wap = c.W(p + "attention_proj.linear_layer.weight").f; const auto& bap = c.W(p + "attention_proj.linear_layer.bias").f;
+    const auto& Wst = c.W(p + "stop_token_layer.linear_layer.weight").f; const auto& bst = c.W(p + "stop_token_layer.linear_layer.bias").f;
+    const auto& bos = c.W(p + "BOS").f;
+    // prenet layer 1 fused with fc_out (linear o linear): Wpf = Wp1 * Wfc [256x512], bpf = Wp1*bfc + bp1
+    std::vector<float> Wpf((size_t)256 * 512, 0.f), bpf(256, 0.f), p1bos(256, 0.f);   // outlive the row pointers below
+    for (int j = 0; j < 256; ++j) {
+        std::vector<double> acc(512, 0.0);
+        double bb = bp1[j], pb = bp1[j];
+        for (int m = 0; m < 80; ++m) {
+            const double w = Wp1[(size_t)j * 80 + m];
+            const float* fr = Wfc.data() + (size_t)m * 512;
+            for (int k = 0; k < 512; ++k) acc[k] += w * fr[k];
+            bb += w * bfc[m];
+            pb += w * bos[m];
+        }
+        for (int k = 0; k < 512; ++k) Wpf[(size_t)j * 512 + k] = (float)acc[k];
+        bpf[j] = (float)bb;
+        p1bos[j] = std::sin((float)pb) * ps1[j];
+    }
+    std::vector<float> b0 = vadd(c.W(p + "decoder_rnn.bias_ih_l0").f, c.W(p + "decoder_rnn.bias_hh_l0").f);
+    std::vector<float> b1 = vadd(c.W(p + "decoder_rnn.bias_ih_l1").f, c.W(p + "decoder_rnn.bias_hh_l1").f);
+    const auto& Wih0 = c.W(p + "decoder_rnn.weight_ih_l0").f; const auto& Whh0 = c.W(p + "decoder_rnn.weight_hh_l0").f;
+    const auto& Wih1 = c.W(p + "decoder_rnn.weight_ih_l1").f; const auto& Whh1 = c.W(p + "decoder_rnn.weight_hh_l1").f;
+
+    std::vector<std::vector<PassBuild>> per_cta(nC);
+    std::vector<std::vector<double>> load(nC, std::vector<double>(ST_COUNT, 0.0));
+    std::vector<size_t> floats(nC, 0);
+
+    // ---- LSTM units: contiguous groups per CTA, chunks of <=4 units ------------------------------
+    {
+        int u = 0;
+        for (int cta = 0; cta < nC; ++cta) {
+            int n = 512 / nC + (cta < 512 % nC ? 1 : 0);
+            for (int done = 0; done < n; done += 4) {
+                int nu = std::min(4, n - done), u0 = u + done;
+                for (int layer = 0; layer < 2; ++layer) {
+                    PassBuild pb{layer == 0 ? ST_D : ST_E, 16, 512, 512, layer == 0 ? SRC_XD : SRC_H0NEW,
+                                 layer == 0 ? SRC_H0OLD : SRC_H1OLD, {}};
+                    for (int ul = 0; ul < 4; ++ul)
+                        for (int g = 0; g < 4; ++g) {
+                            PassBuild::Row r{layer == 0 ? OP_GATE0 : OP_GATE1, -1, 0.f, 0.f, 0.f, nullptr, nullptr};
+                            if (ul < nu) {
+                                int row = g * 512 + u0 + ul;
+                                r.idx = u0 + ul;
+                                r.bias = (layer == 0 ? b0 : b1)[row];
+                                r.w0 = (layer == 0 ? Wih0 : Wih1).data() + (size_t)row * 512;
+                                r.w1 = (layer == 0 ? Whh0 : Whh1).data() + (size_t)row * 512;
+                            }
+                            pb.rows.push_back(r);
+                        }
+                    load[cta][pb.stage] += pb.cost(); floats[cta] += pb.floats();
+                    per_cta[cta].push_back(pb);
+                }
+            }
+            u += n;
+        }
+    }
+    // ---- the other rows, grouped into passes of RA rows ------------------------------------------
+    std::vector<PassBuild> free_passes;
+    auto add_rows = [&](int stage, int R, int K0, int src0, std::vector<PassBuild::Row>& rows) {
+        for (size_t i = 0; i < rows.size(); i += R) {
+            PassBuild pb{stage, R, K0, 0, src0, SRC_NONE, {}};
+            for (int j = 0; j < R; ++j) {
+                if (i + j < rows.size()) pb.rows.push_back(rows[i + j]);
+                else pb.rows.push_back({OP_NONE, 0, 0.f, 0.f, 0.f, nullptr, nullptr});
+            }
+            free_passes.push_back(pb);
+        }
+    };
+    const int RA = 8;
+    {
+        std::vector<PassBuild::Row> rows;
+        for (int j = 0; j < 512; ++j) rows.push_back({OP_Q, j, bq[j], psq[j], 0.f, Wq.data() + (size_t)j * 1024, nullptr});
+        add_rows(ST_A, RA, 1024, SRC_HNEW, rows);
+        rows.clear();
+        for (int j = 0; j < 256; ++j) rows.push_back({OP_CQ, j, bcq[j], 0.f, 0.f, Wcq.data() + (size_t)j * 1024, nullptr});
+        add_rows(ST_A, RA, 1024, SRC_C, rows);
+        rows.clear();
+        for (int j = 0; j < 80; ++j) rows.push_back({OP_FC, j, bfc[j], 0.f, 0.f, Wfc.data() + (size_t)j * 512, nullptr});
+        for (int j = 0; j < 256; ++j) rows.push_back({OP_P1, j, bpf[j], ps1[j], p1bos[j], Wpf.data() + (size_t)j * 512, nullptr});
+        rows.push_back({OP_STOP, 0, bst[0], 0.f, 0.f, Wst.data(), nullptr});
+        add_rows(ST_A, RA, 512, SRC_H1NEW, rows);
+        rows.clear();
+        for (int j = 0; j < 256; ++j) rows.push_back({OP_X2, j, bap[j], 0.f, 0.f, Wap.data() + (size_t)j * 512, nullptr});
+        add_rows(ST_C, RA, 512, SRC_CTX, rows);
+        rows.clear();
+        for (int j = 0; j < 256; ++j) rows.push_back({OP_P2, j, bp2[j], ps2[j], 0.f, Wp2.data() + (size_t)j * 256, nullptr});
+        add_rows(ST_B, RA, 256, SRC_P1, rows);
+    }
+    // attention runs on the low-numbered CTAs in stage B: bias p2 rows away from them
+    for (int cta = 0; cta < nC; ++cta) load[cta][ST_B] += (cta < 64 ? 4096.0 : 0.0) + (nC - 1 - cta) * 1e-3;
+    const size_t scratch_bytes = (size_t)(MV_WARPS * 16 * MV_CLIPS + 16 * MV_CLIPS + 512 + 320 + 256 + 32) * 4;
+    const size_t static_bytes = sizeof(DecPass) * DEC_MAX_PASSES + 64;
+    const size_t cap_floats = ((size_t)c.max_smem_optin - scratch_bytes - static_bytes) / 4;
+    std::stable_sort(free_passes.begin(), free_passes.end(), [](const PassBuild& a, const PassBuild& b) { return a.cost() > b.cost(); });
+    for (auto& pb : free_passes) {
+        int best = -1;
+        for (int cta = 0; cta < nC; ++cta) {
+            if (floats[cta] + pb.floats() > cap_floats) continue;
+            if ((int)per_cta[cta].size() >= DEC_MAX_PASSES) continue;
+            if (best < 0 || load[cta][pb.stage] < load[best][pb.stage] ||
+                (load[cta][pb.stage] == load[best][pb.stage] && floats[cta] < floats[best])) best = cta;
+        }
+        if (best < 0) throw L2sError(1, "decode program does not fit in shared memory on this device");
+        load[best][pb.stage] += pb.cost(); floats[best] += pb.floats();
+        per_cta[best].push_back(pb);
+    }
+    size_t wimg_floats = 0;
+    for (int cta = 0; cta < nC; ++cta) wimg_floats = std::max(wimg_floats, floats[cta]);
+    wimg_floats = (wimg_floats + 3) & ~size_t(3);
+    std::vector<float> wimg((size_t)nC * wimg_floats, 0.f);
+    std::vector<DecPass> passes((size_t)nC * DEC_MAX_PASSES);
+    std::memset(passes.data(), 0, passes.size() * sizeof(DecPass));
+    std::vector<int> npasses(nC, 0);
+    for (int cta = 0; cta < nC; ++cta) {
+        size_t off = 0;
+        if ((int)per_cta[cta].size() > DEC_MAX_PASSES) throw L2sError(1, "too many decode passes per CTA");
+        for (size_t j = 0; j < per_cta[cta].size(); ++j) {
+            const PassBuild& pb = per_cta[cta][j];
+            DecPass& d = passes[(size_t)cta * DEC_MAX_PASSES + j];
+            d.stage = pb.stage; d.R = pb.R; d.K0 = pb.K0; d.K1 = pb.K1; d.src0 = pb.src0; d.src1 = pb.src1; d.w_off = (int)off;
+            const int K = pb.K0 + pb.K1;
+            for (int r = 0; r < 16; ++r) {
+                if (r < pb.R) {
+                    const auto& row = pb.rows[r];
+                    d.op[r] = row.op; d.idx[r] = row.idx; d.bias[r] = row.bias; d.aux[r] = row.aux; d.aux2[r] = row.aux2;
+                    float* dst = wimg.data() + (size_t)cta * wimg_floats + off + (size_t)r * K;
+                    if (row.w0) std::copy(row.w0, row.w0 + pb.K0, dst);
+                    if (row.w1) std::copy(row.w1, row.w1 + pb.K1, dst + pb.K0);
+                } else { d.op[r] = OP_NONE; d.idx[r] = -1; }
+            }
+            off += pb.floats();
+        }
+        npasses[cta] = (int)per_cta[cta].size();
+    }
+    c.upload("d.step.wimg", wimg);
+    c.upload_raw("d.step.passes", passes.data(), passes.size());
+    c.upload_raw("d.step.npasses", npasses.data(), npasses.size());
+    c.meta["d.step.wimg_floats"] = (int64_t)wimg_floats;
+    c.meta["d.step.smem"] = (int64_t)(wimg_floats * 4 + scratch_bytes);
+    // stop token: the encoder_cell half of the weight row (runtime GEMM N=1) — bias already in the pass
+    std::vector<float> wst2(Wst.begin() + 512, Wst.begin() + 1024);
+    c.upload("d.stop.w2", wst2);
+}
+
+inline void pack_decoder(Context& c) {
+    const std::string p = "decoder.";
+    std::vector<float> w, b;
+    // postnet
+    for (int i = 0; i < 5; ++i) {
+        const std::string s = std::to_string(i);
+        pack_conv1d(c, p + "postnet.convolutions." + s + ".0.conv", p + "postnet.convolutions." + s + ".1", w, b);
+        c.upload("d.post" + s + ".w", w); c.upload("d.post" + s + ".b", b);
+        if (i < 4) c.upload("d.post" + s + ".psw", c.W(p + "postnet.sin_activation." + s + ".w").f);
+    }
+    // encoder pre-loop linears
+    auto up_lin = [&](const std::string& key, const std::string& name) {
+        c.upload(name + ".w", c.W(key + ".weight").f); c.upload(name + ".b", c.W(key + ".bias").f);
+    };
+    up_lin(p + "encoder_proj.linear_layer", "d.encproj");
+    up_lin(p + "encoder_site.0.linear_layer", "d.encsite"); c.upload("d.encsite.psw", c.W(p + "encoder_site.1.w").f);
+    up_lin(p + "attention_site.0.linear_layer", "d.attsite"); c.upload("d.attsite.psw", c.W(p + "attention_site.1.w").f);
+    up_lin(p + "residual_bottleneck", "d.resid");            // [512][1024][1] == [512][1024]
+    up_lin(p + "E_C.linear_layer", "d.ec");
+    {   // Bi-LSTM: input projection for both directions as one [4096][1024] GEMM, recurrent chunks
+        std::vector<float> wih = c.W(p + "encoder_rnn.weight_ih_l0").f;
+        const auto& wr = c.W(p + "encoder_rnn.weight_ih_l0_reverse").f;
+        wih.insert(wih.end(), wr.begin(), wr.end());
+        std::vector<float> bsum = vadd(c.W(p + "encoder_rnn.bias_ih_l0").f, c.W(p + "encoder_rnn.bias_hh_l0").f);
+        std::vector<float> br = vadd(c.W(p + "encoder_rnn.bias_ih_l0_reverse").f, c.W(p + "encoder_rnn.bias_hh_l0_reverse").f);
+        bsum.insert(bsum.end(), br.begin(), br.end());
+        c.upload("d.ernn.wih", wih); c.upload("d.ernn.b", bsum);
+        auto gw = [&](int, int d, int which) { return &c.W(p + "encoder_rnn.weight_" + (which ? "hh" : "ih") + "_l0" + (d ? "_reverse" : "")).f; };
+        auto gb = [&](int, int) { return std::vector<float>(); };
+        LstmPack pk = pack_lstm(1, 2, 512, c.num_sms, gw, gb);
+        if (pk.max_chunks > LSTM_MAX_CHUNKS) throw L2sError(1, "encoder LSTM does not fit this SM count");
+        c.upload("d.ernn.w", pk.w);
+        c.upload_raw("d.ernn.chunks", pk.chunks.data(), pk.chunks.size());
+        c.meta["d.ernn.nchunks"] = (int64_t)pk.chunks.size(); c.meta["d.ernn.max_chunks"] = pk.max_chunks;
+    }
+    // K / V MultiHopConv
+    for (const char* kv : {"K", "V"}) {
+        for (int j = 0; j < 4; ++j) {
+            const std::string s = std::to_string(j);
+            pack_conv1d(c, p + kv + ".0.conv." + s + ".0", p + kv + ".0.conv." + s + ".1", w, b);
+            c.upload(std::string("d.") + kv + ".c" + s + ".w", w); c.upload(std::string("d.") + kv + ".c" + s + ".b", b);
+        }
+        pack_conv1d(c, p + kv + ".0.bottleneck", "", w, b);
+        c.upload(std::string("d.") + kv + ".bn.w", w); c.upload(std::string("d.") + kv + ".bn.b", b);
+        c.upload(std::string("d.") + kv + ".psw", c.W(p + kv + ".1.w").f);
+    }
+    // Content.encode
+    for (int j = 0; j < 4; ++j) {
+        const std::string s = std::to_string(j);
+        pack_conv1d(c, p + "content.agg." + s + ".0", p + "content.agg." + s + ".1", w, b);
+        c.upload("d.cagg" + s + ".w", w); c.upload("d.cagg" + s + ".b", b);
+    }
+    pack_conv1d(c, p + "content.bottleneck", "", w, b);
+    c.upload("d.cbn.w", w); c.upload("d.cbn.b", b);
+    up_lin(p + "content.location_fc.0", "d.cloc0"); up_lin(p + "content.location_fc.2", "d.cloc2"); up_lin(p + "content.location_fc.4", "d.cloc4");
+    up_lin(p + "content.K.0", "d.ck0"); up_lin(p + "content.K.2", "d.ck2");
+    c.upload("d.cemb", c.W(p + "content.word_embeddings").f);
+    c.upload("d.pos", c.W(p + "positional_encodings.pos_table").f);
+    c.meta["d.temp_bits"] = 0;
+    pack_decode_program(c);
+}
+
+}  // namespace l2s

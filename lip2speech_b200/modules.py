@@ -1,0 +1,170 @@
+"""Host-side mirror of the reference's nn.Module boundary (reference model/model.py:13-72,
+model/modules/video.py:26-87, audio.py:110-150, decoder.py:274-444).
+
+Same class names, method signatures, return values, error behaviour and `state_dict` keys as the
+reference — so checkpoints written by the reference's train.py load with `strict=True` — but the
+modules own *only parameters*: every `forward` / `inference` body is one call into the C ABI
+(include/l2s_b200.h).  There is no PyTorch implementation of the math in this package; if the CUDA
+library is missing or the input is not on a B200, the call raises.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib, spec
+
+
+class ParamTree(nn.Module):
+    """Registers parameters/buffers under dotted reference key names (e.g. `K.0.conv.1.0.weight`) by
+    building the intermediate containers, so `state_dict()` reproduces the reference's keys."""
+
+    def __init__(self, tensor_spec, seed=None):
+        super().__init__()
+        for key, (shape, kind) in tensor_spec.items():
+            if seed is None:
+                t = torch.zeros(shape, dtype=torch.int64 if kind == spec.BN_N else torch.float32)
+            else:
+                t = spec.seeded_tensor(spec.canonical_key(key, shape), shape, kind, seed)
+            self._register(key, t, spec.is_buffer(key))
+
+    def _register(self, key, tensor, is_buffer):
+        *path, leaf = key.split(".")
+        mod = self
+        for name in path:
+            if name not in mod._modules:
+                mod.add_module(name, nn.Module())
+            mod = mod._modules[name]
+        if is_buffer:
+            mod.register_buffer(leaf, tensor)
+        else:
+            mod.register_parameter(leaf, nn.Parameter(tensor, requires_grad=tensor.is_floating_point()))
+
+
+def _device_index(module: nn.Module) -> int:
+    p = next(module.parameters())
+    if p.device.type != "cuda":
+        raise RuntimeError(f"{type(module).__name__}: parameters are on {p.device}; lip2speech_b200 runs on a CUDA (sm_100a) "
+                           "device only — call .cuda() (there is no CPU fallback)")
+    return p.device.index or 0
+
+
+class VideoExtractor(ParamTree):
+    """Conv3d stem + per-frame ShuffleNetV2 x1.0 trunk + L2 norm (reference video.py:26-87)."""
+
+    def __init__(self, seed=None):
+        super().__init__(spec.encoder_spec(), seed)
+        self.backend_out = spec.VIDEO_FEAT
+        self.precision = _lib.PRECISION_FP32
+
+    def forward(self, x):
+        be = _lib.backend(_device_index(self))
+        be.sync_module(self, "encoder.", _lib.PART_VIDEO)
+        return be.video_fwd(x, self.precision)
+
+
+class SpeakerEncoder(ParamTree):
+    """GE2E-style speaker encoder (reference audio.py:110-150).  `forward` returns the raw (pre-ReLU)
+    embedding, `inference` the normalised one, exactly like the reference."""
+
+    def __init__(self, state_dict=None, seed=None):
+        super().__init__(spec.speaker_spec(), seed)
+        for p in self.parameters():
+            p.requires_grad_(False)
+        if state_dict is not None:
+            self.load_state_dict(state_dict, strict=True)
+
+    def forward(self, utterances, hidden_init=None):
+        if hidden_init is not None:
+            raise NotImplementedError("hidden_init is never passed by the reference's callers (demo.py:84)")
+        be = _lib.backend(_device_index(self))
+        be.sync_module(self, "speaker_encoder.", _lib.PART_SPEAKER)
+        return be.speaker_fwd(utterances, normalize=False)
+
+    def inference(self, x):
+        if self.training:
+            self.eval()
+        be = _lib.backend(_device_index(self))
+        be.sync_module(self, "speaker_encoder.", _lib.PART_SPEAKER)
+        return be.speaker_fwd(x, normalize=True)
+
+
+class Decoder(ParamTree):
+    """Bi-LSTM encoder, K/V MultiHopConv, Content slots, 300-step AR loop, Postnet (reference decoder.py:274-444)."""
+
+    def __init__(self, seed=None):
+        super().__init__(spec.decoder_spec(), seed)
+        self.n_mel_channels = spec.N_MELS
+        self.max_decoder_steps = spec.MAX_DECODER_STEPS
+
+    def _sync(self):
+        be = _lib.backend(_device_index(self))
+        be.sync_module(self, "decoder.", _lib.PART_DECODER)
+        return be
+
+    def draw_gumbel(self, n_clips: int, T: int, device) -> torch.Tensor:
+        """g = -log(Exp(1)) from torch's global generator on `device` — the draw F.gumbel_softmax makes at
+        decoder.py:257 (it is the first RNG consumer of Decoder.inference, so a seeded run consumes the
+        same stream as the reference on the same device)."""
+        rows = n_clips * spec.content_min_t(T)
+        return -torch.empty(rows, spec.VOCAB, device=device, dtype=torch.float32).exponential_().log()
+
+    def inference(self, encoder_outputs, face_features, return_attention_map=False, gumbel_noise=None):
+        """encoder_outputs [B,T,1024]; face_features [B,T,256] (only [:,0] is read, decoder.py:385).
+        Returns (mel_post [B,80,300], output_lengths [B] int64[, attention [B,300,T]])."""
+        be = self._sync()
+        B, T = encoder_outputs.shape[:2]
+        if gumbel_noise is None:
+            gumbel_noise = self.draw_gumbel(B, T, encoder_outputs.device)
+        spk = face_features[:, 0]
+        return be.decoder_infer(encoder_outputs, spk, gumbel_noise, self.max_decoder_steps, return_attention_map)
+
+    def postnet_forward(self, x):
+        """Postnet.forward (eval): x [B,80,L] -> [B,80,L] (reference decoder.py:143-156)."""
+        return self._sync().postnet_fwd(x, add_residual=False)
+
+    def forward(self, encoder_outputs, face_features, mels, text_lengths, output_lengths, tf_ratio):
+        raise NotImplementedError("Decoder.forward (teacher-forced train/eval path, decoder.py:320-379) is not built yet: "
+                                  "SURVEY.md §8 row a10 train flavour / §7 step 7; use .inference()")
+
+
+class Lip2Speech(nn.Module):
+    """Top-level glue (reference model.py:13-59).  `vgg_face` (FaceRecognizer, out of scope: third-party
+    InceptionResnetV1) may be attached by the caller; `inference` needs it only when no speaker embedding
+    is given, as in the reference."""
+
+    def __init__(self, seed=None, vgg_face: nn.Module | None = None):
+        super().__init__()
+        if vgg_face is not None:
+            self.vgg_face = vgg_face
+        self.encoder = VideoExtractor(seed)
+        self.decoder = Decoder(seed)
+
+    def inference(self, video_frames, face_frames, speaker_embedding=None, gumbel_noise=None, **kwargs):
+        with torch.no_grad():
+            video_features = self.encoder(video_frames)
+            if speaker_embedding is None:
+                if not hasattr(self, "vgg_face"):
+                    raise RuntimeError("no speaker_embedding given and no vgg_face module attached (model.py:47-50)")
+                face_features = self.vgg_face.inference(face_frames[:, 0, :, :, :])
+            else:
+                face_features = speaker_embedding
+            N, T, C = video_features.shape
+            face_features = face_features.unsqueeze(1).repeat(1, T, 1)
+            visual_features = torch.cat([video_features, face_features], dim=2)
+            return self.decoder.inference(visual_features, face_features, gumbel_noise=gumbel_noise, **kwargs)
+
+    def forward(self, video_frames, face_frames, audio_frames, melspecs, video_lengths, audio_lengths, melspec_lengths, tf_ratio):
+        raise NotImplementedError("Lip2Speech.forward (train path, model.py:23-40) is not built yet; use .inference()")
+
+
+def get_network(mode: str, seed=None) -> Lip2Speech:
+    """reference model.py:62-72"""
+    assert mode in ("train", "test")
+    model = Lip2Speech(seed)
+    return model.train() if mode == "train" else model.eval()
+
+
+def demo_span(backend: "_lib.Backend", video, wav, gumbel, steps=300, precision=_lib.PRECISION_FP32):
+    """speaker_encoder.inference + net.inference on device tensors in one C-ABI call (demo.py:84-86)."""
+    return backend.infer(video, wav, gumbel, steps, precision)

@@ -1,0 +1,174 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle and the committed golden vectors
+produced by the unmodified reference.  Tolerance: max|a-b|/max|b| <= 1e-3 (north_star, fp32)."""
+import pytest
+import torch
+
+from conftest import rel_err
+from lip2speech_b200 import spec, synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def be(weights):
+    from lip2speech_b200 import _lib, build
+    build.build()
+    b = _lib.backend(0)
+    b.bind_state_dict(weights, "", _lib.PART_VIDEO | _lib.PART_SPEAKER | _lib.PART_DECODER)
+    return b
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import l2s_oracle
+    return l2s_oracle
+
+
+def test_speaker_encoder(be, O, golden, spk_weights):
+    wav = synth.wav(2)
+    raw = be.speaker_fwd(wav.cuda(), normalize=False).cpu()
+    assert rel_err(raw, golden["A_spk_raw"]) < TOL
+    assert rel_err(raw, O.speaker_forward(spk_weights, wav)) < TOL
+    emb = be.speaker_fwd(wav.cuda(), normalize=True).cpu()
+    assert rel_err(emb, golden["A_spk_emb"]) < TOL
+    raw = be.speaker_fwd(synth.wav(1, 48000, seed=9).cuda(), normalize=False).cpu()
+    assert rel_err(raw, golden["F_spk_raw"]) < TOL
+
+
+def test_video_frontend(be, golden):
+    f = be.video_fwd(synth.video(2, 29).cuda()).cpu()
+    assert f.shape == (2, 29, 768)
+    assert rel_err(f, golden["A_video_feat"]) < TOL
+    f = be.video_fwd(synth.video(1, 5, 88, 88, seed=5).cuda()).cpu()
+    assert rel_err(f, golden["D_video_feat"]) < TOL
+
+
+def test_postnet(be, golden):
+    y = be.postnet_fwd(synth.mel_like(2, 77).cuda()).cpu()
+    assert rel_err(y, golden["E_postnet"]) < TOL
+
+
+def test_decoder_preloop_tensors(be, O, weights):
+    visual, face = synth.visual_features(3, 29)
+    g = synth.gumbel(3, 29)
+    be.decoder_infer(visual.cuda(), face[:, 0].cuda(), g.cuda(), steps=2)
+    pre = O.decoder_preloop(weights, visual, face[:, 0], g)
+    assert rel_err(be.debug_read("dec.rnn_out", (3, 29, 1024)), O._lstm(visual, pre_h0(O, weights, face), pre_h0(O, weights, face).clone(), weights, "decoder.encoder_rnn", 1, True)[0]) < TOL
+    assert rel_err(be.debug_read("dec.enc", (3, 29, 512)), pre["enc"]) < TOL
+    assert rel_err(be.debug_read("dec.enc_cell", (3, 512)), pre["enc_cell"]) < TOL
+    assert rel_err(be.debug_read("dec.K", (3, 29, 512)), pre["k"].permute(0, 2, 1)) < TOL
+    assert rel_err(be.debug_read("dec.V", (3, 29, 512)), pre["v"]) < TOL
+    assert rel_err(be.debug_read("dec.ckey", (3, 4, 256)), pre["ckey"].permute(0, 2, 1)) < TOL
+    assert rel_err(be.debug_read("dec.cval", (3, 4, 256)), pre["cval"]) < TOL
+
+
+def pre_h0(O, weights, face):
+    p = "decoder."
+    s = O.psine(torch.nn.functional.linear(face[:, 0], weights[p + "encoder_site.0.linear_layer.weight"],
+                                           weights[p + "encoder_site.0.linear_layer.bias"]), weights[p + "encoder_site.1.w"])
+    return s.unsqueeze(0).repeat(2, 1, 1)
+
+
+def test_decoder_few_steps(be, O, weights):
+    visual, face = synth.visual_features(3, 29)
+    g = synth.gumbel(3, 29)
+    for steps in (1, 2, 5):
+        mel, lengths = be.decoder_infer(visual.cuda(), face[:, 0].cuda(), g.cuda(), steps=steps)
+        pre = O.decoder_preloop(weights, visual, face[:, 0], g)
+        outs, lens, _ = O.decoder_steps(weights, pre, steps)
+        assert rel_err(be.debug_read("dec.outputs", (3, steps, 80)), outs) < TOL, steps
+        assert torch.equal(lengths.cpu(), lens)
+
+
+def test_decoder_inference_golden(be, golden):
+    visual, face = synth.visual_features(3, 29)
+    mel, lengths, attn = be.decoder_infer(visual.cuda(), face[:, 0].cuda(), synth.gumbel(3, 29).cuda(), return_attention=True)
+    assert mel.shape == (3, 80, 300) and attn.shape == (3, 300, 29)
+    assert torch.equal(lengths.cpu(), golden["B_lengths"])
+    assert rel_err(mel.cpu(), golden["B_mel"]) < TOL
+    assert (attn.cpu() - golden["B_attn"]).abs().max() < 2e-2      # one-hot-sharp softmax (temperature sqrt(512))
+    visual, face = synth.visual_features(1, 75, seed=77)
+    mel, lengths = be.decoder_infer(visual.cuda(), face[:, 0].cuda(), synth.gumbel(1, 75, seed=77).cuda())
+    assert torch.equal(lengths.cpu(), golden["C_lengths"])
+    assert rel_err(mel.cpu(), golden["C_mel"]) < TOL
+
+
+def test_full_span_golden(be, golden):
+    mel, lengths = be.infer(synth.video(2, 29).cuda(), synth.wav(2).cuda(), synth.gumbel(2, 29).cuda())
+    assert torch.equal(lengths.cpu(), golden["A_lengths"])
+    assert rel_err(mel.cpu(), golden["A_mel"]) < TOL
+
+
+def test_batch_33_two_clip_groups_vs_oracle(be, O, weights):
+    """B=33 exercises the second 32-clip group and batch padding."""
+    visual, face = synth.visual_features(33, 29, seed=21)
+    g = synth.gumbel(33, 29, seed=21)
+    mel, lengths = be.decoder_infer(visual.cuda(), face[:, 0].cuda(), g.cuda(), steps=40)
+    ref_mel, ref_len = O.decoder_inference(weights, visual, face, g, steps=40)
+    assert torch.equal(lengths.cpu(), ref_len)
+    assert rel_err(mel.cpu(), ref_mel) < TOL
+
+
+def test_batch_invariance_full_size(be):
+    """Size-independent property at the bench size (B=32, 300 steps): a clip's mel does not depend on
+    which other clips share the batch — bit-exact."""
+    visual, face = synth.visual_features(32, 29, seed=5)
+    g = synth.gumbel(32, 29, seed=5)
+    mel, lengths = be.decoder_infer(visual.cuda(), face[:, 0].cuda(), g.cuda())
+    for i in (0, 17, 31):
+        m1, l1 = be.decoder_infer(visual[i:i + 1].cuda(), face[i:i + 1, 0].cuda(), g[4 * i:4 * i + 4].cuda())
+        assert torch.equal(m1[0], mel[i]) and int(l1[0]) == int(lengths[i])
+
+
+def test_stop_token_midway(O, weights):
+    """Shift the stop bias so the gate fires mid-sequence and check output_lengths (decoder.py:429-435)."""
+    from lip2speech_b200 import _lib
+    w = dict(weights)
+    visual, face = synth.visual_features(4, 29, seed=8)
+    g = synth.gumbel(4, 29, seed=8)
+    # find a bias that makes some clips stop between step 3 and 60
+    pre = O.decoder_preloop(w, visual, face[:, 0], g)
+    key = "decoder.stop_token_layer.linear_layer.bias"
+    best = None
+    for shift in (0.0, 0.5, 1.0, 1.5, 2.0, 3.0, -0.5, -1.0, -2.0):
+        w[key] = weights[key] + shift
+        _, lens, _ = O.decoder_steps(w, pre, 60)
+        if ((lens > 1) & (lens < 60)).any():
+            best = shift
+            break
+    if best is None:
+        pytest.skip("no stop-bias shift produces a mid-sequence stop with these seeded weights")
+    b2 = _lib.Backend(0)
+    b2.bind_state_dict(w, "", _lib.PART_DECODER)
+    _, lengths = b2.decoder_infer(visual.cuda(), face[:, 0].cuda(), g.cuda(), steps=60)
+    assert torch.equal(lengths.cpu(), lens)
+    b2.close()
+
+
+def test_module_mirror_matches_backend(be, weights, golden):
+    """The nn.Module mirror (reference-shaped API) drives the same kernels."""
+    from lip2speech_b200 import modules
+    sd = dict(weights)
+    spk_sd = {k[len("speaker_encoder."):]: sd.pop(k) for k in list(sd) if k.startswith("speaker_encoder.")}
+    net = modules.get_network("test")
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda()
+    spk = modules.SpeakerEncoder(state_dict=spk_sd).eval().cuda()
+    emb = spk.inference(synth.wav(2).cuda())
+    mel, lengths, attn = net.inference(synth.video(2, 29).cuda(), None, emb, return_attention_map=True,
+                                       gumbel_noise=synth.gumbel(2, 29).cuda())
+    assert rel_err(mel.cpu(), golden["A_mel"]) < TOL
+    assert attn.shape == (2, 300, 29)
+    # seeded internal gumbel draw is reproducible
+    torch.manual_seed(7); m1, _ = net.inference(synth.video(2, 29).cuda(), None, emb)
+    torch.manual_seed(7); m2, _ = net.inference(synth.video(2, 29).cuda(), None, emb)
+    assert torch.equal(m1, m2)
+
+
+def test_unsupported_shapes_are_errors(be):
+    visual, face = synth.visual_features(1, 29)
+    with pytest.raises(RuntimeError):
+        be.decoder_infer(visual.cuda(), face[:, 0].cuda(), synth.gumbel(1, 29).cuda(), steps=301)
+    with pytest.raises(RuntimeError):
+        be.video_fwd(torch.zeros(1, 3, 2, 64, 64).cuda())
