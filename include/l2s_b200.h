@@ -89,6 +89,12 @@ int l2s_infer_host(l2s_ctx* ctx, const float* video, const float* wav, const flo
 /* Number of kernels this library has launched on ctx since creation (bench.py `gpu_launches`). */
 int64_t l2s_launch_count(const l2s_ctx* ctx);
 
+/* Stage timing for bench.py's roofline: when enabled, CUDA events are recorded on the caller's stream around
+ * the stages "speaker", "video", "preloop", "decode_loop" (the persistent step kernel alone) and "postnet".
+ * l2s_span_ms synchronises on the closing event and returns the last duration in ms (-1 if never recorded). */
+int l2s_set_profiling(l2s_ctx* ctx, int enabled);
+double l2s_span_ms(l2s_ctx* ctx, const char* name);
+
 /* Debug/test access to the most recent intermediate tensors (device->host copy, synchronising).
  * Names: "dec.K" [B,T,512], "dec.V" [B,T,512], "dec.enc_cell" [B,512], "dec.ckey" [B,minT,256],
  * "dec.cval" [B,minT,256], "dec.outputs" [B,steps,80], "video.stem" [B*T,H/4,W/4,24].

@@ -18,7 +18,7 @@ PRECISION_FP32, PRECISION_BF16 = 0, 1
 
 EXPORTS = ("l2s_version", "l2s_create", "l2s_destroy", "l2s_last_error", "l2s_bind_weight", "l2s_commit_weights",
            "l2s_video_fwd", "l2s_speaker_fwd", "l2s_decoder_infer", "l2s_postnet_fwd", "l2s_infer", "l2s_infer_host",
-           "l2s_launch_count", "l2s_debug_read")
+           "l2s_launch_count", "l2s_debug_read", "l2s_set_profiling", "l2s_span_ms")
 
 _lib = None
 _lock = threading.Lock()
@@ -48,6 +48,8 @@ def load() -> C.CDLL:
         lib.l2s_infer.argtypes = [vp, fp, fp, fp, i, i, i, i, i, i, fp, vp, i, vp]
         lib.l2s_infer_host.argtypes = [vp, fp, fp, fp, i, i, i, i, i, i, fp, vp, i]
         lib.l2s_launch_count.argtypes = [vp]; lib.l2s_launch_count.restype = C.c_int64
+        lib.l2s_set_profiling.argtypes = [vp, i]
+        lib.l2s_span_ms.argtypes = [vp, C.c_char_p]; lib.l2s_span_ms.restype = C.c_double
         lib.l2s_debug_read.argtypes = [vp, C.c_char_p, fp, C.c_int64]; lib.l2s_debug_read.restype = C.c_int64
         _lib = lib
         return lib
@@ -170,6 +172,12 @@ class Backend:
             assert t.device.type == "cpu" and t.dtype == torch.float32 and t.is_contiguous()
         self._check(self.lib.l2s_infer_host(self.h, video.data_ptr(), wav.data_ptr(), gumbel.data_ptr(), B, T, H, W, wav.shape[1], steps,
                                             mel_out.data_ptr(), C.c_void_p(lengths_out.data_ptr()), precision), "l2s_infer_host")
+
+    def set_profiling(self, enabled: bool):
+        self.lib.l2s_set_profiling(self.h, int(enabled))
+
+    def span_ms(self, name: str) -> float:
+        return float(self.lib.l2s_span_ms(self.h, name.encode()))
 
     def launch_count(self) -> int:
         return int(self.lib.l2s_launch_count(self.h))

@@ -220,6 +220,7 @@ static void decoder_infer(Context& c, const float* visual, const float* spk, con
     const float* pos = c.dev("d.pos");
 
     // ---- encoder pre-loop (decoder.py:383-394) --------------------------------------------------
+    c.span_begin("preloop", s);
     float* resid = c.fbuf("ws.d.resid", (size_t)M * 512);
     linear(c, visual, 1024, c.dev("d.resid.w"), c.dev("d.resid.b"), resid, 512, M, 512, 1024, ACT_NONE, nullptr, s, "residual_bottleneck");
     float* encsite = c.fbuf("ws.d.encsite", (size_t)B * 512);
@@ -341,11 +342,16 @@ static void decoder_infer(Context& c, const float* visual, const float* spk, con
         const size_t smem = (size_t)c.meta.at("d.step.smem");
         L2S_CUDA(cudaFuncSetAttribute(decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         void* args[] = {&dp};
+        c.span_end("preloop", s);
+        c.span_begin("decode_loop", s);
         L2S_CUDA(cudaLaunchCooperativeKernel((void*)decode_persistent_kernel, dim3(c.num_sms), dim3(MV_THREADS), args, smem, s));
+        c.span_end("decode_loop", s);
         c.launches++;
     }
+    c.span_begin("postnet", s);
     // ---- postnet + residual (decoder.py:437-439) --------------------------------------------------
     postnet_rows(c, outputs, B, steps, mel_post, true, s);
+    c.span_end("postnet", s);
     c.meta["dbg.B"] = B; c.meta["dbg.T"] = T; c.meta["dbg.minT"] = minT; c.meta["dbg.steps"] = steps;
 }
 
@@ -373,8 +379,12 @@ static void infer_device(Context& c, const float* video, const float* wav, const
     float* emb = c.fbuf("ws.i.emb", (size_t)B * 256);
     float* feat = c.fbuf("ws.i.feat", (size_t)B * T * 768);
     float* visual = c.fbuf("ws.i.visual", (size_t)B * T * 1024);
+    c.span_begin("speaker", s);
     speaker_forward(c, wav, B, S, emb, 1, s);
+    c.span_end("speaker", s);
+    c.span_begin("video", s);
     video_forward(c, video, B, T, H, W, feat, precision, s);
+    c.span_end("video", s);
     concat_visual_kernel<<<ew_grid((size_t)B * T * 1024), 256, 0, s>>>(feat, emb, visual, B, T);
     check_launch(c, "concat visual");
     decoder_infer(c, visual, emb, gumbel, B, T, steps, mel_post, lengths, nullptr, s);
@@ -536,6 +546,23 @@ int l2s_infer_host(l2s_ctx* ctx, const float* video, const float* wav, const flo
 }
 
 int64_t l2s_launch_count(const l2s_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
+
+int l2s_set_profiling(l2s_ctx* ctx, int enabled) {
+    if (!ctx) return L2S_ERR_INVALID;
+    ctx->c.profiling = enabled != 0;
+    return L2S_OK;
+}
+
+double l2s_span_ms(l2s_ctx* ctx, const char* name) {
+    if (!ctx || !name) return -1.0;
+    auto it = ctx->c.spans.find(name);
+    if (it == ctx->c.spans.end() || !it->second.used) return -1.0;
+    cudaSetDevice(ctx->c.device);
+    if (cudaEventSynchronize(it->second.e1) != cudaSuccess) return -1.0;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, it->second.e0, it->second.e1) != cudaSuccess) return -1.0;
+    return (double)ms;
+}
 
 int64_t l2s_debug_read(l2s_ctx* ctx, const char* name, float* out, int64_t n) {
     if (!ctx || !name) return -1;

@@ -44,6 +44,22 @@ struct Context {
     std::map<std::string, int64_t> meta;      // small integers produced by packing (sizes, counts)
     int64_t launches = 0;
     int committed = 0;
+    // optional stage timing (CUDA events on the caller's stream), enabled by l2s_set_profiling
+    bool profiling = false;
+    struct Span { cudaEvent_t e0 = nullptr, e1 = nullptr; bool used = false; };
+    std::map<std::string, Span> spans;
+    void span_begin(const std::string& name, cudaStream_t s) {
+        if (!profiling) return;
+        Span& sp = spans[name];
+        if (!sp.e0) { L2S_CUDA(cudaEventCreate(&sp.e0)); L2S_CUDA(cudaEventCreate(&sp.e1)); }
+        L2S_CUDA(cudaEventRecord(sp.e0, s));
+    }
+    void span_end(const std::string& name, cudaStream_t s) {
+        if (!profiling) return;
+        Span& sp = spans[name];
+        L2S_CUDA(cudaEventRecord(sp.e1, s));
+        sp.used = true;
+    }
 
     const HostTensor& W(const std::string& key) const {
         auto it = w.find(key);
@@ -86,6 +102,11 @@ struct Context {
         for (auto& kv : bufs)
             if (kv.second.p) cudaFree(kv.second.p);
         bufs.clear();
+        for (auto& kv : spans) {
+            if (kv.second.e0) cudaEventDestroy(kv.second.e0);
+            if (kv.second.e1) cudaEventDestroy(kv.second.e1);
+        }
+        spans.clear();
     }
 };
 
