@@ -8,6 +8,7 @@
 #include "lstm.cuh"
 #include "misc.cuh"
 #include "pack.h"
+#include "tc_gemm.cuh"
 #include "video.cuh"
 
 using namespace l2s;
@@ -182,7 +183,70 @@ static void speaker_forward(Context& c, const float* wav, int B, int S, float* e
 // ------------------------------------------------------------------------------------------------
 // postnet (time-major rows [B*L][C])
 // ------------------------------------------------------------------------------------------------
+static void run_tc(Context& c, const TcOperands& o, const TcParams& p, cudaStream_t s, const char* what) {
+    const char* err = launch_tc_gemm(o, p, s);
+    if (err) throw L2sError(L2S_ERR_CUDA, std::string(what) + " (tcgen05 gemm): " + err);
+    c.launches++;
+}
+
+static inline TcParams tc_defaults() {
+    TcParams p{};
+    p.taps = 1; p.cstride = 1;
+    return p;
+}
+
+// dst[b][P + t][:] = src[b][t][:]   (compact rows -> zero-padded per-sequence layout)
+__global__ void pad_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int L, int Lp, int P, int C4) {
+    const size_t total = (size_t)B * L * C4;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int c4 = i % C4; size_t r = i / C4;
+        int t = r % L; int b = r / L;
+        reinterpret_cast<float4*>(dst)[((size_t)b * Lp + P + t) * C4 + c4] = reinterpret_cast<const float4*>(src)[i];
+    }
+}
+
+// (Re)allocate a padded-layout buffer; its pad rows must be zero, so it is cleared whenever the layout changes.
+static float* padded_buf(Context& c, const std::string& name, int B, int Lp, int C, cudaStream_t s) {
+    float* p = c.fbuf(name, (size_t)B * Lp * C);
+    const int64_t sig = ((int64_t)B << 40) ^ ((int64_t)Lp << 20) ^ C;
+    auto it = c.meta.find(name + ".layout");
+    if (it == c.meta.end() || it->second != sig) {
+        L2S_CUDA(cudaMemsetAsync(p, 0, (size_t)B * Lp * C * sizeof(float), s));
+        c.meta[name + ".layout"] = sig;
+    }
+    return p;
+}
+
+// Postnet on the tensor cores: 5 x (k=5 Conv1d as 5-tap implicit GEMM, BN folded, PSine / residual epilogue).
+static void postnet_rows_tc(Context& c, const float* x_rows /*[B*L][80]*/, int B, int L, float* out_bcl, bool add_residual, cudaStream_t s) {
+    const int P = 2, Lp = L + 2 * P, Mp = B * Lp;
+    float* xin = padded_buf(c, "ws.p.xin", B, Lp, 80, s);
+    float* bufs[2] = {padded_buf(c, "ws.p.ta", B, Lp, 512, s), padded_buf(c, "ws.p.tb", B, Lp, 512, s)};
+    pad_rows_kernel<<<ew_grid((size_t)B * L * 20), 256, 0, s>>>(x_rows, xin, B, L, Lp, P, 20);
+    check_launch(c, "pad rows");
+    const float* in = xin; int cin = 80;
+    for (int i = 0; i < 5; ++i) {
+        const std::string n = "d.post" + std::to_string(i);
+        const int kcp = (int)c.meta.at(n + ".kcp");
+        TcOperands o{in, cin, Mp, cin, c.dev(n + ".hi"), c.dev(n + ".lo"), 5 * kcp};
+        TcParams p = tc_defaults();
+        p.M = Mp; p.Kc = cin; p.Kcp = kcp; p.taps = 5; p.pad = 2;
+        p.Lp_in = Lp; p.P_in = P; p.L = L; p.Lp_out = Lp; p.P_out = P;
+        p.bias = c.dev(n + ".b");
+        if (i < 4) {
+            p.N = 512; p.C = bufs[i & 1]; p.ldc = 512; p.act = ACT_PSINE; p.act_w = c.dev(n + ".psw");
+            if (i != 0) { p.resid = in; p.ldr = 512; }
+        } else {
+            p.N = 80; p.C = out_bcl; p.transposed = 1; p.act = ACT_NONE;
+            if (add_residual) { p.resid = xin; p.ldr = 80; }
+        }
+        run_tc(c, o, p, s, "postnet conv");
+        in = bufs[i & 1]; cin = 512;
+    }
+}
+
 static void postnet_rows(Context& c, const float* x_rows /*[B*L][80]*/, int B, int L, float* out_bcl /*[B][80][L]*/, bool add_residual, cudaStream_t s) {
+    if (c.use_tc) { postnet_rows_tc(c, x_rows, B, L, out_bcl, add_residual, s); return; }
     const int M = B * L;
     float* a = c.fbuf("ws.p.a", (size_t)M * 512);
     float* b = c.fbuf("ws.p.b", (size_t)M * 512);
@@ -329,9 +393,10 @@ static void decoder_infer(Context& c, const float* visual, const float* spk, con
         dp.npasses = reinterpret_cast<const int*>(c.dev("d.step.npasses"));
         dp.wimg = c.dev("d.step.wimg"); dp.wimg_floats = (int)c.meta.at("d.step.wimg_floats");
         dp.S = S; dp.Cst = Cst;
-        dp.P1 = c.fbuf("ws.d.P1", (size_t)256 * Bpad); dp.P2 = c.fbuf("ws.d.P2", (size_t)256 * Bpad);
+        dp.P1 = c.fbuf("ws.d.P1", (size_t)256 * Bpad);
         dp.Q = c.fbuf("ws.d.Q", (size_t)512 * Bpad); dp.CQ = c.fbuf("ws.d.CQ", (size_t)256 * Bpad);
-        dp.CTX = c.fbuf("ws.d.CTX", (size_t)512 * Bpad); dp.XD = c.fbuf("ws.d.XD", (size_t)512 * Bpad);
+        dp.XD = c.fbuf("ws.d.XD", (size_t)1024 * Bpad);
+        dp.nsplit = (4 * B <= c.num_sms) ? 4 : (2 * B <= c.num_sms) ? 2 : 1;
         dp.Kmem = Kmem; dp.Vmem = Vmem; dp.ckey = ckey; dp.cval = cval; dp.stop_const = stopc; dp.pos = pos;
         dp.temp = c.W("decoder.temperature").f[0]; dp.ctemp = c.W("decoder.content.temperature").f[0];
         dp.outputs = outputs; dp.lengths = reinterpret_cast<long long*>(lengths); dp.attn = attn;
@@ -339,6 +404,7 @@ static void decoder_infer(Context& c, const float* visual, const float* spk, con
         unsigned* bar = static_cast<unsigned*>(c.buf("ws.barrier", 256));
         L2S_CUDA(cudaMemsetAsync(bar, 0, 4, s));
         dp.barrier = bar;
+        dp.timing = c.profiling ? c.fbuf("ws.d.timing", (size_t)c.num_sms * DEC_TIMING_SLOTS) : nullptr;
         const size_t smem = (size_t)c.meta.at("d.step.smem");
         L2S_CUDA(cudaFuncSetAttribute(decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         void* args[] = {&dp};
@@ -419,6 +485,7 @@ int l2s_create(l2s_ctx** out, int device) {
     ctx->c.device = device;
     ctx->c.num_sms = prop.multiProcessorCount;
     ctx->c.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (const char* e = getenv("L2S_TC")) ctx->c.use_tc = (e[0] != '0');
     *out = ctx;
     return L2S_OK;
 }
@@ -574,6 +641,7 @@ int64_t l2s_debug_read(l2s_ctx* ctx, const char* name, float* out, int64_t n) {
         {"dec.enc", "ws.d.enc", B * T * 512}, {"dec.rnn_out", "ws.d.rnnout", B * T * 1024},
         {"dec.ckey", "ws.d.ckey", B * minT * 256}, {"dec.cval", "ws.d.cval", B * minT * 256},
         {"dec.outputs", "ws.d.outputs", B * steps * 80}, {"dec.clog", "ws.d.clog", B * minT * 501},
+        {"dec.timing", "ws.d.timing", (int64_t)c.num_sms * DEC_TIMING_SLOTS},
     };
     for (auto& t : tab) {
         if (std::strcmp(t.name, name) == 0) {

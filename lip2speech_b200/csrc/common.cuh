@@ -62,6 +62,18 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target
     __syncthreads();
 }
 
+// Split-phase variant: arrive after a stage's global writes, do work that only needs OLDER data, then wait.
+__device__ __forceinline__ void grid_arrive(unsigned* counter) {
+    __syncthreads();                                   // all warps of this CTA finished the stage's writes
+    if (threadIdx.x == 0) red_release_add_u32(counter, 1u);
+}
+__device__ __forceinline__ void grid_wait(const unsigned* counter, unsigned target) {
+    if (threadIdx.x == 0) {
+        while (ld_acquire_u32(counter) < target) {}
+    }
+    __syncthreads();
+}
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace l2s

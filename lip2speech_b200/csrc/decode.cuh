@@ -2,31 +2,36 @@
 // kernel (reference decoder.py:403-435; one step = SURVEY.md §3.4).
 //
 // Design (B200-first, not a translation of the reference's ~25 library calls + 1 host sync per step):
-//  * The 5.4 M step weights (prenet, Q, content.Q, attention_proj, 2 LSTM cells, fc_out, stop) are
-//    partitioned BY OUTPUT ROW over the 148 SMs and stay resident in shared memory for all 300 steps:
-//    HBM weight traffic is paid once per batch instead of once per step.
-//  * Activations are exchanged through L2 in feature-major [feature][clip] buffers; every dependent
-//    layer boundary is one grid barrier (5 per step):
-//        A : fc_out -> mel frame, stop token ; prenet layer 1 (fused with fc_out: W_p1*W_fc) ;
+//  * The step weights (prenet, Q, content.Q, attention_proj, 2 LSTM cells, fc_out, stop) are partitioned
+//    BY OUTPUT ROW over the 148 SMs and stay resident in shared memory for all 300 steps: HBM weight
+//    traffic is paid once per batch instead of once per step.
+//  * Activations are exchanged through L2 in feature-major [feature][clip] buffers.  Every dependent layer
+//    boundary is one grid barrier; linear∘linear pairs are merged on the host so that only FOUR remain:
+//        A : fc_out -> mel frame, stop token ; prenet-1 (fused with fc_out: W_p1·W_fc) ;
 //            Q = PSine(W_q [h0;h1]) + pos[i+1] ; content query = SiLU(W_cq [c0;c1])
-//        B : prenet layer 2 ; per-clip dot-product attention over T (K,V) and over the content slots
-//        C : x2 = prenet2 + attention_proj(ctx)
-//        D : LSTM layer 0 (gates = [W_ih|W_hh] [cv;x2;h0] + b) -> h0', c0'
-//        E : LSTM layer 1 -> h1', c1'
-//  * Which CTA owns which rows is decided on the host (api.cu: pack_decode) and handed over as a list
-//    of `DecPass` descriptors, so load-balancing policy is not baked into the kernel.
+//        B : prenet-2 ; per-clip dot-product attention over T (K,V) and over the content slots
+//        D : LSTM-0 with attention_proj folded in: gates = [W_a|W_b|W_b·W_ap|W_hh] [cv;p2;ctx;h0] + b'
+//        E : LSTM-1: gates = [W_ih|W_hh] [h0';h1] + b
+//  * Barriers are split-phase (arrive / wait).  Each pass has an EARLY segment whose operands were produced
+//    two or more stages ago (h_prev for the LSTMs, h0'/c0' for the queries) and a LATE segment that needs
+//    the previous stage: the early FMAs run between arrive and wait and hide the barrier latency.
+//  * Which CTA owns which rows is decided on the host (pack.h: pack_decode_program) and handed over as a
+//    list of `DecPass` descriptors, so load-balancing policy is not baked into the kernel.
 //  * Stop-token bookkeeping (output_lengths) happens on the device; there is no host sync in the loop.
 #pragma once
 #include "matvec.cuh"
 
 namespace l2s {
 
-enum DecOp { OP_NONE = 0, OP_FC, OP_P1, OP_STOP, OP_Q, OP_CQ, OP_P2, OP_X2, OP_GATE0, OP_GATE1 };
-enum DecSrc { SRC_NONE = 0, SRC_H1NEW, SRC_HNEW, SRC_C, SRC_P1, SRC_CTX, SRC_XD, SRC_H0OLD, SRC_H0NEW, SRC_H1OLD };
-enum DecStage { ST_A = 0, ST_B, ST_C, ST_D, ST_E, ST_COUNT };
+enum DecOp { OP_NONE = 0, OP_FC, OP_P1, OP_STOP, OP_Q, OP_CQ, OP_P2, OP_GATE0, OP_GATE1 };
+enum DecSrc { SRC_NONE = 0, SRC_H0NEW, SRC_H1NEW, SRC_C0, SRC_C1, SRC_P1, SRC_XD, SRC_H0OLD, SRC_H1OLD };
+enum DecStage { ST_A = 0, ST_B, ST_D, ST_E, ST_COUNT };
 
 struct DecPass {
-    int stage, R, K0, K1, src0, src1, w_off, pad_;
+    int stage, R;
+    int Ke, src_e, wcol_e;     // early segment (may be empty)
+    int Kl, src_l, wcol_l;     // late segment
+    int ldw, w_off, pad0_, pad1_;
     int op[16];
     int idx[16];
     float bias[16];
@@ -34,7 +39,9 @@ struct DecPass {
     float aux2[16];    // OP_P1: prenet layer-1 output for the BOS frame (step 0 input)
 };
 
-constexpr int DEC_MAX_PASSES = 10;
+constexpr int DEC_MAX_PASSES = 8;
+constexpr int DEC_RED_ROWS = 8;           // cross-warp reduction buffer holds 8 rows (R=16 passes reduce in two rounds)
+constexpr int DEC_TIMING_SLOTS = 12;      // per stage: early compute, barrier wait, late compute
 
 struct DecodeParams {
     // per-CTA program
@@ -45,18 +52,25 @@ struct DecodeParams {
     // state / activations (feature-major, ld = Bpad)
     float* S;                     // [2][1024][Bpad]  (h0 rows 0..511, h1 rows 512..1023), parity ping-pong
     float* Cst;                   // [1024][Bpad]     (c0, c1)
-    float* P1; float* P2; float* Q; float* CQ; float* CTX; float* XD;
+    float* P1; float* Q; float* CQ;
+    float* XD;                    // [1024][Bpad]: content value cv (0..255), prenet-2 (256..511), attention ctx (512..1023)
     // per-clip memories
     const float* Kmem; const float* Vmem;      // [B][T][512]
     const float* ckey; const float* cval;      // [B][minT][256]
-    const float* stop_const;                   // [B]  W_stop[512:1024].enc_cell + b_stop
+    const float* stop_const;                   // [B]  W_stop[512:1024].enc_cell
     const float* pos;                          // [300][512]
     float temp, ctemp;
     float* outputs;               // [B][steps][80]
     long long* lengths;           // [B]
     float* attn;                  // [B][steps][T] or null
     int B, Bpad, T, minT, steps;
+    int nsplit;                   // CTAs cooperating on one clip's attention (1, 2 or 4)
     unsigned* barrier;
+    float* timing;                // optional [grid][DEC_TIMING_SLOTS] SM cycles
+};
+
+struct DecSmem {
+    float* wsm; float* red; float* gsm; float* qs; float* sc; float* cqs; float* csc;
 };
 
 __device__ __forceinline__ const float* dec_src(const DecodeParams& p, int src, int parity_new) {
@@ -64,37 +78,42 @@ __device__ __forceinline__ const float* dec_src(const DecodeParams& p, int src, 
     const float* Snew = p.S + (size_t)parity_new * plane;
     const float* Sold = p.S + (size_t)(parity_new ^ 1) * plane;
     switch (src) {
+        case SRC_H0NEW: return Snew;
         case SRC_H1NEW: return Snew + (size_t)512 * p.Bpad;
-        case SRC_HNEW: return Snew;
-        case SRC_C: return p.Cst;
+        case SRC_C0: return p.Cst;
+        case SRC_C1: return p.Cst + (size_t)512 * p.Bpad;
         case SRC_P1: return p.P1;
-        case SRC_CTX: return p.CTX;
         case SRC_XD: return p.XD;
         case SRC_H0OLD: return Sold;
-        case SRC_H0NEW: return Snew;
         case SRC_H1OLD: return Sold + (size_t)512 * p.Bpad;
         default: return nullptr;
     }
 }
 
 // Dot-product attention over the T encoder positions and over the minT content slots for one clip
-// (reference decoder.py:414-419 and Content.forward 262-271).
-__device__ void dec_attend_clip(const DecodeParams& p, int b, int step, float* qs, float* sc, float* cqs, float* csc) {
+// (reference decoder.py:414-419 and Content.forward 262-271).  `nsplit` CTAs share a clip: each recomputes
+// the (cheap) scores and produces its 512/nsplit slice of ctx and 256/nsplit slice of the content value.
+__device__ void dec_attend(const DecodeParams& p, const DecSmem& sm, int b, int part, int step) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    qs[tid] = ldcg1(p.Q + (size_t)tid * p.Bpad + b) * p.temp;
-    if (tid < 256) cqs[tid] = ldcg1(p.CQ + (size_t)tid * p.Bpad + b) * p.ctemp;
+    sm.qs[tid] = ldcg1(p.Q + (size_t)tid * p.Bpad + b) * p.temp;
+    if (tid < 256) sm.cqs[tid] = ldcg1(p.CQ + (size_t)tid * p.Bpad + b) * p.ctemp;
     __syncthreads();
-    for (int t = warp; t < p.T; t += MV_WARPS) {
-        const float4* kr = reinterpret_cast<const float4*>(p.Kmem + ((size_t)b * p.T + t) * 512);
-        float a = 0.f;
+    for (int t0 = warp; t0 < p.T; t0 += 2 * MV_WARPS) {
+        const int t1 = t0 + MV_WARPS;
+        const float4* kr0 = reinterpret_cast<const float4*>(p.Kmem + ((size_t)b * p.T + t0) * 512);
+        const float4* kr1 = reinterpret_cast<const float4*>(p.Kmem + ((size_t)b * p.T + (t1 < p.T ? t1 : t0)) * 512);
+        float4 k0[4], k1[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { k0[i] = __ldg(kr0 + lane + 32 * i); k1[i] = __ldg(kr1 + lane + 32 * i); }
+        float a0 = 0.f, a1 = 0.f;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const float4 k = __ldg(kr + lane + 32 * i);
-            const float4 q = *reinterpret_cast<const float4*>(qs + 4 * (lane + 32 * i));
-            a = fmaf(q.x, k.x, a); a = fmaf(q.y, k.y, a); a = fmaf(q.z, k.z, a); a = fmaf(q.w, k.w, a);
+            const float4 q = *reinterpret_cast<const float4*>(sm.qs + 4 * (lane + 32 * i));
+            a0 = fmaf(q.x, k0[i].x, a0); a0 = fmaf(q.y, k0[i].y, a0); a0 = fmaf(q.z, k0[i].z, a0); a0 = fmaf(q.w, k0[i].w, a0);
+            a1 = fmaf(q.x, k1[i].x, a1); a1 = fmaf(q.y, k1[i].y, a1); a1 = fmaf(q.z, k1[i].z, a1); a1 = fmaf(q.w, k1[i].w, a1);
         }
-        a = warp_sum(a);
-        if (lane == 0) sc[t] = a;
+        a0 = warp_sum(a0); a1 = warp_sum(a1);
+        if (lane == 0) { sm.sc[t0] = a0; if (t1 < p.T) sm.sc[t1] = a1; }
     }
     for (int m = warp; m < p.minT; m += MV_WARPS) {
         const float4* kr = reinterpret_cast<const float4*>(p.ckey + ((size_t)b * p.minT + m) * 256);
@@ -102,65 +121,105 @@ __device__ void dec_attend_clip(const DecodeParams& p, int b, int step, float* q
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
             const float4 k = __ldg(kr + lane + 32 * i);
-            const float4 q = *reinterpret_cast<const float4*>(cqs + 4 * (lane + 32 * i));
+            const float4 q = *reinterpret_cast<const float4*>(sm.cqs + 4 * (lane + 32 * i));
             a = fmaf(q.x, k.x, a); a = fmaf(q.y, k.y, a); a = fmaf(q.z, k.z, a); a = fmaf(q.w, k.w, a);
         }
         a = warp_sum(a);
-        if (lane == 0) csc[m] = a;
+        if (lane == 0) sm.csc[m] = a;
     }
     __syncthreads();
     if (warp == 0) {
         float mx = -INFINITY;
-        for (int t = lane; t < p.T; t += 32) mx = fmaxf(mx, sc[t]);
+        for (int t = lane; t < p.T; t += 32) mx = fmaxf(mx, sm.sc[t]);
         mx = warp_max(mx);
         float sum = 0.f;
-        for (int t = lane; t < p.T; t += 32) { float e = expf(sc[t] - mx); sc[t] = e; sum += e; }
+        for (int t = lane; t < p.T; t += 32) { float e = expf(sm.sc[t] - mx); sm.sc[t] = e; sum += e; }
         sum = warp_sum(sum);
         for (int t = lane; t < p.T; t += 32) {
-            float a = sc[t] / sum;
-            sc[t] = a;
-            if (p.attn) p.attn[((size_t)b * p.steps + step) * p.T + t] = a;
+            float a = sm.sc[t] / sum;
+            sm.sc[t] = a;
+            if (p.attn && part == 0) p.attn[((size_t)b * p.steps + step) * p.T + t] = a;
         }
     } else if (warp == 1) {
-        float v = lane < p.minT ? csc[lane] : -INFINITY;
+        float v = lane < p.minT ? sm.csc[lane] : -INFINITY;
         float mx = warp_max(v);
         float e = lane < p.minT ? expf(v - mx) : 0.f;
         float sum = warp_sum(e);
-        if (lane < p.minT) csc[lane] = e / sum;
+        if (lane < p.minT) sm.csc[lane] = e / sum;
     }
     __syncthreads();
-    {
-        const float* vr = p.Vmem + (size_t)b * p.T * 512 + tid;
-        float a = 0.f;
-        for (int t = 0; t < p.T; ++t) a = fmaf(sc[t], __ldg(vr + (size_t)t * 512), a);
-        p.CTX[(size_t)tid * p.Bpad + b] = a;
+    // ctx slice in chunks of 128 features: thread (fq = tid&31, tg = tid>>5) sums its t-group, then the 16
+    // t-groups are combined in a fixed order (independent of nsplit, so results do not depend on B).
+    const int FW = 512 / p.nsplit;
+    float* part_smem = sm.red;                               // [16][128]
+    for (int fc = 0; fc < FW; fc += 128) {
+        const int f0 = part * FW + fc;
+        const int fq = tid & 31, tg = tid >> 5;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int t = tg; t < p.T; t += MV_WARPS) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p.Vmem + ((size_t)b * p.T + t) * 512 + f0) + fq);
+            const float w = sm.sc[t];
+            a.x = fmaf(w, v.x, a.x); a.y = fmaf(w, v.y, a.y); a.z = fmaf(w, v.z, a.z); a.w = fmaf(w, v.w, a.w);
+        }
+        *reinterpret_cast<float4*>(part_smem + tg * 128 + fq * 4) = a;
+        __syncthreads();
+        if (tid < 128) {
+            float s = 0.f;
+#pragma unroll
+            for (int g = 0; g < MV_WARPS; ++g) s += part_smem[g * 128 + tid];
+            p.XD[(size_t)(512 + f0 + tid) * p.Bpad + b] = s;
+        }
+        __syncthreads();
     }
-    if (tid < 256) {
-        const float* vr = p.cval + (size_t)b * p.minT * 256 + tid;
+    const int CW = 256 / p.nsplit;
+    if (tid < CW) {
+        const int f = part * CW + tid;
+        const float* vr = p.cval + (size_t)b * p.minT * 256 + f;
         float a = 0.f;
-        for (int m = 0; m < p.minT; ++m) a = fmaf(csc[m], __ldg(vr + (size_t)m * 256), a);
-        p.XD[(size_t)tid * p.Bpad + b] = a;
+        for (int m = 0; m < p.minT; ++m) a = fmaf(sm.csc[m], __ldg(vr + (size_t)m * 256), a);
+        p.XD[(size_t)f * p.Bpad + b] = a;
     }
     __syncthreads();
 }
 
+struct StageSync {
+    const unsigned* counter; unsigned target; bool waited;
+    float* tacc; long long tmark; int slot0; bool timing;
+    __device__ __forceinline__ void lap(int slot) {
+        if (timing && threadIdx.x == 0) { long long now = clock64(); tacc[slot] += (float)(now - tmark); tmark = now; }
+    }
+    // Block until every CTA has finished the previous stage (idempotent within a stage).
+    __device__ __forceinline__ void wait() {
+        if (!waited) {
+            lap(slot0);
+            grid_wait(counter, target);
+            lap(slot0 + 1);
+            waited = true;
+        }
+    }
+};
+
 template <int R>
-__device__ __forceinline__ void dec_run_pass(const DecodeParams& p, const DecPass& ps, const float* wsm, float* red, float* gsm,
+__device__ __forceinline__ void dec_run_pass(const DecodeParams& p, const DecPass& ps, const DecSmem& sm, StageSync& sync,
                                              int step, int parity_new) {
     const int tid = threadIdx.x;
-    Seg s0, s1;
-    s0.x = dec_src(p, ps.src0, parity_new); s0.K = ps.K0;
-    s1.x = dec_src(p, ps.src1, parity_new); s1.K = ps.K1;
+    const float* xe = dec_src(p, ps.src_e, parity_new);
+    const float* xl = dec_src(p, ps.src_l, parity_new);
+    const float* W = sm.wsm + ps.w_off;
     const size_t plane = (size_t)1024 * p.Bpad;
     float* Snew = p.S + (size_t)parity_new * plane;
     for (int b0 = 0; b0 < p.Bpad; b0 += MV_CLIPS) {
-        float v = mv_pass<R>(wsm + ps.w_off, ps.K0 + ps.K1, s0, s1, p.Bpad, b0, red);
+        float acc[R][2];
+        mv_zero<R>(acc);
+        if (ps.Ke > 0) mv_accumulate<R>(W, ps.ldw, ps.wcol_e, xe, ps.Ke, p.Bpad, b0, acc);
+        sync.wait();
+        mv_accumulate<R>(W, ps.ldw, ps.wcol_l, xl, ps.Kl, p.Bpad, b0, acc);
+        float v = mv_reduce<R, (R == 16 ? DEC_RED_ROWS : R)>(acc, sm.red);
         const int r = tid >> 5, bb = tid & 31, b = b0 + bb;
         const bool live = (tid < R * MV_CLIPS) && (b < p.B);
         const int op = live ? ps.op[r] : OP_NONE;
         const int idx = live ? ps.idx[r] : 0;
         if (live) v += ps.bias[r];
-        bool gate_pass = false;
         switch (op) {
             case OP_FC:
                 if (step >= 0) p.outputs[((size_t)b * p.steps + step) * 80 + idx] = v;
@@ -180,86 +239,101 @@ __device__ __forceinline__ void dec_run_pass(const DecodeParams& p, const DecPas
                 p.CQ[(size_t)idx * p.Bpad + b] = siluf_acc(v);
                 break;
             case OP_P2:
-                p.P2[(size_t)idx * p.Bpad + b] = sinf(v) * ps.aux[r];
-                break;
-            case OP_X2:
-                p.XD[(size_t)(256 + idx) * p.Bpad + b] = v + ldcg1(p.P2 + (size_t)idx * p.Bpad + b);
+                p.XD[(size_t)(256 + idx) * p.Bpad + b] = sinf(v) * ps.aux[r];
                 break;
             default: break;
         }
         // LSTM passes: rows are (unit, gate) = (r>>2, r&3); all 16 rows of the pass are gate rows.
-        if (ps.op[0] == OP_GATE0 || ps.op[0] == OP_GATE1) {
-            gate_pass = true;
-            if (tid < R * MV_CLIPS) gsm[r * MV_CLIPS + bb] = v;
-        }
+        const bool gate_pass = (ps.op[0] == OP_GATE0 || ps.op[0] == OP_GATE1);      // CTA-uniform
+        if (gate_pass && tid < R * MV_CLIPS) sm.gsm[r * MV_CLIPS + bb] = v;
         __syncthreads();
-        if (gate_pass && live && (r & 3) == 0 && idx >= 0) {
-            const int layer = (op == OP_GATE1) ? 1 : 0;
-            const float gi = gsm[(r + 0) * MV_CLIPS + bb], gf = gsm[(r + 1) * MV_CLIPS + bb];
-            const float gg = gsm[(r + 2) * MV_CLIPS + bb], go = gsm[(r + 3) * MV_CLIPS + bb];
-            const size_t si = (size_t)(layer * 512 + idx) * p.Bpad + b;
-            const float c = sigmoidf_acc(gf) * p.Cst[si] + sigmoidf_acc(gi) * tanhf(gg);
-            const float h = sigmoidf_acc(go) * tanhf(c);
-            p.Cst[si] = c;
-            Snew[si] = h;
+        if (gate_pass) {
+            if (live && (r & 3) == 0 && idx >= 0) {
+                const int layer = (op == OP_GATE1) ? 1 : 0;
+                const float gi = sm.gsm[(r + 0) * MV_CLIPS + bb], gf = sm.gsm[(r + 1) * MV_CLIPS + bb];
+                const float gg = sm.gsm[(r + 2) * MV_CLIPS + bb], go = sm.gsm[(r + 3) * MV_CLIPS + bb];
+                const size_t si = (size_t)(layer * 512 + idx) * p.Bpad + b;
+                const float c = sigmoidf_acc(gf) * p.Cst[si] + sigmoidf_acc(gi) * tanhf(gg);
+                const float h = sigmoidf_acc(go) * tanhf(c);
+                p.Cst[si] = c;
+                Snew[si] = h;
+            }
+            __syncthreads();
         }
-        if (gate_pass) __syncthreads();
     }
 }
 
-__device__ __forceinline__ void dec_dispatch(const DecodeParams& p, const DecPass& ps, const float* wsm, float* red, float* gsm,
+__device__ __forceinline__ void dec_dispatch(const DecodeParams& p, const DecPass& ps, const DecSmem& sm, StageSync& sync,
                                              int step, int parity_new) {
-    if (ps.R == 16) dec_run_pass<16>(p, ps, wsm, red, gsm, step, parity_new);
-    else if (ps.R == 8) dec_run_pass<8>(p, ps, wsm, red, gsm, step, parity_new);
-    else dec_run_pass<4>(p, ps, wsm, red, gsm, step, parity_new);
+    if (ps.R == 16) dec_run_pass<16>(p, ps, sm, sync, step, parity_new);
+    else if (ps.R == 8) dec_run_pass<8>(p, ps, sm, sync, step, parity_new);
+    else dec_run_pass<4>(p, ps, sm, sync, step, parity_new);
 }
 
 __global__ void __launch_bounds__(MV_THREADS, 1) decode_persistent_kernel(const DecodeParams p) {
     extern __shared__ __align__(16) float smem[];
-    float* wsm = smem;                                   // weight image
-    float* red = wsm + p.wimg_floats;                    // [16 warps][16][32]
-    float* gsm = red + MV_WARPS * 16 * MV_CLIPS;         // [16][32]
-    float* qs = gsm + 16 * MV_CLIPS;                     // [512]
-    float* sc = qs + 512;                                // [320]
-    float* cqs = sc + 320;                               // [256]
-    float* csc = cqs + 256;                              // [32]
+    DecSmem sm;
+    sm.wsm = smem;                                           // weight image
+    sm.red = sm.wsm + p.wimg_floats;                         // [16 warps][8][32]
+    sm.gsm = sm.red + MV_WARPS * DEC_RED_ROWS * MV_CLIPS;    // [16][32]
+    sm.qs = sm.gsm + 16 * MV_CLIPS;                          // [512]
+    sm.sc = sm.qs + 512;                                     // [320]
+    sm.cqs = sm.sc + 320;                                    // [256]
+    sm.csc = sm.cqs + 256;                                   // [32]
     __shared__ DecPass passes[DEC_MAX_PASSES];
     __shared__ int np;
+    __shared__ float tacc[DEC_TIMING_SLOTS];
 
     const int tid = threadIdx.x;
     if (tid == 0) np = p.npasses[blockIdx.x];
+    if (tid < DEC_TIMING_SLOTS) tacc[tid] = 0.f;
     {
         const int* src = reinterpret_cast<const int*>(p.passes + (size_t)blockIdx.x * DEC_MAX_PASSES);
         int* dst = reinterpret_cast<int*>(passes);
         for (int i = tid; i < (int)(sizeof(DecPass) * DEC_MAX_PASSES / 4); i += MV_THREADS) dst[i] = src[i];
         const float4* wsrc = reinterpret_cast<const float4*>(p.wimg + (size_t)blockIdx.x * p.wimg_floats);
-        float4* wdst = reinterpret_cast<float4*>(wsm);
+        float4* wdst = reinterpret_cast<float4*>(sm.wsm);
         for (int i = tid; i < p.wimg_floats / 4; i += MV_THREADS) wdst[i] = __ldg(wsrc + i);
     }
     __syncthreads();
 
-    unsigned target = 0;
-    // pre-stage A(-1): Q, content query and prenet(BOS) from the initial state in S[0]
+    StageSync sync;
+    sync.counter = p.barrier; sync.target = 0; sync.waited = true;     // nothing to wait for before the prologue
+    sync.tacc = tacc; sync.tmark = 0; sync.slot0 = 0; sync.timing = false;
+    const unsigned n = gridDim.x;
+    const int njobs = p.B * p.nsplit;
+
+    // prologue A(-1): Q, content query and prenet(BOS) from the initial state in S[0]
     for (int j = 0; j < np; ++j)
-        if (passes[j].stage == ST_A) dec_dispatch(p, passes[j], wsm, red, gsm, -1, 0);
-    grid_barrier(p.barrier, target, gridDim.x);
+        if (passes[j].stage == ST_A) dec_dispatch(p, passes[j], sm, sync, -1, 0);
+    grid_arrive(p.barrier);
+    sync.target += n;
+    sync.timing = (p.timing != nullptr);
+    if (tid == 0) sync.tmark = clock64();
 
     for (int step = 0; step < p.steps; ++step) {
         const int parity_new = (step + 1) & 1;
-        // ---- B: prenet layer 2 + attention ----
-        for (int j = 0; j < np; ++j)
-            if (passes[j].stage == ST_B) dec_dispatch(p, passes[j], wsm, red, gsm, step, parity_new);
-        for (int b = blockIdx.x; b < p.B; b += gridDim.x) dec_attend_clip(p, b, step, qs, sc, cqs, csc);
-        grid_barrier(p.barrier, target, gridDim.x);
-        // ---- C, D, E, A ----
 #pragma unroll 1
-        for (int st = ST_C; st <= ST_E + 1; ++st) {
+        for (int st = ST_B; st <= ST_E + 1; ++st) {
             const int stage = (st == ST_E + 1) ? ST_A : st;
+            sync.waited = false;
+            sync.slot0 = 3 * (st - ST_B);
             for (int j = 0; j < np; ++j)
-                if (passes[j].stage == stage) dec_dispatch(p, passes[j], wsm, red, gsm, step, parity_new);
-            grid_barrier(p.barrier, target, gridDim.x);
+                if (passes[j].stage == stage) dec_dispatch(p, passes[j], sm, sync, step, parity_new);
+            if (stage == ST_B) {
+                for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
+                    sync.wait();
+                    dec_attend(p, sm, job / p.nsplit, job % p.nsplit, step);
+                }
+            }
+            sync.wait();                 // barriers must complete in order even for CTAs idle in this stage
+            sync.lap(sync.slot0 + 2);
+            grid_arrive(p.barrier);
+            sync.target += n;
         }
     }
+    __syncthreads();
+    if (p.timing && tid < DEC_TIMING_SLOTS) p.timing[blockIdx.x * DEC_TIMING_SLOTS + tid] = tacc[tid];
 }
 
 }  // namespace l2s

@@ -42,6 +42,26 @@ inline void pack_conv1d(const Context& c, const std::string& conv, const std::st
     }
 }
 
+// Tensor-core (3xTF32) operand form of a [N][taps*Kc] weight: every tap padded to Kcp = roundup(Kc,32)
+// (so a 32-wide K chunk never straddles taps), split into w_hi (low 13 mantissa bits cleared) and
+// w_lo = w - w_hi (exact).  Uploaded as name.hi / name.lo; meta name.kcp.
+inline void upload_tc(Context& c, const std::string& name, const std::vector<float>& w, int N, int taps, int Kc) {
+    const int Kcp = round_up(Kc, 32);
+    std::vector<float> hi((size_t)N * taps * Kcp, 0.f), lo((size_t)N * taps * Kcp, 0.f);
+    for (int n = 0; n < N; ++n)
+        for (int t = 0; t < taps; ++t)
+            for (int k = 0; k < Kc; ++k) {
+                const float v = w[((size_t)n * taps + t) * Kc + k];
+                uint32_t bits; std::memcpy(&bits, &v, 4);
+                bits &= 0xFFFFE000u;
+                float h; std::memcpy(&h, &bits, 4);
+                hi[((size_t)n * taps + t) * Kcp + k] = h;
+                lo[((size_t)n * taps + t) * Kcp + k] = v - h;
+            }
+    c.upload(name + ".hi", hi); c.upload(name + ".lo", lo);
+    c.meta[name + ".kcp"] = Kcp;
+}
+
 // ------------------------------------------------------------------------------------------------
 // video frontend
 // ------------------------------------------------------------------------------------------------
@@ -193,11 +213,13 @@ inline void pack_speaker(Context& c) {
 // decoder: pre-loop, postnet, decode-step program
 // ------------------------------------------------------------------------------------------------
 struct PassBuild {
-    int stage, R, K0, K1, src0, src1;
-    struct Row { int op, idx; float bias, aux, aux2; const float* w0; const float* w1; };
+    int stage, R;
+    int Ke, src_e, wcol_e, Kl, src_l, wcol_l;
+    struct Row { int op, idx; float bias, aux, aux2; std::vector<std::pair<const float*, int>> w; };
     std::vector<Row> rows;
-    double cost() const { return (double)R * (K0 + K1); }
-    size_t floats() const { return (size_t)R * (K0 + K1); }
+    int ldw() const { return Ke + Kl; }
+    double cost() const { return (double)R * (Ke + Kl); }
+    size_t floats() const { return (size_t)R * (Ke + Kl); }
 };
 
 inline void pack_decode_program(Context& c) {
@@ -234,6 +256,25 @@ inline void pack_decode_program(Context& c) {
     std::vector<float> b1 = vadd(c.W(p + "decoder_rnn.bias_ih_l1").f, c.W(p + "decoder_rnn.bias_hh_l1").f);
     const auto& Wih0 = c.W(p + "decoder_rnn.weight_ih_l0").f; const auto& Whh0 = c.W(p + "decoder_rnn.weight_hh_l0").f;
     const auto& Wih1 = c.W(p + "decoder_rnn.weight_ih_l1").f; const auto& Whh1 = c.W(p + "decoder_rnn.weight_hh_l1").f;
+    // attention_proj folded into LSTM-0 (linear o linear): the LSTM input is cat([cv, p2 + W_ap ctx + b_ap]), so
+    // W_ih0[:,256:] (p2 + W_ap ctx + b_ap) = W_ih0b p2 + (W_ih0b W_ap) ctx + W_ih0b b_ap.
+    std::vector<float> Wx((size_t)2048 * 512, 0.f), b0x(2048, 0.f);
+    {
+        std::vector<double> acc(512);
+        for (int row = 0; row < 2048; ++row) {
+            std::fill(acc.begin(), acc.end(), 0.0);
+            double bb = b0[row];
+            const float* wb = Wih0.data() + (size_t)row * 512 + 256;
+            for (int m = 0; m < 256; ++m) {
+                const double w = wb[m];
+                const float* ar = Wap.data() + (size_t)m * 512;
+                for (int k = 0; k < 512; ++k) acc[k] += w * ar[k];
+                bb += w * bap[m];
+            }
+            for (int k = 0; k < 512; ++k) Wx[(size_t)row * 512 + k] = (float)acc[k];
+            b0x[row] = (float)bb;
+        }
+    }
 
     std::vector<std::vector<PassBuild>> per_cta(nC);
     std::vector<std::vector<double>> load(nC, std::vector<double>(ST_COUNT, 0.0));
@@ -247,17 +288,23 @@ inline void pack_decode_program(Context& c) {
             for (int done = 0; done < n; done += 4) {
                 int nu = std::min(4, n - done), u0 = u + done;
                 for (int layer = 0; layer < 2; ++layer) {
-                    PassBuild pb{layer == 0 ? ST_D : ST_E, 16, 512, 512, layer == 0 ? SRC_XD : SRC_H0NEW,
-                                 layer == 0 ? SRC_H0OLD : SRC_H1OLD, {}};
+                    PassBuild pb;
+                    pb.R = 16;
+                    if (layer == 0) { pb.stage = ST_D; pb.Kl = 1024; pb.src_l = SRC_XD; pb.wcol_l = 0; pb.Ke = 512; pb.src_e = SRC_H0OLD; pb.wcol_e = 1024; }
+                    else            { pb.stage = ST_E; pb.Kl = 512;  pb.src_l = SRC_H0NEW; pb.wcol_l = 0; pb.Ke = 512; pb.src_e = SRC_H1OLD; pb.wcol_e = 512; }
                     for (int ul = 0; ul < 4; ++ul)
                         for (int g = 0; g < 4; ++g) {
-                            PassBuild::Row r{layer == 0 ? OP_GATE0 : OP_GATE1, -1, 0.f, 0.f, 0.f, nullptr, nullptr};
+                            PassBuild::Row r{layer == 0 ? OP_GATE0 : OP_GATE1, -1, 0.f, 0.f, 0.f, {}};
                             if (ul < nu) {
-                                int row = g * 512 + u0 + ul;
+                                const int row = g * 512 + u0 + ul;
                                 r.idx = u0 + ul;
-                                r.bias = (layer == 0 ? b0 : b1)[row];
-                                r.w0 = (layer == 0 ? Wih0 : Wih1).data() + (size_t)row * 512;
-                                r.w1 = (layer == 0 ? Whh0 : Whh1).data() + (size_t)row * 512;
+                                if (layer == 0) {
+                                    r.bias = b0x[row];
+                                    r.w = {{Wih0.data() + (size_t)row * 512, 512}, {Wx.data() + (size_t)row * 512, 512}, {Whh0.data() + (size_t)row * 512, 512}};
+                                } else {
+                                    r.bias = b1[row];
+                                    r.w = {{Wih1.data() + (size_t)row * 512, 512}, {Whh1.data() + (size_t)row * 512, 512}};
+                                }
                             }
                             pb.rows.push_back(r);
                         }
@@ -268,14 +315,15 @@ inline void pack_decode_program(Context& c) {
             u += n;
         }
     }
-    // ---- the other rows, grouped into passes of RA rows ------------------------------------------
+    // ---- the other rows, grouped into passes of R rows -------------------------------------------
     std::vector<PassBuild> free_passes;
-    auto add_rows = [&](int stage, int R, int K0, int src0, std::vector<PassBuild::Row>& rows) {
+    auto add_rows = [&](int stage, int R, int Ke, int src_e, int Kl, int src_l, std::vector<PassBuild::Row>& rows) {
         for (size_t i = 0; i < rows.size(); i += R) {
-            PassBuild pb{stage, R, K0, 0, src0, SRC_NONE, {}};
+            PassBuild pb;
+            pb.stage = stage; pb.R = R; pb.Ke = Ke; pb.src_e = src_e; pb.wcol_e = 0; pb.Kl = Kl; pb.src_l = src_l; pb.wcol_l = Ke;
             for (int j = 0; j < R; ++j) {
                 if (i + j < rows.size()) pb.rows.push_back(rows[i + j]);
-                else pb.rows.push_back({OP_NONE, 0, 0.f, 0.f, 0.f, nullptr, nullptr});
+                else pb.rows.push_back({OP_NONE, 0, 0.f, 0.f, 0.f, {}});
             }
             free_passes.push_back(pb);
         }
@@ -283,27 +331,24 @@ inline void pack_decode_program(Context& c) {
     const int RA = 8;
     {
         std::vector<PassBuild::Row> rows;
-        for (int j = 0; j < 512; ++j) rows.push_back({OP_Q, j, bq[j], psq[j], 0.f, Wq.data() + (size_t)j * 1024, nullptr});
-        add_rows(ST_A, RA, 1024, SRC_HNEW, rows);
+        for (int j = 0; j < 512; ++j) rows.push_back({OP_Q, j, bq[j], psq[j], 0.f, {{Wq.data() + (size_t)j * 1024, 1024}}});
+        add_rows(ST_A, RA, 512, SRC_H0NEW, 512, SRC_H1NEW, rows);
         rows.clear();
-        for (int j = 0; j < 256; ++j) rows.push_back({OP_CQ, j, bcq[j], 0.f, 0.f, Wcq.data() + (size_t)j * 1024, nullptr});
-        add_rows(ST_A, RA, 1024, SRC_C, rows);
+        for (int j = 0; j < 256; ++j) rows.push_back({OP_CQ, j, bcq[j], 0.f, 0.f, {{Wcq.data() + (size_t)j * 1024, 1024}}});
+        add_rows(ST_A, RA, 512, SRC_C0, 512, SRC_C1, rows);
         rows.clear();
-        for (int j = 0; j < 80; ++j) rows.push_back({OP_FC, j, bfc[j], 0.f, 0.f, Wfc.data() + (size_t)j * 512, nullptr});
-        for (int j = 0; j < 256; ++j) rows.push_back({OP_P1, j, bpf[j], ps1[j], p1bos[j], Wpf.data() + (size_t)j * 512, nullptr});
-        rows.push_back({OP_STOP, 0, bst[0], 0.f, 0.f, Wst.data(), nullptr});
-        add_rows(ST_A, RA, 512, SRC_H1NEW, rows);
+        for (int j = 0; j < 80; ++j) rows.push_back({OP_FC, j, bfc[j], 0.f, 0.f, {{Wfc.data() + (size_t)j * 512, 512}}});
+        for (int j = 0; j < 256; ++j) rows.push_back({OP_P1, j, bpf[j], ps1[j], p1bos[j], {{Wpf.data() + (size_t)j * 512, 512}}});
+        rows.push_back({OP_STOP, 0, bst[0], 0.f, 0.f, {{Wst.data(), 512}}});
+        add_rows(ST_A, RA, 0, SRC_NONE, 512, SRC_H1NEW, rows);
         rows.clear();
-        for (int j = 0; j < 256; ++j) rows.push_back({OP_X2, j, bap[j], 0.f, 0.f, Wap.data() + (size_t)j * 512, nullptr});
-        add_rows(ST_C, RA, 512, SRC_CTX, rows);
-        rows.clear();
-        for (int j = 0; j < 256; ++j) rows.push_back({OP_P2, j, bp2[j], ps2[j], 0.f, Wp2.data() + (size_t)j * 256, nullptr});
-        add_rows(ST_B, RA, 256, SRC_P1, rows);
+        for (int j = 0; j < 256; ++j) rows.push_back({OP_P2, j, bp2[j], ps2[j], 0.f, {{Wp2.data() + (size_t)j * 256, 256}}});
+        add_rows(ST_B, 16, 0, SRC_NONE, 256, SRC_P1, rows);
     }
-    // attention runs on the low-numbered CTAs in stage B: bias p2 rows away from them
-    for (int cta = 0; cta < nC; ++cta) load[cta][ST_B] += (cta < 64 ? 4096.0 : 0.0) + (nC - 1 - cta) * 1e-3;
-    const size_t scratch_bytes = (size_t)(MV_WARPS * 16 * MV_CLIPS + 16 * MV_CLIPS + 512 + 320 + 256 + 32) * 4;
-    const size_t static_bytes = sizeof(DecPass) * DEC_MAX_PASSES + 64;
+    // attention jobs run on the low-numbered CTAs in stage B: bias prenet-2 rows towards the high-numbered ones
+    for (int cta = 0; cta < nC; ++cta) load[cta][ST_B] += (double)(nC - 1 - cta);
+    const size_t scratch_bytes = (size_t)(MV_WARPS * DEC_RED_ROWS * MV_CLIPS + 16 * MV_CLIPS + 512 + 320 + 256 + 32) * 4;
+    const size_t static_bytes = sizeof(DecPass) * DEC_MAX_PASSES + 256;
     const size_t cap_floats = ((size_t)c.max_smem_optin - scratch_bytes - static_bytes) / 4;
     std::stable_sort(free_passes.begin(), free_passes.end(), [](const PassBuild& a, const PassBuild& b) { return a.cost() > b.cost(); });
     for (auto& pb : free_passes) {
@@ -327,19 +372,19 @@ inline void pack_decode_program(Context& c) {
     std::vector<int> npasses(nC, 0);
     for (int cta = 0; cta < nC; ++cta) {
         size_t off = 0;
-        if ((int)per_cta[cta].size() > DEC_MAX_PASSES) throw L2sError(1, "too many decode passes per CTA");
         for (size_t j = 0; j < per_cta[cta].size(); ++j) {
             const PassBuild& pb = per_cta[cta][j];
             DecPass& d = passes[(size_t)cta * DEC_MAX_PASSES + j];
-            d.stage = pb.stage; d.R = pb.R; d.K0 = pb.K0; d.K1 = pb.K1; d.src0 = pb.src0; d.src1 = pb.src1; d.w_off = (int)off;
-            const int K = pb.K0 + pb.K1;
+            d.stage = pb.stage; d.R = pb.R; d.Ke = pb.Ke; d.src_e = pb.src_e; d.wcol_e = pb.wcol_e;
+            d.Kl = pb.Kl; d.src_l = pb.src_l; d.wcol_l = pb.wcol_l; d.ldw = pb.ldw(); d.w_off = (int)off;
             for (int r = 0; r < 16; ++r) {
                 if (r < pb.R) {
                     const auto& row = pb.rows[r];
                     d.op[r] = row.op; d.idx[r] = row.idx; d.bias[r] = row.bias; d.aux[r] = row.aux; d.aux2[r] = row.aux2;
-                    float* dst = wimg.data() + (size_t)cta * wimg_floats + off + (size_t)r * K;
-                    if (row.w0) std::copy(row.w0, row.w0 + pb.K0, dst);
-                    if (row.w1) std::copy(row.w1, row.w1 + pb.K1, dst + pb.K0);
+                    float* dst = wimg.data() + (size_t)cta * wimg_floats + off + (size_t)r * pb.ldw();
+                    int col = 0;
+                    for (auto& piece : row.w) { std::copy(piece.first, piece.first + piece.second, dst + col); col += piece.second; }
+                    if (col != 0 && col != pb.ldw()) throw L2sError(1, "internal: decode row width mismatch");
                 } else { d.op[r] = OP_NONE; d.idx[r] = -1; }
             }
             off += pb.floats();
@@ -356,6 +401,7 @@ inline void pack_decode_program(Context& c) {
     c.upload("d.stop.w2", wst2);
 }
 
+
 inline void pack_decoder(Context& c) {
     const std::string p = "decoder.";
     std::vector<float> w, b;
@@ -364,6 +410,7 @@ inline void pack_decoder(Context& c) {
         const std::string s = std::to_string(i);
         pack_conv1d(c, p + "postnet.convolutions." + s + ".0.conv", p + "postnet.convolutions." + s + ".1", w, b);
         c.upload("d.post" + s + ".w", w); c.upload("d.post" + s + ".b", b);
+        upload_tc(c, "d.post" + s, w, (int)b.size(), 5, (int)(w.size() / b.size() / 5));
         if (i < 4) c.upload("d.post" + s + ".psw", c.W(p + "postnet.sin_activation." + s + ".w").f);
     }
     // encoder pre-loop linears

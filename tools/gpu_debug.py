@@ -74,3 +74,19 @@ def timing():
         print(f"  B={B}: speaker {tm(lambda: be.speaker_fwd(wav, True)):.3f} ms, video {tm(lambda: be.video_fwd(video)):.3f} ms, "
               f"decoder {tm(lambda: be.decoder_infer(visual, spk_e, g)):.3f} ms, full {tm(lambda: be.infer(video, wav, g)):.3f} ms", flush=True)
 step("timing", timing)
+
+def stage_timing():
+    be.set_profiling(True)
+    for B in (1, 32):
+        visual, face = synth.visual_features(B, 29)
+        g = synth.gumbel(B, 29)
+        be.decoder_infer(visual.cuda(), face[:, 0].cuda(), g.cuda())
+        torch.cuda.synchronize()
+        tm = be.debug_read("dec.timing", (148, 12)) / 1965.0 / 300.0     # us per step
+        names = ["B early", "B wait", "B late", "D early", "D wait", "D late", "E early", "E wait", "E late", "A early", "A wait", "A late"]
+        print(f"  B={B}: decode_loop {be.span_ms('decode_loop'):.3f} ms; per-step us (mean / max over CTAs):")
+        for i, n in enumerate(names):
+            print(f"     {n:7s} {tm[:, i].mean():7.3f} {tm[:, i].max():7.3f}   cta0={tm[0, i]:.3f} cta147={tm[147, i]:.3f}")
+        print("     sum(mean) =", float(tm.mean(0).sum()))
+    be.set_profiling(False)
+step("stage_timing", stage_timing)
