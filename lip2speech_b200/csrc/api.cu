@@ -43,12 +43,65 @@ static void run_gemm(Context& c, GemmParams p, cudaStream_t s, const char* what)
     c.launches++;
 }
 
-// plain linear: C[M,N] = act(A[M,K] W[N,K]^T + b)
-static void linear(Context& c, const float* A, int lda, const float* W, const float* b, float* C, int ldc, int M, int N, int K,
+static void run_tc(Context& c, const TcOperands& o, const TcParams& p, cudaStream_t s, const char* what, bool gather = false);
+static inline TcParams tc_defaults();
+
+// plain linear: C[M,N] = act(A[M,K] W[N,K]^T + b).  `wname` selects the packed weight: wname.hi/.lo (tcgen05 3xTF32
+// path, needs 16-byte aligned rows for TMA) or wname.w (exact-fp32 SIMT path).
+static void linear(Context& c, const float* A, int lda, const std::string& wname, const float* b, float* C, int ldc, int M, int N, int K,
                    int act, const float* act_w, cudaStream_t s, const char* what) {
+    if (c.use_tc && (lda % 4) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0) {
+        const int kcp = (int)c.meta.at(wname + ".kcp");
+        TcOperands o{A, K, M, lda, c.dev(wname + ".hi"), c.dev(wname + ".lo"), kcp};
+        TcParams p = tc_defaults();
+        p.M = M; p.N = N; p.Kc = K; p.Kcp = kcp; p.Lp_in = M; p.L = M; p.Lp_out = M;
+        p.C = C; p.ldc = ldc; p.bias = b; p.act = act; p.act_w = act_w;
+        run_tc(c, o, p, s, what);
+        return;
+    }
     GemmParams p = gemm_defaults();
-    p.A = A; p.lda = lda; p.W = W; p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.Kc = K; p.bias = b; p.act = act; p.act_w = act_w;
+    p.A = A; p.lda = lda; p.W = c.dev(wname + ".w"); p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.Kc = K; p.bias = b; p.act = act; p.act_w = act_w;
     run_gemm(c, p, s, what);
+}
+
+// Dense (1-tap) GEMM described SIMT-style (GemmParams with W unset): tcgen05 path when TMA alignment allows, else SIMT.
+static void gemm_auto(Context& c, GemmParams g, const std::string& wname, cudaStream_t s, const char* what) {
+    if (g.L_out == 0) { g.L_out = g.M; g.L_in = g.M; }
+    if (c.use_tc && g.taps == 1 && g.stride == 1 && !g.stem && (g.lda % 4) == 0 && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0) {
+        const int kcp = (int)c.meta.at(wname + ".kcp");
+        TcOperands o{g.A, g.Kc, g.M, g.lda, c.dev(wname + ".hi"), c.dev(wname + ".lo"), kcp};
+        TcParams p = tc_defaults();
+        p.M = g.M; p.N = g.N; p.Kc = g.Kc; p.Kcp = kcp; p.Lp_in = g.L_out; p.L = g.L_out; p.Lp_out = g.L_out;
+        p.C = g.C; p.ldc = g.ldc; p.bias = g.bias; p.act = g.act; p.act_w = g.act_w; p.addrow = g.addrow;
+        p.addpos = g.addpos; p.ldpos = g.ldpos; p.resid = g.resid; p.ldr = g.ldr;
+        p.cstride = g.cstride; p.coff = g.coff; p.chalf = g.chalf; p.chp = g.chp; p.transposed = g.transposed;
+        run_tc(c, o, p, s, what);
+        return;
+    }
+    g.W = c.dev(wname + ".w");
+    run_gemm(c, g, s, what);
+}
+
+// video [B,3,T,H,W] NCDHW -> space-to-depth, zero-padded rows [B][T+4][H/2+3][W/2+3][12]; channel = (ph*2+pw)*3 + ci.
+__global__ void s2d_pad_kernel(const float* __restrict__ v, float* __restrict__ xs, float* __restrict__ xl, int B, int T, int H, int W, int Tp, int Hpp, int Wpp) {
+    const int Ho = H / 2, Wo = W / 2;
+    const size_t total = (size_t)B * 3 * T * Ho * Wo;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int wq = i % Wo; size_t r = i / Wo;
+        int hq = r % Ho; r /= Ho;
+        int t = r % T; r /= T;
+        int ci = r % 3; int b = r / 3;
+        const float* src = v + ((((size_t)b * 3 + ci) * T + t) * H + 2 * hq) * W + 2 * wq;
+        const float2 top = *reinterpret_cast<const float2*>(src);
+        const float2 bot = *reinterpret_cast<const float2*>(src + W);
+        const size_t o = ((((size_t)b * Tp + t + 2) * Hpp + hq + 2) * Wpp + wq + 2) * 12 + ci;
+        const float vals[4] = {top.x, top.y, bot.x, bot.y};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {                      // 3xTF32 operand split done once here: hi = top 19 bits, lo = exact remainder
+            const float h = __uint_as_float(__float_as_uint(vals[j]) & 0xFFFFE000u);
+            xs[o + 3 * j] = h; xl[o + 3 * j] = vals[j] - h;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -61,7 +114,36 @@ static void video_forward(Context& c, const float* video, int B, int T, int H, i
     const int Ho = H / 2, Wo = W / 2;                 // Conv3d stride (1,2,2), pad 3, k 7
     const int Hp = (Ho - 1) / 2 + 1, Wp = (Wo - 1) / 2 + 1;   // MaxPool 3x3 s2 p1
     float* stem = c.fbuf("ws.v.stem", (size_t)N * Ho * Wo * 24);
-    {
+    if (c.use_tc) {
+        // space-to-depth + zero padding, then a 20-tap implicit GEMM (K = 4 w-taps x 12 channels per tap) on tcgen05
+        const int Tp = T + 4, Hpp = Ho + 3, Wpp = Wo + 3;
+        const size_t rows = (size_t)B * Tp * Hpp * Wpp;
+        // zero slack before/after so the tap-shifted gathers of the first/last tiles never leave the allocation
+        const size_t slack_rows = (size_t)2 * Hpp * Wpp + 2 * Wpp + 2 + TC_BM + 8;
+        const size_t plane = (rows + 2 * slack_rows) * 12;
+        float* xs0 = c.fbuf("ws.v.s2d", 2 * plane);          // [hi | lo]
+        float* xs = xs0 + slack_rows * 12;
+        float* xl = xs + plane;
+        const int64_t sig = ((int64_t)B << 40) ^ ((int64_t)T << 24) ^ ((int64_t)H << 12) ^ W;
+        if (c.meta["ws.v.s2d.layout"] != sig) {
+            L2S_CUDA(cudaMemsetAsync(xs0, 0, 2 * plane * sizeof(float), s));
+            c.meta["ws.v.s2d.layout"] = sig;
+        }
+        s2d_pad_kernel<<<ew_grid((size_t)B * T * Ho * Wo * 3), 256, 0, s>>>(video, xs, xl, B, T, H, W, Tp, Hpp, Wpp);
+        check_launch(c, "space-to-depth");
+        const int kcp = (int)c.meta.at("v.stem.tc.kcp");
+        TcOperands o{xs, 48, (int)rows, 12, c.dev("v.stem.tc.hi"), c.dev("v.stem.tc.lo"), 20 * kcp};
+        TcParams p = tc_defaults();
+        p.M = (int)rows; p.N = 24; p.Kc = 48; p.Kcp = kcp; p.taps = 20; p.C = stem; p.ldc = 24;
+        p.bias = c.dev("v.stem.b"); p.act = ACT_PRELU; p.act_w = c.dev("v.stem.prelu");
+        p.use_shift_table = 1;
+        for (int kt = 0; kt < 5; ++kt)
+            for (int jh = 0; jh < 4; ++jh) p.tap_shift[kt * 4 + jh] = (kt - 2) * Hpp * Wpp + (jh - 2) * Wpp - 2;
+        p.ga_unchecked = 1; p.ga_Alo = xl;
+        p.stem = 1; p.sT = T; p.sTp = Tp; p.sHp = Hpp; p.sWp = Wpp; p.sHo = Ho; p.sWo = Wo;
+        p.Lp_in = 1; p.L = 1; p.Lp_out = 1;
+        run_tc(c, o, p, s, "stem conv3d", /*gather=*/true);
+    } else {
         GemmParams p = gemm_defaults();
         p.stem = 1; p.A = video; p.W = c.dev("v.stem.w"); p.C = stem; p.ldc = 24;
         p.M = N * Ho * Wo; p.N = 24; p.Kc = 735; p.taps = 1; p.L_out = p.M; p.L_in = p.M;
@@ -96,42 +178,42 @@ static void video_forward(Context& c, const float* video, int B, int T, int H, i
                                                                           N, h, w, cin_phys, 2, ho, wo);
             check_launch(c, "b1 dw");
             GemmParams p = gemm_defaults();
-            p.A = t1; p.lda = cin_phys; p.W = c.dev(n + "b1pw.w"); p.bias = c.dev(n + "b1pw.b"); p.act = ACT_RELU;
+            p.A = t1; p.lda = cin_phys; p.bias = c.dev(n + "b1pw.b"); p.act = ACT_RELU;
             p.C = y; p.ldc = cph; p.M = (int)rout; p.N = half; p.Kc = cin_phys; p.cstride = 2; p.coff = 0; p.chalf = half; p.chp = hp;
-            run_gemm(c, p, s, "b1 pw");
+            gemm_auto(c, p, n + "b1pw", s, "b1 pw");
             // branch2: 1x1 (full res) -> dw s2 -> 1x1 -> logical channel 2j+1
             p = gemm_defaults();
-            p.A = x; p.lda = cin_phys; p.W = c.dev(n + "b2pw1.w"); p.bias = c.dev(n + "b2pw1.b"); p.act = ACT_RELU;
+            p.A = x; p.lda = cin_phys; p.bias = c.dev(n + "b2pw1.b"); p.act = ACT_RELU;
             p.C = t2; p.ldc = hp; p.M = (int)rin; p.N = half; p.Kc = cin_phys;
-            run_gemm(c, p, s, "b2 pw1");
+            gemm_auto(c, p, n + "b2pw1", s, "b2 pw1");
             dwconv3x3_kernel<<<ew_grid(rout * (hp / 4)), 256, 0, s>>>(t2, hp, 0, t1, hp, 0, c.dev(n + "b2dw.w"), c.dev(n + "b2dw.b"), N, h, w, hp, 2, ho, wo);
             check_launch(c, "b2 dw");
             p = gemm_defaults();
-            p.A = t1; p.lda = hp; p.W = c.dev(n + "b2pw2.w"); p.bias = c.dev(n + "b2pw2.b"); p.act = ACT_RELU;
+            p.A = t1; p.lda = hp; p.bias = c.dev(n + "b2pw2.b"); p.act = ACT_RELU;
             p.C = y; p.ldc = cph; p.M = (int)rout; p.N = half; p.Kc = hp; p.cstride = 2; p.coff = 1; p.chalf = half; p.chp = hp;
-            run_gemm(c, p, s, "b2 pw2");
+            gemm_auto(c, p, n + "b2pw2", s, "b2 pw2");
             h = ho; w = wo;
         } else {
             const size_t rows = (size_t)N * h * w;
             shuffle_passthrough_kernel<<<ew_grid(rows * half), 256, 0, s>>>(x, y, rows, cph, half, hp);
             check_launch(c, "passthrough");
             GemmParams p = gemm_defaults();
-            p.A = x + hp; p.lda = cph; p.W = c.dev(n + "b2pw1.w"); p.bias = c.dev(n + "b2pw1.b"); p.act = ACT_RELU;
+            p.A = x + hp; p.lda = cph; p.bias = c.dev(n + "b2pw1.b"); p.act = ACT_RELU;
             p.C = t2; p.ldc = hp; p.M = (int)rows; p.N = half; p.Kc = hp;
-            run_gemm(c, p, s, "b2 pw1");
+            gemm_auto(c, p, n + "b2pw1", s, "b2 pw1");
             dwconv3x3_kernel<<<ew_grid(rows * (hp / 4)), 256, 0, s>>>(t2, hp, 0, t1, hp, 0, c.dev(n + "b2dw.w"), c.dev(n + "b2dw.b"), N, h, w, hp, 1, h, w);
             check_launch(c, "b2 dw");
             p = gemm_defaults();
-            p.A = t1; p.lda = hp; p.W = c.dev(n + "b2pw2.w"); p.bias = c.dev(n + "b2pw2.b"); p.act = ACT_RELU;
+            p.A = t1; p.lda = hp; p.bias = c.dev(n + "b2pw2.b"); p.act = ACT_RELU;
             p.C = y; p.ldc = cph; p.M = (int)rows; p.N = half; p.Kc = hp; p.cstride = 2; p.coff = 1; p.chalf = half; p.chp = hp;
-            run_gemm(c, p, s, "b2 pw2");
+            gemm_auto(c, p, n + "b2pw2", s, "b2 pw2");
         }
         std::swap(x, y);
     }
     if (h != 3 || w != 3) throw L2sError(L2S_ERR_INVALID, "video_fwd: trunk output must be 3x3 (H,W in {88,96}) for AvgPool2d(3)");
     const int Kl = (int)c.meta.at("v.last.k"), Nl = (int)c.meta.at("v.last.n");
     float* last = c.fbuf("ws.v.last", (size_t)N * 9 * Nl);
-    linear(c, x, Kl, c.dev("v.last.w"), c.dev("v.last.b"), last, Nl, N * 9, Nl, Kl, ACT_RELU, nullptr, s, "conv_last");
+    linear(c, x, Kl, "v.last", c.dev("v.last.b"), last, Nl, N * 9, Nl, Kl, ACT_RELU, nullptr, s, "conv_last");
     avgpool_l2norm_kernel<<<N, 256, Nl * sizeof(float), s>>>(last, out_feat, 9, Nl);
     check_launch(c, "avgpool_l2norm");
 }
@@ -162,7 +244,7 @@ static void speaker_forward(Context& c, const float* wav, int B, int S, float* e
     melspec_kernel<<<B * F, 256, 0, s>>>(wav, c.dev("s.window"), c.dev("s.fb"), mel, S, F);
     check_launch(c, "melspec");
     float* xproj = c.fbuf("ws.s.xproj", (size_t)B * F * 4 * H);
-    linear(c, mel, 40, c.dev("s.wih0"), c.dev("s.b0"), xproj, 4 * H, B * F, 4 * H, 40, ACT_NONE, nullptr, s, "speaker xproj");
+    linear(c, mel, 40, "s.wih0", c.dev("s.b0"), xproj, 4 * H, B * F, 4 * H, 40, ACT_NONE, nullptr, s, "speaker xproj");
     const size_t plane = (size_t)H * Bpad;
     float* hbuf = c.fbuf("ws.s.h", 2 * L * plane);
     float* cbuf = c.fbuf("ws.s.c", L * plane);
@@ -183,8 +265,8 @@ static void speaker_forward(Context& c, const float* wav, int B, int S, float* e
 // ------------------------------------------------------------------------------------------------
 // postnet (time-major rows [B*L][C])
 // ------------------------------------------------------------------------------------------------
-static void run_tc(Context& c, const TcOperands& o, const TcParams& p, cudaStream_t s, const char* what) {
-    const char* err = launch_tc_gemm(o, p, s);
+static void run_tc(Context& c, const TcOperands& o, const TcParams& p, cudaStream_t s, const char* what, bool gather) {
+    const char* err = launch_tc_gemm(o, p, s, gather);
     if (err) throw L2sError(L2S_ERR_CUDA, std::string(what) + " (tcgen05 gemm): " + err);
     c.launches++;
 }
@@ -286,13 +368,13 @@ static void decoder_infer(Context& c, const float* visual, const float* spk, con
     // ---- encoder pre-loop (decoder.py:383-394) --------------------------------------------------
     c.span_begin("preloop", s);
     float* resid = c.fbuf("ws.d.resid", (size_t)M * 512);
-    linear(c, visual, 1024, c.dev("d.resid.w"), c.dev("d.resid.b"), resid, 512, M, 512, 1024, ACT_NONE, nullptr, s, "residual_bottleneck");
+    linear(c, visual, 1024, "d.resid", c.dev("d.resid.b"), resid, 512, M, 512, 1024, ACT_NONE, nullptr, s, "residual_bottleneck");
     float* encsite = c.fbuf("ws.d.encsite", (size_t)B * 512);
     float* attsite = c.fbuf("ws.d.attsite", (size_t)B * 512);
-    linear(c, spk, 256, c.dev("d.encsite.w"), c.dev("d.encsite.b"), encsite, 512, B, 512, 256, ACT_PSINE, c.dev("d.encsite.psw"), s, "encoder_site");
-    linear(c, spk, 256, c.dev("d.attsite.w"), c.dev("d.attsite.b"), attsite, 512, B, 512, 256, ACT_PSINE, c.dev("d.attsite.psw"), s, "attention_site");
+    linear(c, spk, 256, "d.encsite", c.dev("d.encsite.b"), encsite, 512, B, 512, 256, ACT_PSINE, c.dev("d.encsite.psw"), s, "encoder_site");
+    linear(c, spk, 256, "d.attsite", c.dev("d.attsite.b"), attsite, 512, B, 512, 256, ACT_PSINE, c.dev("d.attsite.psw"), s, "attention_site");
     float* xproj = c.fbuf("ws.d.xproj", (size_t)M * 4096);
-    linear(c, visual, 1024, c.dev("d.ernn.wih"), c.dev("d.ernn.b"), xproj, 4096, M, 4096, 1024, ACT_NONE, nullptr, s, "encoder_rnn xproj");
+    linear(c, visual, 1024, "d.ernn.wih", c.dev("d.ernn.b"), xproj, 4096, M, 4096, 1024, ACT_NONE, nullptr, s, "encoder_rnn xproj");
     const size_t plane = (size_t)512 * Bpad;
     float* eh = c.fbuf("ws.d.eh", 2 * 2 * plane);      // [parity][dir][512][Bpad]
     float* ec = c.fbuf("ws.d.ec", 2 * plane);
@@ -318,13 +400,13 @@ static void decoder_infer(Context& c, const float* visual, const float* spk, con
     fm_to_rows_kernel<<<ew_grid((size_t)1024 * B), 256, 0, s>>>(ec, Bpad, ccat, 1024, 0, 1024, B);
     check_launch(c, "c_n -> rows");
     float* enc_cell = c.fbuf("ws.d.enc_cell", (size_t)B * 512);
-    linear(c, ccat, 1024, c.dev("d.ec.w"), c.dev("d.ec.b"), enc_cell, 512, B, 512, 1024, ACT_NONE, nullptr, s, "E_C");
+    linear(c, ccat, 1024, "d.ec", c.dev("d.ec.b"), enc_cell, 512, B, 512, 1024, ACT_NONE, nullptr, s, "E_C");
     float* enc = c.fbuf("ws.d.enc", (size_t)M * 512);
     {
         GemmParams p = gemm_defaults();
-        p.A = rnn_out; p.lda = 1024; p.W = c.dev("d.encproj.w"); p.bias = c.dev("d.encproj.b"); p.C = enc; p.ldc = 512;
+        p.A = rnn_out; p.lda = 1024; p.bias = c.dev("d.encproj.b"); p.C = enc; p.ldc = 512;
         p.M = M; p.N = 512; p.Kc = 1024; p.L_out = T; p.L_in = T; p.addrow = attsite; p.resid = resid; p.ldr = 512;
-        run_gemm(c, p, s, "encoder_proj");
+        gemm_auto(c, p, "d.encproj", s, "encoder_proj");
     }
     // ---- K / V (MultiHopConv + PSine + positions, decoder.py:396-399) -----------------------------
     float* cat = c.fbuf("ws.d.cat", (size_t)M * 2560);
@@ -332,19 +414,37 @@ static void decoder_infer(Context& c, const float* visual, const float* spk, con
     float* Vmem = c.fbuf("ws.d.V", (size_t)M * 512);
     L2S_CUDA(cudaMemcpy2DAsync(cat, 2560 * sizeof(float), enc, 512 * sizeof(float), 512 * sizeof(float), M, cudaMemcpyDeviceToDevice, s));
     const int mks[4] = {1, 3, 7, 11};
+    const int PM = 5, Tp = T + 2 * PM;                       // zero-padded per-sequence layout for the tap-shifted TMA boxes
+    float* encp = nullptr;
+    if (c.use_tc) {
+        encp = padded_buf(c, "ws.d.encp", B, Tp, 512, s);
+        pad_rows_kernel<<<ew_grid((size_t)M * 128), 256, 0, s>>>(enc, encp, B, T, Tp, PM, 128);
+        check_launch(c, "pad enc rows");
+    }
     for (int kv = 0; kv < 2; ++kv) {
         const std::string n = kv == 0 ? "d.K" : "d.V";
         for (int j = 0; j < 4; ++j) {
-            GemmParams p = gemm_defaults();
-            p.A = enc; p.lda = 512; p.W = c.dev(n + ".c" + std::to_string(j) + ".w"); p.bias = c.dev(n + ".c" + std::to_string(j) + ".b");
-            p.C = cat; p.ldc = 2560; p.coff = 512 * (j + 1); p.M = M; p.N = 512; p.Kc = 512; p.taps = mks[j]; p.pad = mks[j] / 2;
-            p.L_out = T; p.L_in = T; p.act = ACT_SILU;
-            run_gemm(c, p, s, "multihop conv");
+            const std::string wn = n + ".c" + std::to_string(j);
+            if (c.use_tc) {
+                const int kcp = (int)c.meta.at(wn + ".kcp");
+                TcOperands o{encp, 512, B * Tp, 512, c.dev(wn + ".hi"), c.dev(wn + ".lo"), mks[j] * kcp};
+                TcParams p = tc_defaults();
+                p.M = B * Tp; p.N = 512; p.Kc = 512; p.Kcp = kcp; p.taps = mks[j]; p.pad = mks[j] / 2;
+                p.Lp_in = Tp; p.P_in = PM; p.L = T; p.Lp_out = T; p.P_out = 0;
+                p.C = cat; p.ldc = 2560; p.coff = 512 * (j + 1); p.bias = c.dev(wn + ".b"); p.act = ACT_SILU;
+                run_tc(c, o, p, s, "multihop conv");
+            } else {
+                GemmParams p = gemm_defaults();
+                p.A = enc; p.lda = 512; p.W = c.dev(wn + ".w"); p.bias = c.dev(wn + ".b");
+                p.C = cat; p.ldc = 2560; p.coff = 512 * (j + 1); p.M = M; p.N = 512; p.Kc = 512; p.taps = mks[j]; p.pad = mks[j] / 2;
+                p.L_out = T; p.L_in = T; p.act = ACT_SILU;
+                run_gemm(c, p, s, "multihop conv");
+            }
         }
         GemmParams p = gemm_defaults();
-        p.A = cat; p.lda = 2560; p.W = c.dev(n + ".bn.w"); p.bias = c.dev(n + ".bn.b"); p.C = kv == 0 ? Kmem : Vmem; p.ldc = 512;
+        p.A = cat; p.lda = 2560; p.bias = c.dev(n + ".bn.b"); p.C = kv == 0 ? Kmem : Vmem; p.ldc = 512;
         p.M = M; p.N = 512; p.Kc = 2560; p.L_out = T; p.L_in = T; p.act = ACT_PSINE; p.act_w = c.dev(n + ".psw"); p.addpos = pos; p.ldpos = 512;
-        run_gemm(c, p, s, "multihop bottleneck");
+        gemm_auto(c, p, n + ".bn", s, "multihop bottleneck");
     }
     // ---- Content.encode (decoder.py:239-260) -----------------------------------------------------
     const int Mc = B * minT;
@@ -367,17 +467,17 @@ static void decoder_infer(Context& c, const float* visual, const float* spk, con
     float* ckey = c.fbuf("ws.d.ckey", (size_t)Mc * 256);
     float* cval = c.fbuf("ws.d.cval", (size_t)Mc * 256);
     float* clog = c.fbuf("ws.d.clog", (size_t)Mc * 501);
-    linear(c, ccat2, 2560, c.dev("d.cbn.w"), c.dev("d.cbn.b"), cw, 256, Mc, 256, 2560, ACT_NONE, nullptr, s, "content bottleneck");
-    linear(c, cw, 256, c.dev("d.ck0.w"), c.dev("d.ck0.b"), cu, 256, Mc, 256, 256, ACT_SILU, nullptr, s, "content K.0");
-    linear(c, cu, 256, c.dev("d.ck2.w"), c.dev("d.ck2.b"), ckey, 256, Mc, 256, 256, ACT_SILU, nullptr, s, "content K.2");
-    linear(c, cw, 256, c.dev("d.cloc0.w"), c.dev("d.cloc0.b"), cu, 256, Mc, 256, 256, ACT_SILU, nullptr, s, "location_fc.0");
-    linear(c, cu, 256, c.dev("d.cloc2.w"), c.dev("d.cloc2.b"), cv2, 256, Mc, 256, 256, ACT_SILU, nullptr, s, "location_fc.2");
-    linear(c, cv2, 256, c.dev("d.cloc4.w"), c.dev("d.cloc4.b"), clog, 501, Mc, 501, 256, ACT_SILU, nullptr, s, "location_fc.4");
+    linear(c, ccat2, 2560, "d.cbn", c.dev("d.cbn.b"), cw, 256, Mc, 256, 2560, ACT_NONE, nullptr, s, "content bottleneck");
+    linear(c, cw, 256, "d.ck0", c.dev("d.ck0.b"), cu, 256, Mc, 256, 256, ACT_SILU, nullptr, s, "content K.0");
+    linear(c, cu, 256, "d.ck2", c.dev("d.ck2.b"), ckey, 256, Mc, 256, 256, ACT_SILU, nullptr, s, "content K.2");
+    linear(c, cw, 256, "d.cloc0", c.dev("d.cloc0.b"), cu, 256, Mc, 256, 256, ACT_SILU, nullptr, s, "location_fc.0");
+    linear(c, cu, 256, "d.cloc2", c.dev("d.cloc2.b"), cv2, 256, Mc, 256, 256, ACT_SILU, nullptr, s, "location_fc.2");
+    linear(c, cv2, 256, "d.cloc4", c.dev("d.cloc4.b"), clog, 501, Mc, 501, 256, ACT_SILU, nullptr, s, "location_fc.4");
     gumbel_value_kernel<<<Mc, 256, 501 * sizeof(float), s>>>(clog, gumbel, 1.0f / 0.1f, c.dev("d.cemb"), cval, nullptr, 501);
     check_launch(c, "gumbel value");
     // ---- stop-token constant, initial state --------------------------------------------------------
     float* stopc = c.fbuf("ws.d.stopc", (size_t)B);
-    linear(c, enc_cell, 512, c.dev("d.stop.w2"), nullptr, stopc, 1, B, 1, 512, ACT_NONE, nullptr, s, "stop const");
+    linear(c, enc_cell, 512, "d.stop2", nullptr, stopc, 1, B, 1, 512, ACT_NONE, nullptr, s, "stop const");
     float* S = c.fbuf("ws.d.S", 2 * 2 * plane);
     float* Cst = c.fbuf("ws.d.Cst", 2 * plane);
     L2S_CUDA(cudaMemcpyAsync(S, hfinal, 2 * plane * sizeof(float), cudaMemcpyDeviceToDevice, s));

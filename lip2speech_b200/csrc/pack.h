@@ -78,6 +78,22 @@ inline void pack_video(Context& c) {
         const int K = 735;
         for (int o = 0; o < 24; ++o) for (int k = 0; k < K; ++k) w[(size_t)o * K + k] = W.f[(size_t)o * K + k] * scale[o];
         c.upload("v.stem.w", w); c.upload("v.stem.b", shift); c.upload("v.stem.prelu", c.W(p + "frontend3D.2.weight").f);
+        // tensor-core form: stride-2 7x7 -> stride-1 4x4 over the space-to-depth input (12 = 2x2 phases x 3 channels);
+        // tap = (kt, jh), K within a tap = jw*12 + (ph*2+pw)*3 + ci, original kh = 2*jh + ph - 1, kw = 2*jw + pw - 1.
+        std::vector<float> ws((size_t)24 * 20 * 48, 0.f);
+        for (int o = 0; o < 24; ++o)
+            for (int ci = 0; ci < 3; ++ci)
+                for (int kt = 0; kt < 5; ++kt)
+                    for (int jh = 0; jh < 4; ++jh)
+                        for (int ph = 0; ph < 2; ++ph)
+                            for (int jw = 0; jw < 4; ++jw)
+                                for (int pw = 0; pw < 2; ++pw) {
+                                    const int kh = 2 * jh + ph - 1, kw = 2 * jw + pw - 1;
+                                    if (kh < 0 || kw < 0) continue;
+                                    const float v = w[(size_t)o * K + ((ci * 5 + kt) * 7 + kh) * 7 + kw];
+                                    ws[((size_t)o * 20 + kt * 4 + jh) * 48 + jw * 12 + (ph * 2 + pw) * 3 + ci] = v;
+                                }
+        upload_tc(c, "v.stem.tc", ws, 24, 20, 48);
     }
     int blk = 0;
     int in_half = 0, in_hp = 0, cin = 24, cin_phys = 24;       // stem output: identity layout
@@ -101,6 +117,7 @@ inline void pack_video(Context& c) {
                     w[(size_t)o * K_phys + pi] = W.f[(size_t)o * ci + i] * scale[o];
                 }
             c.upload(name + ".w", w); c.upload(name + ".b", shift);
+            upload_tc(c, name, w, co, 1, K_phys);
         };
         auto pack_dw = [&](const std::string& conv, const std::string& bn, int C_phys, bool map_in, const std::string& name) {
             const HostTensor& W = c.W(conv + ".weight");            // [C][1][3][3]
@@ -135,6 +152,7 @@ inline void pack_video(Context& c) {
         for (int o = 0; o < co; ++o)
             for (int i = 0; i < ci; ++i) w[(size_t)o * cin_phys + phys_ch(i, in_half, in_hp)] = W.f[(size_t)o * ci + i] * scale[o];
         c.upload("v.last.w", w); c.upload("v.last.b", shift);
+        upload_tc(c, "v.last", w, co, 1, cin_phys);
         c.meta["v.last.k"] = cin_phys; c.meta["v.last.n"] = co;
     }
     c.meta["v.nblocks"] = blk;
@@ -196,7 +214,8 @@ inline void pack_speaker(Context& c) {
     const std::string p = "speaker_encoder.";
     c.upload("s.window", c.W(p + "mel_spec.spectrogram.window").f);
     c.upload("s.fb", c.W(p + "mel_spec.mel_scale.fb").f);
-    c.upload("s.wih0", c.W(p + "lstm.weight_ih_l0").f);
+    c.upload("s.wih0.w", c.W(p + "lstm.weight_ih_l0").f);
+    upload_tc(c, "s.wih0", c.W(p + "lstm.weight_ih_l0").f, 1024, 1, 40);
     c.upload("s.b0", vadd(c.W(p + "lstm.bias_ih_l0").f, c.W(p + "lstm.bias_hh_l0").f));
     c.upload("s.lin.w", c.W(p + "linear.weight").f);
     c.upload("s.lin.b", c.W(p + "linear.bias").f);
@@ -398,7 +417,8 @@ inline void pack_decode_program(Context& c) {
     c.meta["d.step.smem"] = (int64_t)(wimg_floats * 4 + scratch_bytes);
     // stop token: the encoder_cell half of the weight row (runtime GEMM N=1) — bias already in the pass
     std::vector<float> wst2(Wst.begin() + 512, Wst.begin() + 1024);
-    c.upload("d.stop.w2", wst2);
+    c.upload("d.stop2.w", wst2);
+    upload_tc(c, "d.stop2", wst2, 1, 1, 512);
 }
 
 
@@ -415,7 +435,9 @@ inline void pack_decoder(Context& c) {
     }
     // encoder pre-loop linears
     auto up_lin = [&](const std::string& key, const std::string& name) {
-        c.upload(name + ".w", c.W(key + ".weight").f); c.upload(name + ".b", c.W(key + ".bias").f);
+        const HostTensor& W = c.W(key + ".weight");
+        c.upload(name + ".w", W.f); c.upload(name + ".b", c.W(key + ".bias").f);
+        upload_tc(c, name, W.f, (int)W.shape[0], 1, (int)W.shape[1]);
     };
     up_lin(p + "encoder_proj.linear_layer", "d.encproj");
     up_lin(p + "encoder_site.0.linear_layer", "d.encsite"); c.upload("d.encsite.psw", c.W(p + "encoder_site.1.w").f);
@@ -429,7 +451,8 @@ inline void pack_decoder(Context& c) {
         std::vector<float> bsum = vadd(c.W(p + "encoder_rnn.bias_ih_l0").f, c.W(p + "encoder_rnn.bias_hh_l0").f);
         std::vector<float> br = vadd(c.W(p + "encoder_rnn.bias_ih_l0_reverse").f, c.W(p + "encoder_rnn.bias_hh_l0_reverse").f);
         bsum.insert(bsum.end(), br.begin(), br.end());
-        c.upload("d.ernn.wih", wih); c.upload("d.ernn.b", bsum);
+        c.upload("d.ernn.wih.w", wih); c.upload("d.ernn.b", bsum);
+        upload_tc(c, "d.ernn.wih", wih, 4096, 1, 1024);
         auto gw = [&](int, int d, int which) { return &c.W(p + "encoder_rnn.weight_" + (which ? "hh" : "ih") + "_l0" + (d ? "_reverse" : "")).f; };
         auto gb = [&](int, int) { return std::vector<float>(); };
         LstmPack pk = pack_lstm(1, 2, 512, c.num_sms, gw, gb);
@@ -444,9 +467,11 @@ inline void pack_decoder(Context& c) {
             const std::string s = std::to_string(j);
             pack_conv1d(c, p + kv + ".0.conv." + s + ".0", p + kv + ".0.conv." + s + ".1", w, b);
             c.upload(std::string("d.") + kv + ".c" + s + ".w", w); c.upload(std::string("d.") + kv + ".c" + s + ".b", b);
+            upload_tc(c, std::string("d.") + kv + ".c" + s, w, 512, (int)(w.size() / 512 / 512), 512);
         }
         pack_conv1d(c, p + kv + ".0.bottleneck", "", w, b);
         c.upload(std::string("d.") + kv + ".bn.w", w); c.upload(std::string("d.") + kv + ".bn.b", b);
+        upload_tc(c, std::string("d.") + kv + ".bn", w, 512, 1, 2560);
         c.upload(std::string("d.") + kv + ".psw", c.W(p + kv + ".1.w").f);
     }
     // Content.encode
@@ -457,6 +482,7 @@ inline void pack_decoder(Context& c) {
     }
     pack_conv1d(c, p + "content.bottleneck", "", w, b);
     c.upload("d.cbn.w", w); c.upload("d.cbn.b", b);
+    upload_tc(c, "d.cbn", w, 256, 1, 2560);
     up_lin(p + "content.location_fc.0", "d.cloc0"); up_lin(p + "content.location_fc.2", "d.cloc2"); up_lin(p + "content.location_fc.4", "d.cloc4");
     up_lin(p + "content.K.0", "d.ck0"); up_lin(p + "content.K.2", "d.ck2");
     c.upload("d.cemb", c.W(p + "content.word_embeddings").f);

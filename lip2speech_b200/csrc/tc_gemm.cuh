@@ -40,6 +40,15 @@ struct TcParams {
     const float* resid; int ldr;      // indexed by OUTPUT row, added after act
     int cstride, coff, chalf, chp;    // channel map (see gemm.cuh)
     int transposed;         // 1: C[(seq*N + n)*L + t]
+    // generic tap table (row shift per tap) — used by the Conv3d stem; conv1d uses tap - pad
+    int use_shift_table; int tap_shift[24];
+    // stem mode: input rows are padded space-to-depth positions (b, tp, hp, wp); outputs are compact NHWC rows
+    int stem, sT, sTp, sHp, sWp, sHo, sWo;
+    int debug_niter;        // >0: truncate the K loop (timing experiments only; results are wrong)
+    int ksteps_last;        // valid 8-wide k-steps in the last K chunk of a tap (1..4); zero-padded steps are skipped
+    // gather mode (GATHER_A): source rows of ga_lda floats, ga_rows rows; the window of a row is Kc floats wide
+    // (the caller guarantees zeroed slack around the buffers so tap-shifted rows never leave the allocation)
+    const float* ga_A; const float* ga_Alo; int ga_lda; long long ga_rows; int ga_unchecked;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -113,7 +122,12 @@ struct TcSmem {
     static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN>
+// GATHER_A = false: the A tile arrives by TMA and warps 2..5 split it in place.
+// GATHER_A = true : warps 2..5 ARE the A producers (software im2col): each thread loads 16-byte pieces of the
+//                   tap-shifted rows straight from global/L1 (rows of p.ga_lda floats, window p.Kc wide — windows of
+//                   neighbouring rows may overlap, which is how the Conv3d stem reuses its input through L1 instead
+//                   of re-reading it 40x through L2), splits and stores hi/lo into the swizzled tiles.
+template <int BN, bool GATHER_A>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapWhi,
                const __grid_constant__ CUtensorMap mapWlo, const TcParams p) {
@@ -131,7 +145,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
     const int kchunks = (p.Kc + TC_BK - 1) / TC_BK;
-    const int niter = p.taps * kchunks;
+    const int niter = p.debug_niter > 0 ? p.debug_niter : p.taps * kchunks;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 128); mbar_init(&empty[s], 1); }
@@ -155,8 +169,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 mbar_wait(&empty[s], ph ^ 1);
                 const int tap = it / kchunks, kc = it - tap * kchunks;
                 uint8_t* st = smem + s * SM::STAGE_BYTES;
-                mbar_expect_tx(&full[s], SM::A_BYTES + 2 * SM::W_BYTES);
-                tma_load_2d(&mapA, &full[s], st, kc * TC_BK, m0 + tap - p.pad);
+                mbar_expect_tx(&full[s], (GATHER_A ? 0 : SM::A_BYTES) + 2 * SM::W_BYTES);
+                if (!GATHER_A) tma_load_2d(&mapA, &full[s], st, kc * TC_BK, m0 + (p.use_shift_table ? p.tap_shift[tap] : tap - p.pad));
                 tma_load_2d(&mapWhi, &full[s], st + 2 * SM::A_BYTES, tap * p.Kcp + kc * TC_BK, n0);
                 tma_load_2d(&mapWlo, &full[s], st + 2 * SM::A_BYTES + SM::W_BYTES, tap * p.Kcp + kc * TC_BK, n0);
             }
@@ -168,12 +182,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int it = 0; it < niter; ++it) {
                 const int s = it % STAGES, ph = (it / STAGES) & 1;
                 mbar_wait(&split[s], ph);
+                if (GATHER_A) { mbar_wait(&full[s], ph); fence_proxy_async_smem(); }   // cp.async (generic proxy) data -> tensor core
                 tc_fence_after();
+                const int kc_ = it % kchunks;
+                const int ksteps = (kc_ == kchunks - 1) ? p.ksteps_last : TC_BK / 8;
                 const uint32_t base = smem_u32(smem + s * SM::STAGE_BYTES);
                 const uint64_t a_hi = umma_desc_sw128(base), a_lo = umma_desc_sw128(base + SM::A_BYTES);
                 const uint64_t w_hi = umma_desc_sw128(base + 2 * SM::A_BYTES), w_lo = umma_desc_sw128(base + 2 * SM::A_BYTES + SM::W_BYTES);
-#pragma unroll
-                for (int k = 0; k < TC_BK / 8; ++k) {
+                for (int k = 0; k < ksteps; ++k) {
                     const uint64_t adv = (uint64_t)(k * 32 >> 4);          // 8 tf32 = 32 bytes along K inside the swizzle row
                     umma_tf32(tmem_d, a_lo + adv, w_hi + adv, idesc, (it | k) != 0);
                     umma_tf32(tmem_d, a_hi + adv, w_lo + adv, idesc, 1);
@@ -186,7 +202,36 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     } else {
         // ===== splitters (main loop) =====
         const int t = threadIdx.x - 64;                 // 0..127
-        for (int it = 0; it < niter; ++it) {
+        if (GATHER_A) {
+            // Software im2col with cp.async: the source is already split (ga_A = hi array, ga_Alo = lo array, same layout),
+            // so a stage is 16 x 16-byte asynchronous copies per thread into the swizzled tiles and no ALU work.
+            // Completion is signalled on split[s] by cp.async.mbarrier.arrive (one arrival per thread).
+            const int c = t & 7, r0 = t >> 3;              // 16-byte chunk inside the 128-byte K row; first of 8 rows (stride 16)
+            const long long rstep = 16LL * p.ga_lda;
+            const float* base_hi = p.ga_A + ((long long)m0 + r0) * p.ga_lda + c * 4;
+            const float* base_lo = p.ga_Alo + ((long long)m0 + r0) * p.ga_lda + c * 4;
+            const uint32_t off0 = (uint32_t)(r0 * 128 + ((c ^ (r0 & 7)) << 4));     // (r0 + 16 i) & 7 == r0 & 7
+            int it = 0;
+            for (int tap = 0; tap < p.taps && it < niter; ++tap) {
+                const long long shift = (long long)(p.use_shift_table ? p.tap_shift[tap] : tap - p.pad) * p.ga_lda;
+                for (int kc = 0; kc < kchunks && it < niter; ++kc, ++it) {
+                    const int s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    if (kc * TC_BK + c * 4 < p.Kc) {        // chunks beyond Kc are never read (ksteps_last)
+                        const uint32_t dst = smem_u32(smem + s * SM::STAGE_BYTES) + off0;
+                        const float* sh = base_hi + shift + kc * TC_BK;
+                        const float* sl = base_lo + shift + kc * TC_BK;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + i * 2048), "l"(sh + i * rstep) : "memory");
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + SM::A_BYTES + i * 2048), "l"(sl + i * rstep) : "memory");
+                        }
+                    }
+                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&split[s])) : "memory");
+                }
+            }
+        }
+        for (int it = 0; !GATHER_A && it < niter; ++it) {
             const int s = it % STAGES, ph = (it / STAGES) & 1;
             mbar_wait(&full[s], ph);
             float4* hi = reinterpret_cast<float4*>(smem + s * SM::STAGE_BYTES);
@@ -211,10 +256,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int lg = warp & 3;                          // TMEM lane group this warp may access
         const int row = lg * 32 + lane;
         const int m = m0 + row;
-        const int seq = m / p.Lp_in, tp = m - seq * p.Lp_in;
-        const int tt = tp - p.P_in;
-        const bool valid = (m < p.M) && (tt >= 0) && (tt < p.L);
-        const size_t orow = (size_t)seq * p.Lp_out + p.P_out + tt;
+        int seq, tt; bool valid; size_t orow;
+        if (!p.stem) {
+            seq = m / p.Lp_in;
+            tt = m - seq * p.Lp_in - p.P_in;
+            valid = (m < p.M) && (tt >= 0) && (tt < p.L);
+            orow = (size_t)seq * p.Lp_out + p.P_out + tt;
+        } else {
+            const int wp = m % p.sWp; int r = m / p.sWp;
+            const int hp = r % p.sHp; r /= p.sHp;
+            const int tpp = r % p.sTp; const int b = r / p.sTp;
+            seq = 0; tt = 0;
+            valid = (m < p.M) && tpp >= 2 && tpp < p.sT + 2 && hp >= 2 && hp < p.sHo + 2 && wp >= 2 && wp < p.sWo + 2;
+            orow = ((size_t)(b * p.sT + tpp - 2) * p.sHo + (hp - 2)) * p.sWo + (wp - 2);
+        }
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 16) {
             if (n0 + c0 >= p.N) break;                    // warp-uniform
@@ -286,26 +341,37 @@ struct TcOperands {
     const float* Whi; const float* Wlo; int w_cols;  // [N][w_cols], w_cols = taps*Kcp
 };
 
-inline const char* launch_tc_gemm(const TcOperands& o, const TcParams& p, cudaStream_t s) {
+template <int BN, bool G>
+inline cudaError_t launch_tc_inst(dim3 grid, const CUtensorMap& mA, const CUtensorMap& mWh, const CUtensorMap& mWl, const TcParams& p, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::TOTAL);
+    if (e != cudaSuccess) return e;
+    tc_gemm_kernel<BN, G><<<grid, TC_THREADS, TcSmem<BN>::TOTAL, s>>>(mA, mWh, mWl, p);
+    return cudaGetLastError();
+}
+
+inline const char* launch_tc_gemm(const TcOperands& o, TcParams p, cudaStream_t s, bool gather = false) {
     CUtensorMap mA, mWh, mWl;
     const int BN = (p.N <= 32) ? 32 : (p.N <= 64 ? 64 : 128);
-    if (!make_map_2d(&mA, o.A, o.a_cols, o.a_rows, o.lda, TC_BM)) return "cuTensorMapEncodeTiled(A) failed";
+    const int rem = p.Kc % TC_BK;
+    p.ksteps_last = rem == 0 ? TC_BK / 8 : (rem + 7) / 8;
+    p.ga_A = o.A; p.ga_lda = o.lda; p.ga_rows = o.a_rows;
+    if (const char* e = getenv("L2S_TC_DEBUG_NITER")) p.debug_niter = atoi(e);
+    if (gather) {
+        if ((o.lda & 3) || (p.Kc & 3) || (reinterpret_cast<uintptr_t>(o.A) & 15)) return "gather-A needs 16-byte aligned rows";
+        // the A map is unused in gather mode but must be a valid object: describe the W matrix again
+        if (!make_map_2d(&mA, o.Whi, o.w_cols, p.N, o.w_cols, BN)) return "cuTensorMapEncodeTiled failed";
+    } else if (!make_map_2d(&mA, o.A, o.a_cols, o.a_rows, o.lda, TC_BM)) return "cuTensorMapEncodeTiled(A) failed";
     if (!make_map_2d(&mWh, o.Whi, o.w_cols, p.N, o.w_cols, BN)) return "cuTensorMapEncodeTiled(Whi) failed";
     if (!make_map_2d(&mWl, o.Wlo, o.w_cols, p.N, o.w_cols, BN)) return "cuTensorMapEncodeTiled(Wlo) failed";
     dim3 grid(ceil_div(p.M, TC_BM), ceil_div(p.N, BN));
     cudaError_t e;
-    if (BN == 32) {
-        e = cudaFuncSetAttribute(tc_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<32>::TOTAL);
-        if (e == cudaSuccess) tc_gemm_kernel<32><<<grid, TC_THREADS, TcSmem<32>::TOTAL, s>>>(mA, mWh, mWl, p);
-    } else if (BN == 64) {
-        e = cudaFuncSetAttribute(tc_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<64>::TOTAL);
-        if (e == cudaSuccess) tc_gemm_kernel<64><<<grid, TC_THREADS, TcSmem<64>::TOTAL, s>>>(mA, mWh, mWl, p);
+    if (gather) {
+        e = BN == 32 ? launch_tc_inst<32, true>(grid, mA, mWh, mWl, p, s) : BN == 64 ? launch_tc_inst<64, true>(grid, mA, mWh, mWl, p, s)
+                                                                                  : launch_tc_inst<128, true>(grid, mA, mWh, mWl, p, s);
     } else {
-        e = cudaFuncSetAttribute(tc_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128>::TOTAL);
-        if (e == cudaSuccess) tc_gemm_kernel<128><<<grid, TC_THREADS, TcSmem<128>::TOTAL, s>>>(mA, mWh, mWl, p);
+        e = BN == 32 ? launch_tc_inst<32, false>(grid, mA, mWh, mWl, p, s) : BN == 64 ? launch_tc_inst<64, false>(grid, mA, mWh, mWl, p, s)
+                                                                                   : launch_tc_inst<128, false>(grid, mA, mWh, mWl, p, s);
     }
-    if (e != cudaSuccess) return cudaGetErrorString(e);
-    e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 
