@@ -85,21 +85,30 @@ static void gemm_auto(Context& c, GemmParams g, const std::string& wname, cudaSt
 // video [B,3,T,H,W] NCDHW -> space-to-depth, zero-padded rows [B][T+4][H/2+3][W/2+3][12]; channel = (ph*2+pw)*3 + ci.
 __global__ void s2d_pad_kernel(const float* __restrict__ v, float* __restrict__ xs, float* __restrict__ xl, int B, int T, int H, int W, int Tp, int Hpp, int Wpp) {
     const int Ho = H / 2, Wo = W / 2;
-    const size_t total = (size_t)B * 3 * T * Ho * Wo;
+    const size_t total = (size_t)B * T * Ho * Wo;           // one thread per space-to-depth position: 12 contiguous outputs
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         int wq = i % Wo; size_t r = i / Wo;
         int hq = r % Ho; r /= Ho;
-        int t = r % T; r /= T;
-        int ci = r % 3; int b = r / 3;
-        const float* src = v + ((((size_t)b * 3 + ci) * T + t) * H + 2 * hq) * W + 2 * wq;
-        const float2 top = *reinterpret_cast<const float2*>(src);
-        const float2 bot = *reinterpret_cast<const float2*>(src + W);
-        const size_t o = ((((size_t)b * Tp + t + 2) * Hpp + hq + 2) * Wpp + wq + 2) * 12 + ci;
-        const float vals[4] = {top.x, top.y, bot.x, bot.y};
+        int t = r % T; int b = r / T;
+        float vals[12];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {                      // 3xTF32 operand split done once here: hi = top 19 bits, lo = exact remainder
-            const float h = __uint_as_float(__float_as_uint(vals[j]) & 0xFFFFE000u);
-            xs[o + 3 * j] = h; xl[o + 3 * j] = vals[j] - h;
+        for (int ci = 0; ci < 3; ++ci) {
+            const float* src = v + ((((size_t)b * 3 + ci) * T + t) * H + 2 * hq) * W + 2 * wq;
+            const float2 top = *reinterpret_cast<const float2*>(src);
+            const float2 bot = *reinterpret_cast<const float2*>(src + W);
+            vals[0 + ci] = top.x; vals[3 + ci] = top.y; vals[6 + ci] = bot.x; vals[9 + ci] = bot.y;
+        }
+        const size_t o = ((((size_t)b * Tp + t + 2) * Hpp + hq + 2) * Wpp + wq + 2) * 12;
+        float hi[12], lo[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {                     // 3xTF32 operand split done once here: hi = top 19 bits, lo = exact remainder
+            hi[j] = __uint_as_float(__float_as_uint(vals[j]) & 0xFFFFE000u);
+            lo[j] = vals[j] - hi[j];
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            *reinterpret_cast<float4*>(xs + o + 4 * q) = make_float4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+            *reinterpret_cast<float4*>(xl + o + 4 * q) = make_float4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
         }
     }
 }
@@ -129,7 +138,7 @@ static void video_forward(Context& c, const float* video, int B, int T, int H, i
             L2S_CUDA(cudaMemsetAsync(xs0, 0, 2 * plane * sizeof(float), s));
             c.meta["ws.v.s2d.layout"] = sig;
         }
-        s2d_pad_kernel<<<ew_grid((size_t)B * T * Ho * Wo * 3), 256, 0, s>>>(video, xs, xl, B, T, H, W, Tp, Hpp, Wpp);
+        s2d_pad_kernel<<<ew_grid((size_t)B * T * Ho * Wo), 256, 0, s>>>(video, xs, xl, B, T, H, W, Tp, Hpp, Wpp);
         check_launch(c, "space-to-depth");
         const int kcp = (int)c.meta.at("v.stem.tc.kcp");
         TcOperands o{xs, 48, (int)rows, 12, c.dev("v.stem.tc.hi"), c.dev("v.stem.tc.lo"), 20 * kcp};

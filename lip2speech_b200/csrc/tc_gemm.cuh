@@ -44,6 +44,7 @@ struct TcParams {
     int use_shift_table; int tap_shift[24];
     // stem mode: input rows are padded space-to-depth positions (b, tp, hp, wp); outputs are compact NHWC rows
     int stem, sT, sTp, sHp, sWp, sHo, sWo;
+    int debug_skip;         // timing experiments only: bit0 skip epilogue body, bit1 skip worker split, bit2 skip MMA issue, bit3 skip A TMA
     int debug_niter;        // >0: truncate the K loop (timing experiments only; results are wrong)
     int ksteps_last;        // valid 8-wide k-steps in the last K chunk of a tap (1..4); zero-padded steps are skipped
     // gather mode (GATHER_A): source rows of ga_lda floats, ga_rows rows; the window of a row is Kc floats wide
@@ -122,187 +123,265 @@ struct TcSmem {
     static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-// GATHER_A = false: the A tile arrives by TMA and warps 2..5 split it in place.
-// GATHER_A = true : warps 2..5 ARE the A producers (software im2col): each thread loads 16-byte pieces of the
-//                   tap-shifted rows straight from global/L1 (rows of p.ga_lda floats, window p.Kc wide — windows of
-//                   neighbouring rows may overlap, which is how the Conv3d stem reuses its input through L1 instead
-//                   of re-reading it 40x through L2), splits and stores hi/lo into the swizzled tiles.
+// Persistent, warp-specialised kernel: grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, +gridDim.x, ...
+// (n fastest, so neighbouring CTAs share A rows in L2) with ONE continuous smem ring and a double-buffered TMEM
+// accumulator, so TMEM allocation, barrier setup, pipeline fill and the epilogue of tile i overlap tile i+1.
+//   warp 0      : TMA producer (W hi/lo always; the A tile too unless GATHER_A)
+//   warp 1      : TMEM allocator + MMA issuer (one elected thread)
+//   warps 2..9  : A-side workers (256 threads)
+//                   GATHER_A = false: split the TMA-landed fp32 tile in place into hi / lo
+//                   GATHER_A = true : software im2col with cp.async from pre-split hi/lo arrays (rows of ga_lda floats whose
+//                                     Kc-wide windows may overlap — the Conv3d stem re-reads its input through L1, not L2)
+//   warps 10..17: epilogue (two warps per TMEM lane group; bias/act/residual/positional add, channel-mapped or transposed store)
+constexpr int TC_WORKERS = 256;
+constexpr int TC_EPI = 256;
+constexpr int TC_THREADS_P = 64 + TC_WORKERS + TC_EPI;
+
 template <int BN, bool GATHER_A>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS_P, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapWhi,
                const __grid_constant__ CUtensorMap mapWlo, const TcParams p) {
     using SM = TcSmem<BN>;
     constexpr int STAGES = SM::STAGES;
+    constexpr int TCOLS = (2 * BN < 32) ? 32 : 2 * BN;      // two accumulator buffers
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * SM::STAGE_BYTES);
-    uint64_t* full = bars;                   // TMA landed
-    uint64_t* split = bars + STAGES;         // a_hi/a_lo ready
-    uint64_t* empty = bars + 2 * STAGES;     // MMAs of the stage retired
-    uint64_t* accum = bars + 3 * STAGES;     // all MMAs retired
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+    uint64_t* full = bars;                    // TMA landed
+    uint64_t* split = bars + STAGES;          // a_hi/a_lo ready
+    uint64_t* empty = bars + 2 * STAGES;      // MMAs of the stage retired
+    uint64_t* tfull = bars + 3 * STAGES;      // [2] accumulator complete
+    uint64_t* tempty = bars + 3 * STAGES + 2; // [2] accumulator drained by the epilogue
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+    __shared__ float ep_s[TC_EPI / 32][32 * 17];            // per-warp transpose scratch
+    __shared__ int4 rinfo_s[TC_EPI / 32][32];               // per-warp row info (valid, seq, t, output row)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
     const int kchunks = (p.Kc + TC_BK - 1) / TC_BK;
     const int niter = p.debug_niter > 0 ? p.debug_niter : p.taps * kchunks;
+    const int ntn = (p.N + BN - 1) / BN;
+    const int ntiles = ((p.M + TC_BM - 1) / TC_BM) * ntn;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 128); mbar_init(&empty[s], 1); }
-        mbar_init(accum, 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], TC_WORKERS); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], TC_EPI); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN < 32 ? 32 : BN) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TCOLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_d = *tmem_slot;
+    const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            for (int it = 0; it < niter; ++it) {
-                const int s = it % STAGES, ph = (it / STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                const int tap = it / kchunks, kc = it - tap * kchunks;
-                uint8_t* st = smem + s * SM::STAGE_BYTES;
-                mbar_expect_tx(&full[s], (GATHER_A ? 0 : SM::A_BYTES) + 2 * SM::W_BYTES);
-                if (!GATHER_A) tma_load_2d(&mapA, &full[s], st, kc * TC_BK, m0 + (p.use_shift_table ? p.tap_shift[tap] : tap - p.pad));
-                tma_load_2d(&mapWhi, &full[s], st + 2 * SM::A_BYTES, tap * p.Kcp + kc * TC_BK, n0);
-                tma_load_2d(&mapWlo, &full[s], st + 2 * SM::A_BYTES + SM::W_BYTES, tap * p.Kcp + kc * TC_BK, n0);
+            int git = 0;                                    // global stage counter across tiles
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int m0 = (tile / ntn) * TC_BM, n0 = (tile % ntn) * BN;
+                for (int it = 0; it < niter; ++it, ++git) {
+                    const int s = git % STAGES, ph = (git / STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    const int tap = it / kchunks, kc = it - tap * kchunks;
+                    uint8_t* st = smem + s * SM::STAGE_BYTES;
+                    const bool skipA = GATHER_A || (p.debug_skip & 8);
+                    mbar_expect_tx(&full[s], (skipA ? 0 : SM::A_BYTES) + 2 * SM::W_BYTES);
+                    if (!skipA) tma_load_2d(&mapA, &full[s], st, kc * TC_BK, m0 + (p.use_shift_table ? p.tap_shift[tap] : tap - p.pad));
+                    tma_load_2d(&mapWhi, &full[s], st + 2 * SM::A_BYTES, tap * p.Kcp + kc * TC_BK, n0);
+                    tma_load_2d(&mapWlo, &full[s], st + 2 * SM::A_BYTES + SM::W_BYTES, tap * p.Kcp + kc * TC_BK, n0);
+                }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, BN < 16 ? 16 : BN);
-            for (int it = 0; it < niter; ++it) {
-                const int s = it % STAGES, ph = (it / STAGES) & 1;
-                mbar_wait(&split[s], ph);
-                if (GATHER_A) { mbar_wait(&full[s], ph); fence_proxy_async_smem(); }   // cp.async (generic proxy) data -> tensor core
+            int git = 0, lt = 0;                            // lt = local tile counter (accumulator buffer = lt & 1)
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+                const int buf = lt & 1, bph = (lt >> 1) & 1;
+                mbar_wait(&tempty[buf], bph ^ 1);           // epilogue has drained this accumulator (two tiles ago)
                 tc_fence_after();
-                const int kc_ = it % kchunks;
-                const int ksteps = (kc_ == kchunks - 1) ? p.ksteps_last : TC_BK / 8;
-                const uint32_t base = smem_u32(smem + s * SM::STAGE_BYTES);
-                const uint64_t a_hi = umma_desc_sw128(base), a_lo = umma_desc_sw128(base + SM::A_BYTES);
-                const uint64_t w_hi = umma_desc_sw128(base + 2 * SM::A_BYTES), w_lo = umma_desc_sw128(base + 2 * SM::A_BYTES + SM::W_BYTES);
-                for (int k = 0; k < ksteps; ++k) {
-                    const uint64_t adv = (uint64_t)(k * 32 >> 4);          // 8 tf32 = 32 bytes along K inside the swizzle row
-                    umma_tf32(tmem_d, a_lo + adv, w_hi + adv, idesc, (it | k) != 0);
-                    umma_tf32(tmem_d, a_hi + adv, w_lo + adv, idesc, 1);
-                    umma_tf32(tmem_d, a_hi + adv, w_hi + adv, idesc, 1);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+                for (int it = 0; it < niter; ++it, ++git) {
+                    const int s = git % STAGES, ph = (git / STAGES) & 1;
+                    mbar_wait(&split[s], ph);
+                    mbar_wait(&full[s], ph);
+                    if (GATHER_A) fence_proxy_async_smem();  // cp.async (generic proxy) data -> tensor core
+                    tc_fence_after();
+                    const int kc_ = it % kchunks;
+                    const int ksteps = (kc_ == kchunks - 1) ? p.ksteps_last : TC_BK / 8;
+                    const uint32_t base = smem_u32(smem + s * SM::STAGE_BYTES);
+                    const uint64_t a_hi = umma_desc_sw128(base), a_lo = umma_desc_sw128(base + SM::A_BYTES);
+                    const uint64_t w_hi = umma_desc_sw128(base + 2 * SM::A_BYTES), w_lo = umma_desc_sw128(base + 2 * SM::A_BYTES + SM::W_BYTES);
+                    for (int k = 0; k < ksteps && !(p.debug_skip & 4); ++k) {
+                        const uint64_t adv = (uint64_t)(k * 32 >> 4);      // 8 tf32 = 32 bytes along K inside the swizzle row
+                        umma_tf32(tmem_d, a_lo + adv, w_hi + adv, idesc, (it | k) != 0);
+                        umma_tf32(tmem_d, a_hi + adv, w_lo + adv, idesc, 1);
+                        umma_tf32(tmem_d, a_hi + adv, w_hi + adv, idesc, 1);
+                    }
+                    umma_commit(&empty[s]);
                 }
-                umma_commit(&empty[s]);
+                umma_commit(&tfull[buf]);
             }
-            umma_commit(accum);
+        }
+    } else if (warp < 2 + TC_WORKERS / 32) {
+        // ===== A-side workers =====
+        const int t = threadIdx.x - 64;                     // 0..255
+        int git = 0;
+        if (GATHER_A) {
+            const int c = t & 7, r0 = t >> 3;               // 16-byte chunk inside the 128-byte K row; first of 4 rows (stride 32)
+            const long long rstep = 32LL * p.ga_lda;
+            const uint32_t off0 = (uint32_t)(r0 * 128 + ((c ^ (r0 & 7)) << 4));     // (r0 + 32 i) & 7 == r0 & 7
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int m0 = (tile / ntn) * TC_BM;
+                const float* base_hi = p.ga_A + ((long long)m0 + r0) * p.ga_lda + c * 4;
+                const float* base_lo = p.ga_Alo + ((long long)m0 + r0) * p.ga_lda + c * 4;
+                int it = 0;
+                for (int tap = 0; tap < p.taps && it < niter; ++tap) {
+                    const long long shift = (long long)(p.use_shift_table ? p.tap_shift[tap] : tap - p.pad) * p.ga_lda;
+                    for (int kc = 0; kc < kchunks && it < niter; ++kc, ++it, ++git) {
+                        const int s = git % STAGES, ph = (git / STAGES) & 1;
+                        mbar_wait(&empty[s], ph ^ 1);
+                        if (kc * TC_BK + c * 4 < p.Kc) {     // chunks beyond Kc are never read (ksteps_last)
+                            const uint32_t dst = smem_u32(smem + s * SM::STAGE_BYTES) + off0;
+                            const float* sh = base_hi + shift + kc * TC_BK;
+                            const float* sl = base_lo + shift + kc * TC_BK;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + i * 4096), "l"(sh + i * rstep) : "memory");
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + SM::A_BYTES + i * 4096), "l"(sl + i * rstep) : "memory");
+                            }
+                        }
+                        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&split[s])) : "memory");
+                    }
+                }
+            }
+        } else {
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int it = 0; it < niter; ++it, ++git) {
+                    const int s = git % STAGES, ph = (git / STAGES) & 1;
+                    mbar_wait(&full[s], ph);
+                    float4* hi = reinterpret_cast<float4*>(smem + s * SM::STAGE_BYTES);
+                    float4* lo = reinterpret_cast<float4*>(smem + s * SM::STAGE_BYTES + SM::A_BYTES);
+                    if (p.debug_skip & 2) { mbar_arrive(&split[s]); continue; }
+                    float4 a[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) a[i] = hi[t + i * TC_WORKERS];      // same (swizzled) offset in both tiles
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float4 h, l;
+                        h.x = __uint_as_float(__float_as_uint(a[i].x) & 0xFFFFE000u); l.x = a[i].x - h.x;
+                        h.y = __uint_as_float(__float_as_uint(a[i].y) & 0xFFFFE000u); l.y = a[i].y - h.y;
+                        h.z = __uint_as_float(__float_as_uint(a[i].z) & 0xFFFFE000u); l.z = a[i].z - h.z;
+                        h.w = __uint_as_float(__float_as_uint(a[i].w) & 0xFFFFE000u); l.w = a[i].w - h.w;
+                        hi[t + i * TC_WORKERS] = h; lo[t + i * TC_WORKERS] = l;
+                    }
+                    fence_proxy_async_smem();                // generic-proxy writes -> visible to the tensor core (async proxy)
+                    mbar_arrive(&split[s]);
+                }
+            }
         }
     } else {
-        // ===== splitters (main loop) =====
-        const int t = threadIdx.x - 64;                 // 0..127
-        if (GATHER_A) {
-            // Software im2col with cp.async: the source is already split (ga_A = hi array, ga_Alo = lo array, same layout),
-            // so a stage is 16 x 16-byte asynchronous copies per thread into the swizzled tiles and no ALU work.
-            // Completion is signalled on split[s] by cp.async.mbarrier.arrive (one arrival per thread).
-            const int c = t & 7, r0 = t >> 3;              // 16-byte chunk inside the 128-byte K row; first of 8 rows (stride 16)
-            const long long rstep = 16LL * p.ga_lda;
-            const float* base_hi = p.ga_A + ((long long)m0 + r0) * p.ga_lda + c * 4;
-            const float* base_lo = p.ga_Alo + ((long long)m0 + r0) * p.ga_lda + c * 4;
-            const uint32_t off0 = (uint32_t)(r0 * 128 + ((c ^ (r0 & 7)) << 4));     // (r0 + 16 i) & 7 == r0 & 7
-            int it = 0;
-            for (int tap = 0; tap < p.taps && it < niter; ++tap) {
-                const long long shift = (long long)(p.use_shift_table ? p.tap_shift[tap] : tap - p.pad) * p.ga_lda;
-                for (int kc = 0; kc < kchunks && it < niter; ++kc, ++it) {
-                    const int s = it % STAGES, ph = (it / STAGES) & 1;
-                    mbar_wait(&empty[s], ph ^ 1);
-                    if (kc * TC_BK + c * 4 < p.Kc) {        // chunks beyond Kc are never read (ksteps_last)
-                        const uint32_t dst = smem_u32(smem + s * SM::STAGE_BYTES) + off0;
-                        const float* sh = base_hi + shift + kc * TC_BK;
-                        const float* sl = base_lo + shift + kc * TC_BK;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + i * 2048), "l"(sh + i * rstep) : "memory");
-                            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + SM::A_BYTES + i * 2048), "l"(sl + i * rstep) : "memory");
-                        }
-                    }
-                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&split[s])) : "memory");
-                }
-            }
-        }
-        for (int it = 0; !GATHER_A && it < niter; ++it) {
-            const int s = it % STAGES, ph = (it / STAGES) & 1;
-            mbar_wait(&full[s], ph);
-            float4* hi = reinterpret_cast<float4*>(smem + s * SM::STAGE_BYTES);
-            float4* lo = reinterpret_cast<float4*>(smem + s * SM::STAGE_BYTES + SM::A_BYTES);
-#pragma unroll
-            for (int i = 0; i < SM::A_BYTES / 16 / 128; ++i) {
-                const int idx = t + i * 128;             // same (swizzled) offset in both tiles
-                float4 a = hi[idx];
-                float4 h, l;
-                h.x = __uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u); l.x = a.x - h.x;
-                h.y = __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u); l.y = a.y - h.y;
-                h.z = __uint_as_float(__float_as_uint(a.z) & 0xFFFFE000u); l.z = a.z - h.z;
-                h.w = __uint_as_float(__float_as_uint(a.w) & 0xFFFFE000u); l.w = a.w - h.w;
-                hi[idx] = h; lo[idx] = l;
-            }
-            fence_proxy_async_smem();                    // generic-proxy writes -> visible to the tensor core (async proxy)
-            mbar_arrive(&split[s]);
-        }
-        // ===== epilogue =====
-        mbar_wait(accum, 0);
-        tc_fence_after();
-        const int lg = warp & 3;                          // TMEM lane group this warp may access
+        // ===== epilogue (8 warps: two per TMEM lane group, alternating 16-column chunks) =====
+        const int e = warp - (2 + TC_WORKERS / 32);        // 0..7
+        const int lg = warp & 3;                            // TMEM lane group this warp may access
+        const int half = e >> 2;
         const int row = lg * 32 + lane;
-        const int m = m0 + row;
-        int seq, tt; bool valid; size_t orow;
-        if (!p.stem) {
-            seq = m / p.Lp_in;
-            tt = m - seq * p.Lp_in - p.P_in;
-            valid = (m < p.M) && (tt >= 0) && (tt < p.L);
-            orow = (size_t)seq * p.Lp_out + p.P_out + tt;
-        } else {
-            const int wp = m % p.sWp; int r = m / p.sWp;
-            const int hp = r % p.sHp; r /= p.sHp;
-            const int tpp = r % p.sTp; const int b = r / p.sTp;
-            seq = 0; tt = 0;
-            valid = (m < p.M) && tpp >= 2 && tpp < p.sT + 2 && hp >= 2 && hp < p.sHo + 2 && wp >= 2 && wp < p.sWo + 2;
-            orow = ((size_t)(b * p.sT + tpp - 2) * p.sHo + (hp - 2)) * p.sWo + (wp - 2);
-        }
+        float* ep = ep_s[e];
+        int4* rinfo = rinfo_s[e];
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+            const int m0 = (tile / ntn) * TC_BM, n0 = (tile % ntn) * BN;
+            const int buf = lt & 1, bph = (lt >> 1) & 1;
+            mbar_wait(&tfull[buf], bph);
+            tc_fence_after();
+            if (p.debug_skip & 1) { tc_fence_before(); mbar_arrive(&tempty[buf]); continue; }
+            const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+            const int m = m0 + row;
+            int seq, tt; bool valid; int orow;
+            if (!p.stem) {
+                seq = m / p.Lp_in;
+                tt = m - seq * p.Lp_in - p.P_in;
+                valid = (m < p.M) && (tt >= 0) && (tt < p.L);
+                orow = seq * p.Lp_out + p.P_out + tt;
+            } else {
+                const int wp = m % p.sWp; int r = m / p.sWp;
+                const int hp = r % p.sHp; r /= p.sHp;
+                const int tpp = r % p.sTp; const int b = r / p.sTp;
+                seq = 0; tt = 0;
+                valid = (m < p.M) && tpp >= 2 && tpp < p.sT + 2 && hp >= 2 && hp < p.sHo + 2 && wp >= 2 && wp < p.sWo + 2;
+                orow = ((b * p.sT + tpp - 2) * p.sHo + (hp - 2)) * p.sWo + (wp - 2);
+            }
+            // Row bookkeeping is computed once per tile by the thread that owns the TMEM lane and shared with the warp;
+            // each 32x16 accumulator chunk is transposed through shared memory so that lanes map to CHANNELS: bias /
+            // residual loads and the output stores are then contiguous within a row (a lane-per-row store would touch
+            // 32 different rows = 32 sectors per instruction).
+            rinfo[lane] = make_int4(valid ? 1 : 0, seq, tt, orow);
+            __syncwarp();
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-            if (n0 + c0 >= p.N) break;                    // warp-uniform
-            uint32_t v[16];
-            tmem_ld16(tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, v);
-            if (valid) {
+            for (int c0 = half * 16; c0 < BN; c0 += 32) {
+                if (n0 + c0 >= p.N) break;                   // warp-uniform
+                uint32_t v[16];
+                tmem_ld16(tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, v);
+                if (p.transposed) {                           // [B][N][L] output: consecutive rows are consecutive addresses already
+                    if (valid) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int n = n0 + c0 + j;
-                    if (n < p.N) {
-                        float x = __uint_as_float(v[j]);
-                        if (p.bias) x += __ldg(p.bias + n);
-                        if (p.addrow) x += p.addrow[(size_t)seq * p.N + n];
-                        x = apply_act(x, p.act, p.act_w ? __ldg(p.act_w + n) : 1.f);
-                        if (p.addpos) x += __ldg(p.addpos + (size_t)tt * p.ldpos + n);
-                        if (p.resid) x += p.resid[orow * p.ldr + n];
-                        if (p.transposed) {
-                            p.C[((size_t)seq * p.N + n) * p.L + tt] = x;
-                        } else {
-                            int l = n * p.cstride + p.coff;
-                            if (p.chalf > 0 && l >= p.chalf) l = l - p.chalf + p.chp;
-                            p.C[orow * p.ldc + l] = x;
+                        for (int j = 0; j < 16; ++j) {
+                            const int n = n0 + c0 + j;
+                            if (n < p.N) {
+                                float x = __uint_as_float(v[j]);
+                                if (p.bias) x += __ldg(p.bias + n);
+                                if (p.addrow) x += p.addrow[(size_t)seq * p.N + n];
+                                x = apply_act(x, p.act, p.act_w ? __ldg(p.act_w + n) : 1.f);
+                                if (p.addpos) x += __ldg(p.addpos + (size_t)tt * p.ldpos + n);
+                                if (p.resid) x += p.resid[(size_t)orow * p.ldr + n];
+                                p.C[((size_t)seq * p.N + n) * p.L + tt] = x;
+                            }
                         }
                     }
+                    continue;
                 }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) ep[lane * 17 + j] = __uint_as_float(v[j]);
+                __syncwarp();
+                const int j = lane & 15, n = n0 + c0 + j;
+                if (n < p.N) {
+                    const float bias = p.bias ? __ldg(p.bias + n) : 0.f;
+                    const float aw = p.act_w ? __ldg(p.act_w + n) : 1.f;
+                    int l = n * p.cstride + p.coff;
+                    if (p.chalf > 0 && l >= p.chalf) l = l - p.chalf + p.chp;
+                    float* __restrict__ Cn = p.C + l;
+                    const bool plain = !p.addrow && !p.addpos && !p.resid;
+#pragma unroll 8
+                    for (int rr = 0; rr < 16; ++rr) {
+                        const int r = 2 * rr + (lane >> 4);
+                        const int4 ri = rinfo[r];
+                        float x = ep[r * 17 + j] + bias;
+                        if (plain) {
+                            x = apply_act(x, p.act, aw);
+                        } else if (ri.x) {
+                            if (p.addrow) x += p.addrow[(size_t)ri.y * p.N + n];
+                            x = apply_act(x, p.act, aw);
+                            if (p.addpos) x += __ldg(p.addpos + (size_t)ri.z * p.ldpos + n);
+                            if (p.resid) x += p.resid[(size_t)ri.w * p.ldr + n];
+                        }
+                        if (ri.x) Cn[(size_t)ri.w * p.ldc] = x;
+                    }
+                }
+                __syncwarp();
             }
+            tc_fence_before();
+            mbar_arrive(&tempty[buf]);                        // accumulator may be overwritten (all 256 epilogue threads arrive)
         }
-        tc_fence_before();
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(BN < 32 ? 32 : BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TCOLS) : "memory");
     }
 }
 
@@ -345,7 +424,7 @@ template <int BN, bool G>
 inline cudaError_t launch_tc_inst(dim3 grid, const CUtensorMap& mA, const CUtensorMap& mWh, const CUtensorMap& mWl, const TcParams& p, cudaStream_t s) {
     cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::TOTAL);
     if (e != cudaSuccess) return e;
-    tc_gemm_kernel<BN, G><<<grid, TC_THREADS, TcSmem<BN>::TOTAL, s>>>(mA, mWh, mWl, p);
+    tc_gemm_kernel<BN, G><<<grid, TC_THREADS_P, TcSmem<BN>::TOTAL, s>>>(mA, mWh, mWl, p);
     return cudaGetLastError();
 }
 
@@ -356,6 +435,7 @@ inline const char* launch_tc_gemm(const TcOperands& o, TcParams p, cudaStream_t 
     p.ksteps_last = rem == 0 ? TC_BK / 8 : (rem + 7) / 8;
     p.ga_A = o.A; p.ga_lda = o.lda; p.ga_rows = o.a_rows;
     if (const char* e = getenv("L2S_TC_DEBUG_NITER")) p.debug_niter = atoi(e);
+    if (const char* e = getenv("L2S_TC_DEBUG_SKIP")) p.debug_skip = atoi(e);
     if (gather) {
         if ((o.lda & 3) || (p.Kc & 3) || (reinterpret_cast<uintptr_t>(o.A) & 15)) return "gather-A needs 16-byte aligned rows";
         // the A map is unused in gather mode but must be a valid object: describe the W matrix again
@@ -363,7 +443,10 @@ inline const char* launch_tc_gemm(const TcOperands& o, TcParams p, cudaStream_t 
     } else if (!make_map_2d(&mA, o.A, o.a_cols, o.a_rows, o.lda, TC_BM)) return "cuTensorMapEncodeTiled(A) failed";
     if (!make_map_2d(&mWh, o.Whi, o.w_cols, p.N, o.w_cols, BN)) return "cuTensorMapEncodeTiled(Whi) failed";
     if (!make_map_2d(&mWl, o.Wlo, o.w_cols, p.N, o.w_cols, BN)) return "cuTensorMapEncodeTiled(Wlo) failed";
-    dim3 grid(ceil_div(p.M, TC_BM), ceil_div(p.N, BN));
+    static int num_sms = 0;
+    if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int ntiles = ceil_div(p.M, TC_BM) * ceil_div(p.N, BN);
+    dim3 grid(ntiles < num_sms ? ntiles : num_sms);
     cudaError_t e;
     if (gather) {
         e = BN == 32 ? launch_tc_inst<32, true>(grid, mA, mWh, mWl, p, s) : BN == 64 ? launch_tc_inst<64, true>(grid, mA, mWh, mWl, p, s)
