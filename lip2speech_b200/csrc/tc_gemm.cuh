@@ -143,7 +143,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                const __grid_constant__ CUtensorMap mapWlo, const TcParams p) {
     using SM = TcSmem<BN>;
     constexpr int STAGES = SM::STAGES;
-    constexpr int TCOLS = (2 * BN < 32) ? 32 : 2 * BN;      // two accumulator buffers
+    constexpr int TCOLS = (4 * BN < 32) ? 32 : 4 * BN;      // two accumulator buffers x [a*w_hi (+a_lo*w_hi) | a_hi*w_lo]
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * SM::STAGE_BYTES);
@@ -188,6 +188,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     const int tap = it / kchunks, kc = it - tap * kchunks;
                     uint8_t* st = smem + s * SM::STAGE_BYTES;
                     const bool skipA = GATHER_A || (p.debug_skip & 8);
+                    if (p.debug_skip & 32) { mbar_arrive(&full[s]); continue; }      // skip all TMA traffic
                     mbar_expect_tx(&full[s], (skipA ? 0 : SM::A_BYTES) + 2 * SM::W_BYTES);
                     if (!skipA) tma_load_2d(&mapA, &full[s], st, kc * TC_BK, m0 + (p.use_shift_table ? p.tap_shift[tap] : tap - p.pad));
                     tma_load_2d(&mapWhi, &full[s], st + 2 * SM::A_BYTES, tap * p.Kcp + kc * TC_BK, n0);
@@ -198,31 +199,45 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_tf32(TC_BM, BN < 16 ? 16 : BN);
+            // Per k-step (8 tf32 = 32 bytes) two MMAs instead of three: the W tiles [w_hi ; w_lo] are contiguous in shared
+            // memory, so ONE N=2*BN instruction computes a_hi*w_hi (columns 0..BN) and a_hi*w_lo (columns BN..2BN) with a
+            // single read of the A tile — SS-mode MMAs at small N are bound by the A-operand read, not by N — and a second
+            // N=BN instruction adds a_lo*w_hi.  The epilogue sums the two column groups.
+            constexpr uint32_t idesc2 = umma_idesc_tf32(TC_BM, 2 * BN);
+            constexpr uint32_t idesc1 = umma_idesc_tf32(TC_BM, BN < 16 ? 16 : BN);
+            uint64_t d_ahi[STAGES], d_alo[STAGES], d_w[STAGES];
+#pragma unroll
+            for (int s = 0; s < STAGES; ++s) {
+                const uint32_t base = smem_u32(smem + s * SM::STAGE_BYTES);
+                d_ahi[s] = umma_desc_sw128(base); d_alo[s] = umma_desc_sw128(base + SM::A_BYTES);
+                d_w[s] = umma_desc_sw128(base + 2 * SM::A_BYTES);
+            }
             int git = 0, lt = 0;                            // lt = local tile counter (accumulator buffer = lt & 1)
+            int s = 0, ph = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
                 const int buf = lt & 1, bph = (lt >> 1) & 1;
                 mbar_wait(&tempty[buf], bph ^ 1);           // epilogue has drained this accumulator (two tiles ago)
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * 2 * BN);
+                int kc_ = 0;
                 for (int it = 0; it < niter; ++it, ++git) {
-                    const int s = git % STAGES, ph = (git / STAGES) & 1;
                     mbar_wait(&split[s], ph);
-                    mbar_wait(&full[s], ph);
-                    if (GATHER_A) fence_proxy_async_smem();  // cp.async (generic proxy) data -> tensor core
+                    if (GATHER_A) { mbar_wait(&full[s], ph); fence_proxy_async_smem(); }   // cp.async (generic proxy) data -> tensor core
                     tc_fence_after();
-                    const int kc_ = it % kchunks;
-                    const int ksteps = (kc_ == kchunks - 1) ? p.ksteps_last : TC_BK / 8;
-                    const uint32_t base = smem_u32(smem + s * SM::STAGE_BYTES);
-                    const uint64_t a_hi = umma_desc_sw128(base), a_lo = umma_desc_sw128(base + SM::A_BYTES);
-                    const uint64_t w_hi = umma_desc_sw128(base + 2 * SM::A_BYTES), w_lo = umma_desc_sw128(base + 2 * SM::A_BYTES + SM::W_BYTES);
-                    for (int k = 0; k < ksteps && !(p.debug_skip & 4); ++k) {
-                        const uint64_t adv = (uint64_t)(k * 32 >> 4);      // 8 tf32 = 32 bytes along K inside the swizzle row
-                        umma_tf32(tmem_d, a_lo + adv, w_hi + adv, idesc, (it | k) != 0);
-                        umma_tf32(tmem_d, a_hi + adv, w_lo + adv, idesc, 1);
-                        umma_tf32(tmem_d, a_hi + adv, w_hi + adv, idesc, 1);
+                    const int ksteps = (p.debug_skip & 4) ? 0 : ((kc_ == kchunks - 1) ? p.ksteps_last : TC_BK / 8);
+                    if (++kc_ == kchunks) kc_ = 0;
+                    uint64_t ahi = d_ahi[s], alo = d_alo[s], w = d_w[s];
+                    uint32_t acc = it != 0;
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; ++k) {
+                        if (k < ksteps) {
+                            umma_tf32(tmem_d, ahi, w, idesc2, acc);
+                            umma_tf32(tmem_d, alo, w, idesc1, 1);
+                            acc = 1; ahi += 2; alo += 2; w += 2;           // 8 tf32 = 32 bytes = 2 descriptor units along K
+                        }
                     }
                     umma_commit(&empty[s]);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
                 umma_commit(&tfull[buf]);
             }
@@ -245,7 +260,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     for (int kc = 0; kc < kchunks && it < niter; ++kc, ++it, ++git) {
                         const int s = git % STAGES, ph = (git / STAGES) & 1;
                         mbar_wait(&empty[s], ph ^ 1);
-                        if (kc * TC_BK + c * 4 < p.Kc) {     // chunks beyond Kc are never read (ksteps_last)
+                        if (kc * TC_BK + c * 4 < p.Kc && !(p.debug_skip & 16)) {     // chunks beyond Kc are never read (ksteps_last)
                             const uint32_t dst = smem_u32(smem + s * SM::STAGE_BYTES) + off0;
                             const float* sh = base_hi + shift + kc * TC_BK;
                             const float* sl = base_lo + shift + kc * TC_BK;
@@ -299,7 +314,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             mbar_wait(&tfull[buf], bph);
             tc_fence_after();
             if (p.debug_skip & 1) { tc_fence_before(); mbar_arrive(&tempty[buf]); continue; }
-            const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+            const uint32_t tmem_d = tmem_base + (uint32_t)(buf * 2 * BN);
             const int m = m0 + row;
             int seq, tt; bool valid; int orow;
             if (!p.stem) {
@@ -325,7 +340,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int c0 = half * 16; c0 < BN; c0 += 32) {
                 if (n0 + c0 >= p.N) break;                   // warp-uniform
                 uint32_t v[16];
-                tmem_ld16(tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, v);
+                {
+                    uint32_t v2[16];
+                    tmem_ld16(tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, v);
+                    tmem_ld16(tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)(BN + c0), v2);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+                }
                 if (p.transposed) {                           // [B][N][L] output: consecutive rows are consecutive addresses already
                     if (valid) {
 #pragma unroll
