@@ -296,6 +296,16 @@ __global__ void pad_rows_kernel(const float* __restrict__ src, float* __restrict
     }
 }
 
+// dst[b][t][:] = src[b][t][:] for t < Lk (drops the tail rows of every sequence so that rows become contiguous k-groups)
+__global__ void trim_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int T, int Lk, int C4) {
+    const size_t total = (size_t)B * Lk * C4;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int c4 = i % C4; size_t r = i / C4;
+        int t = r % Lk; int b = r / Lk;
+        reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[((size_t)b * T + t) * C4 + c4];
+    }
+}
+
 // (Re)allocate a padded-layout buffer; its pad rows must be zero, so it is cleared whenever the layout changes.
 static float* padded_buf(Context& c, const std::string& name, int B, int Lp, int C, cudaStream_t s) {
     float* p = c.fbuf(name, (size_t)B * Lp * C);
@@ -418,10 +428,11 @@ static void decoder_infer(Context& c, const float* visual, const float* spk, con
         gemm_auto(c, p, "d.encproj", s, "encoder_proj");
     }
     // ---- K / V (MultiHopConv + PSine + positions, decoder.py:396-399) -----------------------------
-    float* cat = c.fbuf("ws.d.cat", (size_t)M * 2560);
+    float* cat = c.fbuf("ws.d.cat", (size_t)M * 5120);      // [M][K half: enc | 4 convs][V half: enc | 4 convs]
     float* Kmem = c.fbuf("ws.d.K", (size_t)M * 512);
     float* Vmem = c.fbuf("ws.d.V", (size_t)M * 512);
-    L2S_CUDA(cudaMemcpy2DAsync(cat, 2560 * sizeof(float), enc, 512 * sizeof(float), 512 * sizeof(float), M, cudaMemcpyDeviceToDevice, s));
+    L2S_CUDA(cudaMemcpy2DAsync(cat, 5120 * sizeof(float), enc, 512 * sizeof(float), 512 * sizeof(float), M, cudaMemcpyDeviceToDevice, s));
+    L2S_CUDA(cudaMemcpy2DAsync(cat + 2560, 5120 * sizeof(float), enc, 512 * sizeof(float), 512 * sizeof(float), M, cudaMemcpyDeviceToDevice, s));
     const int mks[4] = {1, 3, 7, 11};
     const int PM = 5, Tp = T + 2 * PM;                       // zero-padded per-sequence layout for the tap-shifted TMA boxes
     float* encp = nullptr;
@@ -430,28 +441,31 @@ static void decoder_infer(Context& c, const float* visual, const float* spk, con
         pad_rows_kernel<<<ew_grid((size_t)M * 128), 256, 0, s>>>(enc, encp, B, T, Tp, PM, 128);
         check_launch(c, "pad enc rows");
     }
+    for (int j = 0; j < 4; ++j) {                            // K and V branches of conv j in one launch (N = 1024)
+        const std::string wn = "d.KV.c" + std::to_string(j);
+        const int coff = 512 * (j + 1);
+        if (c.use_tc) {
+            const int kcp = (int)c.meta.at(wn + ".kcp");
+            TcOperands o{encp, 512, B * Tp, 512, c.dev(wn + ".hi"), c.dev(wn + ".lo"), mks[j] * kcp};
+            TcParams p = tc_defaults();
+            p.M = B * Tp; p.N = 1024; p.Kc = 512; p.Kcp = kcp; p.taps = mks[j]; p.pad = mks[j] / 2;
+            p.Lp_in = Tp; p.P_in = PM; p.L = T; p.Lp_out = T; p.P_out = 0;
+            p.C = cat; p.ldc = 5120; p.coff = coff; p.chalf = coff + 512; p.chp = 2560 + coff;
+            p.bias = c.dev(wn + ".b"); p.act = ACT_SILU;
+            run_tc(c, o, p, s, "multihop conv");
+        } else {
+            GemmParams p = gemm_defaults();
+            p.A = enc; p.lda = 512; p.W = c.dev(wn + ".w"); p.bias = c.dev(wn + ".b");
+            p.C = cat; p.ldc = 5120; p.coff = coff; p.chalf = coff + 512; p.chp = 2560 + coff;
+            p.M = M; p.N = 1024; p.Kc = 512; p.taps = mks[j]; p.pad = mks[j] / 2;
+            p.L_out = T; p.L_in = T; p.act = ACT_SILU;
+            run_gemm(c, p, s, "multihop conv");
+        }
+    }
     for (int kv = 0; kv < 2; ++kv) {
         const std::string n = kv == 0 ? "d.K" : "d.V";
-        for (int j = 0; j < 4; ++j) {
-            const std::string wn = n + ".c" + std::to_string(j);
-            if (c.use_tc) {
-                const int kcp = (int)c.meta.at(wn + ".kcp");
-                TcOperands o{encp, 512, B * Tp, 512, c.dev(wn + ".hi"), c.dev(wn + ".lo"), mks[j] * kcp};
-                TcParams p = tc_defaults();
-                p.M = B * Tp; p.N = 512; p.Kc = 512; p.Kcp = kcp; p.taps = mks[j]; p.pad = mks[j] / 2;
-                p.Lp_in = Tp; p.P_in = PM; p.L = T; p.Lp_out = T; p.P_out = 0;
-                p.C = cat; p.ldc = 2560; p.coff = 512 * (j + 1); p.bias = c.dev(wn + ".b"); p.act = ACT_SILU;
-                run_tc(c, o, p, s, "multihop conv");
-            } else {
-                GemmParams p = gemm_defaults();
-                p.A = enc; p.lda = 512; p.W = c.dev(wn + ".w"); p.bias = c.dev(wn + ".b");
-                p.C = cat; p.ldc = 2560; p.coff = 512 * (j + 1); p.M = M; p.N = 512; p.Kc = 512; p.taps = mks[j]; p.pad = mks[j] / 2;
-                p.L_out = T; p.L_in = T; p.act = ACT_SILU;
-                run_gemm(c, p, s, "multihop conv");
-            }
-        }
         GemmParams p = gemm_defaults();
-        p.A = cat; p.lda = 2560; p.bias = c.dev(n + ".bn.b"); p.C = kv == 0 ? Kmem : Vmem; p.ldc = 512;
+        p.A = cat + 2560 * kv; p.lda = 5120; p.bias = c.dev(n + ".bn.b"); p.C = kv == 0 ? Kmem : Vmem; p.ldc = 512;
         p.M = M; p.N = 512; p.Kc = 2560; p.L_out = T; p.L_in = T; p.act = ACT_PSINE; p.act_w = c.dev(n + ".psw"); p.addpos = pos; p.ldpos = 512;
         gemm_auto(c, p, n + ".bn", s, "multihop bottleneck");
     }
@@ -461,12 +475,25 @@ static void decoder_infer(Context& c, const float* visual, const float* spk, con
     float* ctmp = c.fbuf("ws.d.ctmp", (size_t)M * 512);
     adaptive_pool_kernel<<<ew_grid((size_t)Mc * 512), 256, 0, s>>>(enc, 512, T, ccat2, 2560, 0, minT, 512, B);
     check_launch(c, "adaptive pool");
+    float* ctrim = c.fbuf("ws.d.ctrim", (size_t)M * 512);
     for (int j = 0; j < 4; ++j) {
-        GemmParams p = gemm_defaults();
-        p.A = enc; p.lda = 512; p.W = c.dev("d.cagg" + std::to_string(j) + ".w"); p.bias = c.dev("d.cagg" + std::to_string(j) + ".b");
-        p.C = ctmp; p.ldc = 512; p.M = B * Lc[j]; p.N = 512; p.Kc = 512; p.taps = cks[j]; p.pad = 0; p.stride = cks[j];
-        p.L_out = Lc[j]; p.L_in = T; p.act = ACT_SILU;
-        run_gemm(c, p, s, "content agg conv");
+        const std::string wn = "d.cagg" + std::to_string(j);
+        if (c.use_tc) {
+            // kernel == stride: output i reads input rows k*i .. k*i+k-1, i.e. one k*512-wide row of the (trimmed) sequence
+            const float* src = enc;
+            if (cks[j] > 1) {
+                trim_rows_kernel<<<ew_grid((size_t)B * Lc[j] * cks[j] * 128), 256, 0, s>>>(enc, ctrim, B, T, Lc[j] * cks[j], 128);
+                check_launch(c, "trim rows");
+                src = ctrim;
+            }
+            linear(c, src, cks[j] * 512, wn, c.dev(wn + ".b"), ctmp, 512, B * Lc[j], 512, cks[j] * 512, ACT_SILU, nullptr, s, "content agg conv");
+        } else {
+            GemmParams p = gemm_defaults();
+            p.A = enc; p.lda = 512; p.W = c.dev(wn + ".w"); p.bias = c.dev(wn + ".b");
+            p.C = ctmp; p.ldc = 512; p.M = B * Lc[j]; p.N = 512; p.Kc = 512; p.taps = cks[j]; p.pad = 0; p.stride = cks[j];
+            p.L_out = Lc[j]; p.L_in = T; p.act = ACT_SILU;
+            run_gemm(c, p, s, "content agg conv");
+        }
         adaptive_pool_kernel<<<ew_grid((size_t)Mc * 512), 256, 0, s>>>(ctmp, 512, Lc[j], ccat2, 2560, 512 * (j + 1), minT, 512, B);
         check_launch(c, "adaptive pool");
     }

@@ -90,21 +90,53 @@ __device__ __forceinline__ const float* dec_src(const DecodeParams& p, int src, 
     }
 }
 
+struct StageSync {
+    const unsigned* counter; unsigned target; bool waited;
+    float* tacc; long long tmark; int slot0; bool timing;
+    __device__ __forceinline__ void lap(int slot) {
+        if (timing && threadIdx.x == 0) { long long now = clock64(); tacc[slot] += (float)(now - tmark); tmark = now; }
+    }
+    // Block until every CTA has finished the previous stage (idempotent within a stage).
+    __device__ __forceinline__ void wait() {
+        if (!waited) {
+            lap(slot0);
+            grid_wait(counter, target);
+            lap(slot0 + 1);
+            waited = true;
+        }
+    }
+};
+
 // Dot-product attention over the T encoder positions and over the minT content slots for one clip
 // (reference decoder.py:414-419 and Content.forward 262-271).  `nsplit` CTAs share a clip: each recomputes
 // the (cheap) scores and produces its 512/nsplit slice of ctx and 256/nsplit slice of the content value.
-__device__ void dec_attend(const DecodeParams& p, const DecSmem& sm, int b, int part, int step) {
+__device__ void dec_attend(const DecodeParams& p, const DecSmem& sm, StageSync& sync, int b, int part, int step) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // K rows are constants of the whole decode: the first two rows of this warp are fetched BEFORE waiting for the
+    // previous stage, so their L2 latency hides behind the grid barrier.
+    float4 kpre0[4], kpre1[4];
+    if (warp < p.T) {
+        const float4* kr0 = reinterpret_cast<const float4*>(p.Kmem + ((size_t)b * p.T + warp) * 512);
+        const float4* kr1 = reinterpret_cast<const float4*>(p.Kmem + ((size_t)b * p.T + (warp + MV_WARPS < p.T ? warp + MV_WARPS : warp)) * 512);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { kpre0[i] = __ldg(kr0 + lane + 32 * i); kpre1[i] = __ldg(kr1 + lane + 32 * i); }
+    }
+    sync.wait();
     sm.qs[tid] = ldcg1(p.Q + (size_t)tid * p.Bpad + b) * p.temp;
     if (tid < 256) sm.cqs[tid] = ldcg1(p.CQ + (size_t)tid * p.Bpad + b) * p.ctemp;
     __syncthreads();
     for (int t0 = warp; t0 < p.T; t0 += 2 * MV_WARPS) {
         const int t1 = t0 + MV_WARPS;
-        const float4* kr0 = reinterpret_cast<const float4*>(p.Kmem + ((size_t)b * p.T + t0) * 512);
-        const float4* kr1 = reinterpret_cast<const float4*>(p.Kmem + ((size_t)b * p.T + (t1 < p.T ? t1 : t0)) * 512);
         float4 k0[4], k1[4];
+        if (t0 == warp) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { k0[i] = __ldg(kr0 + lane + 32 * i); k1[i] = __ldg(kr1 + lane + 32 * i); }
+            for (int i = 0; i < 4; ++i) { k0[i] = kpre0[i]; k1[i] = kpre1[i]; }
+        } else {
+            const float4* kr0 = reinterpret_cast<const float4*>(p.Kmem + ((size_t)b * p.T + t0) * 512);
+            const float4* kr1 = reinterpret_cast<const float4*>(p.Kmem + ((size_t)b * p.T + (t1 < p.T ? t1 : t0)) * 512);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { k0[i] = __ldg(kr0 + lane + 32 * i); k1[i] = __ldg(kr1 + lane + 32 * i); }
+        }
         float a0 = 0.f, a1 = 0.f;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -181,23 +213,6 @@ __device__ void dec_attend(const DecodeParams& p, const DecSmem& sm, int b, int 
     }
     __syncthreads();
 }
-
-struct StageSync {
-    const unsigned* counter; unsigned target; bool waited;
-    float* tacc; long long tmark; int slot0; bool timing;
-    __device__ __forceinline__ void lap(int slot) {
-        if (timing && threadIdx.x == 0) { long long now = clock64(); tacc[slot] += (float)(now - tmark); tmark = now; }
-    }
-    // Block until every CTA has finished the previous stage (idempotent within a stage).
-    __device__ __forceinline__ void wait() {
-        if (!waited) {
-            lap(slot0);
-            grid_wait(counter, target);
-            lap(slot0 + 1);
-            waited = true;
-        }
-    }
-};
 
 template <int R>
 __device__ __forceinline__ void dec_run_pass(const DecodeParams& p, const DecPass& ps, const DecSmem& sm, StageSync& sync,
@@ -321,10 +336,8 @@ __global__ void __launch_bounds__(MV_THREADS, 1) decode_persistent_kernel(const 
             for (int j = 0; j < np; ++j)
                 if (passes[j].stage == stage) dec_dispatch(p, passes[j], sm, sync, step, parity_new);
             if (stage == ST_B) {
-                for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
-                    sync.wait();
-                    dec_attend(p, sm, job / p.nsplit, job % p.nsplit, step);
-                }
+                for (int job = blockIdx.x; job < njobs; job += gridDim.x)
+                    dec_attend(p, sm, sync, job / p.nsplit, job % p.nsplit, step);
             }
             sync.wait();                 // barriers must complete in order even for CTAs idle in this stage
             sync.lap(sync.slot0 + 2);

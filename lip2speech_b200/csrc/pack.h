@@ -461,14 +461,18 @@ inline void pack_decoder(Context& c) {
         c.upload_raw("d.ernn.chunks", pk.chunks.data(), pk.chunks.size());
         c.meta["d.ernn.nchunks"] = (int64_t)pk.chunks.size(); c.meta["d.ernn.max_chunks"] = pk.max_chunks;
     }
-    // K / V MultiHopConv
+    // K / V MultiHopConv: the four convolutions of K and of V read the same input, so each pair is packed as ONE
+    // conv with 1024 output channels (rows 0..511 = K branch, 512..1023 = V branch)
+    for (int j = 0; j < 4; ++j) {
+        const std::string s = std::to_string(j);
+        std::vector<float> wk, bk, wv, bv;
+        pack_conv1d(c, p + "K.0.conv." + s + ".0", p + "K.0.conv." + s + ".1", wk, bk);
+        pack_conv1d(c, p + "V.0.conv." + s + ".0", p + "V.0.conv." + s + ".1", wv, bv);
+        wk.insert(wk.end(), wv.begin(), wv.end()); bk.insert(bk.end(), bv.begin(), bv.end());
+        c.upload("d.KV.c" + s + ".w", wk); c.upload("d.KV.c" + s + ".b", bk);
+        upload_tc(c, "d.KV.c" + s, wk, 1024, (int)(wk.size() / 1024 / 512), 512);
+    }
     for (const char* kv : {"K", "V"}) {
-        for (int j = 0; j < 4; ++j) {
-            const std::string s = std::to_string(j);
-            pack_conv1d(c, p + kv + ".0.conv." + s + ".0", p + kv + ".0.conv." + s + ".1", w, b);
-            c.upload(std::string("d.") + kv + ".c" + s + ".w", w); c.upload(std::string("d.") + kv + ".c" + s + ".b", b);
-            upload_tc(c, std::string("d.") + kv + ".c" + s, w, 512, (int)(w.size() / 512 / 512), 512);
-        }
         pack_conv1d(c, p + kv + ".0.bottleneck", "", w, b);
         c.upload(std::string("d.") + kv + ".bn.w", w); c.upload(std::string("d.") + kv + ".bn.b", b);
         upload_tc(c, std::string("d.") + kv + ".bn", w, 512, 1, 2560);
@@ -479,6 +483,7 @@ inline void pack_decoder(Context& c) {
         const std::string s = std::to_string(j);
         pack_conv1d(c, p + "content.agg." + s + ".0", p + "content.agg." + s + ".1", w, b);
         c.upload("d.cagg" + s + ".w", w); c.upload("d.cagg" + s + ".b", b);
+        upload_tc(c, "d.cagg" + s, w, 512, 1, (int)(w.size() / 512));       // k == stride: a dense GEMM over k*512-wide rows
     }
     pack_conv1d(c, p + "content.bottleneck", "", w, b);
     c.upload("d.cbn.w", w); c.upload("d.cbn.b", b);
