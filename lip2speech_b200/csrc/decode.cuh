@@ -110,33 +110,18 @@ struct StageSync {
 // Dot-product attention over the T encoder positions and over the minT content slots for one clip
 // (reference decoder.py:414-419 and Content.forward 262-271).  `nsplit` CTAs share a clip: each recomputes
 // the (cheap) scores and produces its 512/nsplit slice of ctx and 256/nsplit slice of the content value.
-__device__ void dec_attend(const DecodeParams& p, const DecSmem& sm, StageSync& sync, int b, int part, int step) {
+__device__ void dec_attend(const DecodeParams& p, const DecSmem& sm, int b, int part, int step) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // K rows are constants of the whole decode: the first two rows of this warp are fetched BEFORE waiting for the
-    // previous stage, so their L2 latency hides behind the grid barrier.
-    float4 kpre0[4], kpre1[4];
-    if (warp < p.T) {
-        const float4* kr0 = reinterpret_cast<const float4*>(p.Kmem + ((size_t)b * p.T + warp) * 512);
-        const float4* kr1 = reinterpret_cast<const float4*>(p.Kmem + ((size_t)b * p.T + (warp + MV_WARPS < p.T ? warp + MV_WARPS : warp)) * 512);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { kpre0[i] = __ldg(kr0 + lane + 32 * i); kpre1[i] = __ldg(kr1 + lane + 32 * i); }
-    }
-    sync.wait();
     sm.qs[tid] = ldcg1(p.Q + (size_t)tid * p.Bpad + b) * p.temp;
     if (tid < 256) sm.cqs[tid] = ldcg1(p.CQ + (size_t)tid * p.Bpad + b) * p.ctemp;
     __syncthreads();
     for (int t0 = warp; t0 < p.T; t0 += 2 * MV_WARPS) {
         const int t1 = t0 + MV_WARPS;
+        const float4* kr0 = reinterpret_cast<const float4*>(p.Kmem + ((size_t)b * p.T + t0) * 512);
+        const float4* kr1 = reinterpret_cast<const float4*>(p.Kmem + ((size_t)b * p.T + (t1 < p.T ? t1 : t0)) * 512);
         float4 k0[4], k1[4];
-        if (t0 == warp) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { k0[i] = kpre0[i]; k1[i] = kpre1[i]; }
-        } else {
-            const float4* kr0 = reinterpret_cast<const float4*>(p.Kmem + ((size_t)b * p.T + t0) * 512);
-            const float4* kr1 = reinterpret_cast<const float4*>(p.Kmem + ((size_t)b * p.T + (t1 < p.T ? t1 : t0)) * 512);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { k0[i] = __ldg(kr0 + lane + 32 * i); k1[i] = __ldg(kr1 + lane + 32 * i); }
-        }
+        for (int i = 0; i < 4; ++i) { k0[i] = __ldg(kr0 + lane + 32 * i); k1[i] = __ldg(kr1 + lane + 32 * i); }
         float a0 = 0.f, a1 = 0.f;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -226,12 +211,23 @@ __device__ __forceinline__ void dec_run_pass(const DecodeParams& p, const DecPas
     for (int b0 = 0; b0 < p.Bpad; b0 += MV_CLIPS) {
         float acc[R][2];
         mv_zero<R>(acc);
-        if (ps.Ke > 0) mv_accumulate<R>(W, ps.ldw, ps.wcol_e, xe, ps.Ke, p.Bpad, b0, acc);
-        sync.wait();
-        mv_accumulate<R>(W, ps.ldw, ps.wcol_l, xl, ps.Kl, p.Bpad, b0, acc);
-        float v = mv_reduce<R, (R == 16 ? DEC_RED_ROWS : R)>(acc, sm.red);
+        const bool narrow = p.B <= 2;                        // CTA-uniform: single-clip inference uses the k-split lane mapping
+        if (narrow) {
+            if (ps.Ke > 0) mv_accumulate_narrow<R>(W, ps.ldw, ps.wcol_e, xe, ps.Ke, p.Bpad, acc);
+            sync.wait();
+            mv_accumulate_narrow<R>(W, ps.ldw, ps.wcol_l, xl, ps.Kl, p.Bpad, acc);
+        } else {
+            if (ps.Ke > 0) mv_accumulate<R>(W, ps.ldw, ps.wcol_e, xe, ps.Ke, p.Bpad, b0, acc);
+            sync.wait();
+            mv_accumulate<R>(W, ps.ldw, ps.wcol_l, xl, ps.Kl, p.Bpad, b0, acc);
+        }
         const int r = tid >> 5, bb = tid & 31, b = b0 + bb;
         const bool live = (tid < R * MV_CLIPS) && (b < p.B);
+        const bool gate_pass = (ps.op[0] == OP_GATE0 || ps.op[0] == OP_GATE1);      // CTA-uniform
+        float c_prev = 0.f;                                  // own cell state: fetched before the reduction to hide its latency
+        if (gate_pass && live && (r & 3) == 0 && ps.idx[r] >= 0)
+            c_prev = p.Cst[(size_t)((ps.op[0] == OP_GATE1 ? 512 : 0) + ps.idx[r]) * p.Bpad + b];
+        float v = narrow ? mv_reduce_narrow<R>(acc, sm.red) : mv_reduce<R, (R == 16 ? DEC_RED_ROWS : R)>(acc, sm.red);
         const int op = live ? ps.op[r] : OP_NONE;
         const int idx = live ? ps.idx[r] : 0;
         if (live) v += ps.bias[r];
@@ -259,7 +255,6 @@ __device__ __forceinline__ void dec_run_pass(const DecodeParams& p, const DecPas
             default: break;
         }
         // LSTM passes: rows are (unit, gate) = (r>>2, r&3); all 16 rows of the pass are gate rows.
-        const bool gate_pass = (ps.op[0] == OP_GATE0 || ps.op[0] == OP_GATE1);      // CTA-uniform
         if (gate_pass && tid < R * MV_CLIPS) sm.gsm[r * MV_CLIPS + bb] = v;
         __syncthreads();
         if (gate_pass) {
@@ -268,7 +263,7 @@ __device__ __forceinline__ void dec_run_pass(const DecodeParams& p, const DecPas
                 const float gi = sm.gsm[(r + 0) * MV_CLIPS + bb], gf = sm.gsm[(r + 1) * MV_CLIPS + bb];
                 const float gg = sm.gsm[(r + 2) * MV_CLIPS + bb], go = sm.gsm[(r + 3) * MV_CLIPS + bb];
                 const size_t si = (size_t)(layer * 512 + idx) * p.Bpad + b;
-                const float c = sigmoidf_acc(gf) * p.Cst[si] + sigmoidf_acc(gi) * tanhf(gg);
+                const float c = sigmoidf_acc(gf) * c_prev + sigmoidf_acc(gi) * tanhf(gg);
                 const float h = sigmoidf_acc(go) * tanhf(c);
                 p.Cst[si] = c;
                 Snew[si] = h;
@@ -336,8 +331,10 @@ __global__ void __launch_bounds__(MV_THREADS, 1) decode_persistent_kernel(const 
             for (int j = 0; j < np; ++j)
                 if (passes[j].stage == stage) dec_dispatch(p, passes[j], sm, sync, step, parity_new);
             if (stage == ST_B) {
-                for (int job = blockIdx.x; job < njobs; job += gridDim.x)
-                    dec_attend(p, sm, sync, job / p.nsplit, job % p.nsplit, step);
+                for (int job = blockIdx.x; job < njobs; job += gridDim.x) {
+                    sync.wait();
+                    dec_attend(p, sm, job / p.nsplit, job % p.nsplit, step);
+                }
             }
             sync.wait();                 // barriers must complete in order even for CTAs idle in this stage
             sync.lap(sync.slot0 + 2);

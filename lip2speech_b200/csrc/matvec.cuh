@@ -140,6 +140,45 @@ __device__ __forceinline__ float mv_reduce(float (&acc)[R][2], float* red) {
     return v;
 }
 
+// ---- narrow variant for B <= 2 (single-clip inference, BASELINE config 1) ---------------------------------------
+// With one or two clips the 16 clip-pair lanes of the wide mapping would multiply padding.  Here all 32 lanes split k
+// instead (lane = k-quad inside a 128-wide group, warp w takes groups w, w+16, ...), each lane keeps R x 2 partials
+// for clips {0,1}, every partial is reduced with warp shuffles and the (at most 16) warp results are summed in smem.
+template <int R>
+__device__ __forceinline__ void mv_accumulate_narrow(const float* __restrict__ Wsm, int ldw, int wcol0,
+                                                     const float* __restrict__ X, int K, int ldb, float (&acc)[R][2]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ngroups = K >> 7;
+    for (int g = warp; g < ngroups; g += MV_WARPS) {
+        const int kb = g * 128 + lane * 4;
+        float2 x[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[i] = ldcg2(X + (size_t)(kb + i) * ldb);
+        mv_group_fma<R>(Wsm + wcol0 + kb, ldw, x, acc);
+    }
+}
+
+// Returns the finished value for (row tid>>5, clip tid&31) in threads with (tid&31) < 2 and tid < R*32; 0 elsewhere.
+template <int R>
+__device__ __forceinline__ float mv_reduce_narrow(float (&acc)[R][2], float* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            float v = warp_sum(acc[r][c]);
+            if (lane == ((2 * r + c) & 31)) red[warp * (2 * R) + 2 * r + c] = v;
+        }
+    __syncthreads();
+    float v = 0.f;
+    const int r = threadIdx.x >> 5, b = threadIdx.x & 31;
+    if (r < R && b < 2) {
+#pragma unroll
+        for (int w = 0; w < MV_WARPS; ++w) v += red[w * (2 * R) + 2 * r + b];
+    }
+    return v;
+}
+
 // Convenience: one- or two-segment pass with a full-size reduction buffer (used by lstm.cuh).
 template <int R>
 __device__ __forceinline__ float mv_pass(const float* __restrict__ Wsm, int ldw,

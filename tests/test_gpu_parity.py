@@ -111,14 +111,18 @@ def test_batch_33_two_clip_groups_vs_oracle(be, O, weights):
 
 
 def test_batch_invariance_full_size(be):
-    """Size-independent property at the bench size (B=32, 300 steps): a clip's mel does not depend on
-    which other clips share the batch — bit-exact."""
+    """Size-independent property at the bench size (B=32, 300 steps): a clip's mel does not depend on which other
+    clips share the batch.  Bit-exact within the batched (wide) lane mapping; the single-clip (narrow, B<=2) mapping
+    sums in a different order, so there the bound is the parity tolerance."""
     visual, face = synth.visual_features(32, 29, seed=5)
     g = synth.gumbel(32, 29, seed=5)
     mel, lengths = be.decoder_infer(visual.cuda(), face[:, 0].cuda(), g.cuda())
-    for i in (0, 17, 31):
+    for lo in (0, 16, 28):                               # 4-clip sub-batches
+        m4, l4 = be.decoder_infer(visual[lo:lo + 4].cuda(), face[lo:lo + 4, 0].cuda(), g[4 * lo:4 * lo + 16].cuda())
+        assert torch.equal(m4, mel[lo:lo + 4]) and torch.equal(l4, lengths[lo:lo + 4])
+    for i in (0, 17, 31):                                # single clips
         m1, l1 = be.decoder_infer(visual[i:i + 1].cuda(), face[i:i + 1, 0].cuda(), g[4 * i:4 * i + 4].cuda())
-        assert torch.equal(m1[0], mel[i]) and int(l1[0]) == int(lengths[i])
+        assert rel_err(m1[0].cpu(), mel[i].cpu()) < TOL and int(l1[0]) == int(lengths[i])
 
 
 def test_stop_token_midway(O, weights):
