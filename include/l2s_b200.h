@@ -72,6 +72,15 @@ int l2s_speaker_fwd(l2s_ctx* ctx, const float* wav, int B, int S, float* emb, in
 int l2s_decoder_infer(l2s_ctx* ctx, const float* visual, const float* spk, const float* gumbel, int B, int T,
                       int steps, float* mel_post, int64_t* lengths, float* attn, void* stream);
 
+/* Decoder.forward in EVAL mode (decoder.py:320-379; the path evaluate.py:38 takes): M = mels.shape[2] steps, teacher
+ * forcing decided by the caller per step (tf_mask[i] = 1: step i consumes the teacher frame — BOS for i = 0, mels[:,:,i-1]
+ * otherwise — exactly the coin flips of decoder.py:355-357; HOST pointer, M bytes).  Outputs (device; any but out_post may
+ * be NULL): out_mel [B,80,M] (pre-postnet), out_post [B,80,M], out_stop [B,M] raw stop logits, out_attn_logits [B,M,T]
+ * PRE-softmax, out_content_dis [B*minT,501].  Train-mode dropout / batch-norm statistics are not implemented. */
+int l2s_decoder_forward(l2s_ctx* ctx, const float* visual, const float* spk, const float* gumbel, const float* mels,
+                        const unsigned char* tf_mask, int B, int T, int M, float* out_mel, float* out_post, float* out_stop,
+                        float* out_attn_logits, float* out_content_dis, void* stream);
+
 /* Postnet.forward in eval mode (decoder.py:143-156): x [B,80,L] -> out [B,80,L]; add_residual=1 returns
  * postnet(x)+x as Decoder.inference does (decoder.py:438-439). */
 int l2s_postnet_fwd(l2s_ctx* ctx, const float* x, int B, int L, float* out, int add_residual, void* stream);

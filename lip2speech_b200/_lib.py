@@ -17,7 +17,7 @@ PART_VIDEO, PART_SPEAKER, PART_DECODER = 1, 2, 4
 PRECISION_FP32, PRECISION_BF16 = 0, 1
 
 EXPORTS = ("l2s_version", "l2s_create", "l2s_destroy", "l2s_last_error", "l2s_bind_weight", "l2s_commit_weights",
-           "l2s_video_fwd", "l2s_speaker_fwd", "l2s_decoder_infer", "l2s_postnet_fwd", "l2s_infer", "l2s_infer_host",
+           "l2s_video_fwd", "l2s_speaker_fwd", "l2s_decoder_infer", "l2s_decoder_forward", "l2s_postnet_fwd", "l2s_infer", "l2s_infer_host",
            "l2s_launch_count", "l2s_debug_read", "l2s_set_profiling", "l2s_span_ms")
 
 _lib = None
@@ -44,6 +44,7 @@ def load() -> C.CDLL:
         lib.l2s_video_fwd.argtypes = [vp, fp, i, i, i, i, fp, i, vp]
         lib.l2s_speaker_fwd.argtypes = [vp, fp, i, i, fp, i, vp]
         lib.l2s_decoder_infer.argtypes = [vp, fp, fp, fp, i, i, i, fp, vp, fp, vp]
+        lib.l2s_decoder_forward.argtypes = [vp, fp, fp, fp, fp, vp, i, i, i, fp, fp, fp, fp, fp, vp]
         lib.l2s_postnet_fwd.argtypes = [vp, fp, i, i, fp, i, vp]
         lib.l2s_infer.argtypes = [vp, fp, fp, fp, i, i, i, i, i, i, fp, vp, i, vp]
         lib.l2s_infer_host.argtypes = [vp, fp, fp, fp, i, i, i, i, i, i, fp, vp, i]
@@ -147,6 +148,26 @@ class Backend:
                                                C.c_void_p(lengths.data_ptr()), attn.data_ptr() if attn is not None else None,
                                                self._stream()), "l2s_decoder_infer")
         return (mel, lengths, attn) if return_attention else (mel, lengths)
+
+    def decoder_forward(self, visual, spk, gumbel, mels, tf_mask):
+        """Decoder.forward, eval flavour.  tf_mask: host bool/uint8 tensor [M]."""
+        visual, spk, gumbel, mels = (_f32c(t, self.device) for t in (visual, spk, gumbel, mels))
+        B, T, _ = visual.shape
+        M = mels.shape[2]
+        min_t = min([T] + [(T - k) // k + 1 for k in (1, 3, 5, 7)])
+        mask = tf_mask.to(torch.uint8).cpu().contiguous()
+        assert mask.numel() == M and mels.shape[:2] == (B, 80)
+        out_mel = torch.empty(B, 80, M, device=self.device)
+        out_post = torch.empty(B, 80, M, device=self.device)
+        out_stop = torch.empty(B, M, 1, device=self.device)
+        out_attn = torch.empty(B, M, T, device=self.device)
+        out_dis = torch.empty(B * min_t, 501, device=self.device)
+        self._check(self.lib.l2s_decoder_forward(self.h, visual.data_ptr(), spk.data_ptr(), gumbel.data_ptr(), mels.data_ptr(),
+                                                 C.c_void_p(mask.data_ptr()), B, T, M, out_mel.data_ptr(), out_post.data_ptr(),
+                                                 out_stop.data_ptr(), out_attn.data_ptr(), out_dis.data_ptr(), self._stream()),
+                    "l2s_decoder_forward")
+        torch.cuda.current_stream(self.device).synchronize()      # `mask` (host) must outlive the async copy
+        return out_mel, out_post, out_stop, out_attn, out_dis
 
     def postnet_fwd(self, x: torch.Tensor, add_residual: bool = False) -> torch.Tensor:
         x = _f32c(x, self.device)

@@ -373,8 +373,45 @@ static void postnet_rows(Context& c, const float* x_rows /*[B*L][80]*/, int B, i
 // ------------------------------------------------------------------------------------------------
 // decoder
 // ------------------------------------------------------------------------------------------------
-static void decoder_infer(Context& c, const float* visual, const float* spk, const float* gumbel, int B, int T, int steps,
-                          float* mel_post, int64_t* lengths, float* attn, cudaStream_t s) {
+struct DecoderForwardIO {          // Decoder.forward flavour (eval mode); null pointer = plain inference
+    const float* mels = nullptr;                 // [B][80][M] teacher frames
+    const unsigned char* tf_mask = nullptr;      // [M] host bytes
+    float* out_mel = nullptr;                    // [B][80][M] decoder outputs before the postnet
+    float* out_stop = nullptr;                   // [B][M]
+    float* out_attn_logits = nullptr;            // [B][M][T]
+    float* out_content_dis = nullptr;            // [B*minT][501]
+};
+
+// rows [B][L][C] -> x [B][C][L]
+__global__ void rows_to_bcl_kernel(const float* __restrict__ rows, float* __restrict__ x, int B, int C, int L) {
+    const size_t total = (size_t)B * C * L;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int t = i % L; size_t r = i / L;
+        int ch = r % C; int b = r / C;
+        x[i] = rows[((size_t)b * L + t) * C + ch];
+    }
+}
+// teacher rows: tr[(b*M + i)][:] = (i == 0) ? BOS : mels[b][:][i-1]      (decoder.py:343: cat([BOS, mels]))
+__global__ void teacher_rows_kernel(const float* __restrict__ mels, const float* __restrict__ bos, float* __restrict__ tr, int B, int M) {
+    const size_t total = (size_t)B * M * 80;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int ch = i % 80; size_t r = i / 80;
+        int st = r % M; int b = r / M;
+        tr[i] = st == 0 ? bos[ch] : mels[((size_t)b * 80 + ch) * M + st - 1];
+    }
+}
+// p1t[(i*256 + f)*Bpad + b] = rows[(b*M + i)*256 + f]
+__global__ void p1_teacher_fm_kernel(const float* __restrict__ rows, float* __restrict__ p1t, int B, int Bpad, int M) {
+    const size_t total = (size_t)M * 256 * Bpad;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int b = i % Bpad; size_t r = i / Bpad;
+        int f = r % 256; int st = r / 256;
+        p1t[i] = b < B ? rows[((size_t)b * M + st) * 256 + f] : 0.f;
+    }
+}
+
+static void decoder_run(Context& c, const float* visual, const float* spk, const float* gumbel, int B, int T, int steps,
+                        float* mel_post, int64_t* lengths, float* attn, const DecoderForwardIO& fw, cudaStream_t s) {
     if (B <= 0 || T < 7 || T > 300 || steps <= 0 || steps > 300) throw L2sError(L2S_ERR_INVALID, "decoder_infer: need 7<=T<=300, 1<=steps<=300 (pos_table has 300 rows)");
     if (!gumbel) throw L2sError(L2S_ERR_INVALID, "decoder_infer: gumbel noise tensor is required");
     const int M = B * T, Bpad = round_up(B, 32);
@@ -509,7 +546,7 @@ static void decoder_infer(Context& c, const float* visual, const float* spk, con
     linear(c, cw, 256, "d.cloc0", c.dev("d.cloc0.b"), cu, 256, Mc, 256, 256, ACT_SILU, nullptr, s, "location_fc.0");
     linear(c, cu, 256, "d.cloc2", c.dev("d.cloc2.b"), cv2, 256, Mc, 256, 256, ACT_SILU, nullptr, s, "location_fc.2");
     linear(c, cv2, 256, "d.cloc4", c.dev("d.cloc4.b"), clog, 501, Mc, 501, 256, ACT_SILU, nullptr, s, "location_fc.4");
-    gumbel_value_kernel<<<Mc, 256, 501 * sizeof(float), s>>>(clog, gumbel, 1.0f / 0.1f, c.dev("d.cemb"), cval, nullptr, 501);
+    gumbel_value_kernel<<<Mc, 256, 501 * sizeof(float), s>>>(clog, gumbel, 1.0f / 0.1f, c.dev("d.cemb"), cval, fw.out_content_dis, 501);
     check_launch(c, "gumbel value");
     // ---- stop-token constant, initial state --------------------------------------------------------
     float* stopc = c.fbuf("ws.d.stopc", (size_t)B);
@@ -536,6 +573,21 @@ static void decoder_infer(Context& c, const float* visual, const float* spk, con
         dp.Kmem = Kmem; dp.Vmem = Vmem; dp.ckey = ckey; dp.cval = cval; dp.stop_const = stopc; dp.pos = pos;
         dp.temp = c.W("decoder.temperature").f[0]; dp.ctemp = c.W("decoder.content.temperature").f[0];
         dp.outputs = outputs; dp.lengths = reinterpret_cast<long long*>(lengths); dp.attn = attn;
+        if (fw.mels) {
+            // teacher frames -> prenet layer 1 for every step (one GEMM), kept feature-major for the step kernel
+            float* tr = c.fbuf("ws.d.trows", (size_t)B * steps * 80);
+            teacher_rows_kernel<<<ew_grid((size_t)B * steps * 80), 256, 0, s>>>(fw.mels, c.dev("d.bos"), tr, B, steps);
+            check_launch(c, "teacher rows");
+            float* p1r = c.fbuf("ws.d.p1rows", (size_t)B * steps * 256);
+            linear(c, tr, 80, "d.prenet0", c.dev("d.prenet0.b"), p1r, 256, B * steps, 256, 80, ACT_PSINE, c.dev("d.prenet0.psw"), s, "prenet.0 (teacher)");
+            float* p1t = c.fbuf("ws.d.p1t", (size_t)steps * 256 * Bpad);
+            p1_teacher_fm_kernel<<<ew_grid((size_t)steps * 256 * Bpad), 256, 0, s>>>(p1r, p1t, B, Bpad, steps);
+            check_launch(c, "p1 teacher fm");
+            unsigned char* dmask = static_cast<unsigned char*>(c.buf("ws.d.tfmask", 512));
+            L2S_CUDA(cudaMemcpyAsync(dmask, fw.tf_mask, steps, cudaMemcpyHostToDevice, s));
+            dp.tf_mask = dmask; dp.p1_teacher = p1t;
+        }
+        dp.stop_out = fw.out_stop; dp.attn_logits = fw.out_attn_logits;
         dp.B = B; dp.Bpad = Bpad; dp.T = T; dp.minT = minT; dp.steps = steps;
         unsigned* bar = static_cast<unsigned*>(c.buf("ws.barrier", 256));
         L2S_CUDA(cudaMemsetAsync(bar, 0, 4, s));
@@ -554,7 +606,16 @@ static void decoder_infer(Context& c, const float* visual, const float* spk, con
     // ---- postnet + residual (decoder.py:437-439) --------------------------------------------------
     postnet_rows(c, outputs, B, steps, mel_post, true, s);
     c.span_end("postnet", s);
+    if (fw.out_mel) {
+        rows_to_bcl_kernel<<<ew_grid((size_t)B * steps * 80), 256, 0, s>>>(outputs, fw.out_mel, B, 80, steps);
+        check_launch(c, "outputs -> [B,80,M]");
+    }
     c.meta["dbg.B"] = B; c.meta["dbg.T"] = T; c.meta["dbg.minT"] = minT; c.meta["dbg.steps"] = steps;
+}
+
+static void decoder_infer(Context& c, const float* visual, const float* spk, const float* gumbel, int B, int T, int steps,
+                          float* mel_post, int64_t* lengths, float* attn, cudaStream_t s) {
+    decoder_run(c, visual, spk, gumbel, B, T, steps, mel_post, lengths, attn, DecoderForwardIO{}, s);
 }
 
 // visual[b,t,:] = [feat[b,t,0:768], emb[b,0:256]]   (model.py:52-55)
@@ -700,6 +761,21 @@ int l2s_decoder_infer(l2s_ctx* ctx, const float* visual, const float* spk, const
     API_BEGIN
     need(ctx, L2S_PART_DECODER, "decoder_infer");
     decoder_infer(ctx->c, visual, spk, gumbel, B, T, steps, mel_post, lengths, attn, (cudaStream_t)stream);
+    API_END(ctx)
+}
+
+int l2s_decoder_forward(l2s_ctx* ctx, const float* visual, const float* spk, const float* gumbel, const float* mels,
+                        const unsigned char* tf_mask, int B, int T, int M, float* out_mel, float* out_post, float* out_stop,
+                        float* out_attn_logits, float* out_content_dis, void* stream) {
+    if (!ctx) return L2S_ERR_INVALID;
+    API_BEGIN
+    need(ctx, L2S_PART_DECODER, "decoder_forward");
+    if (!mels || !tf_mask || !out_post) throw L2sError(L2S_ERR_INVALID, "decoder_forward: mels, tf_mask and out_post are required");
+    DecoderForwardIO fw;
+    fw.mels = mels; fw.tf_mask = tf_mask; fw.out_mel = out_mel; fw.out_stop = out_stop;
+    fw.out_attn_logits = out_attn_logits; fw.out_content_dis = out_content_dis;
+    int64_t* lens = static_cast<int64_t*>(ctx->c.buf("ws.d.fwlens", (size_t)B * sizeof(int64_t)));
+    decoder_run(ctx->c, visual, spk, gumbel, B, T, M, out_post, lens, nullptr, fw, (cudaStream_t)stream);
     API_END(ctx)
 }
 

@@ -67,6 +67,11 @@ struct DecodeParams {
     int nsplit;                   // CTAs cooperating on one clip's attention (1, 2 or 4)
     unsigned* barrier;
     float* timing;                // optional [grid][DEC_TIMING_SLOTS] SM cycles
+    // Decoder.forward flavour (decoder.py:353-375): teacher forcing and per-step logits; all null for inference
+    const unsigned char* tf_mask; // [steps]: 1 = step i consumes the teacher frame (BOS for i=0, mels[:, i-1] otherwise)
+    const float* p1_teacher;      // [steps][256][Bpad] prenet layer-1 output of the teacher frames
+    float* stop_out;              // [B][steps] raw stop logits
+    float* attn_logits;           // [B][steps][T] PRE-softmax attention logits
 };
 
 struct DecSmem {
@@ -146,6 +151,8 @@ __device__ void dec_attend(const DecodeParams& p, const DecSmem& sm, int b, int 
     }
     __syncthreads();
     if (warp == 0) {
+        if (p.attn_logits && part == 0)
+            for (int t = lane; t < p.T; t += 32) p.attn_logits[((size_t)b * p.steps + step) * p.T + t] = sm.sc[t];
         float mx = -INFINITY;
         for (int t = lane; t < p.T; t += 32) mx = fmaxf(mx, sm.sc[t]);
         mx = warp_max(mx);
@@ -235,11 +242,18 @@ __device__ __forceinline__ void dec_run_pass(const DecodeParams& p, const DecPas
             case OP_FC:
                 if (step >= 0) p.outputs[((size_t)b * p.steps + step) * 80 + idx] = v;
                 break;
-            case OP_P1:
-                p.P1[(size_t)idx * p.Bpad + b] = (step >= 0) ? sinf(v) * ps.aux[r] : ps.aux2[r];
-                break;
+            case OP_P1: {
+                float p1 = (step >= 0) ? sinf(v) * ps.aux[r] : ps.aux2[r];
+                if (p.tf_mask && step + 1 < p.steps && p.tf_mask[step + 1])      // next step is teacher-forced
+                    p1 = p.p1_teacher[((size_t)(step + 1) * 256 + idx) * p.Bpad + b];
+                p.P1[(size_t)idx * p.Bpad + b] = p1;
+            } break;
             case OP_STOP:
-                if (step >= 0 && (v + p.stop_const[b]) > 0.f && p.lengths[b] == (long long)p.steps) p.lengths[b] = step + 1;
+                if (step >= 0) {
+                    const float logit = v + p.stop_const[b];
+                    if (p.stop_out) p.stop_out[(size_t)b * p.steps + step] = logit;
+                    if (logit > 0.f && p.lengths[b] == (long long)p.steps) p.lengths[b] = step + 1;
+                }
                 break;
             case OP_Q: {
                 float q = sinf(v) * ps.aux[r];

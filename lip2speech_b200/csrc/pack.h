@@ -491,6 +491,8 @@ inline void pack_decoder(Context& c) {
     up_lin(p + "content.location_fc.0", "d.cloc0"); up_lin(p + "content.location_fc.2", "d.cloc2"); up_lin(p + "content.location_fc.4", "d.cloc4");
     up_lin(p + "content.K.0", "d.ck0"); up_lin(p + "content.K.2", "d.ck2");
     c.upload("d.cemb", c.W(p + "content.word_embeddings").f);
+    c.upload("d.bos", c.W(p + "BOS").f);
+    up_lin(p + "prenet.0.linear_layer", "d.prenet0"); c.upload("d.prenet0.psw", c.W(p + "prenet.1.w").f);   // teacher-forced steps
     c.upload("d.pos", c.W(p + "positional_encodings.pos_table").f);
     c.meta["d.temp_bits"] = 0;
     pack_decode_program(c);

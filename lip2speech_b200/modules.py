@@ -123,9 +123,31 @@ class Decoder(ParamTree):
         """Postnet.forward (eval): x [B,80,L] -> [B,80,L] (reference decoder.py:143-156)."""
         return self._sync().postnet_fwd(x, add_residual=False)
 
-    def forward(self, encoder_outputs, face_features, mels, text_lengths, output_lengths, tf_ratio):
-        raise NotImplementedError("Decoder.forward (teacher-forced train/eval path, decoder.py:320-379) is not built yet: "
-                                  "SURVEY.md §8 row a10 train flavour / §7 step 7; use .inference()")
+    @staticmethod
+    def teacher_forcing_mask(tf_ratio: float, steps: int) -> torch.Tensor:
+        """Per-step teacher-forcing decisions exactly as decoder.py:355-357 makes them: one `torch.rand(1)` from the global
+        CPU generator per step; teacher input when rand > tf_ratio and fewer than int(tf_ratio*steps) were consumed."""
+        mask, consumed = [], 0
+        for _ in range(steps):
+            use = bool(torch.rand(1) > tf_ratio) and consumed < int(tf_ratio * steps)
+            consumed += int(use)
+            mask.append(use)
+        return torch.tensor(mask, dtype=torch.bool)
+
+    def forward(self, encoder_outputs, face_features, mels, text_lengths, output_lengths, tf_ratio, gumbel_noise=None):
+        """Decoder.forward (decoder.py:320-379) in EVAL mode — the path evaluate.py:38 takes.  Returns
+        [outputs [B,80,M], post [B,80,M], stop_logits [B,M,1], face [B,256], attention logits (pre-softmax) [B,M,T],
+        content_dis [B*minT,501]].  Train mode (dropouts, BN batch statistics, autograd) is not built: it raises."""
+        if self.training:
+            raise NotImplementedError("Decoder.forward in train mode (dropout, autograd; SURVEY.md §8 rows a10-train/a13) is not "
+                                      "built yet; call .eval() for the evaluate.py path")
+        be = self._sync()
+        B, T = encoder_outputs.shape[:2]
+        if gumbel_noise is None:
+            gumbel_noise = self.draw_gumbel(B, T, encoder_outputs.device)      # content.encode draws first (decoder.py:340)
+        mask = self.teacher_forcing_mask(float(tf_ratio), mels.shape[2])
+        out_mel, out_post, out_stop, out_attn, out_dis = be.decoder_forward(encoder_outputs, face_features[:, 0], gumbel_noise, mels, mask)
+        return [out_mel, out_post, out_stop, face_features[:, 0], out_attn, out_dis]
 
 
 class Lip2Speech(nn.Module):
@@ -155,7 +177,20 @@ class Lip2Speech(nn.Module):
             return self.decoder.inference(visual_features, face_features, gumbel_noise=gumbel_noise, **kwargs)
 
     def forward(self, video_frames, face_frames, audio_frames, melspecs, video_lengths, audio_lengths, melspec_lengths, tf_ratio):
-        raise NotImplementedError("Lip2Speech.forward (train path, model.py:23-40) is not built yet; use .inference()")
+        """model.py:23-40 in eval mode (what evaluate.py:38 calls).  The face embedding comes from the attached `vgg_face`
+        module (third-party InceptionResnetV1, out of scope) exactly as in the reference."""
+        if self.training:
+            raise NotImplementedError("Lip2Speech.forward in train mode is not built yet (SURVEY.md §8 rows a10-train/a13)")
+        if not hasattr(self, "vgg_face"):
+            raise RuntimeError("Lip2Speech.forward needs the vgg_face module (model.py:31); attach the reference's FaceRecognizer")
+        with torch.no_grad():
+            video_features = self.encoder(video_frames)                    # F.dropout(..., training=False) is the identity
+            face_features = self.vgg_face.inference(face_frames[:, 0, :, :, :])
+            N, T, C = video_features.shape
+            face_features = face_features.unsqueeze(1).repeat(1, T, 1)
+            visual_features = torch.cat([video_features, face_features], dim=2)
+            outputs = self.decoder(visual_features, face_features, melspecs, video_lengths, melspec_lengths, tf_ratio)
+        return outputs + [video_lengths]
 
 
 def get_network(mode: str, seed=None) -> Lip2Speech:

@@ -260,6 +260,59 @@ def decoder_steps(sd, pre, steps, p="decoder.", return_attention=False):
     return outputs, lengths, (torch.cat(attn, 1) if return_attention else None)
 
 
+def teacher_forcing_mask(tf_ratio: float, steps: int, generator=None):
+    """The per-step teacher-forcing decisions of Decoder.forward (decoder.py:355-357): one `torch.rand(1)` draw from the
+    CPU generator per step; teacher input is used when rand > tf_ratio AND fewer than int(tf_ratio*steps) were consumed."""
+    mask, consumed = [], 0
+    for _ in range(steps):
+        use = bool(torch.rand(1, generator=generator) > tf_ratio) and consumed < int(tf_ratio * steps)
+        consumed += int(use)
+        mask.append(use)
+    return torch.tensor(mask, dtype=torch.bool)
+
+
+def decoder_forward(sd, enc_in, face_tiled, mels, tf_mask, gumbel_noise, p="decoder."):
+    """Decoder.forward in EVAL mode (decoder.py:320-379; dropouts inactive), teacher-forcing decisions given explicitly.
+    mels [B,80,M].  Returns [outputs [B,80,M], post [B,80,M], stop_logits [B,M,1], face [B,256],
+    attention logits (PRE-softmax) [B,M,T], content_dis [B*minT,501]]."""
+    pre = decoder_preloop(sd, enc_in, face_tiled[:, 0], gumbel_noise, p)
+    b, m = mels.shape[0], mels.shape[2]
+    hidden = pre["hidden"]
+    h = [hidden[0], hidden[1]]
+    c = [torch.zeros_like(h[0]), torch.zeros_like(h[0])]
+    k, v, ckey, cval, enc_cell = pre["k"], pre["v"], pre["ckey"], pre["cval"], pre["enc_cell"]
+    pos = sd[p + "positional_encodings.pos_table"][0]
+    temp, ctemp = sd[p + "temperature"], sd[p + "content.temperature"]
+    ys = sd[p + "BOS"].reshape(1, -1).repeat(b, 1)
+    teacher = torch.cat([ys.unsqueeze(1), mels.permute(0, 2, 1)], dim=1)       # [B, M+1, 80]
+    outputs = torch.zeros(b, m, ys.shape[1])
+    stops = torch.zeros(b, m, 1)
+    attn = []
+    wl = [(sd[f"{p}decoder_rnn.weight_ih_l{l}"], sd[f"{p}decoder_rnn.weight_hh_l{l}"],
+           sd[f"{p}decoder_rnn.bias_ih_l{l}"], sd[f"{p}decoder_rnn.bias_hh_l{l}"]) for l in range(2)]
+    for i in range(m):
+        if bool(tf_mask[i]):
+            ys = teacher[:, i]
+        y = psine(_lin(sd, p + "prenet.0.linear_layer", ys), sd[p + "prenet.1.w"])
+        y = psine(_lin(sd, p + "prenet.3.linear_layer", y), sd[p + "prenet.4.w"])
+        q = psine(_lin(sd, p + "Q.0.linear_layer", torch.cat(h, 1)), sd[p + "Q.1.w"]) + pos[i]
+        a = torch.bmm((q * temp).unsqueeze(1), k)                                  # logits [B,1,T] (stored pre-softmax, 364)
+        attn.append(a)
+        o = _lin(sd, p + "attention_proj.linear_layer", torch.bmm(torch.softmax(a, dim=-1), v).squeeze(1))
+        y = y + o
+        cq = F.silu(_lin(sd, p + "content.Q.0", torch.cat(c, 1))).unsqueeze(1)
+        co = torch.bmm(torch.softmax(torch.bmm(cq * ctemp, ckey), dim=-1), cval).squeeze(1)
+        x = torch.cat([co, y], -1)
+        h[0], c[0] = lstm_cell(x, h[0], c[0], *wl[0])
+        h[1], c[1] = lstm_cell(h[0], h[1], c[1], *wl[1])
+        ys = _lin(sd, p + "fc_out.linear_layer", h[1])
+        outputs[:, i] = ys
+        stops[:, i] = _lin(sd, p + "stop_token_layer.linear_layer", torch.cat([h[1], enc_cell], 1))
+    outputs = outputs.permute(0, 2, 1)
+    post = postnet(sd, outputs, p + "postnet.") + outputs
+    return [outputs, post, stops, face_tiled[:, 0], torch.cat(attn, 1), pre["cdis"]]
+
+
 def decoder_inference(sd, enc_in, face_tiled, gumbel_noise, steps=300, return_attention=False, p="decoder."):
     """Decoder.inference (decoder.py:382-444).  enc_in [B,T,1024]; face_tiled [B,T,256] (only
     [:,0] is used, line 385).  Returns mel_post [B,80,steps], lengths [B] (, attn [B,steps,T])."""

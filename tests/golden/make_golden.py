@@ -126,6 +126,18 @@ def main():
     # --- case F: speaker encoder on a longer utterance (S=48000 -> 301 frames) ---------------
     out["F_spk_raw"] = spk(synth.wav(1, 48000, seed=9))
 
+    # --- case G: Decoder.forward in eval mode (evaluate.py path), tf_ratio 0.5 and 1.0, B=2, M=24 ---------------
+    visual, face = synth.visual_features(2, 29, seed=11)
+    g = synth.gumbel(2, 29, seed=11)
+    mels = synth.mel_like(2, 24, seed=11)
+    lens = torch.full((2,), 29, dtype=torch.long)
+    for name, tf in (("G5", 0.5), ("G1", 1.0)):
+        torch.manual_seed(4321)                       # the per-step torch.rand(1) coin of decoder.py:355 uses the CPU generator
+        with ExplicitGumbel(g):
+            o = dec(visual, face, mels, lens, lens, tf)
+        out[name + "_outputs"], out[name + "_post"], out[name + "_stop"] = o[0], o[1], o[2]
+        out[name + "_attn_logits"], out[name + "_cdis"] = o[4], o[5]
+
     # --- A.7 check: seeded, unpatched reference == explicit-noise reference ------------------
     visual, face = synth.visual_features(2, 29, seed=3)
     torch.manual_seed(99)

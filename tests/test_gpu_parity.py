@@ -202,6 +202,31 @@ def test_module_mirror_matches_backend(be, weights, golden):
     assert torch.equal(m1, m2)
 
 
+def test_decoder_forward_eval(be, O, golden, weights):
+    """Decoder.forward in eval mode (evaluate.py path) against the reference goldens and the oracle, with and without
+    teacher-forced steps; the mirror module reproduces the reference's seeded coin flips."""
+    from lip2speech_b200 import modules
+    visual, face = synth.visual_features(2, 29, seed=11)
+    g = synth.gumbel(2, 29, seed=11)
+    mels = synth.mel_like(2, 24, seed=11)
+    dec = modules.Decoder()
+    dec.load_state_dict({k[len("decoder."):]: v for k, v in weights.items() if k.startswith("decoder.")}, strict=True)
+    dec = dec.cuda().eval()
+    lens = torch.full((2,), 29, dtype=torch.long)
+    for name, tf in (("G5", 0.5), ("G1", 1.0)):
+        torch.manual_seed(4321)
+        o = dec(visual.cuda(), face.cuda(), mels.cuda(), lens, lens, tf, gumbel_noise=g.cuda())
+        assert rel_err(o[0].cpu(), golden[name + "_outputs"]) < TOL
+        assert rel_err(o[1].cpu(), golden[name + "_post"]) < TOL
+        assert rel_err(o[2].cpu(), golden[name + "_stop"]) < TOL
+        assert rel_err(o[4].cpu(), golden[name + "_attn_logits"]) < TOL
+        assert rel_err(o[5].cpu(), golden[name + "_cdis"]) < TOL
+        assert torch.equal(o[3].cpu(), face[:, 0])
+    dec.train()
+    with pytest.raises(NotImplementedError):
+        dec(visual.cuda(), face.cuda(), mels.cuda(), lens, lens, 0.5)
+
+
 def test_unsupported_shapes_are_errors(be):
     visual, face = synth.visual_features(1, 29)
     with pytest.raises(RuntimeError):

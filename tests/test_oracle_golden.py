@@ -79,3 +79,22 @@ def test_lstm_op_matches_explicit_cell(weights):
 
 def test_min_t():
     assert spec.content_min_t(29) == 4 and spec.content_min_t(75) == 10
+
+
+def test_decoder_forward_eval(golden, weights):
+    """Decoder.forward in eval mode (evaluate.py path): explicit teacher-forcing mask == the reference's seeded coin flips."""
+    visual, face = synth.visual_features(2, 29, seed=11)
+    g = synth.gumbel(2, 29, seed=11)
+    mels = synth.mel_like(2, 24, seed=11)
+    for name, tf in (("G5", 0.5), ("G1", 1.0)):
+        mask = O.teacher_forcing_mask(tf, 24, torch.Generator().manual_seed(4321))
+        if tf == 1.0:
+            assert not mask.any()
+        else:
+            assert mask.any()
+        o = O.decoder_forward(weights, visual, face, mels, mask, g)
+        assert rel_err(o[0], golden[name + "_outputs"]) < 1e-4
+        assert rel_err(o[1], golden[name + "_post"]) < 1e-4
+        assert rel_err(o[2], golden[name + "_stop"]) < 1e-4
+        assert rel_err(o[4], golden[name + "_attn_logits"]) < 1e-4
+        assert rel_err(o[5], golden[name + "_cdis"]) < 1e-4
