@@ -4,6 +4,7 @@
 
 #include "context.h"
 #include "decode.cuh"
+#include "decode3.cuh"
 #include "gemm.cuh"
 #include "lstm.cuh"
 #include "misc.cuh"
@@ -593,13 +594,39 @@ static void decoder_run(Context& c, const float* visual, const float* spk, const
         L2S_CUDA(cudaMemsetAsync(bar, 0, 4, s));
         dp.barrier = bar;
         dp.timing = c.profiling ? c.fbuf("ws.d.timing", (size_t)c.num_sms * DEC_TIMING_SLOTS) : nullptr;
-        const size_t smem = (size_t)c.meta.at("d.step.smem");
-        L2S_CUDA(cudaFuncSetAttribute(decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        void* args[] = {&dp};
         c.span_end("preloop", s);
-        c.span_begin("decode_loop", s);
-        L2S_CUDA(cudaLaunchCooperativeKernel((void*)decode_persistent_kernel, dim3(c.num_sms), dim3(MV_THREADS), args, smem, s));
-        c.span_end("decode_loop", s);
+        // 8 < B <= 32: stage-pipelined kernel (decode3.cuh); otherwise the row-partitioned kernel (decode.cuh)
+        const bool pipelined = c.use_dec3 && B > D3_CG && B <= D3_CG * D3_NG && c.meta.at("d.step3.ok") == 1;
+        c.meta["dbg.dec3"] = pipelined ? 1 : 0;
+        if (pipelined) {
+            Decode3Params q{};
+            dp.nsplit = D3_NSPLIT;
+            // group-major recurrent state for the 8-clip tensor-core passes (same sizes as the feature-major buffers)
+            float* S3 = c.fbuf("ws.d.S3", 2 * 2 * plane);
+            fm_to_group_major_kernel<<<ew_grid(2 * plane), 256, 0, s>>>(S, S3, 1024, Bpad);
+            check_launch(c, "state -> group-major");
+            dp.S = S3;
+            q.d = dp;
+            q.kv_smem = (size_t)(512 + 320 + 256 + 32) + (size_t)2 * T * 768 <= (size_t)c.meta.at("d.step3.wimg_floats") ? 1 : 0;
+            q.passes = reinterpret_cast<const Dec3Pass*>(c.dev("d.step3.passes"));
+            q.role = reinterpret_cast<const int*>(c.dev("d.step3.role"));
+            q.job = reinterpret_cast<const int*>(c.dev("d.step3.job"));
+            q.wimg = c.dev("d.step3.wimg"); q.wimg_floats = (int)c.meta.at("d.step3.wimg_floats");
+            q.timing = c.profiling ? c.fbuf("ws.d.timing3", (size_t)c.num_sms * D3_TIMING_SLOTS) : nullptr;
+            const size_t smem = (size_t)c.meta.at("d.step3.smem");
+            L2S_CUDA(cudaFuncSetAttribute(decode3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            void* args[] = {&q};
+            c.span_begin("decode_loop", s);
+            L2S_CUDA(cudaLaunchCooperativeKernel((void*)decode3_kernel, dim3(c.num_sms), dim3(MV_THREADS), args, smem, s));
+            c.span_end("decode_loop", s);
+        } else {
+            const size_t smem = (size_t)c.meta.at("d.step.smem");
+            L2S_CUDA(cudaFuncSetAttribute(decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            void* args[] = {&dp};
+            c.span_begin("decode_loop", s);
+            L2S_CUDA(cudaLaunchCooperativeKernel((void*)decode_persistent_kernel, dim3(c.num_sms), dim3(MV_THREADS), args, smem, s));
+            c.span_end("decode_loop", s);
+        }
         c.launches++;
     }
     c.span_begin("postnet", s);
@@ -683,6 +710,7 @@ int l2s_create(l2s_ctx** out, int device) {
     ctx->c.num_sms = prop.multiProcessorCount;
     ctx->c.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     if (const char* e = getenv("L2S_TC")) ctx->c.use_tc = (e[0] != '0');
+    if (const char* e = getenv("L2S_DEC3")) ctx->c.use_dec3 = (e[0] != '0');
     *out = ctx;
     return L2S_OK;
 }
@@ -854,6 +882,7 @@ int64_t l2s_debug_read(l2s_ctx* ctx, const char* name, float* out, int64_t n) {
         {"dec.ckey", "ws.d.ckey", B * minT * 256}, {"dec.cval", "ws.d.cval", B * minT * 256},
         {"dec.outputs", "ws.d.outputs", B * steps * 80}, {"dec.clog", "ws.d.clog", B * minT * 501},
         {"dec.timing", "ws.d.timing", (int64_t)c.num_sms * DEC_TIMING_SLOTS},
+        {"dec.timing3", "ws.d.timing3", (int64_t)c.num_sms * D3_TIMING_SLOTS},
     };
     for (auto& t : tab) {
         if (std::strcmp(t.name, name) == 0) {

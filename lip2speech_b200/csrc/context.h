@@ -44,6 +44,7 @@ struct Context {
     std::map<std::string, int64_t> meta;      // small integers produced by packing (sizes, counts)
     int64_t launches = 0;
     int committed = 0;
+    bool use_dec3 = true;                     // stage-pipelined decode kernel for 8 < B <= 32 (L2S_DEC3=0: row-partitioned kernel for every B)
     bool use_tc = true;                       // tcgen05 GEMM path (L2S_TC=0 selects the exact-fp32 SIMT GEMMs for debugging)
     // optional stage timing (CUDA events on the caller's stream), enabled by l2s_set_profiling
     bool profiling = false;

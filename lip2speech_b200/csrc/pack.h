@@ -7,6 +7,7 @@
 
 #include "context.h"
 #include "decode.cuh"
+#include "decode3.cuh"
 #include "lstm.cuh"
 
 namespace l2s {
@@ -241,6 +242,126 @@ struct PassBuild {
     size_t floats() const { return (size_t)R * (Ke + Kl); }
 };
 
+// Row sources of the decode step after the host-side linear∘linear merges (pointers into vectors that outlive the packers).
+struct StepRows {
+    const float *Wfc, *bfc, *Wpf, *bpf, *ps1, *p1bos, *Wp2, *bp2, *ps2, *Wq, *bq, *psq, *Wcq, *bcq, *Wst, *bst;
+    const float *Wih0, *Wx, *Whh0, *b0x, *Wih1, *Whh1, *b1;
+};
+
+// Program for the stage-pipelined kernel (decode3.cuh): every CTA serves ONE stage with ONE pass.  LSTM-0: 8 units per
+// CTA (32 gate rows x 1536); LSTM-1: 12 units (48 x 1024); stage A: query rows (48 x 1024), content-query rows
+// (43 x 1024) and fc_out / fc_out∘prenet-1 / stop rows (68 x 512) on separate CTAs; stage B: 8 clips x nsplit attention
+// CTAs + prenet-2 rows (86 x 256).  Row widths are padded by 16 floats so the tensor-core fragment loads (LDS.128,
+// rows g / g+8) are bank-conflict free.
+inline void pack_decode_program3(Context& c, const StepRows& w) {
+    const int nC = c.num_sms;
+    const int nD = 64, nE = 43, nQ = 11, nCQ = 6, nF = 5, nP2 = 3, nsplit = D3_NSPLIT;
+    const int nAttn = D3_CG * nsplit;
+    c.meta["d.step3.ok"] = 0;
+    if (nD + nE + nQ + nCQ + nF + nP2 + nAttn > nC) return;    // not enough SMs: decode.cuh serves every batch size
+    struct Row { int op, idx; float bias, aux, aux2; std::vector<std::pair<const float*, int>> w; };
+    struct PB { int Ke, src_e, wcol_e, Kl, src_l, wcol_l; std::vector<Row> rows; };
+    std::vector<PB> per_cta(nC, PB{0, SRC_NONE, 0, 0, SRC_NONE, 0, {}});
+    std::vector<int> role(nC, ROLE_B), job(nC, -1);
+    int cta = 0;
+    for (int j = 0; j < nD; ++j, ++cta) {                      // LSTM-0: [W_ih0[:, :256] | W_ih0[:,256:] | W_ih0[:,256:] W_ap | W_hh0] x [cv; p2; ctx; h0]
+        role[cta] = ROLE_D;
+        PB pb{512, SRC_H0OLD, 1024, 1024, SRC_XD, 0, {}};
+        for (int u = 8 * j; u < std::min(512, 8 * j + 8); ++u)
+            for (int g = 0; g < 4; ++g) {
+                const int row = g * 512 + u;
+                pb.rows.push_back({OP_GATE0, u, w.b0x[row], 0.f, 0.f,
+                                   {{w.Wih0 + (size_t)row * 512, 512}, {w.Wx + (size_t)row * 512, 512}, {w.Whh0 + (size_t)row * 512, 512}}});
+            }
+        per_cta[cta] = pb;
+    }
+    for (int j = 0; j < nE; ++j, ++cta) {                      // LSTM-1: [W_ih1 | W_hh1] x [h0'; h1]
+        role[cta] = ROLE_E;
+        PB pb{512, SRC_H1OLD, 512, 512, SRC_H0NEW, 0, {}};
+        for (int u = 12 * j; u < std::min(512, 12 * j + 12); ++u)
+            for (int g = 0; g < 4; ++g) {
+                const int row = g * 512 + u;
+                pb.rows.push_back({OP_GATE1, u, w.b1[row], 0.f, 0.f, {{w.Wih1 + (size_t)row * 512, 512}, {w.Whh1 + (size_t)row * 512, 512}}});
+            }
+        per_cta[cta] = pb;
+    }
+    {
+        const int qn = ceil_div(512, nQ), cn = ceil_div(256, nCQ), fn = ceil_div(337, nF);
+        for (int j = 0; j < nQ; ++j, ++cta) {
+            role[cta] = ROLE_A;
+            PB q{512, SRC_H0NEW, 0, 512, SRC_H1NEW, 512, {}};
+            for (int r = qn * j; r < std::min(512, qn * (j + 1)); ++r) q.rows.push_back({OP_Q, r, w.bq[r], w.psq[r], 0.f, {{w.Wq + (size_t)r * 1024, 1024}}});
+            per_cta[cta] = q;
+        }
+        for (int j = 0; j < nCQ; ++j, ++cta) {
+            role[cta] = ROLE_A;
+            PB cq{512, SRC_C0, 0, 512, SRC_C1, 512, {}};
+            for (int r = cn * j; r < std::min(256, cn * (j + 1)); ++r) cq.rows.push_back({OP_CQ, r, w.bcq[r], 0.f, 0.f, {{w.Wcq + (size_t)r * 1024, 1024}}});
+            per_cta[cta] = cq;
+        }
+        for (int j = 0; j < nF; ++j, ++cta) {
+            role[cta] = ROLE_A;
+            PB f{0, SRC_NONE, 0, 512, SRC_H1NEW, 0, {}};
+            for (int r = fn * j; r < std::min(337, fn * (j + 1)); ++r) {
+                if (r < 80) f.rows.push_back({OP_FC, r, w.bfc[r], 0.f, 0.f, {{w.Wfc + (size_t)r * 512, 512}}});
+                else if (r < 336) f.rows.push_back({OP_P1, r - 80, w.bpf[r - 80], w.ps1[r - 80], w.p1bos[r - 80], {{w.Wpf + (size_t)(r - 80) * 512, 512}}});
+                else f.rows.push_back({OP_STOP, 0, w.bst[0], 0.f, 0.f, {{w.Wst, 512}}});
+            }
+            per_cta[cta] = f;
+        }
+    }
+    for (int j = 0; j < nAttn; ++j, ++cta) job[cta] = j;       // attention CTAs hold no weights
+    {
+        const int pn = ceil_div(256, nP2);
+        for (int j = 0; j < nP2; ++j, ++cta) {
+            PB pb{0, SRC_NONE, 0, 256, SRC_P1, 0, {}};
+            for (int r = pn * j; r < std::min(256, pn * (j + 1)); ++r)
+                pb.rows.push_back({OP_P2, r, w.bp2[r], w.ps2[r], 0.f, {{w.Wp2 + (size_t)r * 256, 256}}});
+            per_cta[cta] = pb;
+        }
+    }
+    size_t wimg_floats = 512 + 320 + 256 + 32;                 // attention scratch shares the weight region
+    for (int i = 0; i < nC; ++i) {
+        if (per_cta[i].rows.size() > (size_t)D3_ROWS) return;
+        wimg_floats = std::max(wimg_floats, per_cta[i].rows.size() * (size_t)(per_cta[i].Ke + per_cta[i].Kl + 16));
+    }
+    const size_t smem = (wimg_floats + MV_WARPS * 2 * 128 + 32 * D3_CG) * sizeof(float);
+    if (smem + sizeof(Dec3Pass) + 1024 > (size_t)c.max_smem_optin) return;
+    std::vector<float> wimg((size_t)nC * wimg_floats, 0.f);
+    std::vector<Dec3Pass> passes(nC);
+    std::memset(passes.data(), 0, passes.size() * sizeof(Dec3Pass));
+    for (int i = 0; i < nC; ++i) {
+        const PB& pb = per_cta[i];
+        Dec3Pass& d = passes[i];
+        d.R = (int)pb.rows.size(); d.RT = ceil_div(d.R, 16);
+        d.Ke = pb.Ke; d.src_e = pb.src_e; d.wcol_e = pb.wcol_e; d.Kl = pb.Kl; d.src_l = pb.src_l; d.wcol_l = pb.wcol_l;
+        d.ldw = pb.Ke + pb.Kl + 16; d.wfloats = d.R * d.ldw;
+        for (int r = 0; r < D3_ROWS; ++r) {
+            if (r < d.R) {
+                const Row& row = pb.rows[r];
+                d.op[r] = row.op; d.idx[r] = row.idx; d.bias[r] = row.bias; d.aux[r] = row.aux; d.aux2[r] = row.aux2;
+                float* dst = wimg.data() + (size_t)i * wimg_floats + (size_t)r * d.ldw;
+                int col = 0;
+                for (auto& piece : row.w) { std::copy(piece.first, piece.first + piece.second, dst + col); col += piece.second; }
+                if (col != pb.Ke + pb.Kl) throw L2sError(1, "internal: decode3 row width mismatch");
+                for (int c0 = 0; c0 < col; c0 += 16) {         // fragment order inside every 16-chunk: position 4t+i <- column 4i+t
+                    float tmp[16];
+                    std::copy(dst + c0, dst + c0 + 16, tmp);
+                    for (int t = 0; t < 4; ++t)
+                        for (int i2 = 0; i2 < 4; ++i2) dst[c0 + 4 * t + i2] = tmp[4 * i2 + t];
+                }
+            } else { d.op[r] = OP_NONE; d.idx[r] = -1; }
+        }
+    }
+    c.upload("d.step3.wimg", wimg);
+    c.upload_raw("d.step3.passes", passes.data(), passes.size());
+    c.upload_raw("d.step3.role", role.data(), role.size());
+    c.upload_raw("d.step3.job", job.data(), job.size());
+    c.meta["d.step3.wimg_floats"] = (int64_t)wimg_floats;
+    c.meta["d.step3.smem"] = (int64_t)smem;
+    c.meta["d.step3.ok"] = 1;
+}
+
 inline void pack_decode_program(Context& c) {
     const std::string p = "decoder.";
     const int nC = c.num_sms;
@@ -419,6 +540,10 @@ inline void pack_decode_program(Context& c) {
     std::vector<float> wst2(Wst.begin() + 512, Wst.begin() + 1024);
     c.upload("d.stop2.w", wst2);
     upload_tc(c, "d.stop2", wst2, 1, 1, 512);
+    StepRows sr{Wfc.data(), bfc.data(), Wpf.data(), bpf.data(), ps1.data(), p1bos.data(), Wp2.data(), bp2.data(), ps2.data(),
+                Wq.data(), bq.data(), psq.data(), Wcq.data(), bcq.data(), Wst.data(), bst.data(),
+                Wih0.data(), Wx.data(), Whh0.data(), b0x.data(), Wih1.data(), Whh1.data(), b1.data()};
+    pack_decode_program3(c, sr);
 }
 
 

@@ -1,0 +1,90 @@
+// Micro-benchmark of the 8-clip tensor-core pass (matvec.cuh: mv8_*) and of the raw mma.sync tf32 issue rate.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I lip2speech_b200/csrc tools/mv8_bench.cu -o tools/mv8_bench.bin
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <cmath>
+#include "matvec.cuh"
+using namespace l2s;
+
+__global__ void __launch_bounds__(512, 1) mma_rate_kernel(float* out, int iters, int nacc) {
+    float acc[8][4];
+    for (int j = 0; j < 8; ++j) for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+    uint32_t a = threadIdx.x, b = blockIdx.x + 1;
+    for (int it = 0; it < iters; ++it) {
+        if (nacc == 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mma_tf32(acc[j], a, a + 1, a + 2, a + 3, b, b + 1);
+        } else if (nacc == 2) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mma_tf32(acc[j & 1], a, a + 1, a + 2, a + 3, b, b + 1);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mma_tf32(acc[0], a, a + 1, a + 2, a + 3, b, b + 1);
+        }
+    }
+    float s = 0.f;
+    for (int j = 0; j < 8; ++j) for (int i = 0; i < 4; ++i) s += acc[j][i];
+    out[blockIdx.x * 512 + threadIdx.x] = s;
+}
+
+template <int MAXRT>
+__global__ void __launch_bounds__(512, 1) pass_kernel(const float* __restrict__ Wg, const float* __restrict__ X, float* __restrict__ out,
+                                                       int R, int K, int ldw, int iters, int do_reduce) {
+    extern __shared__ __align__(16) float smem[];
+    float* red = smem;
+    float* wsm = smem + 4096;
+    for (int i = threadIdx.x; i < R * K; i += 512) wsm[(i / K) * ldw + (i % K)] = Wg[(size_t)blockIdx.x * R * K + i];
+    __syncthreads();
+    const int RT = (R + 15) / 16;
+    float sink = 0.f;
+    for (int it = 0; it < iters; ++it) {
+        const float* x = X + (size_t)(it & 3) * K * 32 + 8 * (it & 3);
+        float acc[MAXRT][4];
+        mv8_zero<MAXRT>(acc);
+        mv8_accumulate<MAXRT>(wsm, ldw, 0, R, x, K, acc);
+        if (do_reduce) { for (int rd = 0; rd < (MAXRT + 1) / 2; ++rd) { sink += mv8_reduce_round<MAXRT>(acc, rd, red); __syncthreads(); } }
+        else for (int r = 0; r < MAXRT; ++r) sink += acc[r][0] + acc[r][1] + acc[r][2] + acc[r][3];
+    }
+    out[(size_t)blockIdx.x * 512 + threadIdx.x] = sink;
+}
+
+int main() {
+    float* o; cudaMalloc(&o, 148 * 512 * 4);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int nacc : {8, 2, 1}) {
+        mma_rate_kernel<<<148, 512>>>(o, 100, nacc);
+        const int iters = 20000;
+        cudaEventRecord(e0);
+        mma_rate_kernel<<<148, 512>>>(o, iters, nacc);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        double mmas_per_smsp = 4.0 * 8 * iters;        // 4 warps per scheduler
+        printf("mma.sync m16n8k8 tf32, %d independent accumulators/warp, 16 warps/SM: %.2f clk per MMA per SMSP (1.965 GHz) -> %.0f MAC/clk/SM\n",
+               nacc, ms * 1e-3 * 1.965e9 / mmas_per_smsp, 1024.0 * 4 / (ms * 1e-3 * 1.965e9 / mmas_per_smsp));
+    }
+    const int KMAX = 1536, RMAX = 48;
+    std::vector<float> hW((size_t)148 * RMAX * KMAX), hX((size_t)4 * KMAX * 32);
+    srand(1);
+    for (auto& v : hW) v = (rand() / (float)RAND_MAX - 0.5f) * 0.1f;
+    for (auto& v : hX) v = (rand() / (float)RAND_MAX - 0.5f) * 2.f;
+    float *W, *X;
+    cudaMalloc(&W, hW.size() * 4); cudaMalloc(&X, hX.size() * 4);
+    cudaMemcpy(W, hW.data(), hW.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(X, hX.data(), hX.size() * 4, cudaMemcpyHostToDevice);
+    struct Cfg { int R, K; } cfgs[] = {{32, 1536}, {32, 1024}, {32, 512}, {48, 1024}, {48, 512}, {16, 512}, {16, 1024}, {24, 1024}, {48, 256}};
+    for (auto cf : cfgs)
+        for (int red = 0; red < 2; ++red) {
+            const int ldw = cf.K + 16, iters = 2000;
+            size_t smem = (size_t)(4096 + cf.R * ldw) * 4;
+            cudaFuncSetAttribute(pass_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            pass_kernel<3><<<148, 512, smem>>>(W, X, o, cf.R, cf.K, ldw, 2, red);
+            cudaEventRecord(e0);
+            pass_kernel<3><<<148, 512, smem>>>(W, X, o, cf.R, cf.K, ldw, iters, red);
+            cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            cudaError_t e = cudaGetLastError();
+            printf("mv8 pass R=%2d K=%4d reduce=%d : %6.3f us/pass %s\n", cf.R, cf.K, red, ms * 1e3 / iters, e == cudaSuccess ? "" : cudaGetErrorString(e));
+        }
+    return 0;
+}
