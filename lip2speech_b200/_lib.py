@@ -203,6 +203,9 @@ class Backend:
     def launch_count(self) -> int:
         return int(self.lib.l2s_launch_count(self.h))
 
+    def debug_flag(self, name: str) -> int:
+        return int(self.lib.l2s_debug_read(self.h, ("flag." + name).encode(), None, 0))
+
     def debug_read(self, name: str, shape) -> torch.Tensor:
         n = 1
         for s in shape:
@@ -216,6 +219,7 @@ class Backend:
 
 
 _backends = {}
+
 
 
 def backend(device: int = 0) -> Backend:

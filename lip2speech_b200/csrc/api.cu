@@ -607,7 +607,7 @@ static void decoder_run(Context& c, const float* visual, const float* spk, const
             check_launch(c, "state -> group-major");
             dp.S = S3;
             q.d = dp;
-            q.kv_smem = (size_t)(512 + 320 + 256 + 32) + (size_t)2 * T * 768 <= (size_t)c.meta.at("d.step3.wimg_floats") ? 1 : 0;
+            q.kv_smem = (size_t)(512 + 320 + 256 + 32) + (size_t)2 * (T * 768 + minT * 384) <= (size_t)c.meta.at("d.step3.wimg_floats") ? 1 : 0;
             q.passes = reinterpret_cast<const Dec3Pass*>(c.dev("d.step3.passes"));
             q.role = reinterpret_cast<const int*>(c.dev("d.step3.role"));
             q.job = reinterpret_cast<const int*>(c.dev("d.step3.job"));
@@ -875,6 +875,7 @@ int64_t l2s_debug_read(l2s_ctx* ctx, const char* name, float* out, int64_t n) {
     if (!ctx || !name) return -1;
     Context& c = ctx->c;
     auto get = [&](const char* k) { auto it = c.meta.find(k); return it == c.meta.end() ? (int64_t)0 : it->second; };
+    if (std::strncmp(name, "flag.", 5) == 0) return get((std::string("dbg.") + (name + 5)).c_str());
     const int64_t B = get("dbg.B"), T = get("dbg.T"), minT = get("dbg.minT"), steps = get("dbg.steps");
     struct { const char* name; const char* buf; int64_t count; } tab[] = {
         {"dec.K", "ws.d.K", B * T * 512}, {"dec.V", "ws.d.V", B * T * 512}, {"dec.enc_cell", "ws.d.enc_cell", B * 512},

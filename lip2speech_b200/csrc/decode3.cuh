@@ -28,7 +28,7 @@
 
 namespace l2s {
 
-constexpr int D3_MAXRT = 6;           // 16-row tiles per CTA (instantiated: 2, 3, 6)
+constexpr int D3_MAXRT = 8;           // 16-row tiles per CTA (instantiated: 2, 3, 4, 8)
 constexpr int D3_ROWS = 16 * D3_MAXRT;
 constexpr int D3_CG = 8;              // clips per group
 constexpr int D3_NG = 4;              // clip groups == pipeline stages
@@ -123,14 +123,15 @@ __device__ __forceinline__ void d3_epilogue(const DecodeParams& p, const Dec3Pas
         default: break;
     }
     if (gate_pass) {                                          // rows are (unit, gate) = (r>>2, r&3); 8 units per round
-        if (tid < 256) sm.gsm[tid] = v;
+        // every thread applies its own gate non-linearity (i, f, o: sigmoid; g: tanh), the gate-0 thread combines
+        if (tid < 256) sm.gsm[tid] = ((r & 3) == 2) ? tanhf(v) : sigmoidf_acc(v);
         __syncthreads();
         if (live && (r & 3) == 0 && idx >= 0) {
             const int layer = (op == OP_GATE1) ? 1 : 0;
             const float gi = sm.gsm[tid], gf = sm.gsm[tid + 8], gg = sm.gsm[tid + 16], go = sm.gsm[tid + 24];
             const size_t si = (size_t)g * 1024 * D3_CG + (size_t)(layer * 512 + idx) * D3_CG + bb;
-            const float c = sigmoidf_acc(gf) * c_prev + sigmoidf_acc(gi) * tanhf(gg);
-            const float h = sigmoidf_acc(go) * tanhf(c);
+            const float c = gf * c_prev + gi * gg;
+            const float h = go * tanhf(c);
             p.Cst[si] = c;
             (p.S + (size_t)parity_new * 1024 * p.Bpad)[si] = h;
         }
@@ -171,27 +172,37 @@ __device__ __forceinline__ void d3_turn(const DecodeParams& p, const Dec3Pass& p
 }
 
 // ---- attention CTAs ------------------------------------------------------------------------------------------------
-// Shared-memory image of one clip: K [T][512] then the CTA's half of V [T][256].
+// Shared-memory image of one clip: K [T][512], the CTA's half of V [T][256], content keys [minT][256] and the CTA's half
+// of the content values [minT][128].
+__device__ __forceinline__ int d3_kv_floats(int T, int minT) { return T * 768 + minT * 384; }
+
+__device__ __forceinline__ void d3_cp16(float* dst, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
 __device__ __forceinline__ void d3_prefetch_kv(const DecodeParams& p, float* buf, int b, int part) {
     const float* K = p.Kmem + (size_t)b * p.T * 512;
     const float* V = p.Vmem + (size_t)b * p.T * 512 + part * 256;
-    const int nk = p.T * 128, nv = p.T * 64;                // 16-byte pieces
-    for (int i = threadIdx.x; i < nk; i += MV_THREADS)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(buf + 4 * i)), "l"(K + 4 * i) : "memory");
+    const float* ck = p.ckey + (size_t)b * p.minT * 256;
+    const float* cv = p.cval + (size_t)b * p.minT * 256 + part * 128;
+    const int nk = p.T * 128, nv = p.T * 64, nck = p.minT * 64, ncv = p.minT * 32;          // 16-byte pieces
+    for (int i = threadIdx.x; i < nk; i += MV_THREADS) d3_cp16(buf + 4 * i, K + 4 * i);
     float* vb = buf + (size_t)p.T * 512;
-    for (int i = threadIdx.x; i < nv; i += MV_THREADS) {
-        const int t = i >> 6, f = (i & 63) * 4;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(vb + t * 256 + f)), "l"(V + (size_t)t * 512 + f) : "memory");
-    }
+    for (int i = threadIdx.x; i < nv; i += MV_THREADS) d3_cp16(vb + 4 * i, V + (size_t)(i >> 6) * 512 + (i & 63) * 4);
+    float* ckb = vb + (size_t)p.T * 256;
+    for (int i = threadIdx.x; i < nck; i += MV_THREADS) d3_cp16(ckb + 4 * i, ck + 4 * i);
+    float* cvb = ckb + (size_t)p.minT * 256;
+    for (int i = threadIdx.x; i < ncv; i += MV_THREADS) d3_cp16(cvb + 4 * i, cv + (size_t)(i >> 5) * 256 + (i & 31) * 4);
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 // Dot-product attention over the T encoder positions and over the minT content slots for clip b (reference
 // decoder.py:414-419 and Content.forward 262-271).  Both CTAs of a clip compute all scores; CTA `part` produces context
 // features [256*part, 256*part+256) and content-value features [128*part, 128*part+128).
-// Kb: [T][512]; Vb: this CTA's 256 features of row 0, row stride vstride (shared memory or global).
+// Kb: [T][512]; Vb: this CTA's 256 features of row 0, row stride vstride; ck: content keys [minT][256]; cv: this CTA's
+// 128 content-value features of slot 0, slot stride cvstride (all four in shared memory or all in global memory).
 __device__ void d3_attend(const DecodeParams& p, const DecSmem& sm, const float* Kb, const float* Vb, int vstride,
-                          int b, int part, int step) {
+                          const float* ck, const float* cv, int cvstride, int b, int part, int step) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = b / D3_CG, bb = b % D3_CG;
     sm.qs[tid] = ldcg1(p.Q + (size_t)b * 512 + tid) * p.temp;
@@ -210,11 +221,11 @@ __device__ void d3_attend(const DecodeParams& p, const DecSmem& sm, const float*
         if (lane == 0) sm.sc[t] = a;
     }
     for (int m = warp; m < p.minT; m += MV_WARPS) {
-        const float4* kr = reinterpret_cast<const float4*>(p.ckey + ((size_t)b * p.minT + m) * 256);
+        const float4* kr = reinterpret_cast<const float4*>(ck + (size_t)m * 256);
         float a = 0.f;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-            const float4 k = __ldg(kr + lane + 32 * i);
+            const float4 k = kr[lane + 32 * i];
             const float4 q = *reinterpret_cast<const float4*>(sm.cqs + 4 * (lane + 32 * i));
             a = fmaf(q.x, k.x, a); a = fmaf(q.y, k.y, a); a = fmaf(q.z, k.z, a); a = fmaf(q.w, k.w, a);
         }
@@ -263,11 +274,10 @@ __device__ void d3_attend(const DecodeParams& p, const DecSmem& sm, const float*
         for (int j = 0; j < 8; ++j) s += sm.red[j * 256 + tid];
         xd[(512 + part * 256 + tid) * D3_CG + bb] = s;
     } else if (tid < 256 + 128) {
-        const int f = part * 128 + (tid - 256);
-        const float* vr = p.cval + (size_t)b * p.minT * 256 + f;
+        const int f = tid - 256;
         float a = 0.f;
-        for (int m = 0; m < p.minT; ++m) a = fmaf(sm.csc[m], __ldg(vr + (size_t)m * 256), a);
-        xd[f * D3_CG + bb] = a;
+        for (int m = 0; m < p.minT; ++m) a = fmaf(sm.csc[m], cv[(size_t)m * cvstride + f], a);
+        xd[(part * 128 + f) * D3_CG + bb] = a;
     }
     __syncthreads();
 }
@@ -279,8 +289,8 @@ __device__ __forceinline__ void d3_loop(const Decode3Params& q, const Dec3Pass& 
     const unsigned n = gridDim.x;
     const bool has_pass = ps.R > 0;
     const int aclip = job / D3_NSPLIT, apart = job % D3_NSPLIT;         // attention CTAs: clip inside the group, half
-    float* kvbuf = sm.csc + 32;                                         // [2][T*768] when q.kv_smem
-    const int kvfloats = p.T * 768;
+    float* kvbuf = sm.csc + 32;                                         // [2][d3_kv_floats] when q.kv_smem
+    const int kvfloats = d3_kv_floats(p.T, p.minT);
     // prologue A(-1): Q, content query and prenet(BOS) of every clip group from the initial state in S[0]
     if (role == ROLE_A && has_pass)
         for (int g = 0; g < D3_NG; ++g) d3_turn<RT>(p, ps, sm, sync, g, -1, 0);
@@ -312,9 +322,11 @@ __device__ __forceinline__ void d3_loop(const Decode3Params& q, const Dec3Pass& 
                 if (b < p.B) {
                     if (q.kv_smem) {
                         const float* kb = kvbuf + (size_t)(turn & 1) * kvfloats;
-                        d3_attend(p, sm, kb, kb + (size_t)p.T * 512, 256, b, apart, step);
+                        const float* ckb = kb + (size_t)p.T * 768;
+                        d3_attend(p, sm, kb, kb + (size_t)p.T * 512, 256, ckb, ckb + (size_t)p.minT * 256, 128, b, apart, step);
                     } else {
-                        d3_attend(p, sm, p.Kmem + (size_t)b * p.T * 512, p.Vmem + (size_t)b * p.T * 512 + apart * 256, 512, b, apart, step);
+                        d3_attend(p, sm, p.Kmem + (size_t)b * p.T * 512, p.Vmem + (size_t)b * p.T * 512 + apart * 256, 512,
+                                  p.ckey + (size_t)b * p.minT * 256, p.cval + (size_t)b * p.minT * 256 + apart * 128, 256, b, apart, step);
                     }
                 }
             }
@@ -346,7 +358,7 @@ __global__ void __launch_bounds__(MV_THREADS, 1) decode3_kernel(const Decode3Par
     sm.qs = sm.wsm;                                          // [512]
     sm.sc = sm.qs + 512;                                     // [320]
     sm.cqs = sm.sc + 320;                                    // [256]
-    sm.csc = sm.cqs + 256;                                   // [32]; then [2][T*768] K/V buffers
+    sm.csc = sm.cqs + 256;                                   // [32]; then [2][d3_kv_floats] K/V images
     if (tid < D3_TIMING_SLOTS) tacc[tid] = 0.f;
     {
         const int* src = reinterpret_cast<const int*>(q.passes + blockIdx.x);
@@ -366,7 +378,8 @@ __global__ void __launch_bounds__(MV_THREADS, 1) decode3_kernel(const Decode3Par
     sync.tacc = tacc; sync.tmark = 0; sync.slot0 = 0; sync.timing = false;
     if (pass.RT <= 2) d3_loop<2>(q, pass, sm, sync, role, job);
     else if (pass.RT == 3) d3_loop<3>(q, pass, sm, sync, role, job);
-    else d3_loop<6>(q, pass, sm, sync, role, job);
+    else if (pass.RT == 4) d3_loop<4>(q, pass, sm, sync, role, job);
+    else d3_loop<8>(q, pass, sm, sync, role, job);
     __syncthreads();
     if (q.timing && tid < D3_TIMING_SLOTS) q.timing[blockIdx.x * D3_TIMING_SLOTS + tid] = tacc[tid];
 }

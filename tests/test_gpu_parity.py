@@ -112,17 +112,47 @@ def test_batch_33_two_clip_groups_vs_oracle(be, O, weights):
 
 def test_batch_invariance_full_size(be):
     """Size-independent property at the bench size (B=32, 300 steps): a clip's mel does not depend on which other
-    clips share the batch.  Bit-exact within the batched (wide) lane mapping; the single-clip (narrow, B<=2) mapping
-    sums in a different order, so there the bound is the parity tolerance."""
+    clips share the batch.  Bit-exact between batches served by the same kernel (the stage-pipelined kernel for
+    8 < B <= 32: every clip is an independent MMA column); the row-partitioned kernel (B <= 8) and its single-clip lane
+    mapping (B <= 2) sum in a different order, so there the bound is the parity tolerance."""
     visual, face = synth.visual_features(32, 29, seed=5)
     g = synth.gumbel(32, 29, seed=5)
     mel, lengths = be.decoder_infer(visual.cuda(), face[:, 0].cuda(), g.cuda())
-    for lo in (0, 16, 28):                               # 4-clip sub-batches
+    for lo, n in ((0, 12), (7, 9), (15, 17)):            # sub-batches served by the pipelined kernel, unaligned to clip groups
+        m, l = be.decoder_infer(visual[lo:lo + n].cuda(), face[lo:lo + n, 0].cuda(), g[4 * lo:4 * (lo + n)].cuda())
+        assert torch.equal(m, mel[lo:lo + n]) and torch.equal(l, lengths[lo:lo + n])
+    for lo in (0, 28):                                   # 4-clip sub-batches (row-partitioned kernel)
         m4, l4 = be.decoder_infer(visual[lo:lo + 4].cuda(), face[lo:lo + 4, 0].cuda(), g[4 * lo:4 * lo + 16].cuda())
-        assert torch.equal(m4, mel[lo:lo + 4]) and torch.equal(l4, lengths[lo:lo + 4])
+        assert rel_err(m4.cpu(), mel[lo:lo + 4].cpu()) < TOL and torch.equal(l4, lengths[lo:lo + 4])
     for i in (0, 17, 31):                                # single clips
         m1, l1 = be.decoder_infer(visual[i:i + 1].cuda(), face[i:i + 1, 0].cuda(), g[4 * i:4 * i + 4].cuda())
         assert rel_err(m1[0].cpu(), mel[i].cpu()) < TOL and int(l1[0]) == int(lengths[i])
+
+
+def test_pipelined_kernel_vs_oracle(be, O, weights):
+    """8 < B <= 32 runs the stage-pipelined kernel (decode3.cuh): partial clip groups (B=11), attention maps, and the
+    Decoder.forward flavour (teacher-forced steps, raw stop logits, pre-softmax attention logits) against the oracle."""
+    visual, face = synth.visual_features(11, 29, seed=31)
+    g = synth.gumbel(11, 29, seed=31)
+    mel, lengths, attn = be.decoder_infer(visual.cuda(), face[:, 0].cuda(), g.cuda(), steps=50, return_attention=True)
+    assert be.debug_flag("dec3") == 1
+    ref_mel, ref_len, ref_attn = O.decoder_inference(weights, visual, face, g, steps=50, return_attention=True)
+    assert torch.equal(lengths.cpu(), ref_len)
+    assert rel_err(mel.cpu(), ref_mel) < TOL
+    assert (attn.cpu() - ref_attn).abs().max() < 2e-2
+    mels = synth.mel_like(11, 20, seed=31)
+    tf_mask = torch.tensor([i % 3 == 0 for i in range(20)])
+    o = be.decoder_forward(visual.cuda(), face[:, 0].cuda(), g.cuda(), mels.cuda(), tf_mask)
+    ref = O.decoder_forward(weights, visual, face, mels, tf_mask, g)
+    for got, want in zip(o[:4], (ref[0], ref[1], ref[2], ref[4])):
+        assert rel_err(got.cpu(), want) < TOL
+    # T = 75: keys/values do not fit in shared memory twice, the attention CTAs stream them from L2
+    visual, face = synth.visual_features(9, 75, seed=32)
+    g = synth.gumbel(9, 75, seed=32)
+    mel, lengths = be.decoder_infer(visual.cuda(), face[:, 0].cuda(), g.cuda(), steps=12)
+    ref_mel, ref_len = O.decoder_inference(weights, visual, face, g, steps=12)
+    assert torch.equal(lengths.cpu(), ref_len)
+    assert rel_err(mel.cpu(), ref_mel) < TOL
 
 
 def _stop_logit_trajectory(O, w, pre, steps):

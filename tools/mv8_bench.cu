@@ -36,10 +36,9 @@ __global__ void __launch_bounds__(512, 1) pass_kernel(const float* __restrict__ 
     float* wsm = smem + 4096;
     for (int i = threadIdx.x; i < R * K; i += 512) wsm[(i / K) * ldw + (i % K)] = Wg[(size_t)blockIdx.x * R * K + i];
     __syncthreads();
-    const int RT = (R + 15) / 16;
     float sink = 0.f;
     for (int it = 0; it < iters; ++it) {
-        const float* x = X + (size_t)(it & 3) * K * 32 + 8 * (it & 3);
+        const float* x = X + (size_t)(it & 3) * K * 8;
         float acc[MAXRT][4];
         mv8_zero<MAXRT>(acc);
         mv8_accumulate<MAXRT>(wsm, ldw, 0, R, x, K, acc);
@@ -78,9 +77,10 @@ int main() {
             const int ldw = cf.K + 16, iters = 2000;
             size_t smem = (size_t)(4096 + cf.R * ldw) * 4;
             cudaFuncSetAttribute(pass_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            pass_kernel<3><<<148, 512, smem>>>(W, X, o, cf.R, cf.K, ldw, 2, red);
+            if (cf.R <= 32) { cudaFuncSetAttribute(pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); }
             cudaEventRecord(e0);
-            pass_kernel<3><<<148, 512, smem>>>(W, X, o, cf.R, cf.K, ldw, iters, red);
+            if (cf.R <= 32) pass_kernel<2><<<148, 512, smem>>>(W, X, o, cf.R, cf.K, ldw, iters, red);
+            else pass_kernel<3><<<148, 512, smem>>>(W, X, o, cf.R, cf.K, ldw, iters, red);
             cudaEventRecord(e1); cudaEventSynchronize(e1);
             float ms; cudaEventElapsedTime(&ms, e0, e1);
             cudaError_t e = cudaGetLastError();
