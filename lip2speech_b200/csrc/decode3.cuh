@@ -19,7 +19,7 @@
 //  * the 16-row x 8-clip tiles go to the tensor cores as error-compensated 3xTF32 (matvec.cuh: mv8_*), every weight is
 //    read from shared memory once per turn;
 //  * the attention SMs hold no weights: they keep the encoder keys/values of the clip they serve in shared memory,
-//    double-buffered (the next turn's clip is fetched with cp.async while the current one is attended);
+//    double-buffered (the next turn's clip is fetched by the TMA engine, cp.async.bulk, while the current one is attended);
 //  * one grid barrier per turn (four per step, as before), split-phase with the same early/late segments.
 // Recurrent state is GROUP-MAJOR ([group][feature][8 clips], see matvec.cuh: mv8_accumulate); queries are clip-major.
 // Outputs do not depend on which other clips share the batch (each clip's columns are independent in the MMA).
@@ -138,10 +138,26 @@ __device__ __forceinline__ void d3_epilogue(const DecodeParams& p, const Dec3Pas
     }
 }
 
+constexpr int D3_EDEPTH = 2;          // chunks per warp of an early segment (Ke <= 512)
+
+// What this CTA's stage does in a given turn of the software pipeline.
+struct D3Slot { int g, step; bool active; };
+__device__ __forceinline__ D3Slot d3_slot(int turn, int role, int steps) {
+    D3Slot s;
+    s.g = (turn - role) & (D3_NG - 1);                       // clip group served by this stage in this turn
+    const int u = turn - s.g;                                // stages completed by that group (u % 4 == role)
+    s.step = u >> 2;
+    s.active = (u >= 0) && (s.step < steps);
+    return s;
+}
+
 // The pass of this CTA for one (clip group, step): early segment, barrier wait, late segment, reduction + epilogue.
-template <int RT>
-__device__ __forceinline__ void d3_turn(const DecodeParams& p, const Dec3Pass& ps, const DecSmem& sm,
-                                        StageSync& sync, int g, int step, int parity_new) {
+// xe: the early segment's activations.  They are at least two turns old when they are used, so they are requested one
+// turn ahead (right after the late MMAs of the previous turn were issued): `xe_valid` says whether that happened; on
+// return xe holds the early activations of `next` (if next.active) and xe_valid is updated.
+template <int RT, bool EARLY>
+__device__ __forceinline__ void d3_turn(const DecodeParams& p, const Dec3Pass& ps, const DecSmem& sm, StageSync& sync,
+                                        int g, int step, int parity_new, float (&xe)[D3_EDEPTH][4], bool& xe_valid, const D3Slot& next) {
     constexpr int ROUNDS = (RT + 1) / 2;
     const int tid = threadIdx.x;
     const bool gate_pass = (ps.op[0] == OP_GATE0 || ps.op[0] == OP_GATE1);
@@ -156,10 +172,20 @@ __device__ __forceinline__ void d3_turn(const DecodeParams& p, const Dec3Pass& p
     }
     float acc[RT][4];
     mv8_zero<RT>(acc);
-    if (ps.Ke > 0)
-        mv8_accumulate<RT>(sm.wsm, ps.ldw, ps.wcol_e, ps.R, d3_src(p, ps.src_e, parity_new, g), ps.Ke, acc);
+    if (EARLY) {
+        if (!xe_valid) mv8_load<D3_EDEPTH>(d3_src(p, ps.src_e, parity_new, g), ps.Ke, xe);
+        mv8_mma<RT, D3_EDEPTH>(sm.wsm, ps.ldw, ps.wcol_e, ps.R, ps.Ke, xe, acc);
+    }
     sync.wait();
-    mv8_accumulate<RT>(sm.wsm, ps.ldw, ps.wcol_l, ps.R, d3_src(p, ps.src_l, parity_new, g), ps.Kl, acc);
+    {
+        float xl[MV8_DEPTH][4];
+        mv8_load<MV8_DEPTH>(d3_src(p, ps.src_l, parity_new, g), ps.Kl, xl);
+        mv8_mma<RT, MV8_DEPTH>(sm.wsm, ps.ldw, ps.wcol_l, ps.R, ps.Kl, xl, acc);
+    }
+    if (EARLY) {
+        xe_valid = next.active;
+        if (next.active) mv8_load<D3_EDEPTH>(d3_src(p, ps.src_e, (next.step + 1) & 1, next.g), ps.Ke, xe);
+    }
     sync.lap(2);
 #pragma unroll
     for (int round = 0; round < ROUNDS; ++round) {
@@ -176,24 +202,25 @@ __device__ __forceinline__ void d3_turn(const DecodeParams& p, const Dec3Pass& p
 // of the content values [minT][128].
 __device__ __forceinline__ int d3_kv_floats(int T, int minT) { return T * 768 + minT * 384; }
 
-__device__ __forceinline__ void d3_cp16(float* dst, const float* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
-
-__device__ __forceinline__ void d3_prefetch_kv(const DecodeParams& p, float* buf, int b, int part) {
+// Issued by warp 0: one expect_tx + T + 6 bulk copies (K in one piece, the strided halves row by row).
+__device__ __forceinline__ void d3_prefetch_kv(const DecodeParams& p, float* buf, uint64_t* bar, int b, int part) {
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
     const float* K = p.Kmem + (size_t)b * p.T * 512;
     const float* V = p.Vmem + (size_t)b * p.T * 512 + part * 256;
     const float* ck = p.ckey + (size_t)b * p.minT * 256;
     const float* cv = p.cval + (size_t)b * p.minT * 256 + part * 128;
-    const int nk = p.T * 128, nv = p.T * 64, nck = p.minT * 64, ncv = p.minT * 32;          // 16-byte pieces
-    for (int i = threadIdx.x; i < nk; i += MV_THREADS) d3_cp16(buf + 4 * i, K + 4 * i);
     float* vb = buf + (size_t)p.T * 512;
-    for (int i = threadIdx.x; i < nv; i += MV_THREADS) d3_cp16(vb + 4 * i, V + (size_t)(i >> 6) * 512 + (i & 63) * 4);
     float* ckb = vb + (size_t)p.T * 256;
-    for (int i = threadIdx.x; i < nck; i += MV_THREADS) d3_cp16(ckb + 4 * i, ck + 4 * i);
     float* cvb = ckb + (size_t)p.minT * 256;
-    for (int i = threadIdx.x; i < ncv; i += MV_THREADS) d3_cp16(cvb + 4 * i, cv + (size_t)(i >> 5) * 256 + (i & 31) * 4);
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (lane == 0) {
+        mbar_expect_tx(bar, (uint32_t)d3_kv_floats(p.T, p.minT) * 4u);
+        bulk_load_1d(buf, K, (uint32_t)p.T * 2048u, bar);
+        bulk_load_1d(ckb, ck, (uint32_t)p.minT * 1024u, bar);
+    }
+    __syncwarp();
+    for (int t = lane; t < p.T; t += 32) bulk_load_1d(vb + t * 256, V + (size_t)t * 512, 1024u, bar);
+    for (int m = lane; m < p.minT; m += 32) bulk_load_1d(cvb + m * 128, cv + (size_t)m * 256, 512u, bar);
 }
 
 // Dot-product attention over the T encoder positions and over the minT content slots for clip b (reference
@@ -282,19 +309,22 @@ __device__ void d3_attend(const DecodeParams& p, const DecSmem& sm, const float*
     __syncthreads();
 }
 
-template <int RT>
+template <int RT, bool EARLY>
 __device__ __forceinline__ void d3_loop(const Decode3Params& q, const Dec3Pass& ps, const DecSmem& sm, StageSync& sync,
-                                        int role, int job) {
+                                        int role, int job, uint64_t* kvbar) {
     const DecodeParams& p = q.d;
     const unsigned n = gridDim.x;
     const bool has_pass = ps.R > 0;
     const int aclip = job / D3_NSPLIT, apart = job % D3_NSPLIT;         // attention CTAs: clip inside the group, half
     float* kvbuf = sm.csc + 32;                                         // [2][d3_kv_floats] when q.kv_smem
     const int kvfloats = d3_kv_floats(p.T, p.minT);
+    float xe[D3_EDEPTH][4];
+    bool xe_valid = false;
+    D3Slot none; none.g = 0; none.step = 0; none.active = false;
     // prologue A(-1): Q, content query and prenet(BOS) of every clip group from the initial state in S[0]
     if (role == ROLE_A && has_pass)
-        for (int g = 0; g < D3_NG; ++g) d3_turn<RT>(p, ps, sm, sync, g, -1, 0);
-    if (job >= 0 && q.kv_smem) d3_prefetch_kv(p, kvbuf, min(aclip, p.B - 1), apart);          // turn 0 serves group 0
+        for (int g = 0; g < D3_NG; ++g) d3_turn<RT, EARLY>(p, ps, sm, sync, g, -1, 0, xe, xe_valid, none);
+    if (job >= 0 && q.kv_smem) d3_prefetch_kv(p, kvbuf, &kvbar[0], min(aclip, p.B - 1), apart);          // turn 0 serves group 0
     grid_arrive(p.barrier);
     sync.target += n;
     sync.timing = (q.timing != nullptr);
@@ -303,21 +333,21 @@ __device__ __forceinline__ void d3_loop(const Decode3Params& q, const Dec3Pass& 
     const int nturns = D3_NG * p.steps + D3_NG - 1;
 #pragma unroll 1
     for (int turn = 0; turn < nturns; ++turn) {
-        const int g = (turn - role) & (D3_NG - 1);           // clip group served by this CTA's stage in this turn
-        const int u = turn - g;                              // stages completed by that group (u % 4 == role)
-        const int step = u >> 2;
+        const D3Slot cur = d3_slot(turn, role, p.steps);
+        const D3Slot next = (turn + 1 < nturns) ? d3_slot(turn + 1, role, p.steps) : none;
+        const int g = cur.g, step = cur.step;
         sync.waited = false;
-        if (job >= 0 && q.kv_smem) {                         // next turn's clip -> the other buffer (free since the last turn ended)
-            const int bn = ((turn + 1) & (D3_NG - 1)) * D3_CG + aclip;
-            d3_prefetch_kv(p, kvbuf + (size_t)((turn + 1) & 1) * kvfloats, min(bn, p.B - 1), apart);
+        if (job >= 0 && q.kv_smem && next.active) {          // next turn's clip -> the other buffer (free since the last turn ended)
+            const int bn = next.g * D3_CG + aclip;
+            d3_prefetch_kv(p, kvbuf + (size_t)((turn + 1) & 1) * kvfloats, &kvbar[(turn + 1) & 1], min(bn, p.B - 1), apart);
         }
-        if (u >= 0 && step < p.steps) {
+        if (cur.active) {
             const int parity_new = (step + 1) & 1;
-            if (has_pass) d3_turn<RT>(p, ps, sm, sync, g, step, parity_new);
+            if (has_pass) d3_turn<RT, EARLY>(p, ps, sm, sync, g, step, parity_new, xe, xe_valid, next);
             if (job >= 0) {
                 const int b = g * D3_CG + aclip;
-                if (q.kv_smem) asm volatile("cp.async.wait_group 1;" ::: "memory");          // this turn's clip has landed
                 sync.wait();
+                if (q.kv_smem) mbar_wait(&kvbar[turn & 1], (turn >> 1) & 1);                  // this turn's clip has landed
                 sync.lap(2);
                 if (b < p.B) {
                     if (q.kv_smem) {
@@ -340,7 +370,6 @@ __device__ __forceinline__ void d3_loop(const Decode3Params& q, const Dec3Pass& 
         sync.lap(5);
         sync.target += n;
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(MV_THREADS, 1) decode3_kernel(const Decode3Params q) {
@@ -348,8 +377,13 @@ __global__ void __launch_bounds__(MV_THREADS, 1) decode3_kernel(const Decode3Par
     extern __shared__ __align__(16) float smem[];
     __shared__ Dec3Pass pass;
     __shared__ float tacc[D3_TIMING_SLOTS];
+    __shared__ __align__(8) uint64_t kvbar[2];              // attention CTAs: K/V image landed (one per buffer)
     const int tid = threadIdx.x;
     const int role = q.role[blockIdx.x], job = q.job[blockIdx.x];
+    if (tid == 0) {
+        mbar_init(&kvbar[0], 1); mbar_init(&kvbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
 
     DecSmem sm;
     sm.red = smem;                                           // [16 warps][2 tiles][128]; attention partials [8][256]
@@ -376,10 +410,11 @@ __global__ void __launch_bounds__(MV_THREADS, 1) decode3_kernel(const Decode3Par
     StageSync sync;
     sync.counter = p.barrier; sync.target = 0; sync.waited = true;     // nothing to wait for before the prologue
     sync.tacc = tacc; sync.tmark = 0; sync.slot0 = 0; sync.timing = false;
-    if (pass.RT <= 2) d3_loop<2>(q, pass, sm, sync, role, job);
-    else if (pass.RT == 3) d3_loop<3>(q, pass, sm, sync, role, job);
-    else if (pass.RT == 4) d3_loop<4>(q, pass, sm, sync, role, job);
-    else d3_loop<8>(q, pass, sm, sync, role, job);
+    const bool early = pass.Ke > 0;                        // (Ke <= 256 * D3_EDEPTH is checked by the packer)
+    if (pass.RT <= 2) { if (early) d3_loop<2, true>(q, pass, sm, sync, role, job, kvbar); else d3_loop<2, false>(q, pass, sm, sync, role, job, kvbar); }
+    else if (pass.RT == 3) { if (early) d3_loop<3, true>(q, pass, sm, sync, role, job, kvbar); else d3_loop<3, false>(q, pass, sm, sync, role, job, kvbar); }
+    else if (pass.RT == 4) d3_loop<4, false>(q, pass, sm, sync, role, job, kvbar);
+    else d3_loop<8, false>(q, pass, sm, sync, role, job, kvbar);
     __syncthreads();
     if (q.timing && tid < D3_TIMING_SLOTS) q.timing[blockIdx.x * D3_TIMING_SLOTS + tid] = tacc[tid];
 }

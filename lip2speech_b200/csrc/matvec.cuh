@@ -336,23 +336,31 @@ __device__ __forceinline__ void mv8_zero(float (&acc)[RT][4]) {
         for (int i = 0; i < 4; ++i) acc[r][i] = 0.f;
 }
 
-// W: first row of the pass in shared memory; R real rows (rows >= R re-read row R-1; their results are never used).
+// Requests the chunks of one segment that this warp owns: x[d][i] = X[(16*(warp + 16 d) + 4 i + t)*8 + g], d < K/256.
 // X: feature 0 of the segment for this clip group (X[k*8 + clip]).
-template <int RT>
-__device__ __forceinline__ void mv8_accumulate(const float* __restrict__ W, int ldw, int wcol0, int R,
-                                               const float* __restrict__ X, int K, float (&acc)[RT][4]) {
+template <int DEPTH>
+__device__ __forceinline__ void mv8_load(const float* __restrict__ X, int K, float (&x)[DEPTH][4]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int npw = K / (MV_KC * MV_WARPS);                  // chunks per warp
     const float* xp = X + (size_t)(warp * MV_KC + t) * 8 + g;
     constexpr int xstride = MV_WARPS * MV_KC * 8;
-    float x[MV8_DEPTH][4];
 #pragma unroll
-    for (int d = 0; d < MV8_DEPTH; ++d)
+    for (int d = 0; d < DEPTH; ++d)
         if (d < npw) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) x[d][i] = __ldcg(xp + d * xstride + i * 32);
         }
+}
+
+// Multiplies the loaded chunks with the weight rows of the pass.  W: first row of the pass in shared memory; R real rows
+// (rows >= R re-read row R-1; their results are never used).
+template <int RT, int DEPTH>
+__device__ __forceinline__ void mv8_mma(const float* __restrict__ W, int ldw, int wcol0, int R, int K,
+                                        const float (&x)[DEPTH][4], float (&acc)[RT][4]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int npw = K / (MV_KC * MV_WARPS);
     const float* wrow[RT][2];
 #pragma unroll
     for (int rt = 0; rt < RT; ++rt) {
@@ -360,7 +368,7 @@ __device__ __forceinline__ void mv8_accumulate(const float* __restrict__ W, int 
         wrow[rt][1] = W + (size_t)min(rt * 16 + g + 8, R - 1) * ldw + wcol0 + warp * MV_KC + 4 * t;
     }
 #pragma unroll
-    for (int d = 0; d < MV8_DEPTH; ++d)
+    for (int d = 0; d < DEPTH; ++d)
         if (d < npw) {
             uint32_t xh[4], xl[4];
 #pragma unroll
@@ -381,6 +389,14 @@ __device__ __forceinline__ void mv8_accumulate(const float* __restrict__ W, int 
                 }
             }
         }
+}
+
+template <int RT>
+__device__ __forceinline__ void mv8_accumulate(const float* __restrict__ W, int ldw, int wcol0, int R,
+                                               const float* __restrict__ X, int K, float (&acc)[RT][4]) {
+    float x[MV8_DEPTH][4];
+    mv8_load<MV8_DEPTH>(X, K, x);
+    mv8_mma<RT, MV8_DEPTH>(W, ldw, wcol0, R, K, x, acc);
 }
 
 // Cross-warp reduction of row tiles 2*round and 2*round+1 through `red` (MV_WARPS x 2 x 128 floats = 16 KB).  Threads

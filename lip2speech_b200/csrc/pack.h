@@ -323,6 +323,8 @@ inline void pack_decode_program3(Context& c, const StepRows& w) {
     size_t wimg_floats = 512 + 320 + 256 + 32;                 // attention scratch shares the weight region
     for (int i = 0; i < nC; ++i) {
         if (per_cta[i].rows.size() > (size_t)D3_ROWS) return;
+        if (per_cta[i].Ke > 256 * D3_EDEPTH || per_cta[i].Kl > 256 * MV8_DEPTH) return;
+        if (per_cta[i].Ke > 0 && per_cta[i].rows.size() > 48) return;      // early segments are instantiated for <= 3 row tiles
         wimg_floats = std::max(wimg_floats, per_cta[i].rows.size() * (size_t)(per_cta[i].Ke + per_cta[i].Kl + 16));
     }
     const size_t smem = (wimg_floats + MV_WARPS * 2 * 128 + 32 * D3_CG) * sizeof(float);
