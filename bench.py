@@ -12,7 +12,7 @@ clips per GPU (29 frames of 96x96, 19 456 audio samples); 300 mel frames are emi
   value : inputs resident in HBM, CUDA-event time per step, L2 flushed between steps, max over ranks
   e2e   : the same span through the public C-ABI host call (l2s_infer_host): pinned host inputs,
           H2D + compute + D2H inside the timed region
-  roofline : the persistent decode-step kernel's algorithmic bytes / its CUDA-event time
+  roofline : the persistent decode-loop kernel's algorithmic bytes / its CUDA-event time
   cpu_baseline : the CPU oracle (port of the reference, torch CPU fp32, all host threads) on the same workload
 
 Multi-GPU: clips are independent -> the batch is sharded, B per rank, no data-path collective
@@ -147,6 +147,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="clips per GPU per step")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
+                    help="Conv3d stem operands: bf16 (BASELINE configs[2]: 'bf16 frontend + fp32 decoder step') or the 3xTF32 fp32-grade path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -174,6 +176,7 @@ def main():
         dist.barrier()
 
     B = args.batch
+    prec = _lib.PRECISION_BF16 if args.precision == "bf16" else _lib.PRECISION_FP32
     be = _lib.backend(local_rank)
     be.bind_state_dict(spec.seeded_state_dict(spec.full_spec(), 1234), "", 7)
     # identical synthetic inputs on every rank's shard (seeded per rank)
@@ -190,7 +193,7 @@ def main():
 
     be.set_profiling(True)
     for _ in range(max(args.warmup, 3)):
-        be.infer(video, wav, g, STEPS_PER_CLIP)
+        be.infer(video, wav, g, STEPS_PER_CLIP, prec)
     barrier()
 
     sampler = ClockSampler(local_rank)
@@ -202,7 +205,7 @@ def main():
     for i in range(args.steps):
         flush.zero_()                       # evict L2 between timed steps (outside the event pair)
         ev[i][0].record()
-        be.infer(video, wav, g, STEPS_PER_CLIP)
+        be.infer(video, wav, g, STEPS_PER_CLIP, prec)
         ev[i][1].record()
         ev[i][1].synchronize()
         for k in spans:
@@ -217,11 +220,11 @@ def main():
     len_h = torch.empty(B, dtype=torch.int64).pin_memory()
     be.set_profiling(False)
     for _ in range(2):
-        be.infer_host(video_h, wav_h, g_h, mel_h, len_h, STEPS_PER_CLIP)
+        be.infer_host(video_h, wav_h, g_h, mel_h, len_h, STEPS_PER_CLIP, prec)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        be.infer_host(video_h, wav_h, g_h, mel_h, len_h, STEPS_PER_CLIP)     # synchronous: returns after D2H
+        be.infer_host(video_h, wav_h, g_h, mel_h, len_h, STEPS_PER_CLIP, prec)     # synchronous: returns after D2H
     torch.cuda.synchronize()
     e2e_s = sharding.max_over_ranks(time.perf_counter() - t0, dev)
     clocks = sampler.stop()
@@ -238,7 +241,10 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"LRW-shape batch={B}/GPU inference: speaker enc + video frontend + decoder (300 steps) + postnet; "
                                    "T=29, 96x96, S=19456 (BASELINE configs[2], north_star target)",
-                       "batch_per_gpu": B, "frames_per_clip": STEPS_PER_CLIP, "precision": "fp32 storage; GEMM-shaped layers on tcgen05 with 3xTF32 error compensation, recurrent step in exact fp32 FMA (mel rel err 3e-5 vs reference)",
+                       "batch_per_gpu": B, "frames_per_clip": STEPS_PER_CLIP, "precision": ("Conv3d stem: bf16 operands / fp32 accumulate on tcgen05 (BASELINE configs[2] 'bf16 frontend'); " if args.precision == "bf16"
+                                     else "Conv3d stem: 3xTF32 on tcgen05; ")
+                                    + "all other GEMM-shaped layers on tcgen05 with 3xTF32 error compensation, recurrent step 3xTF32 on mma.sync "
+                                      "(fp32 storage everywhere; mel rel err 3e-5 vs reference, features 1e-4 with the bf16 stem)",
                        "l2": "flushed between timed steps (256 MiB memset outside the event pair)", "parallelism": f"batch-sharded x{world}, no collective"},
             "e2e": {"value": frames / e2e_s, "unit": "mel-frames/s",
                     "h2d_bytes_per_step": int(video_h.numel() * 4 + wav_h.numel() * 4 + g_h.numel() * 4),
@@ -246,7 +252,7 @@ def main():
                     "api": "l2s_infer_host (C ABI, pinned host buffers)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "decode_persistent_kernel (300 steps, one launch)", "bound": "hbm", "achieved": achieved,
+            "roofline": {"kernel": ("decode3_kernel" if be.debug_flag("dec3") == 1 else "decode_persistent_kernel") + " (300 steps, one launch)", "bound": "hbm", "achieved": achieved,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": ncu_traffic_bytes(B),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "kernel_ms": dec_ms},
             "stage_ms": {k: statistics.mean(v) for k, v in spans.items()},

@@ -46,6 +46,14 @@ inline void pack_conv1d(const Context& c, const std::string& conv, const std::st
 // Tensor-core (3xTF32) operand form of a [N][taps*Kc] weight: every tap padded to Kcp = roundup(Kc,32)
 // (so a 32-wide K chunk never straddles taps), split into w_hi (low 13 mantissa bits cleared) and
 // w_lo = w - w_hi (exact).  Uploaded as name.hi / name.lo; meta name.kcp.
+// round-to-nearest-even fp32 -> bf16 (bit pattern)
+inline uint16_t bf16_bits(float v) {
+    uint32_t b; std::memcpy(&b, &v, 4);
+    if ((b & 0x7f800000u) == 0x7f800000u) return (uint16_t)(b >> 16);      // inf / nan
+    b += 0x7fffu + ((b >> 16) & 1u);
+    return (uint16_t)(b >> 16);
+}
+
 inline void upload_tc(Context& c, const std::string& name, const std::vector<float>& w, int N, int taps, int Kc) {
     const int Kcp = round_up(Kc, 32);
     std::vector<float> hi((size_t)N * taps * Kcp, 0.f), lo((size_t)N * taps * Kcp, 0.f);
@@ -95,6 +103,14 @@ inline void pack_video(Context& c) {
                                     ws[((size_t)o * 20 + kt * 4 + jh) * 48 + jw * 12 + (ph * 2 + pw) * 3 + ci] = v;
                                 }
         upload_tc(c, "v.stem.tc", ws, 24, 20, 48);
+        // bf16 form (precision = bf16): [32 rows][20 taps][4 positions x 16 channels], 12 real channels per position
+        std::vector<uint16_t> w16((size_t)32 * 20 * 64, 0);
+        for (int o = 0; o < 24; ++o)
+            for (int tap = 0; tap < 20; ++tap)
+                for (int jw = 0; jw < 4; ++jw)
+                    for (int ch = 0; ch < 12; ++ch)
+                        w16[((size_t)o * 20 + tap) * 64 + jw * 16 + ch] = bf16_bits(ws[((size_t)o * 20 + tap) * 48 + jw * 12 + ch]);
+        c.upload_raw("v.stem.tc16", w16.data(), w16.size());
     }
     int blk = 0;
     int in_half = 0, in_hp = 0, cin = 24, cin_phys = 24;       // stem output: identity layout

@@ -16,6 +16,8 @@
 //    once, as plain fp32.
 //  * Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 //    warps 2..5 = operand splitters during the main loop, then the epilogue (one TMEM lane per thread).
+//  * BF16 variant (the Conv3d stem at precision = bf16, BASELINE config 2 "bf16 frontend"): operands are single bf16
+//    arrays (no hi/lo pair), one tcgen05.mma.kind::f16 per 16-wide k-step, one 128-byte swizzle row (64 bf16) per tap.
 #pragma once
 #include <cuda.h>
 
@@ -83,6 +85,17 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// D=F32, A=B=BF16.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -117,7 +130,7 @@ constexpr int TC_WORKERS = 256;
 constexpr int TC_EPI = 256;
 constexpr int TC_THREADS_P = 64 + TC_WORKERS + TC_EPI;
 
-template <int BN, bool GATHER_A>
+template <int BN, bool GATHER_A, bool BF16 = false>
 __global__ void __launch_bounds__(TC_THREADS_P, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapWhi,
                const __grid_constant__ CUtensorMap mapWlo, const TcParams p) {
@@ -137,7 +150,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __shared__ int4 rinfo_s[TC_EPI / 32][32];               // per-warp row info (valid, seq, t, output row)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kchunks = (p.Kc + TC_BK - 1) / TC_BK;
+    static_assert(!BF16 || GATHER_A, "the bf16 variant gathers its A operand");
+    const int kchunks = BF16 ? 1 : (p.Kc + TC_BK - 1) / TC_BK;      // bf16: one 64-wide (128-byte) window per tap
     const int niter = p.debug_niter > 0 ? p.debug_niter : p.taps * kchunks;
     const int ntn = (p.N + BN - 1) / BN;
     const int ntiles = ((p.M + TC_BM - 1) / TC_BM) * ntn;
@@ -169,6 +183,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     uint8_t* st = smem + s * SM::STAGE_BYTES;
                     const bool skipA = GATHER_A || (p.debug_skip & 8);
                     if (p.debug_skip & 32) { mbar_arrive(&full[s]); continue; }      // skip all TMA traffic
+                    if (BF16) {                                  // one bf16 W tile: [BN rows][64 bf16] = W_BYTES
+                        mbar_expect_tx(&full[s], SM::W_BYTES);
+                        tma_load_2d(&mapWhi, &full[s], st + 2 * SM::A_BYTES, tap * 64, n0);
+                        continue;
+                    }
                     mbar_expect_tx(&full[s], (skipA ? 0 : SM::A_BYTES) + 2 * SM::W_BYTES);
                     if (!skipA) tma_load_2d(&mapA, &full[s], st, kc * TC_BK, m0 + (p.use_shift_table ? p.tap_shift[tap] : tap - p.pad));
                     tma_load_2d(&mapWhi, &full[s], st + 2 * SM::A_BYTES, tap * p.Kcp + kc * TC_BK, n0);
@@ -208,6 +227,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     if (++kc_ == kchunks) kc_ = 0;
                     uint64_t ahi = d_ahi[s], alo = d_alo[s], w = d_w[s];
                     uint32_t acc = it != 0;
+                    if (BF16) {                                  // 64 bf16 per stage row = four K=16 steps, one product each
+                        constexpr uint32_t idesc16 = umma_idesc_bf16(TC_BM, BN < 16 ? 16 : BN);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (!(p.debug_skip & 4)) umma_f16(tmem_d, ahi, w, idesc16, acc);
+                            acc = 1; ahi += 2; w += 2;               // 16 bf16 = 32 bytes = 2 descriptor units along K
+                        }
+                        umma_commit(&empty[s]);
+                        if (++s == STAGES) { s = 0; ph ^= 1; }
+                        continue;
+                    }
 #pragma unroll
                     for (int k = 0; k < TC_BK / 8; ++k) {
                         if (k < ksteps) {
@@ -226,7 +256,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // ===== A-side workers =====
         const int t = threadIdx.x - 64;                     // 0..255
         int git = 0;
-        if (GATHER_A) {
+        if (BF16) {
+            // bf16 gather: source rows of 16 bf16 (32 bytes) per space-to-depth position; a tap's window is 4 positions =
+            // 128 contiguous bytes = one swizzle row
+            const int c = t & 7, r0 = t >> 3;
+            const uint32_t off0 = (uint32_t)(r0 * 128 + ((c ^ (r0 & 7)) << 4));
+            const char* src0 = reinterpret_cast<const char*>(p.ga_A);
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int m0 = (tile / ntn) * TC_BM;
+                const char* base = src0 + ((long long)m0 + r0) * 32 + c * 16;
+                for (int tap = 0; tap < niter; ++tap, ++git) {
+                    const int s = git % STAGES, ph = (git / STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    const uint32_t dst = smem_u32(smem + s * SM::STAGE_BYTES) + off0;
+                    const char* sp = base + (long long)p.tap_shift[tap] * 32;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + i * 4096), "l"(sp + i * 1024) : "memory");
+                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&split[s])) : "memory");
+                }
+            }
+        } else if (GATHER_A) {
             const int c = t & 7, r0 = t >> 3;               // 16-byte chunk inside the 128-byte K row; first of 4 rows (stride 32)
             const long long rstep = 32LL * p.ga_lda;
             const uint32_t off0 = (uint32_t)(r0 * 128 + ((c ^ (r0 & 7)) << 4));     // (r0 + 32 i) & 7 == r0 & 7
@@ -323,9 +373,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 {
                     uint32_t v2[16];
                     tmem_ld16(tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, v);
-                    tmem_ld16(tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)(BN + c0), v2);
+                    if (!BF16) {
+                        tmem_ld16(tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)(BN + c0), v2);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+                        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+                    }
                 }
                 if (p.transposed) {                           // [B][N][L] output: consecutive rows are consecutive addresses already
                     if (valid) {
@@ -416,6 +468,20 @@ inline bool make_map_2d(CUtensorMap* map, const float* ptr, uint64_t cols, uint6
     return r == CUDA_SUCCESS;
 }
 
+// 2-D bf16 tensor map: inner dimension `cols` bf16 (contiguous), box = [64 cols = 128 bytes][box_rows].
+inline bool make_map_2d_bf16(CUtensorMap* map, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_rows) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 struct TcOperands {
     const float* A; int a_cols, a_rows, lda;         // activations
     const float* Whi; const float* Wlo; int w_cols;  // [N][w_cols], w_cols = taps*Kcp
@@ -456,6 +522,27 @@ inline const char* launch_tc_gemm(const TcOperands& o, TcParams p, cudaStream_t 
         e = BN == 32 ? launch_tc_inst<32, false>(grid, mA, mWh, mWl, p, s) : BN == 64 ? launch_tc_inst<64, false>(grid, mA, mWh, mWl, p, s)
                                                                                    : launch_tc_inst<128, false>(grid, mA, mWh, mWl, p, s);
     }
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+// The Conv3d stem with bf16 operands: A = space-to-depth rows of 16 bf16 per position (tap windows of 64 bf16 gathered by
+// cp.async), W = bf16 [32][taps*64] (rows >= N zero), N <= 32.  p.tap_shift / p.stem* describe the geometry as in the
+// fp32 path.
+inline const char* launch_tc_stem_bf16(const void* A16, const void* W16, int taps, TcParams p, cudaStream_t s) {
+    CUtensorMap mW;
+    if (p.N > 32) return "bf16 stem needs N <= 32";
+    if (reinterpret_cast<uintptr_t>(A16) & 15) return "bf16 stem needs 16-byte aligned rows";
+    if (!make_map_2d_bf16(&mW, W16, (uint64_t)taps * 64, 32, (uint64_t)taps * 64, 32)) return "cuTensorMapEncodeTiled(W bf16) failed";
+    p.ga_A = reinterpret_cast<const float*>(A16); p.taps = taps; p.use_shift_table = 1; p.ksteps_last = 4;
+    if (const char* e = getenv("L2S_TC_DEBUG_SKIP")) p.debug_skip = atoi(e);
+    static int num_sms = 0;
+    if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int ntiles = ceil_div(p.M, TC_BM);
+    dim3 grid(ntiles < num_sms ? ntiles : num_sms);
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<32, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<32>::TOTAL);
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+    tc_gemm_kernel<32, true, true><<<grid, TC_THREADS_P, TcSmem<32>::TOTAL, s>>>(mW, mW, mW, p);
+    e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
 

@@ -44,6 +44,21 @@ def test_video_frontend(be, golden):
     assert rel_err(f, golden["D_video_feat"]) < TOL
 
 
+def test_bf16_stem(be, golden):
+    """precision = bf16 (BASELINE configs[2]: 'bf16 3D frontend + fp32 decoder step'): the Conv3d stem multiplies bf16
+    operands on tcgen05; features and the full-span mel stay inside the parity bound."""
+    from lip2speech_b200 import _lib
+    f = be.video_fwd(synth.video(2, 29).cuda(), precision=_lib.PRECISION_BF16).cpu()
+    assert rel_err(f, golden["A_video_feat"]) < TOL
+    f = be.video_fwd(synth.video(1, 5, 88, 88, seed=5).cuda(), precision=_lib.PRECISION_BF16).cpu()
+    assert rel_err(f, golden["D_video_feat"]) < TOL
+    mel, lengths = be.infer(synth.video(2, 29).cuda(), synth.wav(2).cuda(), synth.gumbel(2, 29).cuda(), precision=_lib.PRECISION_BF16)
+    assert torch.equal(lengths.cpu(), golden["A_lengths"])
+    assert rel_err(mel.cpu(), golden["A_mel"]) < TOL
+    with pytest.raises(RuntimeError):
+        be.video_fwd(synth.video(1, 5).cuda(), precision=7)
+
+
 def test_postnet(be, golden):
     y = be.postnet_fwd(synth.mel_like(2, 77).cuda()).cpu()
     assert rel_err(y, golden["E_postnet"]) < TOL
