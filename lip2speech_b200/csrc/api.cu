@@ -718,14 +718,17 @@ __global__ void bcl_to_rows_kernel(const float* __restrict__ x, float* __restric
     }
 }
 
+// video_ready: optional event after which `video` is valid on the device (the host entry point copies the clips on a
+// second stream while the speaker encoder, which only needs the waveforms, already runs)
 static void infer_device(Context& c, const float* video, const float* wav, const float* gumbel, int B, int T, int H, int W, int S,
-                         int steps, float* mel_post, int64_t* lengths, int precision, cudaStream_t s) {
+                         int steps, float* mel_post, int64_t* lengths, int precision, cudaStream_t s, cudaEvent_t video_ready = nullptr) {
     float* emb = c.fbuf("ws.i.emb", (size_t)B * 256);
     float* feat = c.fbuf("ws.i.feat", (size_t)B * T * 768);
     float* visual = c.fbuf("ws.i.visual", (size_t)B * T * 1024);
     c.span_begin("speaker", s);
     speaker_forward(c, wav, B, S, emb, 1, s);
     c.span_end("speaker", s);
+    if (video_ready) L2S_CUDA(cudaStreamWaitEvent(s, video_ready, 0));
     c.span_begin("video", s);
     video_forward(c, video, B, T, H, W, feat, precision, s);
     c.span_end("video", s);
@@ -895,11 +898,18 @@ int l2s_infer_host(l2s_ctx* ctx, const float* video, const float* wav, const flo
     float* dv = c.fbuf("ws.h.video", nv); float* dw = c.fbuf("ws.h.wav", nw); float* dg = c.fbuf("ws.h.gumbel", ng);
     float* dm = c.fbuf("ws.h.mel", nm);
     int64_t* dl = static_cast<int64_t*>(c.buf("ws.h.len", (size_t)B * sizeof(int64_t)));
-    cudaStream_t s = 0;
-    L2S_CUDA(cudaMemcpyAsync(dv, video, nv * sizeof(float), cudaMemcpyHostToDevice, s));
+    // two non-blocking streams: the 100 MB clip copy overlaps the speaker encoder (which needs only the waveforms)
+    if (!c.host_stream) {
+        L2S_CUDA(cudaStreamCreateWithFlags(&c.host_stream, cudaStreamNonBlocking));
+        L2S_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+        L2S_CUDA(cudaEventCreateWithFlags(&c.copy_done, cudaEventDisableTiming));
+    }
+    cudaStream_t s = c.host_stream;
     L2S_CUDA(cudaMemcpyAsync(dw, wav, nw * sizeof(float), cudaMemcpyHostToDevice, s));
     L2S_CUDA(cudaMemcpyAsync(dg, gumbel, ng * sizeof(float), cudaMemcpyHostToDevice, s));
-    infer_device(c, dv, dw, dg, B, T, H, W, S, steps, dm, dl, precision, s);
+    L2S_CUDA(cudaMemcpyAsync(dv, video, nv * sizeof(float), cudaMemcpyHostToDevice, c.copy_stream));
+    L2S_CUDA(cudaEventRecord(c.copy_done, c.copy_stream));
+    infer_device(c, dv, dw, dg, B, T, H, W, S, steps, dm, dl, precision, s, c.copy_done);
     L2S_CUDA(cudaMemcpyAsync(mel_post, dm, nm * sizeof(float), cudaMemcpyDeviceToHost, s));
     L2S_CUDA(cudaMemcpyAsync(lengths, dl, (size_t)B * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     L2S_CUDA(cudaStreamSynchronize(s));

@@ -44,6 +44,8 @@ struct Context {
     std::map<std::string, int64_t> meta;      // small integers produced by packing (sizes, counts)
     int64_t launches = 0;
     int committed = 0;
+    cudaStream_t host_stream = nullptr, copy_stream = nullptr;   // l2s_infer_host: compute / clip-copy streams (created on first use)
+    cudaEvent_t copy_done = nullptr;
     bool use_dec3 = true;                     // stage-pipelined decode kernel for 8 < B <= 32 (L2S_DEC3=0: row-partitioned kernel for every B)
     bool use_tc = true;                       // tcgen05 GEMM path (L2S_TC=0 selects the exact-fp32 SIMT GEMMs for debugging)
     // optional stage timing (CUDA events on the caller's stream), enabled by l2s_set_profiling
@@ -109,6 +111,10 @@ struct Context {
             if (kv.second.e1) cudaEventDestroy(kv.second.e1);
         }
         spans.clear();
+        if (copy_done) cudaEventDestroy(copy_done);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (host_stream) cudaStreamDestroy(host_stream);
+        copy_done = nullptr; copy_stream = host_stream = nullptr;
     }
 };
 

@@ -115,6 +115,20 @@ def test_full_span_golden(be, golden):
     assert rel_err(mel.cpu(), golden["A_mel"]) < TOL
 
 
+def test_host_entry_point_matches_device_path(be, golden):
+    """l2s_infer_host (pinned host buffers, clip copy overlapped with the speaker encoder on a second stream) returns
+    exactly what the device-pointer entry point returns."""
+    video, wav, g = synth.video(2, 29), synth.wav(2), synth.gumbel(2, 29)
+    mel_h = torch.empty(2, 80, 300).pin_memory()
+    len_h = torch.empty(2, dtype=torch.int64).pin_memory()
+    for _ in range(2):                                   # second call reuses the streams / workspaces
+        mel_h.zero_()
+        be.infer_host(video.pin_memory(), wav.pin_memory(), g.pin_memory(), mel_h, len_h)
+        mel, lengths = be.infer(video.cuda(), wav.cuda(), g.cuda())
+        assert torch.equal(mel_h, mel.cpu()) and torch.equal(len_h, lengths.cpu())
+    assert rel_err(mel_h, golden["A_mel"]) < TOL
+
+
 def test_batch_33_two_clip_groups_vs_oracle(be, O, weights):
     """B=33 exercises the second 32-clip group and batch padding."""
     visual, face = synth.visual_features(33, 29, seed=21)
