@@ -95,6 +95,36 @@ int l2s_infer(l2s_ctx* ctx, const float* video, const float* wav, const float* g
 int l2s_infer_host(l2s_ctx* ctx, const float* video, const float* wav, const float* gumbel, int B, int T,
                    int H, int W, int S, int steps, float* mel_post, int64_t* lengths, int precision);
 
+/* ---- train-step tail (train.py:167-193) ---------------------------------------------------------------------------
+ * The forward-train / backward kernels of the model are not part of this library yet; these entry points cover the loss,
+ * the data-parallel gradient exchange (the only collective of the path) and the optimizer step on FLAT fp32 buffers. */
+
+/* Loss.forward (train_utils/losses.py:35-79) and the gradient of sum(losses) w.r.t. the model outputs, all device fp32:
+ * mel_out, mel_post, mel_target [B,80,M]; gate_logits, gate_target [B,M]; content_dis [rows,501].
+ * losses[4] = {KLD, mel_loss, postnet_mel_loss (x10), gate_loss}; g_* (same shapes as the outputs) may be NULL. */
+int l2s_loss_fwd_bwd(l2s_ctx* ctx, const float* mel_out, const float* mel_post, const float* gate_logits,
+                     const float* content_dis, const float* mel_target, const float* gate_target, int B, int M, int rows,
+                     float* losses, float* g_mel, float* g_post, float* g_gate, float* g_content_dis, void* stream);
+
+/* Data-parallel communicator (one process per GPU; NCCL over NVLink/NVSwitch, loaded with dlopen("libnccl.so.2")).
+ * Rank 0 obtains the id with l2s_nccl_unique_id (128 bytes) and hands it to the other ranks by any side channel
+ * (the Python host uses torch.distributed); every rank then calls l2s_comm_init. */
+int l2s_nccl_unique_id(void* out, int nbytes);
+int l2s_comm_init(l2s_ctx* ctx, const void* unique_id, int nbytes, int rank, int world);
+int l2s_comm_destroy(l2s_ctx* ctx);
+
+/* Between loss.backward() (train.py:184) and clip_grad_norm_ (191): flat_grads <- scale * sum over ranks (in place; with
+ * no communicator or world == 1 only the scaling), and sqnorm_out[0] <- ||flat_grads||^2 after scaling (device scalar, no
+ * host sync).  scale = 1/world reproduces the gradient of the global-batch mean loss. */
+int l2s_allreduce_grads(l2s_ctx* ctx, float* flat_grads, int64_t n, float scale, float* sqnorm_out, void* stream);
+
+/* clip_grad_norm_(max_norm) (train.py:191; max_norm <= 0: no clipping) + AdamW(amsgrad=True) step (train.py:102-104,193)
+ * on flat device buffers p, g, m, v, vmax of n floats; sqnorm = ||g||^2 from l2s_allreduce_grads; step = 1, 2, ...
+ * g is left clipped, as clip_grad_norm_ leaves p.grad. */
+int l2s_clip_adamw_step(l2s_ctx* ctx, float* p, float* g, float* m, float* v, float* vmax, int64_t n, const float* sqnorm,
+                        float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                        void* stream);
+
 /* Number of kernels this library has launched on ctx since creation (bench.py `gpu_launches`). */
 int64_t l2s_launch_count(const l2s_ctx* ctx);
 

@@ -18,7 +18,9 @@ PRECISION_FP32, PRECISION_BF16 = 0, 1
 
 EXPORTS = ("l2s_version", "l2s_create", "l2s_destroy", "l2s_last_error", "l2s_bind_weight", "l2s_commit_weights",
            "l2s_video_fwd", "l2s_speaker_fwd", "l2s_decoder_infer", "l2s_decoder_forward", "l2s_postnet_fwd", "l2s_infer", "l2s_infer_host",
-           "l2s_launch_count", "l2s_debug_read", "l2s_set_profiling", "l2s_span_ms")
+           "l2s_launch_count", "l2s_debug_read", "l2s_set_profiling", "l2s_span_ms",
+           "l2s_loss_fwd_bwd", "l2s_nccl_unique_id", "l2s_comm_init", "l2s_comm_destroy", "l2s_allreduce_grads", "l2s_clip_adamw_step")
+NCCL_UNIQUE_ID_BYTES = 128
 
 _lib = None
 _lock = threading.Lock()
@@ -52,6 +54,13 @@ def load() -> C.CDLL:
         lib.l2s_set_profiling.argtypes = [vp, i]
         lib.l2s_span_ms.argtypes = [vp, C.c_char_p]; lib.l2s_span_ms.restype = C.c_double
         lib.l2s_debug_read.argtypes = [vp, C.c_char_p, fp, C.c_int64]; lib.l2s_debug_read.restype = C.c_int64
+        f = C.c_float
+        lib.l2s_loss_fwd_bwd.argtypes = [vp, fp, fp, fp, fp, fp, fp, i, i, i, fp, fp, fp, fp, fp, vp]
+        lib.l2s_nccl_unique_id.argtypes = [vp, i]
+        lib.l2s_comm_init.argtypes = [vp, vp, i, i, i]
+        lib.l2s_comm_destroy.argtypes = [vp]
+        lib.l2s_allreduce_grads.argtypes = [vp, fp, C.c_int64, f, fp, vp]
+        lib.l2s_clip_adamw_step.argtypes = [vp, fp, fp, fp, fp, fp, C.c_int64, fp, f, f, f, f, f, f, i, vp]
         _lib = lib
         return lib
 
@@ -193,6 +202,42 @@ class Backend:
             assert t.device.type == "cpu" and t.dtype == torch.float32 and t.is_contiguous()
         self._check(self.lib.l2s_infer_host(self.h, video.data_ptr(), wav.data_ptr(), gumbel.data_ptr(), B, T, H, W, wav.shape[1], steps,
                                             mel_out.data_ptr(), C.c_void_p(lengths_out.data_ptr()), precision), "l2s_infer_host")
+
+    # ---- train-step tail (train.py:167-193) --------------------------------------------------------
+    def loss_fwd_bwd(self, mel_out, mel_post, gate_logits, content_dis, mel_target, gate_target, want_grads: bool = True):
+        """Loss.forward (train_utils/losses.py:35-79) -> (losses[4] = KLD, mel, 10*postnet, gate; grads or None)."""
+        mel_out, mel_post, gate_logits, content_dis, mel_target, gate_target = (
+            _f32c(t, self.device) for t in (mel_out, mel_post, gate_logits, content_dis, mel_target, gate_target))
+        B, _, M = mel_out.shape
+        assert mel_post.shape == mel_out.shape == mel_target.shape and gate_logits.numel() == B * M == gate_target.numel()
+        assert content_dis.shape[-1] == 501
+        rows = content_dis.numel() // 501
+        losses = torch.empty(4, device=self.device)
+        grads = [torch.empty_like(t) for t in (mel_out, mel_post, gate_logits, content_dis)] if want_grads else [None] * 4
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        self._check(self.lib.l2s_loss_fwd_bwd(self.h, ptr(mel_out), ptr(mel_post), ptr(gate_logits), ptr(content_dis), ptr(mel_target),
+                                              ptr(gate_target), B, M, rows, ptr(losses), *(ptr(g) for g in grads), self._stream()),
+                    "l2s_loss_fwd_bwd")
+        return losses, (grads if want_grads else None)
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        buf = C.create_string_buffer(bytes(unique_id), NCCL_UNIQUE_ID_BYTES)
+        self._check(self.lib.l2s_comm_init(self.h, buf, NCCL_UNIQUE_ID_BYTES, rank, world), "l2s_comm_init")
+
+    def comm_destroy(self):
+        self._check(self.lib.l2s_comm_destroy(self.h), "l2s_comm_destroy")
+
+    def allreduce_grads(self, flat_grads: torch.Tensor, scale: float, sqnorm_out: torch.Tensor):
+        assert flat_grads.is_cuda and flat_grads.dtype == torch.float32 and flat_grads.is_contiguous()
+        self._check(self.lib.l2s_allreduce_grads(self.h, C.c_void_p(flat_grads.data_ptr()), flat_grads.numel(), scale,
+                                                 C.c_void_p(sqnorm_out.data_ptr()), self._stream()), "l2s_allreduce_grads")
+
+    def clip_adamw_step(self, p, g, m, v, vmax, sqnorm, max_norm, lr, beta1, beta2, eps, weight_decay, step):
+        for t in (p, g, m, v, vmax):
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == p.numel()
+        self._check(self.lib.l2s_clip_adamw_step(self.h, *(C.c_void_p(t.data_ptr()) for t in (p, g, m, v, vmax)), p.numel(),
+                                                 C.c_void_p(sqnorm.data_ptr()) if sqnorm is not None else None, max_norm, lr, beta1, beta2,
+                                                 eps, weight_decay, step, self._stream()), "l2s_clip_adamw_step")
 
     def set_profiling(self, enabled: bool):
         self.lib.l2s_set_profiling(self.h, int(enabled))

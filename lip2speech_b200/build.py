@@ -16,7 +16,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libl2s_b200.so")
 SOURCES = ["api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr"]
+              "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr", "-ldl"]
 
 
 def _nvcc() -> str:

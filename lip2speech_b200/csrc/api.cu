@@ -10,6 +10,9 @@
 #include "misc.cuh"
 #include "pack.h"
 #include "tc_gemm.cuh"
+#include "train_step.cuh"
+#include <dlfcn.h>
+#include <nccl.h>
 #include "video.cuh"
 
 using namespace l2s;
@@ -737,6 +740,8 @@ static void infer_device(Context& c, const float* video, const float* wav, const
     decoder_infer(c, visual, emb, gumbel, B, T, steps, mel_post, lengths, nullptr, s);
 }
 
+static void destroy_comm_quiet(Context& c);
+
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
@@ -776,6 +781,7 @@ void l2s_destroy(l2s_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->c.device);
     cudaDeviceSynchronize();
+    destroy_comm_quiet(ctx->c);
     ctx->c.free_all();
     delete ctx;
 }
@@ -913,6 +919,138 @@ int l2s_infer_host(l2s_ctx* ctx, const float* video, const float* wav, const flo
     L2S_CUDA(cudaMemcpyAsync(mel_post, dm, nm * sizeof(float), cudaMemcpyDeviceToHost, s));
     L2S_CUDA(cudaMemcpyAsync(lengths, dl, (size_t)B * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     L2S_CUDA(cudaStreamSynchronize(s));
+    API_END(ctx)
+}
+
+// ---- train-step tail ------------------------------------------------------------------------------------------------
+namespace {
+struct NcclApi {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi& nccl_api() {
+    static NcclApi a;
+    if (!a.h) {
+        a.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!a.h) throw L2sError(L2S_ERR_CUDA, std::string("dlopen(libnccl.so.2): ") + dlerror());
+        auto sym = [&](const char* n) { void* p = dlsym(a.h, n); if (!p) throw L2sError(L2S_ERR_CUDA, std::string("libnccl.so.2 lacks ") + n); return p; };
+        a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(sym("ncclGetUniqueId"));
+        a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(sym("ncclCommInitRank"));
+        a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(sym("ncclAllReduce"));
+        a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(sym("ncclCommDestroy"));
+        a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(sym("ncclGetErrorString"));
+    }
+    return a;
+}
+void nccl_check(ncclResult_t r, const char* what) {
+    if (r != ncclSuccess) throw L2sError(L2S_ERR_CUDA, std::string(what) + ": " + nccl_api().GetErrorString(r));
+}
+int ts_grid(Context& c, size_t n4) {
+    const size_t want = (n4 + TS_THREADS - 1) / TS_THREADS;
+    const size_t cap = (size_t)c.num_sms * 8;                 // a multiple of the SM count; each thread streams several float4
+    return (int)std::max<size_t>(1, std::min(want, cap));
+}
+}  // namespace
+
+}  // extern "C"
+static void destroy_comm_quiet(Context& c) {
+    if (!c.nccl_comm) return;
+    try { nccl_api().CommDestroy(static_cast<ncclComm_t>(c.nccl_comm)); } catch (...) {}
+    c.nccl_comm = nullptr;
+}
+extern "C" {
+
+int l2s_nccl_unique_id(void* out, int nbytes) {
+    if (!out || nbytes < (int)sizeof(ncclUniqueId)) return L2S_ERR_INVALID;
+    try {
+        ncclUniqueId id;
+        nccl_check(nccl_api().GetUniqueId(&id), "ncclGetUniqueId");
+        std::memcpy(out, &id, sizeof(id));
+    } catch (const std::exception& e) { g_create_err = e.what(); return L2S_ERR_CUDA; }
+    return L2S_OK;
+}
+
+int l2s_comm_init(l2s_ctx* ctx, const void* unique_id, int nbytes, int rank, int world) {
+    if (!ctx) return L2S_ERR_INVALID;
+    API_BEGIN
+    Context& c = ctx->c;
+    if (!unique_id || nbytes < (int)sizeof(ncclUniqueId) || world < 1 || rank < 0 || rank >= world) throw L2sError(L2S_ERR_INVALID, "comm_init: bad arguments");
+    if (c.nccl_comm) throw L2sError(L2S_ERR_INVALID, "comm_init: communicator already initialised");
+    L2S_CUDA(cudaSetDevice(c.device));
+    ncclUniqueId id;
+    std::memcpy(&id, unique_id, sizeof(id));
+    ncclComm_t comm = nullptr;
+    nccl_check(nccl_api().CommInitRank(&comm, world, id, rank), "ncclCommInitRank");
+    c.nccl_comm = comm; c.world = world; c.rank = rank;
+    API_END(ctx)
+}
+
+int l2s_comm_destroy(l2s_ctx* ctx) {
+    if (!ctx) return L2S_ERR_INVALID;
+    API_BEGIN
+    Context& c = ctx->c;
+    if (c.nccl_comm) { nccl_check(nccl_api().CommDestroy(static_cast<ncclComm_t>(c.nccl_comm)), "ncclCommDestroy"); c.nccl_comm = nullptr; c.world = 1; c.rank = 0; }
+    API_END(ctx)
+}
+
+int l2s_allreduce_grads(l2s_ctx* ctx, float* flat_grads, int64_t n, float scale, float* sqnorm_out, void* stream) {
+    if (!ctx) return L2S_ERR_INVALID;
+    API_BEGIN
+    Context& c = ctx->c;
+    if (!flat_grads || n <= 0 || !sqnorm_out) throw L2sError(L2S_ERR_INVALID, "allreduce_grads: bad arguments");
+    if (reinterpret_cast<uintptr_t>(flat_grads) & 15) throw L2sError(L2S_ERR_INVALID, "allreduce_grads: the flat buffer must be 16-byte aligned");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    L2S_CUDA(cudaSetDevice(c.device));
+    if (c.nccl_comm && c.world > 1)
+        nccl_check(nccl_api().AllReduce(flat_grads, flat_grads, (size_t)n, ncclFloat32, ncclSum, static_cast<ncclComm_t>(c.nccl_comm), s), "ncclAllReduce");
+    const int grid = ts_grid(c, (size_t)n / 4);
+    double* part = static_cast<double*>(c.buf("ws.t.part", (size_t)c.num_sms * 8 * 4 * sizeof(double)));
+    grad_scale_sqnorm_kernel<<<grid, TS_THREADS, 0, s>>>(flat_grads, (size_t)n, scale, part);
+    check_launch(c, "grad scale + norm");
+    sqnorm_finish_kernel<<<1, 32, 0, s>>>(part, grid, sqnorm_out);
+    check_launch(c, "grad norm finish");
+    API_END(ctx)
+}
+
+int l2s_clip_adamw_step(l2s_ctx* ctx, float* p, float* g, float* m, float* v, float* vmax, int64_t n, const float* sqnorm,
+                        float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay, int step, void* stream) {
+    if (!ctx) return L2S_ERR_INVALID;
+    API_BEGIN
+    Context& c = ctx->c;
+    if (!p || !g || !m || !v || !vmax || n <= 0 || step < 1 || (max_norm > 0.f && !sqnorm)) throw L2sError(L2S_ERR_INVALID, "clip_adamw_step: bad arguments");
+    for (const void* q : {(const void*)p, (const void*)g, (const void*)m, (const void*)v, (const void*)vmax})
+        if (reinterpret_cast<uintptr_t>(q) & 15) throw L2sError(L2S_ERR_INVALID, "clip_adamw_step: flat buffers must be 16-byte aligned");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    L2S_CUDA(cudaSetDevice(c.device));
+    AdamWParams a{lr, beta1, beta2, eps, weight_decay, max_norm,
+                  (float)(1.0 - std::pow((double)beta1, (double)step)), (float)std::sqrt(1.0 - std::pow((double)beta2, (double)step))};
+    clip_adamw_kernel<<<ts_grid(c, (size_t)n / 4), TS_THREADS, 0, s>>>(p, g, m, v, vmax, (size_t)n, sqnorm, a);
+    check_launch(c, "clip + AdamW");
+    API_END(ctx)
+}
+
+int l2s_loss_fwd_bwd(l2s_ctx* ctx, const float* mel_out, const float* mel_post, const float* gate_logits, const float* content_dis,
+                     const float* mel_target, const float* gate_target, int B, int M, int rows, float* losses,
+                     float* g_mel, float* g_post, float* g_gate, float* g_content_dis, void* stream) {
+    if (!ctx) return L2S_ERR_INVALID;
+    API_BEGIN
+    Context& c = ctx->c;
+    if (!mel_out || !mel_post || !gate_logits || !content_dis || !mel_target || !gate_target || !losses || B <= 0 || M <= 0 || rows <= 0)
+        throw L2sError(L2S_ERR_INVALID, "loss_fwd_bwd: bad arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    L2S_CUDA(cudaSetDevice(c.device));
+    const size_t n_mel = (size_t)B * 80 * M, n_gate = (size_t)B * M, n_dis = (size_t)rows * 501;
+    const int grid = ts_grid(c, std::max(n_mel, n_dis));
+    double* part = static_cast<double*>(c.buf("ws.t.part", (size_t)c.num_sms * 8 * 4 * sizeof(double)));
+    loss_partial_kernel<<<grid, TS_THREADS, 0, s>>>(mel_out, mel_post, mel_target, n_mel, gate_logits, gate_target, n_gate, content_dis, n_dis, 501,
+                                                    g_mel, g_post, g_gate, g_content_dis, part);
+    check_launch(c, "loss partial sums");
+    loss_finish_kernel<<<1, 32, 0, s>>>(part, grid, n_mel, n_gate, (size_t)rows, losses);
+    check_launch(c, "loss finish");
     API_END(ctx)
 }
 
