@@ -1044,7 +1044,7 @@ int l2s_loss_fwd_bwd(l2s_ctx* ctx, const float* mel_out, const float* mel_post, 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     L2S_CUDA(cudaSetDevice(c.device));
     const size_t n_mel = (size_t)B * 80 * M, n_gate = (size_t)B * M, n_dis = (size_t)rows * 501;
-    const int grid = ts_grid(c, std::max(n_mel, n_dis));
+    const int grid = ts_grid(c, std::max(n_mel, n_dis) / 4);      // a thread handles ~4 elements of the longest array
     double* part = static_cast<double*>(c.buf("ws.t.part", (size_t)c.num_sms * 8 * 4 * sizeof(double)));
     loss_partial_kernel<<<grid, TS_THREADS, 0, s>>>(mel_out, mel_post, mel_target, n_mel, gate_logits, gate_target, n_gate, content_dis, n_dis, 501,
                                                     g_mel, g_post, g_gate, g_content_dis, part);

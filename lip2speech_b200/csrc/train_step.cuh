@@ -14,7 +14,6 @@
 namespace l2s {
 
 constexpr int TS_THREADS = 256;
-constexpr int TS_MAX_BLOCKS = 148 * 8;
 
 __device__ __forceinline__ float block_sum_256(float v, float* sh) {
     v = warp_sum(v);
@@ -29,39 +28,41 @@ __device__ __forceinline__ float block_sum_256(float v, float* sh) {
     return r;                                                // valid in thread 0
 }
 
-// g <- g*scale ; partial[blockIdx] = sum over this block's elements of (g*scale)^2 (double accumulation across the
-// grid-stride iterations of a thread, fixed order: deterministic for a fixed grid)
+// g <- g*scale ; partial[blockIdx] = sum over this block's elements of (g*scale)^2.  A thread adds at most a few dozen
+// float4 in fp32, blocks are combined in double in a fixed order: deterministic for a fixed grid.
 __global__ void __launch_bounds__(TS_THREADS) grad_scale_sqnorm_kernel(float* __restrict__ g, size_t n, float scale, double* __restrict__ partial) {
     __shared__ float sh[TS_THREADS / 32];
     const size_t n4 = n / 4;
     float4* g4 = reinterpret_cast<float4*>(g);
-    double acc = 0.0;
+    float acc = 0.f;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
         float4 v = g4[i];
         v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
         g4[i] = v;
-        acc += (double)(v.x * v.x + v.y * v.y) + (double)(v.z * v.z + v.w * v.w);
+        acc += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
     }
     if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {          // tail (n not a multiple of 4)
         const size_t i = n4 * 4 + threadIdx.x;
         const float v = g[i] * scale;
         g[i] = v;
-        acc += (double)v * v;
+        acc += v * v;
     }
-    // block reduction in double through two float halves would lose the point of double: reduce hi/lo separately
-    const float hi = (float)acc, lo = (float)(acc - (double)hi);
-    const float shi = block_sum_256(hi, sh);
-    __syncthreads();
-    const float slo = block_sum_256(lo, sh);
-    if (threadIdx.x == 0) partial[blockIdx.x] = (double)shi + (double)slo;
+    const float s = block_sum_256(acc, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = (double)s;
+}
+
+// one warp: lane l adds partial[l], partial[l+32], ... in order, then a shuffle tree (fixed order)
+__device__ __forceinline__ double warp_sum_partials(const double* __restrict__ partial, int nblocks, int stride, int offset) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nblocks; i += 32) s += partial[(size_t)i * stride + offset];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
 }
 
 __global__ void sqnorm_finish_kernel(const double* __restrict__ partial, int nblocks, float* __restrict__ sqnorm_out) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double s = 0.0;
-        for (int i = 0; i < nblocks; ++i) s += partial[i];
-        *sqnorm_out = (float)s;
-    }
+    const double s = warp_sum_partials(partial, nblocks, 1, 0);
+    if (threadIdx.x == 0) *sqnorm_out = (float)s;
 }
 
 struct AdamWParams {
@@ -153,10 +154,10 @@ __global__ void __launch_bounds__(TS_THREADS) loss_partial_kernel(const float* _
 }
 
 __global__ void loss_finish_kernel(const double* __restrict__ part, int nblocks, size_t n_mel, size_t n_gate, size_t n_rows, float* __restrict__ losses) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double s[4] = {0, 0, 0, 0};
-        for (int i = 0; i < nblocks; ++i)
-            for (int j = 0; j < 4; ++j) s[j] += part[(size_t)i * 4 + j];
+    double s[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s[j] = warp_sum_partials(part, nblocks, 4, j);
+    if (threadIdx.x == 0) {
         losses[0] = (float)(s[0] / (double)n_rows);
         losses[1] = (float)(s[1] / (double)n_mel);
         losses[2] = (float)(10.0 * s[2] / (double)n_mel);
