@@ -44,6 +44,15 @@ class Loss(torch.nn.Module):
         return losses
 
 
+def flat_layout(sizes):
+    """Offsets of the parameters inside the flat buffers (every parameter starts 16-byte aligned) and the total length."""
+    offsets, off = [], 0
+    for n in sizes:
+        offsets.append(off)
+        off += (n + 3) // 4 * 4
+    return offsets, off
+
+
 class ClipAdamW:
     """optim.zero_grad() / [backward] / clip_grad_norm_ / optim.step() of train.py:180-193 on flat buffers.
 
@@ -58,12 +67,7 @@ class ClipAdamW:
         dev = self.params[0].device
         self.be = backend or _lib.backend(dev.index or 0)
         self.lr, self.betas, self.eps, self.weight_decay, self.max_norm, self.world = lr, betas, eps, weight_decay, max_norm, world
-        sizes = [p.numel() for p in self.params]
-        self.offsets, off = [], 0
-        for n in sizes:
-            self.offsets.append(off)
-            off += (n + 3) // 4 * 4                       # every parameter starts 16-byte aligned
-        self.n = off
+        self.offsets, self.n = flat_layout([p.numel() for p in self.params])
         self.p = torch.zeros(self.n, device=dev)
         self.g = torch.zeros(self.n, device=dev)
         self.m = torch.zeros(self.n, device=dev)
@@ -106,3 +110,4 @@ def init_data_parallel(backend: "_lib.Backend", rank: int, world: int, group=Non
     else:
         dist.broadcast(buf, 0, group=group)
     backend.comm_init(bytes(buf.tolist()), rank, world)
+    return bytes(buf.tolist())
