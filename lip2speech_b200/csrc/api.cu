@@ -9,6 +9,7 @@
 #include "lstm.cuh"
 #include "misc.cuh"
 #include "pack.h"
+#include "pw_mma.cuh"
 #include "tc_gemm.cuh"
 #include "train_step.cuh"
 #include <dlfcn.h>
@@ -71,6 +72,20 @@ static void linear(Context& c, const float* A, int lda, const std::string& wname
 // Dense (1-tap) GEMM described SIMT-style (GemmParams with W unset): tcgen05 path when TMA alignment allows, else SIMT.
 static void gemm_auto(Context& c, GemmParams g, const std::string& wname, cudaStream_t s, const char* what) {
     if (g.L_out == 0) { g.L_out = g.M; g.L_in = g.M; }
+    // tall-skinny pointwise convolutions of the trunk (K, N <= 240, >= 16 K rows: stages 2 and 3): streaming mma.sync kernel
+    // (measured 50 vs 70 us at 12x12, 37 vs 40 us at 6x6; at 3x3 — 8 K rows — the tcgen05 GEMM is faster, 31 vs 40 us)
+    if (c.use_tc && c.use_pw && g.taps == 1 && g.stride == 1 && !g.stem && g.Kc <= 240 && g.M >= 16384 && (g.act == ACT_NONE || g.act == ACT_RELU) &&
+        !g.addrow && !g.addpos && !g.resid && !g.transposed && (g.lda % 4) == 0 && (g.Kc % 4) == 0 && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0) {
+        PwParams p{};
+        p.A = g.A; p.lda = g.lda; p.M = g.M; p.N = g.N; p.Kc = g.Kc;
+        p.Whi = c.dev(wname + ".hi"); p.Wlo = c.dev(wname + ".lo"); p.kcp = (int)c.meta.at(wname + ".kcp");
+        p.bias = g.bias; p.relu = g.act == ACT_RELU; p.C = g.C; p.ldc = g.ldc;
+        p.cstride = g.cstride; p.coff = g.coff; p.chalf = g.chalf; p.chp = g.chp;
+        const char* err = launch_pw_mma(p, c.num_sms, s);
+        if (err) throw L2sError(L2S_ERR_CUDA, std::string(what) + " (pointwise mma): " + err);
+        c.launches++;
+        return;
+    }
     if (c.use_tc && g.taps == 1 && g.stride == 1 && !g.stem && (g.lda % 4) == 0 && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0) {
         const int kcp = (int)c.meta.at(wname + ".kcp");
         TcOperands o{g.A, g.Kc, g.M, g.lda, c.dev(wname + ".hi"), c.dev(wname + ".lo"), kcp};
@@ -773,6 +788,7 @@ int l2s_create(l2s_ctx** out, int device) {
     ctx->c.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     if (const char* e = getenv("L2S_TC")) ctx->c.use_tc = (e[0] != '0');
     if (const char* e = getenv("L2S_DEC3")) ctx->c.use_dec3 = (e[0] != '0');
+    if (const char* e = getenv("L2S_PW")) ctx->c.use_pw = (e[0] != '0');
     *out = ctx;
     return L2S_OK;
 }

@@ -1,0 +1,143 @@
+// Pointwise (1x1) convolution of the ShuffleNetV2 trunk as a STREAMING tensor-core GEMM (reference
+// shufflenetv2.py:51-89: every 1x1 Conv2d + BatchNorm2d + ReLU of the InvertedResidual blocks).
+//
+//   C[m, map(n)] = relu( sum_k A[m, k] * W[n, k] + bias[n] ),   M = frames*h*w rows (8 K .. 535 K), K, N in 24..232
+//
+// These GEMMs are tiny in K and N and huge in M: HBM-bound (64 MB in+out at stage 2 = 10 us) with ~1 GFLOP of math.
+// The tcgen05 pipeline (TMA -> smem split -> MMA -> TMEM -> transposed store) pays its per-tile latency chain 7 times
+// per SM at K = 64 and ran them at 7x the memory bound.  Here every warp streams 16-row tiles straight from global
+// memory into mma.sync fragments (no staging, no CTA-level synchronisation in the loop), so 16 warps per SM keep enough
+// loads in flight to cover HBM latency (measured at B=32: 50 us vs 70 us at stage 2, 37 vs 40 us at stage 3; tensor pipe
+// 28-43 % active, DRAM traffic 2x the compulsory bytes because the two branches of a block write interleaved channels
+// of the same sectors at different times — still 3-5x above the memory bound, the next thing to fix here):
+//  * A: lane (g = lane>>2, t = lane&3) reads A[row g / g+8][k0 + 4t .. +3] as two LDG.128 per 16-wide k chunk (each row
+//    contributes one full 64-byte segment per chunk), splits them into tf32 hi / lo in registers;
+//  * W: the slice's rows, pre-split hi / lo at pack time, resident in shared memory ([64][Kp + 16] each, LDS.128
+//    conflict-free); N is cut into slices of 64 columns (grid.y) so the accumulators stay at 32 registers;
+//  * 3xTF32 error compensation (a_lo*w_hi + a_hi*w_lo + a_hi*w_hi), fp32 accumulation: same accuracy class as the
+//    tcgen05 path; MMA column t / t+4 of k-step s <-> real k = k0 + 4t + 2s / + 2s + 1 for both operands;
+//  * epilogue straight from the accumulator fragments: bias + ReLU, ShuffleNet's concat + channel_shuffle folded into
+//    the store address (cstride / coff / chalf / chp as in gemm.cuh).
+#pragma once
+#include "matvec.cuh"
+
+namespace l2s {
+
+constexpr int PW_THREADS = 256;
+constexpr int PW_NT = 8;                  // n-tiles of 8 columns per slice
+constexpr int PW_NSLICE = 8 * PW_NT;      // 64 output columns per CTA
+
+struct PwParams {
+    const float* A; int lda;
+    int M, N, Kc;
+    const float* Whi; const float* Wlo; int kcp;       // packed [N][kcp], zero-padded beyond Kc
+    const float* bias; int relu;
+    float* C; int ldc;
+    int cstride, coff, chalf, chp;
+    int Kp, ldw;                                        // Kp = round_up(Kc, 16); ldw = Kp or Kp + 16, whichever is 16 mod 32
+};
+
+__global__ void __launch_bounds__(PW_THREADS, 2) pw_mma_kernel(const PwParams p) {
+    extern __shared__ __align__(16) float smem[];
+    float* whi = smem;
+    float* wlo = smem + (size_t)PW_NSLICE * p.ldw;
+    const int n_base = blockIdx.y * PW_NSLICE;
+    for (int i = threadIdx.x; i < PW_NSLICE * (p.Kp / 4); i += PW_THREADS) {
+        const int r = i / (p.Kp / 4), c4 = i - r * (p.Kp / 4);
+        float4 h = make_float4(0.f, 0.f, 0.f, 0.f), l = h;
+        if (n_base + r < p.N) {
+            h = __ldg(reinterpret_cast<const float4*>(p.Whi + (size_t)(n_base + r) * p.kcp) + c4);
+            l = __ldg(reinterpret_cast<const float4*>(p.Wlo + (size_t)(n_base + r) * p.kcp) + c4);
+        }
+        *reinterpret_cast<float4*>(whi + (size_t)r * p.ldw + 4 * c4) = h;
+        *reinterpret_cast<float4*>(wlo + (size_t)r * p.ldw + 4 * c4) = l;
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int nchunks = p.Kp / 16;
+    const int ntiles = (p.M + 15) / 16;
+    const int wstride = gridDim.x * (PW_THREADS / 32);
+    // per-lane epilogue constants: this lane owns columns n_base + 8*nt + 2t, +1
+    const float* wh_lane = whi + (size_t)g * p.ldw + 4 * t;
+    const float* wl_lane = wlo + (size_t)g * p.ldw + 4 * t;
+
+    for (int tile = blockIdx.x * (PW_THREADS / 32) + warp; tile < ntiles; tile += wstride) {
+        const int r0 = tile * 16 + g, r1 = r0 + 8;
+        const bool v0 = r0 < p.M, v1 = r1 < p.M;
+        const float* a0p = p.A + (size_t)(v0 ? r0 : 0) * p.lda + 4 * t;
+        const float* a1p = p.A + (size_t)(v1 ? r1 : 0) * p.lda + 4 * t;
+        float acc[PW_NT][4];
+#pragma unroll
+        for (int nt = 0; nt < PW_NT; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+        float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), xb = xa;
+        if (4 * t < p.Kc) { xa = __ldg(reinterpret_cast<const float4*>(a0p)); xb = __ldg(reinterpret_cast<const float4*>(a1p)); }
+        for (int c = 0; c < nchunks; ++c) {
+            float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb = na;
+            if (c + 1 < nchunks && (c + 1) * 16 + 4 * t < p.Kc) {          // next chunk in flight while this one is multiplied
+                na = __ldg(reinterpret_cast<const float4*>(a0p + (c + 1) * 16));
+                nb = __ldg(reinterpret_cast<const float4*>(a1p + (c + 1) * 16));
+            }
+            const float av[4] = {xa.x, xa.y, xa.z, xa.w}, bv[4] = {xb.x, xb.y, xb.z, xb.w};
+            uint32_t ah[4], al[4], bh[4], bl[4];                           // rows g (a*) and g+8 (b*)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { split_tf32(av[i], ah[i], al[i]); split_tf32(bv[i], bh[i], bl[i]); }
+#pragma unroll
+            for (int nt = 0; nt < PW_NT; ++nt) {
+                const float4 wh = *reinterpret_cast<const float4*>(wh_lane + (size_t)nt * 8 * p.ldw + c * 16);
+                const float4 wl = *reinterpret_cast<const float4*>(wl_lane + (size_t)nt * 8 * p.ldw + c * 16);
+                const uint32_t whv[4] = {__float_as_uint(wh.x), __float_as_uint(wh.y), __float_as_uint(wh.z), __float_as_uint(wh.w)};
+                const uint32_t wlv[4] = {__float_as_uint(wl.x), __float_as_uint(wl.y), __float_as_uint(wl.z), __float_as_uint(wl.w)};
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    mma_tf32(acc[nt], al[2 * s], bl[2 * s], al[2 * s + 1], bl[2 * s + 1], whv[2 * s], whv[2 * s + 1]);
+                    mma_tf32(acc[nt], ah[2 * s], bh[2 * s], ah[2 * s + 1], bh[2 * s + 1], wlv[2 * s], wlv[2 * s + 1]);
+                    mma_tf32(acc[nt], ah[2 * s], bh[2 * s], ah[2 * s + 1], bh[2 * s + 1], whv[2 * s], whv[2 * s + 1]);
+                }
+            }
+            xa = na; xb = nb;
+        }
+        // epilogue: acc[nt] = {(r0, n), (r0, n+1), (r1, n), (r1, n+1)}, n = n_base + 8 nt + 2 t
+#pragma unroll
+        for (int nt = 0; nt < PW_NT; ++nt) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int n = n_base + nt * 8 + 2 * t + j;
+                if (n < p.N) {
+                    const float b = p.bias ? __ldg(p.bias + n) : 0.f;
+                    int l = n * p.cstride + p.coff;
+                    if (p.chalf > 0 && l >= p.chalf) l = l - p.chalf + p.chp;
+                    float y0 = acc[nt][j] + b, y1 = acc[nt][2 + j] + b;
+                    if (p.relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+                    if (v0) p.C[(size_t)r0 * p.ldc + l] = y0;
+                    if (v1) p.C[(size_t)r1 * p.ldc + l] = y1;
+                }
+            }
+        }
+    }
+}
+
+inline int pw_ldw(int Kp) { return (Kp % 32 == 0) ? Kp + 16 : Kp; }      // rows 16 floats apart modulo the 32 banks: LDS.128 conflict-free
+inline size_t pw_smem_bytes(int Kc) { const int Kp = (Kc + 15) / 16 * 16; return (size_t)2 * PW_NSLICE * pw_ldw(Kp) * sizeof(float); }
+
+// Returns nullptr on success.
+inline const char* launch_pw_mma(PwParams p, int num_sms, cudaStream_t s) {
+    if ((p.lda & 3) || (p.Kc & 3) || (reinterpret_cast<uintptr_t>(p.A) & 15) || (p.kcp & 3)) return "pointwise conv needs 16-byte aligned rows";
+    p.Kp = (p.Kc + 15) / 16 * 16;
+    p.ldw = pw_ldw(p.Kp);
+    if (p.Kp > p.kcp) return "packed weights narrower than the padded K";
+    const size_t smem = pw_smem_bytes(p.Kc);
+    cudaError_t e = cudaFuncSetAttribute(pw_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cudaGetErrorString(e);
+    const int nslices = (p.N + PW_NSLICE - 1) / PW_NSLICE;
+    const int per_sm = smem * 2 + 4096 <= 227 * 1024 ? 2 : 1;
+    const int ntiles = (p.M + 15) / 16;
+    int gx = std::max(1, num_sms * per_sm / nslices);                   // grid = a multiple of the SM count (resident CTAs)
+    gx = std::min(gx, (ntiles + PW_THREADS / 32 - 1) / (PW_THREADS / 32));
+    pw_mma_kernel<<<dim3(gx, nslices), PW_THREADS, smem, s>>>(p);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+
+}  // namespace l2s
