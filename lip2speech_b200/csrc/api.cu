@@ -51,10 +51,38 @@ static void run_gemm(Context& c, GemmParams p, cudaStream_t s, const char* what)
 static void run_tc(Context& c, const TcOperands& o, const TcParams& p, cudaStream_t s, const char* what, bool gather = false);
 static inline TcParams tc_defaults();
 
+// Few rows, long K (the pre-loop's site / content / E_C layers at B=32: 32-928 rows): the tcgen05 GEMM would run on 2-32
+// CTAs, each streaming megabytes of weights alone.  Split K over the whole chip with the streaming mma.sync kernel
+// (pw_mma.cuh) and add the partial sums in a fixed order.  Returns false when the shape does not qualify.
+static bool splitk_small_m(Context& c, const float* A, int lda, const std::string& wname, const float* b, float* C, int ldc, int M, int N, int K,
+                           int act, const float* act_w, cudaStream_t s, const char* what) {
+    if (!c.use_tc || !c.use_pw || M > 1024 || (size_t)N * K < 32768 || (lda % 4) || (K % 4) || (reinterpret_cast<uintptr_t>(A) & 15)) return false;
+    const int bn = (N <= 32) ? 32 : (N <= 64 ? 64 : 128);
+    if (ceil_div(M, TC_BM) * ceil_div(N, bn) > 48) return false;             // enough tiles for the tcgen05 kernel
+    // the split depends on N and K only: a row's result must not depend on how many other rows (clips) share the batch
+    const int nslices = ceil_div(N, PW_NSLICE);
+    const int want = std::max(1, 2 * c.num_sms / nslices);
+    int ksplit = round_up(ceil_div(K, want), 16);
+    ksplit = std::min(std::max(ksplit, 64), 224);
+    const int nsplits = ceil_div(K, ksplit);
+    PwParams p{};
+    p.A = A; p.lda = lda; p.M = M; p.N = N; p.Kc = K;
+    p.Whi = c.dev(wname + ".hi"); p.Wlo = c.dev(wname + ".lo"); p.kcp = (int)c.meta.at(wname + ".kcp");
+    p.cstride = 1; p.ksplit = ksplit;
+    p.partial = c.fbuf("ws.pw.partial", (size_t)nsplits * M * N);
+    const char* err = launch_pw_mma(p, c.num_sms, s);
+    if (err) throw L2sError(L2S_ERR_CUDA, std::string(what) + " (split-K mma): " + err);
+    c.launches++;
+    pw_reduce_kernel<<<ew_grid((size_t)M * N), 256, 0, s>>>(p.partial, nsplits, M, N, b, act, act_w, C, ldc);
+    check_launch(c, what);
+    return true;
+}
+
 // plain linear: C[M,N] = act(A[M,K] W[N,K]^T + b).  `wname` selects the packed weight: wname.hi/.lo (tcgen05 3xTF32
 // path, needs 16-byte aligned rows for TMA) or wname.w (exact-fp32 SIMT path).
 static void linear(Context& c, const float* A, int lda, const std::string& wname, const float* b, float* C, int ldc, int M, int N, int K,
                    int act, const float* act_w, cudaStream_t s, const char* what) {
+    if (splitk_small_m(c, A, lda, wname, b, C, ldc, M, N, K, act, act_w, s, what)) return;
     if (c.use_tc && (lda % 4) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0) {
         const int kcp = (int)c.meta.at(wname + ".kcp");
         TcOperands o{A, K, M, lda, c.dev(wname + ".hi"), c.dev(wname + ".lo"), kcp};

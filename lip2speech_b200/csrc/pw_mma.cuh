@@ -34,7 +34,10 @@ struct PwParams {
     const float* bias; int relu;
     float* C; int ldc;
     int cstride, coff, chalf, chp;
-    int Kp, ldw;                                        // Kp = round_up(Kc, 16); ldw = Kp or Kp + 16, whichever is 16 mod 32
+    int Kp, ldw;                                        // Kp = round_up(K per split, 16); ldw = Kp or Kp + 16, whichever is 16 mod 32
+    // split-K mode (few rows, long K: the decoder pre-loop's small GEMMs): grid.z splits of `ksplit` columns write raw
+    // partial sums to partial[z][M][N]; pw_reduce_kernel adds them in a fixed order and applies the epilogue
+    int ksplit; float* partial;
 };
 
 __global__ void __launch_bounds__(PW_THREADS, 2) pw_mma_kernel(const PwParams p) {
@@ -42,12 +45,15 @@ __global__ void __launch_bounds__(PW_THREADS, 2) pw_mma_kernel(const PwParams p)
     float* whi = smem;
     float* wlo = smem + (size_t)PW_NSLICE * p.ldw;
     const int n_base = blockIdx.y * PW_NSLICE;
-    for (int i = threadIdx.x; i < PW_NSLICE * (p.Kp / 4); i += PW_THREADS) {
-        const int r = i / (p.Kp / 4), c4 = i - r * (p.Kp / 4);
+    const int kb = blockIdx.z * p.ksplit;                    // this CTA's K range: [kb, kb + Kc)
+    const int Kc = min(p.Kc - kb, p.ksplit);
+    const int Kp = (Kc + 15) / 16 * 16;
+    for (int i = threadIdx.x; i < PW_NSLICE * (Kp / 4); i += PW_THREADS) {
+        const int r = i / (Kp / 4), c4 = i - r * (Kp / 4);
         float4 h = make_float4(0.f, 0.f, 0.f, 0.f), l = h;
         if (n_base + r < p.N) {
-            h = __ldg(reinterpret_cast<const float4*>(p.Whi + (size_t)(n_base + r) * p.kcp) + c4);
-            l = __ldg(reinterpret_cast<const float4*>(p.Wlo + (size_t)(n_base + r) * p.kcp) + c4);
+            h = __ldg(reinterpret_cast<const float4*>(p.Whi + (size_t)(n_base + r) * p.kcp + kb) + c4);
+            l = __ldg(reinterpret_cast<const float4*>(p.Wlo + (size_t)(n_base + r) * p.kcp + kb) + c4);
         }
         *reinterpret_cast<float4*>(whi + (size_t)r * p.ldw + 4 * c4) = h;
         *reinterpret_cast<float4*>(wlo + (size_t)r * p.ldw + 4 * c4) = l;
@@ -56,7 +62,7 @@ __global__ void __launch_bounds__(PW_THREADS, 2) pw_mma_kernel(const PwParams p)
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int nchunks = p.Kp / 16;
+    const int nchunks = Kp / 16;
     const int ntiles = (p.M + 15) / 16;
     const int wstride = gridDim.x * (PW_THREADS / 32);
     // per-lane epilogue constants: this lane owns columns n_base + 8*nt + 2t, +1
@@ -66,16 +72,16 @@ __global__ void __launch_bounds__(PW_THREADS, 2) pw_mma_kernel(const PwParams p)
     for (int tile = blockIdx.x * (PW_THREADS / 32) + warp; tile < ntiles; tile += wstride) {
         const int r0 = tile * 16 + g, r1 = r0 + 8;
         const bool v0 = r0 < p.M, v1 = r1 < p.M;
-        const float* a0p = p.A + (size_t)(v0 ? r0 : 0) * p.lda + 4 * t;
-        const float* a1p = p.A + (size_t)(v1 ? r1 : 0) * p.lda + 4 * t;
+        const float* a0p = p.A + (size_t)(v0 ? r0 : 0) * p.lda + kb + 4 * t;
+        const float* a1p = p.A + (size_t)(v1 ? r1 : 0) * p.lda + kb + 4 * t;
         float acc[PW_NT][4];
 #pragma unroll
         for (int nt = 0; nt < PW_NT; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
         float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), xb = xa;
-        if (4 * t < p.Kc) { xa = __ldg(reinterpret_cast<const float4*>(a0p)); xb = __ldg(reinterpret_cast<const float4*>(a1p)); }
+        if (4 * t < Kc) { xa = __ldg(reinterpret_cast<const float4*>(a0p)); xb = __ldg(reinterpret_cast<const float4*>(a1p)); }
         for (int c = 0; c < nchunks; ++c) {
             float4 na = make_float4(0.f, 0.f, 0.f, 0.f), nb = na;
-            if (c + 1 < nchunks && (c + 1) * 16 + 4 * t < p.Kc) {          // next chunk in flight while this one is multiplied
+            if (c + 1 < nchunks && (c + 1) * 16 + 4 * t < Kc) {          // next chunk in flight while this one is multiplied
                 na = __ldg(reinterpret_cast<const float4*>(a0p + (c + 1) * 16));
                 nb = __ldg(reinterpret_cast<const float4*>(a1p + (c + 1) * 16));
             }
@@ -99,6 +105,27 @@ __global__ void __launch_bounds__(PW_THREADS, 2) pw_mma_kernel(const PwParams p)
             xa = na; xb = nb;
         }
         // epilogue: acc[nt] = {(r0, n), (r0, n+1), (r1, n), (r1, n+1)}, n = n_base + 8 nt + 2 t
+        if (p.partial) {
+            float* P = p.partial + (size_t)blockIdx.z * p.M * p.N;
+#pragma unroll
+            for (int nt = 0; nt < PW_NT; ++nt) {
+                const int n = n_base + nt * 8 + 2 * t;
+                if (n + 1 < p.N && !(p.N & 1)) {                       // 8-byte stores need an even row stride
+                    if (v0) *reinterpret_cast<float2*>(P + (size_t)r0 * p.N + n) = make_float2(acc[nt][0], acc[nt][1]);
+                    if (v1) *reinterpret_cast<float2*>(P + (size_t)r1 * p.N + n) = make_float2(acc[nt][2], acc[nt][3]);
+                } else {
+                    if (n < p.N) {
+                        if (v0) P[(size_t)r0 * p.N + n] = acc[nt][0];
+                        if (v1) P[(size_t)r1 * p.N + n] = acc[nt][2];
+                    }
+                    if (n + 1 < p.N) {
+                        if (v0) P[(size_t)r0 * p.N + n + 1] = acc[nt][1];
+                        if (v1) P[(size_t)r1 * p.N + n + 1] = acc[nt][3];
+                    }
+                }
+            }
+            continue;
+        }
 #pragma unroll
         for (int nt = 0; nt < PW_NT; ++nt) {
 #pragma unroll
@@ -121,21 +148,37 @@ __global__ void __launch_bounds__(PW_THREADS, 2) pw_mma_kernel(const PwParams p)
 inline int pw_ldw(int Kp) { return (Kp % 32 == 0) ? Kp + 16 : Kp; }      // rows 16 floats apart modulo the 32 banks: LDS.128 conflict-free
 inline size_t pw_smem_bytes(int Kc) { const int Kp = (Kc + 15) / 16 * 16; return (size_t)2 * PW_NSLICE * pw_ldw(Kp) * sizeof(float); }
 
-// Returns nullptr on success.
+// C[m][n] = act( sum_z partial[z][m][n] + bias[n] ), splits added in index order (deterministic)
+__global__ void pw_reduce_kernel(const float* __restrict__ partial, int nsplits, int M, int N, const float* __restrict__ bias, int act,
+                                 const float* __restrict__ act_w, float* __restrict__ C, int ldc) {
+    const size_t total = (size_t)M * N;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int n = i % N; const size_t m = i / N;
+        float v = 0.f;
+        for (int z = 0; z < nsplits; ++z) v += partial[(size_t)z * total + i];
+        if (bias) v += __ldg(bias + n);
+        C[m * ldc + n] = apply_act(v, act, act_w ? __ldg(act_w + n) : 1.f);
+    }
+}
+
+// Returns nullptr on success.  p.ksplit == 0: single pass over K with the fused epilogue.
 inline const char* launch_pw_mma(PwParams p, int num_sms, cudaStream_t s) {
     if ((p.lda & 3) || (p.Kc & 3) || (reinterpret_cast<uintptr_t>(p.A) & 15) || (p.kcp & 3)) return "pointwise conv needs 16-byte aligned rows";
-    p.Kp = (p.Kc + 15) / 16 * 16;
+    if (p.ksplit <= 0) { p.ksplit = (p.Kc + 15) / 16 * 16; p.partial = nullptr; }
+    if (p.ksplit & 15) return "K split must be a multiple of 16";
+    const int nsplits = (p.Kc + p.ksplit - 1) / p.ksplit;
+    p.Kp = (std::min(p.ksplit, p.Kc) + 15) / 16 * 16;
     p.ldw = pw_ldw(p.Kp);
-    if (p.Kp > p.kcp) return "packed weights narrower than the padded K";
-    const size_t smem = pw_smem_bytes(p.Kc);
+    if ((p.Kc + 15) / 16 * 16 > p.kcp) return "packed weights narrower than the padded K";
+    const size_t smem = pw_smem_bytes(std::min(p.ksplit, p.Kc));
     cudaError_t e = cudaFuncSetAttribute(pw_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cudaGetErrorString(e);
     const int nslices = (p.N + PW_NSLICE - 1) / PW_NSLICE;
     const int per_sm = smem * 2 + 4096 <= 227 * 1024 ? 2 : 1;
     const int ntiles = (p.M + 15) / 16;
-    int gx = std::max(1, num_sms * per_sm / nslices);                   // grid = a multiple of the SM count (resident CTAs)
+    int gx = std::max(1, num_sms * per_sm / (nslices * nsplits));       // grid = a multiple of the SM count (resident CTAs)
     gx = std::min(gx, (ntiles + PW_THREADS / 32 - 1) / (PW_THREADS / 32));
-    pw_mma_kernel<<<dim3(gx, nslices), PW_THREADS, smem, s>>>(p);
+    pw_mma_kernel<<<dim3(gx, nslices, nsplits), PW_THREADS, smem, s>>>(p);
     e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }
