@@ -98,13 +98,20 @@ static void linear(Context& c, const float* A, int lda, const std::string& wname
 }
 
 // Dense (1-tap) GEMM described SIMT-style (GemmParams with W unset): tcgen05 path when TMA alignment allows, else SIMT.
-static void gemm_auto(Context& c, GemmParams g, const std::string& wname, cudaStream_t s, const char* what) {
+static bool pw_eligible(const Context& c, const GemmParams& g) {
+    return c.use_tc && c.use_pw && g.taps == 1 && g.stride == 1 && !g.stem && g.Kc <= 240 && g.M >= 16384 && (g.act == ACT_NONE || g.act == ACT_RELU) &&
+           !g.addrow && !g.addpos && !g.resid && !g.transposed && (g.lda % 4) == 0 && (g.Kc % 4) == 0 && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0;
+}
+
+// pass_x / pass_ld: fuse the pass-through half of a stride-1 block into the store (only valid when pw_eligible(g))
+static void gemm_auto(Context& c, GemmParams g, const std::string& wname, cudaStream_t s, const char* what,
+                      const float* pass_x = nullptr, int pass_ld = 0) {
     if (g.L_out == 0) { g.L_out = g.M; g.L_in = g.M; }
     // tall-skinny pointwise convolutions of the trunk (K, N <= 240, >= 16 K rows: stages 2 and 3): streaming mma.sync kernel
     // (measured 50 vs 70 us at 12x12, 37 vs 40 us at 6x6; at 3x3 — 8 K rows — the tcgen05 GEMM is faster, 31 vs 40 us)
-    if (c.use_tc && c.use_pw && g.taps == 1 && g.stride == 1 && !g.stem && g.Kc <= 240 && g.M >= 16384 && (g.act == ACT_NONE || g.act == ACT_RELU) &&
-        !g.addrow && !g.addpos && !g.resid && !g.transposed && (g.lda % 4) == 0 && (g.Kc % 4) == 0 && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0) {
+    if (pw_eligible(c, g)) {
         PwParams p{};
+        p.pass_x = pass_x; p.pass_ld = pass_ld;
         p.A = g.A; p.lda = g.lda; p.M = g.M; p.N = g.N; p.Kc = g.Kc;
         p.Whi = c.dev(wname + ".hi"); p.Wlo = c.dev(wname + ".lo"); p.kcp = (int)c.meta.at(wname + ".kcp");
         p.bias = g.bias; p.relu = g.act == ACT_RELU; p.C = g.C; p.ldc = g.ldc;
@@ -114,6 +121,7 @@ static void gemm_auto(Context& c, GemmParams g, const std::string& wname, cudaSt
         c.launches++;
         return;
     }
+    if (pass_x) throw L2sError(L2S_ERR_INVALID, std::string(what) + ": internal: fused pass-through requested on a non-streaming GEMM");
     if (c.use_tc && g.taps == 1 && g.stride == 1 && !g.stem && (g.lda % 4) == 0 && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0) {
         const int kcp = (int)c.meta.at(wname + ".kcp");
         TcOperands o{g.A, g.Kc, g.M, g.lda, c.dev(wname + ".hi"), c.dev(wname + ".lo"), kcp};
@@ -305,8 +313,6 @@ static void video_forward(Context& c, const float* video, int B, int T, int H, i
             h = ho; w = wo;
         } else {
             const size_t rows = (size_t)N * h * w;
-            shuffle_passthrough_kernel<<<ew_grid(rows * half), 256, 0, s>>>(x, y, rows, cph, half, hp);
-            check_launch(c, "passthrough");
             GemmParams p = gemm_defaults();
             p.A = x + hp; p.lda = cph; p.bias = c.dev(n + "b2pw1.b"); p.act = ACT_RELU;
             p.C = t2; p.ldc = hp; p.M = (int)rows; p.N = half; p.Kc = hp;
@@ -316,7 +322,13 @@ static void video_forward(Context& c, const float* video, int B, int T, int H, i
             p = gemm_defaults();
             p.A = t1; p.lda = hp; p.bias = c.dev(n + "b2pw2.b"); p.act = ACT_RELU;
             p.C = y; p.ldc = cph; p.M = (int)rows; p.N = half; p.Kc = hp; p.cstride = 2; p.coff = 1; p.chalf = half; p.chp = hp;
-            gemm_auto(c, p, n + "b2pw2", s, "b2 pw2");
+            if (pw_eligible(c, p)) {
+                gemm_auto(c, p, n + "b2pw2", s, "b2 pw2 + pass-through", x, cph);      // x1 -> even channels inside the GEMM's store
+            } else {
+                shuffle_passthrough_kernel<<<ew_grid(rows * half), 256, 0, s>>>(x, y, rows, cph, half, hp);
+                check_launch(c, "passthrough");
+                gemm_auto(c, p, n + "b2pw2", s, "b2 pw2");
+            }
         }
         std::swap(x, y);
     }

@@ -38,6 +38,11 @@ struct PwParams {
     // split-K mode (few rows, long K: the decoder pre-loop's small GEMMs): grid.z splits of `ksplit` columns write raw
     // partial sums to partial[z][M][N]; pw_reduce_kernel adds them in a fixed order and applies the epilogue
     int ksplit; float* partial;
+    // stride-1 InvertedResidual blocks (shufflenetv2.py:97-100 + channel_shuffle): the pass-through half x[:, j] -> logical
+    // channel 2j is written here together with the branch output (logical 2j+1), so every 32-byte sector of the block's
+    // output is completed by one warp at once (no partial-sector fills from DRAM, no separate copy kernel).
+    // Requires cstride == 2, coff == 1, N even.
+    const float* pass_x; int pass_ld;
 };
 
 __global__ void __launch_bounds__(PW_THREADS, 2) pw_mma_kernel(const PwParams p) {
@@ -126,6 +131,31 @@ __global__ void __launch_bounds__(PW_THREADS, 2) pw_mma_kernel(const PwParams p)
             }
             continue;
         }
+        if (p.pass_x) {
+#pragma unroll
+            for (int nt = 0; nt < PW_NT; ++nt) {
+                const int n = n_base + nt * 8 + 2 * t;                 // even; n + 1 < N because N is even
+                if (n < p.N) {
+                    const float b0 = p.bias ? __ldg(p.bias + n) : 0.f, b1 = p.bias ? __ldg(p.bias + n + 1) : 0.f;
+                    int l0 = 2 * n, l1 = 2 * n + 2;                    // logical channels (2n, 2n+1) and (2n+2, 2n+3)
+                    if (l0 >= p.chalf) l0 = l0 - p.chalf + p.chp;
+                    if (l1 >= p.chalf) l1 = l1 - p.chalf + p.chp;
+                    float y00 = acc[nt][0] + b0, y01 = acc[nt][1] + b1, y10 = acc[nt][2] + b0, y11 = acc[nt][3] + b1;
+                    if (p.relu) { y00 = fmaxf(y00, 0.f); y01 = fmaxf(y01, 0.f); y10 = fmaxf(y10, 0.f); y11 = fmaxf(y11, 0.f); }
+                    if (v0) {
+                        const float2 x = __ldg(reinterpret_cast<const float2*>(p.pass_x + (size_t)r0 * p.pass_ld + n));
+                        *reinterpret_cast<float2*>(p.C + (size_t)r0 * p.ldc + l0) = make_float2(x.x, y00);
+                        *reinterpret_cast<float2*>(p.C + (size_t)r0 * p.ldc + l1) = make_float2(x.y, y01);
+                    }
+                    if (v1) {
+                        const float2 x = __ldg(reinterpret_cast<const float2*>(p.pass_x + (size_t)r1 * p.pass_ld + n));
+                        *reinterpret_cast<float2*>(p.C + (size_t)r1 * p.ldc + l0) = make_float2(x.x, y10);
+                        *reinterpret_cast<float2*>(p.C + (size_t)r1 * p.ldc + l1) = make_float2(x.y, y11);
+                    }
+                }
+            }
+            continue;
+        }
 #pragma unroll
         for (int nt = 0; nt < PW_NT; ++nt) {
 #pragma unroll
@@ -164,6 +194,8 @@ __global__ void pw_reduce_kernel(const float* __restrict__ partial, int nsplits,
 // Returns nullptr on success.  p.ksplit == 0: single pass over K with the fused epilogue.
 inline const char* launch_pw_mma(PwParams p, int num_sms, cudaStream_t s) {
     if ((p.lda & 3) || (p.Kc & 3) || (reinterpret_cast<uintptr_t>(p.A) & 15) || (p.kcp & 3)) return "pointwise conv needs 16-byte aligned rows";
+    if (p.pass_x && (p.cstride != 2 || p.coff != 1 || (p.N & 1) || (p.chalf & 1) || (p.chp & 1) || (p.ldc & 1) || (p.pass_ld & 1) || p.ksplit > 0))
+        return "fused pass-through needs the channel-shuffle store pattern (cstride 2, coff 1, even sizes)";
     if (p.ksplit <= 0) { p.ksplit = (p.Kc + 15) / 16 * 16; p.partial = nullptr; }
     if (p.ksplit & 15) return "K split must be a multiple of 16";
     const int nsplits = (p.Kc + p.ksplit - 1) / p.ksplit;

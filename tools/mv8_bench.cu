@@ -28,6 +28,23 @@ __global__ void __launch_bounds__(512, 1) mma_rate_kernel(float* out, int iters,
     out[blockIdx.x * 512 + threadIdx.x] = s;
 }
 
+// distinct operands per MMA (8 A fragments x 8 B fragments from registers), 8 independent accumulators
+__global__ void __launch_bounds__(512, 1) mma_rate_distinct_kernel(float* out, int iters, const uint32_t* __restrict__ src) {
+    float acc[8][4];
+    for (int j = 0; j < 8; ++j) for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+    uint32_t a[8][4], b[8][2];
+    for (int j = 0; j < 8; ++j) { for (int i = 0; i < 4; ++i) a[j][i] = src[(threadIdx.x + 37 * (4 * j + i)) & 1023]; for (int i = 0; i < 2; ++i) b[j][i] = src[(threadIdx.x + 91 * (2 * j + i) + 5) & 1023]; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mma_tf32(acc[k], a[j][0], a[j][1], a[j][2], a[j][3], b[(j + k) & 7][0], b[(j + k) & 7][1]);
+    }
+    float s = 0.f;
+    for (int j = 0; j < 8; ++j) for (int i = 0; i < 4; ++i) s += acc[j][i];
+    out[blockIdx.x * 512 + threadIdx.x] = s;
+}
+
 template <int MAXRT>
 __global__ void __launch_bounds__(512, 1) pass_kernel(const float* __restrict__ Wg, const float* __restrict__ X, float* __restrict__ out,
                                                        int R, int K, int ldw, int iters, int do_reduce) {
@@ -61,6 +78,19 @@ int main() {
         double mmas_per_smsp = 4.0 * 8 * iters;        // 4 warps per scheduler
         printf("mma.sync m16n8k8 tf32, %d independent accumulators/warp, 16 warps/SM: %.2f clk per MMA per SMSP (1.965 GHz) -> %.0f MAC/clk/SM\n",
                nacc, ms * 1e-3 * 1.965e9 / mmas_per_smsp, 1024.0 * 4 / (ms * 1e-3 * 1.965e9 / mmas_per_smsp));
+    }
+    {
+        uint32_t* src; cudaMalloc(&src, 4096); cudaMemset(src, 0x3c, 4096);
+        for (int warps : {16, 8, 4}) {
+            mma_rate_distinct_kernel<<<148, warps * 32>>>(o, 10, src);
+            const int iters = 4000;
+            cudaEventRecord(e0);
+            mma_rate_distinct_kernel<<<148, warps * 32>>>(o, iters, src);
+            cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            double mmas_per_smsp = (warps / 4.0) * 64 * iters;
+            printf("mma.sync tf32 distinct operands, %d warps/SM: %.2f clk per MMA per SMSP\n", warps, ms * 1e-3 * 1.965e9 / mmas_per_smsp);
+        }
     }
     const int KMAX = 1536, RMAX = 48;
     std::vector<float> hW((size_t)148 * RMAX * KMAX), hX((size_t)4 * KMAX * 32);
