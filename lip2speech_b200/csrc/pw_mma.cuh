@@ -47,8 +47,7 @@ struct PwParams {
 
 __global__ void __launch_bounds__(PW_THREADS, 2) pw_mma_kernel(const PwParams p) {
     extern __shared__ __align__(16) float smem[];
-    float* whi = smem;
-    float* wlo = smem + (size_t)PW_NSLICE * p.ldw;
+    float* wsm = smem;                                       // full-precision weights (hi + lo is exact), split per use
     const int n_base = blockIdx.y * PW_NSLICE;
     const int kb = blockIdx.z * p.ksplit;                    // this CTA's K range: [kb, kb + Kc)
     const int Kc = min(p.Kc - kb, p.ksplit);
@@ -60,8 +59,7 @@ __global__ void __launch_bounds__(PW_THREADS, 2) pw_mma_kernel(const PwParams p)
             h = __ldg(reinterpret_cast<const float4*>(p.Whi + (size_t)(n_base + r) * p.kcp + kb) + c4);
             l = __ldg(reinterpret_cast<const float4*>(p.Wlo + (size_t)(n_base + r) * p.kcp + kb) + c4);
         }
-        *reinterpret_cast<float4*>(whi + (size_t)r * p.ldw + 4 * c4) = h;
-        *reinterpret_cast<float4*>(wlo + (size_t)r * p.ldw + 4 * c4) = l;
+        *reinterpret_cast<float4*>(wsm + (size_t)r * p.ldw + 4 * c4) = make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w);
     }
     __syncthreads();
 
@@ -71,8 +69,7 @@ __global__ void __launch_bounds__(PW_THREADS, 2) pw_mma_kernel(const PwParams p)
     const int ntiles = (p.M + 15) / 16;
     const int wstride = gridDim.x * (PW_THREADS / 32);
     // per-lane epilogue constants: this lane owns columns n_base + 8*nt + 2t, +1
-    const float* wh_lane = whi + (size_t)g * p.ldw + 4 * t;
-    const float* wl_lane = wlo + (size_t)g * p.ldw + 4 * t;
+    const float* w_lane = wsm + (size_t)g * p.ldw + 4 * t;
 
     for (int tile = blockIdx.x * (PW_THREADS / 32) + warp; tile < ntiles; tile += wstride) {
         const int r0 = tile * 16 + g, r1 = r0 + 8;
@@ -96,10 +93,11 @@ __global__ void __launch_bounds__(PW_THREADS, 2) pw_mma_kernel(const PwParams p)
             for (int i = 0; i < 4; ++i) { split_tf32(av[i], ah[i], al[i]); split_tf32(bv[i], bh[i], bl[i]); }
 #pragma unroll
             for (int nt = 0; nt < PW_NT; ++nt) {
-                const float4 wh = *reinterpret_cast<const float4*>(wh_lane + (size_t)nt * 8 * p.ldw + c * 16);
-                const float4 wl = *reinterpret_cast<const float4*>(wl_lane + (size_t)nt * 8 * p.ldw + c * 16);
-                const uint32_t whv[4] = {__float_as_uint(wh.x), __float_as_uint(wh.y), __float_as_uint(wh.z), __float_as_uint(wh.w)};
-                const uint32_t wlv[4] = {__float_as_uint(wl.x), __float_as_uint(wl.y), __float_as_uint(wl.z), __float_as_uint(wl.w)};
+                const float4 w4 = *reinterpret_cast<const float4*>(w_lane + (size_t)nt * 8 * p.ldw + c * 16);
+                const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+                uint32_t whv[4], wlv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) split_tf32(wv[i], whv[i], wlv[i]);
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
                     mma_tf32(acc[nt], al[2 * s], bl[2 * s], al[2 * s + 1], bl[2 * s + 1], whv[2 * s], whv[2 * s + 1]);
@@ -176,7 +174,7 @@ __global__ void __launch_bounds__(PW_THREADS, 2) pw_mma_kernel(const PwParams p)
 }
 
 inline int pw_ldw(int Kp) { return (Kp % 32 == 0) ? Kp + 16 : Kp; }      // rows 16 floats apart modulo the 32 banks: LDS.128 conflict-free
-inline size_t pw_smem_bytes(int Kc) { const int Kp = (Kc + 15) / 16 * 16; return (size_t)2 * PW_NSLICE * pw_ldw(Kp) * sizeof(float); }
+inline size_t pw_smem_bytes(int Kc) { const int Kp = (Kc + 15) / 16 * 16; return (size_t)PW_NSLICE * pw_ldw(Kp) * sizeof(float); }
 
 // C[m][n] = act( sum_z partial[z][m][n] + bias[n] ), splits added in index order (deterministic)
 __global__ void pw_reduce_kernel(const float* __restrict__ partial, int nsplits, int M, int N, const float* __restrict__ bias, int act,
