@@ -188,10 +188,8 @@ __device__ __forceinline__ float mv_reduce_narrow(float (&acc)[R][2], float* red
 // tcgen05 is not usable here: it takes operands from shared memory only (no room for pre-split weights: 2 x 25 MB
 // > 148 x 227 KB) and needs M >= 64 rows per CTA while a CTA owns ~14 rows of each layer.
 //
-// Fragment mapping (g = lane>>2, t = lane&3): MMA column t / t+4 of k8-step s <-> real k = k0 + 4t + 2s / + 2s + 1,
-// so a lane reads W[g][k0+4t..+3] and W[g+8][k0+4t..+3] as two LDS.128 (conflict-free when ldw % 32 == 16);
-// MMA column n of n-tile j <-> clip 4n + j, so a lane reads X[k][4g..4g+3] as one LDG.128 per k (full 128-byte lines
-// per warp) and ends up holding 8 consecutive clips of rows g and g+8.
+// (A 32-clip form of this pass — four n-tiles per weight tile on the row-partitioned layout — lives in
+// tools/mvt_bench.cu: it measured 4.65 us against the FMA pass's 6.5 us and showed the L2 broadcast bound.)
 constexpr int MV_KC = 16;         // k values per warp iteration of the tensor-core pass
 
 __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
@@ -203,116 +201,6 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-
-__device__ __forceinline__ void mvt_zero(float (&acc)[4][4]) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
-}
-
-// One 16-k chunk: weights wa (row g) / wb (row g+8), activations x[i] = X[k0+4t+i][4g..4g+3].
-__device__ __forceinline__ void mvt_chunk(const float4& wa, const float4& wb, const float4 (&x)[4], float (&acc)[4][4]) {
-    const float wav[4] = {wa.x, wa.y, wa.z, wa.w}, wbv[4] = {wb.x, wb.y, wb.z, wb.w};
-    uint32_t ah[4], al[4], bh[4], bl[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { split_tf32(wav[i], ah[i], al[i]); split_tf32(wbv[i], bh[i], bl[i]); }
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-        const float xs0[4] = {x[2 * s].x, x[2 * s].y, x[2 * s].z, x[2 * s].w};
-        const float xs1[4] = {x[2 * s + 1].x, x[2 * s + 1].y, x[2 * s + 1].z, x[2 * s + 1].w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            uint32_t h0, l0, h1, l1;
-            split_tf32(xs0[j], h0, l0);
-            split_tf32(xs1[j], h1, l1);
-            mma_tf32(acc[j], al[2 * s], bl[2 * s], al[2 * s + 1], bl[2 * s + 1], h0, h1);
-            mma_tf32(acc[j], ah[2 * s], bh[2 * s], ah[2 * s + 1], bh[2 * s + 1], l0, l1);
-            mma_tf32(acc[j], ah[2 * s], bh[2 * s], ah[2 * s + 1], bh[2 * s + 1], h0, h1);
-        }
-    }
-}
-
-// Accumulates rows [0,16) x clips [b0, b0+32) over one K segment (K % 16 == 0).  Rows >= R re-read row R-1 (their
-// results are never used).  Warp w takes chunks w, w+16, ...; the activations of the next chunk are in flight while
-// the current one is multiplied.
-template <int R>
-__device__ __forceinline__ void mvt_accumulate(const float* __restrict__ Wsm, int ldw, int wcol0,
-                                               const float* __restrict__ X, int K, int ldb, int b0,
-                                               float (&acc)[4][4]) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = lane >> 2, t = lane & 3;
-    const int nchunks = K / MV_KC;
-    int c = warp;
-    if (c >= nchunks) return;
-    const int ra = g < R ? g : R - 1, rb = g + 8 < R ? g + 8 : R - 1;
-    const float* wpa = Wsm + (size_t)ra * ldw + wcol0 + c * MV_KC + 4 * t;
-    const float* wpb = Wsm + (size_t)rb * ldw + wcol0 + c * MV_KC + 4 * t;
-    const float* xp = X + (size_t)(c * MV_KC + 4 * t) * ldb + b0 + 4 * g;
-    const size_t cstride = (size_t)MV_WARPS * MV_KC * ldb;
-    float4 xa[4], xb[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) xa[i] = ldcg4(xp + (size_t)i * ldb);
-    for (; c < nchunks; c += 2 * MV_WARPS) {
-        const bool more1 = c + MV_WARPS < nchunks;
-        if (more1) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) xb[i] = ldcg4(xp + cstride + (size_t)i * ldb);
-        }
-        mvt_chunk(*reinterpret_cast<const float4*>(wpa), *reinterpret_cast<const float4*>(wpb), xa, acc);
-        if (more1) {
-            if (c + 2 * MV_WARPS < nchunks) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) xa[i] = ldcg4(xp + 2 * cstride + (size_t)i * ldb);
-            }
-            mvt_chunk(*reinterpret_cast<const float4*>(wpa + MV_WARPS * MV_KC), *reinterpret_cast<const float4*>(wpb + MV_WARPS * MV_KC), xb, acc);
-        }
-        xp += 2 * cstride;
-        wpa += 2 * MV_WARPS * MV_KC;
-        wpb += 2 * MV_WARPS * MV_KC;
-    }
-}
-
-// Cross-warp reduction of the tensor-core partial tiles.  `red` holds MV_WARPS x RED_ROWS x 32 floats (RED_ROWS = 16:
-// one round; RED_ROWS = 8: rows [0,8) then rows [8,16) through the same buffer).  Returns the finished value for
-// (row tid>>5, clip tid&31) in threads tid < 16*32.  Contains __syncthreads(); the caller must __syncthreads() again
-// before `red` is reused.
-template <int RED_ROWS>
-__device__ __forceinline__ float mvt_reduce(const float (&acc)[4][4], float* red) {
-    static_assert(RED_ROWS == 16 || RED_ROWS == 8, "RED_ROWS must be 16 or 8");
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = lane >> 2, t = lane & 3;
-    float v = 0.f;
-    if (RED_ROWS == 16) {
-        float* base = red + (size_t)warp * 16 * MV_CLIPS;
-        *reinterpret_cast<float4*>(base + g * MV_CLIPS + 8 * t) = make_float4(acc[0][0], acc[1][0], acc[2][0], acc[3][0]);
-        *reinterpret_cast<float4*>(base + g * MV_CLIPS + 8 * t + 4) = make_float4(acc[0][1], acc[1][1], acc[2][1], acc[3][1]);
-        *reinterpret_cast<float4*>(base + (g + 8) * MV_CLIPS + 8 * t) = make_float4(acc[0][2], acc[1][2], acc[2][2], acc[3][2]);
-        *reinterpret_cast<float4*>(base + (g + 8) * MV_CLIPS + 8 * t + 4) = make_float4(acc[0][3], acc[1][3], acc[2][3], acc[3][3]);
-        __syncthreads();
-        const int r = threadIdx.x >> 5, b = threadIdx.x & 31;
-#pragma unroll
-        for (int w = 0; w < MV_WARPS; ++w) v += red[(size_t)(w * 16 + r) * MV_CLIPS + b];
-    } else {
-        float* base = red + (size_t)warp * 8 * MV_CLIPS;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            if (half == 1) __syncthreads();
-            *reinterpret_cast<float4*>(base + g * MV_CLIPS + 8 * t) =
-                make_float4(acc[0][2 * half], acc[1][2 * half], acc[2][2 * half], acc[3][2 * half]);
-            *reinterpret_cast<float4*>(base + g * MV_CLIPS + 8 * t + 4) =
-                make_float4(acc[0][2 * half + 1], acc[1][2 * half + 1], acc[2][2 * half + 1], acc[3][2 * half + 1]);
-            __syncthreads();
-            const int tt = (int)threadIdx.x - half * 8 * MV_CLIPS;
-            if (tt >= 0 && tt < 8 * MV_CLIPS) {
-                const int r = tt >> 5, b = tt & 31;
-#pragma unroll
-                for (int w = 0; w < MV_WARPS; ++w) v += red[(size_t)(w * 8 + r) * MV_CLIPS + b];
-            }
-        }
-    }
-    return v;
 }
 
 // ---- 8-clip variant for the stage-pipelined decode kernel (decode3.cuh) ------------------------------------------
