@@ -53,3 +53,16 @@ mel2, _ = b2.decoder_infer(visual.cuda(), face[:, 0].cuda(), g.cuda())
 print("B=32, 300 steps: dec3 vs dec2", rel(mel3, mel2))
 m12, _ = b3.decoder_infer(visual[8:20].cuda(), face[8:20, 0].cuda(), g[32:80].cuda())
 print("B=12 sub-batch bit-identical to B=32:", torch.equal(m12, mel3[8:20]))
+
+for B in (64, 128, 256):
+    visual, face = synth.visual_features(B, 29, seed=6)
+    g = synth.gumbel(B, 29, seed=6)
+    v, f, gg = visual.cuda(), face[:, 0].cuda(), g.cuda()
+    line = f"B={B}:"
+    for name, be in (("dec3", b3), ("dec2", b2)):
+        be.set_profiling(True)
+        for _ in range(2):
+            mel, _ = be.decoder_infer(v, f, gg)
+        torch.cuda.synchronize()
+        line += f"  {name} decode_loop {be.span_ms('decode_loop'):.2f} ms"
+    print(line, flush=True)
