@@ -707,8 +707,9 @@ static void decoder_run(Context& c, const float* visual, const float* spk, const
         dp.barrier = bar;
         dp.timing = c.profiling ? c.fbuf("ws.d.timing", (size_t)c.num_sms * DEC_TIMING_SLOTS) : nullptr;
         c.span_end("preloop", s);
-        // 8 < B <= 32: stage-pipelined kernel (decode3.cuh); otherwise the row-partitioned kernel (decode.cuh)
-        const bool pipelined = c.use_dec3 && B > D3_CG && B <= D3_CG * D3_NG && c.meta.at("d.step3.ok") == 1;
+        // B <= 32: stage-pipelined kernel (decode3.cuh) — also for a single clip: a step is four dependent turns whatever
+        // the batch, and a turn of this kernel is shorter than a stage of the row-partitioned one (decode.cuh, B > 32)
+        const bool pipelined = c.use_dec3 && B <= D3_CG * D3_NG && c.meta.at("d.step3.ok") == 1;
         c.meta["dbg.dec3"] = pipelined ? 1 : 0;
         if (pipelined) {
             Decode3Params q{};

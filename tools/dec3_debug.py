@@ -54,7 +54,7 @@ print("B=32, 300 steps: dec3 vs dec2", rel(mel3, mel2))
 m12, _ = b3.decoder_infer(visual[8:20].cuda(), face[8:20, 0].cuda(), g[32:80].cuda())
 print("B=12 sub-batch bit-identical to B=32:", torch.equal(m12, mel3[8:20]))
 
-for B in (64, 128, 256):
+for B in (1, 2, 4, 8, 64):
     visual, face = synth.visual_features(B, 29, seed=6)
     g = synth.gumbel(B, 29, seed=6)
     v, f, gg = visual.cuda(), face[:, 0].cuda(), g.cuda()
