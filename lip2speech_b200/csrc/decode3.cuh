@@ -142,12 +142,12 @@ constexpr int D3_EDEPTH = 2;          // chunks per warp of an early segment (Ke
 
 // What this CTA's stage does in a given turn of the software pipeline.
 struct D3Slot { int g, step; bool active; };
-__device__ __forceinline__ D3Slot d3_slot(int turn, int role, int steps) {
+__device__ __forceinline__ D3Slot d3_slot(int turn, int role, int steps, int B) {
     D3Slot s;
     s.g = (turn - role) & (D3_NG - 1);                       // clip group served by this stage in this turn
     const int u = turn - s.g;                                // stages completed by that group (u % 4 == role)
     s.step = u >> 2;
-    s.active = (u >= 0) && (s.step < steps);
+    s.active = (u >= 0) && (s.step < steps) && (s.g * D3_CG < B);        // empty clip groups (B <= 24) are skipped
     return s;
 }
 
@@ -323,7 +323,7 @@ __device__ __forceinline__ void d3_loop(const Decode3Params& q, const Dec3Pass& 
     D3Slot none; none.g = 0; none.step = 0; none.active = false;
     // prologue A(-1): Q, content query and prenet(BOS) of every clip group from the initial state in S[0]
     if (role == ROLE_A && has_pass)
-        for (int g = 0; g < D3_NG; ++g) d3_turn<RT, EARLY>(p, ps, sm, sync, g, -1, 0, xe, xe_valid, none);
+        for (int g = 0; g * D3_CG < p.B; ++g) d3_turn<RT, EARLY>(p, ps, sm, sync, g, -1, 0, xe, xe_valid, none);
     if (job >= 0 && q.kv_smem) d3_prefetch_kv(p, kvbuf, &kvbar[0], min(aclip, p.B - 1), apart);          // turn 0 serves group 0
     grid_arrive(p.barrier);
     sync.target += n;
@@ -331,27 +331,35 @@ __device__ __forceinline__ void d3_loop(const Decode3Params& q, const Dec3Pass& 
     if (threadIdx.x == 0) sync.tmark = clock64();
 
     const int nturns = D3_NG * p.steps + D3_NG - 1;
+    // attention CTAs: K/V image number n lives in buffer n & 1 and is that buffer's (n >> 1)-th use (mbarrier parity);
+    // image n + 1 (the clip of this CTA's NEXT ACTIVE turn — empty clip groups are skipped) is requested when image n is
+    // about to be consumed, i.e. after the previous reader of its buffer has finished.
+    int kv_issued = (job >= 0 && q.kv_smem) ? 1 : 0, kv_consumed = 0;
 #pragma unroll 1
     for (int turn = 0; turn < nturns; ++turn) {
-        const D3Slot cur = d3_slot(turn, role, p.steps);
-        const D3Slot next = (turn + 1 < nturns) ? d3_slot(turn + 1, role, p.steps) : none;
+        const D3Slot cur = d3_slot(turn, role, p.steps, p.B);
+        const D3Slot next = (turn + 1 < nturns) ? d3_slot(turn + 1, role, p.steps, p.B) : none;
         const int g = cur.g, step = cur.step;
         sync.waited = false;
-        if (job >= 0 && q.kv_smem && next.active) {          // next turn's clip -> the other buffer (free since the last turn ended)
-            const int bn = next.g * D3_CG + aclip;
-            d3_prefetch_kv(p, kvbuf + (size_t)((turn + 1) & 1) * kvfloats, &kvbar[(turn + 1) & 1], min(bn, p.B - 1), apart);
-        }
         if (cur.active) {
             const int parity_new = (step + 1) & 1;
             if (has_pass) d3_turn<RT, EARLY>(p, ps, sm, sync, g, step, parity_new, xe, xe_valid, next);
             if (job >= 0) {
                 const int b = g * D3_CG + aclip;
+                if (q.kv_smem) {
+                    D3Slot na = none;                        // this CTA's next active turn (at most D3_NG turns ahead)
+                    for (int d = 1; d <= D3_NG && !na.active && turn + d < nturns; ++d) na = d3_slot(turn + d, role, p.steps, p.B);
+                    if (na.active) {
+                        d3_prefetch_kv(p, kvbuf + (size_t)(kv_issued & 1) * kvfloats, &kvbar[kv_issued & 1], min(na.g * D3_CG + aclip, p.B - 1), apart);
+                        ++kv_issued;
+                    }
+                }
                 sync.wait();
-                if (q.kv_smem) mbar_wait(&kvbar[turn & 1], (turn >> 1) & 1);                  // this turn's clip has landed
+                if (q.kv_smem) mbar_wait(&kvbar[kv_consumed & 1], (kv_consumed >> 1) & 1);     // this turn's clip has landed
                 sync.lap(2);
                 if (b < p.B) {
                     if (q.kv_smem) {
-                        const float* kb = kvbuf + (size_t)(turn & 1) * kvfloats;
+                        const float* kb = kvbuf + (size_t)(kv_consumed & 1) * kvfloats;
                         const float* ckb = kb + (size_t)p.T * 768;
                         d3_attend(p, sm, kb, kb + (size_t)p.T * 512, 256, ckb, ckb + (size_t)p.minT * 256, 128, b, apart, step);
                     } else {
@@ -359,6 +367,7 @@ __device__ __forceinline__ void d3_loop(const Decode3Params& q, const Dec3Pass& 
                                   p.ckey + (size_t)b * p.minT * 256, p.cval + (size_t)b * p.minT * 256 + apart * 128, 256, b, apart, step);
                     }
                 }
+                ++kv_consumed;
             }
             sync.wait();
             sync.lap(3);

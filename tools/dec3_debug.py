@@ -28,8 +28,10 @@ for B, steps in ((12, 6), (32, 40), (9, 40)):
     print(f"B={B} steps={steps}: dec3 vs oracle {rel(m3.cpu(), ref_mel):.2e}  dec2 vs oracle {rel(m2.cpu(), ref_mel):.2e}  "
           f"dec3 vs dec2 {rel(m3, m2):.2e}  lengths3 ok {torch.equal(l3.cpu(), ref_len)} lengths2 ok {torch.equal(l2.cpu(), ref_len)}", flush=True)
 
-visual, face = synth.visual_features(32, 29, seed=5)
-g = synth.gumbel(32, 29, seed=5)
+import sys as _sys
+PB = int(_sys.argv[1]) if len(_sys.argv) > 1 else 32
+visual, face = synth.visual_features(PB, 29, seed=5)
+g = synth.gumbel(PB, 29, seed=5)
 for name, be in (("dec3", b3), ("dec2", b2)):
     be.set_profiling(True)
     for _ in range(3):
