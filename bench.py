@@ -10,8 +10,8 @@ clips per GPU (29 frames of 96x96, 19 456 audio samples); 300 mel frames are emi
 (decoder.py:412 always runs max_decoder_steps).  value = N*B*300*K / time.
 
   value : inputs resident in HBM, CUDA-event time per step, L2 flushed between steps, max over ranks
-  e2e   : the same span through the public C-ABI host call (l2s_infer_host): pinned host inputs,
-          H2D + compute + D2H inside the timed region
+  e2e   : the same span through the public C-ABI host calls (l2s_infer_host_submit / _wait): pinned host inputs,
+          H2D + compute + D2H of every step inside the timed region, consecutive steps double-buffered
   roofline : the persistent decode-loop kernel's algorithmic bytes / its CUDA-event time
   cpu_baseline : the CPU oracle (port of the reference, torch CPU fp32, all host threads) on the same workload
 
@@ -215,18 +215,29 @@ def main():
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = sharding.max_over_ranks(sum(step_ms), dev)      # device time, max over ranks
 
-    # ---- e2e: public host-buffer call, H2D + compute + D2H inside the timed region ----------------
-    mel_h = torch.empty(B, 80, STEPS_PER_CLIP).pin_memory()
-    len_h = torch.empty(B, dtype=torch.int64).pin_memory()
+    # ---- e2e: public host-buffer calls, H2D + compute + D2H of EVERY step inside the timed region ---------------------
+    # The caller streams batches the way demo.py / evaluate.py loop over a DataLoader: l2s_infer_host_submit / _wait with two
+    # staging slots, so the clip copy of step i+1 overlaps the compute of step i; every step's inputs come from pinned host
+    # memory and every step's mel / lengths are read back to the host.
+    mel_h = [torch.empty(B, 80, STEPS_PER_CLIP).pin_memory() for _ in range(2)]
+    len_h = [torch.empty(B, dtype=torch.int64).pin_memory() for _ in range(2)]
     be.set_profiling(False)
     for _ in range(2):
-        be.infer_host(video_h, wav_h, g_h, mel_h, len_h, STEPS_PER_CLIP, prec)
+        be.infer_host(video_h, wav_h, g_h, mel_h[0], len_h[0], STEPS_PER_CLIP, prec)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        be.infer_host(video_h, wav_h, g_h, mel_h, len_h, STEPS_PER_CLIP, prec)     # synchronous: returns after D2H
+    for i in range(args.steps):
+        be.infer_host_submit(i & 1, video_h, wav_h, g_h, mel_h[i & 1], len_h[i & 1], STEPS_PER_CLIP, prec)
+        if i > 0:
+            be.infer_host_wait((i - 1) & 1)                  # step i-1's results are on the host
+    be.infer_host_wait((args.steps - 1) & 1)
     torch.cuda.synchronize()
     e2e_s = sharding.max_over_ranks(time.perf_counter() - t0, dev)
+    # latency of one synchronous call (no cross-step overlap), for reference
+    t0 = time.perf_counter()
+    for _ in range(3):
+        be.infer_host(video_h, wav_h, g_h, mel_h[0], len_h[0], STEPS_PER_CLIP, prec)
+    sync_call_ms = 1e3 * (time.perf_counter() - t0) / 3
     clocks = sampler.stop()
 
     if rank == 0:
@@ -248,8 +259,10 @@ def main():
                        "l2": "flushed between timed steps (256 MiB memset outside the event pair)", "parallelism": f"batch-sharded x{world}, no collective"},
             "e2e": {"value": frames / e2e_s, "unit": "mel-frames/s",
                     "h2d_bytes_per_step": int(video_h.numel() * 4 + wav_h.numel() * 4 + g_h.numel() * 4),
-                    "d2h_bytes_per_step": int(mel_h.numel() * 4 + len_h.numel() * 8), "ms_per_step": 1e3 * e2e_s / args.steps,
-                    "api": "l2s_infer_host (C ABI, pinned host buffers)"},
+                    "d2h_bytes_per_step": int(mel_h[0].numel() * 4 + len_h[0].numel() * 8), "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "api": "l2s_infer_host_submit / l2s_infer_host_wait (C ABI, pinned host buffers, two staging slots: step i+1's copy "
+                           "overlaps step i's compute)",
+                    "synchronous_call_ms": sync_call_ms},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": ("decode3_kernel" if be.debug_flag("dec3") == 1 else "decode_persistent_kernel") + " (300 steps, one launch)", "bound": "hbm", "achieved": achieved,

@@ -95,6 +95,14 @@ int l2s_infer(l2s_ctx* ctx, const float* video, const float* wav, const float* g
 int l2s_infer_host(l2s_ctx* ctx, const float* video, const float* wav, const float* gumbel, int B, int T,
                    int H, int W, int S, int steps, float* mel_post, int64_t* lengths, int precision);
 
+/* Pipelined form of l2s_infer_host for a caller that streams batches (the loop of demo.py / evaluate.py): `submit` enqueues
+ * copies + compute + result copies for staging slot 0 or 1 and returns; `wait` blocks until that slot's mel_post / lengths
+ * are in the caller's buffers.  With two submissions in flight the clip copy of batch i+1 overlaps the compute of batch i.
+ * The caller's buffers must stay valid (and pinned, for the copies to be asynchronous) until `wait` returns. */
+int l2s_infer_host_submit(l2s_ctx* ctx, int slot, const float* video, const float* wav, const float* gumbel, int B, int T,
+                          int H, int W, int S, int steps, float* mel_post, int64_t* lengths, int precision);
+int l2s_infer_host_wait(l2s_ctx* ctx, int slot);
+
 /* ---- train-step tail (train.py:167-193) ---------------------------------------------------------------------------
  * The forward-train / backward kernels of the model are not part of this library yet; these entry points cover the loss,
  * the data-parallel gradient exchange (the only collective of the path) and the optimizer step on FLAT fp32 buffers. */

@@ -17,7 +17,7 @@ PART_VIDEO, PART_SPEAKER, PART_DECODER = 1, 2, 4
 PRECISION_FP32, PRECISION_BF16 = 0, 1
 
 EXPORTS = ("l2s_version", "l2s_create", "l2s_destroy", "l2s_last_error", "l2s_bind_weight", "l2s_commit_weights",
-           "l2s_video_fwd", "l2s_speaker_fwd", "l2s_decoder_infer", "l2s_decoder_forward", "l2s_postnet_fwd", "l2s_infer", "l2s_infer_host",
+           "l2s_video_fwd", "l2s_speaker_fwd", "l2s_decoder_infer", "l2s_decoder_forward", "l2s_postnet_fwd", "l2s_infer", "l2s_infer_host", "l2s_infer_host_submit", "l2s_infer_host_wait",
            "l2s_launch_count", "l2s_debug_read", "l2s_set_profiling", "l2s_span_ms",
            "l2s_loss_fwd_bwd", "l2s_nccl_unique_id", "l2s_comm_init", "l2s_comm_destroy", "l2s_allreduce_grads", "l2s_clip_adamw_step")
 NCCL_UNIQUE_ID_BYTES = 128
@@ -50,6 +50,8 @@ def load() -> C.CDLL:
         lib.l2s_postnet_fwd.argtypes = [vp, fp, i, i, fp, i, vp]
         lib.l2s_infer.argtypes = [vp, fp, fp, fp, i, i, i, i, i, i, fp, vp, i, vp]
         lib.l2s_infer_host.argtypes = [vp, fp, fp, fp, i, i, i, i, i, i, fp, vp, i]
+        lib.l2s_infer_host_submit.argtypes = [vp, i, fp, fp, fp, i, i, i, i, i, i, fp, vp, i]
+        lib.l2s_infer_host_wait.argtypes = [vp, i]
         lib.l2s_launch_count.argtypes = [vp]; lib.l2s_launch_count.restype = C.c_int64
         lib.l2s_set_profiling.argtypes = [vp, i]
         lib.l2s_span_ms.argtypes = [vp, C.c_char_p]; lib.l2s_span_ms.restype = C.c_double
@@ -202,6 +204,18 @@ class Backend:
             assert t.device.type == "cpu" and t.dtype == torch.float32 and t.is_contiguous()
         self._check(self.lib.l2s_infer_host(self.h, video.data_ptr(), wav.data_ptr(), gumbel.data_ptr(), B, T, H, W, wav.shape[1], steps,
                                             mel_out.data_ptr(), C.c_void_p(lengths_out.data_ptr()), precision), "l2s_infer_host")
+
+    def infer_host_submit(self, slot, video, wav, gumbel, mel_out, lengths_out, steps: int = 300, precision: int = PRECISION_FP32):
+        """Asynchronous form: enqueue copies + compute for staging slot 0 / 1; the HOST tensors must stay alive (and should be
+        pinned) until infer_host_wait(slot) returns.  Two slots in flight overlap batch i+1's clip copy with batch i's compute."""
+        B, _, T, H, W = video.shape
+        for t in (video, wav, gumbel, mel_out):
+            assert t.device.type == "cpu" and t.dtype == torch.float32 and t.is_contiguous()
+        self._check(self.lib.l2s_infer_host_submit(self.h, slot, video.data_ptr(), wav.data_ptr(), gumbel.data_ptr(), B, T, H, W, wav.shape[1],
+                                                   steps, mel_out.data_ptr(), C.c_void_p(lengths_out.data_ptr()), precision), "l2s_infer_host_submit")
+
+    def infer_host_wait(self, slot):
+        self._check(self.lib.l2s_infer_host_wait(self.h, slot), "l2s_infer_host_wait")
 
     # ---- train-step tail (train.py:167-193) --------------------------------------------------------
     def loss_fwd_bwd(self, mel_out, mel_post, gate_logits, content_dis, mel_target, gate_target, want_grads: bool = True):

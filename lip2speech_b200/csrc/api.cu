@@ -949,33 +949,70 @@ int l2s_infer(l2s_ctx* ctx, const float* video, const float* wav, const float* g
     API_END(ctx)
 }
 
+// Host-buffer entry points.  Two slots of device staging buffers: `submit` enqueues H2D copies (the 100 MB clip tensor on
+// a second stream, overlapped with the speaker encoder — which needs only the waveforms — and, when the caller keeps two
+// submissions in flight, with the previous batch's compute), the whole span, and the D2H copies of the results; `wait`
+// blocks until that slot's results are in the caller's buffers.
+static void infer_host_submit(Context& c, int slot, const float* video, const float* wav, const float* gumbel, int B, int T, int H, int W, int S,
+                              int steps, float* mel_post, int64_t* lengths, int precision) {
+    if (slot < 0 || slot > 1) throw L2sError(L2S_ERR_INVALID, "infer_host: slot must be 0 or 1");
+    int minT = T;
+    for (int k : {1, 3, 5, 7}) minT = std::min(minT, (T - k) / k + 1);
+    const size_t nv = (size_t)B * 3 * T * H * W, nw = (size_t)B * S, ng = (size_t)B * minT * 501, nm = (size_t)B * 80 * steps;
+    const std::string sfx = slot ? ".1" : "";
+    // grow every staging buffer of this slot before anything is enqueued (a reallocation synchronises the device)
+    float* dv = c.fbuf("ws.h.video" + sfx, nv); float* dw = c.fbuf("ws.h.wav" + sfx, nw); float* dg = c.fbuf("ws.h.gumbel" + sfx, ng);
+    float* dm = c.fbuf("ws.h.mel" + sfx, nm);
+    int64_t* dl = static_cast<int64_t*>(c.buf("ws.h.len" + sfx, (size_t)B * sizeof(int64_t)));
+    if (!c.host_stream) {
+        L2S_CUDA(cudaStreamCreateWithFlags(&c.host_stream, cudaStreamNonBlocking));
+        L2S_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            L2S_CUDA(cudaEventCreateWithFlags(&c.copy_done[i], cudaEventDisableTiming));
+            L2S_CUDA(cudaEventCreateWithFlags(&c.slot_done[i], cudaEventDisableTiming));
+            L2S_CUDA(cudaEventCreateWithFlags(&c.video_consumed[i], cudaEventDisableTiming));
+        }
+    }
+    cudaStream_t s = c.host_stream;
+    // the copy stream must not overwrite this slot's clip buffer while an earlier submission still reads it
+    if (c.slot_used[slot]) L2S_CUDA(cudaStreamWaitEvent(c.copy_stream, c.video_consumed[slot], 0));
+    L2S_CUDA(cudaMemcpyAsync(dv, video, nv * sizeof(float), cudaMemcpyHostToDevice, c.copy_stream));
+    L2S_CUDA(cudaEventRecord(c.copy_done[slot], c.copy_stream));
+    L2S_CUDA(cudaMemcpyAsync(dw, wav, nw * sizeof(float), cudaMemcpyHostToDevice, s));
+    L2S_CUDA(cudaMemcpyAsync(dg, gumbel, ng * sizeof(float), cudaMemcpyHostToDevice, s));
+    infer_device(c, dv, dw, dg, B, T, H, W, S, steps, dm, dl, precision, s, c.copy_done[slot]);
+    L2S_CUDA(cudaEventRecord(c.video_consumed[slot], s));
+    L2S_CUDA(cudaMemcpyAsync(mel_post, dm, nm * sizeof(float), cudaMemcpyDeviceToHost, s));
+    L2S_CUDA(cudaMemcpyAsync(lengths, dl, (size_t)B * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    L2S_CUDA(cudaEventRecord(c.slot_done[slot], s));
+    c.slot_used[slot] = true;
+}
+
+int l2s_infer_host_submit(l2s_ctx* ctx, int slot, const float* video, const float* wav, const float* gumbel, int B, int T, int H, int W, int S,
+                          int steps, float* mel_post, int64_t* lengths, int precision) {
+    if (!ctx) return L2S_ERR_INVALID;
+    API_BEGIN
+    need(ctx, L2S_PART_VIDEO | L2S_PART_SPEAKER | L2S_PART_DECODER, "infer_host_submit");
+    infer_host_submit(ctx->c, slot, video, wav, gumbel, B, T, H, W, S, steps, mel_post, lengths, precision);
+    API_END(ctx)
+}
+
+int l2s_infer_host_wait(l2s_ctx* ctx, int slot) {
+    if (!ctx) return L2S_ERR_INVALID;
+    API_BEGIN
+    Context& c = ctx->c;
+    if (slot < 0 || slot > 1 || !c.slot_used[slot]) throw L2sError(L2S_ERR_INVALID, "infer_host_wait: nothing was submitted to this slot");
+    L2S_CUDA(cudaEventSynchronize(c.slot_done[slot]));
+    API_END(ctx)
+}
+
 int l2s_infer_host(l2s_ctx* ctx, const float* video, const float* wav, const float* gumbel, int B, int T, int H, int W, int S, int steps,
                    float* mel_post, int64_t* lengths, int precision) {
     if (!ctx) return L2S_ERR_INVALID;
     API_BEGIN
     need(ctx, L2S_PART_VIDEO | L2S_PART_SPEAKER | L2S_PART_DECODER, "infer_host");
-    Context& c = ctx->c;
-    int minT = T;
-    for (int k : {1, 3, 5, 7}) minT = std::min(minT, (T - k) / k + 1);
-    const size_t nv = (size_t)B * 3 * T * H * W, nw = (size_t)B * S, ng = (size_t)B * minT * 501, nm = (size_t)B * 80 * steps;
-    float* dv = c.fbuf("ws.h.video", nv); float* dw = c.fbuf("ws.h.wav", nw); float* dg = c.fbuf("ws.h.gumbel", ng);
-    float* dm = c.fbuf("ws.h.mel", nm);
-    int64_t* dl = static_cast<int64_t*>(c.buf("ws.h.len", (size_t)B * sizeof(int64_t)));
-    // two non-blocking streams: the 100 MB clip copy overlaps the speaker encoder (which needs only the waveforms)
-    if (!c.host_stream) {
-        L2S_CUDA(cudaStreamCreateWithFlags(&c.host_stream, cudaStreamNonBlocking));
-        L2S_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
-        L2S_CUDA(cudaEventCreateWithFlags(&c.copy_done, cudaEventDisableTiming));
-    }
-    cudaStream_t s = c.host_stream;
-    L2S_CUDA(cudaMemcpyAsync(dw, wav, nw * sizeof(float), cudaMemcpyHostToDevice, s));
-    L2S_CUDA(cudaMemcpyAsync(dg, gumbel, ng * sizeof(float), cudaMemcpyHostToDevice, s));
-    L2S_CUDA(cudaMemcpyAsync(dv, video, nv * sizeof(float), cudaMemcpyHostToDevice, c.copy_stream));
-    L2S_CUDA(cudaEventRecord(c.copy_done, c.copy_stream));
-    infer_device(c, dv, dw, dg, B, T, H, W, S, steps, dm, dl, precision, s, c.copy_done);
-    L2S_CUDA(cudaMemcpyAsync(mel_post, dm, nm * sizeof(float), cudaMemcpyDeviceToHost, s));
-    L2S_CUDA(cudaMemcpyAsync(lengths, dl, (size_t)B * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-    L2S_CUDA(cudaStreamSynchronize(s));
+    infer_host_submit(ctx->c, 0, video, wav, gumbel, B, T, H, W, S, steps, mel_post, lengths, precision);
+    L2S_CUDA(cudaEventSynchronize(ctx->c.slot_done[0]));
     API_END(ctx)
 }
 

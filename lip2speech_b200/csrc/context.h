@@ -45,7 +45,8 @@ struct Context {
     int64_t launches = 0;
     int committed = 0;
     cudaStream_t host_stream = nullptr, copy_stream = nullptr;   // l2s_infer_host: compute / clip-copy streams (created on first use)
-    cudaEvent_t copy_done = nullptr;
+    cudaEvent_t copy_done[2] = {nullptr, nullptr}, slot_done[2] = {nullptr, nullptr}, video_consumed[2] = {nullptr, nullptr};
+    bool slot_used[2] = {false, false};
     void* nccl_comm = nullptr; int world = 1, rank = 0;          // data-parallel gradient exchange (l2s_comm_init)
     bool use_pw = true;                       // streaming mma.sync kernel for the trunk's 1x1 convolutions (L2S_PW=0: tcgen05 GEMM)
     bool use_dec3 = true;                     // stage-pipelined decode kernel for 8 < B <= 32 (L2S_DEC3=0: row-partitioned kernel for every B)
@@ -83,6 +84,10 @@ struct Context {
             size_t alloc = (bytes + 255) & ~size_t(255);
             L2S_CUDA(cudaMalloc(&b.p, alloc));
             L2S_CUDA(cudaMemset(b.p, 0, alloc));
+            // cudaMemset on device memory is asynchronous on the legacy default stream, which does not order against the
+            // caller's (possibly non-blocking) streams: without this, a copy enqueued on such a stream right after the
+            // allocation can be overtaken by the zero fill (seen once per fresh l2s_infer_host_submit slot)
+            L2S_CUDA(cudaDeviceSynchronize());
             b.bytes = alloc;
         }
         return b.p;
@@ -113,10 +118,15 @@ struct Context {
             if (kv.second.e1) cudaEventDestroy(kv.second.e1);
         }
         spans.clear();
-        if (copy_done) cudaEventDestroy(copy_done);
+        for (int i = 0; i < 2; ++i) {
+            if (copy_done[i]) cudaEventDestroy(copy_done[i]);
+            if (slot_done[i]) cudaEventDestroy(slot_done[i]);
+            if (video_consumed[i]) cudaEventDestroy(video_consumed[i]);
+            copy_done[i] = slot_done[i] = video_consumed[i] = nullptr; slot_used[i] = false;
+        }
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (host_stream) cudaStreamDestroy(host_stream);
-        copy_done = nullptr; copy_stream = host_stream = nullptr;
+        copy_stream = host_stream = nullptr;
     }
 };
 

@@ -127,6 +127,20 @@ def test_host_entry_point_matches_device_path(be, golden):
         mel, lengths = be.infer(video.cuda(), wav.cuda(), g.cuda())
         assert torch.equal(mel_h, mel.cpu()) and torch.equal(len_h, lengths.cpu())
     assert rel_err(mel_h, golden["A_mel"]) < TOL
+    # pipelined form: two different batches in flight in the two staging slots
+    v2, w2, g2 = synth.video(3, 29, seed=8), synth.wav(3, seed=8), synth.gumbel(3, 29, seed=8)
+    pins = [t.pin_memory() for t in (video, wav, g, v2, w2, g2)]
+    out = [(torch.empty(2, 80, 300).pin_memory(), torch.empty(2, dtype=torch.int64).pin_memory()),
+           (torch.empty(3, 80, 300).pin_memory(), torch.empty(3, dtype=torch.int64).pin_memory())]
+    be.infer_host_submit(0, pins[0], pins[1], pins[2], *out[0])
+    be.infer_host_submit(1, pins[3], pins[4], pins[5], *out[1])
+    be.infer_host_submit(0, pins[0], pins[1], pins[2], *out[0])          # slot 0 again while slot 1 is still in flight
+    be.infer_host_wait(1); be.infer_host_wait(0)
+    assert torch.equal(out[0][0], mel.cpu())
+    m2, l2 = be.infer(v2.cuda(), w2.cuda(), g2.cuda())
+    assert torch.equal(out[1][0], m2.cpu()) and torch.equal(out[1][1], l2.cpu())
+    with pytest.raises(RuntimeError):
+        be.infer_host_wait(2)
 
 
 def test_batch_33_two_clip_groups_vs_oracle(be, O, weights):
