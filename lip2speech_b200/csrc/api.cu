@@ -317,7 +317,12 @@ static void video_forward(Context& c, const float* video, int B, int T, int H, i
             p.A = x + hp; p.lda = cph; p.bias = c.dev(n + "b2pw1.b"); p.act = ACT_RELU;
             p.C = t2; p.ldc = hp; p.M = (int)rows; p.N = half; p.Kc = hp;
             gemm_auto(c, p, n + "b2pw1", s, "b2 pw1");
-            dwconv3x3_kernel<<<ew_grid(rows * (hp / 4)), 256, 0, s>>>(t2, hp, 0, t1, hp, 0, c.dev(n + "b2dw.w"), c.dev(n + "b2dw.b"), N, h, w, hp, 1, h, w);
+            if (w % 4 == 0)
+                dwconv3x3_s1_strip_kernel<4><<<ew_grid(rows / 4 * (hp / 4)), 256, 0, s>>>(t2, hp, 0, t1, hp, 0, c.dev(n + "b2dw.w"), c.dev(n + "b2dw.b"), N, h, w, hp);
+            else if (w % 3 == 0)
+                dwconv3x3_s1_strip_kernel<3><<<ew_grid(rows / 3 * (hp / 4)), 256, 0, s>>>(t2, hp, 0, t1, hp, 0, c.dev(n + "b2dw.w"), c.dev(n + "b2dw.b"), N, h, w, hp);
+            else
+                dwconv3x3_kernel<<<ew_grid(rows * (hp / 4)), 256, 0, s>>>(t2, hp, 0, t1, hp, 0, c.dev(n + "b2dw.w"), c.dev(n + "b2dw.b"), N, h, w, hp, 1, h, w);
             check_launch(c, "b2 dw");
             p = gemm_defaults();
             p.A = t1; p.lda = hp; p.bias = c.dev(n + "b2pw2.b"); p.act = ACT_RELU;

@@ -63,6 +63,50 @@ __global__ void dwconv3x3_kernel(const float* __restrict__ x, int ldx, int xoff,
     }
 }
 
+// Stride-1 variant: one thread produces WT consecutive outputs along w for its channel quad, keeping the nine weights and
+// a (WT+2)-wide input window in registers: (WT+2)*3 activation loads per WT outputs instead of 9 per output.
+template <int WT>
+__global__ void dwconv3x3_s1_strip_kernel(const float* __restrict__ x, int ldx, int xoff, float* __restrict__ y, int ldy, int yoff,
+                                          const float* __restrict__ w, const float* __restrict__ bias, int N, int H, int W, int C) {
+    const int c4n = C >> 2, nstrip = W / WT;
+    const size_t total = (size_t)N * H * nstrip * c4n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int c4 = i % c4n; size_t r = i / c4n;
+        int st = r % nstrip; r /= nstrip;
+        int ho = r % H; int n = r / H;
+        const int wo0 = st * WT;
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c4 * 4));
+        float4 acc[WT];
+#pragma unroll
+        for (int j = 0; j < WT; ++j) acc[j] = b;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const int hi = ho + kh - 1;
+            if (hi < 0 || hi >= H) continue;
+            float4 k[3];
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) k[kw] = __ldg(reinterpret_cast<const float4*>(w + (kh * 3 + kw) * C + c4 * 4));
+            const float* row = x + ((size_t)n * H + hi) * W * ldx + xoff + c4 * 4;
+            float4 v[WT + 2];
+#pragma unroll
+            for (int j = 0; j < WT + 2; ++j) {
+                const int wi = wo0 + j - 1;
+                v[j] = (wi >= 0 && wi < W) ? *reinterpret_cast<const float4*>(row + (size_t)wi * ldx) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < WT; ++j)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    acc[j].x = fmaf(v[j + kw].x, k[kw].x, acc[j].x); acc[j].y = fmaf(v[j + kw].y, k[kw].y, acc[j].y);
+                    acc[j].z = fmaf(v[j + kw].z, k[kw].z, acc[j].z); acc[j].w = fmaf(v[j + kw].w, k[kw].w, acc[j].w);
+                }
+        }
+#pragma unroll
+        for (int j = 0; j < WT; ++j)
+            *reinterpret_cast<float4*>(y + (((size_t)n * H + ho) * W + wo0 + j) * ldy + yoff + c4 * 4) = acc[j];
+    }
+}
+
 // Pass-through half of a stride-1 block followed by channel_shuffle(2): logical output channel 2j takes
 // logical input channel j (< half).  Physical channel of logical l: l < half ? l : l - half + hp.
 __global__ void shuffle_passthrough_kernel(const float* __restrict__ x, float* __restrict__ y, size_t rows, int ld, int half, int hp) {
