@@ -352,9 +352,9 @@ static void launch_lstm(Context& c, LstmParams lp, cudaStream_t s) {
     unsigned* bar = static_cast<unsigned*>(c.buf("ws.barrier", 256));
     L2S_CUDA(cudaMemsetAsync(bar, 0, 4, s));
     lp.barrier = bar;
-    const size_t smem = ((size_t)lp.max_chunks * 16 * 2 * lp.H + MV_WARPS * 16 * MV_CLIPS + 16 * MV_CLIPS) * sizeof(float);
+    const size_t smem = lstm_smem_bytes(lp.H);
     L2S_CUDA(cudaFuncSetAttribute(lstm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = std::min(c.num_sms, lp.nchunks);
+    const int grid = c.num_sms;
     void* args[] = {&lp};
     L2S_CUDA(cudaLaunchCooperativeKernel((void*)lstm_persistent_kernel, dim3(grid), dim3(MV_THREADS), args, smem, s));
     c.launches++;
@@ -390,9 +390,9 @@ static void speaker_forward(Context& c, const float* wav, int B, int S, float* e
     L2S_CUDA(cudaMemsetAsync(cbuf, 0, L * plane * sizeof(float), s));
     LstmParams lp{};
     lp.xproj = xproj; lp.ldx = 4 * H; lp.wpk = c.dev("s.lstm.w");
-    lp.chunks = reinterpret_cast<const LstmChunk*>(c.dev("s.lstm.chunks")); lp.nchunks = (int)c.meta.at("s.lstm.nchunks");
+    lp.blocks = reinterpret_cast<const LstmBlock*>(c.dev("s.lstm.blocks"));
     lp.hbuf = hbuf; lp.cbuf = cbuf; lp.out = nullptr; lp.ldo = 0;
-    lp.T = F; lp.B = B; lp.Bpad = Bpad; lp.H = H; lp.L = L; lp.dirs = 1; lp.max_chunks = (int)c.meta.at("s.lstm.max_chunks");
+    lp.T = F; lp.B = B; lp.Bpad = Bpad; lp.H = H; lp.L = L; lp.dirs = 1;
     launch_lstm(c, lp, s);
     const int nsteps = F + L - 1;
     const float* hfinal = hbuf + (size_t)(nsteps & 1) * L * plane + (size_t)(L - 1) * plane;
@@ -575,9 +575,9 @@ static void decoder_run(Context& c, const float* visual, const float* spk, const
     {
         LstmParams lp{};
         lp.xproj = xproj; lp.ldx = 4096; lp.wpk = c.dev("d.ernn.w");
-        lp.chunks = reinterpret_cast<const LstmChunk*>(c.dev("d.ernn.chunks")); lp.nchunks = (int)c.meta.at("d.ernn.nchunks");
+        lp.blocks = reinterpret_cast<const LstmBlock*>(c.dev("d.ernn.blocks"));
         lp.hbuf = eh; lp.cbuf = ec; lp.out = rnn_out; lp.ldo = 1024;
-        lp.T = T; lp.B = B; lp.Bpad = Bpad; lp.H = 512; lp.L = 1; lp.dirs = 2; lp.max_chunks = (int)c.meta.at("d.ernn.max_chunks");
+        lp.T = T; lp.B = B; lp.Bpad = Bpad; lp.H = 512; lp.L = 1; lp.dirs = 2;
         launch_lstm(c, lp, s);
     }
     const float* hfinal = eh + (size_t)(T & 1) * 2 * plane;      // feature-major [h_fwd ; h_bwd] = decoder (h0 ; h1)

@@ -203,6 +203,84 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// ---- 32-clip tensor-core pass on the feature-major layout (lstm.cuh) ----------------------------------------------
+// RT 16-row weight tiles x four n-tiles of 8 clips.  MMA column n of n-tile j <-> clip 4n + j, so lane (g, t) reads
+// X[k][4g..4g+3] as one LDG.128 per k (full 128-byte lines per warp) and ends up holding 8 consecutive clips of rows g and
+// g+8; MMA column t / t+4 of k8-step s <-> real k = k0 + 4t + 2s / + 2s + 1, weights W[g][k0+4t..+3] as LDS.128.
+// K % 256 == 0 and K <= 512 per segment: a warp owns K/256 chunks and requests them all before its first MMA.
+template <int RT>
+__device__ __forceinline__ void mv32_zero(float (&acc)[RT][4][4]) {
+#pragma unroll
+    for (int r = 0; r < RT; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[r][j][i] = 0.f;
+}
+
+template <int RT>
+__device__ __forceinline__ void mv32_accumulate(const float* __restrict__ W, int ldw, int wcol0, int R,
+                                                const float* __restrict__ X, int K, int ldb, int b0, float (&acc)[RT][4][4]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int npw = K / (MV_KC * MV_WARPS);                  // 1 or 2 chunks per warp
+    float4 x[2][4];
+#pragma unroll
+    for (int d = 0; d < 2; ++d)
+        if (d < npw) {
+            const float* xp = X + (size_t)((warp + d * MV_WARPS) * MV_KC + 4 * t) * ldb + b0 + 4 * g;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) x[d][i] = ldcg4(xp + (size_t)i * ldb);
+        }
+#pragma unroll
+    for (int d = 0; d < 2; ++d)
+        if (d < npw) {
+            const int k0 = wcol0 + (warp + d * MV_WARPS) * MV_KC + 4 * t;
+            uint32_t xh[4][4], xl[4][4];                      // [k index i][clip j]
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                split_tf32(x[d][i].x, xh[i][0], xl[i][0]); split_tf32(x[d][i].y, xh[i][1], xl[i][1]);
+                split_tf32(x[d][i].z, xh[i][2], xl[i][2]); split_tf32(x[d][i].w, xh[i][3], xl[i][3]);
+            }
+#pragma unroll
+            for (int rt = 0; rt < RT; ++rt) {
+                const float4 wa = *reinterpret_cast<const float4*>(W + (size_t)min(rt * 16 + g, R - 1) * ldw + k0);
+                const float4 wb = *reinterpret_cast<const float4*>(W + (size_t)min(rt * 16 + g + 8, R - 1) * ldw + k0);
+                const float wav[4] = {wa.x, wa.y, wa.z, wa.w}, wbv[4] = {wb.x, wb.y, wb.z, wb.w};
+                uint32_t ah[4], al[4], bh[4], bl[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { split_tf32(wav[i], ah[i], al[i]); split_tf32(wbv[i], bh[i], bl[i]); }
+#pragma unroll
+                for (int s = 0; s < 2; ++s)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        mma_tf32(acc[rt][j], al[2 * s], bl[2 * s], al[2 * s + 1], bl[2 * s + 1], xh[2 * s][j], xh[2 * s + 1][j]);
+                        mma_tf32(acc[rt][j], ah[2 * s], bh[2 * s], ah[2 * s + 1], bh[2 * s + 1], xl[2 * s][j], xl[2 * s + 1][j]);
+                        mma_tf32(acc[rt][j], ah[2 * s], bh[2 * s], ah[2 * s + 1], bh[2 * s + 1], xh[2 * s][j], xh[2 * s + 1][j]);
+                    }
+            }
+        }
+}
+
+// Cross-warp reduction of one row tile through `red` (MV_WARPS x 16 x 32 floats).  Thread tid receives the finished value
+// for (row tid>>5 of the tile, clip tid&31).  Contains one __syncthreads(); the caller must __syncthreads() again before
+// `red` is reused.
+__device__ __forceinline__ float mv32_reduce_tile(const float (&a)[4][4], float* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    float* base = red + (size_t)warp * 16 * MV_CLIPS;
+    *reinterpret_cast<float4*>(base + g * MV_CLIPS + 8 * t) = make_float4(a[0][0], a[1][0], a[2][0], a[3][0]);
+    *reinterpret_cast<float4*>(base + g * MV_CLIPS + 8 * t + 4) = make_float4(a[0][1], a[1][1], a[2][1], a[3][1]);
+    *reinterpret_cast<float4*>(base + (g + 8) * MV_CLIPS + 8 * t) = make_float4(a[0][2], a[1][2], a[2][2], a[3][2]);
+    *reinterpret_cast<float4*>(base + (g + 8) * MV_CLIPS + 8 * t + 4) = make_float4(a[0][3], a[1][3], a[2][3], a[3][3]);
+    __syncthreads();
+    const int r = threadIdx.x >> 5, b = threadIdx.x & 31;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < MV_WARPS; ++w) v += red[(size_t)(w * 16 + r) * MV_CLIPS + b];
+    return v;
+}
+
 // ---- 8-clip variant for the stage-pipelined decode kernel (decode3.cuh) ------------------------------------------
 // One n-tile (8 clips) and RT 16-row tiles per pass, so the activation fragment of a chunk (4 floats per lane) is reused
 // by every row tile.  Activations are GROUP-MAJOR here: X[k][8] for one clip group, so the 16 k x 8 clips of a chunk are

@@ -184,40 +184,47 @@ inline void pack_video(Context& c) {
 // ------------------------------------------------------------------------------------------------
 // LSTM chunking shared by the decoder's encoder_rnn and the speaker encoder
 // ------------------------------------------------------------------------------------------------
-struct LstmPack { std::vector<LstmChunk> chunks; std::vector<float> w; int max_chunks = 0; };
+struct LstmPack { std::vector<LstmBlock> blocks; std::vector<float> w; bool ok = true; };
 
-// layers x dirs x H units in chunks of <=4 units.  get_w(layer, dir, which /*0 ih, 1 hh*/) returns the
-// torch-layout [4H][in] matrix, get_b(layer, dir) the summed bias.
+// layers x dirs planes of H units; the CTAs are divided evenly among the planes and every CTA gets ONE block of
+// <= LSTM_MAX_UNITS consecutive units of its plane.  get_w(layer, dir, which /*0 ih, 1 hh*/) returns the torch-layout
+// [4H][in] matrix, get_b(layer, dir) the summed bias.
 template <typename GW, typename GB>
 inline LstmPack pack_lstm(int L, int dirs, int H, int num_ctas, GW get_w, GB get_b) {
     LstmPack pk;
+    pk.blocks.assign(num_ctas, LstmBlock{});
+    const int planes = L * dirs;
+    int cta = 0;
     for (int l = 0; l < L; ++l)
-        for (int d = 0; d < dirs; ++d)
-            for (int u0 = 0; u0 < H; u0 += 4) {
-                LstmChunk ck{};
-                ck.layer = l; ck.dir = d; ck.u0 = u0; ck.nu = std::min(4, H - u0);
-                ck.K0 = H; ck.K1 = (l == 0) ? 0 : H;
-                ck.w_off = (int)pk.w.size();
-                const int K = ck.K0 + ck.K1;
-                pk.w.resize(pk.w.size() + (size_t)16 * K, 0.f);
-                const std::vector<float>* wih = (l == 0) ? nullptr : get_w(l, d, 0);
-                const std::vector<float>* whh = get_w(l, d, 1);
-                const std::vector<float> bsum = get_b(l, d);
-                for (int ul = 0; ul < ck.nu; ++ul)
+        for (int d = 0; d < dirs; ++d) {
+            const int pl = l * dirs + d;
+            const int nc = num_ctas / planes + (pl < num_ctas % planes ? 1 : 0);      // CTAs of this plane
+            const int per = (H + nc - 1) / nc;
+            if (nc == 0 || per > LSTM_MAX_UNITS) { pk.ok = false; return pk; }
+            const std::vector<float>* wih = (l == 0) ? nullptr : get_w(l, d, 0);
+            const std::vector<float>* whh = get_w(l, d, 1);
+            const std::vector<float> bsum = get_b(l, d);
+            for (int j = 0; j < nc; ++j, ++cta) {
+                LstmBlock& bk = pk.blocks[cta];
+                bk.layer = l; bk.dir = d; bk.u0 = std::min(H, j * per); bk.nu = std::min(per, H - bk.u0);
+                bk.K0 = H; bk.K1 = (l == 0) ? 0 : H;
+                bk.w_off = (int)pk.w.size();
+                const int K = bk.K0 + bk.K1;
+                pk.w.resize(pk.w.size() + (size_t)4 * bk.nu * K, 0.f);
+                for (int ul = 0; ul < bk.nu; ++ul)
                     for (int g = 0; g < 4; ++g) {
-                        const int r = 4 * ul + g, row = g * H + u0 + ul;
-                        float* dst = pk.w.data() + ck.w_off + (size_t)r * K;
+                        const int r = 4 * ul + g, row = g * H + bk.u0 + ul;
+                        float* dst = pk.w.data() + bk.w_off + (size_t)r * K;
                         if (l == 0) {
                             std::copy(whh->begin() + (size_t)row * H, whh->begin() + (size_t)(row + 1) * H, dst);
                         } else {
                             std::copy(wih->begin() + (size_t)row * H, wih->begin() + (size_t)(row + 1) * H, dst);
                             std::copy(whh->begin() + (size_t)row * H, whh->begin() + (size_t)(row + 1) * H, dst + H);
                         }
-                        ck.bias[r] = (l == 0) ? 0.f : bsum[row];
+                        bk.bias[r] = (l == 0) ? 0.f : bsum[row];
                     }
-                pk.chunks.push_back(ck);
             }
-    pk.max_chunks = ((int)pk.chunks.size() + num_ctas - 1) / num_ctas;
+        }
     return pk;
 }
 
@@ -251,10 +258,9 @@ inline void pack_speaker(Context& c) {
     auto gw = [&](int l, int, int which) { return &c.W(p + "lstm.weight_" + (which ? "hh" : "ih") + "_l" + std::to_string(l)).f; };
     auto gb = [&](int l, int) { return vadd(c.W(p + "lstm.bias_ih_l" + std::to_string(l)).f, c.W(p + "lstm.bias_hh_l" + std::to_string(l)).f); };
     LstmPack pk = pack_lstm(3, 1, 256, c.num_sms, gw, gb);
-    if (pk.max_chunks > LSTM_MAX_CHUNKS) throw L2sError(1, "speaker LSTM does not fit this SM count");
+    if (!pk.ok) throw L2sError(1, "speaker LSTM does not fit this SM count");
     c.upload("s.lstm.w", pk.w);
-    c.upload_raw("s.lstm.chunks", pk.chunks.data(), pk.chunks.size());
-    c.meta["s.lstm.nchunks"] = (int64_t)pk.chunks.size(); c.meta["s.lstm.max_chunks"] = pk.max_chunks;
+    c.upload_raw("s.lstm.blocks", pk.blocks.data(), pk.blocks.size());
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -611,10 +617,9 @@ inline void pack_decoder(Context& c) {
         auto gw = [&](int, int d, int which) { return &c.W(p + "encoder_rnn.weight_" + (which ? "hh" : "ih") + "_l0" + (d ? "_reverse" : "")).f; };
         auto gb = [&](int, int) { return std::vector<float>(); };
         LstmPack pk = pack_lstm(1, 2, 512, c.num_sms, gw, gb);
-        if (pk.max_chunks > LSTM_MAX_CHUNKS) throw L2sError(1, "encoder LSTM does not fit this SM count");
+        if (!pk.ok) throw L2sError(1, "encoder LSTM does not fit this SM count");
         c.upload("d.ernn.w", pk.w);
-        c.upload_raw("d.ernn.chunks", pk.chunks.data(), pk.chunks.size());
-        c.meta["d.ernn.nchunks"] = (int64_t)pk.chunks.size(); c.meta["d.ernn.max_chunks"] = pk.max_chunks;
+        c.upload_raw("d.ernn.blocks", pk.blocks.data(), pk.blocks.size());
     }
     // K / V MultiHopConv: the four convolutions of K and of V read the same input, so each pair is packed as ONE
     // conv with 1024 output channels (rows 0..511 = K branch, 512..1023 = V branch)
