@@ -72,6 +72,20 @@ __global__ void __launch_bounds__(MV_THREADS, 1) lstm_persistent_kernel(const Ls
             const float* x0 = (bk.layer == 0) ? hcur + plane * lstride : hcur + (plane - p.dirs) * lstride;
             const float* x1 = hcur + plane * lstride;
             for (int b0 = 0; b0 < p.Bpad; b0 += MV_CLIPS) {
+                // operands of the epilogue that do not depend on this step's pass are requested first: the layer-0 input
+                // projection (or nothing) for this thread's two gate rows, and the cell state of its (unit, clip)
+                float xin[2] = {0.f, 0.f};
+                if (bk.layer == 0) {
+#pragma unroll
+                    for (int rt = 0; rt < 2; ++rt) {
+                        const int r = 16 * rt + (tid >> 5), b = b0 + (tid & 31);
+                        if ((r >> 2) < bk.nu && b < p.B)
+                            xin[rt] = __ldg(p.xproj + ((size_t)b * p.T + t) * p.ldx + bk.dir * 4 * p.H + (r & 3) * p.H + bk.u0 + (r >> 2));
+                    }
+                }
+                float c_prev = 0.f;
+                if (tid < bk.nu * MV_CLIPS && b0 + (tid & 31) < p.B)
+                    c_prev = __ldcg(p.cbuf + (size_t)plane * lstride + (size_t)(bk.u0 + (tid >> 5)) * p.Bpad + b0 + (tid & 31));
                 float acc[2][4][4];                          // two row tiles (rows >= R re-read row R-1, results unused)
                 mv32_zero<2>(acc);
                 mv32_accumulate<2>(wsm, ldw, 0, R, x0, bk.K0, p.Bpad, b0, acc);
@@ -81,11 +95,8 @@ __global__ void __launch_bounds__(MV_THREADS, 1) lstm_persistent_kernel(const Ls
                     if (rt < RT) {
                         float v = mv32_reduce_tile(acc[rt], red);
                         const int r = 16 * rt + (tid >> 5), bb = tid & 31, b = b0 + bb;
-                        const int ul = r >> 2, g = r & 3, u = bk.u0 + ul;
-                        if (ul < bk.nu && b < p.B) {
-                            if (bk.layer == 0) v += __ldg(p.xproj + ((size_t)b * p.T + t) * p.ldx + bk.dir * 4 * p.H + g * p.H + u);
-                            else v += bk.bias[r];
-                        }
+                        const int ul = r >> 2, g = r & 3;
+                        if (ul < bk.nu && b < p.B) v += (bk.layer == 0) ? xin[rt] : bk.bias[r];
                         gsm[r * MV_CLIPS + bb] = (g == 2) ? tanhf(v) : sigmoidf_acc(v);      // i, f, o: sigmoid; g: tanh
                         __syncthreads();
                     }
@@ -97,7 +108,7 @@ __global__ void __launch_bounds__(MV_THREADS, 1) lstm_persistent_kernel(const Ls
                         const float gg = gsm[(r + 2) * MV_CLIPS + bb], go = gsm[(r + 3) * MV_CLIPS + bb];
                         const int u = bk.u0 + ul;
                         const size_t si = (size_t)plane * lstride + (size_t)u * p.Bpad + b;
-                        const float c = gf * p.cbuf[si] + gi * gg;
+                        const float c = gf * c_prev + gi * gg;
                         const float h = go * tanhf(c);
                         p.cbuf[si] = c;
                         hnext[si] = h;
