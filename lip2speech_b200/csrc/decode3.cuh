@@ -347,8 +347,8 @@ __device__ __forceinline__ void d3_loop(const Decode3Params& q, const Dec3Pass& 
             if (job >= 0) {
                 const int b = g * D3_CG + aclip;
                 if (q.kv_smem) {
-                    D3Slot na = none;                        // this CTA's next active turn (at most D3_NG turns ahead)
-                    for (int d = 1; d <= D3_NG && !na.active && turn + d < nturns; ++d) na = d3_slot(turn + d, role, p.steps, p.B);
+                    D3Slot na = next;                        // this CTA's next active turn (at most D3_NG turns ahead)
+                    for (int d = 2; d <= D3_NG && !na.active && turn + d < nturns; ++d) na = d3_slot(turn + d, role, p.steps, p.B);
                     if (na.active) {
                         d3_prefetch_kv(p, kvbuf + (size_t)(kv_issued & 1) * kvfloats, &kvbar[kv_issued & 1], min(na.g * D3_CG + aclip, p.B - 1), apart);
                         ++kv_issued;
