@@ -1,5 +1,6 @@
-// Weight-stationary batched mat-vec pass used by the persistent recurrent kernels
-// (decoder step loop, Bi-LSTM encoder, speaker-encoder LSTM).
+// Weight-stationary batched mat-vec passes used by the persistent recurrent kernels: the FMA pass (mv_*, row-partitioned
+// decode kernel), the 32-clip tensor-core pass (mv32_*, Bi-LSTM encoder and speaker-encoder LSTM) and the 8-clip
+// tensor-core pass (mv8_*, stage-pipelined decode kernel).
 //
 // One CTA (512 threads = 16 warps) owns R rows of a weight matrix, resident in shared memory as
 // Wsm[R][ldw] fp32.  Activations live in global memory (L2) FEATURE-MAJOR: X[k][ldb] with the clip
@@ -22,10 +23,6 @@ constexpr int MV_WARPS = 16;
 constexpr int MV_CLIPS = 32;      // clips per pass invocation
 constexpr int MV_GW = 8;          // k values per warp-group (2 k-quads x 4)
 
-struct Seg {
-    const float* x;   // feature-major [K][ldb], already offset to the first feature of the segment
-    int K;            // multiple of 8
-};
 
 template <int R>
 __device__ __forceinline__ void mv_zero(float (&acc)[R][2]) {
@@ -390,17 +387,6 @@ __device__ __forceinline__ float mv8_reduce_round(const float (&acc)[RT][4], int
         for (int w = 0; w < MV_WARPS; ++w) v += part[w];
     }
     return v;
-}
-
-// Convenience: one- or two-segment pass with a full-size reduction buffer (used by lstm.cuh).
-template <int R>
-__device__ __forceinline__ float mv_pass(const float* __restrict__ Wsm, int ldw,
-                                         const Seg& s0, const Seg& s1, int ldb, int b0, float* red) {
-    float acc[R][2];
-    mv_zero<R>(acc);
-    mv_accumulate<R>(Wsm, ldw, 0, s0.x, s0.K, ldb, b0, acc);
-    if (s1.K > 0) mv_accumulate<R>(Wsm, ldw, s0.K, s1.x, s1.K, ldb, b0, acc);
-    return mv_reduce<R, R>(acc, red);
 }
 
 }  // namespace l2s
