@@ -99,7 +99,7 @@ static void linear(Context& c, const float* A, int lda, const std::string& wname
 
 // Dense (1-tap) GEMM described SIMT-style (GemmParams with W unset): tcgen05 path when TMA alignment allows, else SIMT.
 static bool pw_eligible(const Context& c, const GemmParams& g) {
-    return c.use_tc && c.use_pw && g.taps == 1 && g.stride == 1 && !g.stem && g.Kc <= 240 && g.M >= 16384 && (g.act == ACT_NONE || g.act == ACT_RELU) &&
+    return c.use_tc && c.use_pw && g.taps == 1 && g.stride == 1 && !g.stem && g.Kc <= 240 && g.M >= c.pw_min_rows && (g.act == ACT_NONE || g.act == ACT_RELU) &&
            !g.addrow && !g.addpos && !g.resid && !g.transposed && (g.lda % 4) == 0 && (g.Kc % 4) == 0 && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0;
 }
 
@@ -736,6 +736,13 @@ static void decoder_run(Context& c, const float* visual, const float* spk, const
             check_launch(c, "state -> group-major");
             dp.S = S3;
             q.d = dp;
+            float* vsplit = c.fbuf("ws.d.Vsplit", (size_t)B * T * 512);
+            float* cvsplit = c.fbuf("ws.d.cvsplit", (size_t)B * minT * 256);
+            split_halves_kernel<<<ew_grid((size_t)B * T * 512), 256, 0, s>>>(Vmem, vsplit, B, T, 256);
+            check_launch(c, "V halves");
+            split_halves_kernel<<<ew_grid((size_t)B * minT * 256), 256, 0, s>>>(cval, cvsplit, B, minT, 128);
+            check_launch(c, "content value halves");
+            q.Vsplit = vsplit; q.cvsplit = cvsplit;
             q.kv_smem = (size_t)(512 + 320 + 256 + 32) + (size_t)2 * (T * 768 + minT * 384) <= (size_t)c.meta.at("d.step3.wimg_floats") ? 1 : 0;
             q.passes = reinterpret_cast<const Dec3Pass*>(c.dev("d.step3.passes"));
             q.role = reinterpret_cast<const int*>(c.dev("d.step3.role"));
@@ -846,6 +853,7 @@ int l2s_create(l2s_ctx** out, int device) {
     if (const char* e = getenv("L2S_TC")) ctx->c.use_tc = (e[0] != '0');
     if (const char* e = getenv("L2S_DEC3")) ctx->c.use_dec3 = (e[0] != '0');
     if (const char* e = getenv("L2S_PW")) ctx->c.use_pw = (e[0] != '0');
+    if (const char* e = getenv("L2S_PW_MIN_ROWS")) ctx->c.pw_min_rows = std::max(1, atoi(e));
     *out = ctx;
     return L2S_OK;
 }

@@ -58,7 +58,9 @@ struct Decode3Params {
     const int* job;               // [grid] attention job inside a clip group (clip*D3_NSPLIT + part) or -1
     const float* wimg;            // [grid][wimg_floats]
     int wimg_floats;
-    int kv_smem;                  // 1: two clips' K + V-half fit in shared memory (T <= 33)
+    int kv_smem;                  // 1: two clips' K + V-half fit in shared memory (T <= 31)
+    const float* Vsplit;          // [B][2][T][256]: the two feature halves of V, each contiguous (one bulk copy per image)
+    const float* cvsplit;         // [B][2][minT][128]: likewise for the content values
     float* timing;                // optional [grid][D3_TIMING_SLOTS]
 };
 
@@ -202,25 +204,20 @@ __device__ __forceinline__ void d3_turn(const DecodeParams& p, const Dec3Pass& p
 // of the content values [minT][128].
 __device__ __forceinline__ int d3_kv_floats(int T, int minT) { return T * 768 + minT * 384; }
 
-// Issued by warp 0: one expect_tx + T + 6 bulk copies (K in one piece, the strided halves row by row).
-__device__ __forceinline__ void d3_prefetch_kv(const DecodeParams& p, float* buf, uint64_t* bar, int b, int part) {
-    if (threadIdx.x >= 32) return;
-    const int lane = threadIdx.x;
-    const float* K = p.Kmem + (size_t)b * p.T * 512;
-    const float* V = p.Vmem + (size_t)b * p.T * 512 + part * 256;
-    const float* ck = p.ckey + (size_t)b * p.minT * 256;
-    const float* cv = p.cval + (size_t)b * p.minT * 256 + part * 128;
+// Issued by one thread: expect_tx + four bulk copies (K, this CTA's half of V, content keys, its half of the content values;
+// the halves come from the pre-split copies so that each is one contiguous piece — 35 row-wise bulk copies per image
+// cost the issuing warp 1.2 us per turn).
+__device__ __forceinline__ void d3_prefetch_kv(const Decode3Params& q, float* buf, uint64_t* bar, int b, int part) {
+    if (threadIdx.x != 0) return;
+    const DecodeParams& p = q.d;
     float* vb = buf + (size_t)p.T * 512;
     float* ckb = vb + (size_t)p.T * 256;
     float* cvb = ckb + (size_t)p.minT * 256;
-    if (lane == 0) {
-        mbar_expect_tx(bar, (uint32_t)d3_kv_floats(p.T, p.minT) * 4u);
-        bulk_load_1d(buf, K, (uint32_t)p.T * 2048u, bar);
-        bulk_load_1d(ckb, ck, (uint32_t)p.minT * 1024u, bar);
-    }
-    __syncwarp();
-    for (int t = lane; t < p.T; t += 32) bulk_load_1d(vb + t * 256, V + (size_t)t * 512, 1024u, bar);
-    for (int m = lane; m < p.minT; m += 32) bulk_load_1d(cvb + m * 128, cv + (size_t)m * 256, 512u, bar);
+    mbar_expect_tx(bar, (uint32_t)d3_kv_floats(p.T, p.minT) * 4u);
+    bulk_load_1d(buf, p.Kmem + (size_t)b * p.T * 512, (uint32_t)p.T * 2048u, bar);
+    bulk_load_1d(vb, q.Vsplit + ((size_t)b * 2 + part) * p.T * 256, (uint32_t)p.T * 1024u, bar);
+    bulk_load_1d(ckb, p.ckey + (size_t)b * p.minT * 256, (uint32_t)p.minT * 1024u, bar);
+    bulk_load_1d(cvb, q.cvsplit + ((size_t)b * 2 + part) * p.minT * 128, (uint32_t)p.minT * 512u, bar);
 }
 
 // Dot-product attention over the T encoder positions and over the minT content slots for clip b (reference
@@ -324,7 +321,7 @@ __device__ __forceinline__ void d3_loop(const Decode3Params& q, const Dec3Pass& 
     // prologue A(-1): Q, content query and prenet(BOS) of every clip group from the initial state in S[0]
     if (role == ROLE_A && has_pass)
         for (int g = 0; g * D3_CG < p.B; ++g) d3_turn<RT, EARLY>(p, ps, sm, sync, g, -1, 0, xe, xe_valid, none);
-    if (job >= 0 && q.kv_smem) d3_prefetch_kv(p, kvbuf, &kvbar[0], min(aclip, p.B - 1), apart);          // turn 0 serves group 0
+    if (job >= 0 && q.kv_smem) d3_prefetch_kv(q, kvbuf, &kvbar[0], min(aclip, p.B - 1), apart);          // turn 0 serves group 0
     grid_arrive(p.barrier);
     sync.target += n;
     sync.timing = (q.timing != nullptr);
@@ -350,7 +347,7 @@ __device__ __forceinline__ void d3_loop(const Decode3Params& q, const Dec3Pass& 
                     D3Slot na = next;                        // this CTA's next active turn (at most D3_NG turns ahead)
                     for (int d = 2; d <= D3_NG && !na.active && turn + d < nturns; ++d) na = d3_slot(turn + d, role, p.steps, p.B);
                     if (na.active) {
-                        d3_prefetch_kv(p, kvbuf + (size_t)(kv_issued & 1) * kvfloats, &kvbar[kv_issued & 1], min(na.g * D3_CG + aclip, p.B - 1), apart);
+                        d3_prefetch_kv(q, kvbuf + (size_t)(kv_issued & 1) * kvfloats, &kvbar[kv_issued & 1], min(na.g * D3_CG + aclip, p.B - 1), apart);
                         ++kv_issued;
                     }
                 }
@@ -426,6 +423,16 @@ __global__ void __launch_bounds__(MV_THREADS, 1) decode3_kernel(const Decode3Par
     else d3_loop<8, false>(q, pass, sm, sync, role, job, kvbar);
     __syncthreads();
     if (q.timing && tid < D3_TIMING_SLOTS) q.timing[blockIdx.x * D3_TIMING_SLOTS + tid] = tacc[tid];
+}
+
+// src [B][rows][2*half] -> dst [B][2][rows][half] (feature halves made contiguous for the attention CTAs' bulk copies)
+__global__ void split_halves_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int rows, int half) {
+    const size_t total = (size_t)B * rows * 2 * half;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int f = i % (2 * half); size_t r = i / (2 * half);
+        const int row = r % rows; const int b = r / rows;
+        dst[(((size_t)b * 2 + f / half) * rows + row) * half + f % half] = src[i];
+    }
 }
 
 // recurrent state of the row-partitioned layout ([feature][Bpad]) -> group-major ([group][feature][8])
