@@ -84,12 +84,12 @@ __device__ __forceinline__ const float* d3_src(const DecodeParams& p, int src, i
     }
 }
 
-// Per-row epilogue of reduction round `round` (rows 32*round .. 32*round+31) for clip group g; threads tid < 256.
+// Per-row epilogue of reduction round `round` (rows 48*round .. 48*round+47) for clip group g; threads tid < 384.
 __device__ __forceinline__ void d3_epilogue(const DecodeParams& p, const Dec3Pass& ps, const DecSmem& sm, float v, float c_prev,
                                             int round, int g, int step, int parity_new) {
     const int tid = threadIdx.x;
-    const int r = 32 * round + (tid >> 3), bb = tid & 7, b = g * D3_CG + bb;
-    const bool live = (tid < 256) && (r < ps.R) && (b < p.B);
+    const int r = 16 * MV8_RTILES * round + (tid >> 3), bb = tid & 7, b = g * D3_CG + bb;
+    const bool live = (tid < 128 * MV8_RTILES) && (r < ps.R) && (b < p.B);
     const bool gate_pass = (ps.op[0] == OP_GATE0 || ps.op[0] == OP_GATE1);      // CTA-uniform
     const int op = live ? ps.op[r] : OP_NONE;
     const int idx = live ? ps.idx[r] : 0;
@@ -124,9 +124,9 @@ __device__ __forceinline__ void d3_epilogue(const DecodeParams& p, const Dec3Pas
             break;
         default: break;
     }
-    if (gate_pass) {                                          // rows are (unit, gate) = (r>>2, r&3); 8 units per round
+    if (gate_pass) {                                          // rows are (unit, gate) = (r>>2, r&3); 12 units per round
         // every thread applies its own gate non-linearity (i, f, o: sigmoid; g: tanh), the gate-0 thread combines
-        if (tid < 256) sm.gsm[tid] = ((r & 3) == 2) ? tanhf(v) : sigmoidf_acc(v);
+        if (tid < 128 * MV8_RTILES) sm.gsm[tid] = ((r & 3) == 2) ? tanhf(v) : sigmoidf_acc(v);
         __syncthreads();
         if (live && (r & 3) == 0 && idx >= 0) {
             const int layer = (op == OP_GATE1) ? 1 : 0;
@@ -160,16 +160,16 @@ __device__ __forceinline__ D3Slot d3_slot(int turn, int role, int steps, int B) 
 template <int RT, bool EARLY>
 __device__ __forceinline__ void d3_turn(const DecodeParams& p, const Dec3Pass& ps, const DecSmem& sm, StageSync& sync,
                                         int g, int step, int parity_new, float (&xe)[D3_EDEPTH][4], bool& xe_valid, const D3Slot& next) {
-    constexpr int ROUNDS = (RT + 1) / 2;
+    constexpr int ROUNDS = (RT + MV8_RTILES - 1) / MV8_RTILES;
     const int tid = threadIdx.x;
     const bool gate_pass = (ps.op[0] == OP_GATE0 || ps.op[0] == OP_GATE1);
     // own cell state (written by this very CTA four turns ago): requested first, consumed in the epilogue
     float c_prev[ROUNDS];
 #pragma unroll
     for (int round = 0; round < ROUNDS; ++round) {
-        const int r = 32 * round + (tid >> 3), b = g * D3_CG + (tid & 7);
+        const int r = 16 * MV8_RTILES * round + (tid >> 3), b = g * D3_CG + (tid & 7);
         c_prev[round] = 0.f;
-        if (gate_pass && tid < 256 && (r & 3) == 0 && r < ps.R && b < p.B)
+        if (gate_pass && tid < 128 * MV8_RTILES && (r & 3) == 0 && r < ps.R && b < p.B)
             c_prev[round] = __ldcg(p.Cst + (size_t)g * 1024 * D3_CG + (size_t)((ps.op[0] == OP_GATE1 ? 512 : 0) + ps.idx[r]) * D3_CG + (tid & 7));
     }
     float acc[RT][4];
@@ -191,7 +191,7 @@ __device__ __forceinline__ void d3_turn(const DecodeParams& p, const Dec3Pass& p
     sync.lap(2);
 #pragma unroll
     for (int round = 0; round < ROUNDS; ++round) {
-        if (32 * round < ps.R) {
+        if (16 * MV8_RTILES * round < ps.R) {
             const float v = mv8_reduce_round<RT>(acc, round, sm.red);
             d3_epilogue(p, ps, sm, v, c_prev[round], round, g, step, parity_new);
             __syncthreads();
@@ -392,9 +392,9 @@ __global__ void __launch_bounds__(MV_THREADS, 1) decode3_kernel(const Decode3Par
     }
 
     DecSmem sm;
-    sm.red = smem;                                           // [16 warps][2 tiles][128]; attention partials [8][256]
-    sm.gsm = sm.red + MV_WARPS * 2 * 128;                    // [32][8]
-    sm.wsm = sm.gsm + 32 * D3_CG;                            // weight image (absent on attention CTAs, whose scratch + K/V live here)
+    sm.red = smem;                                           // [16 warps][3 tiles][128]; attention partials [8][256]
+    sm.gsm = sm.red + MV_WARPS * MV8_RTILES * 128;           // [48][8]
+    sm.wsm = sm.gsm + 16 * MV8_RTILES * D3_CG;                            // weight image (absent on attention CTAs, whose scratch + K/V live here)
     sm.qs = sm.wsm;                                          // [512]
     sm.sc = sm.qs + 512;                                     // [320]
     sm.cqs = sm.sc + 320;                                    // [256]

@@ -362,27 +362,28 @@ __device__ __forceinline__ void mv8_accumulate(const float* __restrict__ W, int 
     mv8_mma<RT, MV8_DEPTH>(W, ldw, wcol0, R, K, x, acc);
 }
 
-// Cross-warp reduction of row tiles 2*round and 2*round+1 through `red` (MV_WARPS x 2 x 128 floats = 16 KB).  Threads
-// tid < 256 receive the finished value for (row 32*round + (tid>>3), clip tid&7).  Contains one __syncthreads(); the
+// Cross-warp reduction of row tiles 3*round .. 3*round+2 through `red` (MV_WARPS x 3 x 128 floats = 24 KB).  Threads
+// tid < 384 receive the finished value for (row 48*round + (tid>>3), clip tid&7).  Contains one __syncthreads(); the
 // caller must __syncthreads() again before `red` is reused.
+constexpr int MV8_RTILES = 3;     // row tiles per reduction round
 template <int RT>
 __device__ __forceinline__ float mv8_reduce_round(const float (&acc)[RT][4], int round, float* red) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
 #pragma unroll
     for (int rt = 0; rt < RT; ++rt)
-        if ((rt >> 1) == round) {
-            float* base = red + (size_t)(warp * 2 + (rt & 1)) * 128;
+        if ((rt / MV8_RTILES) == round) {
+            float* base = red + (size_t)(warp * MV8_RTILES + (rt % MV8_RTILES)) * 128;
             *reinterpret_cast<float2*>(base + g * 8 + 2 * t) = make_float2(acc[rt][0], acc[rt][1]);
             *reinterpret_cast<float2*>(base + (g + 8) * 8 + 2 * t) = make_float2(acc[rt][2], acc[rt][3]);
         }
     __syncthreads();
     float v = 0.f;
-    if (threadIdx.x < 256) {
+    if (threadIdx.x < MV8_RTILES * 128) {
         const int j = threadIdx.x >> 7, e = threadIdx.x & 127;
         float part[MV_WARPS];
 #pragma unroll
-        for (int w = 0; w < MV_WARPS; ++w) part[w] = red[(size_t)(w * 2 + j) * 128 + e];
+        for (int w = 0; w < MV_WARPS; ++w) part[w] = red[(size_t)(w * MV8_RTILES + j) * 128 + e];
 #pragma unroll
         for (int w = 0; w < MV_WARPS; ++w) v += part[w];
     }

@@ -361,7 +361,7 @@ inline void pack_decode_program3(Context& c, const StepRows& w) {
         if (per_cta[i].Ke > 0 && per_cta[i].rows.size() > 48) return;      // early segments are instantiated for <= 3 row tiles
         wimg_floats = std::max(wimg_floats, per_cta[i].rows.size() * (size_t)(per_cta[i].Ke + per_cta[i].Kl + 16));
     }
-    const size_t smem = (wimg_floats + MV_WARPS * 2 * 128 + 32 * D3_CG) * sizeof(float);
+    const size_t smem = (wimg_floats + MV_WARPS * MV8_RTILES * 128 + 16 * MV8_RTILES * D3_CG) * sizeof(float);
     if (smem + sizeof(Dec3Pass) + 1024 > (size_t)c.max_smem_optin) return;
     std::vector<float> wimg((size_t)nC * wimg_floats, 0.f);
     std::vector<Dec3Pass> passes(nC);

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(512, 1) pass_kernel(const float* __restrict__ 
                                                        int R, int K, int ldw, int iters, int do_reduce) {
     extern __shared__ __align__(16) float smem[];
     float* red = smem;
-    float* wsm = smem + 4096;
+    float* wsm = smem + 6144;
     for (int i = threadIdx.x; i < R * K; i += 512) wsm[(i / K) * ldw + (i % K)] = Wg[(size_t)blockIdx.x * R * K + i];
     __syncthreads();
     float sink = 0.f;
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(512, 1) pass_kernel(const float* __restrict__ 
         float acc[MAXRT][4];
         mv8_zero<MAXRT>(acc);
         mv8_accumulate<MAXRT>(wsm, ldw, 0, R, x, K, acc);
-        if (do_reduce) { for (int rd = 0; rd < (MAXRT + 1) / 2; ++rd) { sink += mv8_reduce_round<MAXRT>(acc, rd, red); __syncthreads(); } }
+        if (do_reduce) { for (int rd = 0; rd < (MAXRT + 2) / 3; ++rd) { sink += mv8_reduce_round<MAXRT>(acc, rd, red); __syncthreads(); } }
         else for (int r = 0; r < MAXRT; ++r) sink += acc[r][0] + acc[r][1] + acc[r][2] + acc[r][3];
     }
     out[(size_t)blockIdx.x * 512 + threadIdx.x] = sink;
@@ -105,7 +105,7 @@ int main() {
     for (auto cf : cfgs)
         for (int red = 0; red < 2; ++red) {
             const int ldw = cf.K + 16, iters = 2000;
-            size_t smem = (size_t)(4096 + cf.R * ldw) * 4;
+            size_t smem = (size_t)(6144 + cf.R * ldw) * 4;
             cudaFuncSetAttribute(pass_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (cf.R <= 32) { cudaFuncSetAttribute(pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); }
             cudaEventRecord(e0);
