@@ -28,7 +28,7 @@
 
 namespace l2s {
 
-constexpr int D3_MAXRT = 8;           // 16-row tiles per CTA (instantiated: 2, 3, 4, 8)
+constexpr int D3_MAXRT = 8;           // 16-row tiles per CTA (instantiated: 2, 3, 4, 5, 6, 8)
 constexpr int D3_ROWS = 16 * D3_MAXRT;
 constexpr int D3_CG = 8;              // clips per group
 constexpr int D3_NG = 4;              // clip groups == pipeline stages
@@ -420,6 +420,8 @@ __global__ void __launch_bounds__(MV_THREADS, 1) decode3_kernel(const Decode3Par
     if (pass.RT <= 2) { if (early) d3_loop<2, true>(q, pass, sm, sync, role, job, kvbar); else d3_loop<2, false>(q, pass, sm, sync, role, job, kvbar); }
     else if (pass.RT == 3) { if (early) d3_loop<3, true>(q, pass, sm, sync, role, job, kvbar); else d3_loop<3, false>(q, pass, sm, sync, role, job, kvbar); }
     else if (pass.RT == 4) d3_loop<4, false>(q, pass, sm, sync, role, job, kvbar);
+    else if (pass.RT == 5) d3_loop<5, false>(q, pass, sm, sync, role, job, kvbar);
+    else if (pass.RT == 6) d3_loop<6, false>(q, pass, sm, sync, role, job, kvbar);
     else d3_loop<8, false>(q, pass, sm, sync, role, job, kvbar);
     __syncthreads();
     if (q.timing && tid < D3_TIMING_SLOTS) q.timing[blockIdx.x * D3_TIMING_SLOTS + tid] = tacc[tid];

@@ -284,12 +284,12 @@ struct StepRows {
 
 // Program for the stage-pipelined kernel (decode3.cuh): every CTA serves ONE stage with ONE pass.  LSTM-0: 8 units per
 // CTA (32 gate rows x 1536); LSTM-1: 12 units (48 x 1024); stage A: query rows (48 x 1024), content-query rows
-// (43 x 1024) and fc_out / fc_out∘prenet-1 / stop rows (57 x 512) on separate CTAs; stage B: 8 clips x nsplit attention
-// CTAs + prenet-2 rows (128 x 256).  Row widths are padded by 16 floats so the tensor-core fragment loads (LDS.128,
+// (43 x 1024) and fc_out / fc_out∘prenet-1 / stop rows (68 x 512) on separate CTAs; stage B: 8 clips x nsplit attention
+// CTAs + prenet-2 rows (86 x 256).  The split follows the measured per-turn critical path (tools/dec3_debug.py).  Row widths are padded by 16 floats so the tensor-core fragment loads (LDS.128,
 // rows g / g+8) are bank-conflict free.
 inline void pack_decode_program3(Context& c, const StepRows& w) {
     const int nC = c.num_sms;
-    const int nD = 64, nE = 43, nQ = 11, nCQ = 6, nF = 6, nP2 = 2, nsplit = D3_NSPLIT;
+    const int nD = 64, nE = 43, nQ = 11, nCQ = 6, nF = 5, nP2 = 3, nsplit = D3_NSPLIT;
     const int nAttn = D3_CG * nsplit;
     c.meta["d.step3.ok"] = 0;
     if (nD + nE + nQ + nCQ + nF + nP2 + nAttn > nC) return;    // not enough SMs: decode.cuh serves every batch size

@@ -43,7 +43,7 @@ for name, be in (("dec3", b3), ("dec2", b2)):
             t = be.debug_read("dec.timing3", (148, 6))
             role = ["B"] * 148
             # CTA order of pack_decode_program3
-            names = ["D"] * 64 + ["E"] * 43 + ["A.Q"] * 11 + ["A.CQ"] * 6 + ["A.F"] * 6 + ["Battn"] * 16 + ["Bp2"] * 2
+            names = ["D"] * 64 + ["E"] * 43 + ["A.Q"] * 11 + ["A.CQ"] * 6 + ["A.F"] * 5 + ["Battn"] * 16 + ["Bp2"] * 3
             for r in ("D", "E", "A.Q", "A.CQ", "A.F", "Battn", "Bp2"):
                 idx = [i for i, n in enumerate(names) if n == r]
                 tt = t[idx].mean(0) / 1.965e3 / 300      # us per step (4 turns)
