@@ -45,6 +45,33 @@ __global__ void __launch_bounds__(512, 1) mma_rate_distinct_kernel(float* out, i
     out[blockIdx.x * 512 + threadIdx.x] = s;
 }
 
+// mv8_mma without the hi/lo splits (same loads, same MMA count; operands used raw): isolates the cost of the split ALU work
+template <int RT>
+__device__ __forceinline__ void mv8_mma_nosplit(const float* __restrict__ W, int ldw, int R, int K, const float (&x)[MV8_DEPTH][4], float (&acc)[RT][4]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int npw = K / (MV_KC * MV_WARPS);
+#pragma unroll
+    for (int d = 0; d < MV8_DEPTH; ++d)
+        if (d < npw) {
+            uint32_t xh[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) xh[i] = __float_as_uint(x[d][i]);
+#pragma unroll
+            for (int rt = 0; rt < RT; ++rt) {
+                const float4 wa = *reinterpret_cast<const float4*>(W + (size_t)min(rt * 16 + g, R - 1) * ldw + (warp + d * MV_WARPS) * MV_KC + 4 * t);
+                const float4 wb = *reinterpret_cast<const float4*>(W + (size_t)min(rt * 16 + g + 8, R - 1) * ldw + (warp + d * MV_WARPS) * MV_KC + 4 * t);
+                const uint32_t ah[4] = {__float_as_uint(wa.x), __float_as_uint(wa.y), __float_as_uint(wa.z), __float_as_uint(wa.w)};
+                const uint32_t bh[4] = {__float_as_uint(wb.x), __float_as_uint(wb.y), __float_as_uint(wb.z), __float_as_uint(wb.w)};
+#pragma unroll
+                for (int s = 0; s < 2; ++s)
+#pragma unroll
+                    for (int rep = 0; rep < 3; ++rep)
+                        mma_tf32(acc[rt], ah[2 * s], bh[2 * s], ah[2 * s + 1], bh[2 * s + 1], xh[2 * s], xh[2 * s + 1]);
+            }
+        }
+}
+
 template <int MAXRT>
 __global__ void __launch_bounds__(512, 1) pass_kernel(const float* __restrict__ Wg, const float* __restrict__ X, float* __restrict__ out,
                                                        int R, int K, int ldw, int iters, int do_reduce) {
@@ -58,8 +85,9 @@ __global__ void __launch_bounds__(512, 1) pass_kernel(const float* __restrict__ 
         const float* x = X + (size_t)(it & 3) * K * 8;
         float acc[MAXRT][4];
         mv8_zero<MAXRT>(acc);
-        mv8_accumulate<MAXRT>(wsm, ldw, 0, R, x, K, acc);
-        if (do_reduce) { for (int rd = 0; rd < (MAXRT + 2) / 3; ++rd) { sink += mv8_reduce_round<MAXRT>(acc, rd, red); __syncthreads(); } }
+        if (do_reduce >= 2) { float xx[MV8_DEPTH][4]; mv8_load<MV8_DEPTH>(x, K, xx); mv8_mma_nosplit<MAXRT>(wsm, ldw, R, K, xx, acc); }   // mode 2: no splits, no reduce
+        else mv8_accumulate<MAXRT>(wsm, ldw, 0, R, x, K, acc);
+        if (do_reduce == 1) { for (int rd = 0; rd < (MAXRT + 2) / 3; ++rd) { sink += mv8_reduce_round<MAXRT>(acc, rd, red); __syncthreads(); } }
         else for (int r = 0; r < MAXRT; ++r) sink += acc[r][0] + acc[r][1] + acc[r][2] + acc[r][3];
     }
     out[(size_t)blockIdx.x * 512 + threadIdx.x] = sink;
@@ -103,7 +131,7 @@ int main() {
     cudaMemcpy(X, hX.data(), hX.size() * 4, cudaMemcpyHostToDevice);
     struct Cfg { int R, K; } cfgs[] = {{32, 1536}, {32, 1024}, {32, 512}, {48, 1024}, {48, 512}, {16, 512}, {16, 1024}, {24, 1024}, {48, 256}};
     for (auto cf : cfgs)
-        for (int red = 0; red < 2; ++red) {
+        for (int red = 0; red < 3; ++red) {
             const int ldw = cf.K + 16, iters = 2000;
             size_t smem = (size_t)(6144 + cf.R * ldw) * 4;
             cudaFuncSetAttribute(pass_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
