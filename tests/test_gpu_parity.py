@@ -255,6 +255,21 @@ def test_stop_token_midway(O, weights):
     b2.close()
 
 
+@pytest.mark.parametrize("B,T,steps", [(9, 31, 5), (9, 32, 5), (10, 7, 4), (32, 30, 3), (1, 29, 6)])
+def test_pipelined_kernel_shape_edges(be, O, weights, B, T, steps):
+    """Edges of the pipelined decode kernel: T = 31 is the largest encoder length whose K/V images fit twice in shared
+    memory (T = 32 streams them from L2), T = 7 the smallest the Content convolutions accept (minT = 1), a full batch at
+    an even T, and a single clip (one clip group, three SM groups idle every turn)."""
+    visual, face = synth.visual_features(B, T, seed=40 + T)
+    g = synth.gumbel(B, T, seed=40 + T)
+    mel, lengths, attn = be.decoder_infer(visual.cuda(), face[:, 0].cuda(), g.cuda(), steps=steps, return_attention=True)
+    assert be.debug_flag("dec3") == 1
+    ref_mel, ref_len, ref_attn = O.decoder_inference(weights, visual, face, g, steps=steps, return_attention=True)
+    assert torch.equal(lengths.cpu(), ref_len)
+    assert rel_err(mel.cpu(), ref_mel) < TOL
+    assert (attn.cpu() - ref_attn).abs().max() < 2e-2
+
+
 def test_module_mirror_matches_backend(be, weights, golden):
     """The nn.Module mirror (reference-shaped API) drives the same kernels."""
     from lip2speech_b200 import modules
