@@ -147,7 +147,7 @@ double l2s_span_ms(l2s_ctx* ctx, const char* name);
  * "dec.cval" [B,minT,256], "dec.outputs" [B,steps,80], "video.stem" [B*T,H/4,W/4,24].
  * Returns the number of floats available (copies min(n, available)), or -1 if unknown.
  * "flag.<name>" copies nothing and returns an integer fact about the last call: "flag.dec3" = 1 when the decode loop ran
- * on the stage-pipelined kernel (8 < B <= 32), 0 when it ran on the row-partitioned one. */
+ * on the stage-pipelined kernel (B <= 32), 0 when it ran on the row-partitioned one (B > 32). */
 int64_t l2s_debug_read(l2s_ctx* ctx, const char* name, float* out, int64_t n);
 
 #ifdef __cplusplus

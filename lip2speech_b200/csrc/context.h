@@ -50,7 +50,7 @@ struct Context {
     void* nccl_comm = nullptr; int world = 1, rank = 0;          // data-parallel gradient exchange (l2s_comm_init)
     int pw_min_rows = 16384;                  // streaming 1x1 kernel for GEMMs with at least this many rows (L2S_PW_MIN_ROWS)
     bool use_pw = true;                       // streaming mma.sync kernel for the trunk's 1x1 convolutions (L2S_PW=0: tcgen05 GEMM)
-    bool use_dec3 = true;                     // stage-pipelined decode kernel for 8 < B <= 32 (L2S_DEC3=0: row-partitioned kernel for every B)
+    bool use_dec3 = true;                     // stage-pipelined decode kernel for B <= 32 (L2S_DEC3=0: row-partitioned kernel for every B)
     bool use_tc = true;                       // tcgen05 GEMM path (L2S_TC=0 selects the exact-fp32 SIMT GEMMs for debugging)
     // optional stage timing (CUDA events on the caller's stream), enabled by l2s_set_profiling
     bool profiling = false;

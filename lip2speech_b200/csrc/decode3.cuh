@@ -1,4 +1,4 @@
-// Stage-pipelined persistent decode loop (8 < B <= 32): same arithmetic per clip as decode.cuh (reference
+// Stage-pipelined persistent decode loop (B <= 32; clip groups without clips are skipped): same arithmetic per clip as decode.cuh (reference
 // decoder.py:403-435, one step = SURVEY.md §3.4), different mapping onto the chip.
 //
 // Why: in decode.cuh every SM owns rows of EVERY layer, so every SM reads every activation of every clip from L2

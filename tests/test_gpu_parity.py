@@ -155,16 +155,16 @@ def test_batch_33_two_clip_groups_vs_oracle(be, O, weights):
 
 def test_batch_invariance_full_size(be):
     """Size-independent property at the bench size (B=32, 300 steps): a clip's mel does not depend on which other
-    clips share the batch.  Bit-exact between batches served by the same kernel (the stage-pipelined kernel for
-    8 < B <= 32: every clip is an independent MMA column); the row-partitioned kernel (B <= 8) and its single-clip lane
-    mapping (B <= 2) sum in a different order, so there the bound is the parity tolerance."""
+    clips share the batch.  The stage-pipelined kernel serves every B <= 32 and every clip is an independent MMA column, so
+    sub-batches of any size — aligned to its 8-clip groups or not, down to a single clip — must agree (bit-exact for the
+    group-sized ones; the parity tolerance is asserted for the 4-clip and single-clip cases)."""
     visual, face = synth.visual_features(32, 29, seed=5)
     g = synth.gumbel(32, 29, seed=5)
     mel, lengths = be.decoder_infer(visual.cuda(), face[:, 0].cuda(), g.cuda())
     for lo, n in ((0, 12), (7, 9), (15, 17)):            # sub-batches served by the pipelined kernel, unaligned to clip groups
         m, l = be.decoder_infer(visual[lo:lo + n].cuda(), face[lo:lo + n, 0].cuda(), g[4 * lo:4 * (lo + n)].cuda())
         assert torch.equal(m, mel[lo:lo + n]) and torch.equal(l, lengths[lo:lo + n])
-    for lo in (0, 28):                                   # 4-clip sub-batches (row-partitioned kernel)
+    for lo in (0, 28):                                   # 4-clip sub-batches (one partial clip group)
         m4, l4 = be.decoder_infer(visual[lo:lo + 4].cuda(), face[lo:lo + 4, 0].cuda(), g[4 * lo:4 * lo + 16].cuda())
         assert rel_err(m4.cpu(), mel[lo:lo + 4].cpu()) < TOL and torch.equal(l4, lengths[lo:lo + 4])
     for i in (0, 17, 31):                                # single clips
@@ -173,7 +173,7 @@ def test_batch_invariance_full_size(be):
 
 
 def test_pipelined_kernel_vs_oracle(be, O, weights):
-    """8 < B <= 32 runs the stage-pipelined kernel (decode3.cuh): partial clip groups (B=11), attention maps, and the
+    """B <= 32 runs the stage-pipelined kernel (decode3.cuh): partial clip groups (B=11), attention maps, and the
     Decoder.forward flavour (teacher-forced steps, raw stop logits, pre-softmax attention logits) against the oracle."""
     visual, face = synth.visual_features(11, 29, seed=31)
     g = synth.gumbel(11, 29, seed=31)
