@@ -107,6 +107,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Stem mode: a 128-row tile whose first and last rows both lie in temporal padding planes (tp < 2 or tp >= T + 2) holds
+// no valid output row (a tile spans at most two planes) and is skipped by every warp role alike.
+__device__ __forceinline__ bool tc_stem_pad_tile(const TcParams& p, int m0) {
+    if (!p.stem) return false;
+    const int plane = p.sHp * p.sWp;
+    const int t0 = (m0 / plane) % p.sTp;
+    const int m1 = min(m0 + TC_BM - 1, p.M - 1);
+    const int t1 = (m1 / plane) % p.sTp;
+    const bool pad0 = t0 < 2 || t0 >= p.sT + 2, pad1 = t1 < 2 || t1 >= p.sT + 2;
+    return pad0 && pad1;
+}
+
 template <int BN>
 struct TcSmem {
     static constexpr int STAGES = (BN >= 128) ? 3 : 4;
@@ -176,6 +188,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             int git = 0;                                    // global stage counter across tiles
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int m0 = (tile / ntn) * TC_BM, n0 = (tile % ntn) * BN;
+                if (tc_stem_pad_tile(p, m0)) continue;
                 for (int it = 0; it < niter; ++it, ++git) {
                     const int s = git % STAGES, ph = (git / STAGES) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
@@ -213,7 +226,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             }
             int git = 0, lt = 0;                            // lt = local tile counter (accumulator buffer = lt & 1)
             int s = 0, ph = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                if (tc_stem_pad_tile(p, (tile / ntn) * TC_BM)) continue;
                 const int buf = lt & 1, bph = (lt >> 1) & 1;
                 mbar_wait(&tempty[buf], bph ^ 1);           // epilogue has drained this accumulator (two tiles ago)
                 tc_fence_after();
@@ -250,6 +264,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
                 umma_commit(&tfull[buf]);
+                ++lt;
             }
         }
     } else if (warp < 2 + TC_WORKERS / 32) {
@@ -264,6 +279,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const char* src0 = reinterpret_cast<const char*>(p.ga_A);
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int m0 = (tile / ntn) * TC_BM;
+                if (tc_stem_pad_tile(p, m0)) continue;
                 const char* base = src0 + ((long long)m0 + r0) * 32 + c * 16;
                 for (int tap = 0; tap < niter; ++tap, ++git) {
                     const int s = git % STAGES, ph = (git / STAGES) & 1;
@@ -282,6 +298,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const uint32_t off0 = (uint32_t)(r0 * 128 + ((c ^ (r0 & 7)) << 4));     // (r0 + 32 i) & 7 == r0 & 7
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int m0 = (tile / ntn) * TC_BM;
+                if (tc_stem_pad_tile(p, m0)) continue;
                 const float* base_hi = p.ga_A + ((long long)m0 + r0) * p.ga_lda + c * 4;
                 const float* base_lo = p.ga_Alo + ((long long)m0 + r0) * p.ga_lda + c * 4;
                 int it = 0;
@@ -306,6 +323,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             }
         } else {
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                if (tc_stem_pad_tile(p, (tile / ntn) * TC_BM)) continue;
                 for (int it = 0; it < niter; ++it, ++git) {
                     const int s = git % STAGES, ph = (git / STAGES) & 1;
                     mbar_wait(&full[s], ph);
@@ -338,9 +356,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         float* ep = ep_s[e];
         int4* rinfo = rinfo_s[e];
         int lt = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int m0 = (tile / ntn) * TC_BM, n0 = (tile % ntn) * BN;
+            if (tc_stem_pad_tile(p, m0)) continue;
             const int buf = lt & 1, bph = (lt >> 1) & 1;
+            ++lt;
             mbar_wait(&tfull[buf], bph);
             tc_fence_after();
             if (p.debug_skip & 1) { tc_fence_before(); mbar_arrive(&tempty[buf]); continue; }
