@@ -154,6 +154,23 @@ __global__ void __launch_bounds__(PW_THREADS, 2) pw_mma_kernel(const PwParams p)
             }
             continue;
         }
+        if (p.cstride == 1 && !((p.coff | p.ldc | p.chalf | p.chp | p.N) & 1)) {
+            // contiguous channels: the two columns a lane owns are neighbours in memory -> one 8-byte store per row
+#pragma unroll
+            for (int nt = 0; nt < PW_NT; ++nt) {
+                const int n = n_base + nt * 8 + 2 * t;
+                if (n < p.N) {
+                    const float b0 = p.bias ? __ldg(p.bias + n) : 0.f, b1 = p.bias ? __ldg(p.bias + n + 1) : 0.f;
+                    int l = n + p.coff;
+                    if (p.chalf > 0 && l >= p.chalf) l = l - p.chalf + p.chp;
+                    float y00 = acc[nt][0] + b0, y01 = acc[nt][1] + b1, y10 = acc[nt][2] + b0, y11 = acc[nt][3] + b1;
+                    if (p.relu) { y00 = fmaxf(y00, 0.f); y01 = fmaxf(y01, 0.f); y10 = fmaxf(y10, 0.f); y11 = fmaxf(y11, 0.f); }
+                    if (v0) *reinterpret_cast<float2*>(p.C + (size_t)r0 * p.ldc + l) = make_float2(y00, y01);
+                    if (v1) *reinterpret_cast<float2*>(p.C + (size_t)r1 * p.ldc + l) = make_float2(y10, y11);
+                }
+            }
+            continue;
+        }
 #pragma unroll
         for (int nt = 0; nt < PW_NT; ++nt) {
 #pragma unroll
