@@ -27,7 +27,7 @@ def test_algorithmic_decode_bytes_match_survey():
 
 
 def test_committed_bench_line_has_contract_keys():
-    line = json.loads(open(os.path.join(ROOT, "profiles", "r1f_bench_line.json")).read().strip().splitlines()[-1])
+    line = json.loads(open(os.path.join(ROOT, "profiles", "r1g_bench_line.json")).read().strip().splitlines()[-1])
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
               "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
         assert k in line, k
