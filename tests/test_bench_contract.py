@@ -36,3 +36,16 @@ def test_committed_bench_line_has_contract_keys():
     assert {"value", "unit", "cores", "kind", "sample"} <= set(line["cpu_baseline"])
     assert line["gpu_launches"] > 0 and "workload" in line["config"] and "model" not in line["config"]
     assert abs(line["roofline"]["frac"] - line["roofline"]["achieved"] / line["roofline"]["peak"]) < 1e-9
+
+
+def test_reference_arm_runs_on_cpu():
+    """`bench.py --impl reference` (the CPU port of the reference's path, timed on host cores) needs no GPU and prints the
+    contract's JSON line with impl / cpu_baseline / zero-copy e2e."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--batch", "2"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-1000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "mel-frames/s" and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert line["value"] > 0
