@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE ONLY — CPU restatement of the reference's train-step tail, used as the checker for
 csrc/train_step.cuh.  Only tests/ may import this.
 
-* `loss_forward` restates train_utils/losses.py:35-79 (Loss.forward) in plain torch.
+* `loss_forward` restates train_utils/losses.py:35-79 (Loss.forward) in plain torch; pinned bit for bit (values and
+  gradients) against the unmodified reference module by tests/test_train_oracle_vs_reference.py where /root/reference exists.
 * `clip_adamw_steps` runs the reference's own calls — torch.nn.utils.clip_grad_norm_ (train.py:191) and
   torch.optim.AdamW(lr, weight_decay, amsgrad=True) (train.py:102-104,193) — on CPU copies; torch is the third-party
   arithmetic the reference pins (requirements.txt:10), so parity is against torch 2.11 CPU fp32 semantics
