@@ -103,6 +103,20 @@ int l2s_infer_host_submit(l2s_ctx* ctx, int slot, const float* video, const floa
                           int H, int W, int S, int steps, float* mel_post, int64_t* lengths, int precision);
 int l2s_infer_host_wait(l2s_ctx* ctx, int slot);
 
+/* ---- raw-frame input (the step before the path: datasets/lrw/dataset.py:20-24 loadframes -> 82-86 face_resize) ----------------
+ * `frames` is uint8 [B,T,H,W,3] RGB, exactly what loadframes() returns per clip; the dataset's `im.float() / 255.0` followed by
+ * Normalize(mean, std) is applied on the device while the stem's input rows are written (same fp32 arithmetic, IEEE division:
+ * results are bit-identical to feeding the normalised fp32 tensor).  mean_std: HOST pointer to {mean[3], std[3]}
+ * (LRW: 0.485,0.456,0.406 / 0.229,0.224,0.225).  A quarter of the bytes cross PCIe; the fp32 NCDHW tensor never exists. */
+int l2s_video_fwd_u8(l2s_ctx* ctx, const unsigned char* frames, const float* mean_std, int B, int T, int H, int W, float* out_feat,
+                     int precision, void* stream);
+int l2s_infer_u8(l2s_ctx* ctx, const unsigned char* frames, const float* mean_std, const float* wav, const float* gumbel, int B, int T,
+                 int H, int W, int S, int steps, float* mel_post, int64_t* lengths, int precision, void* stream);
+/* Host-buffer form (frames, wav, gumbel, mel_post, lengths on the host); pairs with l2s_infer_host_wait. */
+int l2s_infer_host_submit_u8(l2s_ctx* ctx, int slot, const unsigned char* frames, const float* mean_std, const float* wav,
+                             const float* gumbel, int B, int T, int H, int W, int S, int steps, float* mel_post, int64_t* lengths,
+                             int precision);
+
 /* ---- train-step tail (train.py:167-193) ---------------------------------------------------------------------------
  * The forward-train / backward kernels of the model are not part of this library yet; these entry points cover the loss,
  * the data-parallel gradient exchange (the only collective of the path) and the optimizer step on FLAT fp32 buffers. */

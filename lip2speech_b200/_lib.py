@@ -15,9 +15,11 @@ LIB_PATH = os.path.join(_HERE, "lib", "libl2s_b200.so")
 
 PART_VIDEO, PART_SPEAKER, PART_DECODER = 1, 2, 4
 PRECISION_FP32, PRECISION_BF16 = 0, 1
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)      # datasets/lrw/dataset.py:84-85
 
 EXPORTS = ("l2s_version", "l2s_create", "l2s_destroy", "l2s_last_error", "l2s_bind_weight", "l2s_commit_weights",
            "l2s_video_fwd", "l2s_speaker_fwd", "l2s_decoder_infer", "l2s_decoder_forward", "l2s_postnet_fwd", "l2s_infer", "l2s_infer_host", "l2s_infer_host_submit", "l2s_infer_host_wait",
+           "l2s_video_fwd_u8", "l2s_infer_u8", "l2s_infer_host_submit_u8",
            "l2s_launch_count", "l2s_debug_read", "l2s_set_profiling", "l2s_span_ms",
            "l2s_loss_fwd_bwd", "l2s_nccl_unique_id", "l2s_comm_init", "l2s_comm_destroy", "l2s_allreduce_grads", "l2s_clip_adamw_step")
 NCCL_UNIQUE_ID_BYTES = 128
@@ -52,6 +54,9 @@ def load() -> C.CDLL:
         lib.l2s_infer_host.argtypes = [vp, fp, fp, fp, i, i, i, i, i, i, fp, vp, i]
         lib.l2s_infer_host_submit.argtypes = [vp, i, fp, fp, fp, i, i, i, i, i, i, fp, vp, i]
         lib.l2s_infer_host_wait.argtypes = [vp, i]
+        lib.l2s_video_fwd_u8.argtypes = [vp, vp, vp, i, i, i, i, fp, i, vp]
+        lib.l2s_infer_u8.argtypes = [vp, vp, vp, fp, fp, i, i, i, i, i, i, fp, vp, i, vp]
+        lib.l2s_infer_host_submit_u8.argtypes = [vp, i, vp, vp, fp, fp, i, i, i, i, i, i, fp, vp, i]
         lib.l2s_launch_count.argtypes = [vp]; lib.l2s_launch_count.restype = C.c_int64
         lib.l2s_set_profiling.argtypes = [vp, i]
         lib.l2s_span_ms.argtypes = [vp, C.c_char_p]; lib.l2s_span_ms.restype = C.c_double
@@ -87,6 +92,8 @@ class Backend:
             raise RuntimeError("l2s_create failed: " + self.lib.l2s_last_error(None).decode())
         self.h = h
         self._sig = {}
+        self._generation = 0
+        self.world = 1          # data-parallel size of the library's communicator (comm_init)
 
     def close(self):
         if getattr(self, "h", None):
@@ -125,12 +132,18 @@ class Backend:
         self._check(self.lib.l2s_commit_weights(self.h, part), "l2s_commit_weights")
 
     def sync_module(self, module: torch.nn.Module, prefix: str, part: int):
-        """(Re)bind when any parameter/buffer changed (data_ptr or in-place version counter)."""
+        """(Re)bind when any parameter/buffer changed: data_ptr, in-place version counter, or an explicit
+        invalidate_weights() (raw-pointer writers such as ClipAdamW.step() change neither of the first two)."""
         sd = module.state_dict(keep_vars=True)
-        sig = tuple((k, t.data_ptr(), t._version) for k, t in sd.items())
+        sig = (self._generation,) + tuple((k, t.data_ptr(), t._version) for k, t in sd.items())
         if self._sig.get(prefix) != sig:
             self.bind_state_dict(sd, prefix, part)
             self._sig[prefix] = sig
+
+    def invalidate_weights(self):
+        """Parameters were modified behind autograd's back (a kernel wrote through raw pointers, or `p.data` was edited):
+        the next forward re-binds and re-packs them."""
+        self._generation += 1
 
     # ---- forward calls ---------------------------------------------------------------------------
     def video_fwd(self, video: torch.Tensor, precision: int = PRECISION_FP32) -> torch.Tensor:
@@ -214,6 +227,43 @@ class Backend:
         self._check(self.lib.l2s_infer_host_submit(self.h, slot, video.data_ptr(), wav.data_ptr(), gumbel.data_ptr(), B, T, H, W, wav.shape[1],
                                                    steps, mel_out.data_ptr(), C.c_void_p(lengths_out.data_ptr()), precision), "l2s_infer_host_submit")
 
+    # ---- raw uint8 frames [B,T,H,W,3] RGB (datasets/lrw/dataset.py:20-24); /255 + Normalize fused on the device -------------
+    @staticmethod
+    def _mean_std(mean, std):
+        return (C.c_float * 6)(*[float(x) for x in tuple(mean) + tuple(std)])
+
+    def video_fwd_u8(self, frames: torch.Tensor, precision: int = PRECISION_FP32, mean=IMAGENET_MEAN, std=IMAGENET_STD) -> torch.Tensor:
+        assert frames.dtype == torch.uint8 and frames.dim() == 5 and frames.shape[-1] == 3
+        frames = frames.to(self.device).contiguous()
+        B, T, H, W, _ = frames.shape
+        out = torch.empty(B, T, 768, device=self.device, dtype=torch.float32)
+        self._check(self.lib.l2s_video_fwd_u8(self.h, C.c_void_p(frames.data_ptr()), self._mean_std(mean, std), B, T, H, W, out.data_ptr(),
+                                              precision, self._stream()), "l2s_video_fwd_u8")
+        return out
+
+    def infer_u8(self, frames, wav, gumbel, steps: int = 300, precision: int = PRECISION_FP32, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+        assert frames.dtype == torch.uint8 and frames.dim() == 5 and frames.shape[-1] == 3
+        frames = frames.to(self.device).contiguous()
+        wav, gumbel = _f32c(wav, self.device), _f32c(gumbel, self.device)
+        B, T, H, W, _ = frames.shape
+        mel = torch.empty(B, 80, steps, device=self.device, dtype=torch.float32)
+        lengths = torch.empty(B, device=self.device, dtype=torch.int64)
+        self._check(self.lib.l2s_infer_u8(self.h, C.c_void_p(frames.data_ptr()), self._mean_std(mean, std), wav.data_ptr(), gumbel.data_ptr(),
+                                          B, T, H, W, wav.shape[1], steps, mel.data_ptr(), C.c_void_p(lengths.data_ptr()), precision,
+                                          self._stream()), "l2s_infer_u8")
+        return mel, lengths
+
+    def infer_host_submit_u8(self, slot, frames, wav, gumbel, mel_out, lengths_out, steps: int = 300, precision: int = PRECISION_FP32,
+                             mean=IMAGENET_MEAN, std=IMAGENET_STD):
+        """Host uint8 frames [B,T,H,W,3] (ideally pinned) + host fp32 wav / gumbel; pairs with infer_host_wait(slot)."""
+        B, T, H, W, _ = frames.shape
+        assert frames.device.type == "cpu" and frames.dtype == torch.uint8 and frames.is_contiguous()
+        for t in (wav, gumbel, mel_out):
+            assert t.device.type == "cpu" and t.dtype == torch.float32 and t.is_contiguous()
+        self._check(self.lib.l2s_infer_host_submit_u8(self.h, slot, C.c_void_p(frames.data_ptr()), self._mean_std(mean, std), wav.data_ptr(),
+                                                      gumbel.data_ptr(), B, T, H, W, wav.shape[1], steps, mel_out.data_ptr(),
+                                                      C.c_void_p(lengths_out.data_ptr()), precision), "l2s_infer_host_submit_u8")
+
     def infer_host_wait(self, slot):
         self._check(self.lib.l2s_infer_host_wait(self.h, slot), "l2s_infer_host_wait")
 
@@ -237,9 +287,11 @@ class Backend:
     def comm_init(self, unique_id: bytes, rank: int, world: int):
         buf = C.create_string_buffer(bytes(unique_id), NCCL_UNIQUE_ID_BYTES)
         self._check(self.lib.l2s_comm_init(self.h, buf, NCCL_UNIQUE_ID_BYTES, rank, world), "l2s_comm_init")
+        self.world = world
 
     def comm_destroy(self):
         self._check(self.lib.l2s_comm_destroy(self.h), "l2s_comm_destroy")
+        self.world = 1
 
     def allreduce_grads(self, flat_grads: torch.Tensor, scale: float, sqnorm_out: torch.Tensor):
         assert flat_grads.is_cuda and flat_grads.dtype == torch.float32 and flat_grads.is_contiguous()

@@ -137,8 +137,48 @@ static void gemm_auto(Context& c, GemmParams g, const std::string& wname, cudaSt
     run_gemm(c, g, s, what);
 }
 
-// video [B,3,T,H,W] NCDHW -> space-to-depth, zero-padded rows [B][T+4][H/2+3][W/2+3][12]; channel = (ph*2+pw)*3 + ci.
-__global__ void s2d_pad_kernel(const float* __restrict__ v, float* __restrict__ xs, float* __restrict__ xl, int B, int T, int H, int W, int Tp, int Hpp, int Wpp) {
+// Where the clips come from.  kind 0: the caller's [B,3,T,H,W] fp32 NCDHW tensor, already normalised (what
+// train_collate_fn_pad hands to the model, datasets/__init__.py:7-46).  kind 1: raw decoded frames uint8 [B,T,H,W,3] RGB (what
+// loadframes returns, datasets/lrw/dataset.py:20-24); the dataset's `im.float() / 255.0` + Normalize(mean, std)
+// (datasets/lrw/dataset.py:82-86) is applied while the space-to-depth rows are written, so a quarter of the bytes cross PCIe
+// and HBM and the fp32 NCDHW tensor never exists.
+struct VideoSrc {
+    const void* p = nullptr;
+    int kind = 0;
+    float mean[3] = {0.f, 0.f, 0.f}, stdv[3] = {1.f, 1.f, 1.f};
+};
+
+// The 12 space-to-depth values of output position (b, t, hq, wq): index = (ph*2 + pw)*3 + ci.
+__device__ __forceinline__ void s2d_fetch(const VideoSrc& v, int b, int t, int hq, int wq, int T, int H, int W, float (&vals)[12]) {
+    if (v.kind == 0) {
+        const float* base = static_cast<const float*>(v.p);
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+            const float* src = base + ((((size_t)b * 3 + ci) * T + t) * H + 2 * hq) * W + 2 * wq;
+            const float2 top = *reinterpret_cast<const float2*>(src);
+            const float2 bot = *reinterpret_cast<const float2*>(src + W);
+            vals[0 + ci] = top.x; vals[3 + ci] = top.y; vals[6 + ci] = bot.x; vals[9 + ci] = bot.y;
+        }
+    } else {
+        // two pixels x RGB = 6 contiguous bytes per row (offset 6*wq: 2-byte aligned)
+        const unsigned char* base = static_cast<const unsigned char*>(v.p) + ((((size_t)b * T + t) * H + 2 * hq) * W + 2 * wq) * 3;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const unsigned short* row = reinterpret_cast<const unsigned short*>(base + (size_t)r * W * 3);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const unsigned short u = __ldg(row + j);
+                const int i0 = 6 * r + 2 * j, i1 = i0 + 1;
+                // exactly the dataset's arithmetic: (u / 255.0 - mean) / std in fp32, IEEE division
+                vals[i0] = __fdiv_rn(__fdiv_rn((float)(u & 0xff), 255.0f) - v.mean[i0 % 3], v.stdv[i0 % 3]);
+                vals[i1] = __fdiv_rn(__fdiv_rn((float)(u >> 8), 255.0f) - v.mean[i1 % 3], v.stdv[i1 % 3]);
+            }
+        }
+    }
+}
+
+// clips -> space-to-depth, zero-padded rows [B][T+4][H/2+3][W/2+3][12]; channel = (ph*2+pw)*3 + ci.
+__global__ void s2d_pad_kernel(const VideoSrc v, float* __restrict__ xs, float* __restrict__ xl, int B, int T, int H, int W, int Tp, int Hpp, int Wpp) {
     const int Ho = H / 2, Wo = W / 2;
     const size_t total = (size_t)B * T * Ho * Wo;           // one thread per space-to-depth position: 12 contiguous outputs
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -146,13 +186,7 @@ __global__ void s2d_pad_kernel(const float* __restrict__ v, float* __restrict__ 
         int hq = r % Ho; r /= Ho;
         int t = r % T; int b = r / T;
         float vals[12];
-#pragma unroll
-        for (int ci = 0; ci < 3; ++ci) {
-            const float* src = v + ((((size_t)b * 3 + ci) * T + t) * H + 2 * hq) * W + 2 * wq;
-            const float2 top = *reinterpret_cast<const float2*>(src);
-            const float2 bot = *reinterpret_cast<const float2*>(src + W);
-            vals[0 + ci] = top.x; vals[3 + ci] = top.y; vals[6 + ci] = bot.x; vals[9 + ci] = bot.y;
-        }
+        s2d_fetch(v, b, t, hq, wq, T, H, W, vals);
         const size_t o = ((((size_t)b * Tp + t + 2) * Hpp + hq + 2) * Wpp + wq + 2) * 12;
         float hi[12], lo[12];
 #pragma unroll
@@ -169,7 +203,7 @@ __global__ void s2d_pad_kernel(const float* __restrict__ v, float* __restrict__ 
 }
 
 // bf16 flavour: rows of 16 bf16 per position (12 channels + 4 zeros), so a tap window (4 positions) is 128 contiguous bytes.
-__global__ void s2d_pad_bf16_kernel(const float* __restrict__ v, uint4* __restrict__ xs, int B, int T, int H, int W, int Tp, int Hpp, int Wpp) {
+__global__ void s2d_pad_bf16_kernel(const VideoSrc v, uint4* __restrict__ xs, int B, int T, int H, int W, int Tp, int Hpp, int Wpp) {
     const int Ho = H / 2, Wo = W / 2;
     const size_t total = (size_t)B * T * Ho * Wo;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -177,13 +211,7 @@ __global__ void s2d_pad_bf16_kernel(const float* __restrict__ v, uint4* __restri
         int hq = r % Ho; r /= Ho;
         int t = r % T; int b = r / T;
         float vals[12];
-#pragma unroll
-        for (int ci = 0; ci < 3; ++ci) {
-            const float* src = v + ((((size_t)b * 3 + ci) * T + t) * H + 2 * hq) * W + 2 * wq;
-            const float2 top = *reinterpret_cast<const float2*>(src);
-            const float2 bot = *reinterpret_cast<const float2*>(src + W);
-            vals[0 + ci] = top.x; vals[3 + ci] = top.y; vals[6 + ci] = bot.x; vals[9 + ci] = bot.y;
-        }
+        s2d_fetch(v, b, t, hq, wq, T, H, W, vals);
         uint32_t pk[8];
 #pragma unroll
         for (int j = 0; j < 6; ++j)
@@ -198,7 +226,7 @@ __global__ void s2d_pad_bf16_kernel(const float* __restrict__ v, uint4* __restri
 // ------------------------------------------------------------------------------------------------
 // video frontend
 // ------------------------------------------------------------------------------------------------
-static void video_forward(Context& c, const float* video, int B, int T, int H, int W, float* out_feat, int precision, cudaStream_t s) {
+static void video_forward_chunk(Context& c, const VideoSrc& video, int B, int T, int H, int W, float* out_feat, int precision, cudaStream_t s) {
     if (B <= 0 || T <= 0 || (H & 3) || (W & 3)) throw L2sError(L2S_ERR_INVALID, "video_fwd: bad shape");
     if (precision != L2S_PRECISION_FP32 && precision != L2S_PRECISION_BF16) throw L2sError(L2S_ERR_INVALID, "video_fwd: unknown precision");
     if (precision == L2S_PRECISION_BF16 && !c.use_tc) throw L2sError(L2S_ERR_INVALID, "video_fwd: the bf16 stem needs the tcgen05 path (L2S_TC=0 is set)");
@@ -263,7 +291,8 @@ static void video_forward(Context& c, const float* video, int B, int T, int H, i
         run_tc(c, o, p, s, "stem conv3d", /*gather=*/true);
     } else {
         GemmParams p = gemm_defaults();
-        p.stem = 1; p.A = video; p.W = c.dev("v.stem.w"); p.C = stem; p.ldc = 24;
+        if (video.kind != 0) throw L2sError(L2S_ERR_INVALID, "video_fwd: uint8 frames need the tcgen05 path");
+        p.stem = 1; p.A = static_cast<const float*>(video.p); p.W = c.dev("v.stem.w"); p.C = stem; p.ldc = 24;
         p.M = N * Ho * Wo; p.N = 24; p.Kc = 735; p.taps = 1; p.L_out = p.M; p.L_in = p.M;
         p.bias = c.dev("v.stem.b"); p.act = ACT_PRELU; p.act_w = c.dev("v.stem.prelu");
         p.T = T; p.H = H; p.Wd = W; p.Ho = Ho; p.Wo = Wo;
@@ -343,6 +372,26 @@ static void video_forward(Context& c, const float* video, int B, int T, int H, i
     linear(c, x, Kl, "v.last", c.dev("v.last.b"), last, Nl, N * 9, Nl, Kl, ACT_RELU, nullptr, s, "conv_last");
     avgpool_l2norm_kernel<<<N, 256, Nl * sizeof(float), s>>>(last, out_feat, 9, Nl);
     check_launch(c, "avgpool_l2norm");
+}
+
+// Whole-batch entry: clips are independent in the frontend (eval BatchNorm), so large batches run in chunks of 32 clips —
+// workspaces stay bounded (the unfused stem output is 16.6 MB per T=75 clip) and row counts stay far from 2^31.
+constexpr int VIDEO_CHUNK = 32;
+static void video_forward(Context& c, const VideoSrc& video, int B, int T, int H, int W, float* out_feat, int precision, cudaStream_t s) {
+    if (B <= 0) throw L2sError(L2S_ERR_INVALID, "video_fwd: bad shape");
+    const size_t clip_elems = (size_t)3 * T * H * W;
+    for (int b0 = 0; b0 < B; b0 += VIDEO_CHUNK) {
+        VideoSrc v = video;
+        v.p = video.kind == 0 ? static_cast<const void*>(static_cast<const float*>(video.p) + (size_t)b0 * clip_elems)
+                              : static_cast<const void*>(static_cast<const unsigned char*>(video.p) + (size_t)b0 * clip_elems);
+        video_forward_chunk(c, v, std::min(VIDEO_CHUNK, B - b0), T, H, W, out_feat + (size_t)b0 * T * 768, precision, s);
+    }
+}
+static inline VideoSrc video_f32(const float* p) { VideoSrc v; v.p = p; v.kind = 0; return v; }
+static inline VideoSrc video_u8(const unsigned char* p, const float* mean_std) {
+    VideoSrc v; v.p = p; v.kind = 1;
+    for (int i = 0; i < 3; ++i) { v.mean[i] = mean_std[i]; v.stdv[i] = mean_std[3 + i]; }
+    return v;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -723,47 +772,73 @@ static void decoder_run(Context& c, const float* visual, const float* spk, const
         dp.barrier = bar;
         dp.timing = c.profiling ? c.fbuf("ws.d.timing", (size_t)c.num_sms * DEC_TIMING_SLOTS) : nullptr;
         c.span_end("preloop", s);
-        // B <= 32: stage-pipelined kernel (decode3.cuh) — also for a single clip: a step is four dependent turns whatever
-        // the batch, and a turn of this kernel is shorter than a stage of the row-partitioned one (decode.cuh, B > 32)
-        const bool pipelined = c.use_dec3 && B <= D3_CG * D3_NG && c.meta.at("d.step3.ok") == 1;
+        // The stage-pipelined kernel (decode3.cuh) decodes up to D3_CG * D3_NG = 32 clips per launch; larger batches are decoded
+        // in consecutive 32-clip chunks (pre-loop and postnet stay whole-batch GEMMs).  Each chunk sees its own clips
+        // through shifted pointers; the feature-/group-major planes keep the whole batch's stride (Bpad).
+        if (c.meta.at("d.step3.ok") != 1) throw L2sError(L2S_ERR_INVALID, "decoder: the stage-pipelined decode kernel needs >= 148 SMs");
+#ifdef L2S_DEBUG
+        const bool pipelined = c.use_dec3;
+#else
+        const bool pipelined = true;
+#endif
         c.meta["dbg.dec3"] = pipelined ? 1 : 0;
         if (pipelined) {
-            Decode3Params q{};
             dp.nsplit = D3_NSPLIT;
             // group-major recurrent state for the 8-clip tensor-core passes (same sizes as the feature-major buffers)
             float* S3 = c.fbuf("ws.d.S3", 2 * 2 * plane);
             fm_to_group_major_kernel<<<ew_grid(2 * plane), 256, 0, s>>>(S, S3, 1024, Bpad);
             check_launch(c, "state -> group-major");
-            dp.S = S3;
-            q.d = dp;
             float* vsplit = c.fbuf("ws.d.Vsplit", (size_t)B * T * 512);
             float* cvsplit = c.fbuf("ws.d.cvsplit", (size_t)B * minT * 256);
             split_halves_kernel<<<ew_grid((size_t)B * T * 512), 256, 0, s>>>(Vmem, vsplit, B, T, 256);
             check_launch(c, "V halves");
             split_halves_kernel<<<ew_grid((size_t)B * minT * 256), 256, 0, s>>>(cval, cvsplit, B, minT, 128);
             check_launch(c, "content value halves");
-            q.Vsplit = vsplit; q.cvsplit = cvsplit;
-            q.kv_smem = (size_t)(512 + 320 + 256 + 32) + (size_t)2 * (T * 768 + minT * 384) <= (size_t)c.meta.at("d.step3.wimg_floats") ? 1 : 0;
-            q.passes = reinterpret_cast<const Dec3Pass*>(c.dev("d.step3.passes"));
-            q.role = reinterpret_cast<const int*>(c.dev("d.step3.role"));
-            q.job = reinterpret_cast<const int*>(c.dev("d.step3.job"));
-            q.wimg = c.dev("d.step3.wimg"); q.wimg_floats = (int)c.meta.at("d.step3.wimg_floats");
-            q.timing = c.profiling ? c.fbuf("ws.d.timing3", (size_t)c.num_sms * D3_TIMING_SLOTS) : nullptr;
             const size_t smem = (size_t)c.meta.at("d.step3.smem");
             L2S_CUDA(cudaFuncSetAttribute(decode3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            void* args[] = {&q};
+            const int chunk = D3_CG * D3_NG;
             c.span_begin("decode_loop", s);
-            L2S_CUDA(cudaLaunchCooperativeKernel((void*)decode3_kernel, dim3(c.num_sms), dim3(MV_THREADS), args, smem, s));
+            for (int b0 = 0; b0 < B; b0 += chunk) {
+                const int g0 = b0 / D3_CG;
+                Decode3Params q{};
+                q.d = dp;
+                q.d.B = std::min(chunk, B - b0);
+                q.d.S = S3 + (size_t)g0 * 1024 * D3_CG; q.d.Cst = dp.Cst + (size_t)g0 * 1024 * D3_CG;
+                q.d.P1 = dp.P1 + (size_t)g0 * 256 * D3_CG; q.d.XD = dp.XD + (size_t)g0 * 1024 * D3_CG;
+                q.d.Q = dp.Q + (size_t)b0 * 512; q.d.CQ = dp.CQ + (size_t)b0 * 256;
+                q.d.Kmem = Kmem + (size_t)b0 * T * 512; q.d.Vmem = Vmem + (size_t)b0 * T * 512;
+                q.d.ckey = ckey + (size_t)b0 * minT * 256; q.d.cval = cval + (size_t)b0 * minT * 256;
+                q.d.stop_const = stopc + b0;
+                q.d.outputs = outputs + (size_t)b0 * steps * 80; q.d.lengths = dp.lengths + b0;
+                if (attn) q.d.attn = attn + (size_t)b0 * steps * T;
+                if (dp.p1_teacher) q.d.p1_teacher = dp.p1_teacher + b0;
+                if (dp.stop_out) q.d.stop_out = dp.stop_out + (size_t)b0 * steps;
+                if (dp.attn_logits) q.d.attn_logits = dp.attn_logits + (size_t)b0 * steps * T;
+                if (b0) L2S_CUDA(cudaMemsetAsync(bar, 0, 4, s));
+                q.Vsplit = vsplit + (size_t)b0 * T * 512; q.cvsplit = cvsplit + (size_t)b0 * minT * 256;
+                q.kv_smem = (size_t)(512 + 320 + 256 + 32) + (size_t)2 * (T * 768 + minT * 384) <= (size_t)c.meta.at("d.step3.wimg_floats") ? 1 : 0;
+                q.passes = reinterpret_cast<const Dec3Pass*>(c.dev("d.step3.passes"));
+                q.role = reinterpret_cast<const int*>(c.dev("d.step3.role"));
+                q.job = reinterpret_cast<const int*>(c.dev("d.step3.job"));
+                q.wimg = c.dev("d.step3.wimg"); q.wimg_floats = (int)c.meta.at("d.step3.wimg_floats");
+                q.timing = c.profiling ? c.fbuf("ws.d.timing3", (size_t)c.num_sms * D3_TIMING_SLOTS) : nullptr;
+                void* args[] = {&q};
+                L2S_CUDA(cudaLaunchCooperativeKernel((void*)decode3_kernel, dim3(c.num_sms), dim3(MV_THREADS), args, smem, s));
+                c.launches++;
+            }
             c.span_end("decode_loop", s);
-        } else {
+        }
+#ifdef L2S_DEBUG
+        else {
             const size_t smem = (size_t)c.meta.at("d.step.smem");
             L2S_CUDA(cudaFuncSetAttribute(decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             void* args[] = {&dp};
             c.span_begin("decode_loop", s);
             L2S_CUDA(cudaLaunchCooperativeKernel((void*)decode_persistent_kernel, dim3(c.num_sms), dim3(MV_THREADS), args, smem, s));
             c.span_end("decode_loop", s);
+            c.launches++;
         }
-        c.launches++;
+#endif
     }
     c.span_begin("postnet", s);
     // ---- postnet + residual (decoder.py:437-439) --------------------------------------------------
@@ -802,7 +877,7 @@ __global__ void bcl_to_rows_kernel(const float* __restrict__ x, float* __restric
 
 // video_ready: optional event after which `video` is valid on the device (the host entry point copies the clips on a
 // second stream while the speaker encoder, which only needs the waveforms, already runs)
-static void infer_device(Context& c, const float* video, const float* wav, const float* gumbel, int B, int T, int H, int W, int S,
+static void infer_device(Context& c, const VideoSrc& video, const float* wav, const float* gumbel, int B, int T, int H, int W, int S,
                          int steps, float* mel_post, int64_t* lengths, int precision, cudaStream_t s, cudaEvent_t video_ready = nullptr) {
     float* emb = c.fbuf("ws.i.emb", (size_t)B * 256);
     float* feat = c.fbuf("ws.i.feat", (size_t)B * T * 768);
@@ -850,10 +925,12 @@ int l2s_create(l2s_ctx** out, int device) {
     ctx->c.device = device;
     ctx->c.num_sms = prop.multiProcessorCount;
     ctx->c.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+#ifdef L2S_DEBUG
     if (const char* e = getenv("L2S_TC")) ctx->c.use_tc = (e[0] != '0');
     if (const char* e = getenv("L2S_DEC3")) ctx->c.use_dec3 = (e[0] != '0');
     if (const char* e = getenv("L2S_PW")) ctx->c.use_pw = (e[0] != '0');
     if (const char* e = getenv("L2S_PW_MIN_ROWS")) ctx->c.pw_min_rows = std::max(1, atoi(e));
+#endif
     *out = ctx;
     return L2S_OK;
 }
@@ -915,7 +992,7 @@ int l2s_video_fwd(l2s_ctx* ctx, const float* video, int B, int T, int H, int W, 
     if (!ctx) return L2S_ERR_INVALID;
     API_BEGIN
     need(ctx, L2S_PART_VIDEO, "video_fwd");
-    video_forward(ctx->c, video, B, T, H, W, out_feat, precision, (cudaStream_t)stream);
+    video_forward(ctx->c, video_f32(video), B, T, H, W, out_feat, precision, (cudaStream_t)stream);
     API_END(ctx)
 }
 
@@ -969,7 +1046,7 @@ int l2s_infer(l2s_ctx* ctx, const float* video, const float* wav, const float* g
     if (!ctx) return L2S_ERR_INVALID;
     API_BEGIN
     need(ctx, L2S_PART_VIDEO | L2S_PART_SPEAKER | L2S_PART_DECODER, "infer");
-    infer_device(ctx->c, video, wav, gumbel, B, T, H, W, S, steps, mel_post, lengths, precision, (cudaStream_t)stream);
+    infer_device(ctx->c, video_f32(video), wav, gumbel, B, T, H, W, S, steps, mel_post, lengths, precision, (cudaStream_t)stream);
     API_END(ctx)
 }
 
@@ -977,7 +1054,7 @@ int l2s_infer(l2s_ctx* ctx, const float* video, const float* wav, const float* g
 // a second stream, overlapped with the speaker encoder — which needs only the waveforms — and, when the caller keeps two
 // submissions in flight, with the previous batch's compute), the whole span, and the D2H copies of the results; `wait`
 // blocks until that slot's results are in the caller's buffers.
-static void infer_host_submit(Context& c, int slot, const float* video, const float* wav, const float* gumbel, int B, int T, int H, int W, int S,
+static void infer_host_submit(Context& c, int slot, const VideoSrc& video, const float* wav, const float* gumbel, int B, int T, int H, int W, int S,
                               int steps, float* mel_post, int64_t* lengths, int precision) {
     if (slot < 0 || slot > 1) throw L2sError(L2S_ERR_INVALID, "infer_host: slot must be 0 or 1");
     int minT = T;
@@ -985,7 +1062,8 @@ static void infer_host_submit(Context& c, int slot, const float* video, const fl
     const size_t nv = (size_t)B * 3 * T * H * W, nw = (size_t)B * S, ng = (size_t)B * minT * 501, nm = (size_t)B * 80 * steps;
     const std::string sfx = slot ? ".1" : "";
     // grow every staging buffer of this slot before anything is enqueued (a reallocation synchronises the device)
-    float* dv = c.fbuf("ws.h.video" + sfx, nv); float* dw = c.fbuf("ws.h.wav" + sfx, nw); float* dg = c.fbuf("ws.h.gumbel" + sfx, ng);
+    const size_t vbytes = nv * (video.kind == 0 ? sizeof(float) : 1);
+    void* dv = c.buf("ws.h.video" + sfx, vbytes); float* dw = c.fbuf("ws.h.wav" + sfx, nw); float* dg = c.fbuf("ws.h.gumbel" + sfx, ng);
     float* dm = c.fbuf("ws.h.mel" + sfx, nm);
     int64_t* dl = static_cast<int64_t*>(c.buf("ws.h.len" + sfx, (size_t)B * sizeof(int64_t)));
     if (!c.host_stream) {
@@ -1000,11 +1078,12 @@ static void infer_host_submit(Context& c, int slot, const float* video, const fl
     cudaStream_t s = c.host_stream;
     // the copy stream must not overwrite this slot's clip buffer while an earlier submission still reads it
     if (c.slot_used[slot]) L2S_CUDA(cudaStreamWaitEvent(c.copy_stream, c.video_consumed[slot], 0));
-    L2S_CUDA(cudaMemcpyAsync(dv, video, nv * sizeof(float), cudaMemcpyHostToDevice, c.copy_stream));
+    L2S_CUDA(cudaMemcpyAsync(dv, video.p, vbytes, cudaMemcpyHostToDevice, c.copy_stream));
     L2S_CUDA(cudaEventRecord(c.copy_done[slot], c.copy_stream));
     L2S_CUDA(cudaMemcpyAsync(dw, wav, nw * sizeof(float), cudaMemcpyHostToDevice, s));
     L2S_CUDA(cudaMemcpyAsync(dg, gumbel, ng * sizeof(float), cudaMemcpyHostToDevice, s));
-    infer_device(c, dv, dw, dg, B, T, H, W, S, steps, dm, dl, precision, s, c.copy_done[slot]);
+    VideoSrc dsrc = video; dsrc.p = dv;
+    infer_device(c, dsrc, dw, dg, B, T, H, W, S, steps, dm, dl, precision, s, c.copy_done[slot]);
     L2S_CUDA(cudaEventRecord(c.video_consumed[slot], s));
     L2S_CUDA(cudaMemcpyAsync(mel_post, dm, nm * sizeof(float), cudaMemcpyDeviceToHost, s));
     L2S_CUDA(cudaMemcpyAsync(lengths, dl, (size_t)B * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
@@ -1017,7 +1096,7 @@ int l2s_infer_host_submit(l2s_ctx* ctx, int slot, const float* video, const floa
     if (!ctx) return L2S_ERR_INVALID;
     API_BEGIN
     need(ctx, L2S_PART_VIDEO | L2S_PART_SPEAKER | L2S_PART_DECODER, "infer_host_submit");
-    infer_host_submit(ctx->c, slot, video, wav, gumbel, B, T, H, W, S, steps, mel_post, lengths, precision);
+    infer_host_submit(ctx->c, slot, video_f32(video), wav, gumbel, B, T, H, W, S, steps, mel_post, lengths, precision);
     API_END(ctx)
 }
 
@@ -1030,12 +1109,41 @@ int l2s_infer_host_wait(l2s_ctx* ctx, int slot) {
     API_END(ctx)
 }
 
+int l2s_video_fwd_u8(l2s_ctx* ctx, const unsigned char* frames, const float* mean_std, int B, int T, int H, int W, float* out_feat, int precision, void* stream) {
+    if (!ctx) return L2S_ERR_INVALID;
+    API_BEGIN
+    need(ctx, L2S_PART_VIDEO, "video_fwd_u8");
+    if (!frames || !mean_std) throw L2sError(L2S_ERR_INVALID, "video_fwd_u8: frames and mean_std are required");
+    video_forward(ctx->c, video_u8(frames, mean_std), B, T, H, W, out_feat, precision, (cudaStream_t)stream);
+    API_END(ctx)
+}
+
+int l2s_infer_u8(l2s_ctx* ctx, const unsigned char* frames, const float* mean_std, const float* wav, const float* gumbel, int B, int T, int H, int W,
+                 int S, int steps, float* mel_post, int64_t* lengths, int precision, void* stream) {
+    if (!ctx) return L2S_ERR_INVALID;
+    API_BEGIN
+    need(ctx, L2S_PART_VIDEO | L2S_PART_SPEAKER | L2S_PART_DECODER, "infer_u8");
+    if (!frames || !mean_std) throw L2sError(L2S_ERR_INVALID, "infer_u8: frames and mean_std are required");
+    infer_device(ctx->c, video_u8(frames, mean_std), wav, gumbel, B, T, H, W, S, steps, mel_post, lengths, precision, (cudaStream_t)stream);
+    API_END(ctx)
+}
+
+int l2s_infer_host_submit_u8(l2s_ctx* ctx, int slot, const unsigned char* frames, const float* mean_std, const float* wav, const float* gumbel,
+                             int B, int T, int H, int W, int S, int steps, float* mel_post, int64_t* lengths, int precision) {
+    if (!ctx) return L2S_ERR_INVALID;
+    API_BEGIN
+    need(ctx, L2S_PART_VIDEO | L2S_PART_SPEAKER | L2S_PART_DECODER, "infer_host_submit_u8");
+    if (!frames || !mean_std) throw L2sError(L2S_ERR_INVALID, "infer_host_submit_u8: frames and mean_std are required");
+    infer_host_submit(ctx->c, slot, video_u8(frames, mean_std), wav, gumbel, B, T, H, W, S, steps, mel_post, lengths, precision);
+    API_END(ctx)
+}
+
 int l2s_infer_host(l2s_ctx* ctx, const float* video, const float* wav, const float* gumbel, int B, int T, int H, int W, int S, int steps,
                    float* mel_post, int64_t* lengths, int precision) {
     if (!ctx) return L2S_ERR_INVALID;
     API_BEGIN
     need(ctx, L2S_PART_VIDEO | L2S_PART_SPEAKER | L2S_PART_DECODER, "infer_host");
-    infer_host_submit(ctx->c, 0, video, wav, gumbel, B, T, H, W, S, steps, mel_post, lengths, precision);
+    infer_host_submit(ctx->c, 0, video_f32(video), wav, gumbel, B, T, H, W, S, steps, mel_post, lengths, precision);
     L2S_CUDA(cudaEventSynchronize(ctx->c.slot_done[0]));
     API_END(ctx)
 }
@@ -1053,14 +1161,22 @@ struct NcclApi {
 NcclApi& nccl_api() {
     static NcclApi a;
     if (!a.h) {
-        a.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-        if (!a.h) throw L2sError(L2S_ERR_CUDA, std::string("dlopen(libnccl.so.2): ") + dlerror());
-        auto sym = [&](const char* n) { void* p = dlsym(a.h, n); if (!p) throw L2sError(L2S_ERR_CUDA, std::string("libnccl.so.2 lacks ") + n); return p; };
-        a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(sym("ncclGetUniqueId"));
-        a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(sym("ncclCommInitRank"));
-        a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(sym("ncclAllReduce"));
-        a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(sym("ncclCommDestroy"));
-        a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(sym("ncclGetErrorString"));
+        // resolve into a local table and publish it only when every symbol is there: a failed attempt must not leave a
+        // half-filled static behind (the next call would jump through a null pointer)
+        NcclApi t;
+        t.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!t.h) throw L2sError(L2S_ERR_CUDA, std::string("dlopen(libnccl.so.2): ") + dlerror());
+        auto sym = [&](const char* n) {
+            void* p = dlsym(t.h, n);
+            if (!p) { dlclose(t.h); throw L2sError(L2S_ERR_CUDA, std::string("libnccl.so.2 lacks ") + n); }
+            return p;
+        };
+        t.GetUniqueId = reinterpret_cast<decltype(t.GetUniqueId)>(sym("ncclGetUniqueId"));
+        t.CommInitRank = reinterpret_cast<decltype(t.CommInitRank)>(sym("ncclCommInitRank"));
+        t.AllReduce = reinterpret_cast<decltype(t.AllReduce)>(sym("ncclAllReduce"));
+        t.CommDestroy = reinterpret_cast<decltype(t.CommDestroy)>(sym("ncclCommDestroy"));
+        t.GetErrorString = reinterpret_cast<decltype(t.GetErrorString)>(sym("ncclGetErrorString"));
+        a = t;
     }
     return a;
 }

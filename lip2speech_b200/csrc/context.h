@@ -49,9 +49,14 @@ struct Context {
     bool slot_used[2] = {false, false};
     void* nccl_comm = nullptr; int world = 1, rank = 0;          // data-parallel gradient exchange (l2s_comm_init)
     int pw_min_rows = 16384;                  // streaming 1x1 kernel for GEMMs with at least this many rows (L2S_PW_MIN_ROWS)
-    bool use_pw = true;                       // streaming mma.sync kernel for the trunk's 1x1 convolutions (L2S_PW=0: tcgen05 GEMM)
-    bool use_dec3 = true;                     // stage-pipelined decode kernel for B <= 32 (L2S_DEC3=0: row-partitioned kernel for every B)
-    bool use_tc = true;                       // tcgen05 GEMM path (L2S_TC=0 selects the exact-fp32 SIMT GEMMs for debugging)
+#ifdef L2S_DEBUG
+    // debug builds only (nvcc -DL2S_DEBUG): environment toggles that swap kernels for bisecting; a release library has ONE path
+    bool use_pw = true;                       // L2S_PW=0: tcgen05 GEMM instead of the streaming mma.sync kernel for the trunk's 1x1 convolutions
+    bool use_dec3 = true;                     // L2S_DEC3=0: row-partitioned decode kernel for every B
+    bool use_tc = true;                       // L2S_TC=0: exact-fp32 SIMT GEMMs
+#else
+    static constexpr bool use_pw = true, use_dec3 = true, use_tc = true;
+#endif
     // optional stage timing (CUDA events on the caller's stream), enabled by l2s_set_profiling
     bool profiling = false;
     struct Span { cudaEvent_t e0 = nullptr, e1 = nullptr; bool used = false; };

@@ -521,8 +521,10 @@ inline const char* launch_tc_gemm(const TcOperands& o, TcParams p, cudaStream_t 
     const int rem = p.Kc % TC_BK;
     p.ksteps_last = rem == 0 ? TC_BK / 8 : (rem + 7) / 8;
     p.ga_A = o.A; p.ga_lda = o.lda; p.ga_rows = o.a_rows;
+#ifdef L2S_DEBUG
     if (const char* e = getenv("L2S_TC_DEBUG_NITER")) p.debug_niter = atoi(e);
     if (const char* e = getenv("L2S_TC_DEBUG_SKIP")) p.debug_skip = atoi(e);
+#endif
     if (gather) {
         if ((o.lda & 3) || (p.Kc & 3) || (reinterpret_cast<uintptr_t>(o.A) & 15)) return "gather-A needs 16-byte aligned rows";
         // the A map is unused in gather mode but must be a valid object: describe the W matrix again
@@ -554,7 +556,9 @@ inline const char* launch_tc_stem_bf16(const void* A16, const void* W16, int tap
     if (reinterpret_cast<uintptr_t>(A16) & 15) return "bf16 stem needs 16-byte aligned rows";
     if (!make_map_2d_bf16(&mW, W16, (uint64_t)taps * 64, 32, (uint64_t)taps * 64, 32)) return "cuTensorMapEncodeTiled(W bf16) failed";
     p.ga_A = reinterpret_cast<const float*>(A16); p.taps = taps; p.use_shift_table = 1; p.ksteps_last = 4;
+#ifdef L2S_DEBUG
     if (const char* e = getenv("L2S_TC_DEBUG_SKIP")) p.debug_skip = atoi(e);
+#endif
     static int num_sms = 0;
     if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
     const int ntiles = ceil_div(p.M, TC_BM);

@@ -58,6 +58,9 @@ class VideoExtractor(ParamTree):
         self.precision = _lib.PRECISION_FP32
 
     def forward(self, x):
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError("VideoExtractor.forward in train mode (BatchNorm batch statistics, autograd) is not built; "
+                                      "call .eval() or wrap the call in torch.no_grad()")
         be = _lib.backend(_device_index(self))
         be.sync_module(self, "encoder.", _lib.PART_VIDEO)
         return be.video_fwd(x, self.precision)

@@ -23,6 +23,10 @@ _saved = {}
 
 
 def _video_forward(self, x):
+    import torch
+    if self.training and torch.is_grad_enabled():
+        raise NotImplementedError("VideoExtractor.forward in train mode (BatchNorm batch statistics, autograd) is not built on the "
+                                  "B200 backend; call .eval() or lip2speech_b200.patch.unpatch() to train in PyTorch")
     be = _lib.backend(modules._device_index(self))
     be.sync_module(self, "encoder.", _lib.PART_VIDEO)
     return be.video_fwd(x, getattr(self, "precision", _lib.PRECISION_FP32))

@@ -21,6 +21,21 @@ def video(B, T=29, H=96, W=96, seed=1234) -> torch.Tensor:
     return torch.from_numpy(a)
 
 
+def frames_u8(B, T=29, H=96, W=96, seed=1234) -> torch.Tensor:
+    """[B,T,H,W,3] uint8 RGB: decoded mouth crops as loadframes() returns them (datasets/lrw/dataset.py:20-24)."""
+    a = _rng(seed, 7).integers(0, 256, (B, T, H, W, 3), dtype=np.uint8)
+    return torch.from_numpy(a)
+
+
+def normalise_frames(frames: torch.Tensor) -> torch.Tensor:
+    """The dataset's host-side arithmetic (datasets/lrw/dataset.py:82-86,132) + the collate permute
+    (datasets/__init__.py:7-46): uint8 [B,T,H,W,3] -> fp32 [B,3,T,H,W] = (x/255 - mean) / std."""
+    x = frames.permute(0, 1, 4, 2, 3).float() / 255.0                 # [B,T,3,H,W]
+    mean = torch.tensor((0.485, 0.456, 0.406)).view(1, 1, 3, 1, 1)
+    std = torch.tensor((0.229, 0.224, 0.225)).view(1, 1, 3, 1, 1)
+    return ((x - mean) / std).permute(0, 2, 1, 3, 4).contiguous()
+
+
 def wav(B, S=19456, seed=1234) -> torch.Tensor:
     """[B,S] fp32, 0.1*N(0,1): 1.216 s of 16 kHz audio per LRW clip."""
     a = _rng(seed, 2).standard_normal((B, S), dtype=np.float32) * np.float32(0.1)

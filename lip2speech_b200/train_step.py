@@ -61,12 +61,25 @@ class ClipAdamW:
     (what clip_grad_norm_ returns), after: sum over ranks (NCCL, if a communicator was set up) x 1/world, global L2
     norm, clip to max_norm, AdamW(amsgrad) update."""
 
-    def __init__(self, params, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-6, max_norm=1.0, backend=None, world=1):
-        self.params = [p for p in params]
+    def __init__(self, params, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-6, max_norm=1.0, backend=None, world=None):
+        """`params` may be an iterable of parameters or of {'params': [...]} groups, as train.py:102-104 passes them
+        (every group shares the hyper-parameters).  `world`: data-parallel size the gradients are averaged over; by default
+        the size of the communicator set up with init_data_parallel (1 without one)."""
+        params = list(params)
+        if params and isinstance(params[0], dict):
+            self._group_sizes = [len(list(g["params"])) for g in params]
+            params = [p for g in params for p in g["params"]]
+        else:
+            self._group_sizes = [len(params)]
+        self.params = params
         assert self.params and all(p.is_cuda and p.dtype == torch.float32 for p in self.params)
         dev = self.params[0].device
         self.be = backend or _lib.backend(dev.index or 0)
-        self.lr, self.betas, self.eps, self.weight_decay, self.max_norm, self.world = lr, betas, eps, weight_decay, max_norm, world
+        comm_world = getattr(self.be, "world", 1)
+        if world is not None and comm_world > 1 and world != comm_world:
+            raise ValueError(f"ClipAdamW(world={world}) but the backend's communicator spans {comm_world} ranks")
+        self.lr, self.betas, self.eps, self.weight_decay, self.max_norm = lr, betas, eps, weight_decay, max_norm
+        self.world = world if world is not None else comm_world
         self.offsets, self.n = flat_layout([p.numel() for p in self.params])
         self.p = torch.zeros(self.n, device=dev)
         self.g = torch.zeros(self.n, device=dev)
@@ -89,7 +102,52 @@ class ClipAdamW:
         self.be.allreduce_grads(self.g, 1.0 / self.world, self.sqnorm)
         self.be.clip_adamw_step(self.p, self.g, self.m, self.v, self.vmax, self.sqnorm, self.max_norm, self.lr, self.betas[0],
                                 self.betas[1], self.eps, self.weight_decay, self.t)
+        # the kernel wrote the parameters through raw pointers: neither data_ptr nor the autograd version counter moved, so
+        # tell the backend that its packed copies (BN folded, tiles repacked) are stale
+        self.be.invalidate_weights()
         return self.sqnorm.sqrt()
+
+    # ---- torch.optim.AdamW-compatible checkpoint state (train.py:125 load_state_dict, :211 'optimize_state') ---------------
+    @property
+    def param_groups(self):
+        groups, i = [], 0
+        for n in self._group_sizes:
+            groups.append({"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.weight_decay,
+                           "amsgrad": True, "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
+                           "fused": None, "params": list(range(i, i + n))})
+            i += n
+        return groups
+
+    def state_dict(self):
+        """Same layout as torch.optim.AdamW(amsgrad=True).state_dict(): per-parameter step / exp_avg / exp_avg_sq /
+        max_exp_avg_sq (copies sliced from the flat buffers; empty before the first step, like torch) + param_groups."""
+        state = {}
+        if self.t > 0:
+            for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+                sl = slice(o, o + p.numel())
+                state[i] = {"step": torch.tensor(float(self.t)), "exp_avg": self.m[sl].view_as(p).clone(),
+                            "exp_avg_sq": self.v[sl].view_as(p).clone(), "max_exp_avg_sq": self.vmax[sl].view_as(p).clone()}
+        return {"state": state, "param_groups": self.param_groups}
+
+    def load_state_dict(self, sd):
+        groups = sd["param_groups"]
+        if [len(g["params"]) for g in groups] != self._group_sizes:
+            raise ValueError("loaded state dict has a different number of parameter groups / parameters")
+        g0 = groups[0]
+        if not g0.get("amsgrad", False):
+            raise ValueError("ClipAdamW implements AdamW(amsgrad=True) only (train.py:104)")
+        self.lr, self.betas, self.eps, self.weight_decay = g0["lr"], tuple(g0["betas"]), g0["eps"], g0["weight_decay"]
+        state = sd["state"]
+        steps = {int(st["step"]) for st in state.values()}
+        if len(steps) > 1:
+            raise ValueError("per-parameter step counts differ; the flat update keeps one step counter")
+        self.t = steps.pop() if steps else 0
+        self.m.zero_(); self.v.zero_(); self.vmax.zero_()
+        for i, st in state.items():
+            p, o = self.params[int(i)], self.offsets[int(i)]
+            sl = slice(o, o + p.numel())
+            self.m[sl].copy_(st["exp_avg"].reshape(-1)); self.v[sl].copy_(st["exp_avg_sq"].reshape(-1))
+            self.vmax[sl].copy_(st["max_exp_avg_sq"].reshape(-1))
 
 
 def init_data_parallel(backend: "_lib.Backend", rank: int, world: int, group=None):
@@ -110,4 +168,5 @@ def init_data_parallel(backend: "_lib.Backend", rank: int, world: int, group=Non
     else:
         dist.broadcast(buf, 0, group=group)
     backend.comm_init(bytes(buf.tolist()), rank, world)
+    backend.world = world
     return bytes(buf.tolist())

@@ -136,7 +136,7 @@ def speaker_forward(sd, wav, p=""):
     """SpeakerEncoder.forward: raw (pre-ReLU) embedding [B,256] (audio.py:132-142)."""
     mel = speaker_melspec(sd, wav, p).permute(0, 2, 1)
     b = wav.shape[0]
-    z = torch.zeros(3, b, 256)
+    z = torch.zeros(3, b, 256, device=wav.device)
     _, h, _ = _lstm(mel, z, z.clone(), sd, p + "lstm", 3)
     return F.linear(h[-1], sd[p + "linear.weight"], sd[p + "linear.bias"])
 
@@ -232,8 +232,8 @@ def decoder_steps(sd, pre, steps, p="decoder.", return_attention=False):
     pos = sd[p + "positional_encodings.pos_table"][0]
     temp, ctemp = sd[p + "temperature"], sd[p + "content.temperature"]
     ys = sd[p + "BOS"].reshape(1, -1).repeat(b, 1)
-    outputs = torch.zeros(b, steps, ys.shape[1])
-    lengths = torch.full((b,), steps, dtype=torch.int64)
+    outputs = torch.zeros(b, steps, ys.shape[1], device=ys.device)
+    lengths = torch.full((b,), steps, dtype=torch.int64, device=ys.device)
     attn = []
     wl = [(sd[f"{p}decoder_rnn.weight_ih_l{l}"], sd[f"{p}decoder_rnn.weight_hh_l{l}"],
            sd[f"{p}decoder_rnn.bias_ih_l{l}"], sd[f"{p}decoder_rnn.bias_hh_l{l}"]) for l in range(2)]
@@ -285,8 +285,8 @@ def decoder_forward(sd, enc_in, face_tiled, mels, tf_mask, gumbel_noise, p="deco
     temp, ctemp = sd[p + "temperature"], sd[p + "content.temperature"]
     ys = sd[p + "BOS"].reshape(1, -1).repeat(b, 1)
     teacher = torch.cat([ys.unsqueeze(1), mels.permute(0, 2, 1)], dim=1)       # [B, M+1, 80]
-    outputs = torch.zeros(b, m, ys.shape[1])
-    stops = torch.zeros(b, m, 1)
+    outputs = torch.zeros(b, m, ys.shape[1], device=ys.device)
+    stops = torch.zeros(b, m, 1, device=ys.device)
     attn = []
     wl = [(sd[f"{p}decoder_rnn.weight_ih_l{l}"], sd[f"{p}decoder_rnn.weight_hh_l{l}"],
            sd[f"{p}decoder_rnn.bias_ih_l{l}"], sd[f"{p}decoder_rnn.bias_hh_l{l}"]) for l in range(2)]

@@ -104,6 +104,98 @@ def test_clip_adamw_matches_torch(be, max_norm, grad_scale):
     assert float(opt.p[opt.offsets[0] + 7:opt.offsets[1]].abs().max()) == 0.0
 
 
+def test_clip_adamw_state_dict_round_trip(be):
+    """the reference checkpoints optim.state_dict() (train.py:211) and restores it on resume (train.py:125).
+    ClipAdamW's state_dict has torch.optim.AdamW's layout and values; loading it (from ours or from torch's) continues the
+    run exactly."""
+    from lip2speech_b200.train_step import ClipAdamW
+    params = _param_set(4)
+    g = torch.Generator().manual_seed(12)
+    grads = [[torch.randn(p.shape, generator=g) for p in params] for _ in range(6)]
+    ps = [torch.nn.Parameter(p.clone()) for p in params]
+    ref = torch.optim.AdamW([{"params": ps[:2]}, {"params": ps[2:]}], lr=1e-3, weight_decay=1e-2, amsgrad=True)   # two groups, as train.py:102
+    cu = [torch.nn.Parameter(p.clone().cuda()) for p in params]
+    opt = ClipAdamW([{"params": cu[:2]}, {"params": cu[2:]}], lr=1e-3, weight_decay=1e-2, max_norm=0.0, backend=be)
+    assert opt.state_dict()["state"] == {}
+    for s in range(3):
+        for p, gr in zip(ps, grads[s]):
+            p.grad = gr.clone()
+        ref.step()
+        opt.zero_grad()
+        for p, gr in zip(cu, grads[s]):
+            p.grad.copy_(gr)
+        opt.step()
+    sd, rsd = opt.state_dict(), ref.state_dict()
+    assert [g_["params"] for g_ in sd["param_groups"]] == [g_["params"] for g_ in rsd["param_groups"]]
+    for k in ("lr", "betas", "eps", "weight_decay", "amsgrad"):
+        assert sd["param_groups"][0][k] == rsd["param_groups"][0][k]
+    assert set(sd["state"]) == set(rsd["state"])
+    for i in rsd["state"]:
+        assert float(sd["state"][i]["step"]) == float(rsd["state"][i]["step"])
+        for k in ("exp_avg", "exp_avg_sq", "max_exp_avg_sq"):
+            assert rel_err(sd["state"][i][k].cpu(), rsd["state"][i][k]) < 2e-6, (i, k)
+    # resume in a fresh optimizer from TORCH's state dict and continue: same parameters as the uninterrupted torch run
+    cu2 = [torch.nn.Parameter(p.detach().clone().cuda()) for p in ps]
+    opt2 = ClipAdamW([{"params": cu2[:2]}, {"params": cu2[2:]}], lr=5e-2, max_norm=0.0, backend=be)
+    opt2.load_state_dict(rsd)
+    assert opt2.t == 3 and opt2.lr == 1e-3
+    for s in range(3, 6):
+        for p, gr in zip(ps, grads[s]):
+            p.grad = gr.clone()
+        ref.step()
+        opt2.zero_grad()
+        for p, gr in zip(cu2, grads[s]):
+            p.grad.copy_(gr)
+        opt2.step()
+    for p, r in zip(cu2, ps):
+        assert rel_err(p.detach().cpu(), r.detach()) < 2e-6
+
+
+def test_forward_after_optimizer_step_sees_new_weights(be):
+    """ClipAdamW.step() writes the parameters through raw pointers (no data_ptr / version change); the next
+    forward must run on the UPDATED weights, not on the copies packed before the step."""
+    from lip2speech_b200 import modules, spec, synth
+    from lip2speech_b200.train_step import ClipAdamW
+    from oracle import l2s_oracle as O
+    dec = modules.Decoder(seed=1234).cuda().eval()
+    visual, face = synth.visual_features(2, 29, seed=3)
+    g = synth.gumbel(2, 29, seed=3)
+    with torch.no_grad():
+        mel0, _ = dec.inference(visual.cuda(), face.cuda(), gumbel_noise=g.cuda())
+    opt = ClipAdamW(dec.parameters(), lr=1e-2, max_norm=0.0)
+    opt.zero_grad()
+    gen = torch.Generator().manual_seed(5)
+    for p in dec.parameters():
+        p.grad.copy_(torch.randn(p.shape, generator=gen))
+    opt.step()
+    with torch.no_grad():
+        mel1, len1 = dec.inference(visual.cuda(), face.cuda(), gumbel_noise=g.cuda())
+    w = {"decoder." + k: v.detach().cpu() for k, v in dec.state_dict().items()}
+    ref_mel, ref_len = O.decoder_inference(w, visual, face, g)
+    assert rel_err(mel1.cpu(), ref_mel) < 1e-3 and torch.equal(len1.cpu(), ref_len)
+    assert rel_err(mel0.cpu(), ref_mel) > 1e-2, "the step should have moved the output"
+
+
+def test_gradient_exchange_single_rank_nccl(be):
+    """The NCCL path of l2s_allreduce_grads on a 1-GPU box: a world-size-1 communicator (ncclCommInitRank through the
+    library's dlopen'ed NCCL) leaves the gradient unchanged; scale and squared norm are applied on the device."""
+    import ctypes as C
+    from lip2speech_b200 import _lib
+    lib = _lib.load()
+    raw = C.create_string_buffer(_lib.NCCL_UNIQUE_ID_BYTES)
+    assert lib.l2s_nccl_unique_id(raw, _lib.NCCL_UNIQUE_ID_BYTES) == 0
+    b2 = _lib.Backend(0)
+    b2.comm_init(raw.raw, 0, 1)
+    g = torch.randn(1_000_003 // 4 * 4, generator=torch.Generator().manual_seed(2)).cuda()
+    ref = g.clone()
+    sq = torch.zeros(1, device="cuda")
+    b2.allreduce_grads(g, 0.5, sq)
+    assert torch.equal(g, ref * 0.5)
+    assert abs(float(sq) - float((ref.double() * 0.5).pow(2).sum())) < 1e-4 * float(sq)
+    b2.comm_destroy()
+    b2.close()
+
+
 def test_train_step_argument_errors(be):
     x = torch.zeros(16, device="cuda")
     with pytest.raises(RuntimeError):
