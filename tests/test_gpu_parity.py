@@ -201,7 +201,7 @@ def test_soft_attention_regime(O, weights):
     mel, lengths, attn = b2.decoder_infer(visual.cuda(), face[:, 0].cuda(), g.cuda(), steps=80, return_attention=True)
     ref_mel, ref_len, ref_attn = O.decoder_inference(w, visual, face, g, steps=80, return_attention=True)
     b2.close()
-    assert float(ref_attn.max(-1).values.median()) < 0.9, "temperature 1.0 should give a soft attention distribution"
+    assert float((ref_attn.max(-1).values < 0.9).float().mean()) > 0.2, "temperature 1.0 should give soft attention on many steps"
     assert torch.equal(lengths.cpu(), ref_len)
     assert rel_err(mel.cpu(), ref_mel) < TOL
     assert (attn.cpu() - ref_attn).abs().max() < 1e-3
