@@ -729,28 +729,18 @@ static void decoder_run(Context& c, const float* visual, const float* spk, const
     // ---- stop-token constant, initial state --------------------------------------------------------
     float* stopc = c.fbuf("ws.d.stopc", (size_t)B);
     linear(c, enc_cell, 512, "d.stop2", nullptr, stopc, 1, B, 1, 512, ACT_NONE, nullptr, s, "stop const");
-    float* S = c.fbuf("ws.d.S", 2 * 2 * plane);
-    float* Cst = c.fbuf("ws.d.Cst", 2 * plane);
-    L2S_CUDA(cudaMemcpyAsync(S, hfinal, 2 * plane * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    L2S_CUDA(cudaMemsetAsync(Cst, 0, 2 * plane * sizeof(float), s));           // cell.fill_(0), decoder.py:406
     float* outputs = c.fbuf("ws.d.outputs", (size_t)B * steps * 80);
     fill_i64_kernel<<<ceil_div(B, 256), 256, 0, s>>>(reinterpret_cast<long long*>(lengths), (long long)steps, B);
     check_launch(c, "lengths init");
 
-    // ---- the 300-step loop: one persistent cooperative kernel ------------------------------------
+    // ---- the 300-step loop: one persistent cooperative kernel per 32 clips -----------------------
     {
+        if (c.meta.at("d.step3.ok") != 1) throw L2sError(L2S_ERR_INVALID, "decoder: the stage-pipelined decode kernel needs >= 148 SMs");
         DecodeParams dp{};
-        dp.passes = reinterpret_cast<const DecPass*>(c.dev("d.step.passes"));
-        dp.npasses = reinterpret_cast<const int*>(c.dev("d.step.npasses"));
-        dp.wimg = c.dev("d.step.wimg"); dp.wimg_floats = (int)c.meta.at("d.step.wimg_floats");
-        dp.S = S; dp.Cst = Cst;
-        dp.P1 = c.fbuf("ws.d.P1", (size_t)256 * Bpad);
-        dp.Q = c.fbuf("ws.d.Q", (size_t)512 * Bpad); dp.CQ = c.fbuf("ws.d.CQ", (size_t)256 * Bpad);
-        dp.XD = c.fbuf("ws.d.XD", (size_t)1024 * Bpad);
-        dp.nsplit = (4 * B <= c.num_sms) ? 4 : (2 * B <= c.num_sms) ? 2 : 1;
-        dp.Kmem = Kmem; dp.Vmem = Vmem; dp.ckey = ckey; dp.cval = cval; dp.stop_const = stopc; dp.pos = pos;
+        dp.pos = pos;
         dp.temp = c.W("decoder.temperature").f[0]; dp.ctemp = c.W("decoder.content.temperature").f[0];
-        dp.outputs = outputs; dp.lengths = reinterpret_cast<long long*>(lengths); dp.attn = attn;
+        dp.Bpad = Bpad; dp.T = T; dp.minT = minT; dp.steps = steps;
+        const unsigned char* tfm = nullptr; const float* p1t = nullptr;
         if (fw.mels) {
             // teacher frames -> prenet layer 1 for every step (one GEMM), kept feature-major for the step kernel
             float* tr = c.fbuf("ws.d.trows", (size_t)B * steps * 80);
@@ -758,87 +748,75 @@ static void decoder_run(Context& c, const float* visual, const float* spk, const
             check_launch(c, "teacher rows");
             float* p1r = c.fbuf("ws.d.p1rows", (size_t)B * steps * 256);
             linear(c, tr, 80, "d.prenet0", c.dev("d.prenet0.b"), p1r, 256, B * steps, 256, 80, ACT_PSINE, c.dev("d.prenet0.psw"), s, "prenet.0 (teacher)");
-            float* p1t = c.fbuf("ws.d.p1t", (size_t)steps * 256 * Bpad);
-            p1_teacher_fm_kernel<<<ew_grid((size_t)steps * 256 * Bpad), 256, 0, s>>>(p1r, p1t, B, Bpad, steps);
+            float* p1tb = c.fbuf("ws.d.p1t", (size_t)steps * 256 * Bpad);
+            p1_teacher_fm_kernel<<<ew_grid((size_t)steps * 256 * Bpad), 256, 0, s>>>(p1r, p1tb, B, Bpad, steps);
             check_launch(c, "p1 teacher fm");
             unsigned char* dmask = static_cast<unsigned char*>(c.buf("ws.d.tfmask", 512));
             L2S_CUDA(cudaMemcpyAsync(dmask, fw.tf_mask, steps, cudaMemcpyHostToDevice, s));
-            dp.tf_mask = dmask; dp.p1_teacher = p1t;
+            tfm = dmask; p1t = p1tb;
         }
-        dp.stop_out = fw.out_stop; dp.attn_logits = fw.out_attn_logits;
-        dp.B = B; dp.Bpad = Bpad; dp.T = T; dp.minT = minT; dp.steps = steps;
-        unsigned* bar = static_cast<unsigned*>(c.buf("ws.barrier", 256));
-        L2S_CUDA(cudaMemsetAsync(bar, 0, 4, s));
-        dp.barrier = bar;
-        dp.timing = c.profiling ? c.fbuf("ws.d.timing", (size_t)c.num_sms * DEC_TIMING_SLOTS) : nullptr;
+        // exchange buffers of tagged 64-bit words (decode3.cuh); tags of this call live in [tag_base, tag_base + D3_TAG_SPAN)
+        ll_t* xS = static_cast<ll_t*>(c.buf("ws.d.xS", 2 * 2 * plane * sizeof(ll_t)));
+        ll_t* xC = static_cast<ll_t*>(c.buf("ws.d.xC", 2 * plane * sizeof(ll_t)));
+        ll_t* xP1 = static_cast<ll_t*>(c.buf("ws.d.xP1", (size_t)256 * Bpad * sizeof(ll_t)));
+        ll_t* xXD = static_cast<ll_t*>(c.buf("ws.d.xXD", (size_t)1024 * Bpad * sizeof(ll_t)));
+        ll_t* xQ = static_cast<ll_t*>(c.buf("ws.d.xQ", (size_t)512 * Bpad * sizeof(ll_t)));
+        ll_t* xCQ = static_cast<ll_t*>(c.buf("ws.d.xCQ", (size_t)256 * Bpad * sizeof(ll_t)));
+        unsigned* abortw = static_cast<unsigned*>(c.buf("ws.d.abort", 256));
+        int64_t& epoch = c.meta["d.step3.epoch"];
+        if (++epoch >= (int64_t)(0xffffffffu / D3_TAG_SPAN) - 1) {        // tag space exhausted: wipe every stale tag and start over
+            for (const char* n : {"ws.d.xS", "ws.d.xC", "ws.d.xP1", "ws.d.xXD", "ws.d.xQ", "ws.d.xCQ"})
+                L2S_CUDA(cudaMemsetAsync(c.bufs.at(n).p, 0, c.bufs.at(n).bytes, s));
+            epoch = 1;
+        }
+        const uint32_t tag_base = (uint32_t)epoch * D3_TAG_SPAN;
+        // initial state: hidden = the Bi-LSTM's final (h_fwd ; h_bwd), cell.fill_(0) (decoder.py:392,406)
+        d3_init_state_kernel<<<ew_grid(2 * plane), 256, 0, s>>>(hfinal, xS, xC, Bpad, tag_base);
+        check_launch(c, "initial decoder state");
+        float* vsplit = c.fbuf("ws.d.Vsplit", (size_t)B * T * 512);
+        float* cvsplit = c.fbuf("ws.d.cvsplit", (size_t)B * minT * 256);
+        split_halves_kernel<<<ew_grid((size_t)B * T * 512), 256, 0, s>>>(Vmem, vsplit, B, T, 256);
+        check_launch(c, "V halves");
+        split_halves_kernel<<<ew_grid((size_t)B * minT * 256), 256, 0, s>>>(cval, cvsplit, B, minT, 128);
+        check_launch(c, "content value halves");
+        const size_t smem = (size_t)c.meta.at("d.step3.smem");
+        L2S_CUDA(cudaFuncSetAttribute(decode3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int chunk = D3_CG * D3_NG;
+        c.meta["dbg.dec3"] = 1;
         c.span_end("preloop", s);
-        // The stage-pipelined kernel (decode3.cuh) decodes up to D3_CG * D3_NG = 32 clips per launch; larger batches are decoded
-        // in consecutive 32-clip chunks (pre-loop and postnet stay whole-batch GEMMs).  Each chunk sees its own clips
-        // through shifted pointers; the feature-/group-major planes keep the whole batch's stride (Bpad).
-        if (c.meta.at("d.step3.ok") != 1) throw L2sError(L2S_ERR_INVALID, "decoder: the stage-pipelined decode kernel needs >= 148 SMs");
-#ifdef L2S_DEBUG
-        const bool pipelined = c.use_dec3;
-#else
-        const bool pipelined = true;
-#endif
-        c.meta["dbg.dec3"] = pipelined ? 1 : 0;
-        if (pipelined) {
-            dp.nsplit = D3_NSPLIT;
-            // group-major recurrent state for the 8-clip tensor-core passes (same sizes as the feature-major buffers)
-            float* S3 = c.fbuf("ws.d.S3", 2 * 2 * plane);
-            fm_to_group_major_kernel<<<ew_grid(2 * plane), 256, 0, s>>>(S, S3, 1024, Bpad);
-            check_launch(c, "state -> group-major");
-            float* vsplit = c.fbuf("ws.d.Vsplit", (size_t)B * T * 512);
-            float* cvsplit = c.fbuf("ws.d.cvsplit", (size_t)B * minT * 256);
-            split_halves_kernel<<<ew_grid((size_t)B * T * 512), 256, 0, s>>>(Vmem, vsplit, B, T, 256);
-            check_launch(c, "V halves");
-            split_halves_kernel<<<ew_grid((size_t)B * minT * 256), 256, 0, s>>>(cval, cvsplit, B, minT, 128);
-            check_launch(c, "content value halves");
-            const size_t smem = (size_t)c.meta.at("d.step3.smem");
-            L2S_CUDA(cudaFuncSetAttribute(decode3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const int chunk = D3_CG * D3_NG;
-            c.span_begin("decode_loop", s);
-            for (int b0 = 0; b0 < B; b0 += chunk) {
-                const int g0 = b0 / D3_CG;
-                Decode3Params q{};
-                q.d = dp;
-                q.d.B = std::min(chunk, B - b0);
-                q.d.S = S3 + (size_t)g0 * 1024 * D3_CG; q.d.Cst = dp.Cst + (size_t)g0 * 1024 * D3_CG;
-                q.d.P1 = dp.P1 + (size_t)g0 * 256 * D3_CG; q.d.XD = dp.XD + (size_t)g0 * 1024 * D3_CG;
-                q.d.Q = dp.Q + (size_t)b0 * 512; q.d.CQ = dp.CQ + (size_t)b0 * 256;
-                q.d.Kmem = Kmem + (size_t)b0 * T * 512; q.d.Vmem = Vmem + (size_t)b0 * T * 512;
-                q.d.ckey = ckey + (size_t)b0 * minT * 256; q.d.cval = cval + (size_t)b0 * minT * 256;
-                q.d.stop_const = stopc + b0;
-                q.d.outputs = outputs + (size_t)b0 * steps * 80; q.d.lengths = dp.lengths + b0;
-                if (attn) q.d.attn = attn + (size_t)b0 * steps * T;
-                if (dp.p1_teacher) q.d.p1_teacher = dp.p1_teacher + b0;
-                if (dp.stop_out) q.d.stop_out = dp.stop_out + (size_t)b0 * steps;
-                if (dp.attn_logits) q.d.attn_logits = dp.attn_logits + (size_t)b0 * steps * T;
-                if (b0) L2S_CUDA(cudaMemsetAsync(bar, 0, 4, s));
-                q.Vsplit = vsplit + (size_t)b0 * T * 512; q.cvsplit = cvsplit + (size_t)b0 * minT * 256;
-                q.kv_smem = (size_t)(512 + 320 + 256 + 32) + (size_t)2 * (T * 768 + minT * 384) <= (size_t)c.meta.at("d.step3.wimg_floats") ? 1 : 0;
-                q.passes = reinterpret_cast<const Dec3Pass*>(c.dev("d.step3.passes"));
-                q.role = reinterpret_cast<const int*>(c.dev("d.step3.role"));
-                q.job = reinterpret_cast<const int*>(c.dev("d.step3.job"));
-                q.wimg = c.dev("d.step3.wimg"); q.wimg_floats = (int)c.meta.at("d.step3.wimg_floats");
-                q.timing = c.profiling ? c.fbuf("ws.d.timing3", (size_t)c.num_sms * D3_TIMING_SLOTS) : nullptr;
-                void* args[] = {&q};
-                L2S_CUDA(cudaLaunchCooperativeKernel((void*)decode3_kernel, dim3(c.num_sms), dim3(MV_THREADS), args, smem, s));
-                c.launches++;
-            }
-            c.span_end("decode_loop", s);
-        }
-#ifdef L2S_DEBUG
-        else {
-            const size_t smem = (size_t)c.meta.at("d.step.smem");
-            L2S_CUDA(cudaFuncSetAttribute(decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            void* args[] = {&dp};
-            c.span_begin("decode_loop", s);
-            L2S_CUDA(cudaLaunchCooperativeKernel((void*)decode_persistent_kernel, dim3(c.num_sms), dim3(MV_THREADS), args, smem, s));
-            c.span_end("decode_loop", s);
+        c.span_begin("decode_loop", s);
+        // The kernel decodes up to 32 clips per launch; larger batches run in consecutive 32-clip chunks (pre-loop and
+        // postnet stay whole-batch GEMMs).  A chunk sees its own clips through shifted pointers; the group-major planes keep
+        // the whole batch's stride (Bpad).
+        for (int b0 = 0; b0 < B; b0 += chunk) {
+            const int g0 = b0 / D3_CG;
+            Decode3Params q{};
+            q.d = dp;
+            q.d.B = std::min(chunk, B - b0);
+            q.S = xS + (size_t)g0 * 1024 * D3_CG; q.Cst = xC + (size_t)g0 * 1024 * D3_CG;
+            q.P1 = xP1 + (size_t)g0 * 256 * D3_CG; q.XD = xXD + (size_t)g0 * 1024 * D3_CG;
+            q.Q = xQ + (size_t)b0 * 512; q.CQ = xCQ + (size_t)b0 * 256;
+            q.tag_base = tag_base; q.abort_word = abortw;
+            q.d.Kmem = Kmem + (size_t)b0 * T * 512; q.d.Vmem = Vmem + (size_t)b0 * T * 512;
+            q.d.ckey = ckey + (size_t)b0 * minT * 256; q.d.cval = cval + (size_t)b0 * minT * 256;
+            q.d.stop_const = stopc + b0;
+            q.d.outputs = outputs + (size_t)b0 * steps * 80; q.d.lengths = reinterpret_cast<long long*>(lengths) + b0;
+            q.d.attn = attn ? attn + (size_t)b0 * steps * T : nullptr;
+            q.d.tf_mask = tfm; q.d.p1_teacher = p1t ? p1t + b0 : nullptr;
+            q.d.stop_out = fw.out_stop ? fw.out_stop + (size_t)b0 * steps : nullptr;
+            q.d.attn_logits = fw.out_attn_logits ? fw.out_attn_logits + (size_t)b0 * steps * T : nullptr;
+            q.Vsplit = vsplit + (size_t)b0 * T * 512; q.cvsplit = cvsplit + (size_t)b0 * minT * 256;
+            q.kv_smem = (size_t)(512 + 320 + 256 + 32) + (size_t)2 * (T * 768 + minT * 384) <= (size_t)c.meta.at("d.step3.wimg_floats") ? 1 : 0;
+            q.passes = reinterpret_cast<const Dec3Pass*>(c.dev("d.step3.passes"));
+            q.role = reinterpret_cast<const int*>(c.dev("d.step3.role"));
+            q.job = reinterpret_cast<const int*>(c.dev("d.step3.job"));
+            q.wimg = c.dev("d.step3.wimg"); q.wimg_floats = (int)c.meta.at("d.step3.wimg_floats");
+            q.timing = c.profiling ? c.fbuf("ws.d.timing3", (size_t)c.num_sms * D3_TIMING_SLOTS) : nullptr;
+            void* args[] = {&q};
+            L2S_CUDA(cudaLaunchCooperativeKernel((void*)decode3_kernel, dim3(c.num_sms), dim3(MV_THREADS), args, smem, s));
             c.launches++;
         }
-#endif
+        c.span_end("decode_loop", s);
     }
     c.span_begin("postnet", s);
     // ---- postnet + residual (decoder.py:437-439) --------------------------------------------------
@@ -927,7 +905,6 @@ int l2s_create(l2s_ctx** out, int device) {
     ctx->c.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
 #ifdef L2S_DEBUG
     if (const char* e = getenv("L2S_TC")) ctx->c.use_tc = (e[0] != '0');
-    if (const char* e = getenv("L2S_DEC3")) ctx->c.use_dec3 = (e[0] != '0');
     if (const char* e = getenv("L2S_PW")) ctx->c.use_pw = (e[0] != '0');
     if (const char* e = getenv("L2S_PW_MIN_ROWS")) ctx->c.pw_min_rows = std::max(1, atoi(e));
 #endif
@@ -1311,6 +1288,14 @@ int64_t l2s_debug_read(l2s_ctx* ctx, const char* name, float* out, int64_t n) {
     if (!ctx || !name) return -1;
     Context& c = ctx->c;
     auto get = [&](const char* k) { auto it = c.meta.find(k); return it == c.meta.end() ? (int64_t)0 : it->second; };
+    if (std::strcmp(name, "flag.dec_abort") == 0) {          // 1: a wait inside the decode kernel gave up (decode3.cuh: LLWait) — results invalid
+        auto it = c.bufs.find("ws.d.abort");
+        if (it == c.bufs.end() || !it->second.p) return 0;
+        unsigned v = 0;
+        cudaSetDevice(c.device); cudaDeviceSynchronize();
+        cudaMemcpy(&v, it->second.p, sizeof(v), cudaMemcpyDeviceToHost);
+        return (int64_t)v;
+    }
     if (std::strncmp(name, "flag.", 5) == 0) return get((std::string("dbg.") + (name + 5)).c_str());
     const int64_t B = get("dbg.B"), T = get("dbg.T"), minT = get("dbg.minT"), steps = get("dbg.steps");
     struct { const char* name; const char* buf; int64_t count; } tab[] = {
@@ -1318,7 +1303,6 @@ int64_t l2s_debug_read(l2s_ctx* ctx, const char* name, float* out, int64_t n) {
         {"dec.enc", "ws.d.enc", B * T * 512}, {"dec.rnn_out", "ws.d.rnnout", B * T * 1024},
         {"dec.ckey", "ws.d.ckey", B * minT * 256}, {"dec.cval", "ws.d.cval", B * minT * 256},
         {"dec.outputs", "ws.d.outputs", B * steps * 80}, {"dec.clog", "ws.d.clog", B * minT * 501},
-        {"dec.timing", "ws.d.timing", (int64_t)c.num_sms * DEC_TIMING_SLOTS},
         {"dec.timing3", "ws.d.timing3", (int64_t)c.num_sms * D3_TIMING_SLOTS},
     };
     for (auto& t : tab) {

@@ -52,10 +52,9 @@ struct Context {
 #ifdef L2S_DEBUG
     // debug builds only (nvcc -DL2S_DEBUG): environment toggles that swap kernels for bisecting; a release library has ONE path
     bool use_pw = true;                       // L2S_PW=0: tcgen05 GEMM instead of the streaming mma.sync kernel for the trunk's 1x1 convolutions
-    bool use_dec3 = true;                     // L2S_DEC3=0: row-partitioned decode kernel for every B
     bool use_tc = true;                       // L2S_TC=0: exact-fp32 SIMT GEMMs
 #else
-    static constexpr bool use_pw = true, use_dec3 = true, use_tc = true;
+    static constexpr bool use_pw = true, use_tc = true;
 #endif
     // optional stage timing (CUDA events on the caller's stream), enabled by l2s_set_profiling
     bool profiling = false;

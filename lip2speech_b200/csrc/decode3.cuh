@@ -20,7 +20,9 @@
 //    read from shared memory once per turn;
 //  * the attention SMs hold no weights: they keep the encoder keys/values of the clip they serve in shared memory,
 //    double-buffered (the next turn's clip is fetched by the TMA engine, cp.async.bulk, while the current one is attended);
-//  * one grid barrier per turn (four per step, as before), split-phase with the same early/late segments.
+//  * NO grid barrier: every exchanged activation is a {value, turn tag} word that consumers poll (the LL protocol of
+//    collective libraries): release fence + barrier counter + acquire poll + data load collapse into one L2 round trip;
+//    write-after-read safety follows from the ring dependency B -> D -> E -> A -> B of a clip group.
 // Recurrent state is GROUP-MAJOR ([group][feature][8 clips], see matvec.cuh: mv8_accumulate); queries are clip-major.
 // Outputs do not depend on which other clips share the batch (each clip's columns are independent in the MMA).
 #pragma once
@@ -33,7 +35,9 @@ constexpr int D3_ROWS = 16 * D3_MAXRT;
 constexpr int D3_CG = 8;              // clips per group
 constexpr int D3_NG = 4;              // clip groups == pipeline stages
 constexpr int D3_NSPLIT = 2;          // attention CTAs per clip (each: all scores, half of the context features)
-constexpr int D3_TIMING_SLOTS = 6;    // early compute, barrier wait, late accumulate, reduce + epilogue / attention, idle turns, arrive
+constexpr int D3_TIMING_SLOTS = 6;    // early MMAs, wait for the late activations, late MMAs, reduce + epilogue / attention, (unused), idle turns
+constexpr int D3_TAG_BIAS = 8;        // tag = tag_base + turn + D3_TAG_BIAS (the prologue and the initial state have negative turns)
+constexpr int D3_TAG_SPAN = 4096;     // tags of one launch live in [tag_base, tag_base + D3_TAG_SPAN)
 
 enum D3Role { ROLE_B = 0, ROLE_D = 1, ROLE_E = 2, ROLE_A = 3 };
 
@@ -50,9 +54,50 @@ struct Dec3Pass {
     float aux2[D3_ROWS];
 };
 
+// ---- the exchange: flag-carrying words ---------------------------------------------------------------------------------
+// Every activation that crosses CTAs is a 64-bit word {fp32 value, 32-bit tag}; tag = the pipeline turn that produced it (+ a
+// per-launch base).  A producer stores the word with ONE 8-byte store; a consumer loads the word and knows from the tag whether
+// it holds this turn's value — no release fence, no barrier counter, no second round trip: data and "ready" travel together
+// (the LL protocol of collective libraries).  Scalar 64-bit accesses are single-copy atomic in the PTX memory model.
+typedef unsigned long long ll_t;
+
+__device__ __forceinline__ void ll_store(ll_t* p, float v, uint32_t tag) {
+    const ll_t w = ((ll_t)tag << 32) | (ll_t)__float_as_uint(v);
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ ll_t ll_load(const ll_t* p) {
+    ll_t w;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+    return w;
+}
+__device__ __forceinline__ uint32_t ll_tag(ll_t w) { return (uint32_t)(w >> 32); }
+__device__ __forceinline__ float ll_val(ll_t w) { return __uint_as_float((uint32_t)w); }
+
+// Spin bookkeeping: a wait that lasts absurdly long (a bug, never a legal schedule: a turn takes microseconds) raises the
+// launch-wide abort word, and every thread that sees it stops waiting for the rest of the launch, so the kernel always
+// terminates (results are then garbage and `abort` tells the host).
+struct LLWait {
+    unsigned* abort_word;
+    bool dead;
+    __device__ __forceinline__ bool give_up(unsigned& spins) {
+        if ((++spins & 1023u) == 0u) {
+            if (spins > (1u << 19)) atomicExch(abort_word, 1u);
+            if (*reinterpret_cast<volatile unsigned*>(abort_word) != 0u) dead = true;
+        }
+        return dead;
+    }
+};
+
 struct Decode3Params {
-    DecodeParams d;               // sizes, attention memories, outputs; d.S / d.Cst / d.P1 / d.XD are group-major here,
-                                  // d.Q [B][512] and d.CQ [B][256] clip-major (d.passes / d.npasses / d.wimg unused)
+    DecodeParams d;               // sizes, attention memories, outputs (d.S / d.Cst / d.P1 / d.XD / d.Q / d.CQ / d.barrier unused here)
+    ll_t* S;                      // [2 parity][groups][1024][8]   h0 rows 0..511, h1 rows 512..1023     (group-major, see matvec.cuh)
+    ll_t* Cst;                    // [groups][1024][8]             c0, c1
+    ll_t* P1;                     // [groups][256][8]              prenet layer 1
+    ll_t* XD;                     // [groups][1024][8]             content value (0..255), prenet-2 (256..511), attention context (512..1023)
+    ll_t* Q;                      // [clips][512]                  attention queries (clip-major)
+    ll_t* CQ;                     // [clips][256]                  content queries
+    uint32_t tag_base;
+    unsigned* abort_word;
     const Dec3Pass* passes;       // [grid]  (R == 0: no pass)
     const int* role;              // [grid] D3Role
     const int* job;               // [grid] attention job inside a clip group (clip*D3_NSPLIT + part) or -1
@@ -64,63 +109,121 @@ struct Decode3Params {
     float* timing;                // optional [grid][D3_TIMING_SLOTS]
 };
 
-// group-major addressing: buffer of `rows` features, clip group g
-__device__ __forceinline__ float* d3_group(float* buf, int rows, int g) { return buf + (size_t)g * rows * D3_CG; }
+// Which stage wrote a source, and how many turns before the reader's turn (same clip group).
+__device__ __forceinline__ int d3_producer(int src) {
+    switch (src) {
+        case SRC_H0NEW: case SRC_H0OLD: case SRC_C0: return ROLE_D;
+        case SRC_H1NEW: case SRC_H1OLD: case SRC_C1: return ROLE_E;
+        case SRC_P1: return ROLE_A;
+        default: return ROLE_B;       // SRC_XD
+    }
+}
+__device__ __forceinline__ uint32_t d3_src_tag(const Decode3Params& q, int src, int role, int turn) {
+    int delta = (role - d3_producer(src)) & 3;
+    if (delta == 0) delta = 4;                               // own stage's output of the previous step
+    return q.tag_base + (uint32_t)(turn - delta + D3_TAG_BIAS);
+}
 
-__device__ __forceinline__ const float* d3_src(const DecodeParams& p, int src, int parity_new, int g) {
-    const size_t plane = (size_t)1024 * p.Bpad;
-    const float* Snew = p.S + (size_t)parity_new * plane + (size_t)g * 1024 * D3_CG;
-    const float* Sold = p.S + (size_t)(parity_new ^ 1) * plane + (size_t)g * 1024 * D3_CG;
+__device__ __forceinline__ const ll_t* d3_src(const Decode3Params& q, int src, int parity_new, int g) {
+    const size_t plane = (size_t)1024 * q.d.Bpad;
+    const ll_t* Snew = q.S + (size_t)parity_new * plane + (size_t)g * 1024 * D3_CG;
+    const ll_t* Sold = q.S + (size_t)(parity_new ^ 1) * plane + (size_t)g * 1024 * D3_CG;
     switch (src) {
         case SRC_H0NEW: return Snew;
         case SRC_H1NEW: return Snew + 512 * D3_CG;
-        case SRC_C0: return p.Cst + (size_t)g * 1024 * D3_CG;
-        case SRC_C1: return p.Cst + (size_t)g * 1024 * D3_CG + 512 * D3_CG;
-        case SRC_P1: return p.P1 + (size_t)g * 256 * D3_CG;
-        case SRC_XD: return p.XD + (size_t)g * 1024 * D3_CG;
+        case SRC_C0: return q.Cst + (size_t)g * 1024 * D3_CG;
+        case SRC_C1: return q.Cst + (size_t)g * 1024 * D3_CG + 512 * D3_CG;
+        case SRC_P1: return q.P1 + (size_t)g * 256 * D3_CG;
+        case SRC_XD: return q.XD + (size_t)g * 1024 * D3_CG;
         case SRC_H0OLD: return Sold;
         case SRC_H1OLD: return Sold + 512 * D3_CG;
         default: return nullptr;
     }
 }
 
+// Requests the chunks of one segment that this warp owns (see mv8_load) as tagged words.
+template <int DEPTH>
+__device__ __forceinline__ void d3_request(const ll_t* __restrict__ X, int K, ll_t (&w)[DEPTH][4]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int npw = K / (MV_KC * MV_WARPS);
+    const ll_t* xp = X + (size_t)(warp * MV_KC + t) * 8 + g;
+    constexpr int xstride = MV_WARPS * MV_KC * 8;
+#pragma unroll
+    for (int d = 0; d < DEPTH; ++d)
+        if (d < npw) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) w[d][i] = ll_load(xp + d * xstride + i * 32);
+        }
+}
+// Waits until every requested word carries `tag` (re-requesting the ones that do not yet) and unpacks the values.
+template <int DEPTH>
+__device__ __forceinline__ void d3_collect(const ll_t* __restrict__ X, int K, uint32_t tag, ll_t (&w)[DEPTH][4], float (&x)[DEPTH][4], LLWait& lw) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int npw = K / (MV_KC * MV_WARPS);
+    const ll_t* xp = X + (size_t)(warp * MV_KC + t) * 8 + g;
+    constexpr int xstride = MV_WARPS * MV_KC * 8;
+    unsigned spins = 0;
+    bool again = !lw.dead;
+    while (again) {
+        again = false;
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d)
+            if (d < npw) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (ll_tag(w[d][i]) != tag) { w[d][i] = ll_load(xp + d * xstride + i * 32); again = true; }
+            }
+        if (again && lw.give_up(spins)) break;
+    }
+#pragma unroll
+    for (int d = 0; d < DEPTH; ++d)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[d][i] = ll_val(w[d][i]);
+}
+
 // Per-row epilogue of reduction round `round` (rows 48*round .. 48*round+47) for clip group g; threads tid < 384.
-__device__ __forceinline__ void d3_epilogue(const DecodeParams& p, const Dec3Pass& ps, const DecSmem& sm, float v, float c_prev,
-                                            int round, int g, int step, int parity_new) {
+// Exchanged outputs are written for all 8 clip slots of the group (padding clips included: consumers wait for every
+// word); only the caller-visible outputs are masked by b < B.
+__device__ __forceinline__ void d3_epilogue(const Decode3Params& q, const Dec3Pass& ps, const DecSmem& sm, float v, float c_prev,
+                                            int round, int g, int step, int parity_new, uint32_t tag) {
+    const DecodeParams& p = q.d;
     const int tid = threadIdx.x;
     const int r = 16 * MV8_RTILES * round + (tid >> 3), bb = tid & 7, b = g * D3_CG + bb;
-    const bool live = (tid < 128 * MV8_RTILES) && (r < ps.R) && (b < p.B);
+    const bool rowlive = (tid < 128 * MV8_RTILES) && (r < ps.R);
+    const bool real = b < p.B;
     const bool gate_pass = (ps.op[0] == OP_GATE0 || ps.op[0] == OP_GATE1);      // CTA-uniform
-    const int op = live ? ps.op[r] : OP_NONE;
-    const int idx = live ? ps.idx[r] : 0;
-    if (live) v += ps.bias[r];
+    const int op = rowlive ? ps.op[r] : OP_NONE;
+    const int idx = rowlive ? ps.idx[r] : 0;
+    if (rowlive) v += ps.bias[r];
     switch (op) {
         case OP_FC:
-            if (step >= 0) p.outputs[((size_t)b * p.steps + step) * 80 + idx] = v;
+            if (step >= 0 && real) p.outputs[((size_t)b * p.steps + step) * 80 + idx] = v;
             break;
         case OP_P1: {
             float p1 = (step >= 0) ? sinf(v) * ps.aux[r] : ps.aux2[r];
             if (p.tf_mask && step + 1 < p.steps && p.tf_mask[step + 1])      // next step is teacher-forced
                 p1 = p.p1_teacher[((size_t)(step + 1) * 256 + idx) * p.Bpad + b];
-            d3_group(p.P1, 256, g)[idx * D3_CG + bb] = p1;
+            ll_store(q.P1 + ((size_t)g * 256 + idx) * D3_CG + bb, p1, tag);
         } break;
         case OP_STOP:
-            if (step >= 0) {
+            if (step >= 0 && real) {
                 const float logit = v + p.stop_const[b];
                 if (p.stop_out) p.stop_out[(size_t)b * p.steps + step] = logit;
                 if (logit > 0.f && p.lengths[b] == (long long)p.steps) p.lengths[b] = step + 1;
             }
             break;
         case OP_Q: {
-            float q = sinf(v) * ps.aux[r];
-            if (step + 1 < p.steps) q += __ldg(p.pos + (size_t)(step + 1) * 512 + idx);
-            p.Q[(size_t)b * 512 + idx] = q;
+            float qv = sinf(v) * ps.aux[r];
+            if (step + 1 < p.steps) qv += __ldg(p.pos + (size_t)(step + 1) * 512 + idx);
+            ll_store(q.Q + (size_t)b * 512 + idx, qv, tag);
         } break;
         case OP_CQ:
-            p.CQ[(size_t)b * 256 + idx] = siluf_acc(v);
+            ll_store(q.CQ + (size_t)b * 256 + idx, siluf_acc(v), tag);
             break;
         case OP_P2:
-            d3_group(p.XD, 1024, g)[(256 + idx) * D3_CG + bb] = sinf(v) * ps.aux[r];
+            ll_store(q.XD + ((size_t)g * 1024 + 256 + idx) * D3_CG + bb, sinf(v) * ps.aux[r], tag);
             break;
         default: break;
     }
@@ -128,14 +231,14 @@ __device__ __forceinline__ void d3_epilogue(const DecodeParams& p, const Dec3Pas
         // every thread applies its own gate non-linearity (i, f, o: sigmoid; g: tanh), the gate-0 thread combines
         if (tid < 128 * MV8_RTILES) sm.gsm[tid] = ((r & 3) == 2) ? tanhf(v) : sigmoidf_acc(v);
         __syncthreads();
-        if (live && (r & 3) == 0 && idx >= 0) {
+        if (rowlive && (r & 3) == 0 && idx >= 0) {
             const int layer = (op == OP_GATE1) ? 1 : 0;
             const float gi = sm.gsm[tid], gf = sm.gsm[tid + 8], gg = sm.gsm[tid + 16], go = sm.gsm[tid + 24];
             const size_t si = (size_t)g * 1024 * D3_CG + (size_t)(layer * 512 + idx) * D3_CG + bb;
             const float c = gf * c_prev + gi * gg;
             const float h = go * tanhf(c);
-            p.Cst[si] = c;
-            (p.S + (size_t)parity_new * 1024 * p.Bpad)[si] = h;
+            ll_store(q.Cst + si, c, tag);
+            ll_store(q.S + (size_t)parity_new * 1024 * p.Bpad + si, h, tag);
         }
     }
 }
@@ -143,9 +246,10 @@ __device__ __forceinline__ void d3_epilogue(const DecodeParams& p, const Dec3Pas
 constexpr int D3_EDEPTH = 2;          // chunks per warp of an early segment (Ke <= 512)
 
 // What this CTA's stage does in a given turn of the software pipeline.
-struct D3Slot { int g, step; bool active; };
+struct D3Slot { int g, step, turn; bool active; };
 __device__ __forceinline__ D3Slot d3_slot(int turn, int role, int steps, int B) {
     D3Slot s;
+    s.turn = turn;
     s.g = (turn - role) & (D3_NG - 1);                       // clip group served by this stage in this turn
     const int u = turn - s.g;                                // stages completed by that group (u % 4 == role)
     s.step = u >> 2;
@@ -153,50 +257,68 @@ __device__ __forceinline__ D3Slot d3_slot(int turn, int role, int steps, int B) 
     return s;
 }
 
-// The pass of this CTA for one (clip group, step): early segment, barrier wait, late segment, reduction + epilogue.
-// xe: the early segment's activations.  They are at least two turns old when they are used, so they are requested one
-// turn ahead (right after the late MMAs of the previous turn were issued): `xe_valid` says whether that happened; on
-// return xe holds the early activations of `next` (if next.active) and xe_valid is updated.
+struct D3Timing {
+    float* tacc; long long tmark; bool on;
+    __device__ __forceinline__ void lap(int slot) {
+        if (on && threadIdx.x == 0) { long long now = clock64(); tacc[slot] += (float)(now - tmark); tmark = now; }
+    }
+};
+
+// The pass of this CTA for one (clip group, step): early segment (operands at least two turns old), late segment (the
+// previous stage's output of the previous turn), reduction + epilogue.
+// xe: the early segment's words.  They are requested one turn ahead (right after the late MMAs of the previous turn were
+// issued): `xe_valid` says whether that happened; on return xe holds the request for `next` (if next.active).
 template <int RT, bool EARLY>
-__device__ __forceinline__ void d3_turn(const DecodeParams& p, const Dec3Pass& ps, const DecSmem& sm, StageSync& sync,
-                                        int g, int step, int parity_new, float (&xe)[D3_EDEPTH][4], bool& xe_valid, const D3Slot& next) {
+__device__ __forceinline__ void d3_turn(const Decode3Params& q, const Dec3Pass& ps, const DecSmem& sm, D3Timing& tm, LLWait& lw, int role,
+                                        int g, int step, int turn, int parity_new, ll_t (&xe)[D3_EDEPTH][4], bool& xe_valid, const D3Slot& next) {
     constexpr int ROUNDS = (RT + MV8_RTILES - 1) / MV8_RTILES;
+    const DecodeParams& p = q.d;
     const int tid = threadIdx.x;
     const bool gate_pass = (ps.op[0] == OP_GATE0 || ps.op[0] == OP_GATE1);
-    // own cell state (written by this very CTA four turns ago): requested first, consumed in the epilogue
+    const uint32_t tag = q.tag_base + (uint32_t)(turn + D3_TAG_BIAS);
+    // the late request goes out first: it is the one the turn waits for
+    const ll_t* Xl = d3_src(q, ps.src_l, parity_new, g);
+    ll_t wl[MV8_DEPTH][4];
+    d3_request<MV8_DEPTH>(Xl, ps.Kl, wl);
+    // own cell state (written by this very thread four turns ago): consumed in the epilogue
     float c_prev[ROUNDS];
 #pragma unroll
     for (int round = 0; round < ROUNDS; ++round) {
-        const int r = 16 * MV8_RTILES * round + (tid >> 3), b = g * D3_CG + (tid & 7);
+        const int r = 16 * MV8_RTILES * round + (tid >> 3);
         c_prev[round] = 0.f;
-        if (gate_pass && tid < 128 * MV8_RTILES && (r & 3) == 0 && r < ps.R && b < p.B)
-            c_prev[round] = __ldcg(p.Cst + (size_t)g * 1024 * D3_CG + (size_t)((ps.op[0] == OP_GATE1 ? 512 : 0) + ps.idx[r]) * D3_CG + (tid & 7));
+        if (gate_pass && tid < 128 * MV8_RTILES && (r & 3) == 0 && r < ps.R)
+            c_prev[round] = ll_val(ll_load(q.Cst + (size_t)g * 1024 * D3_CG + (size_t)((ps.op[0] == OP_GATE1 ? 512 : 0) + ps.idx[r]) * D3_CG + (tid & 7)));
     }
     float acc[RT][4];
     mv8_zero<RT>(acc);
     if (EARLY) {
-        if (!xe_valid) mv8_load<D3_EDEPTH>(d3_src(p, ps.src_e, parity_new, g), ps.Ke, xe);
-        mv8_mma<RT, D3_EDEPTH>(sm.wsm, ps.ldw, ps.wcol_e, ps.R, ps.Ke, xe, acc);
+        const ll_t* Xe = d3_src(q, ps.src_e, parity_new, g);
+        if (!xe_valid) d3_request<D3_EDEPTH>(Xe, ps.Ke, xe);
+        float xv[D3_EDEPTH][4];
+        d3_collect<D3_EDEPTH>(Xe, ps.Ke, d3_src_tag(q, ps.src_e, role, turn), xe, xv, lw);
+        mv8_mma<RT, D3_EDEPTH>(sm.wsm, ps.ldw, ps.wcol_e, ps.R, ps.Ke, xv, acc);
     }
-    sync.wait();
+    tm.lap(0);
     {
         float xl[MV8_DEPTH][4];
-        mv8_load<MV8_DEPTH>(d3_src(p, ps.src_l, parity_new, g), ps.Kl, xl);
+        d3_collect<MV8_DEPTH>(Xl, ps.Kl, d3_src_tag(q, ps.src_l, role, turn), wl, xl, lw);
+        tm.lap(1);
         mv8_mma<RT, MV8_DEPTH>(sm.wsm, ps.ldw, ps.wcol_l, ps.R, ps.Kl, xl, acc);
     }
     if (EARLY) {
         xe_valid = next.active;
-        if (next.active) mv8_load<D3_EDEPTH>(d3_src(p, ps.src_e, (next.step + 1) & 1, next.g), ps.Ke, xe);
+        if (next.active) d3_request<D3_EDEPTH>(d3_src(q, ps.src_e, (next.step + 1) & 1, next.g), ps.Ke, xe);
     }
-    sync.lap(2);
+    tm.lap(2);
 #pragma unroll
     for (int round = 0; round < ROUNDS; ++round) {
         if (16 * MV8_RTILES * round < ps.R) {
             const float v = mv8_reduce_round<RT>(acc, round, sm.red);
-            d3_epilogue(p, ps, sm, v, c_prev[round], round, g, step, parity_new);
+            d3_epilogue(q, ps, sm, v, c_prev[round], round, g, step, parity_new, tag);
             __syncthreads();
         }
     }
+    tm.lap(3);
 }
 
 // ---- attention CTAs ------------------------------------------------------------------------------------------------
@@ -220,17 +342,35 @@ __device__ __forceinline__ void d3_prefetch_kv(const Decode3Params& q, float* bu
     bulk_load_1d(cvb, q.cvsplit + ((size_t)b * 2 + part) * p.minT * 128, (uint32_t)p.minT * 512u, bar);
 }
 
-// Dot-product attention over the T encoder positions and over the minT content slots for clip b (reference
-// decoder.py:414-419 and Content.forward 262-271).  Both CTAs of a clip compute all scores; CTA `part` produces context
-// features [256*part, 256*part+256) and content-value features [128*part, 128*part+128).
+// Dot-product attention over the T encoder positions and over the minT content slots for the clip in slot `b` of the batch
+// (reference decoder.py:414-419 and Content.forward 262-271); `bsrc` = the clip whose keys/values are used (b itself, or
+// the last real clip for a padding slot).  Both CTAs of a clip compute all scores; CTA `part` produces context features
+// [256*part, 256*part+256) and content-value features [128*part, 128*part+128).
 // Kb: [T][512]; Vb: this CTA's 256 features of row 0, row stride vstride; ck: content keys [minT][256]; cv: this CTA's
 // 128 content-value features of slot 0, slot stride cvstride (all four in shared memory or all in global memory).
-__device__ void d3_attend(const DecodeParams& p, const DecSmem& sm, const float* Kb, const float* Vb, int vstride,
-                          const float* ck, const float* cv, int cvstride, int b, int part, int step) {
+// Three CTA barriers: queries in shared memory | scores | (softmax recomputed by every warp) context + stores.
+__device__ void d3_attend(const Decode3Params& q, const DecSmem& sm, const float* Kb, const float* Vb, int vstride,
+                          const float* ck, const float* cv, int cvstride, int b, int part, int step, int turn, LLWait& lw, D3Timing& tm) {
+    const DecodeParams& p = q.d;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = b / D3_CG, bb = b % D3_CG;
-    sm.qs[tid] = ldcg1(p.Q + (size_t)b * 512 + tid) * p.temp;
-    if (tid < 256) sm.cqs[tid] = ldcg1(p.CQ + (size_t)b * 256 + tid) * p.ctemp;
+    const bool real = b < p.B;
+    const uint32_t tag_in = q.tag_base + (uint32_t)(turn - 1 + D3_TAG_BIAS);      // stage A wrote the queries one turn ago
+    const uint32_t tag = q.tag_base + (uint32_t)(turn + D3_TAG_BIAS);
+    {
+        const ll_t* qp = q.Q + (size_t)b * 512 + tid;
+        const ll_t* cp = q.CQ + (size_t)b * 256 + (tid & 255);
+        ll_t wq = ll_load(qp), wc = ll_load(cp);
+        unsigned spins = 0;
+        while (!lw.dead && (ll_tag(wq) != tag_in || ll_tag(wc) != tag_in)) {
+            if (ll_tag(wq) != tag_in) wq = ll_load(qp);
+            if (ll_tag(wc) != tag_in) wc = ll_load(cp);
+            if (lw.give_up(spins)) break;
+        }
+        sm.qs[tid] = ll_val(wq) * p.temp;
+        if (tid < 256) sm.cqs[tid] = ll_val(wc) * p.ctemp;
+    }
+    tm.lap(1);
     __syncthreads();
     for (int t = warp; t < p.T; t += MV_WARPS) {
         const float4* kr = reinterpret_cast<const float4*>(Kb + (size_t)t * 512);
@@ -238,8 +378,8 @@ __device__ void d3_attend(const DecodeParams& p, const DecSmem& sm, const float*
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const float4 k = kr[lane + 32 * i];
-            const float4 q = *reinterpret_cast<const float4*>(sm.qs + 4 * (lane + 32 * i));
-            a = fmaf(q.x, k.x, a); a = fmaf(q.y, k.y, a); a = fmaf(q.z, k.z, a); a = fmaf(q.w, k.w, a);
+            const float4 qv = *reinterpret_cast<const float4*>(sm.qs + 4 * (lane + 32 * i));
+            a = fmaf(qv.x, k.x, a); a = fmaf(qv.y, k.y, a); a = fmaf(qv.z, k.z, a); a = fmaf(qv.w, k.w, a);
         }
         a = warp_sum(a);
         if (lane == 0) sm.sc[t] = a;
@@ -250,82 +390,72 @@ __device__ void d3_attend(const DecodeParams& p, const DecSmem& sm, const float*
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
             const float4 k = kr[lane + 32 * i];
-            const float4 q = *reinterpret_cast<const float4*>(sm.cqs + 4 * (lane + 32 * i));
-            a = fmaf(q.x, k.x, a); a = fmaf(q.y, k.y, a); a = fmaf(q.z, k.z, a); a = fmaf(q.w, k.w, a);
+            const float4 qv = *reinterpret_cast<const float4*>(sm.cqs + 4 * (lane + 32 * i));
+            a = fmaf(qv.x, k.x, a); a = fmaf(qv.y, k.y, a); a = fmaf(qv.z, k.z, a); a = fmaf(qv.w, k.w, a);
         }
         a = warp_sum(a);
         if (lane == 0) sm.csc[m] = a;
     }
     __syncthreads();
-    if (warp == 0) {
-        if (p.attn_logits && part == 0)
-            for (int t = lane; t < p.T; t += 32) p.attn_logits[((size_t)b * p.steps + step) * p.T + t] = sm.sc[t];
+    ll_t* xd = q.XD + (size_t)g * 1024 * D3_CG;
+    if (warp < 8 || warp == 12) {
+        // softmax over the T positions, recomputed by every warp that needs it (same instructions, same order: identical bits)
         float mx = -INFINITY;
         for (int t = lane; t < p.T; t += 32) mx = fmaxf(mx, sm.sc[t]);
         mx = warp_max(mx);
         float sum = 0.f;
-        for (int t = lane; t < p.T; t += 32) { float e = expf(sm.sc[t] - mx); sm.sc[t] = e; sum += e; }
+        for (int t = lane; t < p.T; t += 32) sum += expf(sm.sc[t] - mx);
         sum = warp_sum(sum);
-        for (int t = lane; t < p.T; t += 32) {
-            float a = sm.sc[t] / sum;
-            sm.sc[t] = a;
-            if (p.attn && part == 0) p.attn[((size_t)b * p.steps + step) * p.T + t] = a;
+        if (warp == 12) {                                    // the caller-visible maps (one CTA of the pair writes them)
+            if (part == 0 && real) {
+                for (int t = lane; t < p.T; t += 32) {
+                    if (p.attn_logits) p.attn_logits[((size_t)b * p.steps + step) * p.T + t] = sm.sc[t];
+                    if (p.attn) p.attn[((size_t)b * p.steps + step) * p.T + t] = expf(sm.sc[t] - mx) / sum;
+                }
+            }
+        } else {
+            // context feature f = tid (256 per CTA): positions in ascending order, weights broadcast lane by lane
+            const float* vcol = Vb + tid;
+            float acc = 0.f;
+            for (int t0 = 0; t0 < p.T; t0 += 32) {
+                const int n = min(32, p.T - t0);
+                const float mine = (lane < n) ? expf(sm.sc[t0 + lane] - mx) / sum : 0.f;
+                for (int j = 0; j < n; ++j) acc = fmaf(__shfl_sync(0xffffffffu, mine, j), vcol[(size_t)(t0 + j) * vstride], acc);
+            }
+            ll_store(xd + (size_t)(512 + part * 256 + tid) * D3_CG + bb, acc, tag);
         }
-    } else if (warp == 1) {
-        float v = lane < p.minT ? sm.csc[lane] : -INFINITY;
-        float mx = warp_max(v);
-        float e = lane < p.minT ? expf(v - mx) : 0.f;
-        float sum = warp_sum(e);
-        if (lane < p.minT) sm.csc[lane] = e / sum;
-    }
-    __syncthreads();
-    // context: thread (fq = tid&63: 4 features, tg = tid>>6: every 8th position) -> partial sums, combined in a fixed order
-    {
-        const int fq = tid & 63, tg = tid >> 6;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int t = tg; t < p.T; t += 8) {
-            const float4 v = *reinterpret_cast<const float4*>(Vb + (size_t)t * vstride + 4 * fq);
-            const float w = sm.sc[t];
-            a.x = fmaf(w, v.x, a.x); a.y = fmaf(w, v.y, a.y); a.z = fmaf(w, v.z, a.z); a.w = fmaf(w, v.w, a.w);
-        }
-        *reinterpret_cast<float4*>(sm.red + tg * 256 + fq * 4) = a;
-    }
-    __syncthreads();
-    float* xd = d3_group(p.XD, 1024, g);
-    if (tid < 256) {
-        float s = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s += sm.red[j * 256 + tid];
-        xd[(512 + part * 256 + tid) * D3_CG + bb] = s;
-    } else if (tid < 256 + 128) {
+    } else if (warp < 12) {
+        // content slots (minT <= 32): softmax per warp, value feature f = tid - 256 (128 per CTA)
+        const float v = lane < p.minT ? sm.csc[lane] : -INFINITY;
+        const float mx = warp_max(v);
+        const float e = lane < p.minT ? expf(v - mx) : 0.f;
+        const float mine = e / warp_sum(e);
         const int f = tid - 256;
-        float a = 0.f;
-        for (int m = 0; m < p.minT; ++m) a = fmaf(sm.csc[m], cv[(size_t)m * cvstride + f], a);
-        xd[(part * 128 + f) * D3_CG + bb] = a;
+        float acc = 0.f;
+        for (int m = 0; m < p.minT; ++m) acc = fmaf(__shfl_sync(0xffffffffu, mine, m), cv[(size_t)m * cvstride + f], acc);
+        ll_store(xd + (size_t)(part * 128 + f) * D3_CG + bb, acc, tag);
     }
-    __syncthreads();
+    __syncthreads();                                         // scratch (qs, sc) is rewritten by the next turn
 }
 
 template <int RT, bool EARLY>
-__device__ __forceinline__ void d3_loop(const Decode3Params& q, const Dec3Pass& ps, const DecSmem& sm, StageSync& sync,
+__device__ __forceinline__ void d3_loop(const Decode3Params& q, const Dec3Pass& ps, const DecSmem& sm, D3Timing& tm,
                                         int role, int job, uint64_t* kvbar) {
     const DecodeParams& p = q.d;
-    const unsigned n = gridDim.x;
     const bool has_pass = ps.R > 0;
     const int aclip = job / D3_NSPLIT, apart = job % D3_NSPLIT;         // attention CTAs: clip inside the group, half
     float* kvbuf = sm.csc + 32;                                         // [2][d3_kv_floats] when q.kv_smem
     const int kvfloats = d3_kv_floats(p.T, p.minT);
-    float xe[D3_EDEPTH][4];
+    ll_t xe[D3_EDEPTH][4];
     bool xe_valid = false;
-    D3Slot none; none.g = 0; none.step = 0; none.active = false;
+    LLWait lw; lw.abort_word = q.abort_word; lw.dead = false;
+    D3Slot none; none.g = 0; none.step = 0; none.turn = 0; none.active = false;
     // prologue A(-1): Q, content query and prenet(BOS) of every clip group from the initial state in S[0]
     if (role == ROLE_A && has_pass)
-        for (int g = 0; g * D3_CG < p.B; ++g) d3_turn<RT, EARLY>(p, ps, sm, sync, g, -1, 0, xe, xe_valid, none);
+        for (int g = 0; g * D3_CG < p.B; ++g) d3_turn<RT, EARLY>(q, ps, sm, tm, lw, role, g, -1, g - 1, 0, xe, xe_valid, none);
     if (job >= 0 && q.kv_smem) d3_prefetch_kv(q, kvbuf, &kvbar[0], min(aclip, p.B - 1), apart);          // turn 0 serves group 0
-    grid_arrive(p.barrier);
-    sync.target += n;
-    sync.timing = (q.timing != nullptr);
-    if (threadIdx.x == 0) sync.tmark = clock64();
+    tm.on = (q.timing != nullptr);
+    if (threadIdx.x == 0) tm.tmark = clock64();
 
     const int nturns = D3_NG * p.steps + D3_NG - 1;
     // attention CTAs: K/V image number n lives in buffer n & 1 and is that buffer's (n >> 1)-th use (mbarrier parity);
@@ -335,51 +465,36 @@ __device__ __forceinline__ void d3_loop(const Decode3Params& q, const Dec3Pass& 
 #pragma unroll 1
     for (int turn = 0; turn < nturns; ++turn) {
         const D3Slot cur = d3_slot(turn, role, p.steps, p.B);
-        const D3Slot next = (turn + 1 < nturns) ? d3_slot(turn + 1, role, p.steps, p.B) : none;
+        if (!cur.active) continue;
+        D3Slot next = none;                                  // this CTA's next active turn (at most D3_NG turns ahead)
+        for (int d = 1; d <= D3_NG && !next.active && turn + d < nturns; ++d) next = d3_slot(turn + d, role, p.steps, p.B);
         const int g = cur.g, step = cur.step;
-        sync.waited = false;
-        if (cur.active) {
-            const int parity_new = (step + 1) & 1;
-            if (has_pass) d3_turn<RT, EARLY>(p, ps, sm, sync, g, step, parity_new, xe, xe_valid, next);
-            if (job >= 0) {
-                const int b = g * D3_CG + aclip;
-                if (q.kv_smem) {
-                    D3Slot na = next;                        // this CTA's next active turn (at most D3_NG turns ahead)
-                    for (int d = 2; d <= D3_NG && !na.active && turn + d < nturns; ++d) na = d3_slot(turn + d, role, p.steps, p.B);
-                    if (na.active) {
-                        d3_prefetch_kv(q, kvbuf + (size_t)(kv_issued & 1) * kvfloats, &kvbar[kv_issued & 1], min(na.g * D3_CG + aclip, p.B - 1), apart);
-                        ++kv_issued;
-                    }
+        const int parity_new = (step + 1) & 1;
+        if (has_pass) d3_turn<RT, EARLY>(q, ps, sm, tm, lw, role, g, step, turn, parity_new, xe, xe_valid, next);
+        if (job >= 0) {
+            const int b = g * D3_CG + aclip, bsrc = min(b, p.B - 1);
+            if (q.kv_smem) {
+                if (next.active) {
+                    d3_prefetch_kv(q, kvbuf + (size_t)(kv_issued & 1) * kvfloats, &kvbar[kv_issued & 1], min(next.g * D3_CG + aclip, p.B - 1), apart);
+                    ++kv_issued;
                 }
-                sync.wait();
-                if (q.kv_smem) mbar_wait(&kvbar[kv_consumed & 1], (kv_consumed >> 1) & 1);     // this turn's clip has landed
-                sync.lap(2);
-                if (b < p.B) {
-                    if (q.kv_smem) {
-                        const float* kb = kvbuf + (size_t)(kv_consumed & 1) * kvfloats;
-                        const float* ckb = kb + (size_t)p.T * 768;
-                        d3_attend(p, sm, kb, kb + (size_t)p.T * 512, 256, ckb, ckb + (size_t)p.minT * 256, 128, b, apart, step);
-                    } else {
-                        d3_attend(p, sm, p.Kmem + (size_t)b * p.T * 512, p.Vmem + (size_t)b * p.T * 512 + apart * 256, 512,
-                                  p.ckey + (size_t)b * p.minT * 256, p.cval + (size_t)b * p.minT * 256 + apart * 128, 256, b, apart, step);
-                    }
-                }
-                ++kv_consumed;
+                mbar_wait(&kvbar[kv_consumed & 1], (kv_consumed >> 1) & 1);     // this turn's clip has landed
+                tm.lap(0);
+                const float* kb = kvbuf + (size_t)(kv_consumed & 1) * kvfloats;
+                const float* ckb = kb + (size_t)p.T * 768;
+                d3_attend(q, sm, kb, kb + (size_t)p.T * 512, 256, ckb, ckb + (size_t)p.minT * 256, 128, b, apart, step, turn, lw, tm);
+            } else {
+                tm.lap(0);
+                d3_attend(q, sm, p.Kmem + (size_t)bsrc * p.T * 512, p.Vmem + (size_t)bsrc * p.T * 512 + apart * 256, 512,
+                          p.ckey + (size_t)bsrc * p.minT * 256, p.cval + (size_t)bsrc * p.minT * 256 + apart * 128, 256, b, apart, step, turn, lw, tm);
             }
-            sync.wait();
-            sync.lap(3);
-        } else {
-            sync.wait();
-            sync.lap(4);
+            ++kv_consumed;
+            tm.lap(3);
         }
-        grid_arrive(p.barrier);
-        sync.lap(5);
-        sync.target += n;
     }
 }
 
 __global__ void __launch_bounds__(MV_THREADS, 1) decode3_kernel(const Decode3Params q) {
-    const DecodeParams& p = q.d;
     extern __shared__ __align__(16) float smem[];
     __shared__ Dec3Pass pass;
     __shared__ float tacc[D3_TIMING_SLOTS];
@@ -392,7 +507,7 @@ __global__ void __launch_bounds__(MV_THREADS, 1) decode3_kernel(const Decode3Par
     }
 
     DecSmem sm;
-    sm.red = smem;                                           // [16 warps][3 tiles][128]; attention partials [8][256]
+    sm.red = smem;                                           // [16 warps][3 tiles][128]
     sm.gsm = sm.red + MV_WARPS * MV8_RTILES * 128;           // [48][8]
     sm.wsm = sm.gsm + 16 * MV8_RTILES * D3_CG;                            // weight image (absent on attention CTAs, whose scratch + K/V live here)
     sm.qs = sm.wsm;                                          // [512]
@@ -413,16 +528,14 @@ __global__ void __launch_bounds__(MV_THREADS, 1) decode3_kernel(const Decode3Par
     }
     __syncthreads();
 
-    StageSync sync;
-    sync.counter = p.barrier; sync.target = 0; sync.waited = true;     // nothing to wait for before the prologue
-    sync.tacc = tacc; sync.tmark = 0; sync.slot0 = 0; sync.timing = false;
+    D3Timing tm; tm.tacc = tacc; tm.tmark = 0; tm.on = false;
     const bool early = pass.Ke > 0;                        // (Ke <= 256 * D3_EDEPTH is checked by the packer)
-    if (pass.RT <= 2) { if (early) d3_loop<2, true>(q, pass, sm, sync, role, job, kvbar); else d3_loop<2, false>(q, pass, sm, sync, role, job, kvbar); }
-    else if (pass.RT == 3) { if (early) d3_loop<3, true>(q, pass, sm, sync, role, job, kvbar); else d3_loop<3, false>(q, pass, sm, sync, role, job, kvbar); }
-    else if (pass.RT == 4) d3_loop<4, false>(q, pass, sm, sync, role, job, kvbar);
-    else if (pass.RT == 5) d3_loop<5, false>(q, pass, sm, sync, role, job, kvbar);
-    else if (pass.RT == 6) d3_loop<6, false>(q, pass, sm, sync, role, job, kvbar);
-    else d3_loop<8, false>(q, pass, sm, sync, role, job, kvbar);
+    if (pass.RT <= 2) { if (early) d3_loop<2, true>(q, pass, sm, tm, role, job, kvbar); else d3_loop<2, false>(q, pass, sm, tm, role, job, kvbar); }
+    else if (pass.RT == 3) { if (early) d3_loop<3, true>(q, pass, sm, tm, role, job, kvbar); else d3_loop<3, false>(q, pass, sm, tm, role, job, kvbar); }
+    else if (pass.RT == 4) d3_loop<4, false>(q, pass, sm, tm, role, job, kvbar);
+    else if (pass.RT == 5) d3_loop<5, false>(q, pass, sm, tm, role, job, kvbar);
+    else if (pass.RT == 6) d3_loop<6, false>(q, pass, sm, tm, role, job, kvbar);
+    else d3_loop<8, false>(q, pass, sm, tm, role, job, kvbar);
     __syncthreads();
     if (q.timing && tid < D3_TIMING_SLOTS) q.timing[blockIdx.x * D3_TIMING_SLOTS + tid] = tacc[tid];
 }
@@ -437,12 +550,18 @@ __global__ void split_halves_kernel(const float* __restrict__ src, float* __rest
     }
 }
 
-// recurrent state of the row-partitioned layout ([feature][Bpad]) -> group-major ([group][feature][8])
-__global__ void fm_to_group_major_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int Bpad) {
-    const size_t total = (size_t)rows * Bpad;
+// Initial recurrent state: h (feature-major [1024][Bpad], the Bi-LSTM's final hidden states) -> S[parity 0] and zero cell
+// state -> Cst, group-major tagged words.  They stand for "the output of LSTM-0 / LSTM-1 at step -1", i.e. of turn
+// g - 3 / g - 2 for clip group g of its 32-clip launch (decode3.cuh turn numbering: turn = 4*step + role + g).
+__global__ void d3_init_state_kernel(const float* __restrict__ h, ll_t* __restrict__ S, ll_t* __restrict__ Cst, int Bpad, uint32_t tag_base) {
+    const size_t total = (size_t)1024 * Bpad;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int b = i % Bpad; const int k = i / Bpad;
-        dst[((size_t)(b / D3_CG) * rows + k) * D3_CG + (b % D3_CG)] = src[i];
+        const int g = (b / D3_CG) % D3_NG;
+        const uint32_t tag = tag_base + (uint32_t)(-4 + (k < 512 ? ROLE_D : ROLE_E) + g + D3_TAG_BIAS);
+        const size_t o = ((size_t)(b / D3_CG) * 1024 + k) * D3_CG + (b % D3_CG);
+        ll_store(S + o, h[i], tag);
+        ll_store(Cst + o, 0.f, tag);
     }
 }
 

@@ -266,16 +266,6 @@ inline void pack_speaker(Context& c) {
 // ------------------------------------------------------------------------------------------------
 // decoder: pre-loop, postnet, decode-step program
 // ------------------------------------------------------------------------------------------------
-struct PassBuild {
-    int stage, R;
-    int Ke, src_e, wcol_e, Kl, src_l, wcol_l;
-    struct Row { int op, idx; float bias, aux, aux2; std::vector<std::pair<const float*, int>> w; };
-    std::vector<Row> rows;
-    int ldw() const { return Ke + Kl; }
-    double cost() const { return (double)R * (Ke + Kl); }
-    size_t floats() const { return (size_t)R * (Ke + Kl); }
-};
-
 // Row sources of the decode step after the host-side linear∘linear merges (pointers into vectors that outlive the packers).
 struct StepRows {
     const float *Wfc, *bfc, *Wpf, *bpf, *ps1, *p1bos, *Wp2, *bp2, *ps2, *Wq, *bq, *psq, *Wcq, *bcq, *Wst, *bst;
@@ -292,7 +282,7 @@ inline void pack_decode_program3(Context& c, const StepRows& w) {
     const int nD = 64, nE = 43, nQ = 11, nCQ = 6, nF = 5, nP2 = 3, nsplit = D3_NSPLIT;
     const int nAttn = D3_CG * nsplit;
     c.meta["d.step3.ok"] = 0;
-    if (nD + nE + nQ + nCQ + nF + nP2 + nAttn > nC) return;    // not enough SMs: decode.cuh serves every batch size
+    if (nD + nE + nQ + nCQ + nF + nP2 + nAttn > nC) return;    // not enough SMs (the decoder then refuses to run: B200 has 148)
     struct Row { int op, idx; float bias, aux, aux2; std::vector<std::pair<const float*, int>> w; };
     struct PB { int Ke, src_e, wcol_e, Kl, src_l, wcol_l; std::vector<Row> rows; };
     std::vector<PB> per_cta(nC, PB{0, SRC_NONE, 0, 0, SRC_NONE, 0, {}});
@@ -452,126 +442,6 @@ inline void pack_decode_program(Context& c) {
         }
     }
 
-    std::vector<std::vector<PassBuild>> per_cta(nC);
-    std::vector<std::vector<double>> load(nC, std::vector<double>(ST_COUNT, 0.0));
-    std::vector<size_t> floats(nC, 0);
-
-    // ---- LSTM units: contiguous groups per CTA, chunks of <=4 units ------------------------------
-    {
-        int u = 0;
-        for (int cta = 0; cta < nC; ++cta) {
-            int n = 512 / nC + (cta < 512 % nC ? 1 : 0);
-            for (int done = 0; done < n; done += 4) {
-                int nu = std::min(4, n - done), u0 = u + done;
-                for (int layer = 0; layer < 2; ++layer) {
-                    PassBuild pb;
-                    pb.R = 16;
-                    if (layer == 0) { pb.stage = ST_D; pb.Kl = 1024; pb.src_l = SRC_XD; pb.wcol_l = 0; pb.Ke = 512; pb.src_e = SRC_H0OLD; pb.wcol_e = 1024; }
-                    else            { pb.stage = ST_E; pb.Kl = 512;  pb.src_l = SRC_H0NEW; pb.wcol_l = 0; pb.Ke = 512; pb.src_e = SRC_H1OLD; pb.wcol_e = 512; }
-                    for (int ul = 0; ul < 4; ++ul)
-                        for (int g = 0; g < 4; ++g) {
-                            PassBuild::Row r{layer == 0 ? OP_GATE0 : OP_GATE1, -1, 0.f, 0.f, 0.f, {}};
-                            if (ul < nu) {
-                                const int row = g * 512 + u0 + ul;
-                                r.idx = u0 + ul;
-                                if (layer == 0) {
-                                    r.bias = b0x[row];
-                                    r.w = {{Wih0.data() + (size_t)row * 512, 512}, {Wx.data() + (size_t)row * 512, 512}, {Whh0.data() + (size_t)row * 512, 512}};
-                                } else {
-                                    r.bias = b1[row];
-                                    r.w = {{Wih1.data() + (size_t)row * 512, 512}, {Whh1.data() + (size_t)row * 512, 512}};
-                                }
-                            }
-                            pb.rows.push_back(r);
-                        }
-                    load[cta][pb.stage] += pb.cost(); floats[cta] += pb.floats();
-                    per_cta[cta].push_back(pb);
-                }
-            }
-            u += n;
-        }
-    }
-    // ---- the other rows, grouped into passes of R rows -------------------------------------------
-    std::vector<PassBuild> free_passes;
-    auto add_rows = [&](int stage, int R, int Ke, int src_e, int Kl, int src_l, std::vector<PassBuild::Row>& rows) {
-        for (size_t i = 0; i < rows.size(); i += R) {
-            PassBuild pb;
-            pb.stage = stage; pb.R = R; pb.Ke = Ke; pb.src_e = src_e; pb.wcol_e = 0; pb.Kl = Kl; pb.src_l = src_l; pb.wcol_l = Ke;
-            for (int j = 0; j < R; ++j) {
-                if (i + j < rows.size()) pb.rows.push_back(rows[i + j]);
-                else pb.rows.push_back({OP_NONE, 0, 0.f, 0.f, 0.f, {}});
-            }
-            free_passes.push_back(pb);
-        }
-    };
-    const int RA = 8;
-    {
-        std::vector<PassBuild::Row> rows;
-        for (int j = 0; j < 512; ++j) rows.push_back({OP_Q, j, bq[j], psq[j], 0.f, {{Wq.data() + (size_t)j * 1024, 1024}}});
-        add_rows(ST_A, RA, 512, SRC_H0NEW, 512, SRC_H1NEW, rows);
-        rows.clear();
-        for (int j = 0; j < 256; ++j) rows.push_back({OP_CQ, j, bcq[j], 0.f, 0.f, {{Wcq.data() + (size_t)j * 1024, 1024}}});
-        add_rows(ST_A, RA, 512, SRC_C0, 512, SRC_C1, rows);
-        rows.clear();
-        for (int j = 0; j < 80; ++j) rows.push_back({OP_FC, j, bfc[j], 0.f, 0.f, {{Wfc.data() + (size_t)j * 512, 512}}});
-        for (int j = 0; j < 256; ++j) rows.push_back({OP_P1, j, bpf[j], ps1[j], p1bos[j], {{Wpf.data() + (size_t)j * 512, 512}}});
-        rows.push_back({OP_STOP, 0, bst[0], 0.f, 0.f, {{Wst.data(), 512}}});
-        add_rows(ST_A, RA, 0, SRC_NONE, 512, SRC_H1NEW, rows);
-        rows.clear();
-        for (int j = 0; j < 256; ++j) rows.push_back({OP_P2, j, bp2[j], ps2[j], 0.f, {{Wp2.data() + (size_t)j * 256, 256}}});
-        add_rows(ST_B, 16, 0, SRC_NONE, 256, SRC_P1, rows);
-    }
-    // attention jobs run on the low-numbered CTAs in stage B: bias prenet-2 rows towards the high-numbered ones
-    for (int cta = 0; cta < nC; ++cta) load[cta][ST_B] += (double)(nC - 1 - cta);
-    const size_t scratch_bytes = (size_t)(MV_WARPS * DEC_RED_ROWS * MV_CLIPS + 16 * MV_CLIPS + 512 + 320 + 256 + 32) * 4;
-    const size_t static_bytes = sizeof(DecPass) * DEC_MAX_PASSES + 256;
-    const size_t cap_floats = ((size_t)c.max_smem_optin - scratch_bytes - static_bytes) / 4;
-    std::stable_sort(free_passes.begin(), free_passes.end(), [](const PassBuild& a, const PassBuild& b) { return a.cost() > b.cost(); });
-    for (auto& pb : free_passes) {
-        int best = -1;
-        for (int cta = 0; cta < nC; ++cta) {
-            if (floats[cta] + pb.floats() > cap_floats) continue;
-            if ((int)per_cta[cta].size() >= DEC_MAX_PASSES) continue;
-            if (best < 0 || load[cta][pb.stage] < load[best][pb.stage] ||
-                (load[cta][pb.stage] == load[best][pb.stage] && floats[cta] < floats[best])) best = cta;
-        }
-        if (best < 0) throw L2sError(1, "decode program does not fit in shared memory on this device");
-        load[best][pb.stage] += pb.cost(); floats[best] += pb.floats();
-        per_cta[best].push_back(pb);
-    }
-    size_t wimg_floats = 0;
-    for (int cta = 0; cta < nC; ++cta) wimg_floats = std::max(wimg_floats, floats[cta]);
-    wimg_floats = (wimg_floats + 3) & ~size_t(3);
-    std::vector<float> wimg((size_t)nC * wimg_floats, 0.f);
-    std::vector<DecPass> passes((size_t)nC * DEC_MAX_PASSES);
-    std::memset(passes.data(), 0, passes.size() * sizeof(DecPass));
-    std::vector<int> npasses(nC, 0);
-    for (int cta = 0; cta < nC; ++cta) {
-        size_t off = 0;
-        for (size_t j = 0; j < per_cta[cta].size(); ++j) {
-            const PassBuild& pb = per_cta[cta][j];
-            DecPass& d = passes[(size_t)cta * DEC_MAX_PASSES + j];
-            d.stage = pb.stage; d.R = pb.R; d.Ke = pb.Ke; d.src_e = pb.src_e; d.wcol_e = pb.wcol_e;
-            d.Kl = pb.Kl; d.src_l = pb.src_l; d.wcol_l = pb.wcol_l; d.ldw = pb.ldw(); d.w_off = (int)off;
-            for (int r = 0; r < 16; ++r) {
-                if (r < pb.R) {
-                    const auto& row = pb.rows[r];
-                    d.op[r] = row.op; d.idx[r] = row.idx; d.bias[r] = row.bias; d.aux[r] = row.aux; d.aux2[r] = row.aux2;
-                    float* dst = wimg.data() + (size_t)cta * wimg_floats + off + (size_t)r * pb.ldw();
-                    int col = 0;
-                    for (auto& piece : row.w) { std::copy(piece.first, piece.first + piece.second, dst + col); col += piece.second; }
-                    if (col != 0 && col != pb.ldw()) throw L2sError(1, "internal: decode row width mismatch");
-                } else { d.op[r] = OP_NONE; d.idx[r] = -1; }
-            }
-            off += pb.floats();
-        }
-        npasses[cta] = (int)per_cta[cta].size();
-    }
-    c.upload("d.step.wimg", wimg);
-    c.upload_raw("d.step.passes", passes.data(), passes.size());
-    c.upload_raw("d.step.npasses", npasses.data(), npasses.size());
-    c.meta["d.step.wimg_floats"] = (int64_t)wimg_floats;
-    c.meta["d.step.smem"] = (int64_t)(wimg_floats * 4 + scratch_bytes);
     // stop token: the encoder_cell half of the weight row (runtime GEMM N=1) — bias already in the pass
     std::vector<float> wst2(Wst.begin() + 512, Wst.begin() + 1024);
     c.upload("d.stop2.w", wst2);

@@ -23,8 +23,22 @@ import torch.nn.functional as F
 BN_EPS = 1e-5
 
 
+class _BnMode:
+    """Train-mode switch for every BatchNorm of the restatement (oracle/train_oracle.py flips it): batch statistics
+    (biased variance) normalise, and the updated running statistics (momentum 0.1, unbiased variance, as
+    nn.BatchNorm*d does in train()) are collected in `updated` keyed by state_dict name."""
+    train = False
+    updated = None
+
+
 def _bn(sd, name, x):
-    """Eval-mode BatchNorm{1,2,3}d: (x-mean)/sqrt(var+eps)*gamma+beta."""
+    """BatchNorm{1,2,3}d: (x-mean)/sqrt(var+eps)*gamma+beta with running (eval) or batch (train) statistics."""
+    if _BnMode.train:
+        rm, rv = sd[name + ".running_mean"].detach().clone(), sd[name + ".running_var"].detach().clone()
+        y = F.batch_norm(x, rm, rv, sd[name + ".weight"], sd[name + ".bias"], True, 0.1, BN_EPS)
+        if _BnMode.updated is not None:
+            _BnMode.updated[name + ".running_mean"], _BnMode.updated[name + ".running_var"] = rm, rv
+        return y
     return F.batch_norm(x, sd[name + ".running_mean"], sd[name + ".running_var"],
                         sd[name + ".weight"], sd[name + ".bias"], False, 0.0, BN_EPS)
 
