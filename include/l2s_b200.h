@@ -118,8 +118,8 @@ int l2s_infer_host_submit_u8(l2s_ctx* ctx, int slot, const unsigned char* frames
                              int precision);
 
 /* ---- train-step tail (train.py:167-193) ---------------------------------------------------------------------------
- * The forward-train / backward kernels of the model are not part of this library yet; these entry points cover the loss,
- * the data-parallel gradient exchange (the only collective of the path) and the optimizer step on FLAT fp32 buffers. */
+ * Loss, the data-parallel gradient exchange (the only collective of the path) and the optimizer step on FLAT fp32 buffers
+ * (the train-mode forward / backward of the model is further down: l2s_decoder_train_fwd / _bwd). */
 
 /* Loss.forward (train_utils/losses.py:35-79) and the gradient of sum(losses) w.r.t. the model outputs, all device fp32:
  * mel_out, mel_post, mel_target [B,80,M]; gate_logits, gate_target [B,M]; content_dis [rows,501].
@@ -146,6 +146,31 @@ int l2s_allreduce_grads(l2s_ctx* ctx, float* flat_grads, int64_t n, float scale,
 int l2s_clip_adamw_step(l2s_ctx* ctx, float* p, float* g, float* m, float* v, float* vmax, int64_t n, const float* sqnorm,
                         float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                         void* stream);
+
+/* ---- train-mode forward + backward (train.py:167 net(...), :184 loss.backward()) -----------------------------------------
+ * Parameters are NOT copied for training: l2s_train_bind registers, under the reference's state_dict key ("decoder.Q.0.
+ * linear_layer.weight", ...), the caller's fp32 DEVICE parameter memory and the gradient memory the backward pass
+ * accumulates into (grad may be NULL: frozen tensor / buffer; BatchNorm running_mean / running_var buffers, when bound, are
+ * updated in place by the forward pass as nn.BatchNorm*d does in train()).  Pointers stay owned by the caller and must stay
+ * valid; re-binding a key replaces it.  An optimizer step therefore needs no re-bind / re-pack. */
+int l2s_train_bind(l2s_ctx* ctx, const char* key, float* param, float* grad, int64_t numel);
+
+/* Decoder.forward in TRAIN mode (decoder.py:320-379): BatchNorm batch statistics, and every random draw of the reference as an
+ * explicit device input so that results are reproducible and checkable: tf_mask (HOST, M bytes: the coin flips of :355-357),
+ * gumbel [B*minT,501] (:257), and KEEP masks (1.0 = kept, 0.0 = dropped; the 1/(1-p) scale is applied here): prenet_mask
+ * [M,B,256] (:308, p=0.2), attn_mask [M,B,T] (:363, p=0.1), lstm_mask [M,B,512] (:312, nn.LSTM inter-layer dropout, p=0.1),
+ * post_masks[5] each [B,C,M] (:152-154, p=0.5; C = 512,512,512,512,80).  visual [B,T,1024], spk [B,256], mels [B,80,M].
+ * Outputs (any may be NULL): out_mel / out_post [B,80,M], out_stop [B,M], out_attn_logits [B,M,T] (pre-softmax, after the
+ * logit dropout), out_content_dis [B*minT,501].  Activations are kept inside the context until l2s_decoder_train_bwd. */
+int l2s_decoder_train_fwd(l2s_ctx* ctx, const float* visual, const float* spk, const float* mels, const unsigned char* tf_mask,
+                          const float* gumbel, const float* prenet_mask, const float* attn_mask, const float* lstm_mask,
+                          const float* const* post_masks, int B, int T, int M, int want_input_grads, float* out_mel, float* out_post,
+                          float* out_stop, float* out_attn_logits, float* out_content_dis, void* stream);
+/* Backward of the last l2s_decoder_train_fwd: g_* = gradient of the scalar objective w.r.t. out_mel, out_post, out_stop,
+ * out_content_dis (NULL = zero; l2s_loss_fwd_bwd produces exactly these).  Parameter gradients are ACCUMULATED into the bound
+ * gradient memory; g_visual [B,T,1024] / g_spk [B,256] (optional, need want_input_grads=1) receive the input gradients. */
+int l2s_decoder_train_bwd(l2s_ctx* ctx, const float* g_mel, const float* g_post, const float* g_stop, const float* g_content_dis,
+                          float* g_visual, float* g_spk, void* stream);
 
 /* Number of kernels this library has launched on ctx since creation (bench.py `gpu_launches`). */
 int64_t l2s_launch_count(const l2s_ctx* ctx);

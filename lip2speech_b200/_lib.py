@@ -20,6 +20,7 @@ IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)      
 EXPORTS = ("l2s_version", "l2s_create", "l2s_destroy", "l2s_last_error", "l2s_bind_weight", "l2s_commit_weights",
            "l2s_video_fwd", "l2s_speaker_fwd", "l2s_decoder_infer", "l2s_decoder_forward", "l2s_postnet_fwd", "l2s_infer", "l2s_infer_host", "l2s_infer_host_submit", "l2s_infer_host_wait",
            "l2s_video_fwd_u8", "l2s_infer_u8", "l2s_infer_host_submit_u8",
+           "l2s_train_bind", "l2s_decoder_train_fwd", "l2s_decoder_train_bwd",
            "l2s_launch_count", "l2s_debug_read", "l2s_set_profiling", "l2s_span_ms",
            "l2s_loss_fwd_bwd", "l2s_nccl_unique_id", "l2s_comm_init", "l2s_comm_destroy", "l2s_allreduce_grads", "l2s_clip_adamw_step")
 NCCL_UNIQUE_ID_BYTES = 128
@@ -57,6 +58,9 @@ def load() -> C.CDLL:
         lib.l2s_video_fwd_u8.argtypes = [vp, vp, vp, i, i, i, i, fp, i, vp]
         lib.l2s_infer_u8.argtypes = [vp, vp, vp, fp, fp, i, i, i, i, i, i, fp, vp, i, vp]
         lib.l2s_infer_host_submit_u8.argtypes = [vp, i, vp, vp, fp, fp, i, i, i, i, i, i, fp, vp, i]
+        lib.l2s_train_bind.argtypes = [vp, C.c_char_p, vp, vp, C.c_int64]
+        lib.l2s_decoder_train_fwd.argtypes = [vp, fp, fp, fp, vp, fp, fp, fp, fp, C.POINTER(vp), i, i, i, i, fp, fp, fp, fp, fp, vp]
+        lib.l2s_decoder_train_bwd.argtypes = [vp, fp, fp, fp, fp, fp, fp, vp]
         lib.l2s_launch_count.argtypes = [vp]; lib.l2s_launch_count.restype = C.c_int64
         lib.l2s_set_profiling.argtypes = [vp, i]
         lib.l2s_span_ms.argtypes = [vp, C.c_char_p]; lib.l2s_span_ms.restype = C.c_double
@@ -304,6 +308,47 @@ class Backend:
         self._check(self.lib.l2s_clip_adamw_step(self.h, *(C.c_void_p(t.data_ptr()) for t in (p, g, m, v, vmax)), p.numel(),
                                                  C.c_void_p(sqnorm.data_ptr()) if sqnorm is not None else None, max_norm, lr, beta1, beta2,
                                                  eps, weight_decay, step, self._stream()), "l2s_clip_adamw_step")
+
+    # ---- train-mode forward / backward (train.py:167,184) --------------------------------------------------------------
+    def train_bind(self, key: str, param: torch.Tensor, grad):
+        """Register caller-owned parameter memory (and the gradient memory backward accumulates into; None = frozen)."""
+        assert param.is_cuda and param.dtype == torch.float32 and param.is_contiguous()
+        assert grad is None or (grad.is_cuda and grad.dtype == torch.float32 and grad.is_contiguous() and grad.numel() == param.numel())
+        self._check(self.lib.l2s_train_bind(self.h, key.encode(), C.c_void_p(param.data_ptr()),
+                                            C.c_void_p(grad.data_ptr()) if grad is not None else None, param.numel()), f"l2s_train_bind({key})")
+
+    def decoder_train_fwd(self, visual, spk, mels, noise, want_input_grads=True):
+        """noise: object with tf_mask [M] (host bool), gumbel, prenet [M,B,256], attn [M,B,T], lstm [M,B,512], post (5 x [B,C,M])
+        — KEEP masks, float32 on the device.  Returns (out_mel, out_post, out_stop [B,M,1], attn_logits [B,M,T], content_dis)."""
+        visual, spk, mels = (_f32c(t, self.device) for t in (visual, spk, mels))
+        B, T, _ = visual.shape
+        M = mels.shape[2]
+        min_t = min([T] + [(T - k) // k + 1 for k in (1, 3, 5, 7)])
+        mask = noise.tf_mask.to(torch.uint8).cpu().contiguous()
+        gum, pm, am, lm = (_f32c(t, self.device) for t in (noise.gumbel, noise.prenet, noise.attn, noise.lstm))
+        post = [_f32c(t, self.device) for t in noise.post]
+        assert mask.numel() == M and pm.shape == (M, B, 256) and am.shape == (M, B, T) and lm.shape == (M, B, 512) and gum.shape == (B * min_t, 501)
+        assert [tuple(t.shape) for t in post] == [(B, c, M) for c in (512, 512, 512, 512, 80)]
+        out_mel = torch.empty(B, 80, M, device=self.device); out_post = torch.empty(B, 80, M, device=self.device)
+        out_stop = torch.empty(B, M, 1, device=self.device); out_attn = torch.empty(B, M, T, device=self.device)
+        out_dis = torch.empty(B * min_t, 501, device=self.device)
+        pp = (C.c_void_p * 5)(*[t.data_ptr() for t in post])
+        self._check(self.lib.l2s_decoder_train_fwd(self.h, visual.data_ptr(), spk.data_ptr(), mels.data_ptr(), C.c_void_p(mask.data_ptr()),
+                                                   gum.data_ptr(), pm.data_ptr(), am.data_ptr(), lm.data_ptr(), pp, B, T, M, int(want_input_grads),
+                                                   out_mel.data_ptr(), out_post.data_ptr(), out_stop.data_ptr(), out_attn.data_ptr(),
+                                                   out_dis.data_ptr(), self._stream()), "l2s_decoder_train_fwd")
+        # the masks are read again by the backward pass: keep them (and the inputs) alive until then
+        self._train_keep = (visual, spk, mels, gum, pm, am, lm, post, mask)
+        return out_mel, out_post, out_stop, out_attn, out_dis
+
+    def decoder_train_bwd(self, g_mel, g_post, g_stop, g_dis, B, T, want_input_grads=True):
+        gs = [None if g is None else _f32c(g, self.device) for g in (g_mel, g_post, g_stop, g_dis)]
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        g_visual = torch.empty(B, T, 1024, device=self.device) if want_input_grads else None
+        g_spk = torch.empty(B, 256, device=self.device) if want_input_grads else None
+        self._check(self.lib.l2s_decoder_train_bwd(self.h, *(ptr(g) for g in gs), ptr(g_visual), ptr(g_spk), self._stream()), "l2s_decoder_train_bwd")
+        self._train_keep = None
+        return g_visual, g_spk
 
     def set_profiling(self, enabled: bool):
         self.lib.l2s_set_profiling(self.h, int(enabled))

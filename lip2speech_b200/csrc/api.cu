@@ -11,6 +11,7 @@
 #include "pack.h"
 #include "pw_mma.cuh"
 #include "tc_gemm.cuh"
+#include "train_model.cuh"
 #include "train_step.cuh"
 #include <dlfcn.h>
 #include <nccl.h>
@@ -20,6 +21,8 @@ using namespace l2s;
 
 struct l2s_ctx {
     Context c;
+    std::map<std::string, tr::Param> train_params;      // caller-owned parameter / gradient memory (l2s_train_bind)
+    tr::DecoderTrain dec_train;
 };
 
 static std::string g_create_err;
@@ -917,6 +920,7 @@ void l2s_destroy(l2s_ctx* ctx) {
     cudaSetDevice(ctx->c.device);
     cudaDeviceSynchronize();
     destroy_comm_quiet(ctx->c);
+    ctx->dec_train.e.vals.free_all(); ctx->dec_train.e.grads.free_all();
     ctx->c.free_all();
     delete ctx;
 }
@@ -1262,6 +1266,43 @@ int l2s_loss_fwd_bwd(l2s_ctx* ctx, const float* mel_out, const float* mel_post, 
     check_launch(c, "loss partial sums");
     loss_finish_kernel<<<1, 32, 0, s>>>(part, grid, n_mel, n_gate, (size_t)rows, losses);
     check_launch(c, "loss finish");
+    API_END(ctx)
+}
+
+// ---- train-mode forward / backward ------------------------------------------------------------------------------------
+int l2s_train_bind(l2s_ctx* ctx, const char* key, float* param, float* grad, int64_t numel) {
+    if (!ctx) return L2S_ERR_INVALID;
+    API_BEGIN
+    if (!key || !param || numel <= 0) throw L2sError(L2S_ERR_INVALID, "train_bind: bad arguments");
+    tr::Param p; p.v = param; p.g = grad; p.n = numel;
+    ctx->train_params[key] = p;
+    API_END(ctx)
+}
+
+int l2s_decoder_train_fwd(l2s_ctx* ctx, const float* visual, const float* spk, const float* mels, const unsigned char* tf_mask, const float* gumbel,
+                          const float* prenet_mask, const float* attn_mask, const float* lstm_mask, const float* const* post_masks, int B, int T, int M,
+                          int want_input_grads, float* out_mel, float* out_post, float* out_stop, float* out_attn_logits, float* out_content_dis,
+                          void* stream) {
+    if (!ctx) return L2S_ERR_INVALID;
+    API_BEGIN
+    if (!visual || !spk || !mels || !tf_mask || !gumbel || !prenet_mask || !attn_mask || !lstm_mask || !post_masks)
+        throw L2sError(L2S_ERR_INVALID, "decoder_train_fwd: every input and every noise tensor is required");
+    L2S_CUDA(cudaSetDevice(ctx->c.device));
+    tr::DecoderTrainIO io{};
+    io.visual = visual; io.spk = spk; io.mels = mels; io.tf_mask = tf_mask; io.gumbel = gumbel;
+    io.prenet_mask = prenet_mask; io.attn_mask = attn_mask; io.lstm_mask = lstm_mask;
+    for (int i = 0; i < 5; ++i) { if (!post_masks[i]) throw L2sError(L2S_ERR_INVALID, "decoder_train_fwd: five postnet masks are required"); io.post_mask[i] = post_masks[i]; }
+    io.out_mel = out_mel; io.out_post = out_post; io.out_stop = out_stop; io.out_attn_logits = out_attn_logits; io.out_content_dis = out_content_dis;
+    ctx->dec_train.forward(ctx->c, ctx->train_params, io, B, T, M, want_input_grads != 0, (cudaStream_t)stream);
+    API_END(ctx)
+}
+
+int l2s_decoder_train_bwd(l2s_ctx* ctx, const float* g_mel, const float* g_post, const float* g_stop, const float* g_content_dis, float* g_visual,
+                          float* g_spk, void* stream) {
+    if (!ctx) return L2S_ERR_INVALID;
+    API_BEGIN
+    L2S_CUDA(cudaSetDevice(ctx->c.device));
+    ctx->dec_train.backward(g_mel, g_post, g_stop, g_content_dis, g_visual, g_spk, (cudaStream_t)stream);
     API_END(ctx)
 }
 

@@ -1,0 +1,821 @@
+// Train-mode engine: a reverse-mode tape over hand-written CUDA kernels (forward-with-saved-activations + backward) for the
+// layers of Decoder.forward / VideoExtractor.forward in train() mode (reference decoder.py:320-379, video.py:76-87,
+// shufflenetv2.py:42-104; autograd at train.py:184).
+//
+// Design: every activation is a 2-D row-major view [rows][cols] with a row stride (channels last: a Conv1d activation
+// [B,C,L] lives as rows (b,l) x C columns; an NHWC frame as rows (n,h,w) x C), values in one bump arena, gradients in a second
+// arena that is zero-filled once per backward.  An op runs its forward kernel(s) and pushes a closure with its backward
+// kernels on the tape; `backward()` replays the tape in reverse.  Parameters are NOT copied: the library reads the caller's
+// (PyTorch-owned) fp32 parameter memory and accumulates into the caller's gradient memory (l2s_train_bind), so an optimizer
+// step needs no re-bind / re-pack.  All reductions have a fixed order (no floating-point atomics): results are
+// run-to-run deterministic.  Exact fp32 FMA arithmetic (the GEMMs here are SIMT; the inference path's tcgen05 kernels stay
+// the fast path — this file is the correctness-first train path).
+#pragma once
+#include <functional>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "context.h"
+
+namespace l2s {
+namespace tr {
+
+struct TT {                       // train tensor: [rows][cols] view, element (r, c) at v[r*rs + c]
+    float* v = nullptr;
+    float* g = nullptr;           // gradient with the same layout (null: no gradient wanted)
+    int rows = 0, cols = 0, rs = 0;
+    size_t numel() const { return (size_t)rows * cols; }
+    bool dense() const { return rs == cols; }
+    TT colslice(int c0, int n) const { TT t = *this; t.v += c0; if (t.g) t.g += c0; t.cols = n; return t; }
+    // rows r0, r0+step, ... (n of them)
+    TT rowslice(int r0, int n, int step = 1) const {
+        TT t = *this; t.v += (size_t)r0 * rs; if (t.g) t.g += (size_t)r0 * rs; t.rows = n; t.rs = rs * step; return t;
+    }
+};
+
+// ---- kernels: GEMM ------------------------------------------------------------------------------------------------------
+// C[M,N] (+)= A' B'  with A' = A (TA=0: A[m*lda + k]) or A^T (TA=1: A[k*lda + m]); B' = B (TB=0: B[k*ldb + n]) or B^T (TB=1: B[n*ldb + k]).
+template <int TA, int TB>
+__global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                                                    float* __restrict__ C, int ldc, int accumulate) {
+    constexpr int BM = 64, BN = 64, BK = 16;
+    __shared__ float As[BK][BM + 1];
+    __shared__ float Bs[BK][BN + 1];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += BK) {
+        // 1024 elements per tile, 4 per thread
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = tid + i * 256;
+            {
+                int m, k;
+                if (TA == 0) { k = e & 15; m = e >> 4; } else { m = e & 63; k = e >> 6; }     // contiguous index fastest
+                const int gm = m0 + m, gk = k0 + k;
+                float v = 0.f;
+                if (gm < M && gk < K) v = TA == 0 ? A[(size_t)gm * lda + gk] : A[(size_t)gk * lda + gm];
+                As[k][m] = v;
+            }
+            {
+                int n, k;
+                if (TB == 0) { n = e & 63; k = e >> 6; } else { k = e & 15; n = e >> 4; }
+                const int gn = n0 + n, gk = k0 + k;
+                float v = 0.f;
+                if (gn < N && gk < K) v = TB == 0 ? B[(size_t)gk * ldb + gn] : B[(size_t)gn * ldb + gk];
+                Bs[k][n] = v;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = As[k][ty + 16 * i]; b[i] = Bs[k][tx + 16 * i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int m = m0 + ty + 16 * i, n = n0 + tx + 16 * j;
+            if (m < M && n < N) {
+                float* c = C + (size_t)m * ldc + n;
+                *c = accumulate ? *c + acc[i][j] : acc[i][j];
+            }
+        }
+}
+
+// Few-row GEMM (M <= 16: the per-step layers of the decode loop at a per-GPU batch of 8): C[m][n] = sum_k A[m][k] W[n][k] (+bias),
+// one warp per output column n, lanes split k; the weight row is read once and reused for every m.
+__global__ void __launch_bounds__(256) skinny_nt_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
+                                                        const float* __restrict__ bias, float* __restrict__ C, int ldc, int accumulate) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= N) return;
+    float acc[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) acc[m] = 0.f;
+    const float* w = W + (size_t)warp * ldw;
+    for (int k = lane; k < K; k += 32) {
+        const float wv = w[k];
+#pragma unroll
+        for (int m = 0; m < 16; ++m)
+            if (m < M) acc[m] = fmaf(A[(size_t)m * lda + k], wv, acc[m]);
+    }
+#pragma unroll
+    for (int m = 0; m < 16; ++m)
+        if (m < M) {
+            const float v = warp_sum(acc[m]);
+            if (lane == 0) {
+                float* c = C + (size_t)m * ldc + warp;
+                const float r = v + (bias ? bias[warp] : 0.f);
+                *c = accumulate ? *c + r : r;
+            }
+        }
+}
+// dx[m][k] (+)= sum_n dy[m][n] W[n][k]  for M <= 16: thread per k, loops n (W rows are read coalesced across k, dy broadcast).
+__global__ void __launch_bounds__(256) skinny_nn_kernel(int M, int N, int K, const float* __restrict__ dY, int ldy, const float* __restrict__ W, int ldw,
+                                                        float* __restrict__ dX, int ldx, int accumulate) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    float acc[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) acc[m] = 0.f;
+    for (int n = 0; n < N; ++n) {
+        const float wv = W[(size_t)n * ldw + k];
+#pragma unroll
+        for (int m = 0; m < 16; ++m)
+            if (m < M) acc[m] = fmaf(__ldg(dY + (size_t)m * ldy + n), wv, acc[m]);
+    }
+#pragma unroll
+    for (int m = 0; m < 16; ++m)
+        if (m < M) {
+            float* d = dX + (size_t)m * ldx + k;
+            *d = accumulate ? *d + acc[m] : acc[m];
+        }
+}
+
+// ---- kernels: column reductions ---------------------------------------------------------------------------------------
+// out[c] (+)= sum_r f(r, c).  One CTA per 32 columns: 8 row lanes x 32 columns, fixed summation order.
+enum ColOp { COL_SUM = 0, COL_SUM_XY = 1, COL_PSINE_DW = 2, COL_PRELU_DW = 3 };
+template <int OP>
+__global__ void __launch_bounds__(256) colreduce_kernel(int rows, int cols, const float* __restrict__ X, int xs, const float* __restrict__ Y, int ys,
+                                                        float* __restrict__ out, int accumulate) {
+    __shared__ float part[8][33];
+    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    float a = 0.f;
+    if (c < cols)
+        for (int r = rl; r < rows; r += 8) {
+            const float x = X[(size_t)r * xs + c];
+            if (OP == COL_SUM) a += x;
+            else if (OP == COL_SUM_XY) a = fmaf(x, Y[(size_t)r * ys + c], a);
+            else if (OP == COL_PSINE_DW) a = fmaf(sinf(x), Y[(size_t)r * ys + c], a);            // X = pre-activation, Y = dy
+            else if (OP == COL_PRELU_DW) a += x < 0.f ? x * Y[(size_t)r * ys + c] : 0.f;
+        }
+    part[rl][cl] = a;
+    __syncthreads();
+    if (rl == 0 && c < cols) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += part[i][cl];
+        out[c] = accumulate ? out[c] + s : s;
+    }
+}
+
+// Batch statistics per column: mean and biased variance (two passes inside the CTA's column strip; fixed order).
+__global__ void __launch_bounds__(256) colstats_kernel(int rows, int cols, const float* __restrict__ X, int xs, float* __restrict__ mean, float* __restrict__ var) {
+    __shared__ float part[8][33];
+    __shared__ float mu[32];
+    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    float a = 0.f;
+    if (c < cols) for (int r = rl; r < rows; r += 8) a += X[(size_t)r * xs + c];
+    part[rl][cl] = a;
+    __syncthreads();
+    if (rl == 0) { float s = 0.f; for (int i = 0; i < 8; ++i) s += part[i][cl]; mu[cl] = s / (float)rows; }
+    __syncthreads();
+    const float m = mu[cl];
+    a = 0.f;
+    if (c < cols) for (int r = rl; r < rows; r += 8) { const float d = X[(size_t)r * xs + c] - m; a = fmaf(d, d, a); }
+    part[rl][cl] = a;
+    __syncthreads();
+    if (rl == 0 && c < cols) { float s = 0.f; for (int i = 0; i < 8; ++i) s += part[i][cl]; mean[c] = m; var[c] = s / (float)rows; }
+}
+
+// Full reduction sum(X*Y) -> out[0] (+)=, single CTA (used for the two scalar temperatures).
+__global__ void __launch_bounds__(1024) dot_all_kernel(int rows, int cols, const float* __restrict__ X, int xs, const float* __restrict__ Y, int ys,
+                                                       float* __restrict__ out, int accumulate) {
+    __shared__ float part[32];
+    float a = 0.f;
+    const size_t n = (size_t)rows * cols;
+    for (size_t i = threadIdx.x; i < n; i += 1024) { const int r = i / cols, c = i % cols; a = fmaf(X[(size_t)r * xs + c], Y[(size_t)r * ys + c], a); }
+    a = warp_sum(a);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float s = warp_sum(part[threadIdx.x]);
+        if (threadIdx.x == 0) out[0] = accumulate ? out[0] + s : s;
+    }
+}
+
+// ---- kernels: elementwise ---------------------------------------------------------------------------------------------
+#define TR_EW_LOOP(total) for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (total); i += (size_t)gridDim.x * blockDim.x)
+
+enum EwOp { EW_COPY = 0, EW_ADD, EW_SILU, EW_RELU, EW_PSINE, EW_PRELU, EW_SCALE, EW_MASK, EW_ADDCONST, EW_ADDROW };
+// y[r][c] = f(x[r][c], ...)   aux: per-column parameter (PSINE / PRELU), second operand (ADD / MASK / ADDCONST, row stride as),
+// scalar alpha (SCALE / MASK).  ADDROW: aux is [rows/group][cols] broadcast over `group` consecutive rows.
+template <int OP>
+__global__ void ew_fwd_kernel(int rows, int cols, const float* X, int xs, const float* __restrict__ aux, int as, float alpha, int group,
+                              float* Y, int ys) {
+    TR_EW_LOOP((size_t)rows * cols) {
+        const int r = i / cols, c = i % cols;
+        const float x = X[(size_t)r * xs + c];
+        float y;
+        if (OP == EW_COPY) y = x;
+        else if (OP == EW_ADD || OP == EW_ADDCONST) y = x + aux[(size_t)r * as + c];
+        else if (OP == EW_SILU) y = siluf_acc(x);
+        else if (OP == EW_RELU) y = x > 0.f ? x : 0.f;
+        else if (OP == EW_PSINE) y = sinf(x) * aux[c];
+        else if (OP == EW_PRELU) y = x >= 0.f ? x : aux[c] * x;
+        else if (OP == EW_SCALE) y = x * alpha;
+        else if (OP == EW_MASK) y = x * (aux[(size_t)r * as + c] * alpha);
+        else y = x + aux[(size_t)(r / group) * as + c];      // EW_ADDROW
+        Y[(size_t)r * ys + c] = y;
+    }
+}
+// dX[r][c] += dY[r][c] * f'(...)   (X = the op's INPUT saved by the forward)
+template <int OP>
+__global__ void ew_bwd_kernel(int rows, int cols, const float* __restrict__ X, int xs, const float* __restrict__ aux, int as, float alpha,
+                              const float* __restrict__ dY, int dys, float* __restrict__ dX, int dxs) {
+    TR_EW_LOOP((size_t)rows * cols) {
+        const int r = i / cols, c = i % cols;
+        const float dy = dY[(size_t)r * dys + c];
+        float d;
+        if (OP == EW_COPY || OP == EW_ADD || OP == EW_ADDCONST || OP == EW_ADDROW) d = dy;
+        else if (OP == EW_SILU) { const float x = X[(size_t)r * xs + c]; const float s = sigmoidf_acc(x); d = dy * (s * (1.f + x * (1.f - s))); }
+        else if (OP == EW_RELU) d = X[(size_t)r * xs + c] > 0.f ? dy : 0.f;
+        else if (OP == EW_PSINE) d = dy * cosf(X[(size_t)r * xs + c]) * aux[c];
+        else if (OP == EW_PRELU) d = X[(size_t)r * xs + c] >= 0.f ? dy : aux[c] * dy;
+        else if (OP == EW_SCALE) d = dy * alpha;
+        else d = dy * (aux[(size_t)r * as + c] * alpha);      // EW_MASK
+        dX[(size_t)r * dxs + c] += d;
+    }
+}
+// dAux[g][c] += sum over the `group` rows of group g of dY   (backward of EW_ADDROW w.r.t. the broadcast operand)
+__global__ void addrow_bwd_kernel(int groups, int group, int cols, const float* __restrict__ dY, int dys, float* __restrict__ dA, int das) {
+    TR_EW_LOOP((size_t)groups * cols) {
+        const int g = i / cols, c = i % cols;
+        float a = 0.f;
+        for (int j = 0; j < group; ++j) a += dY[(size_t)(g * group + j) * dys + c];
+        dA[(size_t)g * das + c] += a;
+    }
+}
+
+// y = x * w[0] (learnable scalar: the attention temperatures, decoder.py:302,237)
+__global__ void scale_param_kernel(int rows, int cols, const float* __restrict__ X, int xs, const float* __restrict__ w, float* __restrict__ Y, int ys) {
+    const float a = w[0];
+    TR_EW_LOOP((size_t)rows * cols) { const int r = i / cols, c = i % cols; Y[(size_t)r * ys + c] = X[(size_t)r * xs + c] * a; }
+}
+__global__ void scale_param_bwd_kernel(int rows, int cols, const float* __restrict__ w, const float* __restrict__ dY, int dys, float* __restrict__ dX, int dxs) {
+    const float a = w[0];
+    TR_EW_LOOP((size_t)rows * cols) { const int r = i / cols, c = i % cols; dX[(size_t)r * dxs + c] += dY[(size_t)r * dys + c] * a; }
+}
+
+// BatchNorm (train): y = (x - mean) * rstd * gamma + beta
+__global__ void bn_fwd_kernel(int rows, int cols, const float* __restrict__ X, int xs, const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                              const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ Y, int ys) {
+    TR_EW_LOOP((size_t)rows * cols) {
+        const int r = i / cols, c = i % cols;
+        Y[(size_t)r * ys + c] = (X[(size_t)r * xs + c] - mean[c]) * rsqrtf(var[c] + eps) * gamma[c] + beta[c];
+    }
+}
+// dx = gamma*rstd * (dy - dbeta/R - xhat * dgamma/R)
+__global__ void bn_bwd_kernel(int rows, int cols, const float* __restrict__ X, int xs, const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                              const float* __restrict__ gamma, const float* __restrict__ dgamma, const float* __restrict__ dbeta,
+                              const float* __restrict__ dY, int dys, float* __restrict__ dX, int dxs) {
+    const float invR = 1.f / (float)rows;
+    TR_EW_LOOP((size_t)rows * cols) {
+        const int r = i / cols, c = i % cols;
+        const float rstd = rsqrtf(var[c] + eps);
+        const float xhat = (X[(size_t)r * xs + c] - mean[c]) * rstd;
+        dX[(size_t)r * dxs + c] += gamma[c] * rstd * (dY[(size_t)r * dys + c] - dbeta[c] * invR - xhat * dgamma[c] * invR);
+    }
+}
+// dgamma[c] = sum_r dy * xhat (needs mean/var): computed by a column reduction over a temporary xhat*dy? -> fused here.
+__global__ void __launch_bounds__(256) bn_dgamma_kernel(int rows, int cols, const float* __restrict__ X, int xs, const float* __restrict__ mean,
+                                                        const float* __restrict__ var, float eps, const float* __restrict__ dY, int dys,
+                                                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    __shared__ float pg[8][33], pb[8][33];
+    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    float ag = 0.f, ab = 0.f;
+    if (c < cols) {
+        const float m = mean[c], rstd = rsqrtf(var[c] + eps);
+        for (int r = rl; r < rows; r += 8) {
+            const float dy = dY[(size_t)r * dys + c];
+            ag = fmaf(dy, (X[(size_t)r * xs + c] - m) * rstd, ag);
+            ab += dy;
+        }
+    }
+    pg[rl][cl] = ag; pb[rl][cl] = ab;
+    __syncthreads();
+    if (rl == 0 && c < cols) {
+        float sg = 0.f, sb = 0.f;
+        for (int i = 0; i < 8; ++i) { sg += pg[i][cl]; sb += pb[i][cl]; }
+        dgamma[c] = sg; dbeta[c] = sb;
+    }
+}
+// running = (1 - momentum) * running + momentum * stat  (variance: unbiased, x rows/(rows-1)); nn.BatchNorm*d in train()
+__global__ void bn_running_kernel(int cols, int rows, float momentum, const float* __restrict__ mean, const float* __restrict__ var,
+                                  float* __restrict__ rmean, float* __restrict__ rvar) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    rmean[c] = (1.f - momentum) * rmean[c] + momentum * mean[c];
+    const float unbiased = rows > 1 ? var[c] * ((float)rows / (float)(rows - 1)) : var[c];
+    rvar[c] = (1.f - momentum) * rvar[c] + momentum * unbiased;
+}
+
+// softmax over the columns of every row (one warp per row)
+__global__ void __launch_bounds__(256) softmax_fwd_kernel(int rows, int cols, const float* __restrict__ X, int xs, float* __restrict__ Y, int ys) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const float* x = X + (size_t)r * xs;
+    float mx = -INFINITY;
+    for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, x[c]);
+    mx = warp_max(mx);
+    float s = 0.f;
+    for (int c = lane; c < cols; c += 32) s += expf(x[c] - mx);
+    s = warp_sum(s);
+    for (int c = lane; c < cols; c += 32) Y[(size_t)r * ys + c] = expf(x[c] - mx) / s;
+}
+// dx += y * (dy - sum(dy*y))
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(int rows, int cols, const float* __restrict__ Y, int ys, const float* __restrict__ dY, int dys,
+                                                          float* __restrict__ dX, int dxs) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    float s = 0.f;
+    for (int c = lane; c < cols; c += 32) s = fmaf(dY[(size_t)r * dys + c], Y[(size_t)r * ys + c], s);
+    s = warp_sum(s);
+    for (int c = lane; c < cols; c += 32) dX[(size_t)r * dxs + c] += Y[(size_t)r * ys + c] * (dY[(size_t)r * dys + c] - s);
+}
+
+// ---- kernels: per-clip attention (decoder.py:414-419, 262-271) ---------------------------------------------------------
+// scores[b][t] = sum_k q[b][k] * Kmem[(b*T + t)][k]       (one warp per (b, t))
+__global__ void __launch_bounds__(256) attn_scores_kernel(int B, int T, int D, const float* __restrict__ Q, int qs, const float* __restrict__ Km, int ks,
+                                                          float* __restrict__ S, int ss) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= B * T) return;
+    const int b = w / T, t = w % T;
+    float a = 0.f;
+    for (int k = lane; k < D; k += 32) a = fmaf(Q[(size_t)b * qs + k], Km[(size_t)(b * T + t) * ks + k], a);
+    a = warp_sum(a);
+    if (lane == 0) S[(size_t)b * ss + t] = a;
+}
+// dq[b][k] += sum_t dS[b][t] K[b,t,k] ;  dK[b,t,k] += dS[b][t] q[b][k]      (thread per (b, k))
+__global__ void attn_scores_bwd_kernel(int B, int T, int D, const float* __restrict__ Q, int qs, const float* __restrict__ Km, int ks,
+                                       const float* __restrict__ dS, int dss, float* __restrict__ dQ, int dqs, float* __restrict__ dK, int dks) {
+    TR_EW_LOOP((size_t)B * D) {
+        const int b = i / D, k = i % D;
+        const float q = Q[(size_t)b * qs + k];
+        float a = 0.f;
+        for (int t = 0; t < T; ++t) {
+            const float ds = dS[(size_t)b * dss + t];
+            a = fmaf(ds, Km[(size_t)(b * T + t) * ks + k], a);
+            if (dK) dK[(size_t)(b * T + t) * dks + k] += ds * q;
+        }
+        if (dQ) dQ[(size_t)b * dqs + k] += a;
+    }
+}
+// ctx[b][k] = sum_t a[b][t] V[(b*T + t)][k]
+__global__ void attn_context_kernel(int B, int T, int D, const float* __restrict__ A, int as, const float* __restrict__ V, int vs, float* __restrict__ C, int cs) {
+    TR_EW_LOOP((size_t)B * D) {
+        const int b = i / D, k = i % D;
+        float acc = 0.f;
+        for (int t = 0; t < T; ++t) acc = fmaf(A[(size_t)b * as + t], V[(size_t)(b * T + t) * vs + k], acc);
+        C[(size_t)b * cs + k] = acc;
+    }
+}
+// dA[b][t] += sum_k dC[b][k] V[b,t,k]  (warp per (b,t)) ; dV[b,t,k] += a[b][t] dC[b][k]
+__global__ void __launch_bounds__(256) attn_context_bwd_kernel(int B, int T, int D, const float* __restrict__ A, int as, const float* __restrict__ V, int vs,
+                                                               const float* __restrict__ dC, int dcs, float* __restrict__ dA, int das, float* __restrict__ dV, int dvs) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= B * T) return;
+    const int b = w / T, t = w % T;
+    const float a = A[(size_t)b * as + t];
+    float s = 0.f;
+    for (int k = lane; k < D; k += 32) {
+        const float dc = dC[(size_t)b * dcs + k];
+        s = fmaf(dc, V[(size_t)(b * T + t) * vs + k], s);
+        if (dV) dV[(size_t)(b * T + t) * dvs + k] += a * dc;
+    }
+    s = warp_sum(s);
+    if (lane == 0 && dA) dA[(size_t)b * das + t] += s;
+}
+
+// ---- kernels: LSTM cell (gate order i, f, g, o) -------------------------------------------------------------
+// gates [B][4H] (pre-activation) + c_prev [B][H] -> act [B][4H] (sigmoid/tanh applied, saved for backward), c [B][H], h [B][H]
+__global__ void lstm_cell_fwd_kernel(int B, int H, const float* __restrict__ G, int gs, const float* __restrict__ Cp, int cps,
+                                     float* __restrict__ Act, float* __restrict__ Cn, int cns, float* __restrict__ Hn, int hns) {
+    TR_EW_LOOP((size_t)B * H) {
+        const int b = i / H, j = i % H;
+        const float* g = G + (size_t)b * gs;
+        const float gi = sigmoidf_acc(g[j]), gf = sigmoidf_acc(g[H + j]), gg = tanhf(g[2 * H + j]), go = sigmoidf_acc(g[3 * H + j]);
+        const float c = gf * Cp[(size_t)b * cps + j] + gi * gg;
+        float* a = Act + (size_t)b * 4 * H;
+        a[j] = gi; a[H + j] = gf; a[2 * H + j] = gg; a[3 * H + j] = go;
+        Cn[(size_t)b * cns + j] = c;
+        Hn[(size_t)b * hns + j] = go * tanhf(c);
+    }
+}
+// Given dH, dC (of the outputs): dG (pre-activation gates, OVERWRITTEN) and dCp += .
+__global__ void lstm_cell_bwd_kernel(int B, int H, const float* __restrict__ Act, const float* __restrict__ Cp, int cps, const float* __restrict__ Cn, int cns,
+                                     const float* __restrict__ dH, int dhs, const float* __restrict__ dCn, int dcns,
+                                     float* __restrict__ dG, int dgs, float* __restrict__ dCp, int dcps) {
+    TR_EW_LOOP((size_t)B * H) {
+        const int b = i / H, j = i % H;
+        const float* a = Act + (size_t)b * 4 * H;
+        const float gi = a[j], gf = a[H + j], gg = a[2 * H + j], go = a[3 * H + j];
+        const float tc = tanhf(Cn[(size_t)b * cns + j]);
+        const float dh = dH ? dH[(size_t)b * dhs + j] : 0.f;
+        const float dc = (dCn ? dCn[(size_t)b * dcns + j] : 0.f) + dh * go * (1.f - tc * tc);
+        float* dg = dG + (size_t)b * dgs;
+        dg[j] = dc * gg * gi * (1.f - gi);
+        dg[H + j] = dc * Cp[(size_t)b * cps + j] * gf * (1.f - gf);
+        dg[2 * H + j] = dc * gi * (1.f - gg * gg);
+        dg[3 * H + j] = dh * tc * go * (1.f - go);
+        if (dCp) dCp[(size_t)b * dcps + j] += dc * gf;
+    }
+}
+
+// ---- kernels: Conv1d support (rows (b, l) x channels) ------------------------------------------------------------------
+// col[(b*Lo + lo)][ci*K + kk] = x[(b*L + lo*stride - pad + kk)][ci]  (zero outside [0, L))    — weight layout [co][ci][k]
+__global__ void im2col1d_kernel(int B, int L, int Lo, int C, int K, int stride, int pad, const float* __restrict__ X, int xs, float* __restrict__ col) {
+    const size_t total = (size_t)B * Lo * C * K;
+    TR_EW_LOOP(total) {
+        const int kk = i % K; size_t r = i / K;
+        const int ci = r % C; r /= C;
+        const int lo = r % Lo; const int b = r / Lo;
+        const int l = lo * stride - pad + kk;
+        col[i] = (l >= 0 && l < L) ? X[(size_t)(b * L + l) * xs + ci] : 0.f;
+    }
+}
+// dx[(b*L + l)][ci] += sum_kk dcol[(b*Lo + lo)][ci*K + kk]  over (lo, kk) with lo*stride - pad + kk == l
+__global__ void col2im1d_kernel(int B, int L, int Lo, int C, int K, int stride, int pad, const float* __restrict__ dcol, float* __restrict__ dX, int dxs) {
+    TR_EW_LOOP((size_t)B * L * C) {
+        const int ci = i % C; size_t r = i / C;
+        const int l = r % L; const int b = r / L;
+        float a = 0.f;
+        for (int kk = 0; kk < K; ++kk) {
+            const int num = l + pad - kk;
+            if (num < 0 || num % stride) continue;
+            const int lo = num / stride;
+            if (lo >= Lo) continue;
+            a += dcol[((size_t)(b * Lo + lo) * C + ci) * K + kk];
+        }
+        dX[(size_t)(b * L + l) * dxs + ci] += a;
+    }
+}
+// adaptive_avg_pool1d over rows: y[(b*m + i)][c] = mean of x[(b*L + l)][c] for l in [floor(i L / m), ceil((i+1) L / m))
+__global__ void adaptive_pool_fwd_kernel(int B, int L, int m, int C, const float* __restrict__ X, int xs, float* __restrict__ Y, int ys) {
+    TR_EW_LOOP((size_t)B * m * C) {
+        const int c = i % C; size_t r = i / C;
+        const int j = r % m; const int b = r / m;
+        const int lo = (j * L) / m, hi = ((j + 1) * L + m - 1) / m;
+        float a = 0.f;
+        for (int l = lo; l < hi; ++l) a += X[(size_t)(b * L + l) * xs + c];
+        Y[(size_t)(b * m + j) * ys + c] = a / (float)(hi - lo);
+    }
+}
+__global__ void adaptive_pool_bwd_kernel(int B, int L, int m, int C, const float* __restrict__ dY, int dys, float* __restrict__ dX, int dxs) {
+    TR_EW_LOOP((size_t)B * L * C) {
+        const int c = i % C; size_t r = i / C;
+        const int l = r % L; const int b = r / L;
+        float a = 0.f;
+        for (int j = 0; j < m; ++j) {
+            const int lo = (j * L) / m, hi = ((j + 1) * L + m - 1) / m;
+            if (l >= lo && l < hi) a += dY[(size_t)(b * m + j) * dys + c] / (float)(hi - lo);
+        }
+        dX[(size_t)(b * L + l) * dxs + c] += a;
+    }
+}
+// [B][C][L] <-> rows (b, l) x C
+__global__ void bcl_to_rows_tr_kernel(int B, int C, int L, const float* __restrict__ X, float* __restrict__ Y, int ys) {
+    TR_EW_LOOP((size_t)B * C * L) { const int l = i % L; size_t r = i / L; const int c = r % C; const int b = r / C; Y[(size_t)(b * L + l) * ys + c] = X[i]; }
+}
+__global__ void rows_to_bcl_tr_kernel(int B, int C, int L, const float* __restrict__ X, int xs, float* __restrict__ Y) {
+    TR_EW_LOOP((size_t)B * C * L) { const int l = i % L; size_t r = i / L; const int c = r % C; const int b = r / C; Y[i] = X[(size_t)(b * L + l) * xs + c]; }
+}
+
+}  // namespace tr
+}  // namespace l2s
+
+// ========================================================================================================================
+// host side: arenas, tape, ops
+// ========================================================================================================================
+namespace l2s {
+namespace tr {
+
+struct Arena {                     // bump allocator over cudaMalloc'ed blocks that persist across steps
+    struct Block { char* p; size_t cap, used; };
+    std::vector<Block> blocks;
+    size_t cur = 0;
+    size_t block_bytes = (size_t)256 << 20;
+    float* alloc(size_t floats) {
+        const size_t bytes = (std::max<size_t>(floats, 1) * sizeof(float) + 255) & ~size_t(255);
+        while (cur < blocks.size() && blocks[cur].cap - blocks[cur].used < bytes) ++cur;
+        if (cur == blocks.size()) {
+            Block nb; nb.cap = std::max(block_bytes, bytes); nb.used = 0; nb.p = nullptr;
+            L2S_CUDA(cudaMalloc(&nb.p, nb.cap));
+            blocks.push_back(nb);
+        }
+        float* r = reinterpret_cast<float*>(blocks[cur].p + blocks[cur].used);
+        blocks[cur].used += bytes;
+        return r;
+    }
+    void reset() { for (auto& b : blocks) b.used = 0; cur = 0; }
+    void zero_used(cudaStream_t s) { for (auto& b : blocks) if (b.used) L2S_CUDA(cudaMemsetAsync(b.p, 0, b.used, s)); }
+    void free_all() { for (auto& b : blocks) cudaFree(b.p); blocks.clear(); cur = 0; }
+};
+
+struct Param { float* v = nullptr; float* g = nullptr; int64_t n = 0; };
+
+inline int ew_blocks(size_t total) { return (int)std::min<size_t>(std::max<size_t>((total + 255) / 256, 1), 148 * 16); }
+
+struct Engine {
+    Context* ctx = nullptr;
+    cudaStream_t s = nullptr;
+    Arena vals, grads;
+    std::vector<std::function<void()>> tape;
+    std::map<std::string, Param>* params = nullptr;
+    bool update_bn_running = true;
+    int64_t* launches = nullptr;
+
+    void begin(Context* c, cudaStream_t stream, std::map<std::string, Param>* p) {
+        ctx = c; s = stream; params = p; launches = &c->launches;
+        vals.reset(); grads.reset(); tape.clear();
+    }
+    void ck(const char* what) {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) throw L2sError(2, std::string("train: ") + what + ": " + cudaGetErrorString(e));
+        ++*launches;
+    }
+    TT make(int rows, int cols, bool grad = true) {
+        TT t; t.rows = rows; t.cols = cols; t.rs = cols;
+        t.v = vals.alloc((size_t)rows * cols);
+        t.g = grad ? grads.alloc((size_t)rows * cols) : nullptr;
+        return t;
+    }
+    float* scratch(size_t floats) { return vals.alloc(floats); }
+    // wraps caller memory (inputs)
+    TT wrap(const float* p, int rows, int cols, bool grad) {
+        TT t; t.v = const_cast<float*>(p); t.rows = rows; t.cols = cols; t.rs = cols;
+        t.g = grad ? grads.alloc((size_t)rows * cols) : nullptr;
+        return t;
+    }
+    TT param(const std::string& key, int rows, int cols) {
+        auto it = params->find(key);
+        if (it == params->end()) throw L2sError(3, "train: parameter not bound: " + key + " (l2s_train_bind)");
+        if (it->second.n != (int64_t)rows * cols) throw L2sError(1, "train: parameter " + key + " has " + std::to_string(it->second.n) + " elements, expected " + std::to_string((int64_t)rows * cols));
+        TT t; t.v = it->second.v; t.g = it->second.g; t.rows = rows; t.cols = cols; t.rs = cols;
+        return t;
+    }
+    // Runs the tape in reverse.  Gradients of the outputs must have been written into their .g before the call; the
+    // gradient arena was zero-filled by begin_backward().
+    void begin_backward() { grads.zero_used(s); }
+    void backward() {
+        for (size_t i = tape.size(); i-- > 0;) tape[i]();
+        tape.clear();
+    }
+
+    // ---- GEMM helpers ----------------------------------------------------------------------------------------------------
+    template <int TA, int TB>
+    void gemm(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, bool acc) {
+        if (M <= 0 || N <= 0 || K <= 0) return;
+        dim3 grid((N + 63) / 64, (M + 63) / 64);
+        sgemm_kernel<TA, TB><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, acc ? 1 : 0);
+        ck("sgemm");
+    }
+
+    // y = x W^T (+ b): x [R,K], W [N,K] (nn.Linear / flattened Conv1d weight), b [N] or empty
+    TT linear(const TT& x, const TT& W, const TT* b) {
+        const int R = x.rows, K = x.cols, N = W.rows;
+        if (W.cols != K) throw L2sError(1, "train: linear shape mismatch");
+        TT y = make(R, N);
+        if (R <= 16) {
+            skinny_nt_kernel<<<(N * 32 + 255) / 256, 256, 0, s>>>(R, N, K, x.v, x.rs, W.v, W.rs, b ? b->v : nullptr, y.v, y.rs, 0);
+            ck("skinny_nt");
+        } else {
+            gemm<0, 1>(R, N, K, x.v, x.rs, W.v, W.rs, y.v, y.rs, false);
+            if (b) {
+                ew_fwd_kernel<EW_ADDROW><<<ew_blocks(y.numel()), 256, 0, s>>>(R, N, y.v, y.rs, b->v, 0, 0.f, R, y.v, y.rs);   // group = R: one broadcast row
+                ck("bias");
+            }
+        }
+        TT bb; if (b) bb = *b;
+        const bool hasb = b != nullptr;
+        tape.push_back([=]() {
+            if (x.g) {
+                if (R <= 16) { skinny_nn_kernel<<<(K + 255) / 256, 256, 0, s>>>(R, N, K, y.g, y.rs, W.v, W.rs, x.g, x.rs, 1); ck("skinny_nn"); }
+                else gemm<0, 0>(R, K, N, y.g, y.rs, W.v, W.rs, x.g, x.rs, true);
+            }
+            if (W.g) gemm<1, 0>(N, K, R, y.g, y.rs, x.v, x.rs, W.g, W.rs, true);
+            if (hasb && bb.g) { colreduce_kernel<COL_SUM><<<(N + 31) / 32, 256, 0, s>>>(R, N, y.g, y.rs, nullptr, 0, bb.g, 1); ck("bias grad"); }
+        });
+        return y;
+    }
+    // y = x E  (E [K,N] row-major parameter: z @ word_embeddings, decoder.py:258)
+    TT matmul_nn(const TT& x, const TT& E) {
+        const int R = x.rows, K = x.cols, N = E.cols;
+        TT y = make(R, N);
+        gemm<0, 0>(R, N, K, x.v, x.rs, E.v, E.rs, y.v, y.rs, false);
+        tape.push_back([=]() {
+            if (x.g) gemm<0, 1>(R, K, N, y.g, y.rs, E.v, E.rs, x.g, x.rs, true);
+            if (E.g) gemm<1, 0>(K, N, R, x.v, x.rs, y.g, y.rs, E.g, E.rs, true);
+        });
+        return y;
+    }
+
+    // ---- elementwise ------------------------------------------------------------------------------------------------------
+    template <int OP>
+    TT ew(const TT& x, const float* aux, int as, float alpha, int group = 1) {
+        TT y = make(x.rows, x.cols);
+        ew_fwd_kernel<OP><<<ew_blocks(x.numel()), 256, 0, s>>>(x.rows, x.cols, x.v, x.rs, aux, as, alpha, group, y.v, y.rs);
+        ck("elementwise");
+        tape.push_back([=]() {
+            if (!x.g) return;
+            ew_bwd_kernel<OP><<<ew_blocks(x.numel()), 256, 0, s>>>(x.rows, x.cols, x.v, x.rs, aux, as, alpha, y.g, y.rs, x.g, x.rs);
+            ck("elementwise bwd");
+        });
+        return y;
+    }
+    TT silu(const TT& x) { return ew<EW_SILU>(x, nullptr, 0, 0.f); }
+    TT relu(const TT& x) { return ew<EW_RELU>(x, nullptr, 0, 0.f); }
+    TT scale(const TT& x, float a) { return ew<EW_SCALE>(x, nullptr, 0, a); }
+    TT add_const(const TT& x, const float* cst, int cs) { return ew<EW_ADDCONST>(x, cst, cs, 0.f); }        // + a constant tensor (positions, gumbel)
+    TT dropout(const TT& x, const float* keep, int ks, float p) { return ew<EW_MASK>(x, keep, ks, 1.0f / (1.0f - p)); }
+    TT psine(const TT& x, const TT& w) {
+        TT y = ew<EW_PSINE>(x, w.v, 0, 0.f);
+        if (w.g) tape.push_back([=]() { colreduce_kernel<COL_PSINE_DW><<<(x.cols + 31) / 32, 256, 0, s>>>(x.rows, x.cols, x.v, x.rs, y.g, y.rs, w.g, 1); ck("psine dw"); });
+        return y;
+    }
+    TT prelu(const TT& x, const TT& w) {
+        TT y = ew<EW_PRELU>(x, w.v, 0, 0.f);
+        if (w.g) tape.push_back([=]() { colreduce_kernel<COL_PRELU_DW><<<(x.cols + 31) / 32, 256, 0, s>>>(x.rows, x.cols, x.v, x.rs, y.g, y.rs, w.g, 1); ck("prelu dw"); });
+        return y;
+    }
+    TT add(const TT& a, const TT& b) {
+        TT y = make(a.rows, a.cols);
+        ew_fwd_kernel<EW_ADD><<<ew_blocks(a.numel()), 256, 0, s>>>(a.rows, a.cols, a.v, a.rs, b.v, b.rs, 0.f, 1, y.v, y.rs);
+        ck("add");
+        tape.push_back([=]() {
+            for (const TT* t : {&a, &b})
+                if (t->g) { ew_bwd_kernel<EW_COPY><<<ew_blocks(y.numel()), 256, 0, s>>>(y.rows, y.cols, nullptr, 0, nullptr, 0, 0.f, y.g, y.rs, t->g, t->rs); ck("add bwd"); }
+        });
+        return y;
+    }
+    // y[(g*group + j)] = x[(g*group + j)] + v[g]     (attention_site broadcast over the T frames of a clip, decoder.py:327)
+    TT add_rows(const TT& x, const TT& v, int group) {
+        TT y = make(x.rows, x.cols);
+        ew_fwd_kernel<EW_ADDROW><<<ew_blocks(x.numel()), 256, 0, s>>>(x.rows, x.cols, x.v, x.rs, v.v, v.rs, 0.f, group, y.v, y.rs);
+        ck("add rows");
+        tape.push_back([=]() {
+            if (x.g) { ew_bwd_kernel<EW_COPY><<<ew_blocks(y.numel()), 256, 0, s>>>(y.rows, y.cols, nullptr, 0, nullptr, 0, 0.f, y.g, y.rs, x.g, x.rs); ck("add rows bwd"); }
+            if (v.g) { addrow_bwd_kernel<<<ew_blocks((size_t)v.rows * v.cols), 256, 0, s>>>(v.rows, group, v.cols, y.g, y.rs, v.g, v.rs); ck("add rows bwd v"); }
+        });
+        return y;
+    }
+    TT scale_param(const TT& x, const TT& w) {
+        TT y = make(x.rows, x.cols);
+        scale_param_kernel<<<ew_blocks(x.numel()), 256, 0, s>>>(x.rows, x.cols, x.v, x.rs, w.v, y.v, y.rs);
+        ck("scale param");
+        tape.push_back([=]() {
+            if (x.g) { scale_param_bwd_kernel<<<ew_blocks(x.numel()), 256, 0, s>>>(x.rows, x.cols, w.v, y.g, y.rs, x.g, x.rs); ck("scale param bwd"); }
+            if (w.g) { dot_all_kernel<<<1, 1024, 0, s>>>(x.rows, x.cols, x.v, x.rs, y.g, y.rs, w.g, 1); ck("scale param dw"); }
+        });
+        return y;
+    }
+    // dense copy of a (possibly strided) view, gradient flows back
+    TT copy(const TT& x) { return ew<EW_COPY>(x, nullptr, 0, 0.f); }
+    // [a | b | ...] along the columns
+    TT concat_cols(const std::vector<TT>& parts) {
+        int cols = 0;
+        for (auto& p : parts) cols += p.cols;
+        TT y = make(parts[0].rows, cols);
+        int c0 = 0;
+        for (auto& p : parts) {
+            ew_fwd_kernel<EW_COPY><<<ew_blocks(p.numel()), 256, 0, s>>>(p.rows, p.cols, p.v, p.rs, nullptr, 0, 0.f, 1, y.v + c0, y.rs);
+            ck("concat");
+            c0 += p.cols;
+        }
+        std::vector<TT> ps = parts;
+        tape.push_back([=]() {
+            int c = 0;
+            for (auto& p : ps) {
+                if (p.g) { ew_bwd_kernel<EW_COPY><<<ew_blocks(p.numel()), 256, 0, s>>>(p.rows, p.cols, nullptr, 0, nullptr, 0, 0.f, y.g + c, y.rs, p.g, p.rs); ck("concat bwd"); }
+                c += p.cols;
+            }
+        });
+        return y;
+    }
+
+    // BatchNorm{1,2,3}d in train(): batch statistics over the rows; running statistics updated in place when bound.
+    TT batchnorm(const TT& x, const std::string& name, float eps = 1e-5f) {
+        const int R = x.rows, C = x.cols;
+        TT gamma = param(name + ".weight", 1, C), beta = param(name + ".bias", 1, C);
+        float* mean = scratch(C); float* var = scratch(C);
+        colstats_kernel<<<(C + 31) / 32, 256, 0, s>>>(R, C, x.v, x.rs, mean, var);
+        ck("bn stats");
+        TT y = make(R, C);
+        bn_fwd_kernel<<<ew_blocks(x.numel()), 256, 0, s>>>(R, C, x.v, x.rs, mean, var, eps, gamma.v, beta.v, y.v, y.rs);
+        ck("bn fwd");
+        if (update_bn_running) {
+            auto rm = params->find(name + ".running_mean"), rv = params->find(name + ".running_var");
+            if (rm != params->end() && rv != params->end()) {
+                bn_running_kernel<<<(C + 255) / 256, 256, 0, s>>>(C, R, 0.1f, mean, var, rm->second.v, rv->second.v);
+                ck("bn running");
+            }
+        }
+        float* dgamma = scratch(C); float* dbeta = scratch(C);
+        tape.push_back([=]() {
+            bn_dgamma_kernel<<<(C + 31) / 32, 256, 0, s>>>(R, C, x.v, x.rs, mean, var, eps, y.g, y.rs, dgamma, dbeta);
+            ck("bn dgamma");
+            if (x.g) { bn_bwd_kernel<<<ew_blocks(x.numel()), 256, 0, s>>>(R, C, x.v, x.rs, mean, var, eps, gamma.v, dgamma, dbeta, y.g, y.rs, x.g, x.rs); ck("bn bwd"); }
+            if (gamma.g) { ew_bwd_kernel<EW_COPY><<<ew_blocks(C), 256, 0, s>>>(1, C, nullptr, 0, nullptr, 0, 0.f, dgamma, C, gamma.g, C); ck("bn dgamma acc"); }
+            if (beta.g) { ew_bwd_kernel<EW_COPY><<<ew_blocks(C), 256, 0, s>>>(1, C, nullptr, 0, nullptr, 0, 0.f, dbeta, C, beta.g, C); ck("bn dbeta acc"); }
+        });
+        return y;
+    }
+
+    TT softmax(const TT& x) {
+        TT y = make(x.rows, x.cols);
+        softmax_fwd_kernel<<<(x.rows * 32 + 255) / 256, 256, 0, s>>>(x.rows, x.cols, x.v, x.rs, y.v, y.rs);
+        ck("softmax");
+        tape.push_back([=]() {
+            if (!x.g) return;
+            softmax_bwd_kernel<<<(x.rows * 32 + 255) / 256, 256, 0, s>>>(x.rows, x.cols, y.v, y.rs, y.g, y.rs, x.g, x.rs);
+            ck("softmax bwd");
+        });
+        return y;
+    }
+    // scores [B,T] = q [B,D] . Kmem rows (b,t) [B*T, D]
+    TT attn_scores(const TT& q, const TT& Km, int T) {
+        const int B = q.rows, D = q.cols;
+        TT y = make(B, T);
+        attn_scores_kernel<<<(B * T * 32 + 255) / 256, 256, 0, s>>>(B, T, D, q.v, q.rs, Km.v, Km.rs, y.v, y.rs);
+        ck("attn scores");
+        tape.push_back([=]() {
+            attn_scores_bwd_kernel<<<ew_blocks((size_t)B * D), 256, 0, s>>>(B, T, D, q.v, q.rs, Km.v, Km.rs, y.g, y.rs, q.g, q.rs, Km.g, Km.rs);
+            ck("attn scores bwd");
+        });
+        return y;
+    }
+    TT attn_context(const TT& a, const TT& V, int T) {
+        const int B = a.rows, D = V.cols;
+        TT y = make(B, D);
+        attn_context_kernel<<<ew_blocks((size_t)B * D), 256, 0, s>>>(B, T, D, a.v, a.rs, V.v, V.rs, y.v, y.rs);
+        ck("attn context");
+        tape.push_back([=]() {
+            attn_context_bwd_kernel<<<(B * T * 32 + 255) / 256, 256, 0, s>>>(B, T, D, a.v, a.rs, V.v, V.rs, y.g, y.rs, a.g, a.rs, V.g, V.rs);
+            ck("attn context bwd");
+        });
+        return y;
+    }
+
+    // LSTM cell on pre-activation gates [B,4H] and previous cell state; returns (h, c)
+    void lstm_cell(const TT& gates, const TT& cprev, TT& h, TT& c) {
+        const int B = gates.rows, H = gates.cols / 4;
+        float* act = scratch((size_t)B * 4 * H);
+        h = make(B, H); c = make(B, H);
+        lstm_cell_fwd_kernel<<<ew_blocks((size_t)B * H), 256, 0, s>>>(B, H, gates.v, gates.rs, cprev.v, cprev.rs, act, c.v, c.rs, h.v, h.rs);
+        ck("lstm cell");
+        TT hh = h, cc = c;
+        tape.push_back([=]() {
+            // gates.g is overwritten (a gates tensor feeds exactly one cell), then flows on through the tape
+            lstm_cell_bwd_kernel<<<ew_blocks((size_t)B * H), 256, 0, s>>>(B, H, act, cprev.v, cprev.rs, cc.v, cc.rs, hh.g, hh.rs, cc.g, cc.rs, gates.g, gates.rs,
+                                                                          cprev.g, cprev.rs);
+            ck("lstm cell bwd");
+        });
+    }
+
+    // Conv1d over rows (b,l) x Cin -> rows (b,lo) x Cout; weight [Cout][Cin*K] (the nn.Conv1d layout flattened), bias [Cout]
+    TT conv1d(const TT& x, int B, int L, const TT& W, const TT* b, int K, int stride, int pad, int* Lout = nullptr) {
+        const int Cin = x.cols, Lo = (L + 2 * pad - K) / stride + 1;
+        if (Lout) *Lout = Lo;
+        if (K == 1 && stride == 1 && pad == 0) return linear(x, W, b);
+        TT col = make(B * Lo, Cin * K);
+        im2col1d_kernel<<<ew_blocks(col.numel()), 256, 0, s>>>(B, L, Lo, Cin, K, stride, pad, x.v, x.rs, col.v);
+        ck("im2col");
+        tape.push_back([=]() {
+            if (!x.g) return;
+            col2im1d_kernel<<<ew_blocks((size_t)B * L * Cin), 256, 0, s>>>(B, L, Lo, Cin, K, stride, pad, col.g, x.g, x.rs);
+            ck("col2im");
+        });
+        return linear(col, W, b);
+    }
+    TT adaptive_pool(const TT& x, int B, int L, int m) {
+        if (L == m) return x;
+        TT y = make(B * m, x.cols);
+        adaptive_pool_fwd_kernel<<<ew_blocks(y.numel()), 256, 0, s>>>(B, L, m, x.cols, x.v, x.rs, y.v, y.rs);
+        ck("adaptive pool");
+        tape.push_back([=]() {
+            if (!x.g) return;
+            adaptive_pool_bwd_kernel<<<ew_blocks((size_t)B * L * x.cols), 256, 0, s>>>(B, L, m, x.cols, y.g, y.rs, x.g, x.rs);
+            ck("adaptive pool bwd");
+        });
+        return y;
+    }
+};
+
+}  // namespace tr
+}  // namespace l2s

@@ -1,0 +1,227 @@
+// Train-mode forward + backward of the reference's Decoder (decoder.py:320-379) and VideoExtractor (video.py:76-87) on the tape
+// engine (train_engine.cuh).  Every RNG site of the reference is an explicit input: KEEP masks (1 = kept) and
+// the gumbel tensor, so both this path and the oracle (oracle/train_oracle.py) consume identical noise.
+#pragma once
+#include "train_engine.cuh"
+
+namespace l2s {
+namespace tr {
+
+// out[(b*T + t)][c] = pos[t][c]
+__global__ void tile_pos_kernel(int B, int T, int C, const float* __restrict__ pos, float* __restrict__ out) {
+    TR_EW_LOOP((size_t)B * T * C) { const int c = i % C; const int t = (i / C) % T; out[i] = pos[(size_t)t * C + c]; }
+}
+// dst rows (strided view) = src ; backward: src.g += dst.g
+// [B][C][M] keep-mask -> rows (b, m) x C
+__global__ void zero_kernel(float* __restrict__ p, size_t n) { TR_EW_LOOP(n) p[i] = 0.f; }
+
+struct DecoderTrainIO {
+    const float* visual; const float* spk; const float* mels;      // [B,T,1024], [B,256], [B,80,M]
+    const unsigned char* tf_mask;                                   // host [M]
+    const float* gumbel;                                            // [B*minT,501]
+    const float* prenet_mask; const float* attn_mask; const float* lstm_mask;   // [M,B,256], [M,B,T], [M,B,512] keep masks
+    const float* post_mask[5];                                      // [B,C,M] keep masks (C = 512 x4, 80)
+    float* out_mel; float* out_post; float* out_stop; float* out_attn_logits; float* out_content_dis;
+};
+
+struct DecoderTrain {
+    Engine e;
+    int B = 0, T = 0, M = 0, minT = 0;
+    TT visual, spk, outputs, post, stops, cdis;
+    bool live = false;
+
+    static TT assign(Engine& e, const TT& dst_view, const TT& src) {
+        ew_fwd_kernel<EW_COPY><<<ew_blocks(src.numel()), 256, 0, e.s>>>(src.rows, src.cols, src.v, src.rs, nullptr, 0, 0.f, 1, dst_view.v, dst_view.rs);
+        e.ck("assign");
+        cudaStream_t s = e.s; Engine* pe = &e;
+        e.tape.push_back([=]() {
+            if (!src.g || !dst_view.g) return;
+            ew_bwd_kernel<EW_COPY><<<ew_blocks(src.numel()), 256, 0, s>>>(src.rows, src.cols, nullptr, 0, nullptr, 0, 0.f, dst_view.g, dst_view.rs, src.g, src.rs);
+            pe->ck("assign bwd");
+        });
+        return dst_view;
+    }
+    TT lin(const TT& x, const std::string& name, int N) {          // LinearNorm / nn.Linear / k=1 Conv1d named `name`(.weight/.bias)
+        TT W = e.param(name + ".weight", N, x.cols), b = e.param(name + ".bias", 1, N);
+        return e.linear(x, W, &b);
+    }
+    TT multihop(const TT& x, const std::string& p) {               // MultiHopConv, decoder.py:159-196
+        static const int ks[4] = {1, 3, 7, 11};
+        std::vector<TT> feats{x};
+        for (int j = 0; j < 4; ++j) {
+            const std::string n = p + "conv." + std::to_string(j);
+            TT W = e.param(n + ".0.weight", 512, 512 * ks[j]), b = e.param(n + ".0.bias", 1, 512);
+            TT y = e.conv1d(x, B, T, W, &b, ks[j], 1, ks[j] / 2);
+            feats.push_back(e.silu(e.batchnorm(y, n + ".1")));
+        }
+        return lin(e.concat_cols(feats), p + "bottleneck", 512);
+    }
+    // one direction of the encoder Bi-LSTM (decoder.py:296,325); writes h_t into rnn_out[:, dir*512 : dir*512+512]
+    void encoder_dir(const TT& x, const TT& site, const TT& rnn_out, int dir, TT& h_final, TT& c_final) {
+        const std::string sfx = dir ? "_reverse" : "";
+        const std::string p = "decoder.encoder_rnn.";
+        TT Wih = e.param(p + "weight_ih_l0" + sfx, 2048, 1024), bih = e.param(p + "bias_ih_l0" + sfx, 1, 2048);
+        TT Whh = e.param(p + "weight_hh_l0" + sfx, 2048, 512), bhh = e.param(p + "bias_hh_l0" + sfx, 1, 2048);
+        TT xproj = e.linear(x, Wih, &bih);                          // [B*T, 2048], all time steps at once
+        TT h = site, c = site;
+        for (int k = 0; k < T; ++k) {
+            const int t = dir ? T - 1 - k : k;
+            TT g = e.add(xproj.rowslice(t, B, T), e.linear(h, Whh, &bhh));
+            TT hn, cn;
+            e.lstm_cell(g, c, hn, cn);
+            assign(e, rnn_out.rowslice(t, B, T).colslice(dir * 512, 512), hn);
+            h = hn; c = cn;
+        }
+        h_final = h; c_final = c;
+    }
+
+    void forward(Context& ctx, std::map<std::string, Param>& params, const DecoderTrainIO& io, int B_, int T_, int M_, bool want_input_grads, cudaStream_t s) {
+        B = B_; T = T_; M = M_;
+        if (B <= 0 || T < 7 || T > 300 || M <= 0 || M > 300) throw L2sError(1, "decoder_train_fwd: need 7<=T<=300, 1<=M<=300");
+        e.begin(&ctx, s, &params);
+        live = false;
+        const std::string P = "decoder.";
+        visual = e.wrap(io.visual, B * T, 1024, want_input_grads);
+        spk = e.wrap(io.spk, B, 256, want_input_grads);
+        const float* pos = e.param(P + "positional_encodings.pos_table", 300, 512).v;
+        // ---- pre-loop (decoder.py:321-340) -------------------------------------------------------------------------------
+        TT residual = lin(visual, P + "residual_bottleneck", 512);
+        TT enc_site = e.psine(lin(spk, P + "encoder_site.0.linear_layer", 512), e.param(P + "encoder_site.1.w", 1, 512));
+        TT att_site = e.psine(lin(spk, P + "attention_site.0.linear_layer", 512), e.param(P + "attention_site.1.w", 1, 512));
+        TT rnn_out = e.make(B * T, 1024);
+        TT hf, cf, hb, cb;
+        encoder_dir(visual, enc_site, rnn_out, 0, hf, cf);
+        encoder_dir(visual, enc_site, rnn_out, 1, hb, cb);
+        TT enc_cell = lin(e.concat_cols({cf, cb}), P + "E_C.linear_layer", 512);
+        TT enc = e.add(e.add_rows(lin(rnn_out, P + "encoder_proj.linear_layer", 512), att_site, T), residual);
+        float* pos_tile = e.scratch((size_t)B * T * 512);
+        tile_pos_kernel<<<ew_blocks((size_t)B * T * 512), 256, 0, s>>>(B, T, 512, pos, pos_tile);
+        e.ck("pos tile");
+        TT Kmem = e.add_const(e.psine(multihop(enc, P + "K.0."), e.param(P + "K.1.w", 1, 512)), pos_tile, 512);
+        TT Vmem = e.add_const(e.psine(multihop(enc, P + "V.0."), e.param(P + "V.1.w", 1, 512)), pos_tile, 512);
+        // ---- Content.encode (decoder.py:239-260) --------------------------------------------------------------------------
+        TT ckey, cval;
+        {
+            static const int ks[4] = {1, 3, 5, 7};
+            std::vector<TT> feats{enc};
+            std::vector<int> Ls{T};
+            minT = T;
+            for (int j = 0; j < 4; ++j) {
+                const std::string n = P + "content.agg." + std::to_string(j);
+                TT W = e.param(n + ".0.weight", 512, 512 * ks[j]), b = e.param(n + ".0.bias", 1, 512);
+                int Lo = 0;
+                TT y = e.conv1d(enc, B, T, W, &b, ks[j], ks[j], 0, &Lo);
+                feats.push_back(e.silu(e.batchnorm(y, n + ".1")));
+                Ls.push_back(Lo);
+                minT = std::min(minT, Lo);
+            }
+            std::vector<TT> pooled;
+            for (size_t j = 0; j < feats.size(); ++j) pooled.push_back(e.adaptive_pool(feats[j], B, Ls[j], minT));
+            TT w = lin(e.concat_cols(pooled), P + "content.bottleneck", 256);                  // rows (b, m) x 256
+            ckey = e.silu(lin(e.silu(lin(w, P + "content.K.0", 256)), P + "content.K.2", 256));
+            TT l = e.silu(lin(w, P + "content.location_fc.0", 256));
+            l = e.silu(lin(l, P + "content.location_fc.2", 256));
+            l = e.silu(lin(l, P + "content.location_fc.4", 501));
+            TT z = e.softmax(e.scale(e.add_const(l, io.gumbel, 501), 1.0f / 0.1f));             // F.gumbel_softmax(w_y, 0.1), soft
+            cval = e.matmul_nn(z, e.param(P + "content.word_embeddings", 501, 256));
+            cdis = e.softmax(l);
+        }
+        // ---- the M-step loop (decoder.py:343-375) ---------------------------------------------------------------------------
+        TT mel_rows = e.make(B * M, 80, false);                     // teacher frames as rows (b, i)
+        bcl_to_rows_tr_kernel<<<ew_blocks((size_t)B * 80 * M), 256, 0, s>>>(B, 80, M, io.mels, mel_rows.v, 80);
+        e.ck("mels -> rows");
+        TT zeros80 = e.make(B, 80, false);
+        zero_kernel<<<ew_blocks((size_t)B * 80), 256, 0, s>>>(zeros80.v, (size_t)B * 80);
+        e.ck("zeros");
+        TT bos = e.add_rows(zeros80, e.param(P + "BOS", 1, 80), B);                            // torch.tile(self.BOS, (N,1,1))
+        TT zc = e.make(B, 512, false);
+        zero_kernel<<<ew_blocks((size_t)B * 512), 256, 0, s>>>(zc.v, (size_t)B * 512);
+        e.ck("zeros");
+        outputs = e.make(B * M, 80);
+        stops = e.make(B * M, 1);
+        TT h0 = hf, h1 = hb, c0 = zc, c1 = zc;                      // hidden = encoder h_n; cell.fill_(0) (347)
+        TT ys = bos;
+        TT temp = e.param(P + "temperature", 1, 1), ctemp = e.param(P + "content.temperature", 1, 1);
+        TT Wq_w = e.param(P + "Q.1.w", 1, 512), p1w = e.param(P + "prenet.1.w", 1, 256), p4w = e.param(P + "prenet.4.w", 1, 256);
+        const std::string R = P + "decoder_rnn.";
+        TT Wih0 = e.param(R + "weight_ih_l0", 2048, 512), bih0 = e.param(R + "bias_ih_l0", 1, 2048), Whh0 = e.param(R + "weight_hh_l0", 2048, 512), bhh0 = e.param(R + "bias_hh_l0", 1, 2048);
+        TT Wih1 = e.param(R + "weight_ih_l1", 2048, 512), bih1 = e.param(R + "bias_ih_l1", 1, 2048), Whh1 = e.param(R + "weight_hh_l1", 2048, 512), bhh1 = e.param(R + "bias_hh_l1", 1, 2048);
+        for (int i = 0; i < M; ++i) {
+            if (io.tf_mask[i]) ys = i == 0 ? bos : mel_rows.rowslice(i - 1, B, M);              // teacher_input[:, i] (355-357)
+            TT p1 = e.psine(lin(ys, P + "prenet.0.linear_layer", 256), p1w);
+            TT p1d = e.dropout(p1, io.prenet_mask + (size_t)i * B * 256, 256, 0.2f);
+            TT p2 = e.psine(lin(p1d, P + "prenet.3.linear_layer", 256), p4w);
+            TT q = e.add_const(e.psine(lin(e.concat_cols({h0, h1}), P + "Q.0.linear_layer", 512), Wq_w), pos + (size_t)i * 512, 0);
+            TT a = e.dropout(e.attn_scores(e.scale_param(q, temp), Kmem, T), io.attn_mask + (size_t)i * B * T, T, 0.1f);
+            if (io.out_attn_logits) {
+                // rows b of a -> out[b][i][:]
+                ew_fwd_kernel<EW_COPY><<<ew_blocks(a.numel()), 256, 0, s>>>(B, T, a.v, a.rs, nullptr, 0, 0.f, 1, io.out_attn_logits + (size_t)i * T, M * T);
+                e.ck("attn logits out");
+            }
+            TT o = lin(e.attn_context(e.softmax(a), Vmem, T), P + "attention_proj.linear_layer", 256);
+            TT y = e.add(p2, o);
+            TT cq = e.silu(lin(e.concat_cols({c0, c1}), P + "content.Q.0", 256));
+            TT co = e.attn_context(e.softmax(e.attn_scores(e.scale_param(cq, ctemp), ckey, minT)), cval, minT);
+            TT x = e.concat_cols({co, y});
+            TT h0n, c0n, h1n, c1n;
+            e.lstm_cell(e.add(e.linear(x, Wih0, &bih0), e.linear(h0, Whh0, &bhh0)), c0, h0n, c0n);
+            TT h0d = e.dropout(h0n, io.lstm_mask + (size_t)i * B * 512, 512, 0.1f);            // nn.LSTM(dropout=0.1): layer 1's input only
+            e.lstm_cell(e.add(e.linear(h0d, Wih1, &bih1), e.linear(h1, Whh1, &bhh1)), c1, h1n, c1n);
+            h0 = h0n; c0 = c0n; h1 = h1n; c1 = c1n;
+            ys = lin(h1, P + "fc_out.linear_layer", 80);
+            assign(e, outputs.rowslice(i, B, M), ys);
+            assign(e, stops.rowslice(i, B, M), lin(e.concat_cols({h1, enc_cell}), P + "stop_token_layer.linear_layer", 1));
+        }
+        // ---- postnet (decoder.py:143-156, 377-378) -------------------------------------------------------------------------
+        {
+            const std::string PP = P + "postnet.";
+            TT x = outputs;
+            for (int i = 0; i < 5; ++i) {
+                const int cin = i == 0 ? 80 : 512, cout = i == 4 ? 80 : 512;
+                const std::string n = PP + "convolutions." + std::to_string(i);
+                TT W = e.param(n + ".0.conv.weight", cout, cin * 5), b = e.param(n + ".0.conv.bias", 1, cout);
+                TT y = e.batchnorm(e.conv1d(x, B, M, W, &b, 5, 1, 2), n + ".1");
+                if (i < 4) {
+                    y = e.psine(y, e.param(PP + "sin_activation." + std::to_string(i) + ".w", 1, 512));
+                    if (i != 0) y = e.add(y, x);
+                }
+                TT mrows = e.make(B * M, cout, false);              // keep mask [B,C,M] -> rows (b, m) x C
+                bcl_to_rows_tr_kernel<<<ew_blocks((size_t)B * cout * M), 256, 0, s>>>(B, cout, M, io.post_mask[i], mrows.v, cout);
+                e.ck("post mask rows");
+                x = e.dropout(y, mrows.v, cout, 0.5f);
+            }
+            post = e.add(x, outputs);
+        }
+        // ---- caller-visible outputs ------------------------------------------------------------------------------------------
+        if (io.out_mel) { rows_to_bcl_tr_kernel<<<ew_blocks((size_t)B * 80 * M), 256, 0, s>>>(B, 80, M, outputs.v, outputs.rs, io.out_mel); e.ck("out mel"); }
+        if (io.out_post) { rows_to_bcl_tr_kernel<<<ew_blocks((size_t)B * 80 * M), 256, 0, s>>>(B, 80, M, post.v, post.rs, io.out_post); e.ck("out post"); }
+        if (io.out_stop) L2S_CUDA(cudaMemcpyAsync(io.out_stop, stops.v, (size_t)B * M * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        if (io.out_content_dis) L2S_CUDA(cudaMemcpyAsync(io.out_content_dis, cdis.v, (size_t)B * minT * 501 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        live = true;
+    }
+
+    // Gradients of the scalar objective w.r.t. the four outputs the loss reads (any may be null) -> parameter gradients
+    // (accumulated into the bound gradient memory) and, optionally, the gradients of the inputs.
+    void backward(const float* g_mel, const float* g_post, const float* g_stop, const float* g_cdis, float* g_visual, float* g_spk, cudaStream_t s) {
+        if (!live) throw L2sError(1, "decoder_train_bwd: no forward pass to differentiate (call l2s_decoder_train_fwd first)");
+        e.s = s;
+        e.begin_backward();
+        if (g_mel) { bcl_to_rows_tr_kernel<<<ew_blocks((size_t)B * 80 * M), 256, 0, s>>>(B, 80, M, g_mel, outputs.g, 80); e.ck("g mel"); }
+        if (g_post) { bcl_to_rows_tr_kernel<<<ew_blocks((size_t)B * 80 * M), 256, 0, s>>>(B, 80, M, g_post, post.g, 80); e.ck("g post"); }
+        if (g_stop) L2S_CUDA(cudaMemcpyAsync(stops.g, g_stop, (size_t)B * M * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        if (g_cdis) L2S_CUDA(cudaMemcpyAsync(cdis.g, g_cdis, (size_t)B * minT * 501 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        e.backward();
+        if (g_visual) {
+            if (!visual.g) throw L2sError(1, "decoder_train_bwd: input gradients were not requested in the forward call");
+            L2S_CUDA(cudaMemcpyAsync(g_visual, visual.g, (size_t)B * T * 1024 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        }
+        if (g_spk) {
+            if (!spk.g) throw L2sError(1, "decoder_train_bwd: input gradients were not requested in the forward call");
+            L2S_CUDA(cudaMemcpyAsync(g_spk, spk.g, (size_t)B * 256 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        }
+        live = false;
+    }
+};
+
+}  // namespace tr
+}  // namespace l2s
