@@ -172,6 +172,14 @@ int l2s_decoder_train_fwd(l2s_ctx* ctx, const float* visual, const float* spk, c
 int l2s_decoder_train_bwd(l2s_ctx* ctx, const float* g_mel, const float* g_post, const float* g_stop, const float* g_content_dis,
                           float* g_visual, float* g_spk, void* stream);
 
+/* VideoExtractor.forward in TRAIN mode (video.py:76-87: Conv3d stem, BatchNorm batch statistics everywhere, PReLU, MaxPool3d,
+ * the 16 ShuffleNetV2 blocks, conv_last, AvgPool2d, L2 norm) followed by the feature dropout of model.py:26 when drop_mask
+ * (KEEP mask [B,T,768], p = 0.1) is non-NULL.  video [B,3,T,H,W] fp32 NCDHW -> out_feat [B,T,768].  Parameters under
+ * "encoder.*" come from l2s_train_bind.  l2s_video_train_bwd consumes the gradient w.r.t. out_feat (e.g. the first 768
+ * columns of l2s_decoder_train_bwd's g_visual) and accumulates the parameter gradients. */
+int l2s_video_train_fwd(l2s_ctx* ctx, const float* video, const float* drop_mask, int B, int T, int H, int W, float* out_feat, void* stream);
+int l2s_video_train_bwd(l2s_ctx* ctx, const float* g_feat, void* stream);
+
 /* Number of kernels this library has launched on ctx since creation (bench.py `gpu_launches`). */
 int64_t l2s_launch_count(const l2s_ctx* ctx);
 

@@ -20,7 +20,7 @@ IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)      
 EXPORTS = ("l2s_version", "l2s_create", "l2s_destroy", "l2s_last_error", "l2s_bind_weight", "l2s_commit_weights",
            "l2s_video_fwd", "l2s_speaker_fwd", "l2s_decoder_infer", "l2s_decoder_forward", "l2s_postnet_fwd", "l2s_infer", "l2s_infer_host", "l2s_infer_host_submit", "l2s_infer_host_wait",
            "l2s_video_fwd_u8", "l2s_infer_u8", "l2s_infer_host_submit_u8",
-           "l2s_train_bind", "l2s_decoder_train_fwd", "l2s_decoder_train_bwd",
+           "l2s_train_bind", "l2s_decoder_train_fwd", "l2s_decoder_train_bwd", "l2s_video_train_fwd", "l2s_video_train_bwd",
            "l2s_launch_count", "l2s_debug_read", "l2s_set_profiling", "l2s_span_ms",
            "l2s_loss_fwd_bwd", "l2s_nccl_unique_id", "l2s_comm_init", "l2s_comm_destroy", "l2s_allreduce_grads", "l2s_clip_adamw_step")
 NCCL_UNIQUE_ID_BYTES = 128
@@ -61,6 +61,8 @@ def load() -> C.CDLL:
         lib.l2s_train_bind.argtypes = [vp, C.c_char_p, vp, vp, C.c_int64]
         lib.l2s_decoder_train_fwd.argtypes = [vp, fp, fp, fp, vp, fp, fp, fp, fp, C.POINTER(vp), i, i, i, i, fp, fp, fp, fp, fp, vp]
         lib.l2s_decoder_train_bwd.argtypes = [vp, fp, fp, fp, fp, fp, fp, vp]
+        lib.l2s_video_train_fwd.argtypes = [vp, fp, fp, i, i, i, i, fp, vp]
+        lib.l2s_video_train_bwd.argtypes = [vp, fp, vp]
         lib.l2s_launch_count.argtypes = [vp]; lib.l2s_launch_count.restype = C.c_int64
         lib.l2s_set_profiling.argtypes = [vp, i]
         lib.l2s_span_ms.argtypes = [vp, C.c_char_p]; lib.l2s_span_ms.restype = C.c_double
@@ -349,6 +351,25 @@ class Backend:
         self._check(self.lib.l2s_decoder_train_bwd(self.h, *(ptr(g) for g in gs), ptr(g_visual), ptr(g_spk), self._stream()), "l2s_decoder_train_bwd")
         self._train_keep = None
         return g_visual, g_spk
+
+    def video_train_fwd(self, video, drop_mask=None):
+        """VideoExtractor.forward in train mode (+ model.py:26 dropout when drop_mask [B,T,768] KEEP mask is given)."""
+        video = _f32c(video, self.device)
+        B, Cc, T, H, W = video.shape
+        assert Cc == 3
+        if drop_mask is not None:
+            drop_mask = _f32c(drop_mask, self.device)
+            assert drop_mask.shape == (B, T, 768)
+        out = torch.empty(B, T, 768, device=self.device)
+        self._check(self.lib.l2s_video_train_fwd(self.h, video.data_ptr(), drop_mask.data_ptr() if drop_mask is not None else None, B, T, H, W,
+                                                 out.data_ptr(), self._stream()), "l2s_video_train_fwd")
+        self._video_keep = (video, drop_mask)
+        return out
+
+    def video_train_bwd(self, g_feat):
+        g_feat = _f32c(g_feat, self.device)
+        self._check(self.lib.l2s_video_train_bwd(self.h, g_feat.data_ptr(), self._stream()), "l2s_video_train_bwd")
+        self._video_keep = None
 
     def set_profiling(self, enabled: bool):
         self.lib.l2s_set_profiling(self.h, int(enabled))

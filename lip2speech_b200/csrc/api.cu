@@ -23,6 +23,7 @@ struct l2s_ctx {
     Context c;
     std::map<std::string, tr::Param> train_params;      // caller-owned parameter / gradient memory (l2s_train_bind)
     tr::DecoderTrain dec_train;
+    tr::VideoTrain video_train;
 };
 
 static std::string g_create_err;
@@ -921,6 +922,7 @@ void l2s_destroy(l2s_ctx* ctx) {
     cudaDeviceSynchronize();
     destroy_comm_quiet(ctx->c);
     ctx->dec_train.e.vals.free_all(); ctx->dec_train.e.grads.free_all();
+    ctx->video_train.e.vals.free_all(); ctx->video_train.e.grads.free_all();
     ctx->c.free_all();
     delete ctx;
 }
@@ -1303,6 +1305,24 @@ int l2s_decoder_train_bwd(l2s_ctx* ctx, const float* g_mel, const float* g_post,
     API_BEGIN
     L2S_CUDA(cudaSetDevice(ctx->c.device));
     ctx->dec_train.backward(g_mel, g_post, g_stop, g_content_dis, g_visual, g_spk, (cudaStream_t)stream);
+    API_END(ctx)
+}
+
+int l2s_video_train_fwd(l2s_ctx* ctx, const float* video, const float* drop_mask, int B, int T, int H, int W, float* out_feat, void* stream) {
+    if (!ctx) return L2S_ERR_INVALID;
+    API_BEGIN
+    if (!video || !out_feat) throw L2sError(L2S_ERR_INVALID, "video_train_fwd: video and out_feat are required");
+    L2S_CUDA(cudaSetDevice(ctx->c.device));
+    ctx->video_train.forward(ctx->c, ctx->train_params, video, drop_mask, B, T, H, W, out_feat, (cudaStream_t)stream);
+    API_END(ctx)
+}
+
+int l2s_video_train_bwd(l2s_ctx* ctx, const float* g_feat, void* stream) {
+    if (!ctx) return L2S_ERR_INVALID;
+    API_BEGIN
+    if (!g_feat) throw L2sError(L2S_ERR_INVALID, "video_train_bwd: g_feat is required");
+    L2S_CUDA(cudaSetDevice(ctx->c.device));
+    ctx->video_train.backward(g_feat, (cudaStream_t)stream);
     API_END(ctx)
 }
 

@@ -497,6 +497,241 @@ __global__ void rows_to_bcl_tr_kernel(int B, int C, int L, const float* __restri
     TR_EW_LOOP((size_t)B * C * L) { const int l = i % L; size_t r = i / L; const int c = r % C; const int b = r / C; Y[i] = X[(size_t)(b * L + l) * xs + c]; }
 }
 
+// ---- kernels: video frontend (NHWC rows (n, h, w) x C) ---------------------------------------------------------------
+// Conv3d(3->24,(5,7,7),s(1,2,2),p(2,3,3)) forward: y[(n,ho,wo)][co] over the caller's NCDHW clip tensor; k = ((ci*5+kt)*7+kh)*7+kw.
+// One thread per (position, co); the 735-tap patch is re-read through L1 by the 24 threads of a position.
+__global__ void __launch_bounds__(256) stem_fwd_kernel(int B, int T, int H, int W, int Ho, int Wo, const float* __restrict__ X, const float* __restrict__ Wt,
+                                                       float* __restrict__ Y) {
+    const size_t total = (size_t)B * T * Ho * Wo * 24;
+    TR_EW_LOOP(total) {
+        const int co = i % 24; size_t r = i / 24;
+        const int wo = r % Wo; r /= Wo;
+        const int ho = r % Ho; r /= Ho;
+        const int t = r % T; const int b = r / T;
+        const float* w = Wt + (size_t)co * 735;
+        float acc = 0.f;
+        for (int ci = 0; ci < 3; ++ci)
+            for (int kt = 0; kt < 5; ++kt) {
+                const int ti = t + kt - 2;
+                if (ti < 0 || ti >= T) continue;
+                const float* plane = X + ((size_t)(b * 3 + ci) * T + ti) * H * W;
+                for (int kh = 0; kh < 7; ++kh) {
+                    const int hi = 2 * ho + kh - 3;
+                    if (hi < 0 || hi >= H) continue;
+                    for (int kw = 0; kw < 7; ++kw) {
+                        const int wi = 2 * wo + kw - 3;
+                        if (wi < 0 || wi >= W) continue;
+                        acc = fmaf(__ldg(plane + (size_t)hi * W + wi), w[((ci * 5 + kt) * 7 + kh) * 7 + kw], acc);
+                    }
+                }
+            }
+        Y[i] = acc;
+    }
+}
+// Weight gradient of the stem: part[chunk][co*735 + k] = sum over the chunk's positions of dY[pos][co] * patch[pos][k].
+// Thread t owns taps k = t, t+256, t+512 (735 <= 768) for all 24 output channels: 72 accumulators, the patch values are
+// gathered straight from the clip tensor (each thread decodes its taps once), dY rows are broadcast from shared memory.
+__global__ void __launch_bounds__(256) stem_wgrad_kernel(int B, int T, int H, int W, int Ho, int Wo, int pos_per_chunk, const float* __restrict__ X,
+                                                         const float* __restrict__ dY, float* __restrict__ part) {
+    __shared__ float dys[32][24];
+    const int tid = threadIdx.x;
+    const size_t npos = (size_t)B * T * Ho * Wo;
+    const size_t p0 = (size_t)blockIdx.x * pos_per_chunk, p1 = min(npos, p0 + pos_per_chunk);
+    int ci[3], kt[3], kh[3], kw[3]; bool kv[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int k = tid + 256 * j;
+        kv[j] = k < 735;
+        const int kk = kv[j] ? k : 0;
+        ci[j] = kk / 245; const int r = kk % 245; kt[j] = r / 49; kh[j] = (r % 49) / 7; kw[j] = r % 7;
+    }
+    float acc[3][24];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int c = 0; c < 24; ++c) acc[j][c] = 0.f;
+    for (size_t pb = p0; pb < p1; pb += 32) {
+        const int nb = (int)min((size_t)32, p1 - pb);
+        __syncthreads();
+        for (int e = tid; e < nb * 24; e += 256) dys[e / 24][e % 24] = dY[(pb + e / 24) * 24 + e % 24];
+        __syncthreads();
+        for (int q = 0; q < nb; ++q) {
+            size_t r = pb + q;
+            const int wo = r % Wo; r /= Wo;
+            const int ho = r % Ho; r /= Ho;
+            const int t = r % T; const int b = r / T;
+            float xv[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int ti = t + kt[j] - 2, hi = 2 * ho + kh[j] - 3, wi = 2 * wo + kw[j] - 3;
+                xv[j] = (kv[j] && ti >= 0 && ti < T && hi >= 0 && hi < H && wi >= 0 && wi < W)
+                            ? __ldg(X + (((size_t)(b * 3 + ci[j]) * T + ti) * H + hi) * W + wi) : 0.f;
+            }
+#pragma unroll
+            for (int c = 0; c < 24; ++c) {
+                const float d = dys[q][c];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) acc[j][c] = fmaf(d, xv[j], acc[j][c]);
+            }
+        }
+    }
+    float* out = part + (size_t)blockIdx.x * (24 * 735);
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+        if (kv[j])
+#pragma unroll
+            for (int c = 0; c < 24; ++c) out[c * 735 + tid + 256 * j] = acc[j][c];
+}
+// dst[i] += sum_chunk part[chunk][i]   (fixed order)
+__global__ void sum_chunks_kernel(int n, int chunks, const float* __restrict__ part, float* __restrict__ dst) {
+    TR_EW_LOOP((size_t)n) {
+        float a = 0.f;
+        for (int c = 0; c < chunks; ++c) a += part[(size_t)c * n + i];
+        dst[i] += a;
+    }
+}
+// MaxPool 3x3 stride 2 pad 1 over NHWC rows; idx = flat input row of the maximum (first in scan order on ties)
+__global__ void maxpool_fwd_kernel(int N, int H, int W, int C, int Ho, int Wo, const float* __restrict__ X, float* __restrict__ Y, int* __restrict__ idx) {
+    TR_EW_LOOP((size_t)N * Ho * Wo * C) {
+        const int c = i % C; size_t r = i / C;
+        const int wo = r % Wo; r /= Wo;
+        const int ho = r % Ho; const int n = r / Ho;
+        float best = -INFINITY; int bi = -1;
+        for (int kh = 0; kh < 3; ++kh) {
+            const int h = 2 * ho + kh - 1;
+            if (h < 0 || h >= H) continue;
+            for (int kw = 0; kw < 3; ++kw) {
+                const int w = 2 * wo + kw - 1;
+                if (w < 0 || w >= W) continue;
+                const int row = (n * H + h) * W + w;
+                const float v = X[(size_t)row * C + c];
+                if (v > best) { best = v; bi = row; }
+            }
+        }
+        Y[i] = best; idx[i] = bi;
+    }
+}
+// gather form (deterministic): an input position receives dY of every window whose maximum it is
+__global__ void maxpool_bwd_kernel(int N, int H, int W, int C, int Ho, int Wo, const float* __restrict__ dY, const int* __restrict__ idx, float* __restrict__ dX) {
+    TR_EW_LOOP((size_t)N * H * W * C) {
+        const int c = i % C; size_t r = i / C;
+        const int row = (int)r;
+        const int w = r % W; r /= W;
+        const int h = r % H; const int n = r / H;
+        float a = 0.f;
+        for (int ho = (h + 1 - 2 + 1) / 2; ho <= (h + 1) / 2; ++ho) {
+            if (ho < 0 || ho >= Ho) continue;
+            for (int wo = (w + 1 - 2 + 1) / 2; wo <= (w + 1) / 2; ++wo) {
+                if (wo < 0 || wo >= Wo) continue;
+                const size_t o = ((size_t)(n * Ho + ho) * Wo + wo) * C + c;
+                if (idx[o] == row) a += dY[o];
+            }
+        }
+        dX[i] += a;
+    }
+}
+// depthwise 3x3, pad 1, stride s, no bias; weight [C][9]
+__global__ void dw3x3_fwd_kernel(int N, int H, int W, int C, int s, int Ho, int Wo, const float* __restrict__ X, int xs, const float* __restrict__ Wt,
+                                 float* __restrict__ Y, int ys) {
+    TR_EW_LOOP((size_t)N * Ho * Wo * C) {
+        const int c = i % C; size_t r = i / C;
+        const int wo = r % Wo; r /= Wo;
+        const int ho = r % Ho; const int n = r / Ho;
+        float a = 0.f;
+        for (int kh = 0; kh < 3; ++kh) {
+            const int h = ho * s + kh - 1;
+            if (h < 0 || h >= H) continue;
+            for (int kw = 0; kw < 3; ++kw) {
+                const int w = wo * s + kw - 1;
+                if (w < 0 || w >= W) continue;
+                a = fmaf(X[(size_t)((n * H + h) * W + w) * xs + c], Wt[c * 9 + kh * 3 + kw], a);
+            }
+        }
+        Y[(size_t)((n * Ho + ho) * Wo + wo) * ys + c] = a;
+    }
+}
+__global__ void dw3x3_dgrad_kernel(int N, int H, int W, int C, int s, int Ho, int Wo, const float* __restrict__ dY, int dys, const float* __restrict__ Wt,
+                                   float* __restrict__ dX, int dxs) {
+    TR_EW_LOOP((size_t)N * H * W * C) {
+        const int c = i % C; size_t r = i / C;
+        const int w = r % W; r /= W;
+        const int h = r % H; const int n = r / H;
+        float a = 0.f;
+        for (int kh = 0; kh < 3; ++kh) {
+            const int hn = h + 1 - kh;
+            if (hn < 0 || hn % s) continue;
+            const int ho = hn / s;
+            if (ho >= Ho) continue;
+            for (int kw = 0; kw < 3; ++kw) {
+                const int wn = w + 1 - kw;
+                if (wn < 0 || wn % s) continue;
+                const int wo = wn / s;
+                if (wo >= Wo) continue;
+                a = fmaf(dY[(size_t)((n * Ho + ho) * Wo + wo) * dys + c], Wt[c * 9 + kh * 3 + kw], a);
+            }
+        }
+        dX[(size_t)((n * H + h) * W + w) * dxs + c] += a;
+    }
+}
+// dW[c][tap] += sum over output positions of dY * x(tap)   — grid (ceil(C/32), 9), 8 row lanes x 32 channels, fixed order
+__global__ void __launch_bounds__(256) dw3x3_wgrad_kernel(int N, int H, int W, int C, int s, int Ho, int Wo, const float* __restrict__ X, int xs,
+                                                          const float* __restrict__ dY, int dys, float* __restrict__ dW) {
+    __shared__ float part[8][33];
+    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl, tap = blockIdx.y, kh = tap / 3, kw = tap % 3;
+    const int rows = N * Ho * Wo;
+    float a = 0.f;
+    if (c < C)
+        for (int r = rl; r < rows; r += 8) {
+            const int wo = r % Wo, ho = (r / Wo) % Ho, n = r / (Wo * Ho);
+            const int h = ho * s + kh - 1, w = wo * s + kw - 1;
+            if (h < 0 || h >= H || w < 0 || w >= W) continue;
+            a = fmaf(dY[(size_t)r * dys + c], X[(size_t)((n * H + h) * W + w) * xs + c], a);
+        }
+    part[rl][cl] = a;
+    __syncthreads();
+    if (rl == 0 && c < C) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += part[i][cl];
+        dW[c * 9 + tap] += t;
+    }
+}
+// y[:, 2j] = a[:, j], y[:, 2j+1] = b[:, j]   (torch.cat + channel_shuffle(groups=2), shufflenetv2.py:26-40,92-104)
+__global__ void interleave2_fwd_kernel(int rows, int half, const float* __restrict__ A, int as, const float* __restrict__ Bm, int bs, float* __restrict__ Y, int ys) {
+    TR_EW_LOOP((size_t)rows * 2 * half) {
+        const int c = i % (2 * half); const int r = i / (2 * half);
+        Y[(size_t)r * ys + c] = (c & 1) ? Bm[(size_t)r * bs + (c >> 1)] : A[(size_t)r * as + (c >> 1)];
+    }
+}
+__global__ void interleave2_bwd_kernel(int rows, int half, const float* __restrict__ dY, int dys, float* __restrict__ dA, int das, float* __restrict__ dB, int dbs) {
+    TR_EW_LOOP((size_t)rows * 2 * half) {
+        const int c = i % (2 * half); const int r = i / (2 * half);
+        const float d = dY[(size_t)r * dys + c];
+        if (c & 1) { if (dB) dB[(size_t)r * dbs + (c >> 1)] += d; }
+        else if (dA) dA[(size_t)r * das + (c >> 1)] += d;
+    }
+}
+// F.normalize(p=2, dim=-1, eps=1e-12): y = x / max(||x||, eps); one warp per row; nrm saved
+__global__ void __launch_bounds__(256) l2norm_fwd_kernel(int rows, int cols, const float* __restrict__ X, int xs, float* __restrict__ Y, int ys, float* __restrict__ nrm) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    float s = 0.f;
+    for (int c = lane; c < cols; c += 32) { const float x = X[(size_t)r * xs + c]; s = fmaf(x, x, s); }
+    s = fmaxf(sqrtf(warp_sum(s)), 1e-12f);
+    for (int c = lane; c < cols; c += 32) Y[(size_t)r * ys + c] = X[(size_t)r * xs + c] / s;
+    if (lane == 0) nrm[r] = s;
+}
+__global__ void __launch_bounds__(256) l2norm_bwd_kernel(int rows, int cols, const float* __restrict__ Y, int ys, const float* __restrict__ nrm,
+                                                         const float* __restrict__ dY, int dys, float* __restrict__ dX, int dxs) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    float s = 0.f;
+    for (int c = lane; c < cols; c += 32) s = fmaf(Y[(size_t)r * ys + c], dY[(size_t)r * dys + c], s);
+    s = warp_sum(s);
+    const float inv = 1.f / nrm[r];
+    for (int c = lane; c < cols; c += 32) dX[(size_t)r * dxs + c] += (dY[(size_t)r * dys + c] - Y[(size_t)r * ys + c] * s) * inv;
+}
+
 }  // namespace tr
 }  // namespace l2s
 
@@ -802,6 +1037,75 @@ struct Engine {
             ck("col2im");
         });
         return linear(col, W, b);
+    }
+    // ---- video frontend ops ---------------------------------------------------------------------------------------------------
+    // Conv3d stem over the caller's NCDHW clips -> rows (b,t,ho,wo) x 24.  Only the weight gradient exists (the input is data).
+    TT stem_conv(const float* video, int B, int T, int H, int W, const TT& Wt) {
+        const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+        TT y = make(B * T * Ho * Wo, 24);
+        stem_fwd_kernel<<<ew_blocks(y.numel()), 256, 0, s>>>(B, T, H, W, Ho, Wo, video, Wt.v, y.v);
+        ck("stem conv");
+        tape.push_back([=]() {
+            if (!Wt.g) return;
+            const size_t npos = (size_t)B * T * Ho * Wo;
+            const int chunks = (int)std::min<size_t>(148 * 4, (npos + 255) / 256);
+            const int per = (int)((npos + chunks - 1) / chunks);
+            float* part = grads.alloc((size_t)chunks * 24 * 735);
+            stem_wgrad_kernel<<<chunks, 256, 0, s>>>(B, T, H, W, Ho, Wo, per, video, y.g, part);
+            ck("stem wgrad");
+            sum_chunks_kernel<<<ew_blocks(24 * 735), 256, 0, s>>>(24 * 735, chunks, part, Wt.g);
+            ck("stem wgrad sum");
+        });
+        return y;
+    }
+    TT maxpool3x3s2(const TT& x, int N, int H, int W, int* Hout, int* Wout) {
+        const int C = x.cols, Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+        *Hout = Ho; *Wout = Wo;
+        TT y = make(N * Ho * Wo, C);
+        int* idx = reinterpret_cast<int*>(scratch(y.numel()));
+        maxpool_fwd_kernel<<<ew_blocks(y.numel()), 256, 0, s>>>(N, H, W, C, Ho, Wo, x.v, y.v, idx);
+        ck("maxpool");
+        tape.push_back([=]() {
+            if (!x.g) return;
+            maxpool_bwd_kernel<<<ew_blocks(x.numel()), 256, 0, s>>>(N, H, W, C, Ho, Wo, y.g, idx, x.g);
+            ck("maxpool bwd");
+        });
+        return y;
+    }
+    TT dwconv3x3(const TT& x, int N, int H, int W, int stride, const TT& Wt, int* Hout, int* Wout) {
+        const int C = x.cols, Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+        *Hout = Ho; *Wout = Wo;
+        TT y = make(N * Ho * Wo, C);
+        dw3x3_fwd_kernel<<<ew_blocks(y.numel()), 256, 0, s>>>(N, H, W, C, stride, Ho, Wo, x.v, x.rs, Wt.v, y.v, y.rs);
+        ck("dw conv");
+        tape.push_back([=]() {
+            if (x.g) { dw3x3_dgrad_kernel<<<ew_blocks((size_t)N * H * W * C), 256, 0, s>>>(N, H, W, C, stride, Ho, Wo, y.g, y.rs, Wt.v, x.g, x.rs); ck("dw dgrad"); }
+            if (Wt.g) { dw3x3_wgrad_kernel<<<dim3((C + 31) / 32, 9), 256, 0, s>>>(N, H, W, C, stride, Ho, Wo, x.v, x.rs, y.g, y.rs, Wt.g); ck("dw wgrad"); }
+        });
+        return y;
+    }
+    TT interleave2(const TT& a, const TT& b) {
+        const int half = a.cols;
+        TT y = make(a.rows, 2 * half);
+        interleave2_fwd_kernel<<<ew_blocks(y.numel()), 256, 0, s>>>(a.rows, half, a.v, a.rs, b.v, b.rs, y.v, y.rs);
+        ck("interleave");
+        tape.push_back([=]() {
+            interleave2_bwd_kernel<<<ew_blocks(y.numel()), 256, 0, s>>>(a.rows, half, y.g, y.rs, a.g, a.rs, b.g, b.rs);
+            ck("interleave bwd");
+        });
+        return y;
+    }
+    TT l2normalize(const TT& x) {
+        TT y = make(x.rows, x.cols);
+        float* nrm = scratch(x.rows);
+        l2norm_fwd_kernel<<<(x.rows * 32 + 255) / 256, 256, 0, s>>>(x.rows, x.cols, x.v, x.rs, y.v, y.rs, nrm);
+        ck("l2 normalize");
+        tape.push_back([=]() {
+            if (!x.g) return;
+            l2norm_bwd_kernel<<<(x.rows * 32 + 255) / 256, 256, 0, s>>>(x.rows, x.cols, y.v, y.rs, nrm, y.g, y.rs, x.g, x.rs);
+            ck("l2 normalize bwd");
+        });
+        return y;
     }
     TT adaptive_pool(const TT& x, int B, int L, int m) {
         if (L == m) return x;

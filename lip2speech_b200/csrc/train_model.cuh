@@ -223,5 +223,70 @@ struct DecoderTrain {
     }
 };
 
+// ---- VideoExtractor.forward in train mode (video.py:76-87; shufflenetv2.py:42-104; model.py:26 dropout) ---------------
+struct VideoTrain {
+    Engine e;
+    int B = 0, T = 0;
+    TT feat;
+    bool live = false;
+
+    TT pw(const TT& x, const std::string& name, int cout) {        // 1x1 Conv2d, bias=False
+        return e.linear(x, e.param(name + ".weight", cout, x.cols), nullptr);
+    }
+    void forward(Context& ctx, std::map<std::string, Param>& params, const float* video, const float* drop_mask, int B_, int T_, int H, int W,
+                 float* out_feat, cudaStream_t s) {
+        B = B_; T = T_;
+        if (B <= 0 || T <= 0 || (H & 3) || (W & 3)) throw L2sError(1, "video_train_fwd: bad shape");
+        e.begin(&ctx, s, &params);
+        live = false;
+        const std::string P = "encoder.";
+        const int N = B * T;
+        TT x = e.stem_conv(video, B, T, H, W, e.param(P + "frontend3D.0.weight", 24, 735));
+        x = e.prelu(e.batchnorm(x, P + "frontend3D.1"), e.param(P + "frontend3D.2.weight", 1, 24));
+        int h = (H - 1) / 2 + 1, w = (W - 1) / 2 + 1;
+        x = e.maxpool3x3s2(x, N, h, w, &h, &w);
+        for (int blk = 0;; ++blk) {
+            const std::string q = P + "trunk.0." + std::to_string(blk) + ".";
+            if (!params.count(q + "banch2.0.weight")) break;
+            const bool down = params.count(q + "banch1.0.weight") != 0;
+            if (down) {                                             // benchmodel 2: both branches see x, stride 2
+                const int cin = x.cols, half = (int)(params.at(q + "banch2.0.weight").n / cin);
+                int ho, wo;
+                TT b1 = e.dwconv3x3(x, N, h, w, 2, e.param(q + "banch1.0.weight", cin, 9), &ho, &wo);
+                b1 = e.relu(e.batchnorm(pw(e.batchnorm(b1, q + "banch1.1"), q + "banch1.2", half), q + "banch1.3"));
+                TT b2 = e.relu(e.batchnorm(pw(x, q + "banch2.0", half), q + "banch2.1"));
+                b2 = e.batchnorm(e.dwconv3x3(b2, N, h, w, 2, e.param(q + "banch2.3.weight", half, 9), &ho, &wo), q + "banch2.4");
+                b2 = e.relu(e.batchnorm(pw(b2, q + "banch2.5", half), q + "banch2.6"));
+                x = e.interleave2(b1, b2);
+                h = ho; w = wo;
+            } else {                                                // benchmodel 1: x1 passes through, x2 -> branch 2
+                const int half = x.cols / 2;
+                int ho, wo;
+                TT x1 = x.colslice(0, half), x2 = x.colslice(half, half);
+                TT b2 = e.relu(e.batchnorm(pw(x2, q + "banch2.0", half), q + "banch2.1"));
+                b2 = e.batchnorm(e.dwconv3x3(b2, N, h, w, 1, e.param(q + "banch2.3.weight", half, 9), &ho, &wo), q + "banch2.4");
+                b2 = e.relu(e.batchnorm(pw(b2, q + "banch2.5", half), q + "banch2.6"));
+                x = e.interleave2(x1, b2);
+            }
+        }
+        if (h != 3 || w != 3) throw L2sError(1, "video_train_fwd: trunk output must be 3x3 (H, W in {88, 96}) for AvgPool2d(3)");
+        x = e.relu(e.batchnorm(pw(x, P + "trunk.1.0", 768), P + "trunk.1.1"));
+        x = e.adaptive_pool(x, N, 9, 1);                            // AvgPool2d(3) on the 3x3 map
+        x = e.l2normalize(x);                                       // F.normalize(p=2, dim=2), video.py:85
+        if (drop_mask) x = e.dropout(x, drop_mask, 768, 0.1f);      // F.dropout(video_features, 0.1, training), model.py:26
+        feat = x;
+        L2S_CUDA(cudaMemcpyAsync(out_feat, x.v, (size_t)N * 768 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        live = true;
+    }
+    void backward(const float* g_feat, cudaStream_t s) {
+        if (!live) throw L2sError(1, "video_train_bwd: no forward pass to differentiate (call l2s_video_train_fwd first)");
+        e.s = s;
+        e.begin_backward();
+        L2S_CUDA(cudaMemcpyAsync(feat.g, g_feat, (size_t)B * T * 768 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        e.backward();
+        live = false;
+    }
+};
+
 }  // namespace tr
 }  // namespace l2s

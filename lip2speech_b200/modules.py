@@ -49,6 +49,111 @@ def _device_index(module: nn.Module) -> int:
     return p.device.index or 0
 
 
+class TrainNoise:
+    """Every random draw of one train-mode Decoder.forward as explicit tensors: tf_mask [M] (host bool),
+    gumbel [B*minT,501], and KEEP masks (1 = kept) prenet [M,B,256], attn [M,B,T], lstm [M,B,512], post 5 x [B,C,M]."""
+
+    def __init__(self, tf_mask, gumbel, prenet, attn, lstm, post, video_drop=None):
+        self.tf_mask, self.gumbel, self.prenet, self.attn, self.lstm, self.post, self.video_drop = tf_mask, gumbel, prenet, attn, lstm, post, video_drop
+
+    @staticmethod
+    def draw(B, T, M, tf_ratio, device):
+        """Draws in the reference's order (gumbel first, then per step: coin flip on the CPU generator, prenet / attention /
+        LSTM dropout, then the five postnet dropouts) from torch's global generators."""
+        bern = lambda shape, keep: torch.empty(shape, device=device).bernoulli_(keep)
+        gumbel = -torch.empty(B * spec.content_min_t(T), spec.VOCAB, device=device).exponential_().log()
+        tf, prenet, attn, lstm, consumed = [], [], [], [], 0
+        for _ in range(M):
+            use = bool(torch.rand(1) > tf_ratio) and consumed < int(tf_ratio * M)     # decoder.py:355-357
+            consumed += int(use)
+            tf.append(use)
+            prenet.append(bern((B, 256), 0.8)); attn.append(bern((B, T), 0.9)); lstm.append(bern((B, 512), 0.9))
+        post = [bern((B, c, M), 0.5) for c in (512, 512, 512, 512, 80)]
+        return TrainNoise(torch.tensor(tf, dtype=torch.bool), gumbel, torch.stack(prenet), torch.stack(attn), torch.stack(lstm), post)
+
+
+class _DecoderTrainFn(torch.autograd.Function):
+    """Decoder.forward in train mode as ONE autograd node: forward = l2s_decoder_train_fwd, backward = l2s_decoder_train_bwd.
+    The parameters are inputs of the node, so `loss.backward()` (train.py:184) fills p.grad of whatever optimizer owns them."""
+
+    @staticmethod
+    def forward(ctx, be, noise, keys, visual, spk, mels, *params):
+        sizes = [p.numel() for p in params]
+        offs, total = [], 0
+        for n in sizes:
+            offs.append(total); total += (n + 3) // 4 * 4
+        scratch = torch.zeros(total, device=visual.device)
+        views = [scratch[o:o + n].view_as(p) for o, n, p in zip(offs, sizes, params)]
+        for k, p, g in zip(keys, params, views):
+            be.train_bind(k, p.detach(), g)
+        outs = be.decoder_train_fwd(visual, spk, mels, noise, want_input_grads=True)
+        ctx.be, ctx.views, ctx.scratch, ctx.BT = be, views, scratch, (visual.shape[0], visual.shape[1])
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(outs[3])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_mel, g_post, g_stop, g_attn, g_dis):
+        ctx.scratch.zero_()
+        g_visual, g_spk = ctx.be.decoder_train_bwd(g_mel, g_post, g_stop, g_dis, *ctx.BT)
+        return (None, None, None, g_visual, g_spk, None, *ctx.views)
+
+
+class _VideoTrainFn(torch.autograd.Function):
+    """VideoExtractor.forward in train mode (+ the feature dropout of model.py:26) as one autograd node."""
+
+    @staticmethod
+    def forward(ctx, be, drop_mask, keys, video, *params):
+        sizes = [p.numel() for p in params]
+        offs, total = [], 0
+        for n in sizes:
+            offs.append(total); total += (n + 3) // 4 * 4
+        scratch = torch.zeros(total, device=video.device)
+        views = [scratch[o:o + n].view_as(p) for o, n, p in zip(offs, sizes, params)]
+        for k, p, g in zip(keys, params, views):
+            be.train_bind(k, p.detach(), g)
+        ctx.be, ctx.views, ctx.scratch = be, views, scratch
+        return be.video_train_fwd(video, drop_mask)
+
+    @staticmethod
+    def backward(ctx, g_feat):
+        ctx.scratch.zero_()
+        ctx.be.video_train_bwd(g_feat)
+        return (None, None, None, None, *ctx.views)
+
+
+def _bind_buffers(be, module, prefix):
+    for name, buf in module.named_buffers():
+        if buf.is_floating_point():
+            be.train_bind(prefix + name, buf, None)          # pos_table; BatchNorm running statistics (updated in place)
+        elif name.endswith("num_batches_tracked"):
+            buf += 1                                          # nn.BatchNorm*d bookkeeping in train()
+
+
+def video_forward_train(module, prefix, x, drop_mask=None):
+    """Train-mode VideoExtractor.forward for any module owning the reference's encoder parameters under the reference's names."""
+    be = _lib.backend(_device_index(module))
+    _bind_buffers(be, module, prefix)
+    named = [(prefix + n, p) for n, p in module.named_parameters()]
+    return _VideoTrainFn.apply(be, drop_mask, [k for k, _ in named], x, *[p for _, p in named])
+
+
+def decoder_forward_train(module, prefix, encoder_outputs, face_features, mels, tf_ratio, noise=None):
+    """Train-mode Decoder.forward for any module that owns the reference's decoder parameters under the reference's names
+    (the mirror `Decoder` below, or the reference's own class after lip2speech_b200.patch.patch())."""
+    be = _lib.backend(_device_index(module))
+    B, T = encoder_outputs.shape[:2]
+    M = mels.shape[2]
+    if noise is None:
+        noise = TrainNoise.draw(B, T, M, float(tf_ratio), encoder_outputs.device)
+    _bind_buffers(be, module, prefix)
+    named = [(prefix + n, p) for n, p in module.named_parameters()]
+    keys, params = [k for k, _ in named], [p for _, p in named]
+    spk = face_features[:, 0]
+    out_mel, out_post, out_stop, out_attn, out_dis = _DecoderTrainFn.apply(be, noise, keys, encoder_outputs, spk, mels, *params)
+    return [out_mel, out_post, out_stop, spk, out_attn, out_dis]
+
+
 class VideoExtractor(ParamTree):
     """Conv3d stem + per-frame ShuffleNetV2 x1.0 trunk + L2 norm (reference video.py:26-87)."""
 
@@ -57,10 +162,9 @@ class VideoExtractor(ParamTree):
         self.backend_out = spec.VIDEO_FEAT
         self.precision = _lib.PRECISION_FP32
 
-    def forward(self, x):
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError("VideoExtractor.forward in train mode (BatchNorm batch statistics, autograd) is not built; "
-                                      "call .eval() or wrap the call in torch.no_grad()")
+    def forward(self, x, drop_mask=None):
+        if self.training:                      # BatchNorm batch statistics + autograd (drop_mask: the dropout of model.py:26, fused in)
+            return video_forward_train(self, "encoder.", x, drop_mask)
         be = _lib.backend(_device_index(self))
         be.sync_module(self, "encoder.", _lib.PART_VIDEO)
         return be.video_fwd(x, self.precision)
@@ -137,13 +241,13 @@ class Decoder(ParamTree):
             mask.append(use)
         return torch.tensor(mask, dtype=torch.bool)
 
-    def forward(self, encoder_outputs, face_features, mels, text_lengths, output_lengths, tf_ratio, gumbel_noise=None):
-        """Decoder.forward (decoder.py:320-379) in EVAL mode — the path evaluate.py:38 takes.  Returns
+    def forward(self, encoder_outputs, face_features, mels, text_lengths, output_lengths, tf_ratio, gumbel_noise=None, train_noise=None):
+        """Decoder.forward (decoder.py:320-379).  train(): one autograd node over the train-mode CUDA forward / backward
+        (BatchNorm batch statistics, every dropout site, BPTT; `train_noise` = explicit TrainNoise, drawn if omitted).  EVAL mode — the path evaluate.py:38 takes.  Returns
         [outputs [B,80,M], post [B,80,M], stop_logits [B,M,1], face [B,256], attention logits (pre-softmax) [B,M,T],
-        content_dis [B*minT,501]].  Train mode (dropouts, BN batch statistics, autograd) is not built: it raises."""
+        content_dis [B*minT,501]]."""
         if self.training:
-            raise NotImplementedError("Decoder.forward in train mode (dropout, autograd; SURVEY.md §8 rows a10-train/a13) is not "
-                                      "built yet; call .eval() for the evaluate.py path")
+            return decoder_forward_train(self, "decoder.", encoder_outputs, face_features, mels, tf_ratio, noise=train_noise)
         be = self._sync()
         B, T = encoder_outputs.shape[:2]
         if gumbel_noise is None:
@@ -179,18 +283,30 @@ class Lip2Speech(nn.Module):
             visual_features = torch.cat([video_features, face_features], dim=2)
             return self.decoder.inference(visual_features, face_features, gumbel_noise=gumbel_noise, **kwargs)
 
-    def forward(self, video_frames, face_frames, audio_frames, melspecs, video_lengths, audio_lengths, melspec_lengths, tf_ratio):
-        """model.py:23-40 in eval mode (what evaluate.py:38 calls).  The face embedding comes from the attached `vgg_face`
-        module (third-party InceptionResnetV1, out of scope) exactly as in the reference."""
+    def forward(self, video_frames, face_frames, audio_frames, melspecs, video_lengths, audio_lengths, melspec_lengths, tf_ratio,
+                speaker_embedding=None, train_noise=None):
+        """model.py:23-40.  eval(): what evaluate.py:38 calls.  train(): what train.py:167 calls — train-mode video frontend,
+        feature dropout (model.py:26), train-mode decoder, all on the CUDA train path with autograd nodes, so
+        `loss.backward()` (train.py:184) produces the gradients of every encoder.* / decoder.* parameter.  The face embedding
+        comes from the attached `vgg_face` module (third-party InceptionResnetV1, frozen: not in the optimizer, train.py:102-104)
+        exactly as in the reference, or from `speaker_embedding` [B,256] when given."""
+        if speaker_embedding is None:
+            if not hasattr(self, "vgg_face"):
+                raise RuntimeError("Lip2Speech.forward needs the vgg_face module (model.py:31) or a speaker_embedding; attach the reference's FaceRecognizer")
+            speaker_embedding = self.vgg_face.inference(face_frames[:, 0, :, :, :])
         if self.training:
-            raise NotImplementedError("Lip2Speech.forward in train mode is not built yet (SURVEY.md §8 rows a10-train/a13)")
-        if not hasattr(self, "vgg_face"):
-            raise RuntimeError("Lip2Speech.forward needs the vgg_face module (model.py:31); attach the reference's FaceRecognizer")
+            B, T = video_frames.shape[0], video_frames.shape[2]
+            keep = train_noise.video_drop if train_noise is not None and train_noise.video_drop is not None else \
+                torch.empty(B, T, 768, device=video_frames.device).bernoulli_(0.9)               # F.dropout(..., 0.1, training)
+            video_features = self.encoder(video_frames, keep)
+            face_features = speaker_embedding.unsqueeze(1).repeat(1, T, 1)
+            visual_features = torch.cat([video_features, face_features], dim=2)
+            outputs = self.decoder(visual_features, face_features, melspecs, video_lengths, melspec_lengths, tf_ratio, train_noise=train_noise)
+            return outputs + [video_lengths]
         with torch.no_grad():
             video_features = self.encoder(video_frames)                    # F.dropout(..., training=False) is the identity
-            face_features = self.vgg_face.inference(face_frames[:, 0, :, :, :])
             N, T, C = video_features.shape
-            face_features = face_features.unsqueeze(1).repeat(1, T, 1)
+            face_features = speaker_embedding.unsqueeze(1).repeat(1, T, 1)
             visual_features = torch.cat([video_features, face_features], dim=2)
             outputs = self.decoder(visual_features, face_features, melspecs, video_lengths, melspec_lengths, tf_ratio)
         return outputs + [video_lengths]

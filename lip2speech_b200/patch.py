@@ -10,8 +10,10 @@ state_dict keys — the same keys the mirror modules use), the backend re-packs 
     net = model.get_network('test').cuda()       # everything below model.py now runs in libl2s_b200.so
 
 `Postnet.forward` is not patched on its own: it is only reached through `Decoder.forward/inference`, which are replaced
-as a whole.  Train mode raises (the train-mode forward / backward kernels are not built).  `unpatch()`
-restores the PyTorch bodies.
+as a whole.  In train() mode the same methods run the train-mode CUDA forward as autograd nodes (BatchNorm batch statistics,
+every dropout site, BPTT), so `loss.backward()` of train.py:184 fills the reference modules' own p.grad.  With the patched
+reference classes the feature dropout of model.py:26 stays the reference's own F.dropout call.  `unpatch()` restores the
+PyTorch bodies.
 """
 from __future__ import annotations
 
@@ -23,10 +25,8 @@ _saved = {}
 
 
 def _video_forward(self, x):
-    import torch
-    if self.training and torch.is_grad_enabled():
-        raise NotImplementedError("VideoExtractor.forward in train mode (BatchNorm batch statistics, autograd) is not built on the "
-                                  "B200 backend; call .eval() or lip2speech_b200.patch.unpatch() to train in PyTorch")
+    if self.training:                          # train.py:167 -> model.py:26: BatchNorm batch statistics + autograd on the CUDA train path
+        return modules.video_forward_train(self, "encoder.", x)
     be = _lib.backend(modules._device_index(self))
     be.sync_module(self, "encoder.", _lib.PART_VIDEO)
     return be.video_fwd(x, getattr(self, "precision", _lib.PRECISION_FP32))
@@ -47,9 +47,8 @@ def _decoder_inference(self, encoder_outputs, face_features, return_attention_ma
 
 
 def _decoder_forward(self, encoder_outputs, face_features, mels, text_lengths, output_lengths, tf_ratio, gumbel_noise=None):
-    if self.training:
-        raise NotImplementedError("Decoder.forward in train mode is not built on the B200 backend yet (DESIGN.md §8); "
-                                  "call .eval() for the evaluate.py path or lip2speech_b200.patch.unpatch() to train in PyTorch")
+    if self.training:                          # train.py:167: dropouts, BatchNorm batch statistics, BPTT — one autograd node
+        return modules.decoder_forward_train(self, "decoder.", encoder_outputs, face_features, mels, tf_ratio)
     be = _decoder_sync(self)
     B, T = encoder_outputs.shape[:2]
     if gumbel_noise is None:

@@ -29,8 +29,9 @@ def test_patch_rebinds_reference_classes_and_fails_loudly_without_gpu():
                 dec.inference(torch.zeros(1, 29, 1024), torch.zeros(1, 29, 256))
             with pytest.raises(RuntimeError, match="CUDA"):
                 vid(torch.zeros(1, 3, 5, 96, 96))
-        with pytest.raises(NotImplementedError):
-            Decoder().train()(torch.zeros(1, 29, 1024), torch.zeros(1, 29, 256), torch.zeros(1, 80, 8), None, None, 0.5)
+        if not torch.cuda.is_available():              # train mode routes into the CUDA train path as well: no CPU fallback either
+            with pytest.raises(RuntimeError, match="CUDA"):
+                Decoder().train()(torch.zeros(1, 29, 1024), torch.zeros(1, 29, 256), torch.zeros(1, 80, 8), None, None, 0.5)
     finally:
         b200.unpatch()
     assert (Decoder.inference, Decoder.forward, VideoExtractor.forward, SpeakerEncoder.forward) == orig

@@ -115,3 +115,94 @@ def test_train_backward_is_deterministic_and_accumulates(be):
         assert torch.allclose(grads[k], 2 * v, rtol=1e-6, atol=0), k
     with pytest.raises(RuntimeError):
         be.decoder_train_bwd(*g_out, B, T)           # the tape was consumed
+
+
+def test_video_train_forward_backward_vs_oracle(be):
+    """VideoExtractor.forward in train mode (Conv3d stem + BatchNorm batch statistics + PReLU + MaxPool3d + 16 ShuffleNetV2
+    blocks + conv_last + AvgPool + L2 norm) + the dropout of model.py:26: features and the gradient of every encoder
+    parameter against autograd on the oracle, plus the updated BatchNorm running statistics."""
+    from oracle import l2s_oracle as O, train_oracle as TO
+    B, T, H = 2, 5, 88
+    w = spec.seeded_state_dict(spec.encoder_spec("encoder."), 1234)
+    video = synth.video(B, T, H, H, seed=9)
+    keep = torch.empty(B, T, 768).bernoulli_(0.9, generator=torch.Generator().manual_seed(4))
+    g_out = torch.randn(B, T, 768, generator=torch.Generator().manual_seed(5))
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not spec.is_buffer(k) else v.clone()) for k, v in w.items()}
+    bn_new = {}
+    with TO.bn_train(bn_new):
+        ref = TO._drop(O.video_features(sd, video, "encoder."), keep, 0.1)
+    (ref * g_out).sum().backward()
+
+    dev, grads = _bind(be, w)
+    feat = be.video_train_fwd(video.cuda(), keep.cuda())
+    assert rel_err(feat.cpu(), ref.detach()) < 1e-3
+    be.video_train_bwd(g_out.cuda())
+    torch.cuda.synchronize()
+    errs = {}
+    for k, p in sd.items():
+        if torch.is_tensor(p) and p.requires_grad:
+            assert p.grad is not None, k
+            errs[k] = rel_err(grads[k].cpu(), p.grad)
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
+    print("worst gradient deviations:", worst)
+    assert worst[0][1] < 2e-3, worst
+    assert len(bn_new) == 2 * 56
+    for k, v in bn_new.items():
+        assert rel_err(dev[k].cpu(), v) < 1e-4, k
+
+
+def test_full_train_step_through_mirror_modules(be):
+    """train.py:167-193 with the mirror modules: net.train(); net(...) -> Loss -> loss.backward() -> ClipAdamW.step().
+    Gradients reach every encoder.* and decoder.* parameter through the two autograd nodes and match autograd on the oracle;
+    after the optimizer step the (eval) forward runs on the UPDATED weights."""
+    from lip2speech_b200 import modules
+    from lip2speech_b200.train_step import ClipAdamW, Loss
+    from oracle import train_oracle as TO
+    B, T, M, H = 2, 7, 6, 88
+    w = spec.seeded_state_dict(spec.full_spec(), 1234)
+    w["decoder.temperature"] = torch.full_like(w["decoder.temperature"], 1.0)
+    w["decoder.content.temperature"] = torch.full_like(w["decoder.content.temperature"], 1.0)
+    net_sd = {k: v for k, v in w.items() if not k.startswith("speaker_encoder.")}
+    net = modules.get_network("train")
+    net.load_state_dict(net_sd, strict=True)
+    net = net.cuda()
+    video = synth.video(B, T, H, H, seed=2)
+    spk = synth.speaker_embedding(B, seed=2)
+    mels = synth.mel_like(B, M, seed=2) * 2 - 5
+    gate_t = torch.zeros(B, M); gate_t[:, -2:] = 1
+    noise = TO.reference_noise(B, T, M, 0.5, with_video=True, generator=torch.Generator().manual_seed(8))
+    # oracle
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not spec.is_buffer(k) else v.clone()) for k, v in net_sd.items()}
+    ref = TO.lip2speech_forward_train(sd, video, spk, mels, noise)
+    ref_losses = TO.loss_forward(ref, (mels, gate_t))
+    sum(ref_losses.values()).backward()
+    # CUDA path through the reference-shaped API
+    opt = ClipAdamW([{"params": net.decoder.parameters()}, {"params": net.encoder.parameters()}], lr=1e-3, max_norm=1.0)   # train.py:102-104
+    lens = torch.full((B,), T, dtype=torch.long)
+    tn = modules.TrainNoise(noise.tf_mask, noise.gumbel.cuda(), noise.prenet.cuda(), noise.attn.cuda(), noise.lstm.cuda(),
+                            [t.cuda() for t in noise.post], video_drop=noise.video_drop.cuda())
+    opt.zero_grad()
+    out = net(video.cuda(), None, None, mels.cuda(), lens, None, lens, 0.5, speaker_embedding=spk.cuda(), train_noise=tn)
+    losses = Loss()(out, (mels.cuda(), gate_t.cuda()))
+    loss = sum(losses.values())
+    assert abs(float(loss) - float(sum(ref_losses.values()))) < 1e-3 * abs(float(sum(ref_losses.values())))
+    loss.backward()
+    errs = {}
+    for k, p in net.named_parameters():
+        assert p.grad is not None, k
+        if ZERO_GRAD_BIAS.search(k):
+            continue
+        errs[k] = rel_err(p.grad.cpu(), sd[k].grad)
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
+    print("worst gradient deviations:", worst)
+    assert worst[0][1] < 5e-3, worst
+    before = {k: p.detach().clone() for k, p in net.named_parameters()}
+    opt.step()
+    moved = sum(int(not torch.equal(before[k], p.detach())) for k, p in net.named_parameters())
+    assert moved == len(before)
+    # eval forward after the step: packed weights were invalidated, BatchNorm running statistics moved
+    net.eval()
+    with torch.no_grad():
+        mel, lengths = net.inference(video.cuda(), None, spk.cuda(), gumbel_noise=noise.gumbel.cuda())
+    assert torch.isfinite(mel).all()
+    assert int(net.decoder.state_dict()["postnet.convolutions.0.1.num_batches_tracked"]) == 1
