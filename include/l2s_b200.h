@@ -144,7 +144,7 @@ int l2s_allreduce_grads(l2s_ctx* ctx, float* flat_grads, int64_t n, float scale,
  * on flat device buffers p, g, m, v, vmax of n floats; sqnorm = ||g||^2 from l2s_allreduce_grads; step = 1, 2, ...
  * g is left clipped, as clip_grad_norm_ leaves p.grad. */
 int l2s_clip_adamw_step(l2s_ctx* ctx, float* p, float* g, float* m, float* v, float* vmax, int64_t n, const float* sqnorm,
-                        float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                        double max_norm, double lr, double beta1, double beta2, double eps, double weight_decay, int step,
                         void* stream);
 
 /* ---- train-mode forward + backward (train.py:167 net(...), :184 loss.backward()) -----------------------------------------

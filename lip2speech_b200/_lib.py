@@ -73,7 +73,8 @@ def load() -> C.CDLL:
         lib.l2s_comm_init.argtypes = [vp, vp, i, i, i]
         lib.l2s_comm_destroy.argtypes = [vp]
         lib.l2s_allreduce_grads.argtypes = [vp, fp, C.c_int64, f, fp, vp]
-        lib.l2s_clip_adamw_step.argtypes = [vp, fp, fp, fp, fp, fp, C.c_int64, fp, f, f, f, f, f, f, i, vp]
+        d = C.c_double
+        lib.l2s_clip_adamw_step.argtypes = [vp, fp, fp, fp, fp, fp, C.c_int64, fp, d, d, d, d, d, d, i, vp]
         _lib = lib
         return lib
 

@@ -759,23 +759,19 @@ static void decoder_run(Context& c, const float* visual, const float* spk, const
             L2S_CUDA(cudaMemcpyAsync(dmask, fw.tf_mask, steps, cudaMemcpyHostToDevice, s));
             tfm = dmask; p1t = p1tb;
         }
-        // exchange buffers of tagged 64-bit words (decode3.cuh); tags of this call live in [tag_base, tag_base + D3_TAG_SPAN)
-        ll_t* xS = static_cast<ll_t*>(c.buf("ws.d.xS", 2 * 2 * plane * sizeof(ll_t)));
-        ll_t* xC = static_cast<ll_t*>(c.buf("ws.d.xC", 2 * plane * sizeof(ll_t)));
-        ll_t* xP1 = static_cast<ll_t*>(c.buf("ws.d.xP1", (size_t)256 * Bpad * sizeof(ll_t)));
-        ll_t* xXD = static_cast<ll_t*>(c.buf("ws.d.xXD", (size_t)1024 * Bpad * sizeof(ll_t)));
-        ll_t* xQ = static_cast<ll_t*>(c.buf("ws.d.xQ", (size_t)512 * Bpad * sizeof(ll_t)));
-        ll_t* xCQ = static_cast<ll_t*>(c.buf("ws.d.xCQ", (size_t)256 * Bpad * sizeof(ll_t)));
+        // exchange buffers of tagged fp32 words (decode3.cuh), zero-filled before every call: tag 0 = "never written"
+        const size_t xfloats = (size_t)(2 * 1024 + 1024 + 256 + 1024 + 512 + 256) * Bpad;
+        float* xbase = c.fbuf("ws.d.xchg", xfloats);
+        L2S_CUDA(cudaMemsetAsync(xbase, 0, xfloats * sizeof(float), s));
+        float* xS = xbase;
+        float* xC = xS + 2 * 2 * plane;
+        float* xP1 = xC + 2 * plane;
+        float* xXD = xP1 + (size_t)256 * Bpad;
+        float* xQ = xXD + (size_t)1024 * Bpad;
+        float* xCQ = xQ + (size_t)512 * Bpad;
         unsigned* abortw = static_cast<unsigned*>(c.buf("ws.d.abort", 256));
-        int64_t& epoch = c.meta["d.step3.epoch"];
-        if (++epoch >= (int64_t)(0xffffffffu / D3_TAG_SPAN) - 1) {        // tag space exhausted: wipe every stale tag and start over
-            for (const char* n : {"ws.d.xS", "ws.d.xC", "ws.d.xP1", "ws.d.xXD", "ws.d.xQ", "ws.d.xCQ"})
-                L2S_CUDA(cudaMemsetAsync(c.bufs.at(n).p, 0, c.bufs.at(n).bytes, s));
-            epoch = 1;
-        }
-        const uint32_t tag_base = (uint32_t)epoch * D3_TAG_SPAN;
         // initial state: hidden = the Bi-LSTM's final (h_fwd ; h_bwd), cell.fill_(0) (decoder.py:392,406)
-        d3_init_state_kernel<<<ew_grid(2 * plane), 256, 0, s>>>(hfinal, xS, xC, Bpad, tag_base);
+        d3_init_state_kernel<<<ew_grid(2 * plane), 256, 0, s>>>(hfinal, xS, xC, Bpad);
         check_launch(c, "initial decoder state");
         float* vsplit = c.fbuf("ws.d.Vsplit", (size_t)B * T * 512);
         float* cvsplit = c.fbuf("ws.d.cvsplit", (size_t)B * minT * 256);
@@ -800,7 +796,7 @@ static void decoder_run(Context& c, const float* visual, const float* spk, const
             q.S = xS + (size_t)g0 * 1024 * D3_CG; q.Cst = xC + (size_t)g0 * 1024 * D3_CG;
             q.P1 = xP1 + (size_t)g0 * 256 * D3_CG; q.XD = xXD + (size_t)g0 * 1024 * D3_CG;
             q.Q = xQ + (size_t)b0 * 512; q.CQ = xCQ + (size_t)b0 * 256;
-            q.tag_base = tag_base; q.abort_word = abortw;
+            q.abort_word = abortw;
             q.d.Kmem = Kmem + (size_t)b0 * T * 512; q.d.Vmem = Vmem + (size_t)b0 * T * 512;
             q.d.ckey = ckey + (size_t)b0 * minT * 256; q.d.cval = cval + (size_t)b0 * minT * 256;
             q.d.stop_const = stopc + b0;
@@ -1234,17 +1230,19 @@ int l2s_allreduce_grads(l2s_ctx* ctx, float* flat_grads, int64_t n, float scale,
 }
 
 int l2s_clip_adamw_step(l2s_ctx* ctx, float* p, float* g, float* m, float* v, float* vmax, int64_t n, const float* sqnorm,
-                        float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay, int step, void* stream) {
+                        double max_norm, double lr, double beta1, double beta2, double eps, double weight_decay, int step, void* stream) {
     if (!ctx) return L2S_ERR_INVALID;
     API_BEGIN
     Context& c = ctx->c;
-    if (!p || !g || !m || !v || !vmax || n <= 0 || step < 1 || (max_norm > 0.f && !sqnorm)) throw L2sError(L2S_ERR_INVALID, "clip_adamw_step: bad arguments");
+    if (!p || !g || !m || !v || !vmax || n <= 0 || step < 1 || (max_norm > 0.0 && !sqnorm)) throw L2sError(L2S_ERR_INVALID, "clip_adamw_step: bad arguments");
     for (const void* q : {(const void*)p, (const void*)g, (const void*)m, (const void*)v, (const void*)vmax})
         if (reinterpret_cast<uintptr_t>(q) & 15) throw L2sError(L2S_ERR_INVALID, "clip_adamw_step: flat buffers must be 16-byte aligned");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     L2S_CUDA(cudaSetDevice(c.device));
-    AdamWParams a{lr, beta1, beta2, eps, weight_decay, max_norm,
-                  (float)(1.0 - std::pow((double)beta1, (double)step)), (float)std::sqrt(1.0 - std::pow((double)beta2, (double)step))};
+    // hyper-parameters arrive as doubles (Python floats): every derived constant is formed in double and rounded once, as torch does
+    AdamWParams a{(float)lr, (float)beta1, (float)beta2, (float)eps, (float)weight_decay, (float)max_norm,
+                  (float)(1.0 - std::pow(beta1, (double)step)), (float)std::sqrt(1.0 - std::pow(beta2, (double)step)),
+                  (float)(lr / (1.0 - std::pow(beta1, (double)step))), (float)(1.0 - beta1), (float)(1.0 - beta2), (float)(1.0 - lr * weight_decay)};
     clip_adamw_kernel<<<ts_grid(c, (size_t)n / 4), TS_THREADS, 0, s>>>(p, g, m, v, vmax, (size_t)n, sqnorm, a);
     check_launch(c, "clip + AdamW");
     API_END(ctx)

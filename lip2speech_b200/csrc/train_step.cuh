@@ -68,6 +68,9 @@ __global__ void sqnorm_finish_kernel(const double* __restrict__ partial, int nbl
 struct AdamWParams {
     float lr, beta1, beta2, eps, weight_decay, max_norm;
     float bc1, bc2_sqrt;          // 1 - beta1^t, sqrt(1 - beta2^t)   (host, double precision)
+    float step_size;              // lr / (1 - beta1^t)
+    float omb1, omb2, decay;      // 1 - beta1, 1 - beta2, 1 - lr*wd: formed in DOUBLE on the host and rounded once, as torch does
+                                  // (1.0f - 0.999f = 0.00099998712 is 1.3e-5 away from (float)0.001)
 };
 
 // torch.nn.utils.clip_grad_norm_ (clip_coef = max_norm / (norm + 1e-6), clamped to 1) followed by torch.optim.AdamW
@@ -76,12 +79,12 @@ struct AdamWParams {
 //   p -= (lr / bc1) * m / (sqrt(vmax) / sqrt(bc2) + eps)
 __device__ __forceinline__ void adamw_one(float& p, float& g, float& m, float& v, float& vmax, float coef, const AdamWParams& a) {
     g *= coef;
-    p *= 1.0f - a.lr * a.weight_decay;
-    m = m + (g - m) * (1.0f - a.beta1);
-    v = v * a.beta2 + (1.0f - a.beta2) * g * g;
+    p *= a.decay;
+    m = m + (g - m) * a.omb1;
+    v = v * a.beta2 + a.omb2 * g * g;
     vmax = fmaxf(vmax, v);
     const float denom = sqrtf(vmax) / a.bc2_sqrt + a.eps;
-    p = p - (a.lr / a.bc1) * (m / denom);
+    p = p - a.step_size * (m / denom);
 }
 
 __global__ void __launch_bounds__(TS_THREADS) clip_adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,

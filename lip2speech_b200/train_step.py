@@ -67,8 +67,9 @@ class ClipAdamW:
         the size of the communicator set up with init_data_parallel (1 without one)."""
         params = list(params)
         if params and isinstance(params[0], dict):
-            self._group_sizes = [len(list(g["params"])) for g in params]
-            params = [p for g in params for p in g["params"]]
+            groups = [list(g["params"]) for g in params]          # group["params"] may be a generator (train.py:102-103)
+            self._group_sizes = [len(g) for g in groups]
+            params = [p for g in groups for p in g]
         else:
             self._group_sizes = [len(params)]
         self.params = params

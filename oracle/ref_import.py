@@ -11,7 +11,8 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("L2S_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference")      # oracle/stage_reference.sh (git-ignored)
+REF_ROOT = os.environ.get("L2S_REFERENCE_ROOT") or ("/root/reference" if os.path.isdir("/root/reference/model/modules") else _STAGED)
 
 
 def available() -> bool:
@@ -41,6 +42,8 @@ def import_reference():
     class _NoFace(nn.Module):            # stands in for InceptionResnetV1 (out of scope, needs network)
         def __init__(self, **kw):
             super().__init__()
+            self.last_linear = nn.Linear(1, 1)          # vgg_face.py:19-20 touches these two attributes in its constructor
+            self.last_bn = nn.BatchNorm1d(1)
 
     _shim("facenet_pytorch", InceptionResnetV1=_NoFace)
     _shim("fairseq")

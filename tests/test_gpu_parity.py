@@ -240,9 +240,10 @@ def test_batch_70_chunked_decode_vs_oracle(be, O, weights):
     assert torch.equal(lengths.cpu(), ref_len)
     assert rel_err(mel.cpu(), ref_mel) < TOL
     _attn_agree(attn.cpu(), ref_attn)
-    # a clip's result does not depend on the chunk it lands in
+    # a clip's result does not depend on the chunk it lands in (the pre-loop GEMMs pick their tiling from the row count, so
+    # the comparison across batch sizes is to rounding, not bit-exact)
     m2, l2 = be.decoder_infer(visual[32:64].cuda(), face[32:64, 0].cuda(), g[4 * 32:4 * 64].cuda(), steps=30)
-    assert torch.equal(m2, mel[32:64]) and torch.equal(l2, lengths[32:64])
+    assert rel_err(m2.cpu(), mel[32:64].cpu()) < 1e-4 and torch.equal(l2, lengths[32:64])
     video = synth.video(35, 5, 88, 88, seed=5)
     f = be.video_fwd(video.cuda(), precision=_lib.PRECISION_BF16)
     f1 = be.video_fwd(video[32:].cuda(), precision=_lib.PRECISION_BF16)
@@ -416,9 +417,9 @@ def test_decoder_forward_eval(be, O, golden, weights):
         assert rel_err(o[4].cpu(), golden[name + "_attn_logits"]) < TOL
         assert rel_err(o[5].cpu(), golden[name + "_cdis"]) < TOL
         assert torch.equal(o[3].cpu(), face[:, 0])
-    dec.train()
-    with pytest.raises(NotImplementedError):
-        dec(visual.cuda(), face.cuda(), mels.cuda(), lens, lens, 0.5)
+    dec.train()                                   # train mode: the CUDA train path (tests/test_train_model_gpu.py)
+    o = dec(visual.cuda(), face.cuda(), mels.cuda(), lens, lens, 0.5)
+    assert o[1].requires_grad and o[1].shape == (2, 80, 24)
 
 
 def test_unsupported_shapes_are_errors(be):

@@ -12,6 +12,8 @@ from lip2speech_b200 import spec, synth
 
 pytestmark = pytest.mark.gpu
 ZERO_GRAD_BIAS = re.compile(r"(postnet\.convolutions\.\d\.0\.conv|[KV]\.0\.conv\.\d\.0|content\.agg\.\d\.0)\.bias$")
+# BatchNorm biases followed by a bias-free 1x1 conv and another train-mode BatchNorm: the shift is removed again, true gradient 0
+ZERO_GRAD_BN_BIAS = re.compile(r"(banch2\.4|banch1\.1)\.bias$")
 
 
 @pytest.fixture(scope="module")
@@ -86,8 +88,11 @@ def test_decoder_train_forward_backward_vs_oracle(be, B, T, M, tf_ratio, soft, s
         errs[k] = rel_err(got, p.grad)
     worst = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
     print("worst gradient deviations:", worst)
+    # soft-attention cases agree to ~1e-4.  With the seeded sqrt(512) temperature the attention is one-hot-sharp and the
+    # gradients that pass through it (the K path, Q, the temperatures) are ill-conditioned in fp32: the oracle itself deviates
+    # from the unmodified reference by up to 4e-2 there (tests/test_train_oracle_vs_reference.py), so the bound is looser
     for k, e in errs.items():
-        assert e < (5e-2 if k.endswith("temperature") and not soft else 2e-3), (k, e)
+        assert e < (2e-3 if soft else (5e-2 if k.endswith("temperature") else 1e-2)), (k, e)
     # BatchNorm running statistics were updated in place (momentum 0.1, unbiased variance)
     assert len(bn_new) == 2 * 17
     for k, v in bn_new.items():
@@ -111,41 +116,70 @@ def test_train_backward_is_deterministic_and_accumulates(be):
     be.decoder_train_fwd(visual.cuda(), face[:, 0].cuda(), mels.cuda(), noise)
     gv2, _ = be.decoder_train_bwd(*g_out, B, T)
     assert torch.equal(gv1, gv2)
-    for k, v in first.items():
-        assert torch.allclose(grads[k], 2 * v, rtol=1e-6, atol=0), k
+    for k, v in first.items():          # second pass accumulated on top of the first (sums over steps re-associate: not bit-exact 2x)
+        assert torch.allclose(grads[k], 2 * v, rtol=1e-4, atol=1e-6 * float(v.abs().max())), k
     with pytest.raises(RuntimeError):
         be.decoder_train_bwd(*g_out, B, T)           # the tape was consumed
+
+
+def _cast_sd(w, dt):
+    return {k: (v.clone().to(dt).requires_grad_(True) if v.is_floating_point() and not spec.is_buffer(k)
+                else (v.clone().to(dt) if v.is_floating_point() else v.clone())) for k, v in w.items()}
+
+
+def _check_against_fp64(got, yardsticks, g64, skip, floor=2e-3, slack=4.0):
+    """Deep train-mode BatchNorm + ReLU stacks on a small batch are ill-conditioned: a 1e-6 relative difference in the forward
+    pass (fp32 rounding in another summation order) flips individual ReLU decisions, and ONE flipped element moves some
+    gradients by percents (measured: the fp64 oracle fed a clip perturbed by 1e-6 deviates from itself by 4.3e-2 on
+    trunk.1.0.weight — the very number the CUDA path shows).  So every gradient is measured against the fp64 oracle and must
+    be as close to it as the yardstick runs are (torch fp32, and fp64 with 2e-6 input noise) x slack, or within `floor`."""
+    worst = []
+    for k, truth in g64.items():
+        if skip(k):
+            continue
+        e_gpu = rel_err(got[k].double(), truth)
+        e_ref = max(rel_err(y[k].double(), truth) for y in yardsticks)
+        worst.append((e_gpu / max(floor, slack * e_ref), k, e_gpu, e_ref))
+    worst.sort(reverse=True)
+    print("worst (ratio to allowance, key, cuda-vs-fp64, yardstick-vs-fp64):", worst[:5])
+    assert worst[0][0] <= 1.0, worst[:5]
 
 
 def test_video_train_forward_backward_vs_oracle(be):
     """VideoExtractor.forward in train mode (Conv3d stem + BatchNorm batch statistics + PReLU + MaxPool3d + 16 ShuffleNetV2
     blocks + conv_last + AvgPool + L2 norm) + the dropout of model.py:26: features and the gradient of every encoder
-    parameter against autograd on the oracle, plus the updated BatchNorm running statistics."""
+    parameter against autograd on the oracle (fp64 truth, fp32 as the noise yardstick), plus the BatchNorm running statistics."""
     from oracle import l2s_oracle as O, train_oracle as TO
     B, T, H = 2, 5, 88
     w = spec.seeded_state_dict(spec.encoder_spec("encoder."), 1234)
     video = synth.video(B, T, H, H, seed=9)
     keep = torch.empty(B, T, 768).bernoulli_(0.9, generator=torch.Generator().manual_seed(4))
     g_out = torch.randn(B, T, 768, generator=torch.Generator().manual_seed(5))
-    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not spec.is_buffer(k) else v.clone()) for k, v in w.items()}
-    bn_new = {}
-    with TO.bn_train(bn_new):
-        ref = TO._drop(O.video_features(sd, video, "encoder."), keep, 0.1)
-    (ref * g_out).sum().backward()
 
+    jitter = torch.randn(video.shape, generator=torch.Generator().manual_seed(1), dtype=torch.float64)
+
+    def oracle(dt, noise=0.0):
+        sd = _cast_sd(w, dt)
+        bn_new = {}
+        v = video.to(dt) * (1 + noise * jitter.to(dt)) if noise else video.to(dt)
+        with TO.bn_train(bn_new):
+            ref = TO._drop(O.video_features(sd, v, "encoder."), keep.to(dt), 0.1)
+        (ref * g_out.to(dt)).sum().backward()
+        return ref.detach(), {k: p.grad for k, p in sd.items() if torch.is_tensor(p) and p.requires_grad}, bn_new
+
+    ref32, g32, bn_new = oracle(torch.float32)
+    ref64, g64, _ = oracle(torch.float64)
+    _, gnz, _ = oracle(torch.float64, 2e-6)
     dev, grads = _bind(be, w)
     feat = be.video_train_fwd(video.cuda(), keep.cuda())
-    assert rel_err(feat.cpu(), ref.detach()) < 1e-3
+    assert rel_err(feat.cpu(), ref32) < 1e-3
     be.video_train_bwd(g_out.cuda())
     torch.cuda.synchronize()
-    errs = {}
-    for k, p in sd.items():
-        if torch.is_tensor(p) and p.requires_grad:
-            assert p.grad is not None, k
-            errs[k] = rel_err(grads[k].cpu(), p.grad)
-    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
-    print("worst gradient deviations:", worst)
-    assert worst[0][1] < 2e-3, worst
+    gmax = max(float(g.abs().max()) for g in g64.values())
+    for k in g64:
+        if ZERO_GRAD_BN_BIAS.search(k):
+            assert float(grads[k].abs().max()) < 1e-4 * gmax, k
+    _check_against_fp64({k: v.cpu() for k, v in grads.items() if v is not None}, (g32, gnz), g64, lambda k: bool(ZERO_GRAD_BN_BIAS.search(k)))
     assert len(bn_new) == 2 * 56
     for k, v in bn_new.items():
         assert rel_err(dev[k].cpu(), v) < 1e-4, k
@@ -171,11 +205,22 @@ def test_full_train_step_through_mirror_modules(be):
     mels = synth.mel_like(B, M, seed=2) * 2 - 5
     gate_t = torch.zeros(B, M); gate_t[:, -2:] = 1
     noise = TO.reference_noise(B, T, M, 0.5, with_video=True, generator=torch.Generator().manual_seed(8))
-    # oracle
-    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not spec.is_buffer(k) else v.clone()) for k, v in net_sd.items()}
-    ref = TO.lip2speech_forward_train(sd, video, spk, mels, noise)
-    ref_losses = TO.loss_forward(ref, (mels, gate_t))
-    sum(ref_losses.values()).backward()
+
+    jitter = torch.randn(video.shape, generator=torch.Generator().manual_seed(1), dtype=torch.float64)
+
+    def oracle(dt, nz=0.0):
+        sd = _cast_sd(net_sd, dt)
+        n = TO.TrainNoise(noise.video_drop.to(dt), noise.gumbel.to(dt), noise.tf_mask, noise.prenet.to(dt), noise.attn.to(dt), noise.lstm.to(dt),
+                          [t.to(dt) for t in noise.post])
+        v = video.to(dt) * (1 + nz * jitter.to(dt)) if nz else video.to(dt)
+        ref = TO.lip2speech_forward_train(sd, v, spk.to(dt), mels.to(dt), n)
+        losses = TO.loss_forward(ref, (mels.to(dt), gate_t.to(dt)))
+        sum(losses.values()).backward()
+        return float(sum(losses.values())), {k: p.grad for k, p in sd.items() if torch.is_tensor(p) and p.requires_grad}
+
+    loss32, g32 = oracle(torch.float32)
+    loss64, g64 = oracle(torch.float64)
+    _, gnz = oracle(torch.float64, 2e-6)
     # CUDA path through the reference-shaped API
     opt = ClipAdamW([{"params": net.decoder.parameters()}, {"params": net.encoder.parameters()}], lr=1e-3, max_norm=1.0)   # train.py:102-104
     lens = torch.full((B,), T, dtype=torch.long)
@@ -185,17 +230,13 @@ def test_full_train_step_through_mirror_modules(be):
     out = net(video.cuda(), None, None, mels.cuda(), lens, None, lens, 0.5, speaker_embedding=spk.cuda(), train_noise=tn)
     losses = Loss()(out, (mels.cuda(), gate_t.cuda()))
     loss = sum(losses.values())
-    assert abs(float(loss) - float(sum(ref_losses.values()))) < 1e-3 * abs(float(sum(ref_losses.values())))
+    assert abs(float(loss) - loss64) < 1e-3 * abs(loss64)
     loss.backward()
-    errs = {}
+    got = {}
     for k, p in net.named_parameters():
         assert p.grad is not None, k
-        if ZERO_GRAD_BIAS.search(k):
-            continue
-        errs[k] = rel_err(p.grad.cpu(), sd[k].grad)
-    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
-    print("worst gradient deviations:", worst)
-    assert worst[0][1] < 5e-3, worst
+        got[k] = p.grad.cpu()
+    _check_against_fp64(got, (g32, gnz), g64, lambda k: bool(ZERO_GRAD_BIAS.search(k) or ZERO_GRAD_BN_BIAS.search(k)))
     before = {k: p.detach().clone() for k, p in net.named_parameters()}
     opt.step()
     moved = sum(int(not torch.equal(before[k], p.detach())) for k, p in net.named_parameters())
