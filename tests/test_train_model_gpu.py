@@ -127,21 +127,26 @@ def _cast_sd(w, dt):
                 else (v.clone().to(dt) if v.is_floating_point() else v.clone())) for k, v in w.items()}
 
 
-def _check_against_fp64(got, yardsticks, g64, skip, floor=2e-3, slack=4.0):
+def _l2_err(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+def _check_against_fp64(got, yardsticks, g64, skip, floor=1e-2, slack=4.0):
     """Deep train-mode BatchNorm + ReLU stacks on a small batch are ill-conditioned: a 1e-6 relative difference in the forward
-    pass (fp32 rounding in another summation order) flips individual ReLU decisions, and ONE flipped element moves some
-    gradients by percents (measured: the fp64 oracle fed a clip perturbed by 1e-6 deviates from itself by 4.3e-2 on
-    trunk.1.0.weight — the very number the CUDA path shows).  So every gradient is measured against the fp64 oracle and must
-    be as close to it as the yardstick runs are (torch fp32, and fp64 with 2e-6 input noise) x slack, or within `floor`."""
+    pass (fp32 rounding in another summation order) flips individual ReLU decisions, and ONE flipped element moves single
+    entries of some gradients by percents (measured: the fp64 oracle fed a clip perturbed by 1e-6 deviates from itself by
+    4.3e-2 max-abs on trunk.1.0.weight — the very number the CUDA path shows; which element flips depends on the perturbation).
+    So every gradient is compared with the fp64 oracle in relative L2 norm (a flip is sparse, a wrong kernel is not) and must
+    be within `floor`, or as close as the yardstick runs are (torch fp32; fp64 with 2e-6 input noise) x slack."""
     worst = []
     for k, truth in g64.items():
         if skip(k):
             continue
-        e_gpu = rel_err(got[k].double(), truth)
-        e_ref = max(rel_err(y[k].double(), truth) for y in yardsticks)
+        e_gpu = _l2_err(got[k], truth)
+        e_ref = max(_l2_err(y[k], truth) for y in yardsticks)
         worst.append((e_gpu / max(floor, slack * e_ref), k, e_gpu, e_ref))
     worst.sort(reverse=True)
-    print("worst (ratio to allowance, key, cuda-vs-fp64, yardstick-vs-fp64):", worst[:5])
+    print("worst (ratio to allowance, key, cuda-vs-fp64 rel-L2, yardstick-vs-fp64 rel-L2):", worst[:5])
     assert worst[0][0] <= 1.0, worst[:5]
 
 
@@ -239,8 +244,10 @@ def test_full_train_step_through_mirror_modules(be):
     _check_against_fp64(got, (g32, gnz), g64, lambda k: bool(ZERO_GRAD_BIAS.search(k) or ZERO_GRAD_BN_BIAS.search(k)))
     before = {k: p.detach().clone() for k, p in net.named_parameters()}
     opt.step()
-    moved = sum(int(not torch.equal(before[k], p.detach())) for k, p in net.named_parameters())
-    assert moved == len(before)
+    still = [k for k, p in net.named_parameters() if torch.equal(before[k], p.detach())]
+    # T = 7 gives ONE content slot: the softmax over it is constant, so the content keys / query / temperature have an exactly
+    # zero gradient (and a 1e-9 weight decay does not move an fp32 value); every other parameter moved
+    assert all(re.search(r"decoder\.content\.(K\.|Q\.|temperature)", k) for k in still), still
     # eval forward after the step: packed weights were invalidated, BatchNorm running statistics moved
     net.eval()
     with torch.no_grad():
