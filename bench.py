@@ -11,6 +11,9 @@ decoder pre-loop -> 300 autoregressive steps -> postnet) over one batch of synth
   --config c2 (default) : BASELINE configs[2] — B=32 clips per GPU, T=29 frames of 96x96, S=19 456 samples (weak scaling)
   --config c1           : BASELINE configs[1] — single-clip latency, B=1
   --config c4           : BASELINE configs[4] — AVSpeech shape, T=75, S=48 000, B=256 TOTAL split over the GPUs (strong scaling)
+  --config c3           : BASELINE configs[3] — train.py step (train.py:167-193): train-mode forward (video + decoder, M=77 teacher
+                          frames) + Loss + backward + gradient all-reduce + clip + AdamW, batch 64 TOTAL split over the GPUs
+                          (8 clips per GPU at N=8; at N=1 all 64 on one GPU in 8-clip micro-batches is NOT done: one GPU runs 8)
   --config train-tail   : the train step's flat-buffer tail (train.py:184-193): gradient all-reduce of 38.44 M fp32 over the
                           ranks (NCCL, the path's only collective) + 1/world + norm + clip + AdamW(amsgrad); its own metric (ms)
 
@@ -179,6 +182,122 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def oracle_train_step(batch, T, M, reps):
+    """CPU arm of --config c3: autograd through the train-mode oracle (port of the reference's train step, torch CPU fp32)."""
+    from lip2speech_b200 import spec, synth
+    from oracle import train_oracle as TO
+    torch.set_num_threads(os.cpu_count() or 1)
+    w = {k: v for k, v in spec.seeded_state_dict(spec.full_spec(), 1234).items() if not k.startswith("speaker_encoder.")}
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not spec.is_buffer(k) else v.clone()) for k, v in w.items()}
+    params = [p for p in sd.values() if torch.is_tensor(p) and p.requires_grad]
+    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=1e-6, amsgrad=True)
+    video, spk = synth.video(batch, T, H, W), synth.speaker_embedding(batch)
+    mels = synth.mel_like(batch, M) * 2 - 5
+    gate_t = torch.zeros(batch, M); gate_t[:, -2:] = 1
+    times = []
+    for i in range(reps + 1):
+        noise = TO.reference_noise(batch, T, M, 0.5, with_video=True, generator=torch.Generator().manual_seed(i))
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        out = TO.lip2speech_forward_train(sd, video, spk, mels, noise)
+        sum(TO.loss_forward(out, (mels, gate_t)).values()).backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        if i > 0:
+            times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_train_step(args, rank, local_rank, world):
+    """--config c3: one train.py iteration per step through the reference-shaped mirror modules: net(...) in train() ->
+    Loss -> loss.backward() -> ClipAdamW.step() (gradient all-reduce over the ranks inside).  value = clips x M teacher
+    frames per second over all ranks; inputs resident in HBM; e2e = the same with the batch coming from pinned host memory and
+    the loss read back every step."""
+    import torch.distributed as dist
+    from lip2speech_b200 import _lib, modules, sharding, spec, synth
+    from lip2speech_b200.train_step import ClipAdamW, Loss, init_data_parallel
+    dev = torch.device("cuda", local_rank)
+    total = 64
+    B = args.batch or max(1, total // max(world, 8))          # 8 clips per GPU (64 over 8 GPUs); fewer GPUs keep 8 per GPU
+    T, M = 29, 77
+    be = _lib.backend(local_rank)
+    if world > 1:
+        init_data_parallel(be, rank, world)
+    w = {k: v for k, v in spec.seeded_state_dict(spec.full_spec(), 1234).items() if not k.startswith("speaker_encoder.")}
+    net = modules.get_network("train")
+    net.load_state_dict(w, strict=True)
+    net = net.to(dev)
+    opt = ClipAdamW([{"params": net.decoder.parameters()}, {"params": net.encoder.parameters()}], lr=1e-4, weight_decay=1e-6, max_norm=1.0, backend=be)
+    loss_fn = Loss()
+    video_h = synth.video(B, T, H, W, seed=1234 + rank).pin_memory()
+    spk_h = synth.speaker_embedding(B, seed=1234 + rank).pin_memory()
+    mels_h = (synth.mel_like(B, M, seed=1234 + rank) * 2 - 5).pin_memory()
+    gate_h = torch.zeros(B, M); gate_h[:, -2:] = 1
+    gate_h = gate_h.pin_memory()
+    video, spk, mels, gate = video_h.to(dev), spk_h.to(dev), mels_h.to(dev), gate_h.to(dev)
+    lens = torch.full((B,), T, dtype=torch.long)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(v, s_, m_, g_):
+        opt.zero_grad()
+        out = net(v, None, None, m_, lens, None, lens, 0.5, speaker_embedding=s_)
+        loss = sum(loss_fn(out, (m_, g_)).values())
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(max(args.warmup, 3)):
+        step(video, spk, mels, gate)
+    barrier()
+    sampler = ClockSampler(local_rank); sampler.start()
+    launches0 = be.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.zero_()
+        ev[i][0].record()
+        step(video, spk, mels, gate)
+        ev[i][1].record()
+    barrier()
+    launches = be.launch_count() - launches0
+    total_ms = sharding.max_over_ranks(sum(a.elapsed_time(b) for a, b in ev), dev)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        loss = step(video_h.to(dev, non_blocking=True), spk_h.to(dev, non_blocking=True), mels_h.to(dev, non_blocking=True), gate_h.to(dev, non_blocking=True))
+        float(loss)
+    torch.cuda.synchronize()
+    e2e_s = sharding.max_over_ranks(time.perf_counter() - t0, dev)
+    clocks = sampler.stop()
+    if rank == 0:
+        frames = world * B * M * args.steps
+        line = {"metric": "mel-frames/sec (train step: forward + backward + all-reduce + clip + AdamW) on LRW 29-frame clips, M=77 teacher frames",
+                "value": frames / (total_ms * 1e-3), "unit": "mel-frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 (exact fp32 FMA train kernels)", "data": "synthetic",
+                "config": {"workload": f"train.py:167-193 step, {B} clips per GPU (BASELINE configs[3]: batch 64 over 8 GPUs), T=29, 96x96, M=77; "
+                                       "train-mode video frontend + decoder (BatchNorm batch statistics, all dropout sites, BPTT), Loss, "
+                                       "gradient all-reduce, clip_grad_norm_(1.0), AdamW(amsgrad)", "name": "c3", "batch_per_gpu": B,
+                           "l2": "flushed between timed steps", "parallelism": f"data-parallel x{world}, one ncclAllReduce of 153.7 MB per step"},
+                "e2e": {"value": frames / e2e_s, "unit": "mel-frames/s", "ms_per_step": 1e3 * e2e_s / args.steps,
+                        "h2d_bytes_per_step": int(4 * (video_h.numel() + spk_h.numel() + mels_h.numel() + gate_h.numel())), "d2h_bytes_per_step": 4,
+                        "api": "mirror modules (modules.Lip2Speech in train()) + train_step.Loss + ClipAdamW: pinned host batch in, loss scalar out"},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": {"kernel": "sgemm_kernel (SIMT fp32 GEMM of the train path)", "bound": "tensor", "achieved": None, "peak": None, "unit": "TFLOP/s",
+                             "frac": None, "traffic": None,
+                             "note": "the train path is correctness-first (exact fp32 FMA); no roofline claim is made for it this round"}}
+        if not args.no_cpu_baseline:
+            times = oracle_train_step(min(B, 4), T, M, reps=1)
+            line["cpu_baseline"] = {"value": min(B, 4) * M / statistics.median(times), "unit": "mel-frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"1 train step of {min(B, 4)} clips: autograd through oracle/train_oracle.py (torch CPU fp32) + clip + AdamW"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        be.comm_destroy()
+
+
 def run_train_tail(args, rank, local_rank, world):
     """The one collective of the path: between loss.backward() (train.py:184) and clip_grad_norm_/optim.step() (191-193) the
     flat 38.44 M-float gradient is summed over the ranks (ncclAllReduce through the library's communicator), scaled by
@@ -267,7 +386,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS) + ["train-tail"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS) + ["c3", "train-tail"])
     ap.add_argument("--batch", type=int, default=0, help="clips per GPU per step (default: the config's)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
                     help="Conv3d stem operands: bf16 (BASELINE configs[2]: 'bf16 frontend + fp32 decoder step') or the 3xTF32 fp32-grade path")
@@ -283,6 +402,19 @@ def main():
         if args.config == "train-tail":
             if rank == 0:
                 print(json.dumps({"impl": "reference", "unavailable": "the reference has no distributed code (SURVEY.md §2.1): the train-tail config has no reference arm"}))
+            return
+        if args.config == "c3":
+            if rank == 0:
+                b = min(args.batch or 8, 4)
+                times = oracle_train_step(b, 29, 77, reps=max(1, min(args.steps, 2)))
+                v = b * 77 * len(times) / sum(times)
+                print(json.dumps({"impl": "reference", "metric": "mel-frames/sec (train step) on LRW 29-frame clips, M=77", "value": v, "unit": "mel-frames/s",
+                                  "n_gpus": 0, "steps": len(times), "warmup": 1, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
+                                  "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                                  "config": {"workload": f"train.py:167-193 step on the host CPU, {b} clips per timed step (autograd through the oracle port)", "name": "c3"},
+                                  "cpu_baseline": {"value": v, "unit": "mel-frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                                                   "sample": f"{len(times)} train steps of {b} clips"},
+                                  "e2e": {"value": v, "unit": "mel-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
             return
         if args.steps > 5:
             args.steps = 5          # bounded CPU sample: keep the whole run within a few minutes
@@ -301,8 +433,8 @@ def main():
         build.build()
     if world > 1:
         dist.barrier()
-    if args.config == "train-tail":
-        run_train_tail(args, rank, local_rank, world)
+    if args.config in ("train-tail", "c3"):
+        (run_train_tail if args.config == "train-tail" else run_train_step)(args, rank, local_rank, world)
         if world > 1:
             dist.destroy_process_group()
         return

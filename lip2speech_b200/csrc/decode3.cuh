@@ -405,7 +405,56 @@ __device__ void d3_attend(const Decode3Params& q, const DecSmem& sm, const float
     }
     __syncthreads();
     float* xd = q.XD + (size_t)g * 1024 * D3_CG;
-    if (warp < 8 || warp == 12) {
+    if (vstride != 256) {
+        // keys / values streamed from L2 (T > 31: the images do not fit in shared memory twice): the context sum is split over
+        // the positions as well (thread = 4 features x every 8th position, float4 loads) so that each thread waits for ~T/8
+        // dependent L2 loads instead of T, partials combined in a fixed order
+        if (warp == 0) {
+            float mx = -INFINITY;
+            for (int t = lane; t < p.T; t += 32) mx = fmaxf(mx, sm.sc[t]);
+            mx = warp_max(mx);
+            float sum = 0.f;
+            for (int t = lane; t < p.T; t += 32) sum += expf(sm.sc[t] - mx);
+            sum = warp_sum(sum);
+            for (int t = lane; t < p.T; t += 32) {
+                const float a = expf(sm.sc[t] - mx) / sum;
+                if (part == 0 && real) {
+                    if (p.attn_logits) p.attn_logits[((size_t)b * p.steps + step) * p.T + t] = sm.sc[t];
+                    if (p.attn) p.attn[((size_t)b * p.steps + step) * p.T + t] = a;
+                }
+                sm.sc[t] = a;
+            }
+        } else if (warp == 1) {
+            const float v = lane < p.minT ? sm.csc[lane] : -INFINITY;
+            const float mx = warp_max(v);
+            const float e = lane < p.minT ? expf(v - mx) : 0.f;
+            const float sum = warp_sum(e);
+            if (lane < p.minT) sm.csc[lane] = e / sum;
+        }
+        __syncthreads();
+        {
+            const int fq = tid & 63, tg = tid >> 6;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int t = tg; t < p.T; t += 8) {
+                const float4 v = *reinterpret_cast<const float4*>(Vb + (size_t)t * vstride + 4 * fq);
+                const float w = sm.sc[t];
+                a.x = fmaf(w, v.x, a.x); a.y = fmaf(w, v.y, a.y); a.z = fmaf(w, v.z, a.z); a.w = fmaf(w, v.w, a.w);
+            }
+            *reinterpret_cast<float4*>(sm.red + tg * 256 + fq * 4) = a;
+        }
+        __syncthreads();
+        if (tid < 256) {
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += sm.red[j * 256 + tid];
+            lx_store(xd + (size_t)(512 + part * 256 + tid) * D3_CG + bb, s, tag);
+        } else if (tid < 256 + 128) {
+            const int f = tid - 256;
+            float a = 0.f;
+            for (int m = 0; m < p.minT; ++m) a = fmaf(sm.csc[m], cv[(size_t)m * cvstride + f], a);
+            lx_store(xd + (size_t)(part * 128 + f) * D3_CG + bb, a, tag);
+        }
+    } else if (warp < 8 || warp == 12) {
         // softmax over the T positions, recomputed by every warp that needs it (same instructions, same order: identical bits)
         float mx = -INFINITY;
         for (int t = lane; t < p.T; t += 32) mx = fmaxf(mx, sm.sc[t]);

@@ -123,74 +123,137 @@ __global__ void __launch_bounds__(256) skinny_nt_kernel(int M, int N, int K, con
             }
         }
 }
-// dx[m][k] (+)= sum_n dy[m][n] W[n][k]  for M <= 16: thread per k, loops n (W rows are read coalesced across k, dy broadcast).
-__global__ void __launch_bounds__(256) skinny_nn_kernel(int M, int N, int K, const float* __restrict__ dY, int ldy, const float* __restrict__ W, int ldw,
-                                                        float* __restrict__ dX, int ldx, int accumulate) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= K) return;
+// dx[m][k] (+)= sum_n dy[m][n] W[n][k]  for M <= 16, in two deterministic stages so that the whole chip streams W once:
+// stage 1: block (64 columns k) x (slice of `nslice` rows n), 256 threads = 64 kx x 4 ny -> part[slice][m][k];
+// stage 2: dX (+)= sum over the slices in order.
+__global__ void __launch_bounds__(256) skinny_nn_part_kernel(int M, int N, int K, int nslice, const float* __restrict__ dY, int ldy,
+                                                             const float* __restrict__ W, int ldw, float* __restrict__ part) {
+    __shared__ float red[4][16][65];
+    const int kx = threadIdx.x & 63, ny = threadIdx.x >> 6;
+    const int k = blockIdx.x * 64 + kx;
+    const int n0 = blockIdx.y * nslice, n1 = min(N, n0 + nslice);
     float acc[16];
 #pragma unroll
     for (int m = 0; m < 16; ++m) acc[m] = 0.f;
-    for (int n = 0; n < N; ++n) {
-        const float wv = W[(size_t)n * ldw + k];
+    if (k < K)
+        for (int n = n0 + ny; n < n1; n += 4) {
+            const float wv = W[(size_t)n * ldw + k];
 #pragma unroll
-        for (int m = 0; m < 16; ++m)
-            if (m < M) acc[m] = fmaf(__ldg(dY + (size_t)m * ldy + n), wv, acc[m]);
+            for (int m = 0; m < 16; ++m)
+                if (m < M) acc[m] = fmaf(__ldg(dY + (size_t)m * ldy + n), wv, acc[m]);
+        }
+#pragma unroll
+    for (int m = 0; m < 16; ++m) red[ny][m][kx] = acc[m];
+    __syncthreads();
+    if (ny == 0 && k < K)
+        for (int m = 0; m < M; ++m)
+            part[((size_t)blockIdx.y * M + m) * K + k] = (red[0][m][kx] + red[1][m][kx]) + (red[2][m][kx] + red[3][m][kx]);
+}
+__global__ void skinny_nn_sum_kernel(int M, int K, int nslices, const float* __restrict__ part, float* __restrict__ dX, int ldx, int accumulate) {
+    const size_t total = (size_t)M * K;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int m = i / K, k = i % K;
+        float a = 0.f;
+        for (int z = 0; z < nslices; ++z) a += part[(size_t)z * total + i];
+        float* d = dX + (size_t)m * ldx + k;
+        *d = accumulate ? *d + a : a;
+    }
+}
+
+// dW[n][k] += sum_i A_i[n] * B_i[k] over a LIST of row pairs (A_i = a gradient row, B_i = an input row): the weight gradient of
+// a layer that ran once per decoder step / LSTM time step, gathered over all its invocations in ONE GEMM instead of one
+// read-modify-write of dW per step (rowsA / rowsB: device arrays of row pointers, R entries).
+__global__ void __launch_bounds__(256) sgemm_tn_rows_kernel(int N, int K, int R, const float* const* __restrict__ rowsA, const float* const* __restrict__ rowsB,
+                                                            float* __restrict__ C, int ldc) {
+    constexpr int BM = 64, BN = 64, BK = 16;
+    __shared__ float As[BK][BM + 1];
+    __shared__ float Bs[BK][BN + 1];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int r0 = 0; r0 < R; r0 += BK) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = tid + i * 256;
+            const int c = e & 63, r = e >> 6;
+            const int gr = r0 + r;
+            float va = 0.f, vb = 0.f;
+            if (gr < R) {
+                if (m0 + c < N) va = rowsA[gr][m0 + c];
+                if (n0 + c < K) vb = rowsB[gr][n0 + c];
+            }
+            As[r][c] = va; Bs[r][c] = vb;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = As[k][ty + 16 * i]; b[i] = Bs[k][tx + 16 * i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
     }
 #pragma unroll
-    for (int m = 0; m < 16; ++m)
-        if (m < M) {
-            float* d = dX + (size_t)m * ldx + k;
-            *d = accumulate ? *d + acc[m] : acc[m];
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int m = m0 + ty + 16 * i, n = n0 + tx + 16 * j;
+            if (m < N && n < K) C[(size_t)m * ldc + n] += acc[i][j];
         }
 }
 
 // ---- kernels: column reductions ---------------------------------------------------------------------------------------
-// out[c] (+)= sum_r f(r, c).  One CTA per 32 columns: 8 row lanes x 32 columns, fixed summation order.
-enum ColOp { COL_SUM = 0, COL_SUM_XY = 1, COL_PSINE_DW = 2, COL_PRELU_DW = 3 };
+// out[c] (+)= sum_r f(r, c).  Grid (ceil(cols/32), row splits): each CTA reduces its row range for 32 columns (8 row lanes x
+// 32 columns, fixed order) into part[split][c]; colfinish_kernel adds the splits in order.  (Tall, narrow activations — the
+// stem's 534 K rows x 24 channels — would otherwise be reduced by ONE CTA.)
+enum ColOp { COL_SUM = 0, COL_SUM_XY = 1, COL_PSINE_DW = 2, COL_PRELU_DW = 3, COL_SQDEV = 4, COL_BN_DGAMMA = 5 };
 template <int OP>
 __global__ void __launch_bounds__(256) colreduce_kernel(int rows, int cols, const float* __restrict__ X, int xs, const float* __restrict__ Y, int ys,
-                                                        float* __restrict__ out, int accumulate) {
-    __shared__ float part[8][33];
+                                                        const float* __restrict__ aux, const float* __restrict__ aux2, float eps, float* __restrict__ part) {
+    __shared__ float p0[8][33];
     const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
+    const int per = (rows + gridDim.y - 1) / gridDim.y;
+    const int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
     float a = 0.f;
-    if (c < cols)
-        for (int r = rl; r < rows; r += 8) {
+    if (c < cols) {
+        const float mu = (OP == COL_SQDEV || OP == COL_BN_DGAMMA) ? aux[c] : 0.f;
+        const float rstd = OP == COL_BN_DGAMMA ? rsqrtf(aux2[c] + eps) : 0.f;
+        for (int r = r0 + rl; r < r1; r += 8) {
             const float x = X[(size_t)r * xs + c];
             if (OP == COL_SUM) a += x;
             else if (OP == COL_SUM_XY) a = fmaf(x, Y[(size_t)r * ys + c], a);
             else if (OP == COL_PSINE_DW) a = fmaf(sinf(x), Y[(size_t)r * ys + c], a);            // X = pre-activation, Y = dy
             else if (OP == COL_PRELU_DW) a += x < 0.f ? x * Y[(size_t)r * ys + c] : 0.f;
+            else if (OP == COL_SQDEV) { const float d = x - mu; a = fmaf(d, d, a); }              // aux = mean
+            else a = fmaf(Y[(size_t)r * ys + c], (x - mu) * rstd, a);                             // COL_BN_DGAMMA: aux = mean, aux2 = var, Y = dy
         }
-    part[rl][cl] = a;
+    }
+    p0[rl][cl] = a;
     __syncthreads();
     if (rl == 0 && c < cols) {
         float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s += part[i][cl];
-        out[c] = accumulate ? out[c] + s : s;
+        for (int i = 0; i < 8; ++i) s += p0[i][cl];
+        part[(size_t)blockIdx.y * cols + c] = s;
     }
 }
-
-// Batch statistics per column: mean and biased variance (two passes inside the CTA's column strip; fixed order).
-__global__ void __launch_bounds__(256) colstats_kernel(int rows, int cols, const float* __restrict__ X, int xs, float* __restrict__ mean, float* __restrict__ var) {
-    __shared__ float part[8][33];
-    __shared__ float mu[32];
-    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + cl;
-    float a = 0.f;
-    if (c < cols) for (int r = rl; r < rows; r += 8) a += X[(size_t)r * xs + c];
-    part[rl][cl] = a;
-    __syncthreads();
-    if (rl == 0) { float s = 0.f; for (int i = 0; i < 8; ++i) s += part[i][cl]; mu[cl] = s / (float)rows; }
-    __syncthreads();
-    const float m = mu[cl];
-    a = 0.f;
-    if (c < cols) for (int r = rl; r < rows; r += 8) { const float d = X[(size_t)r * xs + c] - m; a = fmaf(d, d, a); }
-    part[rl][cl] = a;
-    __syncthreads();
-    if (rl == 0 && c < cols) { float s = 0.f; for (int i = 0; i < 8; ++i) s += part[i][cl]; mean[c] = m; var[c] = s / (float)rows; }
+// out[c] = (accumulate ? out[c] : 0) + scale * sum_split part[split][c]
+__global__ void colfinish_kernel(int cols, int splits, const float* __restrict__ part, float scale, float* __restrict__ out, int accumulate) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += part[(size_t)z * cols + c];
+    s *= scale;
+    out[c] = accumulate ? out[c] + s : s;
 }
 
 // Full reduction sum(X*Y) -> out[0] (+)=, single CTA (used for the two scalar temperatures).
@@ -290,30 +353,6 @@ __global__ void bn_bwd_kernel(int rows, int cols, const float* __restrict__ X, i
         const float rstd = rsqrtf(var[c] + eps);
         const float xhat = (X[(size_t)r * xs + c] - mean[c]) * rstd;
         dX[(size_t)r * dxs + c] += gamma[c] * rstd * (dY[(size_t)r * dys + c] - dbeta[c] * invR - xhat * dgamma[c] * invR);
-    }
-}
-// dgamma[c] = sum_r dy * xhat (needs mean/var): computed by a column reduction over a temporary xhat*dy? -> fused here.
-__global__ void __launch_bounds__(256) bn_dgamma_kernel(int rows, int cols, const float* __restrict__ X, int xs, const float* __restrict__ mean,
-                                                        const float* __restrict__ var, float eps, const float* __restrict__ dY, int dys,
-                                                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
-    __shared__ float pg[8][33], pb[8][33];
-    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + cl;
-    float ag = 0.f, ab = 0.f;
-    if (c < cols) {
-        const float m = mean[c], rstd = rsqrtf(var[c] + eps);
-        for (int r = rl; r < rows; r += 8) {
-            const float dy = dY[(size_t)r * dys + c];
-            ag = fmaf(dy, (X[(size_t)r * xs + c] - m) * rstd, ag);
-            ab += dy;
-        }
-    }
-    pg[rl][cl] = ag; pb[rl][cl] = ab;
-    __syncthreads();
-    if (rl == 0 && c < cols) {
-        float sg = 0.f, sb = 0.f;
-        for (int i = 0; i < 8; ++i) { sg += pg[i][cl]; sb += pb[i][cl]; }
-        dgamma[c] = sg; dbeta[c] = sb;
     }
 }
 // running = (1 - momentum) * running + momentum * stat  (variance: unbiased, x rows/(rows-1)); nn.BatchNorm*d in train()
@@ -673,28 +712,39 @@ __global__ void dw3x3_dgrad_kernel(int N, int H, int W, int C, int s, int Ho, in
         dX[(size_t)((n * H + h) * W + w) * dxs + c] += a;
     }
 }
-// dW[c][tap] += sum over output positions of dY * x(tap)   — grid (ceil(C/32), 9), 8 row lanes x 32 channels, fixed order
+// part[split][tap][c] = sum over the split's output positions of dY * x(tap)   — grid (ceil(C/32), 9, splits), 8 row lanes x 32
+// channels, fixed order; dw3x3_wfinish_kernel adds the splits into dW[c][tap]
 __global__ void __launch_bounds__(256) dw3x3_wgrad_kernel(int N, int H, int W, int C, int s, int Ho, int Wo, const float* __restrict__ X, int xs,
-                                                          const float* __restrict__ dY, int dys, float* __restrict__ dW) {
-    __shared__ float part[8][33];
+                                                          const float* __restrict__ dY, int dys, float* __restrict__ part) {
+    __shared__ float red[8][33];
     const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl, tap = blockIdx.y, kh = tap / 3, kw = tap % 3;
     const int rows = N * Ho * Wo;
+    const int per = (rows + gridDim.z - 1) / gridDim.z;
+    const int r0 = blockIdx.z * per, r1 = min(rows, r0 + per);
     float a = 0.f;
     if (c < C)
-        for (int r = rl; r < rows; r += 8) {
+        for (int r = r0 + rl; r < r1; r += 8) {
             const int wo = r % Wo, ho = (r / Wo) % Ho, n = r / (Wo * Ho);
             const int h = ho * s + kh - 1, w = wo * s + kw - 1;
             if (h < 0 || h >= H || w < 0 || w >= W) continue;
             a = fmaf(dY[(size_t)r * dys + c], X[(size_t)((n * H + h) * W + w) * xs + c], a);
         }
-    part[rl][cl] = a;
+    red[rl][cl] = a;
     __syncthreads();
     if (rl == 0 && c < C) {
         float t = 0.f;
-        for (int i = 0; i < 8; ++i) t += part[i][cl];
-        dW[c * 9 + tap] += t;
+        for (int i = 0; i < 8; ++i) t += red[i][cl];
+        part[((size_t)blockIdx.z * 9 + tap) * C + c] = t;
     }
+}
+__global__ void dw3x3_wfinish_kernel(int C, int splits, const float* __restrict__ part, float* __restrict__ dW) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 9 * C) return;
+    const int tap = i / C, c = i % C;
+    float t = 0.f;
+    for (int z = 0; z < splits; ++z) t += part[((size_t)z * 9 + tap) * C + c];
+    dW[c * 9 + tap] += t;
 }
 // y[:, 2j] = a[:, j], y[:, 2j+1] = b[:, j]   (torch.cat + channel_shuffle(groups=2), shufflenetv2.py:26-40,92-104)
 __global__ void interleave2_fwd_kernel(int rows, int half, const float* __restrict__ A, int as, const float* __restrict__ Bm, int bs, float* __restrict__ Y, int ys) {
@@ -778,7 +828,7 @@ struct Engine {
 
     void begin(Context* c, cudaStream_t stream, std::map<std::string, Param>* p) {
         ctx = c; s = stream; params = p; launches = &c->launches;
-        vals.reset(); grads.reset(); tape.clear();
+        vals.reset(); grads.reset(); tape.clear(); deferred.clear();
     }
     void ck(const char* what) {
         cudaError_t e = cudaGetLastError();
@@ -811,6 +861,38 @@ struct Engine {
     void backward() {
         for (size_t i = tape.size(); i-- > 0;) tape[i]();
         tape.clear();
+        flush_deferred();
+    }
+
+    // ---- column reductions (two deterministic stages) -----------------------------------------------------------------------
+    template <int OP>
+    void colred(int rows, int cols, const float* X, int xs, const float* Y, int ys, const float* aux, const float* aux2, float eps, float scale,
+                float* out, bool accumulate) {
+        const int splits = std::max(1, std::min(64, rows / 2048));
+        float* part = scratch((size_t)splits * cols);
+        colreduce_kernel<OP><<<dim3((cols + 31) / 32, splits), 256, 0, s>>>(rows, cols, X, xs, Y, ys, aux, aux2, eps, part);
+        ck("column reduce");
+        colfinish_kernel<<<(cols + 255) / 256, 256, 0, s>>>(cols, splits, part, scale, out, accumulate ? 1 : 0);
+        ck("column reduce finish");
+    }
+
+    // ---- deferred weight gradients of the per-step (few-row) linears ---------------------------------------------------------
+    struct Deferred { TT W; std::vector<const float*> a, b; };
+    std::map<float*, Deferred> deferred;
+    void flush_deferred() {
+        for (auto& kv : deferred) {
+            Deferred& d = kv.second;
+            const int R = (int)d.a.size();
+            const float** tab = reinterpret_cast<const float**>(scratch((size_t)R * 4));      // 2 R pointers of 8 bytes
+            L2S_CUDA(cudaMemcpyAsync(tab, d.a.data(), (size_t)R * sizeof(float*), cudaMemcpyHostToDevice, s));
+            L2S_CUDA(cudaMemcpyAsync(tab + R, d.b.data(), (size_t)R * sizeof(float*), cudaMemcpyHostToDevice, s));
+            const int N = d.W.rows, K = d.W.cols;
+            sgemm_tn_rows_kernel<<<dim3((K + 63) / 64, (N + 63) / 64), 256, 0, s>>>(N, K, R, tab, tab + R, d.W.g, d.W.rs);
+            ck("deferred weight gradient");
+        }
+        // the host pointer tables must outlive the asynchronous copies
+        L2S_CUDA(cudaStreamSynchronize(s));
+        deferred.clear();
     }
 
     // ---- GEMM helpers ----------------------------------------------------------------------------------------------------
@@ -839,13 +921,25 @@ struct Engine {
         }
         TT bb; if (b) bb = *b;
         const bool hasb = b != nullptr;
+        const bool defer = R <= 16 && W.g != nullptr;       // per-step layer: its weight gradient is gathered over all steps at the end
+        if (defer) {
+            Deferred& d = deferred[W.g];
+            d.W = W;
+            for (int r = 0; r < R; ++r) { d.a.push_back(y.g + (size_t)r * y.rs); d.b.push_back(x.v + (size_t)r * x.rs); }
+        }
         tape.push_back([=]() {
             if (x.g) {
-                if (R <= 16) { skinny_nn_kernel<<<(K + 255) / 256, 256, 0, s>>>(R, N, K, y.g, y.rs, W.v, W.rs, x.g, x.rs, 1); ck("skinny_nn"); }
-                else gemm<0, 0>(R, K, N, y.g, y.rs, W.v, W.rs, x.g, x.rs, true);
+                if (R <= 16) {
+                    const int nslice = 128, nslices = (N + nslice - 1) / nslice;
+                    float* part = scratch((size_t)nslices * R * K);
+                    skinny_nn_part_kernel<<<dim3((K + 63) / 64, nslices), 256, 0, s>>>(R, N, K, nslice, y.g, y.rs, W.v, W.rs, part);
+                    ck("skinny_nn part");
+                    skinny_nn_sum_kernel<<<ew_blocks((size_t)R * K), 256, 0, s>>>(R, K, nslices, part, x.g, x.rs, 1);
+                    ck("skinny_nn sum");
+                } else gemm<0, 0>(R, K, N, y.g, y.rs, W.v, W.rs, x.g, x.rs, true);
             }
-            if (W.g) gemm<1, 0>(N, K, R, y.g, y.rs, x.v, x.rs, W.g, W.rs, true);
-            if (hasb && bb.g) { colreduce_kernel<COL_SUM><<<(N + 31) / 32, 256, 0, s>>>(R, N, y.g, y.rs, nullptr, 0, bb.g, 1); ck("bias grad"); }
+            if (W.g && !defer) gemm<1, 0>(N, K, R, y.g, y.rs, x.v, x.rs, W.g, W.rs, true);
+            if (hasb && bb.g) colred<COL_SUM>(R, N, y.g, y.rs, nullptr, 0, nullptr, nullptr, 0.f, 1.f, bb.g, true);
         });
         return y;
     }
@@ -881,12 +975,12 @@ struct Engine {
     TT dropout(const TT& x, const float* keep, int ks, float p) { return ew<EW_MASK>(x, keep, ks, 1.0f / (1.0f - p)); }
     TT psine(const TT& x, const TT& w) {
         TT y = ew<EW_PSINE>(x, w.v, 0, 0.f);
-        if (w.g) tape.push_back([=]() { colreduce_kernel<COL_PSINE_DW><<<(x.cols + 31) / 32, 256, 0, s>>>(x.rows, x.cols, x.v, x.rs, y.g, y.rs, w.g, 1); ck("psine dw"); });
+        if (w.g) tape.push_back([=]() { colred<COL_PSINE_DW>(x.rows, x.cols, x.v, x.rs, y.g, y.rs, nullptr, nullptr, 0.f, 1.f, w.g, true); });
         return y;
     }
     TT prelu(const TT& x, const TT& w) {
         TT y = ew<EW_PRELU>(x, w.v, 0, 0.f);
-        if (w.g) tape.push_back([=]() { colreduce_kernel<COL_PRELU_DW><<<(x.cols + 31) / 32, 256, 0, s>>>(x.rows, x.cols, x.v, x.rs, y.g, y.rs, w.g, 1); ck("prelu dw"); });
+        if (w.g) tape.push_back([=]() { colred<COL_PRELU_DW>(x.rows, x.cols, x.v, x.rs, y.g, y.rs, nullptr, nullptr, 0.f, 1.f, w.g, true); });
         return y;
     }
     TT add(const TT& a, const TT& b) {
@@ -949,8 +1043,8 @@ struct Engine {
         const int R = x.rows, C = x.cols;
         TT gamma = param(name + ".weight", 1, C), beta = param(name + ".bias", 1, C);
         float* mean = scratch(C); float* var = scratch(C);
-        colstats_kernel<<<(C + 31) / 32, 256, 0, s>>>(R, C, x.v, x.rs, mean, var);
-        ck("bn stats");
+        colred<COL_SUM>(R, C, x.v, x.rs, nullptr, 0, nullptr, nullptr, 0.f, 1.f / (float)R, mean, false);
+        colred<COL_SQDEV>(R, C, x.v, x.rs, nullptr, 0, mean, nullptr, 0.f, 1.f / (float)R, var, false);       // biased variance, two passes
         TT y = make(R, C);
         bn_fwd_kernel<<<ew_blocks(x.numel()), 256, 0, s>>>(R, C, x.v, x.rs, mean, var, eps, gamma.v, beta.v, y.v, y.rs);
         ck("bn fwd");
@@ -963,8 +1057,8 @@ struct Engine {
         }
         float* dgamma = scratch(C); float* dbeta = scratch(C);
         tape.push_back([=]() {
-            bn_dgamma_kernel<<<(C + 31) / 32, 256, 0, s>>>(R, C, x.v, x.rs, mean, var, eps, y.g, y.rs, dgamma, dbeta);
-            ck("bn dgamma");
+            colred<COL_BN_DGAMMA>(R, C, x.v, x.rs, y.g, y.rs, mean, var, eps, 1.f, dgamma, false);
+            colred<COL_SUM>(R, C, y.g, y.rs, nullptr, 0, nullptr, nullptr, 0.f, 1.f, dbeta, false);
             if (x.g) { bn_bwd_kernel<<<ew_blocks(x.numel()), 256, 0, s>>>(R, C, x.v, x.rs, mean, var, eps, gamma.v, dgamma, dbeta, y.g, y.rs, x.g, x.rs); ck("bn bwd"); }
             if (gamma.g) { ew_bwd_kernel<EW_COPY><<<ew_blocks(C), 256, 0, s>>>(1, C, nullptr, 0, nullptr, 0, 0.f, dgamma, C, gamma.g, C); ck("bn dgamma acc"); }
             if (beta.g) { ew_bwd_kernel<EW_COPY><<<ew_blocks(C), 256, 0, s>>>(1, C, nullptr, 0, nullptr, 0, 0.f, dbeta, C, beta.g, C); ck("bn dbeta acc"); }
@@ -1080,7 +1174,14 @@ struct Engine {
         ck("dw conv");
         tape.push_back([=]() {
             if (x.g) { dw3x3_dgrad_kernel<<<ew_blocks((size_t)N * H * W * C), 256, 0, s>>>(N, H, W, C, stride, Ho, Wo, y.g, y.rs, Wt.v, x.g, x.rs); ck("dw dgrad"); }
-            if (Wt.g) { dw3x3_wgrad_kernel<<<dim3((C + 31) / 32, 9), 256, 0, s>>>(N, H, W, C, stride, Ho, Wo, x.v, x.rs, y.g, y.rs, Wt.g); ck("dw wgrad"); }
+            if (Wt.g) {
+                const int rows = N * Ho * Wo, splits = std::max(1, std::min(64, rows / 2048));
+                float* part = scratch((size_t)splits * 9 * C);
+                dw3x3_wgrad_kernel<<<dim3((C + 31) / 32, 9, splits), 256, 0, s>>>(N, H, W, C, stride, Ho, Wo, x.v, x.rs, y.g, y.rs, part);
+                ck("dw wgrad");
+                dw3x3_wfinish_kernel<<<(9 * C + 255) / 256, 256, 0, s>>>(C, splits, part, Wt.g);
+                ck("dw wgrad finish");
+            }
         });
         return y;
     }
