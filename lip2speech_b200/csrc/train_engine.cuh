@@ -36,20 +36,25 @@ struct TT {                       // train tensor: [rows][cols] view, element (r
 
 // ---- kernels: GEMM ------------------------------------------------------------------------------------------------------
 // C[M,N] (+)= A' B'  with A' = A (TA=0: A[m*lda + k]) or A^T (TA=1: A[k*lda + m]); B' = B (TB=0: B[k*ldb + n]) or B^T (TB=1: B[n*ldb + k]).
+// gridDim.z > 1: split over K — block z reduces K range [z*kper, (z+1)*kper) into its own [M][N] slab at C + z*M*ldc (the caller
+// sums the slabs in order: a tall-skinny weight gradient, M x N small and K = tens of thousands of rows, would otherwise run on
+// one or four CTAs).
 template <int TA, int TB>
 __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
-                                                    float* __restrict__ C, int ldc, int accumulate) {
+                                                    float* __restrict__ C, int ldc, int accumulate, int kper) {
     constexpr int BM = 64, BN = 64, BK = 16;
     __shared__ float As[BK][BM + 1];
     __shared__ float Bs[BK][BN + 1];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kbeg = blockIdx.z * kper;
+    if (gridDim.z > 1) { C += (size_t)blockIdx.z * M * ldc; K = min(K, kbeg + kper); }
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int k0 = 0; k0 < K; k0 += BK) {
+    for (int k0 = kbeg; k0 < K; k0 += BK) {
         // 1024 elements per tile, 4 per thread
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -900,7 +905,20 @@ struct Engine {
     void gemm(int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc, bool acc) {
         if (M <= 0 || N <= 0 || K <= 0) return;
         dim3 grid((N + 63) / 64, (M + 63) / 64);
-        sgemm_kernel<TA, TB><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, acc ? 1 : 0);
+        const int tiles = grid.x * grid.y;
+        if (tiles < 64 && K >= 2048) {                       // few output tiles, long reduction: split K over the chip
+            const int splits = std::min(std::min(128, 296 / tiles), (K + 511) / 512);
+            const int kper = (((K + splits - 1) / splits) + 15) / 16 * 16;
+            const int nz = (K + kper - 1) / kper;
+            float* part = scratch((size_t)nz * M * N);
+            grid.z = nz;
+            sgemm_kernel<TA, TB><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, part, N, 0, kper);
+            ck("sgemm split-K");
+            skinny_nn_sum_kernel<<<ew_blocks((size_t)M * N), 256, 0, s>>>(M, N, nz, part, C, ldc, acc ? 1 : 0);
+            ck("sgemm split-K sum");
+            return;
+        }
+        sgemm_kernel<TA, TB><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, acc ? 1 : 0, K);
         ck("sgemm");
     }
 
