@@ -180,6 +180,16 @@ int l2s_decoder_train_bwd(l2s_ctx* ctx, const float* g_mel, const float* g_post,
 int l2s_video_train_fwd(l2s_ctx* ctx, const float* video, const float* drop_mask, int B, int T, int H, int W, float* out_feat, void* stream);
 int l2s_video_train_bwd(l2s_ctx* ctx, const float* g_feat, void* stream);
 
+/* ---- after the path: vocoder and metric (demo.py:89-90, evaluate.py:41-45) ----------------------------
+ * MelSpec2Audio (datasets/spectograms.py:76-95): mel [B,80,L] log-mel (device) -> exp -> InverseMelScale -> GriffinLim(n_fft
+ * 1024, hop 256, power 2, momentum) -> wav [B,(L-1)*256] (device).  The inverse mel operator is the weight "vocoder.inv_mel"
+ * [513,80] (l2s_bind_weight; = the least-squares operator torchaudio's InverseMelScale applies: lstsq(fb^T, I)).  init_angles:
+ * the complex tensor GriffinLim(rand_init=True) draws, [B,513,L] viewed as real [B,513,L,2] (device), or NULL for rand_init=False.
+ * The STFT / inverse STFT of every iteration are DFT GEMMs on the tcgen05 kernel (3xTF32). */
+int l2s_vocoder(l2s_ctx* ctx, const float* mel, const float* init_angles, int B, int L, int n_iter, float momentum, float* wav, void* stream);
+/* pystoi.stoi(clean, processed, 16000, extended=True) for B signal pairs [B,S] fp32 at 16 kHz (device) -> out[B] fp64 (device). */
+int l2s_estoi(l2s_ctx* ctx, const float* clean, const float* processed, int B, int S, double* out, void* stream);
+
 /* Number of kernels this library has launched on ctx since creation (bench.py `gpu_launches`). */
 int64_t l2s_launch_count(const l2s_ctx* ctx);
 

@@ -21,6 +21,7 @@ EXPORTS = ("l2s_version", "l2s_create", "l2s_destroy", "l2s_last_error", "l2s_bi
            "l2s_video_fwd", "l2s_speaker_fwd", "l2s_decoder_infer", "l2s_decoder_forward", "l2s_postnet_fwd", "l2s_infer", "l2s_infer_host", "l2s_infer_host_submit", "l2s_infer_host_wait",
            "l2s_video_fwd_u8", "l2s_infer_u8", "l2s_infer_host_submit_u8",
            "l2s_train_bind", "l2s_decoder_train_fwd", "l2s_decoder_train_bwd", "l2s_video_train_fwd", "l2s_video_train_bwd",
+           "l2s_vocoder", "l2s_estoi",
            "l2s_launch_count", "l2s_debug_read", "l2s_set_profiling", "l2s_span_ms",
            "l2s_loss_fwd_bwd", "l2s_nccl_unique_id", "l2s_comm_init", "l2s_comm_destroy", "l2s_allreduce_grads", "l2s_clip_adamw_step")
 NCCL_UNIQUE_ID_BYTES = 128
@@ -63,6 +64,8 @@ def load() -> C.CDLL:
         lib.l2s_decoder_train_bwd.argtypes = [vp, fp, fp, fp, fp, fp, fp, vp]
         lib.l2s_video_train_fwd.argtypes = [vp, fp, fp, i, i, i, i, fp, vp]
         lib.l2s_video_train_bwd.argtypes = [vp, fp, vp]
+        lib.l2s_vocoder.argtypes = [vp, fp, fp, i, i, i, C.c_float, fp, vp]
+        lib.l2s_estoi.argtypes = [vp, fp, fp, i, i, vp, vp]
         lib.l2s_launch_count.argtypes = [vp]; lib.l2s_launch_count.restype = C.c_int64
         lib.l2s_set_profiling.argtypes = [vp, i]
         lib.l2s_span_ms.argtypes = [vp, C.c_char_p]; lib.l2s_span_ms.restype = C.c_double
@@ -371,6 +374,36 @@ class Backend:
         g_feat = _f32c(g_feat, self.device)
         self._check(self.lib.l2s_video_train_bwd(self.h, g_feat.data_ptr(), self._stream()), "l2s_video_train_bwd")
         self._video_keep = None
+
+    # ---- after the path: vocoder + ESTOI (demo.py:89-90, evaluate.py:41-45) ----------------------------------------------------
+    def bind_vocoder(self, inv_mel: torch.Tensor):
+        """inv_mel [513,80]: the operator of torchaudio's InverseMelScale (see lip2speech_b200.audio.inverse_mel_operator)."""
+        t = inv_mel.detach().float().contiguous().cpu()
+        shape = (C.c_int64 * 2)(*t.shape)
+        self._check(self.lib.l2s_bind_weight(self.h, b"vocoder.inv_mel", C.c_void_p(t.data_ptr()), shape, 2, 0, 0), "l2s_bind_weight(vocoder.inv_mel)")
+
+    def vocoder(self, mel, init_angles=None, n_iter: int = 32, momentum: float = 0.99):
+        """mel [B,80,L] log-mel -> waveform [B,(L-1)*256].  init_angles: complex [B,513,L] (GriffinLim's rand_init draw) or None."""
+        mel = _f32c(mel, self.device)
+        B, M, L = mel.shape
+        assert M == 80
+        ia = None
+        if init_angles is not None:
+            ia = torch.view_as_real(init_angles.to(self.device).to(torch.complex64).contiguous()).contiguous()
+            assert ia.shape == (B, 513, L, 2)
+        wav = torch.empty(B, (L - 1) * 256, device=self.device)
+        self._check(self.lib.l2s_vocoder(self.h, mel.data_ptr(), ia.data_ptr() if ia is not None else None, B, L, n_iter, momentum,
+                                         wav.data_ptr(), self._stream()), "l2s_vocoder")
+        return wav
+
+    def estoi(self, clean, processed):
+        """pystoi.stoi(clean, processed, 16000, extended=True) for every row of [B,S] -> [B] float64."""
+        clean, processed = _f32c(clean, self.device), _f32c(processed, self.device)
+        assert clean.shape == processed.shape and clean.dim() == 2
+        out = torch.empty(clean.shape[0], dtype=torch.float64, device=self.device)
+        self._check(self.lib.l2s_estoi(self.h, clean.data_ptr(), processed.data_ptr(), clean.shape[0], clean.shape[1],
+                                       C.c_void_p(out.data_ptr()), self._stream()), "l2s_estoi")
+        return out
 
     def set_profiling(self, enabled: bool):
         self.lib.l2s_set_profiling(self.h, int(enabled))

@@ -2,6 +2,7 @@
 // CUDA kernels for the three reference modules on the inference hot path.
 #include "../../include/l2s_b200.h"
 
+#include "audio.cuh"
 #include "context.h"
 #include "decode.cuh"
 #include "decode3.cuh"
@@ -946,6 +947,7 @@ int l2s_bind_weight(l2s_ctx* ctx, const char* key, const void* ptr, const int64_
         throw L2sError(L2S_ERR_INVALID, std::string("bind_weight: unsupported dtype for ") + key);
     }
     ctx->c.w[key] = std::move(t);
+    if (std::strcmp(key, "vocoder.inv_mel") == 0) ctx->c.meta.erase("voc.ready");      // re-pack the vocoder tables on next use
     API_END(ctx)
 }
 
@@ -1269,6 +1271,68 @@ int l2s_loss_fwd_bwd(l2s_ctx* ctx, const float* mel_out, const float* mel_post, 
     API_END(ctx)
 }
 
+// ---- vocoder + ESTOI (the steps after the path: demo.py:89-90, evaluate.py:41-45) -------------------------------------------
+static void pack_audio_tables(Context& c) {
+    if (c.meta.count("voc.ready")) return;
+    const HostTensor& inv = c.W("vocoder.inv_mel");           // [513][80] = pinv of the mel filterbank (InverseMelScale's lstsq operator)
+    if (inv.numel() != (int64_t)VOC_BINS * 80) throw L2sError(L2S_ERR_INVALID, "vocoder.inv_mel must be [513,80]");
+    c.upload("voc.inv.w", inv.f);
+    upload_tc(c, "voc.inv", inv.f, VOC_BINS, 1, 80);
+    std::vector<float> win(VOC_NFFT);
+    for (int n = 0; n < VOC_NFFT; ++n) win[n] = (float)(0.5 - 0.5 * std::cos(2.0 * M_PI * n / VOC_NFFT));       // torch.hann_window (periodic)
+    c.upload("voc.win", win);
+    // analysis: rows f (re) and IM + f (im) of X[f] = sum_n w[n] x[n] e^{-2 pi i f n / N}
+    std::vector<float> dft((size_t)VOC_LD * VOC_NFFT, 0.f);
+    // synthesis: x[n] = w[n]/N * sum_f c_f (Re X_f cos - Im X_f sin), c_0 = c_{N/2} = 1, else 2 (imaginary parts of DC / Nyquist ignored)
+    std::vector<float> idft((size_t)VOC_NFFT * VOC_LD, 0.f);
+    for (int f = 0; f < VOC_BINS; ++f)
+        for (int n = 0; n < VOC_NFFT; ++n) {
+            const int j = (int)(((long long)f * n) % VOC_NFFT);                  // exact argument reduction
+            const double a = 2.0 * M_PI * (double)j / VOC_NFFT, cs = std::cos(a), sn = std::sin(a);
+            dft[(size_t)f * VOC_NFFT + n] = (float)(win[n] * cs);
+            dft[(size_t)(VOC_IM + f) * VOC_NFFT + n] = (float)(-(double)win[n] * sn);
+            const double cf = (f == 0 || f == VOC_NFFT / 2) ? 1.0 : 2.0;
+            idft[(size_t)n * VOC_LD + f] = (float)(win[n] * cf * cs / VOC_NFFT);
+            idft[(size_t)n * VOC_LD + VOC_IM + f] = (f == 0 || f == VOC_NFFT / 2) ? 0.f : (float)(-(double)win[n] * cf * sn / VOC_NFFT);
+        }
+    c.upload("voc.dft.w", dft); upload_tc(c, "voc.dft", dft, VOC_LD, 1, VOC_NFFT);
+    c.upload("voc.idft.w", idft); upload_tc(c, "voc.idft", idft, VOC_NFFT, 1, VOC_LD);
+    c.meta["voc.ready"] = 1;
+}
+
+static void pack_estoi_tables(Context& c) {
+    if (c.meta.count("es.ready")) return;
+    {
+        auto bessel_i0 = [](double x) { double s = 1.0, t = 1.0; for (int k = 1; k < 60; ++k) { t *= (x / (2.0 * k)) * (x / (2.0 * k)); s += t; } return s; };
+        std::vector<double> h(ES_TAPS);
+        const double fc = 1.0 / 8.0, alpha = (ES_TAPS - 1) / 2.0;
+        double sum = 0.0;
+        for (int n = 0; n < ES_TAPS; ++n) {
+            const double m = n - alpha, r = m / alpha;
+            const double kw = bessel_i0(5.0 * std::sqrt(std::max(0.0, 1.0 - r * r))) / bessel_i0(5.0);
+            const double x = fc * m, sinc = (x == 0.0) ? 1.0 : std::sin(M_PI * x) / (M_PI * x);
+            h[n] = fc * sinc * kw; sum += h[n];
+        }
+        for (auto& v : h) v = v / sum * 5.0;                                     // firwin normalisation (unit DC gain) x up
+        c.upload_raw("es.h", h.data(), h.size());
+        std::vector<double> w(ES_FRAME);
+        for (int n = 0; n < ES_FRAME; ++n) w[n] = 0.5 - 0.5 * std::cos(2.0 * M_PI * (n + 1) / (ES_FRAME + 1));      // np.hanning(258)[1:-1]
+        c.upload_raw("es.win", w.data(), w.size());
+        std::vector<int> lo(ES_BANDS), hi(ES_BANDS);
+        for (int i = 0; i < ES_BANDS; ++i) {                                      // pystoi thirdoct(10000, 512, 15, 150)
+            const double fl = 150.0 * std::pow(2.0, (2.0 * i - 1) / 6.0), fh = 150.0 * std::pow(2.0, (2.0 * i + 1) / 6.0);
+            auto nearest = [](double target) {
+                int best = 0; double bd = 1e300;
+                for (int k = 0; k <= ES_NFFT / 2; ++k) { const double f = (double)ES_FS * k / ES_NFFT, d = (f - target) * (f - target); if (d < bd) { bd = d; best = k; } }
+                return best;
+            };
+            lo[i] = nearest(fl); hi[i] = nearest(fh);
+        }
+        c.upload_raw("es.lo", lo.data(), lo.size()); c.upload_raw("es.hi", hi.data(), hi.size());
+    }
+    c.meta["es.ready"] = 1;
+}
+
 // ---- train-mode forward / backward ------------------------------------------------------------------------------------
 int l2s_train_bind(l2s_ctx* ctx, const char* key, float* param, float* grad, int64_t numel) {
     if (!ctx) return L2S_ERR_INVALID;
@@ -1303,6 +1367,82 @@ int l2s_decoder_train_bwd(l2s_ctx* ctx, const float* g_mel, const float* g_post,
     API_BEGIN
     L2S_CUDA(cudaSetDevice(ctx->c.device));
     ctx->dec_train.backward(g_mel, g_post, g_stop, g_content_dis, g_visual, g_spk, (cudaStream_t)stream);
+    API_END(ctx)
+}
+
+int l2s_vocoder(l2s_ctx* ctx, const float* mel, const float* init_angles, int B, int L, int n_iter, float momentum, float* wav, void* stream) {
+    if (!ctx) return L2S_ERR_INVALID;
+    API_BEGIN
+    Context& c = ctx->c;
+    if (!mel || !wav || B <= 0 || L < 3 || n_iter < 0 || momentum < 0.f || momentum >= 1.f) throw L2sError(L2S_ERR_INVALID, "vocoder: bad arguments");
+    L2S_CUDA(cudaSetDevice(c.device));
+    pack_audio_tables(c);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int R = B * L, n = (L - 1) * VOC_HOP;
+    float* melrows = c.fbuf("ws.voc.melrows", (size_t)R * 80);
+    float* mag = c.fbuf("ws.voc.mag", (size_t)R * VOC_IM);
+    float* ang = c.fbuf("ws.voc.ang", (size_t)R * VOC_LD);
+    float* tprev = c.fbuf("ws.voc.tprev", (size_t)R * VOC_LD);
+    float* spec = c.fbuf("ws.voc.spec", (size_t)R * VOC_LD);
+    float* frames = c.fbuf("ws.voc.frames", (size_t)R * VOC_NFFT);
+    float* inv = c.fbuf("ws.voc.inv", (size_t)B * n);
+    voc_exp_rows_kernel<<<ew_grid((size_t)R * 80), 256, 0, s>>>(mel, melrows, B, L);
+    check_launch(c, "vocoder exp");
+    linear(c, melrows, 80, "voc.inv", nullptr, mag, VOC_IM, R, VOC_BINS, 80, ACT_NONE, nullptr, s, "inverse mel scale");
+    voc_mag_kernel<<<ew_grid((size_t)R * VOC_IM), 256, 0, s>>>(mag, R);
+    check_launch(c, "vocoder magnitude");
+    voc_init_angles_kernel<<<ew_grid((size_t)R * VOC_LD), 256, 0, s>>>(init_angles, ang, tprev, B, L);
+    check_launch(c, "vocoder initial phase");
+    const float mfac = momentum / (1.f + momentum);
+    for (int it = 0; it <= n_iter; ++it) {
+        float* out = it == n_iter ? wav : inv;
+        voc_apply_kernel<<<ew_grid((size_t)R * VOC_LD), 256, 0, s>>>(mag, ang, spec, R);
+        check_launch(c, "vocoder apply phase");
+        linear(c, spec, VOC_LD, "voc.idft", nullptr, frames, VOC_NFFT, R, VOC_NFFT, VOC_LD, ACT_NONE, nullptr, s, "inverse DFT");
+        voc_ola_kernel<<<ew_grid((size_t)B * n), 256, 0, s>>>(frames, c.dev("voc.win"), out, B, L);
+        check_launch(c, "overlap-add");
+        if (it == n_iter) break;
+        voc_frames_kernel<<<ew_grid((size_t)R * VOC_NFFT), 256, 0, s>>>(inv, frames, B, L);
+        check_launch(c, "stft frames");
+        linear(c, frames, VOC_NFFT, "voc.dft", nullptr, spec, VOC_LD, R, VOC_LD, VOC_NFFT, ACT_NONE, nullptr, s, "DFT");
+        voc_angle_kernel<<<ew_grid((size_t)R * VOC_BINS), 256, 0, s>>>(spec, tprev, ang, R, mfac);
+        check_launch(c, "phase update");
+    }
+    API_END(ctx)
+}
+
+int l2s_estoi(l2s_ctx* ctx, const float* clean, const float* processed, int B, int S, double* out, void* stream) {
+    if (!ctx) return L2S_ERR_INVALID;
+    API_BEGIN
+    Context& c = ctx->c;
+    if (!clean || !processed || !out || B <= 0 || S < 1024) throw L2sError(L2S_ERR_INVALID, "estoi: bad arguments");
+    L2S_CUDA(cudaSetDevice(c.device));
+    pack_estoi_tables(c);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int n10 = (int)(((long long)S * 5 + 7) / 8);
+    const int max_frames = n10 >= ES_FRAME ? 1 + (n10 - ES_FRAME) / ES_HOP : 1;
+    double* x10 = static_cast<double*>(c.buf("ws.es.x10", (size_t)B * n10 * 8));
+    double* y10 = static_cast<double*>(c.buf("ws.es.y10", (size_t)B * n10 * 8));
+    double* xs = static_cast<double*>(c.buf("ws.es.xs", (size_t)B * n10 * 8));
+    double* ys = static_cast<double*>(c.buf("ws.es.ys", (size_t)B * n10 * 8));
+    double* xt = static_cast<double*>(c.buf("ws.es.xt", (size_t)B * ES_BANDS * max_frames * 8));
+    double* yt = static_cast<double*>(c.buf("ws.es.yt", (size_t)B * ES_BANDS * max_frames * 8));
+    int* nk = static_cast<int*>(c.buf("ws.es.nk", (size_t)B * 4));
+    const double* h = reinterpret_cast<const double*>(c.dev("es.h"));
+    const double* win = reinterpret_cast<const double*>(c.dev("es.win"));
+    const int* lo = reinterpret_cast<const int*>(c.dev("es.lo")); const int* hi = reinterpret_cast<const int*>(c.dev("es.hi"));
+    es_resample_kernel<<<ew_grid((size_t)B * n10), 256, 0, s>>>(clean, x10, B, S, n10, h);
+    check_launch(c, "estoi resample");
+    es_resample_kernel<<<ew_grid((size_t)B * n10), 256, 0, s>>>(processed, y10, B, S, n10, h);
+    check_launch(c, "estoi resample");
+    es_silent_kernel<<<B, 256, (size_t)max_frames * 12 + 16, s>>>(x10, y10, n10, win, xs, ys, nk, max_frames);
+    check_launch(c, "estoi silent frames");
+    es_bands_kernel<<<dim3(max_frames, B), 256, 0, s>>>(xs, n10, nk, win, lo, hi, xt, max_frames);
+    check_launch(c, "estoi bands");
+    es_bands_kernel<<<dim3(max_frames, B), 256, 0, s>>>(ys, n10, nk, win, lo, hi, yt, max_frames);
+    check_launch(c, "estoi bands");
+    es_score_kernel<<<B, 512, 0, s>>>(xt, yt, nk, out, max_frames);
+    check_launch(c, "estoi score");
     API_END(ctx)
 }
 
