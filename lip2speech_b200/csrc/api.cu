@@ -402,10 +402,29 @@ static inline VideoSrc video_u8(const unsigned char* p, const float* mean_std) {
 // ------------------------------------------------------------------------------------------------
 // persistent LSTM launch helper
 // ------------------------------------------------------------------------------------------------
+// hist[time slot][plane][H][Bpad] is zero-filled ("not written") and slot 0 / the cell state get the initial state:
+// h0 rows [B][lds] for every plane (the encoder Bi-LSTM's site embedding, decoder.py:325) or zeros (h0 == nullptr)
+__global__ void lstm_init_kernel(const float* __restrict__ h0, int lds, float* __restrict__ hist0, float* __restrict__ cbuf, int planes, int H, int B, int Bpad) {
+    const size_t total = (size_t)planes * H * Bpad;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int b = i % Bpad; const int f = (i / Bpad) % H;
+        const float v = (h0 && b < B) ? h0[(size_t)b * lds + f] : 0.f;
+        lstm_st(hist0 + i, v);
+        cbuf[i] = v;
+    }
+}
+
+static float* lstm_history(Context& c, const std::string& name, const float* h0, int lds, float* cbuf, int T, int planes, int H, int B, int Bpad, cudaStream_t s) {
+    const size_t slot = (size_t)planes * H * Bpad;
+    float* hist = c.fbuf(name, (size_t)(T + 1) * slot);
+    L2S_CUDA(cudaMemsetAsync(hist, 0, (size_t)(T + 1) * slot * sizeof(float), s));
+    lstm_init_kernel<<<ew_grid(slot), 256, 0, s>>>(h0, lds, hist, cbuf, planes, H, B, Bpad);
+    check_launch(c, "lstm initial state");
+    return hist;
+}
+
 static void launch_lstm(Context& c, LstmParams lp, cudaStream_t s) {
-    unsigned* bar = static_cast<unsigned*>(c.buf("ws.barrier", 256));
-    L2S_CUDA(cudaMemsetAsync(bar, 0, 4, s));
-    lp.barrier = bar;
+    lp.abort_word = static_cast<unsigned*>(c.buf("ws.d.abort", 256));
     const size_t smem = lstm_smem_bytes(lp.H);
     L2S_CUDA(cudaFuncSetAttribute(lstm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = c.num_sms;
@@ -438,18 +457,15 @@ static void speaker_forward(Context& c, const float* wav, int B, int S, float* e
     float* xproj = c.fbuf("ws.s.xproj", (size_t)B * F * 4 * H);
     linear(c, mel, 40, "s.wih0", c.dev("s.b0"), xproj, 4 * H, B * F, 4 * H, 40, ACT_NONE, nullptr, s, "speaker xproj");
     const size_t plane = (size_t)H * Bpad;
-    float* hbuf = c.fbuf("ws.s.h", 2 * L * plane);
     float* cbuf = c.fbuf("ws.s.c", L * plane);
-    L2S_CUDA(cudaMemsetAsync(hbuf, 0, 2 * L * plane * sizeof(float), s));
-    L2S_CUDA(cudaMemsetAsync(cbuf, 0, L * plane * sizeof(float), s));
+    float* hist = lstm_history(c, "ws.s.hist", nullptr, 0, cbuf, F, L, H, B, Bpad, s);      // zero initial state (audio.py:135)
     LstmParams lp{};
     lp.xproj = xproj; lp.ldx = 4 * H; lp.wpk = c.dev("s.lstm.w");
     lp.blocks = reinterpret_cast<const LstmBlock*>(c.dev("s.lstm.blocks"));
-    lp.hbuf = hbuf; lp.cbuf = cbuf; lp.out = nullptr; lp.ldo = 0;
+    lp.hist = hist; lp.cbuf = cbuf; lp.out = nullptr; lp.ldo = 0;
     lp.T = F; lp.B = B; lp.Bpad = Bpad; lp.H = H; lp.L = L; lp.dirs = 1;
     launch_lstm(c, lp, s);
-    const int nsteps = F + L - 1;
-    const float* hfinal = hbuf + (size_t)(nsteps & 1) * L * plane + (size_t)(L - 1) * plane;
+    const float* hfinal = hist + (size_t)F * L * plane + (size_t)(L - 1) * plane;          // last layer after the last frame
     speaker_head_kernel<<<B, 256, 0, s>>>(hfinal, Bpad, c.dev("s.lin.w"), c.dev("s.lin.b"), emb, normalize);
     check_launch(c, "speaker head");
 }
@@ -615,26 +631,18 @@ static void decoder_run(Context& c, const float* visual, const float* spk, const
     float* xproj = c.fbuf("ws.d.xproj", (size_t)M * 4096);
     linear(c, visual, 1024, "d.ernn.wih", c.dev("d.ernn.b"), xproj, 4096, M, 4096, 1024, ACT_NONE, nullptr, s, "encoder_rnn xproj");
     const size_t plane = (size_t)512 * Bpad;
-    float* eh = c.fbuf("ws.d.eh", 2 * 2 * plane);      // [parity][dir][512][Bpad]
     float* ec = c.fbuf("ws.d.ec", 2 * plane);
-    for (int i = 0; i < 4; ++i) {
-        rows_to_fm_kernel<<<ew_grid(plane), 256, 0, s>>>(encsite, 512, 0, eh + i * plane, 512, B, Bpad);
-        check_launch(c, "site->fm");
-    }
-    for (int i = 0; i < 2; ++i) {
-        rows_to_fm_kernel<<<ew_grid(plane), 256, 0, s>>>(encsite, 512, 0, ec + i * plane, 512, B, Bpad);
-        check_launch(c, "site->fm");
-    }
+    float* eh = lstm_history(c, "ws.d.ehist", encsite, 512, ec, T, 2, 512, B, Bpad, s);    // h0 = c0 = site embedding, both directions
     float* rnn_out = c.fbuf("ws.d.rnnout", (size_t)M * 1024);
     {
         LstmParams lp{};
         lp.xproj = xproj; lp.ldx = 4096; lp.wpk = c.dev("d.ernn.w");
         lp.blocks = reinterpret_cast<const LstmBlock*>(c.dev("d.ernn.blocks"));
-        lp.hbuf = eh; lp.cbuf = ec; lp.out = rnn_out; lp.ldo = 1024;
+        lp.hist = eh; lp.cbuf = ec; lp.out = rnn_out; lp.ldo = 1024;
         lp.T = T; lp.B = B; lp.Bpad = Bpad; lp.H = 512; lp.L = 1; lp.dirs = 2;
         launch_lstm(c, lp, s);
     }
-    const float* hfinal = eh + (size_t)(T & 1) * 2 * plane;      // feature-major [h_fwd ; h_bwd] = decoder (h0 ; h1)
+    const float* hfinal = eh + (size_t)T * 2 * plane;            // slot T: feature-major [h_fwd ; h_bwd] = decoder (h0 ; h1)
     float* ccat = c.fbuf("ws.d.ccat", (size_t)B * 1024);
     fm_to_rows_kernel<<<ew_grid((size_t)1024 * B), 256, 0, s>>>(ec, Bpad, ccat, 1024, 0, 1024, B);
     check_launch(c, "c_n -> rows");
