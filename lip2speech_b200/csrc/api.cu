@@ -59,8 +59,9 @@ static inline TcParams tc_defaults();
 // Few rows, long K (the pre-loop's site / content / E_C layers at B=32: 32-928 rows): the tcgen05 GEMM would run on 2-32
 // CTAs, each streaming megabytes of weights alone.  Split K over the whole chip with the streaming mma.sync kernel
 // (pw_mma.cuh) and add the partial sums in a fixed order.  Returns false when the shape does not qualify.
+struct SplitKExtra { int L = 1; const float* addrow = nullptr; const float* addpos = nullptr; int ldpos = 0; const float* resid = nullptr; int ldr = 0; };
 static bool splitk_small_m(Context& c, const float* A, int lda, const std::string& wname, const float* b, float* C, int ldc, int M, int N, int K,
-                           int act, const float* act_w, cudaStream_t s, const char* what) {
+                           int act, const float* act_w, cudaStream_t s, const char* what, const SplitKExtra& ex = SplitKExtra{}) {
     if (!c.use_tc || !c.use_pw || M > 1024 || (size_t)N * K < 32768 || (lda % 4) || (K % 4) || (reinterpret_cast<uintptr_t>(A) & 15)) return false;
     const int bn = (N <= 32) ? 32 : (N <= 64 ? 64 : 128);
     if (ceil_div(M, TC_BM) * ceil_div(N, bn) > 48) return false;             // enough tiles for the tcgen05 kernel
@@ -78,7 +79,7 @@ static bool splitk_small_m(Context& c, const float* A, int lda, const std::strin
     const char* err = launch_pw_mma(p, c.num_sms, s);
     if (err) throw L2sError(L2S_ERR_CUDA, std::string(what) + " (split-K mma): " + err);
     c.launches++;
-    pw_reduce_kernel<<<ew_grid((size_t)M * N), 256, 0, s>>>(p.partial, nsplits, M, N, b, act, act_w, C, ldc);
+    pw_reduce_kernel<<<ew_grid((size_t)M * N), 256, 0, s>>>(p.partial, nsplits, M, N, b, act, act_w, C, ldc, ex.L, ex.addrow, ex.addpos, ex.ldpos, ex.resid, ex.ldr);
     check_launch(c, what);
     return true;
 }
@@ -127,6 +128,12 @@ static void gemm_auto(Context& c, GemmParams g, const std::string& wname, cudaSt
         return;
     }
     if (pass_x) throw L2sError(L2S_ERR_INVALID, std::string(what) + ": internal: fused pass-through requested on a non-streaming GEMM");
+    // few rows, long K, plain channel order (encoder_proj, the K / V bottlenecks at B=32: 8 x 4 tiles would occupy 32 SMs):
+    // split K over the chip; the reduction kernel applies the row / position / residual terms of the epilogue
+    if (g.taps == 1 && g.stride == 1 && !g.stem && !g.transposed && g.cstride == 1 && g.coff == 0 && g.chalf == 0 ) {
+        SplitKExtra ex; ex.L = g.L_out; ex.addrow = g.addrow; ex.addpos = g.addpos; ex.ldpos = g.ldpos; ex.resid = g.resid; ex.ldr = g.ldr;
+        if (splitk_small_m(c, g.A, g.lda, wname, g.bias, g.C, g.ldc, g.M, g.N, g.Kc, g.act, g.act_w, s, what, ex)) return;
+    }
     if (c.use_tc && g.taps == 1 && g.stride == 1 && !g.stem && (g.lda % 4) == 0 && (reinterpret_cast<uintptr_t>(g.A) & 15) == 0) {
         const int kcp = (int)c.meta.at(wname + ".kcp");
         TcOperands o{g.A, g.Kc, g.M, g.lda, c.dev(wname + ".hi"), c.dev(wname + ".lo"), kcp};

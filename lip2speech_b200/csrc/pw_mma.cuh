@@ -194,15 +194,22 @@ inline int pw_ldw(int Kp) { return (Kp % 32 == 0) ? Kp + 16 : Kp; }      // rows
 inline size_t pw_smem_bytes(int Kc) { const int Kp = (Kc + 15) / 16 * 16; return (size_t)PW_NSLICE * pw_ldw(Kp) * sizeof(float); }
 
 // C[m][n] = act( sum_z partial[z][m][n] + bias[n] ), splits added in index order (deterministic)
+// Optional epilogue operands as in gemm.cuh: + addrow[m / L][n] before the activation, + addpos[m % L][n] and + resid[m][n] after it.
 __global__ void pw_reduce_kernel(const float* __restrict__ partial, int nsplits, int M, int N, const float* __restrict__ bias, int act,
-                                 const float* __restrict__ act_w, float* __restrict__ C, int ldc) {
+                                 const float* __restrict__ act_w, float* __restrict__ C, int ldc,
+                                 int L = 1, const float* __restrict__ addrow = nullptr, const float* __restrict__ addpos = nullptr, int ldpos = 0,
+                                 const float* __restrict__ resid = nullptr, int ldr = 0) {
     const size_t total = (size_t)M * N;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int n = i % N; const size_t m = i / N;
         float v = 0.f;
         for (int z = 0; z < nsplits; ++z) v += partial[(size_t)z * total + i];
         if (bias) v += __ldg(bias + n);
-        C[m * ldc + n] = apply_act(v, act, act_w ? __ldg(act_w + n) : 1.f);
+        if (addrow) v += __ldg(addrow + (m / L) * N + n);
+        v = apply_act(v, act, act_w ? __ldg(act_w + n) : 1.f);
+        if (addpos) v += __ldg(addpos + (m % L) * ldpos + n);
+        if (resid) v += resid[m * ldr + n];
+        C[m * ldc + n] = v;
     }
 }
 
