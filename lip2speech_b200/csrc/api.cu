@@ -433,7 +433,10 @@ static float* lstm_history(Context& c, const std::string& name, const float* h0,
 static void launch_lstm(Context& c, LstmParams lp, cudaStream_t s) {
     lp.abort_word = static_cast<unsigned*>(c.buf("ws.d.abort", 256));
     const size_t smem = lstm_smem_bytes(lp.H);
-    L2S_CUDA(cudaFuncSetAttribute(lstm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if ((int64_t)smem > c.meta["attr.lstm.smem"]) {          // raised when needed, not set on every launch
+        L2S_CUDA(cudaFuncSetAttribute(lstm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        c.meta["attr.lstm.smem"] = (int64_t)smem;
+    }
     const int grid = c.num_sms;
     void* args[] = {&lp};
     L2S_CUDA(cudaLaunchCooperativeKernel((void*)lstm_persistent_kernel, dim3(grid), dim3(MV_THREADS), args, smem, s));
@@ -796,7 +799,10 @@ static void decoder_run(Context& c, const float* visual, const float* spk, const
         split_halves_kernel<<<ew_grid((size_t)B * minT * 256), 256, 0, s>>>(cval, cvsplit, B, minT, 128);
         check_launch(c, "content value halves");
         const size_t smem = (size_t)c.meta.at("d.step3.smem");
-        L2S_CUDA(cudaFuncSetAttribute(decode3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if ((int64_t)smem > c.meta["attr.dec3.smem"]) {
+            L2S_CUDA(cudaFuncSetAttribute(decode3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            c.meta["attr.dec3.smem"] = (int64_t)smem;
+        }
         const int chunk = D3_CG * D3_NG;
         c.meta["dbg.dec3"] = 1;
         c.span_end("preloop", s);

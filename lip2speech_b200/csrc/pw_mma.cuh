@@ -225,8 +225,13 @@ inline const char* launch_pw_mma(PwParams p, int num_sms, cudaStream_t s) {
     p.ldw = pw_ldw(p.Kp);
     if ((p.Kc + 15) / 16 * 16 > p.kcp) return "packed weights narrower than the padded K";
     const size_t smem = pw_smem_bytes(std::min(p.ksplit, p.Kc));
-    cudaError_t e = cudaFuncSetAttribute(pw_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cudaGetErrorString(e);
+    static size_t attr_smem = 0;                           // raised when a launch needs more, not set on every launch
+    cudaError_t e = cudaSuccess;
+    if (smem > attr_smem) {
+        e = cudaFuncSetAttribute(pw_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cudaGetErrorString(e);
+        attr_smem = smem;
+    }
     const int nslices = (p.N + PW_NSLICE - 1) / PW_NSLICE;
     const int per_sm = smem * 2 + 4096 <= 227 * 1024 ? 2 : 1;
     const int ntiles = (p.M + 15) / 16;

@@ -509,8 +509,12 @@ struct TcOperands {
 
 template <int BN, bool G>
 inline cudaError_t launch_tc_inst(dim3 grid, const CUtensorMap& mA, const CUtensorMap& mWh, const CUtensorMap& mWl, const TcParams& p, cudaStream_t s) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::TOTAL);
-    if (e != cudaSuccess) return e;
+    static bool attr_set = false;                          // once per process (one device per process): not on every launch
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::TOTAL);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
     tc_gemm_kernel<BN, G><<<grid, TC_THREADS_P, TcSmem<BN>::TOTAL, s>>>(mA, mWh, mWl, p);
     return cudaGetLastError();
 }
@@ -563,8 +567,13 @@ inline const char* launch_tc_stem_bf16(const void* A16, const void* W16, int tap
     if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
     const int ntiles = ceil_div(p.M, TC_BM);
     dim3 grid(ntiles < num_sms ? ntiles : num_sms);
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<32, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<32>::TOTAL);
-    if (e != cudaSuccess) return cudaGetErrorString(e);
+    static bool attr_set = false;
+    cudaError_t e = cudaSuccess;
+    if (!attr_set) {
+        e = cudaFuncSetAttribute(tc_gemm_kernel<32, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<32>::TOTAL);
+        if (e != cudaSuccess) return cudaGetErrorString(e);
+        attr_set = true;
+    }
     tc_gemm_kernel<32, true, true><<<grid, TC_THREADS_P, TcSmem<32>::TOTAL, s>>>(mW, mW, mW, p);
     e = cudaGetLastError();
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
