@@ -154,6 +154,11 @@ int l2s_clip_adamw_step(l2s_ctx* ctx, float* p, float* g, float* m, float* v, fl
  * updated in place by the forward pass as nn.BatchNorm*d does in train()).  Pointers stay owned by the caller and must stay
  * valid; re-binding a key replaces it.  An optimizer step therefore needs no re-bind / re-pack. */
 int l2s_train_bind(l2s_ctx* ctx, const char* key, float* param, float* grad, int64_t numel);
+/* The train-mode forward / backward calls below launch ~13 K small kernels per step.  With graphs enabled (the default) the
+ * second call with the same shapes captures that launch sequence as a CUDA graph and later calls replay it (inputs are staged
+ * into library memory first, so caller tensors may move between steps; re-binding a key to different memory drops the graphs).
+ * Results are bit-identical either way.  enabled = 0 runs every call eagerly and frees the captured graphs. */
+int l2s_train_set_graphs(l2s_ctx* ctx, int enabled);
 
 /* Decoder.forward in TRAIN mode (decoder.py:320-379): BatchNorm batch statistics, and every random draw of the reference as an
  * explicit device input so that results are reproducible and checkable: tf_mask (HOST, M bytes: the coin flips of :355-357),

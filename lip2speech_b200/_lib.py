@@ -20,7 +20,7 @@ IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)      
 EXPORTS = ("l2s_version", "l2s_create", "l2s_destroy", "l2s_last_error", "l2s_bind_weight", "l2s_commit_weights",
            "l2s_video_fwd", "l2s_speaker_fwd", "l2s_decoder_infer", "l2s_decoder_forward", "l2s_postnet_fwd", "l2s_infer", "l2s_infer_host", "l2s_infer_host_submit", "l2s_infer_host_wait",
            "l2s_video_fwd_u8", "l2s_infer_u8", "l2s_infer_host_submit_u8",
-           "l2s_train_bind", "l2s_decoder_train_fwd", "l2s_decoder_train_bwd", "l2s_video_train_fwd", "l2s_video_train_bwd",
+           "l2s_train_bind", "l2s_train_set_graphs", "l2s_decoder_train_fwd", "l2s_decoder_train_bwd", "l2s_video_train_fwd", "l2s_video_train_bwd",
            "l2s_vocoder", "l2s_estoi",
            "l2s_launch_count", "l2s_debug_read", "l2s_set_profiling", "l2s_span_ms",
            "l2s_loss_fwd_bwd", "l2s_nccl_unique_id", "l2s_comm_init", "l2s_comm_destroy", "l2s_allreduce_grads", "l2s_clip_adamw_step")
@@ -60,6 +60,7 @@ def load() -> C.CDLL:
         lib.l2s_infer_u8.argtypes = [vp, vp, vp, fp, fp, i, i, i, i, i, i, fp, vp, i, vp]
         lib.l2s_infer_host_submit_u8.argtypes = [vp, i, vp, vp, fp, fp, i, i, i, i, i, i, fp, vp, i]
         lib.l2s_train_bind.argtypes = [vp, C.c_char_p, vp, vp, C.c_int64]
+        lib.l2s_train_set_graphs.argtypes = [vp, i]
         lib.l2s_decoder_train_fwd.argtypes = [vp, fp, fp, fp, vp, fp, fp, fp, fp, C.POINTER(vp), i, i, i, i, fp, fp, fp, fp, fp, vp]
         lib.l2s_decoder_train_bwd.argtypes = [vp, fp, fp, fp, fp, fp, fp, vp]
         lib.l2s_video_train_fwd.argtypes = [vp, fp, fp, i, i, i, i, fp, vp]
@@ -323,6 +324,10 @@ class Backend:
         self._check(self.lib.l2s_train_bind(self.h, key.encode(), C.c_void_p(param.data_ptr()),
                                             C.c_void_p(grad.data_ptr()) if grad is not None else None, param.numel()), f"l2s_train_bind({key})")
 
+    def train_set_graphs(self, enabled: bool):
+        """CUDA-graph replay of the train-mode forward / backward launch sequences (on by default; results are bit-identical)."""
+        self._check(self.lib.l2s_train_set_graphs(self.h, int(bool(enabled))), "l2s_train_set_graphs")
+
     def decoder_train_fwd(self, visual, spk, mels, noise, want_input_grads=True):
         """noise: object with tf_mask [M] (host bool), gumbel, prenet [M,B,256], attn [M,B,T], lstm [M,B,512], post (5 x [B,C,M])
         — KEEP masks, float32 on the device.  Returns (out_mel, out_post, out_stop [B,M,1], attn_logits [B,M,T], content_dis)."""
@@ -343,8 +348,6 @@ class Backend:
                                                    gum.data_ptr(), pm.data_ptr(), am.data_ptr(), lm.data_ptr(), pp, B, T, M, int(want_input_grads),
                                                    out_mel.data_ptr(), out_post.data_ptr(), out_stop.data_ptr(), out_attn.data_ptr(),
                                                    out_dis.data_ptr(), self._stream()), "l2s_decoder_train_fwd")
-        # the masks are read again by the backward pass: keep them (and the inputs) alive until then
-        self._train_keep = (visual, spk, mels, gum, pm, am, lm, post, mask)
         return out_mel, out_post, out_stop, out_attn, out_dis
 
     def decoder_train_bwd(self, g_mel, g_post, g_stop, g_dis, B, T, want_input_grads=True):
@@ -353,7 +356,6 @@ class Backend:
         g_visual = torch.empty(B, T, 1024, device=self.device) if want_input_grads else None
         g_spk = torch.empty(B, 256, device=self.device) if want_input_grads else None
         self._check(self.lib.l2s_decoder_train_bwd(self.h, *(ptr(g) for g in gs), ptr(g_visual), ptr(g_spk), self._stream()), "l2s_decoder_train_bwd")
-        self._train_keep = None
         return g_visual, g_spk
 
     def video_train_fwd(self, video, drop_mask=None):
@@ -367,13 +369,11 @@ class Backend:
         out = torch.empty(B, T, 768, device=self.device)
         self._check(self.lib.l2s_video_train_fwd(self.h, video.data_ptr(), drop_mask.data_ptr() if drop_mask is not None else None, B, T, H, W,
                                                  out.data_ptr(), self._stream()), "l2s_video_train_fwd")
-        self._video_keep = (video, drop_mask)
         return out
 
     def video_train_bwd(self, g_feat):
         g_feat = _f32c(g_feat, self.device)
         self._check(self.lib.l2s_video_train_bwd(self.h, g_feat.data_ptr(), self._stream()), "l2s_video_train_bwd")
-        self._video_keep = None
 
     # ---- after the path: vocoder + ESTOI (demo.py:89-90, evaluate.py:41-45) ----------------------------------------------------
     def bind_vocoder(self, inv_mel: torch.Tensor):

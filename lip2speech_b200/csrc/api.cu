@@ -23,6 +23,7 @@ using namespace l2s;
 struct l2s_ctx {
     Context c;
     std::map<std::string, tr::Param> train_params;      // caller-owned parameter / gradient memory (l2s_train_bind)
+    uint64_t train_bind_gen = 1;                        // bumped whenever a binding changes address or size: captured graphs are stale
     tr::DecoderTrain dec_train;
     tr::VideoTrain video_train;
 };
@@ -939,8 +940,8 @@ void l2s_destroy(l2s_ctx* ctx) {
     cudaSetDevice(ctx->c.device);
     cudaDeviceSynchronize();
     destroy_comm_quiet(ctx->c);
-    ctx->dec_train.e.vals.free_all(); ctx->dec_train.e.grads.free_all();
-    ctx->video_train.e.vals.free_all(); ctx->video_train.e.grads.free_all();
+    ctx->dec_train.release();
+    ctx->video_train.release();
     ctx->c.free_all();
     delete ctx;
 }
@@ -1360,7 +1361,17 @@ int l2s_train_bind(l2s_ctx* ctx, const char* key, float* param, float* grad, int
     API_BEGIN
     if (!key || !param || numel <= 0) throw L2sError(L2S_ERR_INVALID, "train_bind: bad arguments");
     tr::Param p; p.v = param; p.g = grad; p.n = numel;
-    ctx->train_params[key] = p;
+    tr::Param& slot = ctx->train_params[key];
+    if (slot.v != p.v || slot.g != p.g || slot.n != p.n) { slot = p; ++ctx->train_bind_gen; }
+    API_END(ctx)
+}
+
+int l2s_train_set_graphs(l2s_ctx* ctx, int enabled) {
+    if (!ctx) return L2S_ERR_INVALID;
+    API_BEGIN
+    L2S_CUDA(cudaSetDevice(ctx->c.device));
+    ctx->dec_train.use_graphs = ctx->video_train.use_graphs = enabled != 0;
+    if (!enabled) { L2S_CUDA(cudaDeviceSynchronize()); ctx->dec_train.drop_graphs(); ctx->video_train.drop_graphs(); }
     API_END(ctx)
 }
 
@@ -1378,7 +1389,7 @@ int l2s_decoder_train_fwd(l2s_ctx* ctx, const float* visual, const float* spk, c
     io.prenet_mask = prenet_mask; io.attn_mask = attn_mask; io.lstm_mask = lstm_mask;
     for (int i = 0; i < 5; ++i) { if (!post_masks[i]) throw L2sError(L2S_ERR_INVALID, "decoder_train_fwd: five postnet masks are required"); io.post_mask[i] = post_masks[i]; }
     io.out_mel = out_mel; io.out_post = out_post; io.out_stop = out_stop; io.out_attn_logits = out_attn_logits; io.out_content_dis = out_content_dis;
-    ctx->dec_train.forward(ctx->c, ctx->train_params, io, B, T, M, want_input_grads != 0, (cudaStream_t)stream);
+    ctx->dec_train.forward(ctx->c, ctx->train_params, ctx->train_bind_gen, io, B, T, M, want_input_grads != 0, (cudaStream_t)stream);
     API_END(ctx)
 }
 
@@ -1387,7 +1398,7 @@ int l2s_decoder_train_bwd(l2s_ctx* ctx, const float* g_mel, const float* g_post,
     if (!ctx) return L2S_ERR_INVALID;
     API_BEGIN
     L2S_CUDA(cudaSetDevice(ctx->c.device));
-    ctx->dec_train.backward(g_mel, g_post, g_stop, g_content_dis, g_visual, g_spk, (cudaStream_t)stream);
+    ctx->dec_train.backward(ctx->c, g_mel, g_post, g_stop, g_content_dis, g_visual, g_spk, (cudaStream_t)stream);
     API_END(ctx)
 }
 
@@ -1472,7 +1483,7 @@ int l2s_video_train_fwd(l2s_ctx* ctx, const float* video, const float* drop_mask
     API_BEGIN
     if (!video || !out_feat) throw L2sError(L2S_ERR_INVALID, "video_train_fwd: video and out_feat are required");
     L2S_CUDA(cudaSetDevice(ctx->c.device));
-    ctx->video_train.forward(ctx->c, ctx->train_params, video, drop_mask, B, T, H, W, out_feat, (cudaStream_t)stream);
+    ctx->video_train.forward(ctx->c, ctx->train_params, ctx->train_bind_gen, video, drop_mask, B, T, H, W, out_feat, (cudaStream_t)stream);
     API_END(ctx)
 }
 
@@ -1481,7 +1492,7 @@ int l2s_video_train_bwd(l2s_ctx* ctx, const float* g_feat, void* stream) {
     API_BEGIN
     if (!g_feat) throw L2sError(L2S_ERR_INVALID, "video_train_bwd: g_feat is required");
     L2S_CUDA(cudaSetDevice(ctx->c.device));
-    ctx->video_train.backward(g_feat, (cudaStream_t)stream);
+    ctx->video_train.backward(ctx->c, g_feat, (cudaStream_t)stream);
     API_END(ctx)
 }
 

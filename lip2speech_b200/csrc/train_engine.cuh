@@ -338,6 +338,15 @@ __global__ void ew_bwd_kernel(int rows, int cols, const float* __restrict__ X, i
         dX[(size_t)r * dxs + c] += d;
     }
 }
+__global__ void select_fwd_kernel(int rows, int cols, const float* __restrict__ flag, const float* __restrict__ A, int as, const float* __restrict__ Bv, int bs,
+                                  float* __restrict__ Y, int ys) {
+    const bool pick_a = flag[0] != 0.f;
+    TR_EW_LOOP((size_t)rows * cols) { const int r = i / cols, c = i % cols; Y[(size_t)r * ys + c] = pick_a ? A[(size_t)r * as + c] : Bv[(size_t)r * bs + c]; }
+}
+__global__ void select_bwd_kernel(int rows, int cols, const float* __restrict__ flag, const float* __restrict__ dY, int dys, float* __restrict__ dB, int dbs) {
+    if (flag[0] != 0.f) return;
+    TR_EW_LOOP((size_t)rows * cols) { const int r = i / cols, c = i % cols; dB[(size_t)r * dbs + c] += dY[(size_t)r * dys + c]; }
+}
 // dAux[g][c] += sum over the `group` rows of group g of dY   (backward of EW_ADDROW w.r.t. the broadcast operand)
 __global__ void addrow_bwd_kernel(int groups, int group, int cols, const float* __restrict__ dY, int dys, float* __restrict__ dA, int das) {
     TR_EW_LOOP((size_t)groups * cols) {
@@ -838,6 +847,53 @@ struct Arena {                     // bump allocator over cudaMalloc'ed blocks t
 
 struct Param { float* v = nullptr; float* g = nullptr; int64_t n = 0; };
 
+// ---- CUDA-graph replay -----------------------------------------------------------------------------------------------------
+// A train step launches ~13 K small kernels from host closures (~8 us of host time each).  The arenas hand out the same
+// addresses for the same shapes, so the whole forward (and the whole backward) of one (B, T, M, ...) key is captured once as a
+// CUDA graph and replayed: the second call with a key captures, later calls replay.  Caller tensors never appear inside a
+// graph — inputs are staged into arena memory before the launch, outputs copied out after it.
+struct HostTables {                // pinned host memory read by the captured H2D copies of the row-pointer tables at every replay
+    char* p = nullptr; size_t cap = 0, used = 0;
+    void reserve(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        L2S_CUDA(cudaMallocHost(&p, bytes));
+        cap = bytes;
+    }
+    void* take(size_t bytes) {
+        if (used + bytes > cap) throw L2sError(2, "train: row-pointer tables outgrew their pinned buffer");
+        void* r = p + used; used += (bytes + 15) & ~size_t(15); return r;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = used = 0; }
+};
+struct GraphSlot {
+    cudaGraphExec_t fwd = nullptr, bwd = nullptr;
+    int64_t fwd_launches = 0, bwd_launches = 0;
+    int seen = 0;
+    size_t table_bytes = 0;        // what the last eager backward needed for its pointer tables
+    HostTables tables;
+    void drop_graphs() {
+        if (fwd) cudaGraphExecDestroy(fwd);
+        if (bwd) cudaGraphExecDestroy(bwd);
+        fwd = bwd = nullptr;
+    }
+    void release() { drop_graphs(); tables.release(); }
+};
+template <class F>
+inline cudaGraphExec_t capture_graph(cudaStream_t cs, F&& body) {
+    L2S_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
+    cudaGraph_t g = nullptr;
+    try { body(); }
+    catch (...) { cudaStreamEndCapture(cs, &g); if (g) cudaGraphDestroy(g); throw; }
+    L2S_CUDA(cudaStreamEndCapture(cs, &g));
+    cudaGraphExec_t x = nullptr;
+    const cudaError_t err = cudaGraphInstantiate(&x, g, 0);
+    cudaGraphDestroy(g);
+    if (err != cudaSuccess) throw L2sError(2, std::string("train: cudaGraphInstantiate: ") + cudaGetErrorString(err));
+    return x;
+}
+
 inline int ew_blocks(size_t total) { return (int)std::min<size_t>(std::max<size_t>((total + 255) / 256, 1), 148 * 16); }
 
 struct Engine {
@@ -848,6 +904,9 @@ struct Engine {
     std::map<std::string, Param>* params = nullptr;
     bool update_bn_running = true;
     int64_t* launches = nullptr;
+    bool capturing = false;            // the body runs under stream capture: no synchronisation, host tables must persist
+    HostTables* tables = nullptr;      // where a captured backward keeps its row-pointer tables
+    size_t table_bytes = 0;            // bytes of pointer tables the last backward uploaded
 
     void begin(Context* c, cudaStream_t stream, std::map<std::string, Param>* p) {
         ctx = c; s = stream; params = p; launches = &c->launches;
@@ -903,18 +962,27 @@ struct Engine {
     struct Deferred { TT W; std::vector<const float*> a, b; };
     std::map<float*, Deferred> deferred;
     void flush_deferred() {
+        table_bytes = 0;
         for (auto& kv : deferred) {
             Deferred& d = kv.second;
             const int R = (int)d.a.size();
+            const size_t half = (size_t)R * sizeof(float*);
             const float** tab = reinterpret_cast<const float**>(scratch((size_t)R * 4));      // 2 R pointers of 8 bytes
-            L2S_CUDA(cudaMemcpyAsync(tab, d.a.data(), (size_t)R * sizeof(float*), cudaMemcpyHostToDevice, s));
-            L2S_CUDA(cudaMemcpyAsync(tab + R, d.b.data(), (size_t)R * sizeof(float*), cudaMemcpyHostToDevice, s));
+            if (capturing) {
+                char* host = static_cast<char*>(tables->take(2 * half));
+                memcpy(host, d.a.data(), half); memcpy(host + half, d.b.data(), half);
+                L2S_CUDA(cudaMemcpyAsync(tab, host, 2 * half, cudaMemcpyHostToDevice, s));
+            } else {
+                L2S_CUDA(cudaMemcpyAsync(tab, d.a.data(), half, cudaMemcpyHostToDevice, s));
+                L2S_CUDA(cudaMemcpyAsync(tab + R, d.b.data(), half, cudaMemcpyHostToDevice, s));
+            }
+            table_bytes += 2 * half + 16;
             const int N = d.W.rows, K = d.W.cols;
             sgemm_tn_rows_kernel<<<dim3((K + 63) / 64, (N + 63) / 64), 256, 0, s>>>(N, K, R, tab, tab + R, d.W.g, d.W.rs);
             ck("deferred weight gradient");
         }
-        // the host pointer tables must outlive the asynchronous copies
-        L2S_CUDA(cudaStreamSynchronize(s));
+        // eager: the host pointer tables must outlive the asynchronous copies
+        if (!capturing) L2S_CUDA(cudaStreamSynchronize(s));
         deferred.clear();
     }
 
@@ -1028,6 +1096,19 @@ struct Engine {
         tape.push_back([=]() {
             for (const TT* t : {&a, &b})
                 if (t->g) { ew_bwd_kernel<EW_COPY><<<ew_blocks(y.numel()), 256, 0, s>>>(y.rows, y.cols, nullptr, 0, nullptr, 0, 0.f, y.g, y.rs, t->g, t->rs); ck("add bwd"); }
+        });
+        return y;
+    }
+    // y = flag[0] != 0 ? a : b, the flag read on the DEVICE (the teacher-forcing coin of decoder.py:355-357: the launch sequence
+    // does not depend on the draw, so one captured graph serves every step).  Only b carries a gradient (a = teacher frames).
+    TT select(const float* flag, const TT& a, const TT& b) {
+        TT y = make(a.rows, a.cols);
+        select_fwd_kernel<<<ew_blocks(a.numel()), 256, 0, s>>>(a.rows, a.cols, flag, a.v, a.rs, b.v, b.rs, y.v, y.rs);
+        ck("select");
+        tape.push_back([=]() {
+            if (!b.g) return;
+            select_bwd_kernel<<<ew_blocks(y.numel()), 256, 0, s>>>(y.rows, y.cols, flag, y.g, y.rs, b.g, b.rs);
+            ck("select bwd");
         });
         return y;
     }

@@ -24,19 +24,49 @@ struct DecoderTrainIO {
     float* out_mel; float* out_post; float* out_stop; float* out_attn_logits; float* out_content_dis;
 };
 
+// Which way a forward ran, and therefore how its backward has to run.
+enum GraphMode { RUN_EAGER = 0, RUN_CAPTURED = 1, RUN_REPLAY = 2 };
+
+inline cudaStream_t capture_stream(cudaStream_t& cs) {            // capture needs a non-legacy stream; the caller's may be stream 0
+    if (!cs) L2S_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    return cs;
+}
+inline int content_min_t(int T) { return T / 7; }                 // Content.agg: four Conv1d(k, stride=k), k = 1,3,5,7 -> shortest output (decoder.py:222-233)
+inline void stage_in(float* dst, const float* src, size_t floats, cudaStream_t s) {      // null source: zeros
+    if (src) L2S_CUDA(cudaMemcpyAsync(dst, src, floats * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    else L2S_CUDA(cudaMemsetAsync(dst, 0, floats * sizeof(float), s));
+}
+
 struct DecoderTrain {
     Engine e;
-    int B = 0, T = 0, M = 0, minT = 0;
-    TT visual, spk, outputs, post, stops, cdis;
+    Arena io;                                                       // staged copies of the caller's tensors (same addresses per shape)
+    int B = 0, T = 0, M = 0;
+    struct Handles { TT visual, spk, outputs, post, stops, cdis; int minT = 0; } h;
+    struct Slot : GraphSlot { Handles h; };
+    std::map<std::string, Slot> slots;
+    Slot* slot = nullptr;
+    GraphMode mode = RUN_EAGER;
+    bool use_graphs = true;
+    uint64_t bind_gen = 0;
+    cudaStream_t cs = nullptr;
     bool live = false;
+    bool want_logits = false;
+    struct Staged {
+        float *visual, *spk, *mels, *tf, *gumbel, *prenet, *attn, *lstm, *post[5];
+        float *out_mel, *out_post, *out_stop, *out_logits, *out_cdis;
+        float *g_mel, *g_post, *g_stop, *g_cdis;
+    } st{};
+
+    void drop_graphs() { for (auto& kv : slots) kv.second.release(); slots.clear(); slot = nullptr; }
+    void release() { drop_graphs(); e.vals.free_all(); e.grads.free_all(); io.free_all(); if (cs) cudaStreamDestroy(cs); cs = nullptr; }
 
     static TT assign(Engine& e, const TT& dst_view, const TT& src) {
         ew_fwd_kernel<EW_COPY><<<ew_blocks(src.numel()), 256, 0, e.s>>>(src.rows, src.cols, src.v, src.rs, nullptr, 0, 0.f, 1, dst_view.v, dst_view.rs);
         e.ck("assign");
-        cudaStream_t s = e.s; Engine* pe = &e;
+        Engine* pe = &e;
         e.tape.push_back([=]() {
             if (!src.g || !dst_view.g) return;
-            ew_bwd_kernel<EW_COPY><<<ew_blocks(src.numel()), 256, 0, s>>>(src.rows, src.cols, nullptr, 0, nullptr, 0, 0.f, dst_view.g, dst_view.rs, src.g, src.rs);
+            ew_bwd_kernel<EW_COPY><<<ew_blocks(src.numel()), 256, 0, pe->s>>>(src.rows, src.cols, nullptr, 0, nullptr, 0, 0.f, dst_view.g, dst_view.rs, src.g, src.rs);
             pe->ck("assign bwd");
         });
         return dst_view;
@@ -75,11 +105,75 @@ struct DecoderTrain {
         h_final = h; c_final = c;
     }
 
-    void forward(Context& ctx, std::map<std::string, Param>& params, const DecoderTrainIO& io, int B_, int T_, int M_, bool want_input_grads, cudaStream_t s) {
+    void forward(Context& ctx, std::map<std::string, Param>& params, uint64_t gen, const DecoderTrainIO& in, int B_, int T_, int M_, bool want_input_grads,
+                 cudaStream_t s) {
         B = B_; T = T_; M = M_;
         if (B <= 0 || T < 7 || T > 300 || M <= 0 || M > 300) throw L2sError(1, "decoder_train_fwd: need 7<=T<=300, 1<=M<=300");
-        e.begin(&ctx, s, &params);
         live = false;
+        if (gen != bind_gen) { drop_graphs(); bind_gen = gen; }     // parameter / gradient memory moved: the graphs point at the old one
+        want_logits = in.out_attn_logits != nullptr;
+        // ---- stage the caller's tensors ---------------------------------------------------------------------------------------
+        io.reset();
+        const size_t nBM = (size_t)B * M;
+        auto in_copy = [&](const float* src, size_t floats) { float* d = io.alloc(floats); stage_in(d, src, floats, s); return d; };
+        st.visual = in_copy(in.visual, (size_t)B * T * 1024);
+        st.spk = in_copy(in.spk, (size_t)B * 256);
+        st.mels = in_copy(in.mels, nBM * 80);
+        st.gumbel = in_copy(in.gumbel, (size_t)B * content_min_t(T) * 501);
+        st.prenet = in_copy(in.prenet_mask, nBM * 256);
+        st.attn = in_copy(in.attn_mask, nBM * T);
+        st.lstm = in_copy(in.lstm_mask, nBM * 512);
+        for (int i = 0; i < 5; ++i) st.post[i] = in_copy(in.post_mask[i], nBM * (i == 4 ? 80 : 512));
+        {
+            std::vector<float> tf(M);
+            for (int i = 0; i < M; ++i) tf[i] = in.tf_mask[i] ? 1.f : 0.f;
+            st.tf = io.alloc(M);
+            L2S_CUDA(cudaMemcpyAsync(st.tf, tf.data(), (size_t)M * sizeof(float), cudaMemcpyHostToDevice, s));     // pageable source: staged before the call returns
+        }
+        st.out_mel = io.alloc(nBM * 80); st.out_post = io.alloc(nBM * 80); st.out_stop = io.alloc(nBM);
+        st.out_logits = io.alloc(nBM * T); st.out_cdis = io.alloc((size_t)B * T * 501);
+        st.g_mel = io.alloc(nBM * 80); st.g_post = io.alloc(nBM * 80); st.g_stop = io.alloc(nBM); st.g_cdis = io.alloc((size_t)B * T * 501);
+        // ---- run: replay, capture + launch, or eager ------------------------------------------------------------------------------
+        const std::string key = std::to_string(B) + "," + std::to_string(T) + "," + std::to_string(M) + "," + (want_input_grads ? "g" : "-") +
+                                (want_logits ? "l" : "-") + (e.update_bn_running ? "r" : "-");
+        slot = &slots[key];
+        if (use_graphs && slot->fwd && slot->bwd) {
+            mode = RUN_REPLAY;
+            h = slot->h;
+            L2S_CUDA(cudaGraphLaunch(slot->fwd, s));
+            ctx.launches += slot->fwd_launches;
+        } else if (use_graphs && slot->seen >= 1) {
+            mode = RUN_CAPTURED;
+            slot->drop_graphs();
+            const int64_t n0 = ctx.launches;
+            e.capturing = true;
+            try { slot->fwd = capture_graph(capture_stream(cs), [&]() { body(ctx, params, want_input_grads, cs); }); }
+            catch (...) { e.capturing = false; throw; }
+            e.capturing = false;
+            slot->fwd_launches = ctx.launches - n0;
+            slot->h = h;
+            L2S_CUDA(cudaGraphLaunch(slot->fwd, s));
+        } else {
+            mode = RUN_EAGER;
+            body(ctx, params, want_input_grads, s);
+        }
+        ++slot->seen;
+        // ---- caller-visible outputs ------------------------------------------------------------------------------------------------
+        auto out_copy = [&](float* dst, const float* src, size_t floats) { if (dst) L2S_CUDA(cudaMemcpyAsync(dst, src, floats * sizeof(float), cudaMemcpyDeviceToDevice, s)); };
+        out_copy(in.out_mel, st.out_mel, nBM * 80);
+        out_copy(in.out_post, st.out_post, nBM * 80);
+        out_copy(in.out_stop, st.out_stop, nBM);
+        out_copy(in.out_attn_logits, st.out_logits, nBM * T);
+        out_copy(in.out_content_dis, st.out_cdis, (size_t)B * h.minT * 501);
+        live = true;
+    }
+
+    // The launch sequence of one forward pass; reads and writes staged memory only (so it can be captured).
+    void body(Context& ctx, std::map<std::string, Param>& params, bool want_input_grads, cudaStream_t s) {
+        const Staged& io = st;
+        TT &visual = h.visual, &spk = h.spk, &outputs = h.outputs, &post = h.post, &stops = h.stops, &cdis = h.cdis;
+        int& minT = h.minT;
+        e.begin(&ctx, s, &params);
         const std::string P = "decoder.";
         visual = e.wrap(io.visual, B * T, 1024, want_input_grads);
         spk = e.wrap(io.spk, B, 256, want_input_grads);
@@ -147,15 +241,15 @@ struct DecoderTrain {
         TT Wih0 = e.param(R + "weight_ih_l0", 2048, 512), bih0 = e.param(R + "bias_ih_l0", 1, 2048), Whh0 = e.param(R + "weight_hh_l0", 2048, 512), bhh0 = e.param(R + "bias_hh_l0", 1, 2048);
         TT Wih1 = e.param(R + "weight_ih_l1", 2048, 512), bih1 = e.param(R + "bias_ih_l1", 1, 2048), Whh1 = e.param(R + "weight_hh_l1", 2048, 512), bhh1 = e.param(R + "bias_hh_l1", 1, 2048);
         for (int i = 0; i < M; ++i) {
-            if (io.tf_mask[i]) ys = i == 0 ? bos : mel_rows.rowslice(i - 1, B, M);              // teacher_input[:, i] (355-357)
+            if (i > 0) ys = e.select(io.tf + i, mel_rows.rowslice(i - 1, B, M), ys);            // teacher_input[:, i] or the previous output (355-357)
             TT p1 = e.psine(lin(ys, P + "prenet.0.linear_layer", 256), p1w);
-            TT p1d = e.dropout(p1, io.prenet_mask + (size_t)i * B * 256, 256, 0.2f);
+            TT p1d = e.dropout(p1, io.prenet + (size_t)i * B * 256, 256, 0.2f);
             TT p2 = e.psine(lin(p1d, P + "prenet.3.linear_layer", 256), p4w);
             TT q = e.add_const(e.psine(lin(e.concat_cols({h0, h1}), P + "Q.0.linear_layer", 512), Wq_w), pos + (size_t)i * 512, 0);
-            TT a = e.dropout(e.attn_scores(e.scale_param(q, temp), Kmem, T), io.attn_mask + (size_t)i * B * T, T, 0.1f);
-            if (io.out_attn_logits) {
+            TT a = e.dropout(e.attn_scores(e.scale_param(q, temp), Kmem, T), io.attn + (size_t)i * B * T, T, 0.1f);
+            if (want_logits) {
                 // rows b of a -> out[b][i][:]
-                ew_fwd_kernel<EW_COPY><<<ew_blocks(a.numel()), 256, 0, s>>>(B, T, a.v, a.rs, nullptr, 0, 0.f, 1, io.out_attn_logits + (size_t)i * T, M * T);
+                ew_fwd_kernel<EW_COPY><<<ew_blocks(a.numel()), 256, 0, s>>>(B, T, a.v, a.rs, nullptr, 0, 0.f, 1, io.out_logits + (size_t)i * T, M * T);
                 e.ck("attn logits out");
             }
             TT o = lin(e.attn_context(e.softmax(a), Vmem, T), P + "attention_proj.linear_layer", 256);
@@ -165,7 +259,7 @@ struct DecoderTrain {
             TT x = e.concat_cols({co, y});
             TT h0n, c0n, h1n, c1n;
             e.lstm_cell(e.add(e.linear(x, Wih0, &bih0), e.linear(h0, Whh0, &bhh0)), c0, h0n, c0n);
-            TT h0d = e.dropout(h0n, io.lstm_mask + (size_t)i * B * 512, 512, 0.1f);            // nn.LSTM(dropout=0.1): layer 1's input only
+            TT h0d = e.dropout(h0n, io.lstm + (size_t)i * B * 512, 512, 0.1f);            // nn.LSTM(dropout=0.1): layer 1's input only
             e.lstm_cell(e.add(e.linear(h0d, Wih1, &bih1), e.linear(h1, Whh1, &bhh1)), c1, h1n, c1n);
             h0 = h0n; c0 = c0n; h1 = h1n; c1 = c1n;
             ys = lin(h1, P + "fc_out.linear_layer", 80);
@@ -186,39 +280,58 @@ struct DecoderTrain {
                     if (i != 0) y = e.add(y, x);
                 }
                 TT mrows = e.make(B * M, cout, false);              // keep mask [B,C,M] -> rows (b, m) x C
-                bcl_to_rows_tr_kernel<<<ew_blocks((size_t)B * cout * M), 256, 0, s>>>(B, cout, M, io.post_mask[i], mrows.v, cout);
+                bcl_to_rows_tr_kernel<<<ew_blocks((size_t)B * cout * M), 256, 0, s>>>(B, cout, M, io.post[i], mrows.v, cout);
                 e.ck("post mask rows");
                 x = e.dropout(y, mrows.v, cout, 0.5f);
             }
             post = e.add(x, outputs);
         }
-        // ---- caller-visible outputs ------------------------------------------------------------------------------------------
-        if (io.out_mel) { rows_to_bcl_tr_kernel<<<ew_blocks((size_t)B * 80 * M), 256, 0, s>>>(B, 80, M, outputs.v, outputs.rs, io.out_mel); e.ck("out mel"); }
-        if (io.out_post) { rows_to_bcl_tr_kernel<<<ew_blocks((size_t)B * 80 * M), 256, 0, s>>>(B, 80, M, post.v, post.rs, io.out_post); e.ck("out post"); }
-        if (io.out_stop) L2S_CUDA(cudaMemcpyAsync(io.out_stop, stops.v, (size_t)B * M * sizeof(float), cudaMemcpyDeviceToDevice, s));
-        if (io.out_content_dis) L2S_CUDA(cudaMemcpyAsync(io.out_content_dis, cdis.v, (size_t)B * minT * 501 * sizeof(float), cudaMemcpyDeviceToDevice, s));
-        live = true;
+        // ---- outputs in the caller's layouts (staged) ------------------------------------------------------------------------------
+        rows_to_bcl_tr_kernel<<<ew_blocks((size_t)B * 80 * M), 256, 0, s>>>(B, 80, M, outputs.v, outputs.rs, io.out_mel); e.ck("out mel");
+        rows_to_bcl_tr_kernel<<<ew_blocks((size_t)B * 80 * M), 256, 0, s>>>(B, 80, M, post.v, post.rs, io.out_post); e.ck("out post");
+        L2S_CUDA(cudaMemcpyAsync(io.out_stop, stops.v, (size_t)B * M * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        L2S_CUDA(cudaMemcpyAsync(io.out_cdis, cdis.v, (size_t)B * minT * 501 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
-
-    // Gradients of the scalar objective w.r.t. the four outputs the loss reads (any may be null) -> parameter gradients
-    // (accumulated into the bound gradient memory) and, optionally, the gradients of the inputs.
-    void backward(const float* g_mel, const float* g_post, const float* g_stop, const float* g_cdis, float* g_visual, float* g_spk, cudaStream_t s) {
-        if (!live) throw L2sError(1, "decoder_train_bwd: no forward pass to differentiate (call l2s_decoder_train_fwd first)");
+    void backward_body(cudaStream_t s) {
         e.s = s;
         e.begin_backward();
-        if (g_mel) { bcl_to_rows_tr_kernel<<<ew_blocks((size_t)B * 80 * M), 256, 0, s>>>(B, 80, M, g_mel, outputs.g, 80); e.ck("g mel"); }
-        if (g_post) { bcl_to_rows_tr_kernel<<<ew_blocks((size_t)B * 80 * M), 256, 0, s>>>(B, 80, M, g_post, post.g, 80); e.ck("g post"); }
-        if (g_stop) L2S_CUDA(cudaMemcpyAsync(stops.g, g_stop, (size_t)B * M * sizeof(float), cudaMemcpyDeviceToDevice, s));
-        if (g_cdis) L2S_CUDA(cudaMemcpyAsync(cdis.g, g_cdis, (size_t)B * minT * 501 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        bcl_to_rows_tr_kernel<<<ew_blocks((size_t)B * 80 * M), 256, 0, s>>>(B, 80, M, st.g_mel, h.outputs.g, 80); e.ck("g mel");
+        bcl_to_rows_tr_kernel<<<ew_blocks((size_t)B * 80 * M), 256, 0, s>>>(B, 80, M, st.g_post, h.post.g, 80); e.ck("g post");
+        L2S_CUDA(cudaMemcpyAsync(h.stops.g, st.g_stop, (size_t)B * M * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        L2S_CUDA(cudaMemcpyAsync(h.cdis.g, st.g_cdis, (size_t)B * h.minT * 501 * sizeof(float), cudaMemcpyDeviceToDevice, s));
         e.backward();
-        if (g_visual) {
-            if (!visual.g) throw L2sError(1, "decoder_train_bwd: input gradients were not requested in the forward call");
-            L2S_CUDA(cudaMemcpyAsync(g_visual, visual.g, (size_t)B * T * 1024 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+
+    // Gradients of the scalar objective w.r.t. the four outputs the loss reads (any may be null = zero) -> parameter gradients
+    // (accumulated into the bound gradient memory) and, optionally, the gradients of the inputs.
+    void backward(Context& ctx, const float* g_mel, const float* g_post, const float* g_stop, const float* g_cdis, float* g_visual, float* g_spk, cudaStream_t s) {
+        if (!live) throw L2sError(1, "decoder_train_bwd: no forward pass to differentiate (call l2s_decoder_train_fwd first)");
+        if ((g_visual || g_spk) && !h.visual.g) throw L2sError(1, "decoder_train_bwd: input gradients were not requested in the forward call");
+        const size_t nBM = (size_t)B * M;
+        stage_in(st.g_mel, g_mel, nBM * 80, s);
+        stage_in(st.g_post, g_post, nBM * 80, s);
+        stage_in(st.g_stop, g_stop, nBM, s);
+        stage_in(st.g_cdis, g_cdis, (size_t)B * h.minT * 501, s);
+        if (mode == RUN_REPLAY) {
+            L2S_CUDA(cudaGraphLaunch(slot->bwd, s));
+            ctx.launches += slot->bwd_launches;
+        } else if (mode == RUN_CAPTURED && slot->table_bytes) {
+            slot->tables.reserve(slot->table_bytes);
+            slot->tables.used = 0;
+            e.tables = &slot->tables;
+            const int64_t n0 = ctx.launches;
+            e.capturing = true;
+            try { slot->bwd = capture_graph(cs, [&]() { backward_body(cs); }); }
+            catch (...) { e.capturing = false; throw; }
+            e.capturing = false;
+            slot->bwd_launches = ctx.launches - n0;
+            L2S_CUDA(cudaGraphLaunch(slot->bwd, s));
+        } else {                                                    // eager (also: a captured forward whose table size is not known yet)
+            backward_body(s);
+            slot->table_bytes = e.table_bytes;
         }
-        if (g_spk) {
-            if (!spk.g) throw L2sError(1, "decoder_train_bwd: input gradients were not requested in the forward call");
-            L2S_CUDA(cudaMemcpyAsync(g_spk, spk.g, (size_t)B * 256 * sizeof(float), cudaMemcpyDeviceToDevice, s));
-        }
+        if (g_visual) L2S_CUDA(cudaMemcpyAsync(g_visual, h.visual.g, (size_t)B * T * 1024 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        if (g_spk) L2S_CUDA(cudaMemcpyAsync(g_spk, h.spk.g, (size_t)B * 256 * sizeof(float), cudaMemcpyDeviceToDevice, s));
         live = false;
     }
 };
@@ -226,19 +339,69 @@ struct DecoderTrain {
 // ---- VideoExtractor.forward in train mode (video.py:76-87; shufflenetv2.py:42-104; model.py:26 dropout) ---------------
 struct VideoTrain {
     Engine e;
-    int B = 0, T = 0;
+    Arena io;
+    int B = 0, T = 0, H = 0, W = 0;
     TT feat;
+    struct Slot : GraphSlot { TT feat; };
+    std::map<std::string, Slot> slots;
+    Slot* slot = nullptr;
+    GraphMode mode = RUN_EAGER;
+    bool use_graphs = true;
+    uint64_t bind_gen = 0;
+    cudaStream_t cs = nullptr;
     bool live = false;
+    float *st_video = nullptr, *st_mask = nullptr, *st_out = nullptr, *st_g = nullptr;
+
+    void drop_graphs() { for (auto& kv : slots) kv.second.release(); slots.clear(); slot = nullptr; }
+    void release() { drop_graphs(); e.vals.free_all(); e.grads.free_all(); io.free_all(); if (cs) cudaStreamDestroy(cs); cs = nullptr; }
 
     TT pw(const TT& x, const std::string& name, int cout) {        // 1x1 Conv2d, bias=False
         return e.linear(x, e.param(name + ".weight", cout, x.cols), nullptr);
     }
-    void forward(Context& ctx, std::map<std::string, Param>& params, const float* video, const float* drop_mask, int B_, int T_, int H, int W,
+    void forward(Context& ctx, std::map<std::string, Param>& params, uint64_t gen, const float* video, const float* drop_mask, int B_, int T_, int H_, int W_,
                  float* out_feat, cudaStream_t s) {
-        B = B_; T = T_;
+        B = B_; T = T_; H = H_; W = W_;
         if (B <= 0 || T <= 0 || (H & 3) || (W & 3)) throw L2sError(1, "video_train_fwd: bad shape");
-        e.begin(&ctx, s, &params);
         live = false;
+        if (gen != bind_gen) { drop_graphs(); bind_gen = gen; }
+        const size_t N = (size_t)B * T;
+        io.reset();
+        st_video = io.alloc(N * 3 * H * W); stage_in(st_video, video, N * 3 * H * W, s);
+        st_mask = io.alloc(N * 768); if (drop_mask) stage_in(st_mask, drop_mask, N * 768, s);
+        st_out = io.alloc(N * 768); st_g = io.alloc(N * 768);
+        const bool masked = drop_mask != nullptr;
+        const std::string key = std::to_string(B) + "," + std::to_string(T) + "," + std::to_string(H) + "," + std::to_string(W) + (masked ? "m" : "-") +
+                                (e.update_bn_running ? "r" : "-");
+        slot = &slots[key];
+        if (use_graphs && slot->fwd && slot->bwd) {
+            mode = RUN_REPLAY;
+            feat = slot->feat;
+            L2S_CUDA(cudaGraphLaunch(slot->fwd, s));
+            ctx.launches += slot->fwd_launches;
+        } else if (use_graphs && slot->seen >= 1) {
+            mode = RUN_CAPTURED;
+            slot->drop_graphs();
+            const int64_t n0 = ctx.launches;
+            e.capturing = true;
+            try { slot->fwd = capture_graph(capture_stream(cs), [&]() { body(ctx, params, masked, cs); }); }
+            catch (...) { e.capturing = false; throw; }
+            e.capturing = false;
+            slot->fwd_launches = ctx.launches - n0;
+            slot->feat = feat;
+            L2S_CUDA(cudaGraphLaunch(slot->fwd, s));
+        } else {
+            mode = RUN_EAGER;
+            body(ctx, params, masked, s);
+        }
+        ++slot->seen;
+        L2S_CUDA(cudaMemcpyAsync(out_feat, st_out, N * 768 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        live = true;
+    }
+    void body(Context& ctx, std::map<std::string, Param>& params, bool masked, cudaStream_t s) {
+        const float* video = st_video;
+        const float* drop_mask = masked ? st_mask : nullptr;
+        float* out_feat = st_out;
+        e.begin(&ctx, s, &params);
         const std::string P = "encoder.";
         const int N = B * T;
         TT x = e.stem_conv(video, B, T, H, W, e.param(P + "frontend3D.0.weight", 24, 735));
@@ -276,14 +439,30 @@ struct VideoTrain {
         if (drop_mask) x = e.dropout(x, drop_mask, 768, 0.1f);      // F.dropout(video_features, 0.1, training), model.py:26
         feat = x;
         L2S_CUDA(cudaMemcpyAsync(out_feat, x.v, (size_t)N * 768 * sizeof(float), cudaMemcpyDeviceToDevice, s));
-        live = true;
     }
-    void backward(const float* g_feat, cudaStream_t s) {
-        if (!live) throw L2sError(1, "video_train_bwd: no forward pass to differentiate (call l2s_video_train_fwd first)");
+    void backward_body(cudaStream_t s) {
         e.s = s;
         e.begin_backward();
-        L2S_CUDA(cudaMemcpyAsync(feat.g, g_feat, (size_t)B * T * 768 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        L2S_CUDA(cudaMemcpyAsync(feat.g, st_g, (size_t)B * T * 768 * sizeof(float), cudaMemcpyDeviceToDevice, s));
         e.backward();
+    }
+    void backward(Context& ctx, const float* g_feat, cudaStream_t s) {
+        if (!live) throw L2sError(1, "video_train_bwd: no forward pass to differentiate (call l2s_video_train_fwd first)");
+        stage_in(st_g, g_feat, (size_t)B * T * 768, s);
+        if (mode == RUN_REPLAY) {
+            L2S_CUDA(cudaGraphLaunch(slot->bwd, s));
+            ctx.launches += slot->bwd_launches;
+        } else if (mode == RUN_CAPTURED) {                          // no per-step layers in the frontend: the backward uploads no pointer tables
+            slot->tables.used = 0;
+            e.tables = &slot->tables;
+            const int64_t n0 = ctx.launches;
+            e.capturing = true;
+            try { slot->bwd = capture_graph(cs, [&]() { backward_body(cs); }); }
+            catch (...) { e.capturing = false; throw; }
+            e.capturing = false;
+            slot->bwd_launches = ctx.launches - n0;
+            L2S_CUDA(cudaGraphLaunch(slot->bwd, s));
+        } else backward_body(s);
         live = false;
     }
 };

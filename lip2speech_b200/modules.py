@@ -62,14 +62,40 @@ class TrainNoise:
         LSTM dropout, then the five postnet dropouts) from torch's global generators."""
         bern = lambda shape, keep: torch.empty(shape, device=device).bernoulli_(keep)
         gumbel = -torch.empty(B * spec.content_min_t(T), spec.VOCAB, device=device).exponential_().log()
-        tf, prenet, attn, lstm, consumed = [], [], [], [], 0
-        for _ in range(M):
-            use = bool(torch.rand(1) > tf_ratio) and consumed < int(tf_ratio * M)     # decoder.py:355-357
+        coins = (torch.rand(M) > tf_ratio).tolist()                                   # decoder.py:355-357 (CPU generator, like np/torch.rand(1) there)
+        tf, consumed = [], 0
+        for c in coins:
+            use = c and consumed < int(tf_ratio * M)
             consumed += int(use)
             tf.append(use)
-            prenet.append(bern((B, 256), 0.8)); attn.append(bern((B, T), 0.9)); lstm.append(bern((B, 512), 0.9))
+        prenet, attn, lstm = bern((M, B, 256), 0.8), bern((M, B, T), 0.9), bern((M, B, 512), 0.9)
         post = [bern((B, c, M), 0.5) for c in (512, 512, 512, 512, 80)]
-        return TrainNoise(torch.tensor(tf, dtype=torch.bool), gumbel, torch.stack(prenet), torch.stack(attn), torch.stack(lstm), post)
+        return TrainNoise(torch.tensor(tf, dtype=torch.bool), gumbel, prenet, attn, lstm, post)
+
+
+def _bind_params(be, tag, keys, params):
+    """Bind the parameters and ONE persistent flat gradient buffer per (backend, module kind): the addresses the library sees
+    stay the same from step to step, which is what lets it replay its captured launch graphs.  Re-binds only when something moved."""
+    sizes = [p.numel() for p in params]
+    offs, total = [], 0
+    for n in sizes:
+        offs.append(total); total += (n + 3) // 4 * 4
+    cache = be.__dict__.setdefault("_train_grads", {})
+    sig = (tuple(keys), tuple(p.data_ptr() for p in params))
+    hit = cache.get(tag)
+    if hit is None or hit[0] != sig:
+        scratch = torch.zeros(total, device=params[0].device)
+        for k, p, o, n in zip(keys, params, offs, sizes):
+            be.train_bind(k, p.detach(), scratch[o:o + n])
+        hit = cache[tag] = (sig, scratch)
+    return hit[1], offs, sizes
+
+
+def _grad_views(scratch, offs, sizes, params):
+    """Fresh storage for what autograd receives (AccumulateGrad may keep the tensor as p.grad; the persistent buffer is rewritten
+    by the next backward)."""
+    out = scratch.clone()
+    return [out[o:o + n].view_as(p) for o, n, p in zip(offs, sizes, params)]
 
 
 class _DecoderTrainFn(torch.autograd.Function):
@@ -78,16 +104,9 @@ class _DecoderTrainFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, be, noise, keys, visual, spk, mels, *params):
-        sizes = [p.numel() for p in params]
-        offs, total = [], 0
-        for n in sizes:
-            offs.append(total); total += (n + 3) // 4 * 4
-        scratch = torch.zeros(total, device=visual.device)
-        views = [scratch[o:o + n].view_as(p) for o, n, p in zip(offs, sizes, params)]
-        for k, p, g in zip(keys, params, views):
-            be.train_bind(k, p.detach(), g)
+        scratch, offs, sizes = _bind_params(be, "decoder", keys, params)
         outs = be.decoder_train_fwd(visual, spk, mels, noise, want_input_grads=True)
-        ctx.be, ctx.views, ctx.scratch, ctx.BT = be, views, scratch, (visual.shape[0], visual.shape[1])
+        ctx.be, ctx.scratch, ctx.layout, ctx.params, ctx.BT = be, scratch, (offs, sizes), params, (visual.shape[0], visual.shape[1])
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(outs[3])
         return outs
@@ -96,7 +115,7 @@ class _DecoderTrainFn(torch.autograd.Function):
     def backward(ctx, g_mel, g_post, g_stop, g_attn, g_dis):
         ctx.scratch.zero_()
         g_visual, g_spk = ctx.be.decoder_train_bwd(g_mel, g_post, g_stop, g_dis, *ctx.BT)
-        return (None, None, None, g_visual, g_spk, None, *ctx.views)
+        return (None, None, None, g_visual, g_spk, None, *_grad_views(ctx.scratch, *ctx.layout, ctx.params))
 
 
 class _VideoTrainFn(torch.autograd.Function):
@@ -104,30 +123,29 @@ class _VideoTrainFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, be, drop_mask, keys, video, *params):
-        sizes = [p.numel() for p in params]
-        offs, total = [], 0
-        for n in sizes:
-            offs.append(total); total += (n + 3) // 4 * 4
-        scratch = torch.zeros(total, device=video.device)
-        views = [scratch[o:o + n].view_as(p) for o, n, p in zip(offs, sizes, params)]
-        for k, p, g in zip(keys, params, views):
-            be.train_bind(k, p.detach(), g)
-        ctx.be, ctx.views, ctx.scratch = be, views, scratch
+        scratch, offs, sizes = _bind_params(be, "encoder", keys, params)
+        ctx.be, ctx.scratch, ctx.layout, ctx.params = be, scratch, (offs, sizes), params
         return be.video_train_fwd(video, drop_mask)
 
     @staticmethod
     def backward(ctx, g_feat):
         ctx.scratch.zero_()
         ctx.be.video_train_bwd(g_feat)
-        return (None, None, None, None, *ctx.views)
+        return (None, None, None, None, *_grad_views(ctx.scratch, *ctx.layout, ctx.params))
 
 
 def _bind_buffers(be, module, prefix):
-    for name, buf in module.named_buffers():
-        if buf.is_floating_point():
-            be.train_bind(prefix + name, buf, None)          # pos_table; BatchNorm running statistics (updated in place)
-        elif name.endswith("num_batches_tracked"):
-            buf += 1                                          # nn.BatchNorm*d bookkeeping in train()
+    named = list(module.named_buffers())
+    floats = [(prefix + n, b) for n, b in named if b.is_floating_point()]
+    cache = be.__dict__.setdefault("_train_buffers", {})
+    sig = tuple((k, b.data_ptr()) for k, b in floats)
+    if cache.get(prefix) != sig:
+        for k, b in floats:
+            be.train_bind(k, b, None)                        # pos_table; BatchNorm running statistics (updated in place)
+        cache[prefix] = sig
+    counters = [b for n, b in named if n.endswith("num_batches_tracked")]
+    if counters:
+        torch._foreach_add_(counters, 1)                     # nn.BatchNorm*d bookkeeping in train()
 
 
 def video_forward_train(module, prefix, x, drop_mask=None):

@@ -122,6 +122,88 @@ def test_train_backward_is_deterministic_and_accumulates(be):
         be.decoder_train_bwd(*g_out, B, T)           # the tape was consumed
 
 
+def test_graph_replay_is_bit_identical_to_eager(be):
+    """The train-mode forward / backward are captured as CUDA graphs on the second call with a key and replayed afterwards
+    (l2s_train_set_graphs).  Eager, captured and replayed passes must agree bit for bit — also when the teacher-forcing coins
+    and every other noise tensor change between replays (the coins are read on the device, not baked into the graph), and when
+    the caller's input tensors live at new addresses."""
+    from oracle import train_oracle as TO
+    B, T, M = 2, 29, 6
+    w = _decoder_weights(1234, True)
+    dev, grads = _bind(be, w)
+    g_out = [torch.randn(B, 80, M, device="cuda"), torch.randn(B, 80, M, device="cuda"), torch.randn(B, M, 1, device="cuda"), None]
+
+    def one_pass(seed):
+        visual, face = synth.visual_features(B, T, seed=seed)
+        mels = synth.mel_like(B, M, seed=seed) * 2 - 5
+        noise = TO.reference_noise(B, T, M, 0.5, with_video=False, generator=torch.Generator().manual_seed(seed)).to("cuda")
+        for v in grads.values():
+            if v is not None:
+                v.zero_()
+        n0 = be.launch_count()
+        out = be.decoder_train_fwd(visual.cuda(), face[:, 0].cuda(), mels.cuda(), noise)
+        gv, gs = be.decoder_train_bwd(*g_out, B, T)
+        torch.cuda.synchronize()
+        return ([o.clone() for o in out], gv.clone(), gs.clone(), {k: v.clone() for k, v in grads.items() if v is not None}, be.launch_count() - n0,
+                noise.tf_mask.clone())
+
+    def same(a, b):
+        assert all(torch.equal(x, y) for x, y in zip(a[0], b[0])), "outputs"
+        assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]), "input gradients"
+        for k in a[3]:
+            assert torch.equal(a[3][k], b[3][k]), k
+        assert a[4] == b[4], "launch accounting"
+
+    be.train_set_graphs(False)
+    eager = {seed: one_pass(seed) for seed in (5, 6, 7)}
+    assert not all(torch.equal(eager[5][5], eager[s][5]) for s in (6, 7)), "the seeds must draw different teacher-forcing coins"
+    be.train_set_graphs(True)
+    try:
+        same(one_pass(5), eager[5])          # captured + launched (the eager passes above already showed the key once)
+        same(one_pass(5), eager[5])          # replayed
+        same(one_pass(6), eager[6])          # replay, new inputs / noise / coins
+        same(one_pass(7), eager[7])
+        same(one_pass(5), eager[5])
+    finally:
+        be.train_set_graphs(True)
+
+
+def test_video_graph_replay_is_bit_identical_to_eager(be):
+    B, T = 2, 5
+    w = {k: v for k, v in spec.seeded_state_dict(spec.encoder_spec("encoder."), 1234).items()}
+    dev, grads = _bind(be, w)
+
+    def one_pass(seed):
+        video = synth.video(B, T, seed=seed).cuda()
+        drop = torch.empty(B, T, 768, device="cuda").bernoulli_(0.9, generator=torch.Generator("cuda").manual_seed(seed))
+        g_feat = torch.randn(B, T, 768, device="cuda", generator=torch.Generator("cuda").manual_seed(seed + 100))
+        for k, v in w.items():               # the forward updates the running statistics in place: restore them
+            if spec.is_buffer(k) and v.is_floating_point():
+                dev[k].copy_(v)
+        for v in grads.values():
+            if v is not None:
+                v.zero_()
+        feat = be.video_train_fwd(video, drop)
+        be.video_train_bwd(g_feat)
+        torch.cuda.synchronize()
+        return feat.clone(), {k: v.clone() for k, v in grads.items() if v is not None}, {k: dev[k].clone() for k in dev if spec.is_buffer(k)}
+
+    def same(a, b):
+        assert torch.equal(a[0], b[0])
+        for k in a[1]:
+            assert torch.equal(a[1][k], b[1][k]), k
+        for k in a[2]:
+            assert torch.equal(a[2][k], b[2][k]), k
+
+    be.train_set_graphs(False)
+    eager = {seed: one_pass(seed) for seed in (1, 2)}
+    be.train_set_graphs(True)
+    same(one_pass(1), eager[1])
+    same(one_pass(1), eager[1])
+    same(one_pass(2), eager[2])
+    same(one_pass(1), eager[1])
+
+
 def _cast_sd(w, dt):
     return {k: (v.clone().to(dt).requires_grad_(True) if v.is_floating_point() and not spec.is_buffer(k)
                 else (v.clone().to(dt) if v.is_floating_point() else v.clone())) for k, v in w.items()}
