@@ -145,6 +145,150 @@ __global__ void __launch_bounds__(256) skinny_nt_kernel(int M, int N, int K, con
             }
         }
 }
+// Sum V = 32 per-lane partial values across the 32 lanes of a warp with 31 shuffles (instead of 32 x 5): each round swaps half
+// of the remaining values with the partner lane, so that lane l ends up owning the complete sum of value #l.
+#define L2S_FOLD_LANES(v, off, cnt)                                                   \
+    {                                                                                 \
+        const bool up_ = (lane & (off)) != 0;                                         \
+        _Pragma("unroll") for (int i_ = 0; i_ < (cnt); ++i_) {                        \
+            const float send_ = up_ ? v[i_] : v[i_ + (cnt)];                          \
+            const float keep_ = up_ ? v[i_ + (cnt)] : v[i_];                          \
+            v[i_] = keep_ + __shfl_xor_sync(0xffffffffu, send_, (off));               \
+        }                                                                             \
+    }
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
+    L2S_FOLD_LANES(v, 16, 16) L2S_FOLD_LANES(v, 8, 8) L2S_FOLD_LANES(v, 4, 4) L2S_FOLD_LANES(v, 2, 2) L2S_FOLD_LANES(v, 1, 1)
+    return v[0];
+}
+
+// Few-row GEMM, second form: the CTA first stages ALL of A (M x K, M <= MT) in shared memory, each warp owns NW weight rows and
+// issues every 16-byte weight load of a 512-wide k chunk before it touches them (4 MB of LSTM weights are in flight at once
+// instead of two loads per warp), NW * MT = 32 accumulators per lane are reduced with warp_transpose_sum32.
+template <int NW, int MT>
+__global__ void __launch_bounds__(256) skinny_nt_smem_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
+                                                             const float* __restrict__ bias, float* __restrict__ C, int ldc) {
+    static_assert(NW * MT == 32, "one output per lane");
+    extern __shared__ float4 xs4[];                                   // [MT][K/4], rows >= M are zero
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = (blockIdx.x * 8 + warp) * NW;
+    const int K4 = K >> 2;
+    float4 wv[NW][4];
+    auto load_w = [&](int kc) {
+#pragma unroll
+        for (int n = 0; n < NW; ++n)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = kc + 128 * j + 4 * lane;
+                wv[n][j] = (n0 + n < N && k < K) ? *reinterpret_cast<const float4*>(W + (size_t)(n0 + n) * ldw + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+    };
+    load_w(0);
+    for (int i = threadIdx.x; i < MT * K4; i += 256) {
+        const int m = i / K4, q = i - m * K4;
+        xs4[i] = m < M ? *reinterpret_cast<const float4*>(A + (size_t)m * lda + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    float acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    for (int kc = 0; kc < K; kc += 512) {
+        if (kc) load_w(kc);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int q = (kc >> 2) + 32 * j + lane;
+            if (q < K4) {
+#pragma unroll
+                for (int m = 0; m < MT; ++m) {
+                    const float4 a = xs4[m * K4 + q];
+#pragma unroll
+                    for (int n = 0; n < NW; ++n) {
+                        float t = acc[n * MT + m];
+                        t = fmaf(a.x, wv[n][j].x, t); t = fmaf(a.y, wv[n][j].y, t); t = fmaf(a.z, wv[n][j].z, t); t = fmaf(a.w, wv[n][j].w, t);
+                        acc[n * MT + m] = t;
+                    }
+                }
+            }
+        }
+    }
+    const float v = warp_transpose_sum32(acc, lane);                  // lane = n * MT + m
+    const int n = n0 + lane / MT, m = lane % MT;
+    if (n < N && m < M) C[(size_t)m * ldc + n] = v + (bias ? bias[n] : 0.f);
+}
+
+// dx[m][k] += sum_n dy[m][n] W[n][k] for M <= MT in ONE launch: grid (k tiles of 256, n slices of 32).  A warp covers 32 k
+// (8 lanes x 4) x 4 interleaved n; every lane issues its 8 weight loads up front; the 4 n-lanes are folded with shuffles; the
+// slice partials go to `part`, and the LAST CTA to finish a k tile (ticket counter, reset for the next launch) adds the slices
+// in index order — deterministic, and without a second launch.
+template <int MT>
+__global__ void __launch_bounds__(256) skinny_nn_fused_kernel(int M, int N, int K, const float* __restrict__ dY, int ldy, const float* __restrict__ W, int ldw,
+                                                              float* __restrict__ part, unsigned* __restrict__ counters, float* __restrict__ dX, int ldx) {
+    constexpr int NS = 32;
+    __shared__ __align__(16) float dys[NS][MT];
+    __shared__ int last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kq = lane & 7, ny = lane >> 3;
+    const int k = blockIdx.x * 256 + warp * 32 + kq * 4;
+    const int n0 = blockIdx.y * NS;
+    float4 wv[NS / 4];
+#pragma unroll
+    for (int j = 0; j < NS / 4; ++j) {
+        const int n = n0 + ny + 4 * j;
+        wv[j] = (n < N && k < K) ? *reinterpret_cast<const float4*>(W + (size_t)n * ldw + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int i = threadIdx.x; i < NS * MT; i += 256) {
+        const int m = i / NS, n = i % NS;
+        dys[n][m] = (m < M && n0 + n < N) ? dY[(size_t)m * ldy + n0 + n] : 0.f;
+    }
+    __syncthreads();
+    float acc[MT * 4];
+#pragma unroll
+    for (int i = 0; i < MT * 4; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NS / 4; ++j) {
+        const float4* d4 = reinterpret_cast<const float4*>(dys[ny + 4 * j]);
+#pragma unroll
+        for (int mq = 0; mq < MT / 4; ++mq) {
+            const float4 d = d4[mq];
+            const float dm[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float* a = acc + (mq * 4 + u) * 4;
+                a[0] = fmaf(dm[u], wv[j].x, a[0]); a[1] = fmaf(dm[u], wv[j].y, a[1]); a[2] = fmaf(dm[u], wv[j].z, a[2]); a[3] = fmaf(dm[u], wv[j].w, a[3]);
+            }
+        }
+    }
+    // fold the 4 n-lanes (lane bits 4 and 3): each round hands half of the remaining values to the partner
+    L2S_FOLD_LANES(acc, 16, MT * 2) L2S_FOLD_LANES(acc, 8, MT)
+    // this lane now owns rows m = (MT/2) * bit4 + (MT/4) * bit3 + [0, MT/4) of its four k
+    const int mbase = (MT / 2) * ((lane >> 4) & 1) + (MT / 4) * ((lane >> 3) & 1);
+    if (k < K)
+#pragma unroll
+        for (int u = 0; u < MT / 4; ++u) {
+            const int m = mbase + u;
+            if (m < M) *reinterpret_cast<float4*>(part + ((size_t)blockIdx.y * M + m) * K + k) = make_float4(acc[u * 4], acc[u * 4 + 1], acc[u * 4 + 2], acc[u * 4 + 3]);
+        }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(counters + blockIdx.x, 1u) == gridDim.y - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    for (int i = threadIdx.x; i < M * 64; i += 256) {
+        const int m = i >> 6, kk = blockIdx.x * 256 + (i & 63) * 4;
+        if (kk >= K) continue;
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int z = 0; z < (int)gridDim.y; ++z) {
+            const float4 p4 = __ldcg(reinterpret_cast<const float4*>(part + ((size_t)z * M + m) * K + kk));
+            sum.x += p4.x; sum.y += p4.y; sum.z += p4.z; sum.w += p4.w;
+        }
+        float4* d = reinterpret_cast<float4*>(dX + (size_t)m * ldx + kk);
+        float4 o = *d;
+        o.x += sum.x; o.y += sum.y; o.z += sum.z; o.w += sum.w;
+        *d = o;
+    }
+    if (threadIdx.x == 0) counters[blockIdx.x] = 0;
+}
+
 // dx[m][k] (+)= sum_n dy[m][n] W[n][k]  for M <= 16, in two deterministic stages so that the whole chip streams W once:
 // stage 1: block (64 columns k) x (slice of `nslice` rows n), 256 threads = 64 kx x 4 ny -> part[slice][m][k];
 // stage 2: dX (+)= sum over the slices in order.
@@ -186,8 +330,9 @@ __global__ void skinny_nn_sum_kernel(int M, int K, int nslices, const float* __r
 // dW[n][k] += sum_i A_i[n] * B_i[k] over a LIST of row pairs (A_i = a gradient row, B_i = an input row): the weight gradient of
 // a layer that ran once per decoder step / LSTM time step, gathered over all its invocations in ONE GEMM instead of one
 // read-modify-write of dW per step (rowsA / rowsB: device arrays of row pointers, R entries).
+// db (optional): the bias gradient db[n] += sum_i A_i[n], formed by the CTAs of the first column block from the tiles they load anyway.
 __global__ void __launch_bounds__(256) sgemm_tn_rows_kernel(int N, int K, int R, const float* const* __restrict__ rowsA, const float* const* __restrict__ rowsB,
-                                                            float* __restrict__ C, int ldc) {
+                                                            float* __restrict__ C, int ldc, float* __restrict__ db) {
     constexpr int BM = 64, BN = 64, BK = 16;
     __shared__ float As[BK][BM + 1];
     __shared__ float Bs[BK][BN + 1];
@@ -198,6 +343,8 @@ __global__ void __launch_bounds__(256) sgemm_tn_rows_kernel(int N, int K, int R,
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const bool sums = db != nullptr && blockIdx.x == 0 && tid < 64;
+    float bsum = 0.f;
     for (int r0 = 0; r0 < R; r0 += BK) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -212,6 +359,9 @@ __global__ void __launch_bounds__(256) sgemm_tn_rows_kernel(int N, int K, int R,
             As[r][c] = va; Bs[r][c] = vb;
         }
         __syncthreads();
+        if (sums)
+#pragma unroll
+            for (int k = 0; k < BK; ++k) bsum += As[k][tid];
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
             float a[4], b[4];
@@ -231,6 +381,7 @@ __global__ void __launch_bounds__(256) sgemm_tn_rows_kernel(int N, int K, int R,
             const int m = m0 + ty + 16 * i, n = n0 + tx + 16 * j;
             if (m < N && n < K) C[(size_t)m * ldc + n] += acc[i][j];
         }
+    if (sums && m0 + tid < N) db[m0 + tid] += bsum;
 }
 
 // ---- kernels: column reductions ---------------------------------------------------------------------------------------
@@ -599,6 +750,75 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(int B, int T, int H, int 
         Y[i] = acc;
     }
 }
+// Tiled form for W <= 96 (the LRW / AVSpeech crops): one CTA = one output frame x 8 output rows x the full output width, for all
+// 24 channels.  The 5 x 21 x (W+5) input patch of the three colour planes is staged in shared memory, split into even and odd
+// columns so that the stride-2 reads of neighbouring output columns hit consecutive banks; the weights sit next to it as
+// [tap][24] and are read as broadcast float4.  Each thread owns 2 output positions x 24 channels (48 accumulators): 48 FMAs per
+// 2 patch words + 6 weight quads, i.e. the kernel runs on the FMA pipe instead of on L1 latency (the one-thread-per-output form
+// above took 8.9 ms for 8 clips; this one is bound by 9.4 GFMA).
+constexpr int STEM_EW = 51, STEM_PR = 21;
+constexpr size_t STEM_TILED_SMEM = (size_t)(735 * 24 + 2 * 15 * STEM_PR * STEM_EW) * sizeof(float);
+__global__ void __launch_bounds__(192) stem_fwd_tiled_kernel(int B, int T, int H, int W, int Ho, int Wo, const float* __restrict__ X, const float* __restrict__ Wt,
+                                                             float* __restrict__ Y) {
+    extern __shared__ float4 stem_sm4[];
+    float* wts = reinterpret_cast<float*>(stem_sm4);              // [735][24]
+    float* ev = wts + 735 * 24;                                      // [(ci*5+kt)][21][51]: input columns 2j - 3
+    float* od = ev + 15 * STEM_PR * STEM_EW;                         //                      input columns 2j - 2
+    const int tiles_h = (Ho + 7) / 8;
+    int blk = blockIdx.x;
+    const int th = blk % tiles_h; blk /= tiles_h;
+    const int t = blk % T, b = blk / T;
+    const int ho0 = th * 8;
+    for (int i = threadIdx.x; i < 735 * 24; i += 192) { const int co = i / 735, k = i - co * 735; wts[k * 24 + co] = Wt[i]; }
+    {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int row = warp; row < 15 * STEM_PR; row += 6) {
+            const int cd = row / STEM_PR, r = row - cd * STEM_PR;
+            const int ci = cd / 5, ti = t + cd % 5 - 2, hi = 2 * ho0 + r - 3;
+            const bool ok = ti >= 0 && ti < T && hi >= 0 && hi < H;
+            const float* src = X + (((size_t)(b * 3 + ci) * T + (ok ? ti : 0)) * H + (ok ? hi : 0)) * W;
+            for (int j = lane; j < 2 * STEM_EW; j += 32) {
+                const int wi = j - 3;
+                const float v = (ok && wi >= 0 && wi < W) ? __ldg(src + wi) : 0.f;
+                ((j & 1) ? od : ev)[row * STEM_EW + (j >> 1)] = v;
+            }
+        }
+    }
+    __syncthreads();
+    const int wo = threadIdx.x % 48, rp = threadIdx.x / 48;          // output rows ho0 + rp and ho0 + rp + 4
+    float acc[2][24];
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int c = 0; c < 24; ++c) acc[p][c] = 0.f;
+    for (int cd = 0; cd < 15; ++cd)
+        for (int kh = 0; kh < 7; ++kh) {
+            const int o0 = (cd * STEM_PR + 2 * rp + kh) * STEM_EW + wo, o1 = o0 + 8 * STEM_EW;
+            const float4* wk = reinterpret_cast<const float4*>(wts + (cd * 7 + kh) * 7 * 24);
+#pragma unroll
+            for (int kw = 0; kw < 7; ++kw) {
+                const float* pl = (kw & 1) ? od : ev;
+                const float x0 = pl[o0 + (kw >> 1)], x1 = pl[o1 + (kw >> 1)];
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    const float4 w4 = wk[kw * 6 + q];
+                    acc[0][4 * q] = fmaf(x0, w4.x, acc[0][4 * q]); acc[0][4 * q + 1] = fmaf(x0, w4.y, acc[0][4 * q + 1]);
+                    acc[0][4 * q + 2] = fmaf(x0, w4.z, acc[0][4 * q + 2]); acc[0][4 * q + 3] = fmaf(x0, w4.w, acc[0][4 * q + 3]);
+                    acc[1][4 * q] = fmaf(x1, w4.x, acc[1][4 * q]); acc[1][4 * q + 1] = fmaf(x1, w4.y, acc[1][4 * q + 1]);
+                    acc[1][4 * q + 2] = fmaf(x1, w4.z, acc[1][4 * q + 2]); acc[1][4 * q + 3] = fmaf(x1, w4.w, acc[1][4 * q + 3]);
+                }
+            }
+        }
+    if (wo >= Wo) return;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const int ho = ho0 + rp + 4 * p;
+        if (ho >= Ho) continue;
+        float4* dst = reinterpret_cast<float4*>(Y + ((((size_t)b * T + t) * Ho + ho) * Wo + wo) * 24);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) dst[q] = make_float4(acc[p][4 * q], acc[p][4 * q + 1], acc[p][4 * q + 2], acc[p][4 * q + 3]);
+    }
+}
 // Weight gradient of the stem: part[chunk][co*735 + k] = sum over the chunk's positions of dY[pos][co] * patch[pos][k].
 // Thread t owns taps k = t, t+256, t+512 (735 <= 768) for all 24 output channels: 72 accumulators, the patch values are
 // gathered straight from the clip tensor (each thread decodes its taps once), dY rows are broadcast from shared memory.
@@ -896,6 +1116,8 @@ inline cudaGraphExec_t capture_graph(cudaStream_t cs, F&& body) {
 
 inline int ew_blocks(size_t total) { return (int)std::min<size_t>(std::max<size_t>((total + 255) / 256, 1), 148 * 16); }
 
+constexpr int SKINNY_SMEM_MAX = 96 * 1024;
+
 struct Engine {
     Context* ctx = nullptr;
     cudaStream_t s = nullptr;
@@ -908,6 +1130,21 @@ struct Engine {
     HostTables* tables = nullptr;      // where a captured backward keeps its row-pointer tables
     size_t table_bytes = 0;            // bytes of pointer tables the last backward uploaded
 
+    unsigned* counters = nullptr;      // tickets of skinny_nn_fused_kernel's last-CTA reduction (always zero between launches)
+    // One-time device state; called outside any stream capture.
+    void setup() {
+        if (counters) return;
+        L2S_CUDA(cudaMalloc(&counters, 64 * sizeof(unsigned)));
+        L2S_CUDA(cudaMemset(counters, 0, 64 * sizeof(unsigned)));
+        static bool attrs = false;
+        if (!attrs) {
+            L2S_CUDA(cudaFuncSetAttribute(skinny_nt_smem_kernel<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKINNY_SMEM_MAX));
+            L2S_CUDA(cudaFuncSetAttribute(skinny_nt_smem_kernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKINNY_SMEM_MAX));
+            L2S_CUDA(cudaFuncSetAttribute(stem_fwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEM_TILED_SMEM));
+            attrs = true;
+        }
+    }
+    void release() { vals.free_all(); grads.free_all(); if (counters) cudaFree(counters); counters = nullptr; }
     void begin(Context* c, cudaStream_t stream, std::map<std::string, Param>* p) {
         ctx = c; s = stream; params = p; launches = &c->launches;
         vals.reset(); grads.reset(); tape.clear(); deferred.clear();
@@ -959,7 +1196,7 @@ struct Engine {
     }
 
     // ---- deferred weight gradients of the per-step (few-row) linears ---------------------------------------------------------
-    struct Deferred { TT W; std::vector<const float*> a, b; };
+    struct Deferred { TT W; float* db = nullptr; std::vector<const float*> a, b; };
     std::map<float*, Deferred> deferred;
     void flush_deferred() {
         table_bytes = 0;
@@ -978,7 +1215,7 @@ struct Engine {
             }
             table_bytes += 2 * half + 16;
             const int N = d.W.rows, K = d.W.cols;
-            sgemm_tn_rows_kernel<<<dim3((K + 63) / 64, (N + 63) / 64), 256, 0, s>>>(N, K, R, tab, tab + R, d.W.g, d.W.rs);
+            sgemm_tn_rows_kernel<<<dim3((K + 63) / 64, (N + 63) / 64), 256, 0, s>>>(N, K, R, tab, tab + R, d.W.g, d.W.rs, d.db);
             ck("deferred weight gradient");
         }
         // eager: the host pointer tables must outlive the asynchronous copies
@@ -1015,7 +1252,12 @@ struct Engine {
         TT y = make(R, N);
         if (R <= 16) {
             const bool vec = !(K & 3) && !(x.rs & 3) && !(W.rs & 3) && !((reinterpret_cast<uintptr_t>(x.v) | reinterpret_cast<uintptr_t>(W.v)) & 15);
-            if (vec) skinny_nt_kernel<true><<<(N * 32 + 255) / 256, 256, 0, s>>>(R, N, K, x.v, x.rs, W.v, W.rs, b ? b->v : nullptr, y.v, y.rs, 0);
+            const int MT = R <= 8 ? 8 : 16;
+            const size_t smem = (size_t)MT * K * sizeof(float);
+            if (vec && smem <= (size_t)SKINNY_SMEM_MAX) {
+                if (MT == 8) skinny_nt_smem_kernel<4, 8><<<(N + 31) / 32, 256, smem, s>>>(R, N, K, x.v, x.rs, W.v, W.rs, b ? b->v : nullptr, y.v, y.rs);
+                else skinny_nt_smem_kernel<2, 16><<<(N + 15) / 16, 256, smem, s>>>(R, N, K, x.v, x.rs, W.v, W.rs, b ? b->v : nullptr, y.v, y.rs);
+            } else if (vec) skinny_nt_kernel<true><<<(N * 32 + 255) / 256, 256, 0, s>>>(R, N, K, x.v, x.rs, W.v, W.rs, b ? b->v : nullptr, y.v, y.rs, 0);
             else skinny_nt_kernel<false><<<(N * 32 + 255) / 256, 256, 0, s>>>(R, N, K, x.v, x.rs, W.v, W.rs, b ? b->v : nullptr, y.v, y.rs, 0);
             ck("skinny_nt");
         } else {
@@ -1031,11 +1273,21 @@ struct Engine {
         if (defer) {
             Deferred& d = deferred[W.g];
             d.W = W;
+            if (hasb && bb.g) d.db = bb.g;                   // the bias gradient rides along with the gathered weight gradient
             for (int r = 0; r < R; ++r) { d.a.push_back(y.g + (size_t)r * y.rs); d.b.push_back(x.v + (size_t)r * x.rs); }
         }
         tape.push_back([=]() {
             if (x.g) {
-                if (R <= 16) {
+                const bool vecb = !(K & 3) && !(x.rs & 3) && !(W.rs & 3) && !((reinterpret_cast<uintptr_t>(x.g) | reinterpret_cast<uintptr_t>(W.v)) & 15) &&
+                                  K <= 64 * 256;
+                if (R <= 16 && vecb) {
+                    const int nslices = (N + 31) / 32;
+                    float* part = scratch((size_t)nslices * R * K);
+                    const dim3 grid((K + 255) / 256, nslices);
+                    if (R <= 8) skinny_nn_fused_kernel<8><<<grid, 256, 0, s>>>(R, N, K, y.g, y.rs, W.v, W.rs, part, counters, x.g, x.rs);
+                    else skinny_nn_fused_kernel<16><<<grid, 256, 0, s>>>(R, N, K, y.g, y.rs, W.v, W.rs, part, counters, x.g, x.rs);
+                    ck("skinny_nn fused");
+                } else if (R <= 16) {
                     const int nslice = 128, nslices = (N + nslice - 1) / nslice;
                     float* part = scratch((size_t)nslices * R * K);
                     skinny_nn_part_kernel<<<dim3((K + 63) / 64, nslices), 256, 0, s>>>(R, N, K, nslice, y.g, y.rs, W.v, W.rs, part);
@@ -1045,7 +1297,7 @@ struct Engine {
                 } else gemm<0, 0>(R, K, N, y.g, y.rs, W.v, W.rs, x.g, x.rs, true);
             }
             if (W.g && !defer) gemm<1, 0>(N, K, R, y.g, y.rs, x.v, x.rs, W.g, W.rs, true);
-            if (hasb && bb.g) colred<COL_SUM>(R, N, y.g, y.rs, nullptr, 0, nullptr, nullptr, 0.f, 1.f, bb.g, true);
+            if (hasb && bb.g && !defer) colred<COL_SUM>(R, N, y.g, y.rs, nullptr, 0, nullptr, nullptr, 0.f, 1.f, bb.g, true);
         });
         return y;
     }
@@ -1256,7 +1508,10 @@ struct Engine {
     TT stem_conv(const float* video, int B, int T, int H, int W, const TT& Wt) {
         const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
         TT y = make(B * T * Ho * Wo, 24);
-        stem_fwd_kernel<<<ew_blocks(y.numel()), 256, 0, s>>>(B, T, H, W, Ho, Wo, video, Wt.v, y.v);
+        if (!(W & 1) && W <= 96 && Wo <= 48)
+            stem_fwd_tiled_kernel<<<B * T * ((Ho + 7) / 8), 192, STEM_TILED_SMEM, s>>>(B, T, H, W, Ho, Wo, video, Wt.v, y.v);
+        else
+            stem_fwd_kernel<<<ew_blocks(y.numel()), 256, 0, s>>>(B, T, H, W, Ho, Wo, video, Wt.v, y.v);
         ck("stem conv");
         tape.push_back([=]() {
             if (!Wt.g) return;

@@ -58,7 +58,7 @@ struct DecoderTrain {
     } st{};
 
     void drop_graphs() { for (auto& kv : slots) kv.second.release(); slots.clear(); slot = nullptr; }
-    void release() { drop_graphs(); e.vals.free_all(); e.grads.free_all(); io.free_all(); if (cs) cudaStreamDestroy(cs); cs = nullptr; }
+    void release() { drop_graphs(); e.release(); io.free_all(); if (cs) cudaStreamDestroy(cs); cs = nullptr; }
 
     static TT assign(Engine& e, const TT& dst_view, const TT& src) {
         ew_fwd_kernel<EW_COPY><<<ew_blocks(src.numel()), 256, 0, e.s>>>(src.rows, src.cols, src.v, src.rs, nullptr, 0, 0.f, 1, dst_view.v, dst_view.rs);
@@ -110,6 +110,7 @@ struct DecoderTrain {
         B = B_; T = T_; M = M_;
         if (B <= 0 || T < 7 || T > 300 || M <= 0 || M > 300) throw L2sError(1, "decoder_train_fwd: need 7<=T<=300, 1<=M<=300");
         live = false;
+        e.setup();
         if (gen != bind_gen) { drop_graphs(); bind_gen = gen; }     // parameter / gradient memory moved: the graphs point at the old one
         want_logits = in.out_attn_logits != nullptr;
         // ---- stage the caller's tensors ---------------------------------------------------------------------------------------
@@ -353,7 +354,7 @@ struct VideoTrain {
     float *st_video = nullptr, *st_mask = nullptr, *st_out = nullptr, *st_g = nullptr;
 
     void drop_graphs() { for (auto& kv : slots) kv.second.release(); slots.clear(); slot = nullptr; }
-    void release() { drop_graphs(); e.vals.free_all(); e.grads.free_all(); io.free_all(); if (cs) cudaStreamDestroy(cs); cs = nullptr; }
+    void release() { drop_graphs(); e.release(); io.free_all(); if (cs) cudaStreamDestroy(cs); cs = nullptr; }
 
     TT pw(const TT& x, const std::string& name, int cout) {        // 1x1 Conv2d, bias=False
         return e.linear(x, e.param(name + ".weight", cout, x.cols), nullptr);
@@ -363,6 +364,7 @@ struct VideoTrain {
         B = B_; T = T_; H = H_; W = W_;
         if (B <= 0 || T <= 0 || (H & 3) || (W & 3)) throw L2sError(1, "video_train_fwd: bad shape");
         live = false;
+        e.setup();
         if (gen != bind_gen) { drop_graphs(); bind_gen = gen; }
         const size_t N = (size_t)B * T;
         io.reset();
