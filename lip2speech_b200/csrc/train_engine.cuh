@@ -42,7 +42,7 @@ struct TT {                       // train tensor: [rows][cols] view, element (r
 template <int TA, int TB>
 __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                                                     float* __restrict__ C, int ldc, int accumulate, int kper) {
-    constexpr int BM = 64, BN = 64, BK = 16;
+    constexpr int BM = 64, BN = 64, BK = 32;
     __shared__ float As[BK][BM + 1];
     __shared__ float Bs[BK][BN + 1];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -54,29 +54,37 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const f
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int k0 = kbeg; k0 < K; k0 += BK) {
-        // 1024 elements per tile, 4 per thread
+    // 2048 elements per operand tile, 8 per thread; the next tile is fetched into registers while the current one is multiplied
+    // (these GEMMs have short K or few tiles: without the prefetch every 16-wide k step paid a full L2 round trip).
+    float ra[8], rb[8];
+    auto fetch = [&](int k0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 8; ++i) {
             const int e = tid + i * 256;
             {
                 int m, k;
-                if (TA == 0) { k = e & 15; m = e >> 4; } else { m = e & 63; k = e >> 6; }     // contiguous index fastest
+                if (TA == 0) { k = e & 31; m = e >> 5; } else { m = e & 63; k = e >> 6; }     // contiguous index fastest
                 const int gm = m0 + m, gk = k0 + k;
-                float v = 0.f;
-                if (gm < M && gk < K) v = TA == 0 ? A[(size_t)gm * lda + gk] : A[(size_t)gk * lda + gm];
-                As[k][m] = v;
+                ra[i] = (gm < M && gk < K) ? (TA == 0 ? A[(size_t)gm * lda + gk] : A[(size_t)gk * lda + gm]) : 0.f;
             }
             {
                 int n, k;
-                if (TB == 0) { n = e & 63; k = e >> 6; } else { k = e & 15; n = e >> 4; }
+                if (TB == 0) { n = e & 63; k = e >> 6; } else { k = e & 31; n = e >> 5; }
                 const int gn = n0 + n, gk = k0 + k;
-                float v = 0.f;
-                if (gn < N && gk < K) v = TB == 0 ? B[(size_t)gk * ldb + gn] : B[(size_t)gn * ldb + gk];
-                Bs[k][n] = v;
+                rb[i] = (gn < N && gk < K) ? (TB == 0 ? B[(size_t)gk * ldb + gn] : B[(size_t)gn * ldb + gk]) : 0.f;
             }
         }
+    };
+    fetch(kbeg);
+    for (int k0 = kbeg; k0 < K; k0 += BK) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int e = tid + i * 256;
+            if (TA == 0) As[e & 31][e >> 5] = ra[i]; else As[e >> 6][e & 63] = ra[i];
+            if (TB == 0) Bs[e >> 6][e & 63] = rb[i]; else Bs[e & 31][e >> 5] = rb[i];
+        }
         __syncthreads();
+        if (k0 + BK < K) fetch(k0 + BK);
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
             float a[4], b[4];
@@ -215,78 +223,83 @@ __global__ void __launch_bounds__(256) skinny_nt_smem_kernel(int M, int N, int K
     if (n < N && m < M) C[(size_t)m * ldc + n] = v + (bias ? bias[n] : 0.f);
 }
 
-// dx[m][k] += sum_n dy[m][n] W[n][k] for M <= MT in ONE launch: grid (k tiles of 256, n slices of 32).  A warp covers 32 k
-// (8 lanes x 4) x 4 interleaved n; every lane issues its 8 weight loads up front; the 4 n-lanes are folded with shuffles; the
-// slice partials go to `part`, and the LAST CTA to finish a k tile (ticket counter, reset for the next launch) adds the slices
-// in index order — deterministic, and without a second launch.
+// dx[m][k] += sum_n dy[m][n] W[n][k] for M <= MT in ONE launch and without partial sums in memory: a CTA owns a strip of 16
+// columns k (64 bytes of every weight row) and walks ALL N rows: lane = (4 k-quads) x (8 rows per load instruction), 8 warps
+// interleave the rows; every lane keeps two batches of 8 weight loads in flight (ping-pong) while dy — staged once in shared
+// memory, transposed to [n][m] — feeds the FMAs.  The 8 row-lanes are folded with shuffles, the 8 warps through shared memory in
+// index order: deterministic.  (The two-stage form below needed two launches and 64 dependent partial reads per output.)
 template <int MT>
-__global__ void __launch_bounds__(256) skinny_nn_fused_kernel(int M, int N, int K, const float* __restrict__ dY, int ldy, const float* __restrict__ W, int ldw,
-                                                              float* __restrict__ part, unsigned* __restrict__ counters, float* __restrict__ dX, int ldx) {
-    constexpr int NS = 32;
-    __shared__ __align__(16) float dys[NS][MT];
-    __shared__ int last;
+__global__ void __launch_bounds__(256) skinny_nn_strip_kernel(int M, int N, int K, const float* __restrict__ dY, int ldy, const float* __restrict__ W, int ldw,
+                                                              float* __restrict__ dX, int ldx) {
+    extern __shared__ float4 nn_sm4[];
+    float* dys = reinterpret_cast<float*>(nn_sm4);                   // [Npad][MT]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int kq = lane & 7, ny = lane >> 3;
-    const int k = blockIdx.x * 256 + warp * 32 + kq * 4;
-    const int n0 = blockIdx.y * NS;
-    float4 wv[NS / 4];
+    const int kq = lane & 3, ny = lane >> 2;
+    const int k = blockIdx.x * 16 + kq * 4;
+    const bool kok = k < K;
+    const int nfirst = warp * 8 + ny;                                // this lane's rows: nfirst + 64 j
+    const int iters = (N + 63) / 64;
+    float4 wv[2][8];
+    auto fetch = [&](int buf, int j0) {
 #pragma unroll
-    for (int j = 0; j < NS / 4; ++j) {
-        const int n = n0 + ny + 4 * j;
-        wv[j] = (n < N && k < K) ? *reinterpret_cast<const float4*>(W + (size_t)n * ldw + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    for (int i = threadIdx.x; i < NS * MT; i += 256) {
-        const int m = i / NS, n = i % NS;
-        dys[n][m] = (m < M && n0 + n < N) ? dY[(size_t)m * ldy + n0 + n] : 0.f;
+        for (int u = 0; u < 8; ++u) {
+            const int n = nfirst + 64 * (j0 + u);
+            wv[buf][u] = (kok && n < N) ? *reinterpret_cast<const float4*>(W + (size_t)n * ldw + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    fetch(0, 0);
+    const int Npad = iters * 64;
+    for (int i = threadIdx.x; i < Npad * MT; i += 256) {
+        const int n = i / MT, m = i % MT;
+        dys[i] = (m < M && n < N) ? dY[(size_t)m * ldy + n] : 0.f;
     }
     __syncthreads();
     float acc[MT * 4];
 #pragma unroll
     for (int i = 0; i < MT * 4; ++i) acc[i] = 0.f;
+    auto compute = [&](int buf, int j0) {
 #pragma unroll
-    for (int j = 0; j < NS / 4; ++j) {
-        const float4* d4 = reinterpret_cast<const float4*>(dys[ny + 4 * j]);
+        for (int u = 0; u < 8; ++u) {
+            if (j0 + u >= iters) break;
+            const float4* d4 = reinterpret_cast<const float4*>(dys + (size_t)(nfirst + 64 * (j0 + u)) * MT);
+            const float4 w4 = wv[buf][u];
 #pragma unroll
-        for (int mq = 0; mq < MT / 4; ++mq) {
-            const float4 d = d4[mq];
-            const float dm[4] = {d.x, d.y, d.z, d.w};
+            for (int mq = 0; mq < MT / 4; ++mq) {
+                const float4 d = d4[mq];
+                const float dm[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                float* a = acc + (mq * 4 + u) * 4;
-                a[0] = fmaf(dm[u], wv[j].x, a[0]); a[1] = fmaf(dm[u], wv[j].y, a[1]); a[2] = fmaf(dm[u], wv[j].z, a[2]); a[3] = fmaf(dm[u], wv[j].w, a[3]);
+                for (int v = 0; v < 4; ++v) {
+                    float* a = acc + (mq * 4 + v) * 4;
+                    a[0] = fmaf(dm[v], w4.x, a[0]); a[1] = fmaf(dm[v], w4.y, a[1]); a[2] = fmaf(dm[v], w4.z, a[2]); a[3] = fmaf(dm[v], w4.w, a[3]);
+                }
             }
         }
+    };
+    for (int j0 = 0; j0 < iters; j0 += 16) {
+        if (j0 + 8 < iters) fetch(1, j0 + 8);
+        compute(0, j0);
+        if (j0 + 16 < iters) fetch(0, j0 + 16);
+        if (j0 + 8 < iters) compute(1, j0 + 8);
     }
-    // fold the 4 n-lanes (lane bits 4 and 3): each round hands half of the remaining values to the partner
-    L2S_FOLD_LANES(acc, 16, MT * 2) L2S_FOLD_LANES(acc, 8, MT)
-    // this lane now owns rows m = (MT/2) * bit4 + (MT/4) * bit3 + [0, MT/4) of its four k
-    const int mbase = (MT / 2) * ((lane >> 4) & 1) + (MT / 4) * ((lane >> 3) & 1);
-    if (k < K)
+    // fold the 8 row-lanes (lane bits 4, 3, 2): each round hands half of the remaining values to the partner
+    L2S_FOLD_LANES(acc, 16, MT * 2) L2S_FOLD_LANES(acc, 8, MT) L2S_FOLD_LANES(acc, 4, MT / 2)
+    // this lane now owns MT/8 rows m = (MT/2) b4 + (MT/4) b3 + (MT/8) b2 + [0, MT/8) of its four k
+    __syncthreads();                                                 // dys is dead: reuse it for the cross-warp sums
+    float* red = dys;                                                // [8 warps][MT][16]
+    const int mbase = (MT / 2) * ((lane >> 4) & 1) + (MT / 4) * ((lane >> 3) & 1) + (MT / 8) * ((lane >> 2) & 1);
 #pragma unroll
-        for (int u = 0; u < MT / 4; ++u) {
-            const int m = mbase + u;
-            if (m < M) *reinterpret_cast<float4*>(part + ((size_t)blockIdx.y * M + m) * K + k) = make_float4(acc[u * 4], acc[u * 4 + 1], acc[u * 4 + 2], acc[u * 4 + 3]);
-        }
-    __threadfence();
+    for (int u = 0; u < MT / 8; ++u)
+        *reinterpret_cast<float4*>(red + ((size_t)warp * MT + mbase + u) * 16 + kq * 4) = make_float4(acc[u * 4], acc[u * 4 + 1], acc[u * 4 + 2], acc[u * 4 + 3]);
     __syncthreads();
-    if (threadIdx.x == 0) last = atomicAdd(counters + blockIdx.x, 1u) == gridDim.y - 1;
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
-    for (int i = threadIdx.x; i < M * 64; i += 256) {
-        const int m = i >> 6, kk = blockIdx.x * 256 + (i & 63) * 4;
-        if (kk >= K) continue;
-        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int z = 0; z < (int)gridDim.y; ++z) {
-            const float4 p4 = __ldcg(reinterpret_cast<const float4*>(part + ((size_t)z * M + m) * K + kk));
-            sum.x += p4.x; sum.y += p4.y; sum.z += p4.z; sum.w += p4.w;
+    if (threadIdx.x < MT * 16) {
+        const int m = threadIdx.x >> 4, kk = blockIdx.x * 16 + (threadIdx.x & 15);
+        if (m < M && kk < K) {
+            float sum = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) sum += red[((size_t)w * MT + m) * 16 + (threadIdx.x & 15)];
+            dX[(size_t)m * ldx + kk] += sum;
         }
-        float4* d = reinterpret_cast<float4*>(dX + (size_t)m * ldx + kk);
-        float4 o = *d;
-        o.x += sum.x; o.y += sum.y; o.z += sum.z; o.w += sum.w;
-        *d = o;
     }
-    if (threadIdx.x == 0) counters[blockIdx.x] = 0;
 }
 
 // dx[m][k] (+)= sum_n dy[m][n] W[n][k]  for M <= 16, in two deterministic stages so that the whole chip streams W once:
@@ -401,6 +414,7 @@ __global__ void __launch_bounds__(256) colreduce_kernel(int rows, int cols, cons
     if (c < cols) {
         const float mu = (OP == COL_SQDEV || OP == COL_BN_DGAMMA) ? aux[c] : 0.f;
         const float rstd = OP == COL_BN_DGAMMA ? rsqrtf(aux2[c] + eps) : 0.f;
+#pragma unroll 8
         for (int r = r0 + rl; r < r1; r += 8) {
             const float x = X[(size_t)r * xs + c];
             if (OP == COL_SUM) a += x;
@@ -420,14 +434,15 @@ __global__ void __launch_bounds__(256) colreduce_kernel(int rows, int cols, cons
         part[(size_t)blockIdx.y * cols + c] = s;
     }
 }
-// out[c] = (accumulate ? out[c] : 0) + scale * sum_split part[split][c]
+// out[c] = (accumulate ? out[c] : 0) + scale * sum_split part[split][c]; one warp per column: lanes stride over the splits, then
+// a fixed shuffle tree (deterministic for a given split count).
 __global__ void colfinish_kernel(int cols, int splits, const float* __restrict__ part, float scale, float* __restrict__ out, int accumulate) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= cols) return;
     float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += part[(size_t)z * cols + c];
-    s *= scale;
-    out[c] = accumulate ? out[c] + s : s;
+    for (int z = lane; z < splits; z += 32) s += part[(size_t)z * cols + c];
+    s = warp_sum(s) * scale;
+    if (lane == 0) out[c] = accumulate ? out[c] + s : s;
 }
 
 // Full reduction sum(X*Y) -> out[0] (+)=, single CTA (used for the two scalar temperatures).
@@ -1116,7 +1131,7 @@ inline cudaGraphExec_t capture_graph(cudaStream_t cs, F&& body) {
 
 inline int ew_blocks(size_t total) { return (int)std::min<size_t>(std::max<size_t>((total + 255) / 256, 1), 148 * 16); }
 
-constexpr int SKINNY_SMEM_MAX = 96 * 1024;
+constexpr int SKINNY_SMEM_MAX = 132 * 1024;
 
 struct Engine {
     Context* ctx = nullptr;
@@ -1130,7 +1145,7 @@ struct Engine {
     HostTables* tables = nullptr;      // where a captured backward keeps its row-pointer tables
     size_t table_bytes = 0;            // bytes of pointer tables the last backward uploaded
 
-    unsigned* counters = nullptr;      // tickets of skinny_nn_fused_kernel's last-CTA reduction (always zero between launches)
+    unsigned* counters = nullptr;      // zeroed device words for kernels that need a ticket (kept zero between launches)
     // One-time device state; called outside any stream capture.
     void setup() {
         if (counters) return;
@@ -1140,6 +1155,8 @@ struct Engine {
         if (!attrs) {
             L2S_CUDA(cudaFuncSetAttribute(skinny_nt_smem_kernel<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKINNY_SMEM_MAX));
             L2S_CUDA(cudaFuncSetAttribute(skinny_nt_smem_kernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKINNY_SMEM_MAX));
+            L2S_CUDA(cudaFuncSetAttribute(skinny_nn_strip_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKINNY_SMEM_MAX));
+            L2S_CUDA(cudaFuncSetAttribute(skinny_nn_strip_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKINNY_SMEM_MAX));
             L2S_CUDA(cudaFuncSetAttribute(stem_fwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEM_TILED_SMEM));
             attrs = true;
         }
@@ -1187,11 +1204,13 @@ struct Engine {
     template <int OP>
     void colred(int rows, int cols, const float* X, int xs, const float* Y, int ys, const float* aux, const float* aux2, float eps, float scale,
                 float* out, bool accumulate) {
-        const int splits = std::max(1, std::min(64, rows / 2048));
+        // enough CTAs to fill the chip even for 24 columns (the stem's 534 K rows were walked by 64 CTAs, 1 044 dependent loads each)
+        const int colblocks = (cols + 31) / 32;
+        const int splits = std::max(1, std::min(std::min(1024, (148 * 8 + colblocks - 1) / colblocks), rows / 256));
         float* part = scratch((size_t)splits * cols);
-        colreduce_kernel<OP><<<dim3((cols + 31) / 32, splits), 256, 0, s>>>(rows, cols, X, xs, Y, ys, aux, aux2, eps, part);
+        colreduce_kernel<OP><<<dim3(colblocks, splits), 256, 0, s>>>(rows, cols, X, xs, Y, ys, aux, aux2, eps, part);
         ck("column reduce");
-        colfinish_kernel<<<(cols + 255) / 256, 256, 0, s>>>(cols, splits, part, scale, out, accumulate ? 1 : 0);
+        colfinish_kernel<<<(cols * 32 + 255) / 256, 256, 0, s>>>(cols, splits, part, scale, out, accumulate ? 1 : 0);
         ck("column reduce finish");
     }
 
@@ -1230,8 +1249,8 @@ struct Engine {
         dim3 grid((N + 63) / 64, (M + 63) / 64);
         const int tiles = grid.x * grid.y;
         if (tiles < 64 && K >= 2048) {                       // few output tiles, long reduction: split K over the chip
-            const int splits = std::min(std::min(128, 296 / tiles), (K + 511) / 512);
-            const int kper = (((K + splits - 1) / splits) + 15) / 16 * 16;
+            const int splits = std::min(std::min(128, 296 / tiles), (K + 255) / 256);
+            const int kper = (((K + splits - 1) / splits) + 31) / 32 * 32;
             const int nz = (K + kper - 1) / kper;
             float* part = scratch((size_t)nz * M * N);
             grid.z = nz;
@@ -1278,15 +1297,14 @@ struct Engine {
         }
         tape.push_back([=]() {
             if (x.g) {
-                const bool vecb = !(K & 3) && !(x.rs & 3) && !(W.rs & 3) && !((reinterpret_cast<uintptr_t>(x.g) | reinterpret_cast<uintptr_t>(W.v)) & 15) &&
-                                  K <= 64 * 256;
+                const bool vecb = !(K & 3) && !(W.rs & 3) && !(reinterpret_cast<uintptr_t>(W.v) & 15) &&
+                                  (size_t)std::max((N + 63) / 64 * 64, 128) * (R <= 8 ? 8 : 16) * sizeof(float) <= (size_t)SKINNY_SMEM_MAX;
                 if (R <= 16 && vecb) {
-                    const int nslices = (N + 31) / 32;
-                    float* part = scratch((size_t)nslices * R * K);
-                    const dim3 grid((K + 255) / 256, nslices);
-                    if (R <= 8) skinny_nn_fused_kernel<8><<<grid, 256, 0, s>>>(R, N, K, y.g, y.rs, W.v, W.rs, part, counters, x.g, x.rs);
-                    else skinny_nn_fused_kernel<16><<<grid, 256, 0, s>>>(R, N, K, y.g, y.rs, W.v, W.rs, part, counters, x.g, x.rs);
-                    ck("skinny_nn fused");
+                    const int MT = R <= 8 ? 8 : 16;
+                    const size_t smem = (size_t)std::max((N + 63) / 64 * 64, 128) * MT * sizeof(float);      // >= the [8][MT][16] cross-warp buffer
+                    if (MT == 8) skinny_nn_strip_kernel<8><<<(K + 15) / 16, 256, smem, s>>>(R, N, K, y.g, y.rs, W.v, W.rs, x.g, x.rs);
+                    else skinny_nn_strip_kernel<16><<<(K + 15) / 16, 256, smem, s>>>(R, N, K, y.g, y.rs, W.v, W.rs, x.g, x.rs);
+                    ck("skinny_nn strip");
                 } else if (R <= 16) {
                     const int nslice = 128, nslices = (N + nslice - 1) / nslice;
                     float* part = scratch((size_t)nslices * R * K);
