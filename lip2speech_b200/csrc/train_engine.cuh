@@ -174,7 +174,7 @@ __device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) 
 // instead of two loads per warp), NW * MT = 32 accumulators per lane are reduced with warp_transpose_sum32.
 template <int NW, int MT>
 __global__ void __launch_bounds__(256) skinny_nt_smem_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
-                                                             const float* __restrict__ bias, float* __restrict__ C, int ldc) {
+                                                             const float* __restrict__ bias, float* __restrict__ C, int ldc, int accumulate) {
     static_assert(NW * MT == 32, "one output per lane");
     extern __shared__ float4 xs4[];                                   // [MT][K/4], rows >= M are zero
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -220,7 +220,11 @@ __global__ void __launch_bounds__(256) skinny_nt_smem_kernel(int M, int N, int K
     }
     const float v = warp_transpose_sum32(acc, lane);                  // lane = n * MT + m
     const int n = n0 + lane / MT, m = lane % MT;
-    if (n < N && m < M) C[(size_t)m * ldc + n] = v + (bias ? bias[n] : 0.f);
+    if (n < N && m < M) {
+        float* c = C + (size_t)m * ldc + n;
+        const float r = v + (bias ? bias[n] : 0.f);
+        *c = accumulate ? *c + r : r;
+    }
 }
 
 // dx[m][k] += sum_n dy[m][n] W[n][k] for M <= MT in ONE launch and without partial sums in memory: a CTA owns a strip of 16
@@ -1265,22 +1269,27 @@ struct Engine {
     }
 
     // y = x W^T (+ b): x [R,K], W [N,K] (nn.Linear / flattened Conv1d weight), b [N] or empty
-    TT linear(const TT& x, const TT& W, const TT* b) {
+    // dst: write into this [R,N] view instead of a fresh tensor; accumulate: y += (a second operand of the same pre-activation,
+    // e.g. the recurrent half of the LSTM gates — the view's gradient then serves both products).
+    TT linear(const TT& x, const TT& W, const TT* b, const TT* dst = nullptr, bool accumulate = false) {
         const int R = x.rows, K = x.cols, N = W.rows;
         if (W.cols != K) throw L2sError(1, "train: linear shape mismatch");
-        TT y = make(R, N);
+        if (dst && (dst->rows != R || dst->cols != N)) throw L2sError(1, "train: linear destination shape mismatch");
+        if (accumulate && !dst) throw L2sError(1, "train: accumulating linear needs a destination");
+        TT y = dst ? *dst : make(R, N);
+        const int accf = accumulate ? 1 : 0;
         if (R <= 16) {
             const bool vec = !(K & 3) && !(x.rs & 3) && !(W.rs & 3) && !((reinterpret_cast<uintptr_t>(x.v) | reinterpret_cast<uintptr_t>(W.v)) & 15);
             const int MT = R <= 8 ? 8 : 16;
             const size_t smem = (size_t)MT * K * sizeof(float);
             if (vec && smem <= (size_t)SKINNY_SMEM_MAX) {
-                if (MT == 8) skinny_nt_smem_kernel<4, 8><<<(N + 31) / 32, 256, smem, s>>>(R, N, K, x.v, x.rs, W.v, W.rs, b ? b->v : nullptr, y.v, y.rs);
-                else skinny_nt_smem_kernel<2, 16><<<(N + 15) / 16, 256, smem, s>>>(R, N, K, x.v, x.rs, W.v, W.rs, b ? b->v : nullptr, y.v, y.rs);
-            } else if (vec) skinny_nt_kernel<true><<<(N * 32 + 255) / 256, 256, 0, s>>>(R, N, K, x.v, x.rs, W.v, W.rs, b ? b->v : nullptr, y.v, y.rs, 0);
-            else skinny_nt_kernel<false><<<(N * 32 + 255) / 256, 256, 0, s>>>(R, N, K, x.v, x.rs, W.v, W.rs, b ? b->v : nullptr, y.v, y.rs, 0);
+                if (MT == 8) skinny_nt_smem_kernel<4, 8><<<(N + 31) / 32, 256, smem, s>>>(R, N, K, x.v, x.rs, W.v, W.rs, b ? b->v : nullptr, y.v, y.rs, accf);
+                else skinny_nt_smem_kernel<2, 16><<<(N + 15) / 16, 256, smem, s>>>(R, N, K, x.v, x.rs, W.v, W.rs, b ? b->v : nullptr, y.v, y.rs, accf);
+            } else if (vec) skinny_nt_kernel<true><<<(N * 32 + 255) / 256, 256, 0, s>>>(R, N, K, x.v, x.rs, W.v, W.rs, b ? b->v : nullptr, y.v, y.rs, accf);
+            else skinny_nt_kernel<false><<<(N * 32 + 255) / 256, 256, 0, s>>>(R, N, K, x.v, x.rs, W.v, W.rs, b ? b->v : nullptr, y.v, y.rs, accf);
             ck("skinny_nt");
         } else {
-            gemm<0, 1>(R, N, K, x.v, x.rs, W.v, W.rs, y.v, y.rs, false);
+            gemm<0, 1>(R, N, K, x.v, x.rs, W.v, W.rs, y.v, y.rs, accumulate);
             if (b) {
                 ew_fwd_kernel<EW_ADDROW><<<ew_blocks(y.numel()), 256, 0, s>>>(R, N, y.v, y.rs, b->v, 0, 0.f, R, y.v, y.rs);   // group = R: one broadcast row
                 ck("bias");
@@ -1359,8 +1368,8 @@ struct Engine {
         if (w.g) tape.push_back([=]() { colred<COL_PRELU_DW>(x.rows, x.cols, x.v, x.rs, y.g, y.rs, nullptr, nullptr, 0.f, 1.f, w.g, true); });
         return y;
     }
-    TT add(const TT& a, const TT& b) {
-        TT y = make(a.rows, a.cols);
+    TT add(const TT& a, const TT& b, const TT* dst = nullptr) {
+        TT y = dst ? *dst : make(a.rows, a.cols);
         ew_fwd_kernel<EW_ADD><<<ew_blocks(a.numel()), 256, 0, s>>>(a.rows, a.cols, a.v, a.rs, b.v, b.rs, 0.f, 1, y.v, y.rs);
         ck("add");
         tape.push_back([=]() {
@@ -1478,9 +1487,9 @@ struct Engine {
         });
         return y;
     }
-    TT attn_context(const TT& a, const TT& V, int T) {
+    TT attn_context(const TT& a, const TT& V, int T, const TT* dst = nullptr) {
         const int B = a.rows, D = V.cols;
-        TT y = make(B, D);
+        TT y = dst ? *dst : make(B, D);
         attn_context_kernel<<<ew_blocks((size_t)B * D), 256, 0, s>>>(B, T, D, a.v, a.rs, V.v, V.rs, y.v, y.rs);
         ck("attn context");
         tape.push_back([=]() {
@@ -1491,10 +1500,10 @@ struct Engine {
     }
 
     // LSTM cell on pre-activation gates [B,4H] and previous cell state; returns (h, c)
-    void lstm_cell(const TT& gates, const TT& cprev, TT& h, TT& c) {
+    void lstm_cell(const TT& gates, const TT& cprev, TT& h, TT& c, const TT* hdst = nullptr, const TT* cdst = nullptr) {
         const int B = gates.rows, H = gates.cols / 4;
         float* act = scratch((size_t)B * 4 * H);
-        h = make(B, H); c = make(B, H);
+        h = hdst ? *hdst : make(B, H); c = cdst ? *cdst : make(B, H);
         lstm_cell_fwd_kernel<<<ew_blocks((size_t)B * H), 256, 0, s>>>(B, H, gates.v, gates.rs, cprev.v, cprev.rs, act, c.v, c.rs, h.v, h.rs);
         ck("lstm cell");
         TT hh = h, cc = c;

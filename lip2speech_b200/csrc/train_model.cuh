@@ -14,6 +14,14 @@ __global__ void tile_pos_kernel(int B, int T, int C, const float* __restrict__ p
 // dst rows (strided view) = src ; backward: src.g += dst.g
 // [B][C][M] keep-mask -> rows (b, m) x C
 __global__ void zero_kernel(float* __restrict__ p, size_t n) { TR_EW_LOOP(n) p[i] = 0.f; }
+// stop[b*M + i] = per_step[i*B + b] + per_clip[b]   (stop-token logit = W_h . h1_i + (W_c . enc_cell + bias), decoder.py:373)
+__global__ void stop_combine_kernel(int B, int M, const float* __restrict__ step, const float* __restrict__ clip, float* __restrict__ out) {
+    TR_EW_LOOP((size_t)B * M) { const int b = i / M, m = i % M; out[i] = step[(size_t)m * B + b] + clip[b]; }
+}
+__global__ void stop_combine_bwd_kernel(int B, int M, const float* __restrict__ g, float* __restrict__ gstep, float* __restrict__ gclip) {
+    TR_EW_LOOP((size_t)B * M) { const int m = i / B, b = i % B; gstep[i] += g[(size_t)b * M + m]; }
+    TR_EW_LOOP((size_t)B) { float a = 0.f; for (int m = 0; m < M; ++m) a += g[(size_t)i * M + m]; gclip[i] += a; }
+}
 
 struct DecoderTrainIO {
     const float* visual; const float* spk; const float* mels;      // [B,T,1024], [B,256], [B,80,M]
@@ -96,10 +104,11 @@ struct DecoderTrain {
         TT h = site, c = site;
         for (int k = 0; k < T; ++k) {
             const int t = dir ? T - 1 - k : k;
-            TT g = e.add(xproj.rowslice(t, B, T), e.linear(h, Whh, &bhh));
+            TT g = xproj.rowslice(t, B, T);                          // the gates of step t, completed in place: += h W_hh^T + b_hh
+            e.linear(h, Whh, &bhh, &g, true);
             TT hn, cn;
-            e.lstm_cell(g, c, hn, cn);
-            assign(e, rnn_out.rowslice(t, B, T).colslice(dir * 512, 512), hn);
+            TT hdst = rnn_out.rowslice(t, B, T).colslice(dir * 512, 512);
+            e.lstm_cell(g, c, hn, cn, &hdst);                       // h_t lands in its slot of the Bi-LSTM output
             h = hn; c = cn;
         }
         h_final = h; c_final = c;
@@ -229,43 +238,66 @@ struct DecoderTrain {
         zero_kernel<<<ew_blocks((size_t)B * 80), 256, 0, s>>>(zeros80.v, (size_t)B * 80);
         e.ck("zeros");
         TT bos = e.add_rows(zeros80, e.param(P + "BOS", 1, 80), B);                            // torch.tile(self.BOS, (N,1,1))
-        TT zc = e.make(B, 512, false);
-        zero_kernel<<<ew_blocks((size_t)B * 512), 256, 0, s>>>(zc.v, (size_t)B * 512);
-        e.ck("zeros");
         outputs = e.make(B * M, 80);
         stops = e.make(B * M, 1);
-        TT h0 = hf, h1 = hb, c0 = zc, c1 = zc;                      // hidden = encoder h_n; cell.fill_(0) (347)
+        // State of all M steps in two buffers, rows (step, clip): [h0 | h1] and [c0 | c1] sit side by side, so the concatenations
+        // the reference feeds to Q / content.Q (decoder.py:359,366) are plain views; hidden = encoder h_n, cell = 0 (347).
+        TT HH = e.make(M * B, 1024), CC = e.make(M * B, 1024);
+        TT hh_prev = e.concat_cols({hf, hb});
+        TT cc_prev = e.make(B, 1024, false);
+        zero_kernel<<<ew_blocks((size_t)B * 1024), 256, 0, s>>>(cc_prev.v, (size_t)B * 1024);
+        e.ck("zeros");
         TT ys = bos;
         TT temp = e.param(P + "temperature", 1, 1), ctemp = e.param(P + "content.temperature", 1, 1);
         TT Wq_w = e.param(P + "Q.1.w", 1, 512), p1w = e.param(P + "prenet.1.w", 1, 256), p4w = e.param(P + "prenet.4.w", 1, 256);
         const std::string R = P + "decoder_rnn.";
         TT Wih0 = e.param(R + "weight_ih_l0", 2048, 512), bih0 = e.param(R + "bias_ih_l0", 1, 2048), Whh0 = e.param(R + "weight_hh_l0", 2048, 512), bhh0 = e.param(R + "bias_hh_l0", 1, 2048);
         TT Wih1 = e.param(R + "weight_ih_l1", 2048, 512), bih1 = e.param(R + "bias_ih_l1", 1, 2048), Whh1 = e.param(R + "weight_hh_l1", 2048, 512), bhh1 = e.param(R + "bias_hh_l1", 1, 2048);
+        TT Wfc = e.param(P + "fc_out.linear_layer.weight", 80, 512), bfc = e.param(P + "fc_out.linear_layer.bias", 1, 80);
         for (int i = 0; i < M; ++i) {
+            TT hh = HH.rowslice(i * B, B), cc = CC.rowslice(i * B, B);
             if (i > 0) ys = e.select(io.tf + i, mel_rows.rowslice(i - 1, B, M), ys);            // teacher_input[:, i] or the previous output (355-357)
             TT p1 = e.psine(lin(ys, P + "prenet.0.linear_layer", 256), p1w);
             TT p1d = e.dropout(p1, io.prenet + (size_t)i * B * 256, 256, 0.2f);
             TT p2 = e.psine(lin(p1d, P + "prenet.3.linear_layer", 256), p4w);
-            TT q = e.add_const(e.psine(lin(e.concat_cols({h0, h1}), P + "Q.0.linear_layer", 512), Wq_w), pos + (size_t)i * 512, 0);
+            TT q = e.add_const(e.psine(lin(hh_prev, P + "Q.0.linear_layer", 512), Wq_w), pos + (size_t)i * 512, 0);
             TT a = e.dropout(e.attn_scores(e.scale_param(q, temp), Kmem, T), io.attn + (size_t)i * B * T, T, 0.1f);
             if (want_logits) {
                 // rows b of a -> out[b][i][:]
                 ew_fwd_kernel<EW_COPY><<<ew_blocks(a.numel()), 256, 0, s>>>(B, T, a.v, a.rs, nullptr, 0, 0.f, 1, io.out_logits + (size_t)i * T, M * T);
                 e.ck("attn logits out");
             }
+            TT xy = e.make(B, 512);                                 // [content read-out | prenet + attention], the input of LSTM layer 0
+            TT xy_c = xy.colslice(0, 256), xy_y = xy.colslice(256, 256);
             TT o = lin(e.attn_context(e.softmax(a), Vmem, T), P + "attention_proj.linear_layer", 256);
-            TT y = e.add(p2, o);
-            TT cq = e.silu(lin(e.concat_cols({c0, c1}), P + "content.Q.0", 256));
-            TT co = e.attn_context(e.softmax(e.attn_scores(e.scale_param(cq, ctemp), ckey, minT)), cval, minT);
-            TT x = e.concat_cols({co, y});
+            e.add(p2, o, &xy_y);
+            TT cq = e.silu(lin(cc_prev, P + "content.Q.0", 256));
+            e.attn_context(e.softmax(e.attn_scores(e.scale_param(cq, ctemp), ckey, minT)), cval, minT, &xy_c);
             TT h0n, c0n, h1n, c1n;
-            e.lstm_cell(e.add(e.linear(x, Wih0, &bih0), e.linear(h0, Whh0, &bhh0)), c0, h0n, c0n);
-            TT h0d = e.dropout(h0n, io.lstm + (size_t)i * B * 512, 512, 0.1f);            // nn.LSTM(dropout=0.1): layer 1's input only
-            e.lstm_cell(e.add(e.linear(h0d, Wih1, &bih1), e.linear(h1, Whh1, &bhh1)), c1, h1n, c1n);
-            h0 = h0n; c0 = c0n; h1 = h1n; c1 = c1n;
-            ys = lin(h1, P + "fc_out.linear_layer", 80);
-            assign(e, outputs.rowslice(i, B, M), ys);
-            assign(e, stops.rowslice(i, B, M), lin(e.concat_cols({h1, enc_cell}), P + "stop_token_layer.linear_layer", 1));
+            TT h0dst = hh.colslice(0, 512), c0dst = cc.colslice(0, 512), h1dst = hh.colslice(512, 512), c1dst = cc.colslice(512, 512);
+            TT g0 = e.linear(xy, Wih0, &bih0);
+            e.linear(hh_prev.colslice(0, 512), Whh0, &bhh0, &g0, true);
+            e.lstm_cell(g0, cc_prev.colslice(0, 512), h0n, c0n, &h0dst, &c0dst);
+            TT h0d = e.dropout(h0n, io.lstm + (size_t)i * B * 512, 512, 0.1f);                 // nn.LSTM(dropout=0.1): layer 1's input only
+            TT g1 = e.linear(h0d, Wih1, &bih1);
+            e.linear(hh_prev.colslice(512, 512), Whh1, &bhh1, &g1, true);
+            e.lstm_cell(g1, cc_prev.colslice(512, 512), h1n, c1n, &h1dst, &c1dst);
+            TT ydst = outputs.rowslice(i, B, M);
+            ys = e.linear(h1n, Wfc, &bfc, &ydst);                   // straight into row (b, i) of the output
+            hh_prev = hh; cc_prev = cc;
+        }
+        {   // stop-token logits of all steps at once: they feed nothing inside the loop (decoder.py:373)
+            TT Wst = e.param(P + "stop_token_layer.linear_layer.weight", 1, 1024), bst = e.param(P + "stop_token_layer.linear_layer.bias", 1, 1);
+            TT Wst_h = Wst.colslice(0, 512), Wst_c = Wst.colslice(512, 512);
+            TT per_step = e.linear(HH.colslice(512, 512), Wst_h, nullptr);                     // [M*B, 1], rows (step, clip)
+            TT per_clip = e.linear(enc_cell, Wst_c, &bst);                                     // [B, 1]
+            stop_combine_kernel<<<ew_blocks((size_t)B * M), 256, 0, s>>>(B, M, per_step.v, per_clip.v, stops.v);
+            e.ck("stop combine");
+            Engine* pe = &e; const int Bc = B, Mc = M; TT st = stops;
+            e.tape.push_back([=]() {
+                stop_combine_bwd_kernel<<<ew_blocks((size_t)Bc * Mc), 256, 0, pe->s>>>(Bc, Mc, st.g, per_step.g, per_clip.g);
+                pe->ck("stop combine bwd");
+            });
         }
         // ---- postnet (decoder.py:143-156, 377-378) -------------------------------------------------------------------------
         {

@@ -74,15 +74,30 @@ class TrainNoise:
 
 
 def _bind_params(be, tag, keys, params):
-    """Bind the parameters and ONE persistent flat gradient buffer per (backend, module kind): the addresses the library sees
-    stay the same from step to step, which is what lets it replay its captured launch graphs.  Re-binds only when something moved."""
+    """Bind parameter and gradient memory at addresses that stay the same from step to step (what lets the library replay its
+    captured launch graphs); re-binds only when something moved.  Two modes:
+    direct  — every trainable parameter already has a dense fp32 .grad (e.g. ClipAdamW's flat buffer, or any optimizer after
+              zero_grad(set_to_none=False)): the backward pass accumulates straight into p.grad, as AccumulateGrad would, and the
+              autograd node returns no parameter gradients (saves one add kernel per parameter);
+    scratch — otherwise: one persistent flat buffer per (backend, module kind); backward hands autograd views of a copy.
+    Returns (scratch or None, offsets, sizes)."""
+    def dense(p):
+        g = p.grad
+        return g is not None and g.dtype == torch.float32 and g.device == p.device and g.is_contiguous() and g.shape == p.shape
+    cache = be.__dict__.setdefault("_train_grads", {})
+    hit = cache.get(tag)
+    if all((not p.requires_grad) or dense(p) for p in params):
+        sig = ("direct", tuple(keys), tuple(p.data_ptr() for p in params), tuple(p.grad.data_ptr() if p.requires_grad else 0 for p in params))
+        if hit is None or hit[0] != sig:
+            for k, p in zip(keys, params):
+                be.train_bind(k, p.detach(), p.grad if p.requires_grad else None)
+            cache[tag] = (sig, None)
+        return None, None, None
     sizes = [p.numel() for p in params]
     offs, total = [], 0
     for n in sizes:
         offs.append(total); total += (n + 3) // 4 * 4
-    cache = be.__dict__.setdefault("_train_grads", {})
-    sig = (tuple(keys), tuple(p.data_ptr() for p in params))
-    hit = cache.get(tag)
+    sig = ("scratch", tuple(keys), tuple(p.data_ptr() for p in params))
     if hit is None or hit[0] != sig:
         scratch = torch.zeros(total, device=params[0].device)
         for k, p, o, n in zip(keys, params, offs, sizes):
@@ -93,7 +108,9 @@ def _bind_params(be, tag, keys, params):
 
 def _grad_views(scratch, offs, sizes, params):
     """Fresh storage for what autograd receives (AccumulateGrad may keep the tensor as p.grad; the persistent buffer is rewritten
-    by the next backward)."""
+    by the next backward).  Direct mode: the gradients are already in p.grad."""
+    if scratch is None:
+        return [None] * len(params)
     out = scratch.clone()
     return [out[o:o + n].view_as(p) for o, n, p in zip(offs, sizes, params)]
 
@@ -113,7 +130,8 @@ class _DecoderTrainFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_mel, g_post, g_stop, g_attn, g_dis):
-        ctx.scratch.zero_()
+        if ctx.scratch is not None:
+            ctx.scratch.zero_()
         g_visual, g_spk = ctx.be.decoder_train_bwd(g_mel, g_post, g_stop, g_dis, *ctx.BT)
         return (None, None, None, g_visual, g_spk, None, *_grad_views(ctx.scratch, *ctx.layout, ctx.params))
 
@@ -129,7 +147,8 @@ class _VideoTrainFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_feat):
-        ctx.scratch.zero_()
+        if ctx.scratch is not None:
+            ctx.scratch.zero_()
         ctx.be.video_train_bwd(g_feat)
         return (None, None, None, None, *_grad_views(ctx.scratch, *ctx.layout, ctx.params))
 
