@@ -172,9 +172,14 @@ __device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) 
 // Few-row GEMM, second form: the CTA first stages ALL of A (M x K, M <= MT) in shared memory, each warp owns NW weight rows and
 // issues every 16-byte weight load of a 512-wide k chunk before it touches them (4 MB of LSTM weights are in flight at once
 // instead of two loads per warp), NW * MT = 32 accumulators per lane are reduced with warp_transpose_sum32.
+// A second operand pair (A2 [M,K2], W2 [N,K2], bias2) is treated as a continuation of the reduction: C = A W^T + A2 W2^T + bias +
+// bias2 in one launch (the two halves of the LSTM gate pre-activation, x W_ih^T + h W_hh^T).  K2 = 0: single product.
 template <int NW, int MT>
-__global__ void __launch_bounds__(256) skinny_nt_smem_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
-                                                             const float* __restrict__ bias, float* __restrict__ C, int ldc, int accumulate) {
+__global__ void __launch_bounds__(256) skinny_nt_smem_kernel(int M, int N, int K1, const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
+                                                             const float* __restrict__ bias, int K2, const float* __restrict__ A2, int lda2,
+                                                             const float* __restrict__ W2, int ldw2, const float* __restrict__ bias2,
+                                                             float* __restrict__ C, int ldc, int accumulate) {
+    const int K = K1 + K2;
     static_assert(NW * MT == 32, "one output per lane");
     extern __shared__ float4 xs4[];                                   // [MT][K/4], rows >= M are zero
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -187,13 +192,15 @@ __global__ void __launch_bounds__(256) skinny_nt_smem_kernel(int M, int N, int K
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int k = kc + 128 * j + 4 * lane;
-                wv[n][j] = (n0 + n < N && k < K) ? *reinterpret_cast<const float4*>(W + (size_t)(n0 + n) * ldw + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float* src = k < K1 ? W + (size_t)(n0 + n) * ldw + k : W2 + (size_t)(n0 + n) * ldw2 + (k - K1);
+                wv[n][j] = (n0 + n < N && k < K) ? *reinterpret_cast<const float4*>(src) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
     };
     load_w(0);
     for (int i = threadIdx.x; i < MT * K4; i += 256) {
         const int m = i / K4, q = i - m * K4;
-        xs4[i] = m < M ? *reinterpret_cast<const float4*>(A + (size_t)m * lda + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* src = 4 * q < K1 ? A + (size_t)m * lda + 4 * q : A2 + (size_t)m * lda2 + (4 * q - K1);
+        xs4[i] = m < M ? *reinterpret_cast<const float4*>(src) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
     float acc[32];
@@ -222,7 +229,7 @@ __global__ void __launch_bounds__(256) skinny_nt_smem_kernel(int M, int N, int K
     const int n = n0 + lane / MT, m = lane % MT;
     if (n < N && m < M) {
         float* c = C + (size_t)m * ldc + n;
-        const float r = v + (bias ? bias[n] : 0.f);
+        const float r = v + (bias ? bias[n] : 0.f) + (bias2 ? bias2[n] : 0.f);
         *c = accumulate ? *c + r : r;
     }
 }
@@ -232,9 +239,13 @@ __global__ void __launch_bounds__(256) skinny_nt_smem_kernel(int M, int N, int K
 // interleave the rows; every lane keeps two batches of 8 weight loads in flight (ping-pong) while dy — staged once in shared
 // memory, transposed to [n][m] — feeds the FMAs.  The 8 row-lanes are folded with shuffles, the 8 warps through shared memory in
 // index order: deterministic.  (The two-stage form below needed two launches and 64 dependent partial reads per output.)
+// gridDim.y = 2: a second problem (W2, K2, dX2) that shares dy (the two operands of one pre-activation).
 template <int MT>
 __global__ void __launch_bounds__(256) skinny_nn_strip_kernel(int M, int N, int K, const float* __restrict__ dY, int ldy, const float* __restrict__ W, int ldw,
-                                                              float* __restrict__ dX, int ldx) {
+                                                              float* __restrict__ dX, int ldx, int K2, const float* __restrict__ W2, int ldw2,
+                                                              float* __restrict__ dX2, int ldx2) {
+    if (blockIdx.y == 1) { K = K2; W = W2; ldw = ldw2; dX = dX2; ldx = ldx2; }
+    if ((int)blockIdx.x * 16 >= K) return;
     extern __shared__ float4 nn_sm4[];
     float* dys = reinterpret_cast<float*>(nn_sm4);                   // [Npad][MT]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -644,6 +655,153 @@ __global__ void __launch_bounds__(256) attn_context_bwd_kernel(int B, int T, int
     if (lane == 0 && dA) dA[(size_t)b * das + t] += s;
 }
 
+// ---- kernels: one decoder-step attention in one launch -----------------------------------------------------------------------
+// One CTA per clip b: s_t = (w q_b) . K_{b,t}  ->  (x keep-mask / (1-p))  ->  softmax over t  ->  ctx_b = sum_t a_t V_{b,t}
+// (decoder.py:360-364 with the logit dropout, 262-271 without).  Saved for the backward pass: the probabilities a and the
+// unscaled products q . K_t (the derivative with respect to the learnable temperature w).  logits (optional): the post-dropout
+// scores, written straight into the caller-visible [B][M][T] tensor.  T <= 320.
+__global__ void __launch_bounds__(256) attn_step_fwd_kernel(int T, int D, int DV, const float* __restrict__ w, const float* __restrict__ Q, int qs,
+                                                            const float* __restrict__ Km, int ks, const float* __restrict__ mask, float alpha,
+                                                            const float* __restrict__ V, int vs, float* __restrict__ sraw, float* __restrict__ A,
+                                                            float* __restrict__ logits, int ls, float* __restrict__ C, int cs) {
+    __shared__ float sc[320];
+    __shared__ float red[2];
+    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float wv = w[0];
+    const float* q = Q + (size_t)b * qs;
+    for (int t = warp; t < T; t += 8) {
+        const float* kr = Km + (size_t)(b * T + t) * ks;
+        float a = 0.f, raw = 0.f;
+        for (int k = lane; k < D; k += 32) { const float qv = q[k], kv = kr[k]; a = fmaf(qv * wv, kv, a); raw = fmaf(qv, kv, raw); }
+        a = warp_sum(a); raw = warp_sum(raw);
+        if (lane == 0) {
+            if (mask) a *= mask[(size_t)b * T + t] * alpha;
+            sc[t] = a;
+            sraw[(size_t)b * T + t] = raw;
+            if (logits) logits[(size_t)b * ls + t] = a;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        float mx = -INFINITY;
+        for (int t = lane; t < T; t += 32) mx = fmaxf(mx, sc[t]);
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int t = lane; t < T; t += 32) sum += expf(sc[t] - mx);
+        sum = warp_sum(sum);
+        if (lane == 0) { red[0] = mx; red[1] = sum; }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += 256) {
+        const float a = expf(sc[t] - red[0]) / red[1];
+        sc[t] = a;
+        A[(size_t)b * T + t] = a;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < DV; k += 256) {
+        float acc = 0.f;
+        for (int t = 0; t < T; ++t) acc = fmaf(sc[t], V[(size_t)(b * T + t) * vs + k], acc);
+        C[(size_t)b * cs + k] = acc;
+    }
+}
+// Backward of the above for clip b = blockIdx.x: dV += a dC^T; da = V dC; softmax and dropout backward; dw partial (one float per
+// clip, summed later in a fixed order); dq += w K^T ds; dK += ds (w q)^T.
+__global__ void __launch_bounds__(256) attn_step_bwd_kernel(int T, int D, int DV, const float* __restrict__ w, const float* __restrict__ Q, int qs,
+                                                            const float* __restrict__ Km, int ks, const float* __restrict__ mask, float alpha,
+                                                            const float* __restrict__ V, int vs, const float* __restrict__ sraw, const float* __restrict__ A,
+                                                            const float* __restrict__ dC, int dcs, float* __restrict__ dQ, int dqs, float* __restrict__ dK, int dks,
+                                                            float* __restrict__ dV, int dvs, float* __restrict__ dwpart) {
+    __shared__ float da[320];
+    __shared__ float ds[320];
+    __shared__ float red[1];
+    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float wv = w[0];
+    const float* dc = dC + (size_t)b * dcs;
+    for (int t = warp; t < T; t += 8) {
+        const float a = A[(size_t)b * T + t];
+        const float* vr = V + (size_t)(b * T + t) * vs;
+        float acc = 0.f;
+        for (int k = lane; k < DV; k += 32) {
+            const float d = dc[k];
+            acc = fmaf(d, vr[k], acc);
+            if (dV) dV[(size_t)(b * T + t) * dvs + k] += a * d;
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) da[t] = acc;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        float s = 0.f;
+        for (int t = lane; t < T; t += 32) s = fmaf(da[t], A[(size_t)b * T + t], s);
+        s = warp_sum(s);
+        if (lane == 0) red[0] = s;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += 256) {
+        float g = A[(size_t)b * T + t] * (da[t] - red[0]);
+        if (mask) g *= mask[(size_t)b * T + t] * alpha;
+        ds[t] = g;
+    }
+    __syncthreads();
+    if (warp == 0 && dwpart) {
+        float s = 0.f;
+        for (int t = lane; t < T; t += 32) s = fmaf(ds[t], sraw[(size_t)b * T + t], s);
+        s = warp_sum(s);
+        if (lane == 0) dwpart[b] = s;
+    }
+    const float* q = Q + (size_t)b * qs;
+    for (int k = threadIdx.x; k < D; k += 256) {
+        const float qw = q[k] * wv;
+        float acc = 0.f;
+        for (int t = 0; t < T; ++t) {
+            const float g = ds[t];
+            acc = fmaf(g, Km[(size_t)(b * T + t) * ks + k], acc);
+            if (dK) dK[(size_t)(b * T + t) * dks + k] += g * qw;
+        }
+        if (dQ) dQ[(size_t)b * dqs + k] += acc * wv;
+    }
+}
+// out[0] += sum over a list of R arrays of n floats, in list order (the per-step, per-clip temperature-gradient partials)
+__global__ void __launch_bounds__(256) sum_list_kernel(int R, int n, const float* const* __restrict__ list, float* __restrict__ out) {
+    __shared__ float part[8];
+    float a = 0.f;
+    for (int i = threadIdx.x; i < R * n; i += 256) a += list[i / n][i % n];
+    a = warp_sum(a);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) { float t = 0.f; for (int i = 0; i < 8; ++i) t += part[i]; out[0] += t; }
+}
+
+// y = psine_w(x) [* keep-mask * alpha] [+ constant]: the activation, the dropout and the positional term that follow a per-step
+// linear, in one pass (prenet: decoder.py:306-309; query: :359-360).
+__global__ void psine_chain_fwd_kernel(int rows, int cols, const float* __restrict__ X, int xs, const float* __restrict__ w, const float* __restrict__ mask, int ms,
+                                       float alpha, const float* __restrict__ addc, int as, float* __restrict__ Y, int ys) {
+    TR_EW_LOOP((size_t)rows * cols) {
+        const int r = i / cols, c = i % cols;
+        float y = sinf(X[(size_t)r * xs + c]) * w[c];
+        if (mask) y *= mask[(size_t)r * ms + c] * alpha;
+        if (addc) y += addc[(size_t)r * as + c];
+        Y[(size_t)r * ys + c] = y;
+    }
+}
+// thread per column: dx += dy m cos(x) w ; dw[c] += sum_r dy m sin(x)   (few rows: the sum is a short serial loop, deterministic)
+__global__ void psine_chain_bwd_kernel(int rows, int cols, const float* __restrict__ X, int xs, const float* __restrict__ w, const float* __restrict__ mask, int ms,
+                                       float alpha, const float* __restrict__ dY, int dys, float* __restrict__ dX, int dxs, float* __restrict__ dw) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    const float wc = w[c];
+    float acc = 0.f;
+    for (int r = 0; r < rows; ++r) {
+        float g = dY[(size_t)r * dys + c];
+        if (mask) g *= mask[(size_t)r * ms + c] * alpha;
+        float sn, cs;
+        sincosf(X[(size_t)r * xs + c], &sn, &cs);
+        if (dX) dX[(size_t)r * dxs + c] += g * cs * wc;
+        acc = fmaf(g, sn, acc);
+    }
+    if (dw) dw[c] += acc;
+}
+
 // ---- kernels: LSTM cell (gate order i, f, g, o) -------------------------------------------------------------
 // gates [B][4H] (pre-activation) + c_prev [B][H] -> act [B][4H] (sigmoid/tanh applied, saved for backward), c [B][H], h [B][H]
 __global__ void lstm_cell_fwd_kernel(int B, int H, const float* __restrict__ G, int gs, const float* __restrict__ Cp, int cps,
@@ -983,39 +1141,56 @@ __global__ void dw3x3_dgrad_kernel(int N, int H, int W, int C, int s, int Ho, in
         dX[(size_t)((n * H + h) * W + w) * dxs + c] += a;
     }
 }
-// part[split][tap][c] = sum over the split's output positions of dY * x(tap)   — grid (ceil(C/32), 9, splits), 8 row lanes x 32
-// channels, fixed order; dw3x3_wfinish_kernel adds the splits into dW[c][tap]
+// part[split][tap][c] = sum over the split's output positions of dY * x(tap)   — grid (ceil(C/32), splits), 8 row lanes x 32
+// channels, fixed order; every thread keeps the nine taps of its channel (dY is read once per position, not once per tap);
+// dw3x3_wfinish_kernel adds the splits into dW[c][tap]
 __global__ void __launch_bounds__(256) dw3x3_wgrad_kernel(int N, int H, int W, int C, int s, int Ho, int Wo, const float* __restrict__ X, int xs,
                                                           const float* __restrict__ dY, int dys, float* __restrict__ part) {
-    __shared__ float red[8][33];
+    __shared__ float red[9][8][33];
     const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + cl, tap = blockIdx.y, kh = tap / 3, kw = tap % 3;
+    const int c = blockIdx.x * 32 + cl;
     const int rows = N * Ho * Wo;
-    const int per = (rows + gridDim.z - 1) / gridDim.z;
-    const int r0 = blockIdx.z * per, r1 = min(rows, r0 + per);
-    float a = 0.f;
+    const int per = (rows + gridDim.y - 1) / gridDim.y;
+    const int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
+    float a[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) a[t] = 0.f;
     if (c < C)
         for (int r = r0 + rl; r < r1; r += 8) {
             const int wo = r % Wo, ho = (r / Wo) % Ho, n = r / (Wo * Ho);
-            const int h = ho * s + kh - 1, w = wo * s + kw - 1;
-            if (h < 0 || h >= H || w < 0 || w >= W) continue;
-            a = fmaf(dY[(size_t)r * dys + c], X[(size_t)((n * H + h) * W + w) * xs + c], a);
+            const float dy = dY[(size_t)r * dys + c];
+            const float* xn = X + (size_t)n * H * W * xs + c;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+                const int h = ho * s + kh - 1;
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const int w = wo * s + kw - 1;
+                    const bool ok = h >= 0 && h < H && w >= 0 && w < W;
+                    const float x = ok ? xn[(size_t)(h * W + w) * xs] : 0.f;
+                    a[kh * 3 + kw] = fmaf(dy, x, a[kh * 3 + kw]);
+                }
+            }
         }
-    red[rl][cl] = a;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) red[t][rl][cl] = a[t];
     __syncthreads();
-    if (rl == 0 && c < C) {
-        float t = 0.f;
-        for (int i = 0; i < 8; ++i) t += red[i][cl];
-        part[((size_t)blockIdx.z * 9 + tap) * C + c] = t;
-    }
+    for (int t = rl; t < 9; t += 8)
+        if (c < C) {
+            float v = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v += red[t][i][cl];
+            part[((size_t)blockIdx.y * 9 + t) * C + c] = v;
+        }
 }
 __global__ void dw3x3_wfinish_kernel(int C, int splits, const float* __restrict__ part, float* __restrict__ dW) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;       // one warp per (tap, channel)
     if (i >= 9 * C) return;
     const int tap = i / C, c = i % C;
     float t = 0.f;
-    for (int z = 0; z < splits; ++z) t += part[((size_t)z * 9 + tap) * C + c];
-    dW[c * 9 + tap] += t;
+    for (int z = lane; z < splits; z += 32) t += part[((size_t)z * 9 + tap) * C + c];
+    t = warp_sum(t);
+    if (lane == 0) dW[c * 9 + tap] += t;
 }
 // y[:, 2j] = a[:, j], y[:, 2j+1] = b[:, j]   (torch.cat + channel_shuffle(groups=2), shufflenetv2.py:26-40,92-104)
 __global__ void interleave2_fwd_kernel(int rows, int half, const float* __restrict__ A, int as, const float* __restrict__ Bm, int bs, float* __restrict__ Y, int ys) {
@@ -1168,7 +1343,7 @@ struct Engine {
     void release() { vals.free_all(); grads.free_all(); if (counters) cudaFree(counters); counters = nullptr; }
     void begin(Context* c, cudaStream_t stream, std::map<std::string, Param>* p) {
         ctx = c; s = stream; params = p; launches = &c->launches;
-        vals.reset(); grads.reset(); tape.clear(); deferred.clear();
+        vals.reset(); grads.reset(); tape.clear(); deferred.clear(); deferred_scalar.clear(); deferred_scalar_n.clear();
     }
     void ck(const char* what) {
         cudaError_t e = cudaGetLastError();
@@ -1221,6 +1396,8 @@ struct Engine {
     // ---- deferred weight gradients of the per-step (few-row) linears ---------------------------------------------------------
     struct Deferred { TT W; float* db = nullptr; std::vector<const float*> a, b; };
     std::map<float*, Deferred> deferred;
+    std::map<float*, std::vector<const float*>> deferred_scalar;      // scalar parameter gradient <- list of partial arrays
+    std::map<float*, int> deferred_scalar_n;
     void flush_deferred() {
         table_bytes = 0;
         for (auto& kv : deferred) {
@@ -1241,9 +1418,22 @@ struct Engine {
             sgemm_tn_rows_kernel<<<dim3((K + 63) / 64, (N + 63) / 64), 256, 0, s>>>(N, K, R, tab, tab + R, d.W.g, d.W.rs, d.db);
             ck("deferred weight gradient");
         }
+        for (auto& kv : deferred_scalar) {
+            const int R = (int)kv.second.size();
+            const size_t bytes = (size_t)R * sizeof(float*);
+            const float** tab = reinterpret_cast<const float**>(scratch((size_t)R * 2));
+            if (capturing) {
+                char* host = static_cast<char*>(tables->take(bytes));
+                memcpy(host, kv.second.data(), bytes);
+                L2S_CUDA(cudaMemcpyAsync(tab, host, bytes, cudaMemcpyHostToDevice, s));
+            } else L2S_CUDA(cudaMemcpyAsync(tab, kv.second.data(), bytes, cudaMemcpyHostToDevice, s));
+            table_bytes += bytes + 16;
+            sum_list_kernel<<<1, 256, 0, s>>>(R, deferred_scalar_n[kv.first], tab, kv.first);
+            ck("deferred scalar gradient");
+        }
         // eager: the host pointer tables must outlive the asynchronous copies
         if (!capturing) L2S_CUDA(cudaStreamSynchronize(s));
-        deferred.clear();
+        deferred.clear(); deferred_scalar.clear(); deferred_scalar_n.clear();
     }
 
     // ---- GEMM helpers ----------------------------------------------------------------------------------------------------
@@ -1283,8 +1473,8 @@ struct Engine {
             const int MT = R <= 8 ? 8 : 16;
             const size_t smem = (size_t)MT * K * sizeof(float);
             if (vec && smem <= (size_t)SKINNY_SMEM_MAX) {
-                if (MT == 8) skinny_nt_smem_kernel<4, 8><<<(N + 31) / 32, 256, smem, s>>>(R, N, K, x.v, x.rs, W.v, W.rs, b ? b->v : nullptr, y.v, y.rs, accf);
-                else skinny_nt_smem_kernel<2, 16><<<(N + 15) / 16, 256, smem, s>>>(R, N, K, x.v, x.rs, W.v, W.rs, b ? b->v : nullptr, y.v, y.rs, accf);
+                if (MT == 8) skinny_nt_smem_kernel<4, 8><<<(N + 31) / 32, 256, smem, s>>>(R, N, K, x.v, x.rs, W.v, W.rs, b ? b->v : nullptr, 0, nullptr, 0, nullptr, 0, nullptr, y.v, y.rs, accf);
+                else skinny_nt_smem_kernel<2, 16><<<(N + 15) / 16, 256, smem, s>>>(R, N, K, x.v, x.rs, W.v, W.rs, b ? b->v : nullptr, 0, nullptr, 0, nullptr, 0, nullptr, y.v, y.rs, accf);
             } else if (vec) skinny_nt_kernel<true><<<(N * 32 + 255) / 256, 256, 0, s>>>(R, N, K, x.v, x.rs, W.v, W.rs, b ? b->v : nullptr, y.v, y.rs, accf);
             else skinny_nt_kernel<false><<<(N * 32 + 255) / 256, 256, 0, s>>>(R, N, K, x.v, x.rs, W.v, W.rs, b ? b->v : nullptr, y.v, y.rs, accf);
             ck("skinny_nt");
@@ -1311,8 +1501,8 @@ struct Engine {
                 if (R <= 16 && vecb) {
                     const int MT = R <= 8 ? 8 : 16;
                     const size_t smem = (size_t)std::max((N + 63) / 64 * 64, 128) * MT * sizeof(float);      // >= the [8][MT][16] cross-warp buffer
-                    if (MT == 8) skinny_nn_strip_kernel<8><<<(K + 15) / 16, 256, smem, s>>>(R, N, K, y.g, y.rs, W.v, W.rs, x.g, x.rs);
-                    else skinny_nn_strip_kernel<16><<<(K + 15) / 16, 256, smem, s>>>(R, N, K, y.g, y.rs, W.v, W.rs, x.g, x.rs);
+                    if (MT == 8) skinny_nn_strip_kernel<8><<<(K + 15) / 16, 256, smem, s>>>(R, N, K, y.g, y.rs, W.v, W.rs, x.g, x.rs, 0, nullptr, 0, nullptr, 0);
+                    else skinny_nn_strip_kernel<16><<<(K + 15) / 16, 256, smem, s>>>(R, N, K, y.g, y.rs, W.v, W.rs, x.g, x.rs, 0, nullptr, 0, nullptr, 0);
                     ck("skinny_nn strip");
                 } else if (R <= 16) {
                     const int nslice = 128, nslices = (N + nslice - 1) / nslice;
@@ -1325,6 +1515,43 @@ struct Engine {
             }
             if (W.g && !defer) gemm<1, 0>(N, K, R, y.g, y.rs, x.v, x.rs, W.g, W.rs, true);
             if (hasb && bb.g && !defer) colred<COL_SUM>(R, N, y.g, y.rs, nullptr, 0, nullptr, nullptr, 0.f, 1.f, bb.g, true);
+        });
+        return y;
+    }
+    // y = x1 W1^T + b1 + x2 W2^T + b2 in one launch forward and one launch backward when the rows are few (the LSTM gates of one
+    // step: input and recurrent product, nn.LSTM's b_ih + b_hh); otherwise two accumulating linears.
+    TT linear2(const TT& x1, const TT& W1, const TT* b1, const TT& x2, const TT& W2, const TT* b2, const TT* dst = nullptr) {
+        const int R = x1.rows, K1 = x1.cols, K2 = x2.cols, N = W1.rows;
+        auto aligned = [](const TT& x, const TT& W) {
+            return !(x.cols & 3) && !(x.rs & 3) && !(W.rs & 3) && !((reinterpret_cast<uintptr_t>(x.v) | reinterpret_cast<uintptr_t>(W.v)) & 15);
+        };
+        const int MT = R <= 8 ? 8 : 16;
+        const size_t smem = (size_t)MT * (K1 + K2) * sizeof(float);
+        const size_t smemb = (size_t)std::max((N + 63) / 64 * 64, 128) * MT * sizeof(float);
+        const bool fused = R <= 16 && x2.rows == R && W2.rows == N && W1.cols == K1 && W2.cols == K2 && aligned(x1, W1) && aligned(x2, W2) &&
+                           smem <= (size_t)SKINNY_SMEM_MAX && smemb <= (size_t)SKINNY_SMEM_MAX && x1.g && x2.g && W1.g && W2.g;
+        if (!fused) {
+            TT y = linear(x1, W1, b1, dst);
+            linear(x2, W2, b2, &y, true);
+            return y;
+        }
+        TT y = dst ? *dst : make(R, N);
+        const float* bv1 = b1 ? b1->v : nullptr; const float* bv2 = b2 ? b2->v : nullptr;
+        if (MT == 8) skinny_nt_smem_kernel<4, 8><<<(N + 31) / 32, 256, smem, s>>>(R, N, K1, x1.v, x1.rs, W1.v, W1.rs, bv1, K2, x2.v, x2.rs, W2.v, W2.rs, bv2, y.v, y.rs, 0);
+        else skinny_nt_smem_kernel<2, 16><<<(N + 15) / 16, 256, smem, s>>>(R, N, K1, x1.v, x1.rs, W1.v, W1.rs, bv1, K2, x2.v, x2.rs, W2.v, W2.rs, bv2, y.v, y.rs, 0);
+        ck("skinny_nt x2");
+        for (int which = 0; which < 2; ++which) {
+            const TT& x = which ? x2 : x1; const TT& W = which ? W2 : W1; const TT* b = which ? b2 : b1;
+            Deferred& d = deferred[W.g];
+            d.W = W;
+            if (b && b->g) d.db = b->g;
+            for (int r = 0; r < R; ++r) { d.a.push_back(y.g + (size_t)r * y.rs); d.b.push_back(x.v + (size_t)r * x.rs); }
+        }
+        tape.push_back([=]() {
+            const dim3 grid((std::max(K1, K2) + 15) / 16, 2);
+            if (MT == 8) skinny_nn_strip_kernel<8><<<grid, 256, smemb, s>>>(R, N, K1, y.g, y.rs, W1.v, W1.rs, x1.g, x1.rs, K2, W2.v, W2.rs, x2.g, x2.rs);
+            else skinny_nn_strip_kernel<16><<<grid, 256, smemb, s>>>(R, N, K1, y.g, y.rs, W1.v, W1.rs, x1.g, x1.rs, K2, W2.v, W2.rs, x2.g, x2.rs);
+            ck("skinny_nn strip x2");
         });
         return y;
     }
@@ -1499,6 +1726,45 @@ struct Engine {
         return y;
     }
 
+    // One attention read-out of a decoder step in one launch each way (see attn_step_fwd_kernel).  w: the learnable scalar
+    // temperature; mask (optional): keep mask [B,T] of the logit dropout with scale alpha; logits (optional): caller-visible
+    // copy of the post-dropout scores, row stride ls.
+    TT attn_step(const TT& q, const TT& w, const TT& Km, const TT& V, int T, const float* mask, float alpha, float* logits, int ls, const TT* dst = nullptr) {
+        const int B = q.rows, D = q.cols, DV = V.cols;
+        if (T > 320) throw L2sError(1, "train: attention over more than 320 positions");
+        TT y = dst ? *dst : make(B, DV);
+        float* sraw = scratch((size_t)B * T); float* probs = scratch((size_t)B * T);
+        attn_step_fwd_kernel<<<B, 256, 0, s>>>(T, D, DV, w.v, q.v, q.rs, Km.v, Km.rs, mask, alpha, V.v, V.rs, sraw, probs, logits, ls, y.v, y.rs);
+        ck("attention step");
+        tape.push_back([=]() {
+            float* dwp = nullptr;
+            if (w.g) { dwp = scratch(B); deferred_scalar[w.g].push_back(dwp); deferred_scalar_n[w.g] = B; }
+            attn_step_bwd_kernel<<<B, 256, 0, s>>>(T, D, DV, w.v, q.v, q.rs, Km.v, Km.rs, mask, alpha, V.v, V.rs, sraw, probs, y.g, y.rs, q.g, q.rs, Km.g, Km.rs,
+                                                   V.g, V.rs, dwp);
+            ck("attention step bwd");
+        });
+        return y;
+    }
+    // psine (+ dropout) (+ constant) after a few-row linear, one launch each way; the PSine weight gradient is formed in the
+    // same backward launch (rows <= 16).
+    TT psine_chain(const TT& x, const TT& w, const float* mask, int ms, float p, const float* addc, int as) {
+        if (x.rows > 16) {
+            TT y = psine(x, w);
+            if (mask) y = dropout(y, mask, ms, p);
+            if (addc) y = add_const(y, addc, as);
+            return y;
+        }
+        const float alpha = 1.0f / (1.0f - p);
+        TT y = make(x.rows, x.cols);
+        psine_chain_fwd_kernel<<<ew_blocks(x.numel()), 256, 0, s>>>(x.rows, x.cols, x.v, x.rs, w.v, mask, ms, alpha, addc, as, y.v, y.rs);
+        ck("psine chain");
+        tape.push_back([=]() {
+            psine_chain_bwd_kernel<<<(x.cols + 127) / 128, 128, 0, s>>>(x.rows, x.cols, x.v, x.rs, w.v, mask, ms, alpha, y.g, y.rs, x.g, x.rs, w.g);
+            ck("psine chain bwd");
+        });
+        return y;
+    }
+
     // LSTM cell on pre-activation gates [B,4H] and previous cell state; returns (h, c)
     void lstm_cell(const TT& gates, const TT& cprev, TT& h, TT& c, const TT* hdst = nullptr, const TT* cdst = nullptr) {
         const int B = gates.rows, H = gates.cols / 4;
@@ -1576,11 +1842,12 @@ struct Engine {
         tape.push_back([=]() {
             if (x.g) { dw3x3_dgrad_kernel<<<ew_blocks((size_t)N * H * W * C), 256, 0, s>>>(N, H, W, C, stride, Ho, Wo, y.g, y.rs, Wt.v, x.g, x.rs); ck("dw dgrad"); }
             if (Wt.g) {
-                const int rows = N * Ho * Wo, splits = std::max(1, std::min(64, rows / 2048));
+                const int rows = N * Ho * Wo, colblocks = (C + 31) / 32;
+                const int splits = std::max(1, std::min(std::min(1024, (148 * 8 + colblocks - 1) / colblocks), rows / 64));
                 float* part = scratch((size_t)splits * 9 * C);
-                dw3x3_wgrad_kernel<<<dim3((C + 31) / 32, 9, splits), 256, 0, s>>>(N, H, W, C, stride, Ho, Wo, x.v, x.rs, y.g, y.rs, part);
+                dw3x3_wgrad_kernel<<<dim3(colblocks, splits), 256, 0, s>>>(N, H, W, C, stride, Ho, Wo, x.v, x.rs, y.g, y.rs, part);
                 ck("dw wgrad");
-                dw3x3_wfinish_kernel<<<(9 * C + 255) / 256, 256, 0, s>>>(C, splits, part, Wt.g);
+                dw3x3_wfinish_kernel<<<(9 * C * 32 + 255) / 256, 256, 0, s>>>(C, splits, part, Wt.g);
                 ck("dw wgrad finish");
             }
         });

@@ -257,30 +257,23 @@ struct DecoderTrain {
         for (int i = 0; i < M; ++i) {
             TT hh = HH.rowslice(i * B, B), cc = CC.rowslice(i * B, B);
             if (i > 0) ys = e.select(io.tf + i, mel_rows.rowslice(i - 1, B, M), ys);            // teacher_input[:, i] or the previous output (355-357)
-            TT p1 = e.psine(lin(ys, P + "prenet.0.linear_layer", 256), p1w);
-            TT p1d = e.dropout(p1, io.prenet + (size_t)i * B * 256, 256, 0.2f);
-            TT p2 = e.psine(lin(p1d, P + "prenet.3.linear_layer", 256), p4w);
-            TT q = e.add_const(e.psine(lin(hh_prev, P + "Q.0.linear_layer", 512), Wq_w), pos + (size_t)i * 512, 0);
-            TT a = e.dropout(e.attn_scores(e.scale_param(q, temp), Kmem, T), io.attn + (size_t)i * B * T, T, 0.1f);
-            if (want_logits) {
-                // rows b of a -> out[b][i][:]
-                ew_fwd_kernel<EW_COPY><<<ew_blocks(a.numel()), 256, 0, s>>>(B, T, a.v, a.rs, nullptr, 0, 0.f, 1, io.out_logits + (size_t)i * T, M * T);
-                e.ck("attn logits out");
-            }
+            TT p1d = e.psine_chain(lin(ys, P + "prenet.0.linear_layer", 256), p1w, io.prenet + (size_t)i * B * 256, 256, 0.2f, nullptr, 0);
+            TT p2 = e.psine_chain(lin(p1d, P + "prenet.3.linear_layer", 256), p4w, nullptr, 0, 0.f, nullptr, 0);
+            TT q = e.psine_chain(lin(hh_prev, P + "Q.0.linear_layer", 512), Wq_w, nullptr, 0, 0.f, pos + (size_t)i * 512, 0);
             TT xy = e.make(B, 512);                                 // [content read-out | prenet + attention], the input of LSTM layer 0
             TT xy_c = xy.colslice(0, 256), xy_y = xy.colslice(256, 256);
-            TT o = lin(e.attn_context(e.softmax(a), Vmem, T), P + "attention_proj.linear_layer", 256);
+            // location attention with the logit dropout (360-364); the post-dropout logits go straight to out[b][i][:]
+            TT ctx = e.attn_step(q, temp, Kmem, Vmem, T, io.attn + (size_t)i * B * T, 1.0f / 0.9f, want_logits ? io.out_logits + (size_t)i * T : nullptr, M * T);
+            TT o = lin(ctx, P + "attention_proj.linear_layer", 256);
             e.add(p2, o, &xy_y);
             TT cq = e.silu(lin(cc_prev, P + "content.Q.0", 256));
-            e.attn_context(e.softmax(e.attn_scores(e.scale_param(cq, ctemp), ckey, minT)), cval, minT, &xy_c);
+            e.attn_step(cq, ctemp, ckey, cval, minT, nullptr, 1.f, nullptr, 0, &xy_c);
             TT h0n, c0n, h1n, c1n;
             TT h0dst = hh.colslice(0, 512), c0dst = cc.colslice(0, 512), h1dst = hh.colslice(512, 512), c1dst = cc.colslice(512, 512);
-            TT g0 = e.linear(xy, Wih0, &bih0);
-            e.linear(hh_prev.colslice(0, 512), Whh0, &bhh0, &g0, true);
+            TT g0 = e.linear2(xy, Wih0, &bih0, hh_prev.colslice(0, 512), Whh0, &bhh0);
             e.lstm_cell(g0, cc_prev.colslice(0, 512), h0n, c0n, &h0dst, &c0dst);
             TT h0d = e.dropout(h0n, io.lstm + (size_t)i * B * 512, 512, 0.1f);                 // nn.LSTM(dropout=0.1): layer 1's input only
-            TT g1 = e.linear(h0d, Wih1, &bih1);
-            e.linear(hh_prev.colslice(512, 512), Whh1, &bhh1, &g1, true);
+            TT g1 = e.linear2(h0d, Wih1, &bih1, hh_prev.colslice(512, 512), Whh1, &bhh1);
             e.lstm_cell(g1, cc_prev.colslice(512, 512), h1n, c1n, &h1dst, &c1dst);
             TT ydst = outputs.rowslice(i, B, M);
             ys = e.linear(h1n, Wfc, &bfc, &ydst);                   // straight into row (b, i) of the output
