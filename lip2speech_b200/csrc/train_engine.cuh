@@ -656,29 +656,42 @@ __global__ void __launch_bounds__(256) attn_context_bwd_kernel(int B, int T, int
 }
 
 // ---- kernels: one decoder-step attention in one launch -----------------------------------------------------------------------
-// One CTA per clip b: s_t = (w q_b) . K_{b,t}  ->  (x keep-mask / (1-p))  ->  softmax over t  ->  ctx_b = sum_t a_t V_{b,t}
-// (decoder.py:360-364 with the logit dropout, 262-271 without).  Saved for the backward pass: the probabilities a and the
-// unscaled products q . K_t (the derivative with respect to the learnable temperature w).  logits (optional): the post-dropout
-// scores, written straight into the caller-visible [B][M][T] tensor.  T <= 320.
+// s_t = (w q_b) . K_{b,t}  ->  (x keep-mask / (1-p))  ->  softmax over t  ->  ctx_b = sum_t a_t V_{b,t}   (decoder.py:360-364 with
+// the logit dropout, 262-271 without).  Grid (B, ATT_SPLIT): the CTAs of a clip each form the full score vector (K is small and
+// L2-resident) and own one quarter of the feature columns of the read-out.  Saved for the backward pass: the probabilities a
+// and the unscaled products q . K_t (the derivative with respect to the learnable temperature w).  logits (optional): the
+// post-dropout scores, written straight into the caller-visible [B][M][T] tensor.  T <= 320; D, DV multiples of 4, rows 16-byte
+// aligned (checked by the host).
+constexpr int ATT_SPLIT = 4;
 __global__ void __launch_bounds__(256) attn_step_fwd_kernel(int T, int D, int DV, const float* __restrict__ w, const float* __restrict__ Q, int qs,
                                                             const float* __restrict__ Km, int ks, const float* __restrict__ mask, float alpha,
                                                             const float* __restrict__ V, int vs, float* __restrict__ sraw, float* __restrict__ A,
                                                             float* __restrict__ logits, int ls, float* __restrict__ C, int cs) {
     __shared__ float sc[320];
     __shared__ float red[2];
+    __shared__ float4 part[8][32];
     const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool first = blockIdx.y == 0;
     const float wv = w[0];
-    const float* q = Q + (size_t)b * qs;
+    const float4* q4 = reinterpret_cast<const float4*>(Q + (size_t)b * qs);
+    const int D4 = D >> 2;
     for (int t = warp; t < T; t += 8) {
-        const float* kr = Km + (size_t)(b * T + t) * ks;
+        const float4* k4 = reinterpret_cast<const float4*>(Km + (size_t)(b * T + t) * ks);
         float a = 0.f, raw = 0.f;
-        for (int k = lane; k < D; k += 32) { const float qv = q[k], kv = kr[k]; a = fmaf(qv * wv, kv, a); raw = fmaf(qv, kv, raw); }
+#pragma unroll 4
+        for (int k = lane; k < D4; k += 32) {
+            const float4 qv = q4[k], kv = k4[k];
+            a = fmaf(qv.x * wv, kv.x, a); a = fmaf(qv.y * wv, kv.y, a); a = fmaf(qv.z * wv, kv.z, a); a = fmaf(qv.w * wv, kv.w, a);
+            raw = fmaf(qv.x, kv.x, raw); raw = fmaf(qv.y, kv.y, raw); raw = fmaf(qv.z, kv.z, raw); raw = fmaf(qv.w, kv.w, raw);
+        }
         a = warp_sum(a); raw = warp_sum(raw);
         if (lane == 0) {
             if (mask) a *= mask[(size_t)b * T + t] * alpha;
             sc[t] = a;
-            sraw[(size_t)b * T + t] = raw;
-            if (logits) logits[(size_t)b * ls + t] = a;
+            if (first) {
+                sraw[(size_t)b * T + t] = raw;
+                if (logits) logits[(size_t)b * ls + t] = a;
+            }
         }
     }
     __syncthreads();
@@ -695,17 +708,36 @@ __global__ void __launch_bounds__(256) attn_step_fwd_kernel(int T, int D, int DV
     for (int t = threadIdx.x; t < T; t += 256) {
         const float a = expf(sc[t] - red[0]) / red[1];
         sc[t] = a;
-        A[(size_t)b * T + t] = a;
+        if (first) A[(size_t)b * T + t] = a;
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < DV; k += 256) {
-        float acc = 0.f;
-        for (int t = 0; t < T; ++t) acc = fmaf(sc[t], V[(size_t)(b * T + t) * vs + k], acc);
-        C[(size_t)b * cs + k] = acc;
+    // read-out: this CTA's quarter of the columns; 32 column quads x 8 position groups, folded in group order
+    const int per = ((DV >> 2) + ATT_SPLIT - 1) / ATT_SPLIT;           // column quads per CTA (<= 32 for DV <= 512)
+    for (int c0 = blockIdx.y * per; c0 < min((int)(blockIdx.y + 1) * per, DV >> 2); c0 += 32) {
+        const int c = c0 + lane;
+        const bool ok = c < min((int)(blockIdx.y + 1) * per, DV >> 2);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok)
+#pragma unroll 4
+            for (int t = warp; t < T; t += 8) {
+                const float4 v = reinterpret_cast<const float4*>(V + (size_t)(b * T + t) * vs)[c];
+                const float a = sc[t];
+                acc.x = fmaf(a, v.x, acc.x); acc.y = fmaf(a, v.y, acc.y); acc.z = fmaf(a, v.z, acc.z); acc.w = fmaf(a, v.w, acc.w);
+            }
+        part[warp][lane] = acc;
+        __syncthreads();
+        if (warp == 0 && ok) {
+            float4 r = part[0][lane];
+#pragma unroll
+            for (int g = 1; g < 8; ++g) { const float4 p4 = part[g][lane]; r.x += p4.x; r.y += p4.y; r.z += p4.z; r.w += p4.w; }
+            reinterpret_cast<float4*>(C + (size_t)b * cs)[c] = r;
+        }
+        __syncthreads();
     }
 }
-// Backward of the above for clip b = blockIdx.x: dV += a dC^T; da = V dC; softmax and dropout backward; dw partial (one float per
-// clip, summed later in a fixed order); dq += w K^T ds; dK += ds (w q)^T.
+// Backward of the above for clip b = blockIdx.x, column quarter blockIdx.y: every CTA forms da = V dC and the softmax / dropout
+// backward for all positions (needs all columns: V is read once per CTA), then updates ITS columns of dV, dK and dq.  The dw partial
+// (one float per clip, summed later in a fixed order) comes from the first CTA.
 __global__ void __launch_bounds__(256) attn_step_bwd_kernel(int T, int D, int DV, const float* __restrict__ w, const float* __restrict__ Q, int qs,
                                                             const float* __restrict__ Km, int ks, const float* __restrict__ mask, float alpha,
                                                             const float* __restrict__ V, int vs, const float* __restrict__ sraw, const float* __restrict__ A,
@@ -714,17 +746,26 @@ __global__ void __launch_bounds__(256) attn_step_bwd_kernel(int T, int D, int DV
     __shared__ float da[320];
     __shared__ float ds[320];
     __shared__ float red[1];
+    __shared__ float4 part[8][32];
     const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float wv = w[0];
-    const float* dc = dC + (size_t)b * dcs;
+    const float4* dc4 = reinterpret_cast<const float4*>(dC + (size_t)b * dcs);
+    const int DV4 = DV >> 2, D4 = D >> 2;
+    const int vper = (DV4 + ATT_SPLIT - 1) / ATT_SPLIT, v0 = blockIdx.y * vper, v1 = min(v0 + vper, DV4);
     for (int t = warp; t < T; t += 8) {
         const float a = A[(size_t)b * T + t];
-        const float* vr = V + (size_t)(b * T + t) * vs;
+        const float4* vr = reinterpret_cast<const float4*>(V + (size_t)(b * T + t) * vs);
+        float4* dvr = dV ? reinterpret_cast<float4*>(dV + (size_t)(b * T + t) * dvs) : nullptr;
         float acc = 0.f;
-        for (int k = lane; k < DV; k += 32) {
-            const float d = dc[k];
-            acc = fmaf(d, vr[k], acc);
-            if (dV) dV[(size_t)(b * T + t) * dvs + k] += a * d;
+#pragma unroll 4
+        for (int k = lane; k < DV4; k += 32) {
+            const float4 d = dc4[k], v = vr[k];
+            acc = fmaf(d.x, v.x, acc); acc = fmaf(d.y, v.y, acc); acc = fmaf(d.z, v.z, acc); acc = fmaf(d.w, v.w, acc);
+            if (dvr && k >= v0 && k < v1) {
+                float4 o = dvr[k];
+                o.x = fmaf(a, d.x, o.x); o.y = fmaf(a, d.y, o.y); o.z = fmaf(a, d.z, o.z); o.w = fmaf(a, d.w, o.w);
+                dvr[k] = o;
+            }
         }
         acc = warp_sum(acc);
         if (lane == 0) da[t] = acc;
@@ -743,22 +784,47 @@ __global__ void __launch_bounds__(256) attn_step_bwd_kernel(int T, int D, int DV
         ds[t] = g;
     }
     __syncthreads();
-    if (warp == 0 && dwpart) {
+    if (warp == 0 && dwpart && blockIdx.y == 0) {
         float s = 0.f;
         for (int t = lane; t < T; t += 32) s = fmaf(ds[t], sraw[(size_t)b * T + t], s);
         s = warp_sum(s);
         if (lane == 0) dwpart[b] = s;
     }
-    const float* q = Q + (size_t)b * qs;
-    for (int k = threadIdx.x; k < D; k += 256) {
-        const float qw = q[k] * wv;
-        float acc = 0.f;
-        for (int t = 0; t < T; ++t) {
-            const float g = ds[t];
-            acc = fmaf(g, Km[(size_t)(b * T + t) * ks + k], acc);
-            if (dK) dK[(size_t)(b * T + t) * dks + k] += g * qw;
+    // dq / dK for this CTA's column quads: 32 quads x 8 position groups
+    const float4* q4 = reinterpret_cast<const float4*>(Q + (size_t)b * qs);
+    const int kper = (D4 + ATT_SPLIT - 1) / ATT_SPLIT, k1 = min((int)(blockIdx.y + 1) * kper, D4);
+    for (int c0 = blockIdx.y * kper; c0 < k1; c0 += 32) {
+        const int c = c0 + lane;
+        const bool ok = c < k1;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) {
+            float4 qw = q4[c];
+            qw.x *= wv; qw.y *= wv; qw.z *= wv; qw.w *= wv;
+#pragma unroll 4
+            for (int t = warp; t < T; t += 8) {
+                const float g = ds[t];
+                const float4 kv = reinterpret_cast<const float4*>(Km + (size_t)(b * T + t) * ks)[c];
+                acc.x = fmaf(g, kv.x, acc.x); acc.y = fmaf(g, kv.y, acc.y); acc.z = fmaf(g, kv.z, acc.z); acc.w = fmaf(g, kv.w, acc.w);
+                if (dK) {
+                    float4* dk = reinterpret_cast<float4*>(dK + (size_t)(b * T + t) * dks) + c;
+                    float4 o = *dk;
+                    o.x = fmaf(g, qw.x, o.x); o.y = fmaf(g, qw.y, o.y); o.z = fmaf(g, qw.z, o.z); o.w = fmaf(g, qw.w, o.w);
+                    *dk = o;
+                }
+            }
         }
-        if (dQ) dQ[(size_t)b * dqs + k] += acc * wv;
+        part[warp][lane] = acc;
+        __syncthreads();
+        if (warp == 0 && ok && dQ) {
+            float4 r = part[0][lane];
+#pragma unroll
+            for (int g = 1; g < 8; ++g) { const float4 p4 = part[g][lane]; r.x += p4.x; r.y += p4.y; r.z += p4.z; r.w += p4.w; }
+            float4* dq = reinterpret_cast<float4*>(dQ + (size_t)b * dqs) + c;
+            float4 o = *dq;
+            o.x = fmaf(r.x, wv, o.x); o.y = fmaf(r.y, wv, o.y); o.z = fmaf(r.z, wv, o.z); o.w = fmaf(r.w, wv, o.w);
+            *dq = o;
+        }
+        __syncthreads();
     }
 }
 // out[0] += sum over a list of R arrays of n floats, in list order (the per-step, per-clip temperature-gradient partials)
@@ -784,22 +850,36 @@ __global__ void psine_chain_fwd_kernel(int rows, int cols, const float* __restri
         Y[(size_t)r * ys + c] = y;
     }
 }
-// thread per column: dx += dy m cos(x) w ; dw[c] += sum_r dy m sin(x)   (few rows: the sum is a short serial loop, deterministic)
-__global__ void psine_chain_bwd_kernel(int rows, int cols, const float* __restrict__ X, int xs, const float* __restrict__ w, const float* __restrict__ mask, int ms,
-                                       float alpha, const float* __restrict__ dY, int dys, float* __restrict__ dX, int dxs, float* __restrict__ dw) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cols) return;
-    const float wc = w[c];
-    float acc = 0.f;
-    for (int r = 0; r < rows; ++r) {
-        float g = dY[(size_t)r * dys + c];
-        if (mask) g *= mask[(size_t)r * ms + c] * alpha;
-        float sn, cs;
-        sincosf(X[(size_t)r * xs + c], &sn, &cs);
-        if (dX) dX[(size_t)r * dxs + c] += g * cs * wc;
-        acc = fmaf(g, sn, acc);
+// dx += dy m cos(x) w ; dw[c] += sum_r dy m sin(x).  CTA = 32 columns x 8 row lanes (rows <= 16: two passes), every load of
+// the launch in flight at once; the column sums are folded in row order (deterministic).
+__global__ void __launch_bounds__(256) psine_chain_bwd_kernel(int rows, int cols, const float* __restrict__ X, int xs, const float* __restrict__ w,
+                                                              const float* __restrict__ mask, int ms, float alpha, const float* __restrict__ dY, int dys,
+                                                              float* __restrict__ dX, int dxs, float* __restrict__ dw) {
+    __shared__ float red[16][33];
+    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    const float wc = c < cols ? w[c] : 0.f;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const int r = rl + 8 * p;
+        float contrib = 0.f;
+        if (c < cols && r < rows) {
+            float g = dY[(size_t)r * dys + c];
+            if (mask) g *= mask[(size_t)r * ms + c] * alpha;
+            float sn, cs;
+            sincosf(X[(size_t)r * xs + c], &sn, &cs);
+            if (dX) dX[(size_t)r * dxs + c] += g * cs * wc;
+            contrib = g * sn;
+        }
+        red[r][cl] = contrib;
     }
-    if (dw) dw[c] += acc;
+    __syncthreads();
+    if (rl == 0 && c < cols && dw) {
+        float acc = 0.f;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) acc += red[r][cl];
+        dw[c] += acc;
+    }
 }
 
 // ---- kernels: LSTM cell (gate order i, f, g, o) -------------------------------------------------------------
@@ -1734,12 +1814,15 @@ struct Engine {
         if (T > 320) throw L2sError(1, "train: attention over more than 320 positions");
         TT y = dst ? *dst : make(B, DV);
         float* sraw = scratch((size_t)B * T); float* probs = scratch((size_t)B * T);
-        attn_step_fwd_kernel<<<B, 256, 0, s>>>(T, D, DV, w.v, q.v, q.rs, Km.v, Km.rs, mask, alpha, V.v, V.rs, sraw, probs, logits, ls, y.v, y.rs);
+        const bool vec = !(D & 3) && !(DV & 3) && !(q.rs & 3) && !(Km.rs & 3) && !(V.rs & 3) && !(y.rs & 3) &&
+                         !((reinterpret_cast<uintptr_t>(q.v) | reinterpret_cast<uintptr_t>(Km.v) | reinterpret_cast<uintptr_t>(V.v) | reinterpret_cast<uintptr_t>(y.v)) & 15);
+        if (!vec) throw L2sError(1, "train: attention operands must be 16-byte aligned with multiples of 4 columns");
+        attn_step_fwd_kernel<<<dim3(B, ATT_SPLIT), 256, 0, s>>>(T, D, DV, w.v, q.v, q.rs, Km.v, Km.rs, mask, alpha, V.v, V.rs, sraw, probs, logits, ls, y.v, y.rs);
         ck("attention step");
         tape.push_back([=]() {
             float* dwp = nullptr;
             if (w.g) { dwp = scratch(B); deferred_scalar[w.g].push_back(dwp); deferred_scalar_n[w.g] = B; }
-            attn_step_bwd_kernel<<<B, 256, 0, s>>>(T, D, DV, w.v, q.v, q.rs, Km.v, Km.rs, mask, alpha, V.v, V.rs, sraw, probs, y.g, y.rs, q.g, q.rs, Km.g, Km.rs,
+            attn_step_bwd_kernel<<<dim3(B, ATT_SPLIT), 256, 0, s>>>(T, D, DV, w.v, q.v, q.rs, Km.v, Km.rs, mask, alpha, V.v, V.rs, sraw, probs, y.g, y.rs, q.g, q.rs, Km.g, Km.rs,
                                                    V.g, V.rs, dwp);
             ck("attention step bwd");
         });
@@ -1759,7 +1842,7 @@ struct Engine {
         psine_chain_fwd_kernel<<<ew_blocks(x.numel()), 256, 0, s>>>(x.rows, x.cols, x.v, x.rs, w.v, mask, ms, alpha, addc, as, y.v, y.rs);
         ck("psine chain");
         tape.push_back([=]() {
-            psine_chain_bwd_kernel<<<(x.cols + 127) / 128, 128, 0, s>>>(x.rows, x.cols, x.v, x.rs, w.v, mask, ms, alpha, y.g, y.rs, x.g, x.rs, w.g);
+            psine_chain_bwd_kernel<<<(x.cols + 31) / 32, 256, 0, s>>>(x.rows, x.cols, x.v, x.rs, w.v, mask, ms, alpha, y.g, y.rs, x.g, x.rs, w.g);
             ck("psine chain bwd");
         });
         return y;
