@@ -288,7 +288,7 @@ def run_train_step(args, rank, local_rank, world):
                 "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"kernel": "sgemm_kernel (SIMT fp32 GEMM of the train path)", "bound": "tensor", "achieved": None, "peak": None, "unit": "TFLOP/s",
                              "frac": None, "traffic": None,
-                             "note": "the train path is correctness-first (exact fp32 FMA); no roofline claim is made for it this round"}}
+                             "note": "exact-fp32 train kernels replayed as CUDA graphs: a chain of ~5 K dependent small launches per step (profiles/r2_train_step_kernel_shares.txt); no single kernel dominates, so no roofline claim is made for this config"}}
         if not args.no_cpu_baseline:
             times = oracle_train_step(min(B, 4), T, M, reps=1)
             line["cpu_baseline"] = {"value": min(B, 4) * M / statistics.median(times), "unit": "mel-frames/s", "cores": torch.get_num_threads(), "kind": "port",
