@@ -174,23 +174,41 @@ __device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) 
 // instead of two loads per warp), NW * MT = 32 accumulators per lane are reduced with warp_transpose_sum32.
 // A second operand pair (A2 [M,K2], W2 [N,K2], bias2) is treated as a continuation of the reduction: C = A W^T + A2 W2^T + bias +
 // bias2 in one launch (the two halves of the LSTM gate pre-activation, x W_ih^T + h W_hh^T).  K2 = 0: single product.
+// Folds V per-lane partial values (V = 8, 16 or 32) across the warp; afterwards lane l holds the complete sum of value
+// l / (32 / V) (every lane of that group of 32 / V lanes holds it).
+template <int V>
+__device__ __forceinline__ float warp_fold(float (&v)[V], int lane) {
+    if constexpr (V == 32) {
+        L2S_FOLD_LANES(v, 16, 16) L2S_FOLD_LANES(v, 8, 8) L2S_FOLD_LANES(v, 4, 4) L2S_FOLD_LANES(v, 2, 2) L2S_FOLD_LANES(v, 1, 1)
+    } else if constexpr (V == 16) {
+        L2S_FOLD_LANES(v, 16, 8) L2S_FOLD_LANES(v, 8, 4) L2S_FOLD_LANES(v, 4, 2) L2S_FOLD_LANES(v, 2, 1)
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+    } else {
+        static_assert(V == 8, "8, 16 or 32 values");
+        L2S_FOLD_LANES(v, 16, 4) L2S_FOLD_LANES(v, 8, 2) L2S_FOLD_LANES(v, 4, 1)
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+    }
+    return v[0];
+}
 template <int NW, int MT>
 __global__ void __launch_bounds__(256) skinny_nt_smem_kernel(int M, int N, int K1, const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
                                                              const float* __restrict__ bias, int K2, const float* __restrict__ A2, int lda2,
                                                              const float* __restrict__ W2, int ldw2, const float* __restrict__ bias2,
                                                              float* __restrict__ C, int ldc, int accumulate) {
     const int K = K1 + K2;
-    static_assert(NW * MT == 32, "one output per lane");
+    constexpr int V = NW * MT;                                        // accumulators per lane
+    constexpr int J = NW * MT <= 16 ? 8 : 4;                          // 16-byte weight loads per row kept in flight: a chunk of 128 J columns
     extern __shared__ float4 xs4[];                                   // [MT][K/4], rows >= M are zero
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = (blockIdx.x * 8 + warp) * NW;
     const int K4 = K >> 2;
-    float4 wv[NW][4];
+    float4 wv[NW][J];
     auto load_w = [&](int kc) {
 #pragma unroll
         for (int n = 0; n < NW; ++n)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < J; ++j) {
                 const int k = kc + 128 * j + 4 * lane;
                 const float* src = k < K1 ? W + (size_t)(n0 + n) * ldw + k : W2 + (size_t)(n0 + n) * ldw2 + (k - K1);
                 wv[n][j] = (n0 + n < N && k < K) ? *reinterpret_cast<const float4*>(src) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -203,13 +221,13 @@ __global__ void __launch_bounds__(256) skinny_nt_smem_kernel(int M, int N, int K
         xs4[i] = m < M ? *reinterpret_cast<const float4*>(src) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
-    float acc[32];
+    float acc[V];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-    for (int kc = 0; kc < K; kc += 512) {
+    for (int i = 0; i < V; ++i) acc[i] = 0.f;
+    for (int kc = 0; kc < K; kc += 128 * J) {
         if (kc) load_w(kc);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < J; ++j) {
             const int q = (kc >> 2) + 32 * j + lane;
             if (q < K4) {
 #pragma unroll
@@ -225,93 +243,104 @@ __global__ void __launch_bounds__(256) skinny_nt_smem_kernel(int M, int N, int K
             }
         }
     }
-    const float v = warp_transpose_sum32(acc, lane);                  // lane = n * MT + m
-    const int n = n0 + lane / MT, m = lane % MT;
-    if (n < N && m < M) {
+    const float v = warp_fold<V>(acc, lane);                          // value index = n * MT + m
+    const int idx = lane / (32 / V);
+    const int n = n0 + idx / MT, m = idx % MT;
+    if ((lane & (32 / V - 1)) == 0 && n < N && m < M) {
         float* c = C + (size_t)m * ldc + n;
         const float r = v + (bias ? bias[n] : 0.f) + (bias2 ? bias2[n] : 0.f);
         *c = accumulate ? *c + r : r;
     }
 }
 
-// dx[m][k] += sum_n dy[m][n] W[n][k] for M <= MT in ONE launch and without partial sums in memory: a CTA owns a strip of 16
-// columns k (64 bytes of every weight row) and walks ALL N rows: lane = (4 k-quads) x (8 rows per load instruction), 8 warps
-// interleave the rows; every lane keeps two batches of 8 weight loads in flight (ping-pong) while dy — staged once in shared
-// memory, transposed to [n][m] — feeds the FMAs.  The 8 row-lanes are folded with shuffles, the 8 warps through shared memory in
-// index order: deterministic.  (The two-stage form below needed two launches and 64 dependent partial reads per output.)
+// dx[m][k] += sum_n dy[m][n] W[n][k] for M <= MT in ONE launch and without partial sums in memory: a CTA of 16 warps owns a
+// strip of 8 columns k (32 bytes = one sector of every weight row) and walks ALL N rows: lane = (2 k-quads) x (16 rows per load
+// instruction), the 16 warps interleave the rows, so N = 2048 is 8 loads per lane and ALL of them are issued before the first
+// is used (the kernel is bound by bytes in flight: 4 MB of L2-resident weights, ~0.1 MFLOP).  dy sits in shared memory in its
+// natural [m][n] layout (16-byte copies in, conflict-free scalar reads out).  The 16 row-lanes are folded with shuffles, the
+// 16 warps through shared memory in index order: deterministic.
 // gridDim.y = 2: a second problem (W2, K2, dX2) that shares dy (the two operands of one pre-activation).
+constexpr int NN_THREADS = 512;
 template <int MT>
-__global__ void __launch_bounds__(256) skinny_nn_strip_kernel(int M, int N, int K, const float* __restrict__ dY, int ldy, const float* __restrict__ W, int ldw,
-                                                              float* __restrict__ dX, int ldx, int K2, const float* __restrict__ W2, int ldw2,
-                                                              float* __restrict__ dX2, int ldx2) {
+__global__ void __launch_bounds__(NN_THREADS) skinny_nn_strip_kernel(int M, int N, int K, const float* __restrict__ dY, int ldy, const float* __restrict__ W, int ldw,
+                                                                     float* __restrict__ dX, int ldx, int K2, const float* __restrict__ W2, int ldw2,
+                                                                     float* __restrict__ dX2, int ldx2) {
     if (blockIdx.y == 1) { K = K2; W = W2; ldw = ldw2; dX = dX2; ldx = ldx2; }
-    if ((int)blockIdx.x * 16 >= K) return;
+    if ((int)blockIdx.x * 8 >= K) return;
     extern __shared__ float4 nn_sm4[];
-    float* dys = reinterpret_cast<float*>(nn_sm4);                   // [Npad][MT]
+    float* dys = reinterpret_cast<float*>(nn_sm4);                   // [MT][Npad]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int kq = lane & 3, ny = lane >> 2;
-    const int k = blockIdx.x * 16 + kq * 4;
+    const int kq = lane & 1, ny = lane >> 1;
+    const int k = blockIdx.x * 8 + kq * 4;
     const bool kok = k < K;
-    const int nfirst = warp * 8 + ny;                                // this lane's rows: nfirst + 64 j
-    const int iters = (N + 63) / 64;
-    float4 wv[2][8];
-    auto fetch = [&](int buf, int j0) {
+    const int nfirst = warp * 16 + ny;                               // this lane's rows: nfirst + 256 j
+    const int iters = (N + 255) / 256;
+    const int Npad = iters * 256;
+    float4 wv[8];
+    auto fetch = [&](int j0) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const int n = nfirst + 64 * (j0 + u);
-            wv[buf][u] = (kok && n < N) ? *reinterpret_cast<const float4*>(W + (size_t)n * ldw + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int n = nfirst + 256 * (j0 + u);
+            wv[u] = (kok && n < N) ? *reinterpret_cast<const float4*>(W + (size_t)n * ldw + k) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
-    fetch(0, 0);
-    const int Npad = iters * 64;
-    for (int i = threadIdx.x; i < Npad * MT; i += 256) {
-        const int n = i / MT, m = i % MT;
-        dys[i] = (m < M && n < N) ? dY[(size_t)m * ldy + n] : 0.f;
+    fetch(0);
+    if (!(ldy & 3) && !(reinterpret_cast<uintptr_t>(dY) & 15)) {
+        const int N4 = Npad >> 2;
+        for (int i = threadIdx.x; i < MT * N4; i += NN_THREADS) {
+            const int m = i / N4, q = i - m * N4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < M && 4 * q + 3 < N) v = *reinterpret_cast<const float4*>(dY + (size_t)m * ldy + 4 * q);
+            else if (m < M) {
+                float t[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int u = 0; u < 4; ++u) if (4 * q + u < N) t[u] = dY[(size_t)m * ldy + 4 * q + u];
+                v = make_float4(t[0], t[1], t[2], t[3]);
+            }
+            nn_sm4[i] = v;
+        }
+    } else {
+        for (int i = threadIdx.x; i < MT * Npad; i += NN_THREADS) {
+            const int m = i / Npad, n = i - m * Npad;
+            dys[i] = (m < M && n < N) ? dY[(size_t)m * ldy + n] : 0.f;
+        }
     }
     __syncthreads();
     float acc[MT * 4];
 #pragma unroll
     for (int i = 0; i < MT * 4; ++i) acc[i] = 0.f;
-    auto compute = [&](int buf, int j0) {
+    for (int j0 = 0; j0 < iters; j0 += 8) {
+        if (j0) fetch(j0);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             if (j0 + u >= iters) break;
-            const float4* d4 = reinterpret_cast<const float4*>(dys + (size_t)(nfirst + 64 * (j0 + u)) * MT);
-            const float4 w4 = wv[buf][u];
+            const float* d = dys + nfirst + 256 * (j0 + u);
+            const float4 w4 = wv[u];
 #pragma unroll
-            for (int mq = 0; mq < MT / 4; ++mq) {
-                const float4 d = d4[mq];
-                const float dm[4] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    float* a = acc + (mq * 4 + v) * 4;
-                    a[0] = fmaf(dm[v], w4.x, a[0]); a[1] = fmaf(dm[v], w4.y, a[1]); a[2] = fmaf(dm[v], w4.z, a[2]); a[3] = fmaf(dm[v], w4.w, a[3]);
-                }
+            for (int m = 0; m < MT; ++m) {
+                const float dm = d[(size_t)m * Npad];
+                float* a = acc + m * 4;
+                a[0] = fmaf(dm, w4.x, a[0]); a[1] = fmaf(dm, w4.y, a[1]); a[2] = fmaf(dm, w4.z, a[2]); a[3] = fmaf(dm, w4.w, a[3]);
             }
         }
-    };
-    for (int j0 = 0; j0 < iters; j0 += 16) {
-        if (j0 + 8 < iters) fetch(1, j0 + 8);
-        compute(0, j0);
-        if (j0 + 16 < iters) fetch(0, j0 + 16);
-        if (j0 + 8 < iters) compute(1, j0 + 8);
     }
-    // fold the 8 row-lanes (lane bits 4, 3, 2): each round hands half of the remaining values to the partner
-    L2S_FOLD_LANES(acc, 16, MT * 2) L2S_FOLD_LANES(acc, 8, MT) L2S_FOLD_LANES(acc, 4, MT / 2)
-    // this lane now owns MT/8 rows m = (MT/2) b4 + (MT/4) b3 + (MT/8) b2 + [0, MT/8) of its four k
+    // fold the 16 row-lanes (lane bits 4..1): each round hands half of the remaining values to the partner
+    L2S_FOLD_LANES(acc, 16, MT * 2) L2S_FOLD_LANES(acc, 8, MT) L2S_FOLD_LANES(acc, 4, MT / 2) L2S_FOLD_LANES(acc, 2, MT / 4)
+    // MT/4 values are left: value index v = (MT*2) b4 + MT b3 + (MT/2) b2 + (MT/4) b1 + [0, MT/4), row v / 4, column v % 4
     __syncthreads();                                                 // dys is dead: reuse it for the cross-warp sums
-    float* red = dys;                                                // [8 warps][MT][16]
-    const int mbase = (MT / 2) * ((lane >> 4) & 1) + (MT / 4) * ((lane >> 3) & 1) + (MT / 8) * ((lane >> 2) & 1);
+    float* red = dys;                                                // [16 warps][MT][8]
+    const int vbase = (MT * 2) * ((lane >> 4) & 1) + MT * ((lane >> 3) & 1) + (MT / 2) * ((lane >> 2) & 1) + (MT / 4) * ((lane >> 1) & 1);
 #pragma unroll
-    for (int u = 0; u < MT / 8; ++u)
-        *reinterpret_cast<float4*>(red + ((size_t)warp * MT + mbase + u) * 16 + kq * 4) = make_float4(acc[u * 4], acc[u * 4 + 1], acc[u * 4 + 2], acc[u * 4 + 3]);
+    for (int u = 0; u < MT / 4; ++u) {
+        const int v = vbase + u;
+        red[((size_t)warp * MT + (v >> 2)) * 8 + kq * 4 + (v & 3)] = acc[u];
+    }
     __syncthreads();
-    if (threadIdx.x < MT * 16) {
-        const int m = threadIdx.x >> 4, kk = blockIdx.x * 16 + (threadIdx.x & 15);
+    if (threadIdx.x < MT * 8) {
+        const int m = threadIdx.x >> 3, kk = blockIdx.x * 8 + (threadIdx.x & 7);
         if (m < M && kk < K) {
             float sum = 0.f;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) sum += red[((size_t)w * MT + m) * 16 + (threadIdx.x & 15)];
+            for (int w = 0; w < NN_THREADS / 32; ++w) sum += red[((size_t)w * MT + m) * 8 + (threadIdx.x & 7)];
             dX[(size_t)m * ldx + kk] += sum;
         }
     }
@@ -1413,7 +1442,10 @@ struct Engine {
         static bool attrs = false;
         if (!attrs) {
             L2S_CUDA(cudaFuncSetAttribute(skinny_nt_smem_kernel<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKINNY_SMEM_MAX));
+            L2S_CUDA(cudaFuncSetAttribute(skinny_nt_smem_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKINNY_SMEM_MAX));
+            L2S_CUDA(cudaFuncSetAttribute(skinny_nt_smem_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKINNY_SMEM_MAX));
             L2S_CUDA(cudaFuncSetAttribute(skinny_nt_smem_kernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKINNY_SMEM_MAX));
+            L2S_CUDA(cudaFuncSetAttribute(skinny_nt_smem_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKINNY_SMEM_MAX));
             L2S_CUDA(cudaFuncSetAttribute(skinny_nn_strip_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKINNY_SMEM_MAX));
             L2S_CUDA(cudaFuncSetAttribute(skinny_nn_strip_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKINNY_SMEM_MAX));
             L2S_CUDA(cudaFuncSetAttribute(stem_fwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEM_TILED_SMEM));
@@ -1539,6 +1571,32 @@ struct Engine {
     }
 
     // y = x W^T (+ b): x [R,K], W [N,K] (nn.Linear / flattened Conv1d weight), b [N] or empty
+    // Few-row product(s) y = x1 W1^T (+ x2 W2^T) + biases: rows per warp chosen so that the launch has ~100+ CTAs (it is bound by
+    // bytes in flight, not by FMAs).
+    void launch_skinny_nt(int R, int N, int K1, const float* x1, int lx1, const float* W1, int lw1, const float* b1, int K2, const float* x2, int lx2,
+                          const float* W2, int lw2, const float* b2, float* y, int ly, int accf) {
+        const int MT = R <= 8 ? 8 : 16;
+        const size_t smem = (size_t)MT * (K1 + K2) * sizeof(float);
+#define L2S_NT(NW_, MT_) skinny_nt_smem_kernel<NW_, MT_><<<(N + 8 * NW_ - 1) / (8 * NW_), 256, smem, s>>>(R, N, K1, x1, lx1, W1, lw1, b1, K2, x2, lx2, W2, lw2, b2, y, ly, accf)
+        if (MT == 8) {
+            if (N >= 3072) L2S_NT(4, 8); else if (N >= 1536) L2S_NT(2, 8); else L2S_NT(1, 8);
+        } else {
+            if (N >= 1536) L2S_NT(2, 16); else L2S_NT(1, 16);
+        }
+#undef L2S_NT
+        ck("skinny_nt");
+    }
+    // dx (+ dx2) += dy W (+ dy W2), few rows
+    void launch_skinny_nn(int R, int N, int K1, const float* dy, int ldy, const float* W1, int lw1, float* dx1, int ldx1, int K2, const float* W2, int lw2,
+                          float* dx2, int ldx2) {
+        const int MT = R <= 8 ? 8 : 16;
+        const size_t smem = skinny_nn_smem(R, N);
+        const dim3 grid((std::max(K1, K2) + 7) / 8, K2 ? 2 : 1);
+        if (MT == 8) skinny_nn_strip_kernel<8><<<grid, NN_THREADS, smem, s>>>(R, N, K1, dy, ldy, W1, lw1, dx1, ldx1, K2, W2, lw2, dx2, ldx2);
+        else skinny_nn_strip_kernel<16><<<grid, NN_THREADS, smem, s>>>(R, N, K1, dy, ldy, W1, lw1, dx1, ldx1, K2, W2, lw2, dx2, ldx2);
+        ck("skinny_nn strip");
+    }
+    static size_t skinny_nn_smem(int R, int N) { return (size_t)(R <= 8 ? 8 : 16) * ((N + 255) / 256 * 256) * sizeof(float); }
     // dst: write into this [R,N] view instead of a fresh tensor; accumulate: y += (a second operand of the same pre-activation,
     // e.g. the recurrent half of the LSTM gates — the view's gradient then serves both products).
     TT linear(const TT& x, const TT& W, const TT* b, const TT* dst = nullptr, bool accumulate = false) {
@@ -1553,11 +1611,10 @@ struct Engine {
             const int MT = R <= 8 ? 8 : 16;
             const size_t smem = (size_t)MT * K * sizeof(float);
             if (vec && smem <= (size_t)SKINNY_SMEM_MAX) {
-                if (MT == 8) skinny_nt_smem_kernel<4, 8><<<(N + 31) / 32, 256, smem, s>>>(R, N, K, x.v, x.rs, W.v, W.rs, b ? b->v : nullptr, 0, nullptr, 0, nullptr, 0, nullptr, y.v, y.rs, accf);
-                else skinny_nt_smem_kernel<2, 16><<<(N + 15) / 16, 256, smem, s>>>(R, N, K, x.v, x.rs, W.v, W.rs, b ? b->v : nullptr, 0, nullptr, 0, nullptr, 0, nullptr, y.v, y.rs, accf);
+                launch_skinny_nt(R, N, K, x.v, x.rs, W.v, W.rs, b ? b->v : nullptr, 0, nullptr, 0, nullptr, 0, nullptr, y.v, y.rs, accf);
             } else if (vec) skinny_nt_kernel<true><<<(N * 32 + 255) / 256, 256, 0, s>>>(R, N, K, x.v, x.rs, W.v, W.rs, b ? b->v : nullptr, y.v, y.rs, accf);
             else skinny_nt_kernel<false><<<(N * 32 + 255) / 256, 256, 0, s>>>(R, N, K, x.v, x.rs, W.v, W.rs, b ? b->v : nullptr, y.v, y.rs, accf);
-            ck("skinny_nt");
+            if (!(vec && smem <= (size_t)SKINNY_SMEM_MAX)) ck("skinny_nt");
         } else {
             gemm<0, 1>(R, N, K, x.v, x.rs, W.v, W.rs, y.v, y.rs, accumulate);
             if (b) {
@@ -1576,14 +1633,9 @@ struct Engine {
         }
         tape.push_back([=]() {
             if (x.g) {
-                const bool vecb = !(K & 3) && !(W.rs & 3) && !(reinterpret_cast<uintptr_t>(W.v) & 15) &&
-                                  (size_t)std::max((N + 63) / 64 * 64, 128) * (R <= 8 ? 8 : 16) * sizeof(float) <= (size_t)SKINNY_SMEM_MAX;
+                const bool vecb = !(K & 3) && !(W.rs & 3) && !(reinterpret_cast<uintptr_t>(W.v) & 15) && skinny_nn_smem(R, N) <= (size_t)SKINNY_SMEM_MAX;
                 if (R <= 16 && vecb) {
-                    const int MT = R <= 8 ? 8 : 16;
-                    const size_t smem = (size_t)std::max((N + 63) / 64 * 64, 128) * MT * sizeof(float);      // >= the [8][MT][16] cross-warp buffer
-                    if (MT == 8) skinny_nn_strip_kernel<8><<<(K + 15) / 16, 256, smem, s>>>(R, N, K, y.g, y.rs, W.v, W.rs, x.g, x.rs, 0, nullptr, 0, nullptr, 0);
-                    else skinny_nn_strip_kernel<16><<<(K + 15) / 16, 256, smem, s>>>(R, N, K, y.g, y.rs, W.v, W.rs, x.g, x.rs, 0, nullptr, 0, nullptr, 0);
-                    ck("skinny_nn strip");
+                    launch_skinny_nn(R, N, K, y.g, y.rs, W.v, W.rs, x.g, x.rs, 0, nullptr, 0, nullptr, 0);
                 } else if (R <= 16) {
                     const int nslice = 128, nslices = (N + nslice - 1) / nslice;
                     float* part = scratch((size_t)nslices * R * K);
@@ -1607,7 +1659,7 @@ struct Engine {
         };
         const int MT = R <= 8 ? 8 : 16;
         const size_t smem = (size_t)MT * (K1 + K2) * sizeof(float);
-        const size_t smemb = (size_t)std::max((N + 63) / 64 * 64, 128) * MT * sizeof(float);
+        const size_t smemb = skinny_nn_smem(R, N);
         const bool fused = R <= 16 && x2.rows == R && W2.rows == N && W1.cols == K1 && W2.cols == K2 && aligned(x1, W1) && aligned(x2, W2) &&
                            smem <= (size_t)SKINNY_SMEM_MAX && smemb <= (size_t)SKINNY_SMEM_MAX && x1.g && x2.g && W1.g && W2.g;
         if (!fused) {
@@ -1617,9 +1669,7 @@ struct Engine {
         }
         TT y = dst ? *dst : make(R, N);
         const float* bv1 = b1 ? b1->v : nullptr; const float* bv2 = b2 ? b2->v : nullptr;
-        if (MT == 8) skinny_nt_smem_kernel<4, 8><<<(N + 31) / 32, 256, smem, s>>>(R, N, K1, x1.v, x1.rs, W1.v, W1.rs, bv1, K2, x2.v, x2.rs, W2.v, W2.rs, bv2, y.v, y.rs, 0);
-        else skinny_nt_smem_kernel<2, 16><<<(N + 15) / 16, 256, smem, s>>>(R, N, K1, x1.v, x1.rs, W1.v, W1.rs, bv1, K2, x2.v, x2.rs, W2.v, W2.rs, bv2, y.v, y.rs, 0);
-        ck("skinny_nt x2");
+        launch_skinny_nt(R, N, K1, x1.v, x1.rs, W1.v, W1.rs, bv1, K2, x2.v, x2.rs, W2.v, W2.rs, bv2, y.v, y.rs, 0);
         for (int which = 0; which < 2; ++which) {
             const TT& x = which ? x2 : x1; const TT& W = which ? W2 : W1; const TT* b = which ? b2 : b1;
             Deferred& d = deferred[W.g];
@@ -1628,10 +1678,7 @@ struct Engine {
             for (int r = 0; r < R; ++r) { d.a.push_back(y.g + (size_t)r * y.rs); d.b.push_back(x.v + (size_t)r * x.rs); }
         }
         tape.push_back([=]() {
-            const dim3 grid((std::max(K1, K2) + 15) / 16, 2);
-            if (MT == 8) skinny_nn_strip_kernel<8><<<grid, 256, smemb, s>>>(R, N, K1, y.g, y.rs, W1.v, W1.rs, x1.g, x1.rs, K2, W2.v, W2.rs, x2.g, x2.rs);
-            else skinny_nn_strip_kernel<16><<<grid, 256, smemb, s>>>(R, N, K1, y.g, y.rs, W1.v, W1.rs, x1.g, x1.rs, K2, W2.v, W2.rs, x2.g, x2.rs);
-            ck("skinny_nn strip x2");
+            launch_skinny_nn(R, N, K1, y.g, y.rs, W1.v, W1.rs, x1.g, x1.rs, K2, W2.v, W2.rs, x2.g, x2.rs);
         });
         return y;
     }
