@@ -390,7 +390,7 @@ __global__ void skinny_nn_sum_kernel(int M, int K, int nslices, const float* __r
 // db (optional): the bias gradient db[n] += sum_i A_i[n], formed by the CTAs of the first column block from the tiles they load anyway.
 __global__ void __launch_bounds__(256) sgemm_tn_rows_kernel(int N, int K, int R, const float* const* __restrict__ rowsA, const float* const* __restrict__ rowsB,
                                                             float* __restrict__ C, int ldc, float* __restrict__ db) {
-    constexpr int BM = 64, BN = 64, BK = 16;
+    constexpr int BM = 64, BN = 64, BK = 32;
     __shared__ float As[BK][BM + 1];
     __shared__ float Bs[BK][BN + 1];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -402,20 +402,29 @@ __global__ void __launch_bounds__(256) sgemm_tn_rows_kernel(int N, int K, int R,
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     const bool sums = db != nullptr && blockIdx.x == 0 && tid < 64;
     float bsum = 0.f;
+    // 32 list rows per tile, 8 elements of each operand per thread, fetched one tile ahead (pointer + data: two dependent loads)
+    float ra[8], rb[8];
+    auto fetch = [&](int r0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int e = tid + i * 256;
+            const int c = e & 63, gr = r0 + (e >> 6);
+            ra[i] = 0.f; rb[i] = 0.f;
+            if (gr < R) {
+                if (m0 + c < N) ra[i] = rowsA[gr][m0 + c];
+                if (n0 + c < K) rb[i] = rowsB[gr][n0 + c];
+            }
+        }
+    };
+    fetch(0);
     for (int r0 = 0; r0 < R; r0 += BK) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 8; ++i) {
             const int e = tid + i * 256;
-            const int c = e & 63, r = e >> 6;
-            const int gr = r0 + r;
-            float va = 0.f, vb = 0.f;
-            if (gr < R) {
-                if (m0 + c < N) va = rowsA[gr][m0 + c];
-                if (n0 + c < K) vb = rowsB[gr][n0 + c];
-            }
-            As[r][c] = va; Bs[r][c] = vb;
+            As[e >> 6][e & 63] = ra[i]; Bs[e >> 6][e & 63] = rb[i];
         }
         __syncthreads();
+        if (r0 + BK < R) fetch(r0 + BK);
         if (sums)
 #pragma unroll
             for (int k = 0; k < BK; ++k) bsum += As[k][tid];
@@ -1110,7 +1119,8 @@ __global__ void __launch_bounds__(192) stem_fwd_tiled_kernel(int B, int T, int H
 // gathered straight from the clip tensor (each thread decodes its taps once), dY rows are broadcast from shared memory.
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(int B, int T, int H, int W, int Ho, int Wo, int pos_per_chunk, const float* __restrict__ X,
                                                          const float* __restrict__ dY, float* __restrict__ part) {
-    __shared__ float dys[32][24];
+    __shared__ __align__(16) float dys[32][24];
+    __shared__ int4 pinfo[32];                                       // per staged position: (b, t, 2 ho - 3, 2 wo - 3)
     const int tid = threadIdx.x;
     const size_t npos = (size_t)B * T * Ho * Wo;
     const size_t p0 = (size_t)blockIdx.x * pos_per_chunk, p1 = min(npos, p0 + pos_per_chunk);
@@ -1120,7 +1130,7 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(int B, int T, int H, in
         const int k = tid + 256 * j;
         kv[j] = k < 735;
         const int kk = kv[j] ? k : 0;
-        ci[j] = kk / 245; const int r = kk % 245; kt[j] = r / 49; kh[j] = (r % 49) / 7; kw[j] = r % 7;
+        ci[j] = kk / 245; const int r = kk % 245; kt[j] = r / 49 - 2; kh[j] = (r % 49) / 7; kw[j] = r % 7;
     }
     float acc[3][24];
 #pragma unroll
@@ -1131,24 +1141,32 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(int B, int T, int H, in
         const int nb = (int)min((size_t)32, p1 - pb);
         __syncthreads();
         for (int e = tid; e < nb * 24; e += 256) dys[e / 24][e % 24] = dY[(pb + e / 24) * 24 + e % 24];
-        __syncthreads();
-        for (int q = 0; q < nb; ++q) {
-            size_t r = pb + q;
+        if (tid < nb) {
+            size_t r = pb + tid;
             const int wo = r % Wo; r /= Wo;
             const int ho = r % Ho; r /= Ho;
-            const int t = r % T; const int b = r / T;
+            pinfo[tid] = make_int4((int)(r / T), (int)(r % T), 2 * ho - 3, 2 * wo - 3);
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int q = 0; q < nb; ++q) {
+            const int4 pi = pinfo[q];
             float xv[3];
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-                const int ti = t + kt[j] - 2, hi = 2 * ho + kh[j] - 3, wi = 2 * wo + kw[j] - 3;
+                const int ti = pi.y + kt[j], hi = pi.z + kh[j], wi = pi.w + kw[j];
                 xv[j] = (kv[j] && ti >= 0 && ti < T && hi >= 0 && hi < H && wi >= 0 && wi < W)
-                            ? __ldg(X + (((size_t)(b * 3 + ci[j]) * T + ti) * H + hi) * W + wi) : 0.f;
+                            ? __ldg(X + (((size_t)(pi.x * 3 + ci[j]) * T + ti) * H + hi) * W + wi) : 0.f;
             }
+            const float4* d4 = reinterpret_cast<const float4*>(dys[q]);
 #pragma unroll
-            for (int c = 0; c < 24; ++c) {
-                const float d = dys[q][c];
+            for (int c4 = 0; c4 < 6; ++c4) {
+                const float4 d = d4[c4];
 #pragma unroll
-                for (int j = 0; j < 3; ++j) acc[j][c] = fmaf(d, xv[j], acc[j][c]);
+                for (int j = 0; j < 3; ++j) {
+                    acc[j][4 * c4] = fmaf(d.x, xv[j], acc[j][4 * c4]); acc[j][4 * c4 + 1] = fmaf(d.y, xv[j], acc[j][4 * c4 + 1]);
+                    acc[j][4 * c4 + 2] = fmaf(d.z, xv[j], acc[j][4 * c4 + 2]); acc[j][4 * c4 + 3] = fmaf(d.w, xv[j], acc[j][4 * c4 + 3]);
+                }
             }
         }
     }
@@ -1554,8 +1572,8 @@ struct Engine {
         if (M <= 0 || N <= 0 || K <= 0) return;
         dim3 grid((N + 63) / 64, (M + 63) / 64);
         const int tiles = grid.x * grid.y;
-        if (tiles < 64 && K >= 2048) {                       // few output tiles, long reduction: split K over the chip
-            const int splits = std::min(std::min(128, 296 / tiles), (K + 255) / 256);
+        if (tiles <= 148 && K >= 1024) {                     // fewer output tiles than SMs, long reduction: split K over the chip
+            const int splits = std::max(2, std::min(std::min(128, 296 / tiles), (K + 255) / 256));
             const int kper = (((K + splits - 1) / splits) + 31) / 32 * 32;
             const int nz = (K + kper - 1) / kper;
             float* part = scratch((size_t)nz * M * N);
