@@ -146,6 +146,7 @@ struct DecoderTrain {
         // ---- run: replay, capture + launch, or eager ------------------------------------------------------------------------------
         const std::string key = std::to_string(B) + "," + std::to_string(T) + "," + std::to_string(M) + "," + (want_input_grads ? "g" : "-") +
                                 (want_logits ? "l" : "-") + (e.update_bn_running ? "r" : "-");
+        if (!slots.count(key) && slots.size() >= 16) drop_graphs();       // ragged workloads (every batch its own M): bound the cache
         slot = &slots[key];
         if (use_graphs && slot->fwd && slot->bwd) {
             mode = RUN_REPLAY;
@@ -399,6 +400,7 @@ struct VideoTrain {
         const bool masked = drop_mask != nullptr;
         const std::string key = std::to_string(B) + "," + std::to_string(T) + "," + std::to_string(H) + "," + std::to_string(W) + (masked ? "m" : "-") +
                                 (e.update_bn_running ? "r" : "-");
+        if (!slots.count(key) && slots.size() >= 16) drop_graphs();
         slot = &slots[key];
         if (use_graphs && slot->fwd && slot->bwd) {
             mode = RUN_REPLAY;

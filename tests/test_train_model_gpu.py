@@ -122,6 +122,50 @@ def test_train_backward_is_deterministic_and_accumulates(be):
         be.decoder_train_bwd(*g_out, B, T)           # the tape was consumed
 
 
+def test_decoder_train_bench_shape_vs_oracle(be):
+    """The shape bench.py --config c3 times (8 clips per GPU, T=29, M=77 teacher frames; BASELINE configs[3]) against autograd
+    on the oracle: outputs, input gradients and every parameter gradient — on the eager first call and again on the
+    CUDA-graph replay the timed steps actually run (third call with the key)."""
+    from oracle import train_oracle as TO
+    B, T, M = 8, 29, 77
+    w = _decoder_weights(1234, True)
+    visual, face = synth.visual_features(B, T, seed=41)
+    mels = synth.mel_like(B, M, seed=41) * 2 - 5
+    gate_t = torch.zeros(B, M); gate_t[:, -2:] = 1
+    noise = TO.reference_noise(B, T, M, 0.5, with_video=False, generator=torch.Generator().manual_seed(41))
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not spec.is_buffer(k) else v.clone()) for k, v in w.items()}
+    vin = visual.clone().requires_grad_(True)
+    fin = face.clone().requires_grad_(True)
+    ref = TO.decoder_forward_train(sd, vin, fin, mels, noise)
+    sum(TO.loss_forward(ref, (mels, gate_t)).values()).backward()
+
+    be.train_set_graphs(True)
+    dev, grads = _bind(be, w)
+    for attempt in ("eager", "captured", "replayed"):
+        for k, v in w.items():                       # undo the in-place running-statistics update of the previous pass
+            if spec.is_buffer(k) and v.is_floating_point():
+                dev[k].copy_(v)
+        for v in grads.values():
+            if v is not None:
+                v.zero_()
+        out = be.decoder_train_fwd(visual.cuda(), face[:, 0].cuda(), mels.cuda(), noise.to("cuda"))
+        for got, want, name in zip(out, (ref[0], ref[1], ref[2], ref[4], ref[5]), ("outputs", "post", "stop", "attn_logits", "content_dis")):
+            assert rel_err(got.cpu(), want.detach()) < 1e-3, (attempt, name)
+        _, g = be.loss_fwd_bwd(out[0], out[1], out[2], out[4], mels.cuda(), gate_t.cuda())
+        g_visual, g_spk = be.decoder_train_bwd(g[0], g[1], g[2], g[3], B, T)
+        torch.cuda.synchronize()
+        assert rel_err(g_visual.cpu(), vin.grad) < 2e-3, attempt
+        assert rel_err(g_spk.cpu(), fin.grad[:, 0]) < 2e-3, attempt
+        for k, p in sd.items():
+            if not (torch.is_tensor(p) and p.requires_grad):
+                continue
+            got = grads[k].cpu()
+            if ZERO_GRAD_BIAS.search(k):
+                assert float(got.abs().max()) < 1e-3 * float(sd[k[:-4] + "weight"].grad.abs().max()) + 1e-7, (attempt, k)
+            else:
+                assert rel_err(got, p.grad) < 2e-3, (attempt, k, rel_err(got, p.grad))
+
+
 def test_graph_replay_is_bit_identical_to_eager(be):
     """The train-mode forward / backward are captured as CUDA graphs on the second call with a key and replayed afterwards
     (l2s_train_set_graphs).  Eager, captured and replayed passes must agree bit for bit — also when the teacher-forcing coins
