@@ -182,27 +182,35 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def oracle_train_step(batch, T, M, reps):
-    """CPU arm of --config c3: autograd through the train-mode oracle (port of the reference's train step, torch CPU fp32)."""
+def oracle_train_step(batch, T, M, reps, device="cpu"):
+    """Baseline arms of --config c3: autograd through the train-mode oracle (port of the reference's train step, torch fp32) +
+    clip_grad_norm_ + torch.optim.AdamW(amsgrad) — on the host cores (device="cpu") or, as the incumbent GPU path, with every tensor
+    on the GPU (PyTorch eager: cuDNN / cuBLAS kernels, one launch per op)."""
     from lip2speech_b200 import spec, synth
     from oracle import train_oracle as TO
     torch.set_num_threads(os.cpu_count() or 1)
+    dev = torch.device(device)
     w = {k: v for k, v in spec.seeded_state_dict(spec.full_spec(), 1234).items() if not k.startswith("speaker_encoder.")}
-    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not spec.is_buffer(k) else v.clone()) for k, v in w.items()}
+    sd = {k: (v.clone().to(dev).requires_grad_(True) if v.is_floating_point() and not spec.is_buffer(k) else v.clone().to(dev)) for k, v in w.items()}
     params = [p for p in sd.values() if torch.is_tensor(p) and p.requires_grad]
     opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=1e-6, amsgrad=True)
-    video, spk = synth.video(batch, T, H, W), synth.speaker_embedding(batch)
-    mels = synth.mel_like(batch, M) * 2 - 5
+    video, spk = synth.video(batch, T, H, W).to(dev), synth.speaker_embedding(batch).to(dev)
+    mels = (synth.mel_like(batch, M) * 2 - 5).to(dev)
     gate_t = torch.zeros(batch, M); gate_t[:, -2:] = 1
+    gate_t = gate_t.to(dev)
     times = []
     for i in range(reps + 1):
-        noise = TO.reference_noise(batch, T, M, 0.5, with_video=True, generator=torch.Generator().manual_seed(i))
+        noise = TO.reference_noise(batch, T, M, 0.5, with_video=True, generator=torch.Generator().manual_seed(i)).to(dev)
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
         opt.zero_grad()
         out = TO.lip2speech_forward_train(sd, video, spk, mels, noise)
         sum(TO.loss_forward(out, (mels, gate_t)).values()).backward()
         torch.nn.utils.clip_grad_norm_(params, 1.0)
         opt.step()
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
         if i > 0:
             times.append(time.perf_counter() - t0)
     return times
@@ -289,6 +297,11 @@ def run_train_step(args, rank, local_rank, world):
                 "roofline": {"kernel": "sgemm_kernel (SIMT fp32 GEMM of the train path)", "bound": "tensor", "achieved": None, "peak": None, "unit": "TFLOP/s",
                              "frac": None, "traffic": None,
                              "note": "exact-fp32 train kernels replayed as CUDA graphs: a chain of ~5 K dependent small launches per step (profiles/r2_train_step_kernel_shares.txt); no single kernel dominates, so no roofline claim is made for this config"}}
+        if not args.no_eager_baseline:
+            times = oracle_train_step(B, T, M, reps=3, device=f"cuda:{local_rank}")
+            line["gpu_eager_baseline"] = {"value": B * M / statistics.median(times), "unit": "mel-frames/s", "ms_per_step": 1e3 * statistics.median(times),
+                                          "sample": f"3 train steps of {B} clips: the same oracle port with every tensor on the GPU (PyTorch eager autograd, "
+                                                    "cuDNN / cuBLAS kernels) + clip_grad_norm_ + torch.optim.AdamW(amsgrad) — the incumbent GPU path"}
         if not args.no_cpu_baseline:
             times = oracle_train_step(min(B, 4), T, M, reps=1)
             line["cpu_baseline"] = {"value": min(B, 4) * M / statistics.median(times), "unit": "mel-frames/s", "cores": torch.get_num_threads(), "kind": "port",

@@ -58,7 +58,10 @@ def _lstm(x, h0, c0, sd, name, layers, bidirectional=False):
         for sfx in ([""] + (["_reverse"] if bidirectional else [])):
             flat += [sd[f"{name}.weight_ih_l{l}{sfx}"], sd[f"{name}.weight_hh_l{l}{sfx}"],
                      sd[f"{name}.bias_ih_l{l}{sfx}"], sd[f"{name}.bias_hh_l{l}{sfx}"]]
-    out, h, c = torch._VF.lstm(x, (h0, c0), flat, True, layers, 0.0, False, bidirectional, True)
+    # train flag: the dropout probability is 0 here, so it changes no value; cuDNN refuses a backward pass without it (only the
+    # eager-CUDA baseline of bench.py --config c3 differentiates this op on the GPU)
+    train = x.is_cuda and torch.is_grad_enabled() and any(t.requires_grad for t in flat)
+    out, h, c = torch._VF.lstm(x, (h0, c0), flat, True, layers, 0.0, train, bidirectional, True)
     return out, h, c
 
 
