@@ -9,7 +9,14 @@
 // (PyTorch-owned) fp32 parameter memory and accumulates into the caller's gradient memory (l2s_train_bind), so an optimizer
 // step needs no re-bind / re-pack.  All reductions have a fixed order (no floating-point atomics): results are
 // run-to-run deterministic.  Exact fp32 FMA arithmetic (the GEMMs here are SIMT; the inference path's tcgen05 kernels stay
-// the fast path — this file is the correctness-first train path).
+// the fast path for inference).
+//
+// Speed: a train step is ~5 K small dependent launches (8 clips per GPU: every per-step layer is a few-row GEMM).  The arenas hand
+// out the same addresses for the same shapes, so the forward and the backward launch sequences of a (B, T, M) key are captured
+// once as CUDA graphs and replayed (GraphSlot below; train_model.cuh stages the caller's tensors so that nothing a graph points at
+// moves).  The kernels that matter are sized for bytes in flight rather than FLOPs: skinny_nt_smem / skinny_nn_strip (few-row
+// GEMMs against L2-resident weights), sgemm_tn_rows (weight AND bias gradients of per-step layers gathered over all steps through
+// a row-pointer list), attn_step_* and psine_chain_* (one launch per attention / activation chain of a decoder step).
 #pragma once
 #include <functional>
 #include <string>
@@ -153,8 +160,8 @@ __global__ void __launch_bounds__(256) skinny_nt_kernel(int M, int N, int K, con
             }
         }
 }
-// Sum V = 32 per-lane partial values across the 32 lanes of a warp with 31 shuffles (instead of 32 x 5): each round swaps half
-// of the remaining values with the partner lane, so that lane l ends up owning the complete sum of value #l.
+// Cross-lane sums of MANY per-lane partial values without one butterfly per value: each round swaps half of the remaining values
+// with the partner lane (offset `off`) and adds, so V values cost V - 1 shuffles in total instead of 5 V.
 #define L2S_FOLD_LANES(v, off, cnt)                                                   \
     {                                                                                 \
         const bool up_ = (lane & (off)) != 0;                                         \
@@ -164,16 +171,6 @@ __global__ void __launch_bounds__(256) skinny_nt_kernel(int M, int N, int K, con
             v[i_] = keep_ + __shfl_xor_sync(0xffffffffu, send_, (off));               \
         }                                                                             \
     }
-__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
-    L2S_FOLD_LANES(v, 16, 16) L2S_FOLD_LANES(v, 8, 8) L2S_FOLD_LANES(v, 4, 4) L2S_FOLD_LANES(v, 2, 2) L2S_FOLD_LANES(v, 1, 1)
-    return v[0];
-}
-
-// Few-row GEMM, second form: the CTA first stages ALL of A (M x K, M <= MT) in shared memory, each warp owns NW weight rows and
-// issues every 16-byte weight load of a 512-wide k chunk before it touches them (4 MB of LSTM weights are in flight at once
-// instead of two loads per warp), NW * MT = 32 accumulators per lane are reduced with warp_transpose_sum32.
-// A second operand pair (A2 [M,K2], W2 [N,K2], bias2) is treated as a continuation of the reduction: C = A W^T + A2 W2^T + bias +
-// bias2 in one launch (the two halves of the LSTM gate pre-activation, x W_ih^T + h W_hh^T).  K2 = 0: single product.
 // Folds V per-lane partial values (V = 8, 16 or 32) across the warp; afterwards lane l holds the complete sum of value
 // l / (32 / V) (every lane of that group of 32 / V lanes holds it).
 template <int V>
@@ -191,6 +188,11 @@ __device__ __forceinline__ float warp_fold(float (&v)[V], int lane) {
     }
     return v[0];
 }
+// Few-row GEMM, second form: the CTA first stages ALL of A (M x K, M <= MT) in shared memory, each warp owns NW weight rows and
+// issues every 16-byte weight load of a 512- or 1024-wide k chunk before it touches them (the LSTM weights of a step are in
+// flight at once instead of two loads per warp); the NW * MT accumulators per lane are reduced with warp_fold.
+// A second operand pair (A2 [M,K2], W2 [N,K2], bias2) is treated as a continuation of the reduction: C = A W^T + A2 W2^T + bias +
+// bias2 in one launch (the two halves of the LSTM gate pre-activation, x W_ih^T + h W_hh^T).  K2 = 0: single product.
 template <int NW, int MT>
 __global__ void __launch_bounds__(256) skinny_nt_smem_kernel(int M, int N, int K1, const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
                                                              const float* __restrict__ bias, int K2, const float* __restrict__ A2, int lda2,
@@ -1451,14 +1453,11 @@ struct Engine {
     HostTables* tables = nullptr;      // where a captured backward keeps its row-pointer tables
     size_t table_bytes = 0;            // bytes of pointer tables the last backward uploaded
 
-    unsigned* counters = nullptr;      // zeroed device words for kernels that need a ticket (kept zero between launches)
-    // One-time device state; called outside any stream capture.
+    bool ready = false;
+    // One-time per-device kernel attributes; called outside any stream capture.
     void setup() {
-        if (counters) return;
-        L2S_CUDA(cudaMalloc(&counters, 64 * sizeof(unsigned)));
-        L2S_CUDA(cudaMemset(counters, 0, 64 * sizeof(unsigned)));
-        static bool attrs = false;
-        if (!attrs) {
+        if (ready) return;
+        {
             L2S_CUDA(cudaFuncSetAttribute(skinny_nt_smem_kernel<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKINNY_SMEM_MAX));
             L2S_CUDA(cudaFuncSetAttribute(skinny_nt_smem_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKINNY_SMEM_MAX));
             L2S_CUDA(cudaFuncSetAttribute(skinny_nt_smem_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKINNY_SMEM_MAX));
@@ -1467,10 +1466,10 @@ struct Engine {
             L2S_CUDA(cudaFuncSetAttribute(skinny_nn_strip_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKINNY_SMEM_MAX));
             L2S_CUDA(cudaFuncSetAttribute(skinny_nn_strip_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKINNY_SMEM_MAX));
             L2S_CUDA(cudaFuncSetAttribute(stem_fwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STEM_TILED_SMEM));
-            attrs = true;
+            ready = true;
         }
     }
-    void release() { vals.free_all(); grads.free_all(); if (counters) cudaFree(counters); counters = nullptr; }
+    void release() { vals.free_all(); grads.free_all(); }
     void begin(Context* c, cudaStream_t stream, std::map<std::string, Param>* p) {
         ctx = c; s = stream; params = p; launches = &c->launches;
         vals.reset(); grads.reset(); tape.clear(); deferred.clear(); deferred_scalar.clear(); deferred_scalar_n.clear();
