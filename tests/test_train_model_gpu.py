@@ -44,7 +44,9 @@ def _bind(be, w):
     return dev, grads
 
 
-@pytest.mark.parametrize("B,T,M,tf_ratio,soft,seed", [(3, 29, 10, 0.5, True, 7), (2, 29, 8, 0.3, False, 11), (4, 31, 6, 0.9, True, 13)])
+# (18, ...): more than 16 rows per step — the per-step layers leave the few-row kernels for the general GEMM path; (12, 75, ...): AVSpeech-length clips
+@pytest.mark.parametrize("B,T,M,tf_ratio,soft,seed", [(3, 29, 10, 0.5, True, 7), (2, 29, 8, 0.3, False, 11), (4, 31, 6, 0.9, True, 13),
+                                                     (18, 29, 4, 0.5, True, 17), (12, 75, 5, 0.5, True, 19)])
 def test_decoder_train_forward_backward_vs_oracle(be, B, T, M, tf_ratio, soft, seed):
     from oracle import train_oracle as TO
     w = _decoder_weights(1234, soft)
