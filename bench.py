@@ -285,7 +285,7 @@ def run_train_step(args, rank, local_rank, world):
         line = {"metric": "mel-frames/sec (train step: forward + backward + all-reduce + clip + AdamW) on LRW 29-frame clips, M=77 teacher frames",
                 "value": frames / (total_ms * 1e-3), "unit": "mel-frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32 (exact fp32 FMA train kernels)", "data": "synthetic",
+                "dtype": "f32 (fp32 FMA kernels; the decoder's large GEMMs as 3xTF32 tensor-core products with fp32 accumulation)", "data": "synthetic",
                 "config": {"workload": f"train.py:167-193 step, {B} clips per GPU (BASELINE configs[3]: batch 64 over 8 GPUs), T=29, 96x96, M=77; "
                                        "train-mode video frontend + decoder (BatchNorm batch statistics, all dropout sites, BPTT), Loss, "
                                        "gradient all-reduce, clip_grad_norm_(1.0), AdamW(amsgrad)", "name": "c3", "batch_per_gpu": B,
@@ -296,7 +296,7 @@ def run_train_step(args, rank, local_rank, world):
                 "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"kernel": "sgemm_kernel (SIMT fp32 GEMM of the train path)", "bound": "tensor", "achieved": None, "peak": None, "unit": "TFLOP/s",
                              "frac": None, "traffic": None,
-                             "note": "exact-fp32 train kernels replayed as CUDA graphs: a chain of ~5 K dependent small launches per step (profiles/r2_train_step_kernel_shares.txt); no single kernel dominates, so no roofline claim is made for this config"}}
+                             "note": "fp32 train kernels replayed as CUDA graphs: a chain of ~5 K dependent small launches per step (profiles/r2_train_step_kernel_shares.txt); no single kernel dominates, so no roofline claim is made for this config"}}
         if not args.no_eager_baseline:
             times = oracle_train_step(B, T, M, reps=3, device=f"cuda:{local_rank}")
             line["gpu_eager_baseline"] = {"value": B * M / statistics.median(times), "unit": "mel-frames/s", "ms_per_step": 1e3 * statistics.median(times),

@@ -24,6 +24,7 @@
 
 #include "common.cuh"
 #include "context.h"
+#include "matvec.cuh"
 
 namespace l2s {
 namespace tr {
@@ -43,16 +44,27 @@ struct TT {                       // train tensor: [rows][cols] view, element (r
 
 // ---- kernels: GEMM ------------------------------------------------------------------------------------------------------
 // C[M,N] (+)= A' B'  with A' = A (TA=0: A[m*lda + k]) or A^T (TA=1: A[k*lda + m]); B' = B (TB=0: B[k*ldb + n]) or B^T (TB=1: B[n*ldb + k]).
+// 64x64 output tile per CTA, 32-deep k tiles fetched one tile ahead into registers; 8 warps = 4 (m16) x 2 (32 columns = four n8
+// tiles) run mma.sync.m16n8k8 with the 3xTF32 split done on the fragments (a_lo b_hi + a_hi b_lo + a_hi b_hi, fp32 accumulate:
+// the accuracy class of the inference path's GEMMs, ~2^-21 per product).  The tiles sit in shared memory in the layout in which
+// BOTH the coalesced global->shared stores and the fragment loads are bank-conflict-free: the contiguous index of the operand
+// in memory stays contiguous (row stride 36 when that is k, 72 when it is m / n).
 // gridDim.z > 1: split over K — block z reduces K range [z*kper, (z+1)*kper) into its own [M][N] slab at C + z*M*ldc (the caller
 // sums the slabs in order: a tall-skinny weight gradient, M x N small and K = tens of thousands of rows, would otherwise run on
 // one or four CTAs).
-template <int TA, int TB>
+// EXACT: the same tiles multiplied with fp32 FMAs (4x4 outputs per thread) instead of tensor cores.  The video frontend needs it:
+// its BatchNorm + ReLU stacks on a small batch amplify a 2^-21 product error into flipped ReLU decisions, and single entries of
+// some gradients then move by percents (tests/test_train_model_gpu.py: _check_against_fp64 measures exactly that).
+template <int TA, int TB, bool EXACT>
 __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                                                     float* __restrict__ C, int ldc, int accumulate, int kper) {
     constexpr int BM = 64, BN = 64, BK = 32;
-    __shared__ float As[BK][BM + 1];
-    __shared__ float Bs[BK][BN + 1];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    constexpr int A_LD = TA == 0 ? BK + 4 : BM + 8, B_LD = TB == 0 ? BN + 8 : BK + 4;
+    __shared__ float As[BM * (BK + 4)];                                // both layouts need 2304 floats
+    __shared__ float Bs[BN * (BK + 4)];
+    static_assert(BM * (BK + 4) == BK * (BM + 8) && BN * (BK + 4) == BK * (BN + 8), "tile layouts");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3, wm = warp & 3, wn = warp >> 2;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int kbeg = blockIdx.z * kper;
     if (gridDim.z > 1) { C += (size_t)blockIdx.z * M * ldc; K = min(K, kbeg + kper); }
@@ -61,8 +73,6 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const f
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    // 2048 elements per operand tile, 8 per thread; the next tile is fetched into registers while the current one is multiplied
-    // (these GEMMs have short K or few tiles: without the prefetch every 16-wide k step paid a full L2 round trip).
     float ra[8], rb[8];
     auto fetch = [&](int k0) {
 #pragma unroll
@@ -82,36 +92,62 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const f
             }
         }
     };
+    auto a_at = [&](int m, int k) -> float { return TA == 0 ? As[m * A_LD + k] : As[k * A_LD + m]; };
+    auto b_at = [&](int k, int n) -> float { return TB == 0 ? Bs[k * B_LD + n] : Bs[n * B_LD + k]; };
     fetch(kbeg);
     for (int k0 = kbeg; k0 < K; k0 += BK) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int e = tid + i * 256;
-            if (TA == 0) As[e & 31][e >> 5] = ra[i]; else As[e >> 6][e & 63] = ra[i];
-            if (TB == 0) Bs[e >> 6][e & 63] = rb[i]; else Bs[e & 31][e >> 5] = rb[i];
+            if (TA == 0) As[(e >> 5) * A_LD + (e & 31)] = ra[i]; else As[(e >> 6) * A_LD + (e & 63)] = ra[i];
+            if (TB == 0) Bs[(e >> 6) * B_LD + (e & 63)] = rb[i]; else Bs[(e >> 5) * B_LD + (e & 31)] = rb[i];
         }
         __syncthreads();
         if (k0 + BK < K) fetch(k0 + BK);
+        if (EXACT) {
+            const int tx = tid & 15, ty = tid >> 4;
 #pragma unroll
-        for (int k = 0; k < BK; ++k) {
-            float a[4], b[4];
+            for (int k = 0; k < BK; ++k) {
+                float a[4], b[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { a[i] = As[k][ty + 16 * i]; b[i] = Bs[k][tx + 16 * i]; }
+                for (int i = 0; i < 4; ++i) { a[i] = a_at(ty + 16 * i, k); b[i] = b_at(k, tx + 16 * i); }
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            }
+        } else
+#pragma unroll
+        for (int ks = 0; ks < BK; ks += 8) {
+            uint32_t ah[4], al[4];
+            split_tf32(a_at(wm * 16 + g, ks + t), ah[0], al[0]);
+            split_tf32(a_at(wm * 16 + g + 8, ks + t), ah[1], al[1]);
+            split_tf32(a_at(wm * 16 + g, ks + t + 4), ah[2], al[2]);
+            split_tf32(a_at(wm * 16 + g + 8, ks + t + 4), ah[3], al[3]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint32_t bh[2], bl[2];
+                const int n = wn * 32 + j * 8 + g;
+                split_tf32(b_at(ks + t, n), bh[0], bl[0]);
+                split_tf32(b_at(ks + t + 4, n), bh[1], bl[1]);
+                mma_tf32(acc[j], al[0], al[1], al[2], al[3], bh[0], bh[1]);
+                mma_tf32(acc[j], ah[0], ah[1], ah[2], ah[3], bl[0], bl[1]);
+                mma_tf32(acc[j], ah[0], ah[1], ah[2], ah[3], bh[0], bh[1]);
+            }
         }
         __syncthreads();
     }
+    // tensor cores: acc[j] = {(r, c), (r, c+1), (r+8, c), (r+8, c+1)}, r = m0 + 16 wm + g, c = n0 + 32 wn + 8 j + 2 t;
+    // EXACT: acc[i][j] = (m0 + ty + 16 i, n0 + tx + 16 j)
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int m = m0 + ty + 16 * i, n = n0 + tx + 16 * j;
+        for (int q = 0; q < 4; ++q) {
+            const int m = EXACT ? m0 + (tid >> 4) + 16 * j : m0 + wm * 16 + g + 8 * (q >> 1);
+            const int n = EXACT ? n0 + (tid & 15) + 16 * q : n0 + wn * 32 + j * 8 + 2 * t + (q & 1);
             if (m < M && n < N) {
                 float* c = C + (size_t)m * ldc + n;
-                *c = accumulate ? *c + acc[i][j] : acc[i][j];
+                *c = accumulate ? *c + acc[j][q] : acc[j][q];
             }
         }
 }
@@ -392,10 +428,11 @@ __global__ void skinny_nn_sum_kernel(int M, int K, int nslices, const float* __r
 // db (optional): the bias gradient db[n] += sum_i A_i[n], formed by the CTAs of the first column block from the tiles they load anyway.
 __global__ void __launch_bounds__(256) sgemm_tn_rows_kernel(int N, int K, int R, const float* const* __restrict__ rowsA, const float* const* __restrict__ rowsB,
                                                             float* __restrict__ C, int ldc, float* __restrict__ db) {
-    constexpr int BM = 64, BN = 64, BK = 32;
-    __shared__ float As[BK][BM + 1];
-    __shared__ float Bs[BK][BN + 1];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    constexpr int BM = 64, BN = 64, BK = 32, LD = 72;                  // both tiles k-major [BK][64 + 8]: see sgemm_kernel
+    __shared__ float As[BK * LD];
+    __shared__ float Bs[BK * LD];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3, wm = warp & 3, wn = warp >> 2;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     float acc[4][4];
 #pragma unroll
@@ -423,31 +460,39 @@ __global__ void __launch_bounds__(256) sgemm_tn_rows_kernel(int N, int K, int R,
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int e = tid + i * 256;
-            As[e >> 6][e & 63] = ra[i]; Bs[e >> 6][e & 63] = rb[i];
+            As[(e >> 6) * LD + (e & 63)] = ra[i]; Bs[(e >> 6) * LD + (e & 63)] = rb[i];
         }
         __syncthreads();
         if (r0 + BK < R) fetch(r0 + BK);
         if (sums)
 #pragma unroll
-            for (int k = 0; k < BK; ++k) bsum += As[k][tid];
+            for (int k = 0; k < BK; ++k) bsum += As[k * LD + tid];
 #pragma unroll
-        for (int k = 0; k < BK; ++k) {
-            float a[4], b[4];
+        for (int ks = 0; ks < BK; ks += 8) {
+            uint32_t ah[4], al[4];
+            split_tf32(As[(ks + t) * LD + wm * 16 + g], ah[0], al[0]);
+            split_tf32(As[(ks + t) * LD + wm * 16 + g + 8], ah[1], al[1]);
+            split_tf32(As[(ks + t + 4) * LD + wm * 16 + g], ah[2], al[2]);
+            split_tf32(As[(ks + t + 4) * LD + wm * 16 + g + 8], ah[3], al[3]);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { a[i] = As[k][ty + 16 * i]; b[i] = Bs[k][tx + 16 * i]; }
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            for (int j = 0; j < 4; ++j) {
+                uint32_t bh[2], bl[2];
+                const int n = wn * 32 + j * 8 + g;
+                split_tf32(Bs[(ks + t) * LD + n], bh[0], bl[0]);
+                split_tf32(Bs[(ks + t + 4) * LD + n], bh[1], bl[1]);
+                mma_tf32(acc[j], al[0], al[1], al[2], al[3], bh[0], bh[1]);
+                mma_tf32(acc[j], ah[0], ah[1], ah[2], ah[3], bl[0], bl[1]);
+                mma_tf32(acc[j], ah[0], ah[1], ah[2], ah[3], bh[0], bh[1]);
+            }
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int m = m0 + ty + 16 * i, n = n0 + tx + 16 * j;
-            if (m < N && n < K) C[(size_t)m * ldc + n] += acc[i][j];
+        for (int q = 0; q < 4; ++q) {
+            const int m = m0 + wm * 16 + g + 8 * (q >> 1), n = n0 + wn * 32 + j * 8 + 2 * t + (q & 1);
+            if (m < N && n < K) C[(size_t)m * ldc + n] += acc[j][q];
         }
     if (sums && m0 + tid < N) db[m0 + tid] += bsum;
 }
@@ -1448,6 +1493,7 @@ struct Engine {
     std::vector<std::function<void()>> tape;
     std::map<std::string, Param>* params = nullptr;
     bool update_bn_running = true;
+    bool exact_gemm = false;           // large GEMMs with fp32 FMAs instead of 3xTF32 tensor-core products (see sgemm_kernel)
     int64_t* launches = nullptr;
     bool capturing = false;            // the body runs under stream capture: no synchronisation, host tables must persist
     HostTables* tables = nullptr;      // where a captured backward keeps its row-pointer tables
@@ -1577,13 +1623,15 @@ struct Engine {
             const int nz = (K + kper - 1) / kper;
             float* part = scratch((size_t)nz * M * N);
             grid.z = nz;
-            sgemm_kernel<TA, TB><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, part, N, 0, kper);
+            if (exact_gemm) sgemm_kernel<TA, TB, true><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, part, N, 0, kper);
+            else sgemm_kernel<TA, TB, false><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, part, N, 0, kper);
             ck("sgemm split-K");
             skinny_nn_sum_kernel<<<ew_blocks((size_t)M * N), 256, 0, s>>>(M, N, nz, part, C, ldc, acc ? 1 : 0);
             ck("sgemm split-K sum");
             return;
         }
-        sgemm_kernel<TA, TB><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, acc ? 1 : 0, K);
+        if (exact_gemm) sgemm_kernel<TA, TB, true><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, acc ? 1 : 0, K);
+        else sgemm_kernel<TA, TB, false><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, acc ? 1 : 0, K);
         ck("sgemm");
     }
 

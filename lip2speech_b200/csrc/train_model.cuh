@@ -391,6 +391,7 @@ struct VideoTrain {
         if (B <= 0 || T <= 0 || (H & 3) || (W & 3)) throw L2sError(1, "video_train_fwd: bad shape");
         live = false;
         e.setup();
+        e.exact_gemm = true;                                        // BatchNorm + ReLU stacks: see sgemm_kernel
         if (gen != bind_gen) { drop_graphs(); bind_gen = gen; }
         const size_t N = (size_t)B * T;
         io.reset();
