@@ -153,8 +153,27 @@ class _VideoTrainFn(torch.autograd.Function):
         return (None, None, None, None, *_grad_views(ctx.scratch, *ctx.layout, ctx.params))
 
 
+def _members(module, prefix):
+    """(keys, parameters, named buffers) of `module`.  named_parameters() / named_buffers() cost ~1 ms per call on these trees,
+    which a 25 ms train step would pay twice per forward — so the tree is walked once per module object and only the (owner, name)
+    slots are remembered: the tensors are re-read from their owners on every call (.to() / .cuda() replace buffer objects, an
+    optimizer may replace parameters).  Registering NEW submodules after the first train-mode forward needs
+    `del module._l2s_members`."""
+    slots = module.__dict__.get("_l2s_members")
+    if slots is None:
+        pslots, bslots = [], []
+        for mname, m in module.named_modules():
+            dot = mname + "." if mname else ""
+            pslots += [(prefix + dot + n, m, n) for n, p in m._parameters.items() if p is not None]
+            bslots += [(dot + n, m, n) for n, b in m._buffers.items() if b is not None]
+        slots = (pslots, bslots)
+        object.__setattr__(module, "_l2s_members", slots)
+    pslots, bslots = slots
+    return [k for k, _, _ in pslots], [m._parameters[n] for _, m, n in pslots], [(k, m._buffers[n]) for k, m, n in bslots]
+
+
 def _bind_buffers(be, module, prefix):
-    named = list(module.named_buffers())
+    named = _members(module, prefix)[2]
     floats = [(prefix + n, b) for n, b in named if b.is_floating_point()]
     cache = be.__dict__.setdefault("_train_buffers", {})
     sig = tuple((k, b.data_ptr()) for k, b in floats)
@@ -171,8 +190,8 @@ def video_forward_train(module, prefix, x, drop_mask=None):
     """Train-mode VideoExtractor.forward for any module owning the reference's encoder parameters under the reference's names."""
     be = _lib.backend(_device_index(module))
     _bind_buffers(be, module, prefix)
-    named = [(prefix + n, p) for n, p in module.named_parameters()]
-    return _VideoTrainFn.apply(be, drop_mask, [k for k, _ in named], x, *[p for _, p in named])
+    keys, params, _ = _members(module, prefix)
+    return _VideoTrainFn.apply(be, drop_mask, keys, x, *params)
 
 
 def decoder_forward_train(module, prefix, encoder_outputs, face_features, mels, tf_ratio, noise=None):
@@ -184,8 +203,7 @@ def decoder_forward_train(module, prefix, encoder_outputs, face_features, mels, 
     if noise is None:
         noise = TrainNoise.draw(B, T, M, float(tf_ratio), encoder_outputs.device)
     _bind_buffers(be, module, prefix)
-    named = [(prefix + n, p) for n, p in module.named_parameters()]
-    keys, params = [k for k, _ in named], [p for _, p in named]
+    keys, params, _ = _members(module, prefix)
     spk = face_features[:, 0]
     out_mel, out_post, out_stop, out_attn, out_dis = _DecoderTrainFn.apply(be, noise, keys, encoder_outputs, spk, mels, *params)
     return [out_mel, out_post, out_stop, spk, out_attn, out_dis]

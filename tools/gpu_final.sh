@@ -6,7 +6,7 @@ timeout 1200 python -m pytest tests -m gpu -q --tb=short 2>&1 | grep -v "UserWar
 python bench.py --steps 20 --warmup 5 > gpurun_out/final_bench_c2.json 2> gpurun_out/final_bench_c2.err
 python bench.py --config c1 --steps 20 --warmup 3 > gpurun_out/final_bench_c1.json 2> gpurun_out/final_bench_c1.err
 timeout 600 python bench.py --config c4 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/final_bench_c4.json 2> gpurun_out/final_bench_c4.err
-timeout 900 python bench.py --config c3 --steps 5 --warmup 3 > gpurun_out/final_bench_c3.json 2> gpurun_out/final_bench_c3.err
+timeout 900 python bench.py --config c3 --steps 20 --warmup 3 > gpurun_out/final_bench_c3.json 2> gpurun_out/final_bench_c3.err
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/final_bench_ref.json 2> gpurun_out/final_bench_ref.err
 tail -2 gpurun_out/final_smoke.txt; grep -E "^(FAILED|ERROR)|passed|failed" gpurun_out/final_pytest.txt
 python - <<'PY'
