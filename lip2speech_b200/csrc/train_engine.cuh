@@ -29,6 +29,28 @@
 namespace l2s {
 namespace tr {
 
+// ---- launches ---------------------------------------------------------------------------------------------------------------------
+// A train step is a chain of ~5 K small DEPENDENT kernels; what separates two of them is mostly launch latency.  Every kernel of
+// this file therefore starts with griddepcontrol.wait and is launched with programmatic stream serialization (programmatic
+// dependent launch): the next kernel's CTAs are scheduled while the previous kernel drains, and block at the wait until that grid
+// has completed and its memory is visible — the semantics of a plain stream dependency, without the gap.  Right after its own wait
+// a kernel lets its dependents launch (they do nothing before THEIR wait, so nothing runs ahead of its inputs; one kernel deep).
+// The attribute is also honoured inside captured graphs (programmatic edges).
+#define TR_PDL_WAIT() asm volatile("griddepcontrol.wait;\n\tgriddepcontrol.launch_dependents;" ::: "memory")
+inline bool& pdl_enabled() { static bool on = true; return on; }
+template <typename... KArgs, typename... Args>
+inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    static_assert(sizeof...(KArgs) == sizeof...(Args), "kernel argument count");
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+    if (e != cudaSuccess) throw L2sError(2, std::string("train: kernel launch: ") + cudaGetErrorString(e));
+}
+
 struct TT {                       // train tensor: [rows][cols] view, element (r, c) at v[r*rs + c]
     float* v = nullptr;
     float* g = nullptr;           // gradient with the same layout (null: no gradient wanted)
@@ -58,6 +80,7 @@ struct TT {                       // train tensor: [rows][cols] view, element (r
 template <int TA, int TB, bool EXACT>
 __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                                                     float* __restrict__ C, int ldc, int accumulate, int kper) {
+    TR_PDL_WAIT();
     constexpr int BM = 64, BN = 64, BK = 32;
     constexpr int A_LD = TA == 0 ? BK + 4 : BM + 8, B_LD = TB == 0 ? BN + 8 : BK + 4;
     __shared__ float As[BM * (BK + 4)];                                // both layouts need 2304 floats
@@ -159,6 +182,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const f
 template <bool VEC>
 __global__ void __launch_bounds__(256) skinny_nt_kernel(int M, int N, int K, const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
                                                         const float* __restrict__ bias, float* __restrict__ C, int ldc, int accumulate) {
+    TR_PDL_WAIT();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= N) return;
     float acc[16];
@@ -234,6 +258,7 @@ __global__ void __launch_bounds__(256) skinny_nt_smem_kernel(int M, int N, int K
                                                              const float* __restrict__ bias, int K2, const float* __restrict__ A2, int lda2,
                                                              const float* __restrict__ W2, int ldw2, const float* __restrict__ bias2,
                                                              float* __restrict__ C, int ldc, int accumulate) {
+    TR_PDL_WAIT();
     const int K = K1 + K2;
     constexpr int V = NW * MT;                                        // accumulators per lane
     constexpr int J = NW * MT <= 16 ? 8 : 4;                          // 16-byte weight loads per row kept in flight: a chunk of 128 J columns
@@ -303,6 +328,7 @@ template <int MT>
 __global__ void __launch_bounds__(NN_THREADS) skinny_nn_strip_kernel(int M, int N, int K, const float* __restrict__ dY, int ldy, const float* __restrict__ W, int ldw,
                                                                      float* __restrict__ dX, int ldx, int K2, const float* __restrict__ W2, int ldw2,
                                                                      float* __restrict__ dX2, int ldx2) {
+    TR_PDL_WAIT();
     if (blockIdx.y == 1) { K = K2; W = W2; ldw = ldw2; dX = dX2; ldx = ldx2; }
     if ((int)blockIdx.x * 8 >= K) return;
     extern __shared__ float4 nn_sm4[];
@@ -389,6 +415,7 @@ __global__ void __launch_bounds__(NN_THREADS) skinny_nn_strip_kernel(int M, int 
 // stage 2: dX (+)= sum over the slices in order.
 __global__ void __launch_bounds__(256) skinny_nn_part_kernel(int M, int N, int K, int nslice, const float* __restrict__ dY, int ldy,
                                                              const float* __restrict__ W, int ldw, float* __restrict__ part) {
+    TR_PDL_WAIT();
     __shared__ float red[4][16][65];
     const int kx = threadIdx.x & 63, ny = threadIdx.x >> 6;
     const int k = blockIdx.x * 64 + kx;
@@ -412,6 +439,7 @@ __global__ void __launch_bounds__(256) skinny_nn_part_kernel(int M, int N, int K
             part[((size_t)blockIdx.y * M + m) * K + k] = (red[0][m][kx] + red[1][m][kx]) + (red[2][m][kx] + red[3][m][kx]);
 }
 __global__ void skinny_nn_sum_kernel(int M, int K, int nslices, const float* __restrict__ part, float* __restrict__ dX, int ldx, int accumulate) {
+    TR_PDL_WAIT();
     const size_t total = (size_t)M * K;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int m = i / K, k = i % K;
@@ -428,6 +456,7 @@ __global__ void skinny_nn_sum_kernel(int M, int K, int nslices, const float* __r
 // db (optional): the bias gradient db[n] += sum_i A_i[n], formed by the CTAs of the first column block from the tiles they load anyway.
 __global__ void __launch_bounds__(256) sgemm_tn_rows_kernel(int N, int K, int R, const float* const* __restrict__ rowsA, const float* const* __restrict__ rowsB,
                                                             float* __restrict__ C, int ldc, float* __restrict__ db) {
+    TR_PDL_WAIT();
     constexpr int BM = 64, BN = 64, BK = 32, LD = 72;                  // both tiles k-major [BK][64 + 8]: see sgemm_kernel
     __shared__ float As[BK * LD];
     __shared__ float Bs[BK * LD];
@@ -505,6 +534,7 @@ enum ColOp { COL_SUM = 0, COL_SUM_XY = 1, COL_PSINE_DW = 2, COL_PRELU_DW = 3, CO
 template <int OP>
 __global__ void __launch_bounds__(256) colreduce_kernel(int rows, int cols, const float* __restrict__ X, int xs, const float* __restrict__ Y, int ys,
                                                         const float* __restrict__ aux, const float* __restrict__ aux2, float eps, float* __restrict__ part) {
+    TR_PDL_WAIT();
     __shared__ float p0[8][33];
     const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
@@ -537,6 +567,7 @@ __global__ void __launch_bounds__(256) colreduce_kernel(int rows, int cols, cons
 // out[c] = (accumulate ? out[c] : 0) + scale * sum_split part[split][c]; one warp per column: lanes stride over the splits, then
 // a fixed shuffle tree (deterministic for a given split count).
 __global__ void colfinish_kernel(int cols, int splits, const float* __restrict__ part, float scale, float* __restrict__ out, int accumulate) {
+    TR_PDL_WAIT();
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= cols) return;
     float s = 0.f;
@@ -548,6 +579,7 @@ __global__ void colfinish_kernel(int cols, int splits, const float* __restrict__
 // Full reduction sum(X*Y) -> out[0] (+)=, single CTA (used for the two scalar temperatures).
 __global__ void __launch_bounds__(1024) dot_all_kernel(int rows, int cols, const float* __restrict__ X, int xs, const float* __restrict__ Y, int ys,
                                                        float* __restrict__ out, int accumulate) {
+    TR_PDL_WAIT();
     __shared__ float part[32];
     float a = 0.f;
     const size_t n = (size_t)rows * cols;
@@ -570,6 +602,7 @@ enum EwOp { EW_COPY = 0, EW_ADD, EW_SILU, EW_RELU, EW_PSINE, EW_PRELU, EW_SCALE,
 template <int OP>
 __global__ void ew_fwd_kernel(int rows, int cols, const float* X, int xs, const float* __restrict__ aux, int as, float alpha, int group,
                               float* Y, int ys) {
+    TR_PDL_WAIT();
     TR_EW_LOOP((size_t)rows * cols) {
         const int r = i / cols, c = i % cols;
         const float x = X[(size_t)r * xs + c];
@@ -590,6 +623,7 @@ __global__ void ew_fwd_kernel(int rows, int cols, const float* X, int xs, const 
 template <int OP>
 __global__ void ew_bwd_kernel(int rows, int cols, const float* __restrict__ X, int xs, const float* __restrict__ aux, int as, float alpha,
                               const float* __restrict__ dY, int dys, float* __restrict__ dX, int dxs) {
+    TR_PDL_WAIT();
     TR_EW_LOOP((size_t)rows * cols) {
         const int r = i / cols, c = i % cols;
         const float dy = dY[(size_t)r * dys + c];
@@ -606,15 +640,18 @@ __global__ void ew_bwd_kernel(int rows, int cols, const float* __restrict__ X, i
 }
 __global__ void select_fwd_kernel(int rows, int cols, const float* __restrict__ flag, const float* __restrict__ A, int as, const float* __restrict__ Bv, int bs,
                                   float* __restrict__ Y, int ys) {
+    TR_PDL_WAIT();
     const bool pick_a = flag[0] != 0.f;
     TR_EW_LOOP((size_t)rows * cols) { const int r = i / cols, c = i % cols; Y[(size_t)r * ys + c] = pick_a ? A[(size_t)r * as + c] : Bv[(size_t)r * bs + c]; }
 }
 __global__ void select_bwd_kernel(int rows, int cols, const float* __restrict__ flag, const float* __restrict__ dY, int dys, float* __restrict__ dB, int dbs) {
+    TR_PDL_WAIT();
     if (flag[0] != 0.f) return;
     TR_EW_LOOP((size_t)rows * cols) { const int r = i / cols, c = i % cols; dB[(size_t)r * dbs + c] += dY[(size_t)r * dys + c]; }
 }
 // dAux[g][c] += sum over the `group` rows of group g of dY   (backward of EW_ADDROW w.r.t. the broadcast operand)
 __global__ void addrow_bwd_kernel(int groups, int group, int cols, const float* __restrict__ dY, int dys, float* __restrict__ dA, int das) {
+    TR_PDL_WAIT();
     TR_EW_LOOP((size_t)groups * cols) {
         const int g = i / cols, c = i % cols;
         float a = 0.f;
@@ -625,10 +662,12 @@ __global__ void addrow_bwd_kernel(int groups, int group, int cols, const float* 
 
 // y = x * w[0] (learnable scalar: the attention temperatures, decoder.py:302,237)
 __global__ void scale_param_kernel(int rows, int cols, const float* __restrict__ X, int xs, const float* __restrict__ w, float* __restrict__ Y, int ys) {
+    TR_PDL_WAIT();
     const float a = w[0];
     TR_EW_LOOP((size_t)rows * cols) { const int r = i / cols, c = i % cols; Y[(size_t)r * ys + c] = X[(size_t)r * xs + c] * a; }
 }
 __global__ void scale_param_bwd_kernel(int rows, int cols, const float* __restrict__ w, const float* __restrict__ dY, int dys, float* __restrict__ dX, int dxs) {
+    TR_PDL_WAIT();
     const float a = w[0];
     TR_EW_LOOP((size_t)rows * cols) { const int r = i / cols, c = i % cols; dX[(size_t)r * dxs + c] += dY[(size_t)r * dys + c] * a; }
 }
@@ -636,6 +675,7 @@ __global__ void scale_param_bwd_kernel(int rows, int cols, const float* __restri
 // BatchNorm (train): y = (x - mean) * rstd * gamma + beta
 __global__ void bn_fwd_kernel(int rows, int cols, const float* __restrict__ X, int xs, const float* __restrict__ mean, const float* __restrict__ var, float eps,
                               const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ Y, int ys) {
+    TR_PDL_WAIT();
     TR_EW_LOOP((size_t)rows * cols) {
         const int r = i / cols, c = i % cols;
         Y[(size_t)r * ys + c] = (X[(size_t)r * xs + c] - mean[c]) * rsqrtf(var[c] + eps) * gamma[c] + beta[c];
@@ -645,6 +685,7 @@ __global__ void bn_fwd_kernel(int rows, int cols, const float* __restrict__ X, i
 __global__ void bn_bwd_kernel(int rows, int cols, const float* __restrict__ X, int xs, const float* __restrict__ mean, const float* __restrict__ var, float eps,
                               const float* __restrict__ gamma, const float* __restrict__ dgamma, const float* __restrict__ dbeta,
                               const float* __restrict__ dY, int dys, float* __restrict__ dX, int dxs) {
+    TR_PDL_WAIT();
     const float invR = 1.f / (float)rows;
     TR_EW_LOOP((size_t)rows * cols) {
         const int r = i / cols, c = i % cols;
@@ -656,6 +697,7 @@ __global__ void bn_bwd_kernel(int rows, int cols, const float* __restrict__ X, i
 // running = (1 - momentum) * running + momentum * stat  (variance: unbiased, x rows/(rows-1)); nn.BatchNorm*d in train()
 __global__ void bn_running_kernel(int cols, int rows, float momentum, const float* __restrict__ mean, const float* __restrict__ var,
                                   float* __restrict__ rmean, float* __restrict__ rvar) {
+    TR_PDL_WAIT();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cols) return;
     rmean[c] = (1.f - momentum) * rmean[c] + momentum * mean[c];
@@ -665,6 +707,7 @@ __global__ void bn_running_kernel(int cols, int rows, float momentum, const floa
 
 // softmax over the columns of every row (one warp per row)
 __global__ void __launch_bounds__(256) softmax_fwd_kernel(int rows, int cols, const float* __restrict__ X, int xs, float* __restrict__ Y, int ys) {
+    TR_PDL_WAIT();
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (r >= rows) return;
     const float* x = X + (size_t)r * xs;
@@ -679,6 +722,7 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(int rows, int cols, co
 // dx += y * (dy - sum(dy*y))
 __global__ void __launch_bounds__(256) softmax_bwd_kernel(int rows, int cols, const float* __restrict__ Y, int ys, const float* __restrict__ dY, int dys,
                                                           float* __restrict__ dX, int dxs) {
+    TR_PDL_WAIT();
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (r >= rows) return;
     float s = 0.f;
@@ -691,6 +735,7 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(int rows, int cols, co
 // scores[b][t] = sum_k q[b][k] * Kmem[(b*T + t)][k]       (one warp per (b, t))
 __global__ void __launch_bounds__(256) attn_scores_kernel(int B, int T, int D, const float* __restrict__ Q, int qs, const float* __restrict__ Km, int ks,
                                                           float* __restrict__ S, int ss) {
+    TR_PDL_WAIT();
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= B * T) return;
     const int b = w / T, t = w % T;
@@ -702,6 +747,7 @@ __global__ void __launch_bounds__(256) attn_scores_kernel(int B, int T, int D, c
 // dq[b][k] += sum_t dS[b][t] K[b,t,k] ;  dK[b,t,k] += dS[b][t] q[b][k]      (thread per (b, k))
 __global__ void attn_scores_bwd_kernel(int B, int T, int D, const float* __restrict__ Q, int qs, const float* __restrict__ Km, int ks,
                                        const float* __restrict__ dS, int dss, float* __restrict__ dQ, int dqs, float* __restrict__ dK, int dks) {
+    TR_PDL_WAIT();
     TR_EW_LOOP((size_t)B * D) {
         const int b = i / D, k = i % D;
         const float q = Q[(size_t)b * qs + k];
@@ -716,6 +762,7 @@ __global__ void attn_scores_bwd_kernel(int B, int T, int D, const float* __restr
 }
 // ctx[b][k] = sum_t a[b][t] V[(b*T + t)][k]
 __global__ void attn_context_kernel(int B, int T, int D, const float* __restrict__ A, int as, const float* __restrict__ V, int vs, float* __restrict__ C, int cs) {
+    TR_PDL_WAIT();
     TR_EW_LOOP((size_t)B * D) {
         const int b = i / D, k = i % D;
         float acc = 0.f;
@@ -726,6 +773,7 @@ __global__ void attn_context_kernel(int B, int T, int D, const float* __restrict
 // dA[b][t] += sum_k dC[b][k] V[b,t,k]  (warp per (b,t)) ; dV[b,t,k] += a[b][t] dC[b][k]
 __global__ void __launch_bounds__(256) attn_context_bwd_kernel(int B, int T, int D, const float* __restrict__ A, int as, const float* __restrict__ V, int vs,
                                                                const float* __restrict__ dC, int dcs, float* __restrict__ dA, int das, float* __restrict__ dV, int dvs) {
+    TR_PDL_WAIT();
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= B * T) return;
     const int b = w / T, t = w % T;
@@ -752,6 +800,7 @@ __global__ void __launch_bounds__(256) attn_step_fwd_kernel(int T, int D, int DV
                                                             const float* __restrict__ Km, int ks, const float* __restrict__ mask, float alpha,
                                                             const float* __restrict__ V, int vs, float* __restrict__ sraw, float* __restrict__ A,
                                                             float* __restrict__ logits, int ls, float* __restrict__ C, int cs) {
+    TR_PDL_WAIT();
     __shared__ float sc[320];
     __shared__ float red[2];
     __shared__ float4 part[8][32];
@@ -828,6 +877,7 @@ __global__ void __launch_bounds__(256) attn_step_bwd_kernel(int T, int D, int DV
                                                             const float* __restrict__ V, int vs, const float* __restrict__ sraw, const float* __restrict__ A,
                                                             const float* __restrict__ dC, int dcs, float* __restrict__ dQ, int dqs, float* __restrict__ dK, int dks,
                                                             float* __restrict__ dV, int dvs, float* __restrict__ dwpart) {
+    TR_PDL_WAIT();
     __shared__ float da[320];
     __shared__ float ds[320];
     __shared__ float red[1];
@@ -914,6 +964,7 @@ __global__ void __launch_bounds__(256) attn_step_bwd_kernel(int T, int D, int DV
 }
 // out[0] += sum over a list of R arrays of n floats, in list order (the per-step, per-clip temperature-gradient partials)
 __global__ void __launch_bounds__(256) sum_list_kernel(int R, int n, const float* const* __restrict__ list, float* __restrict__ out) {
+    TR_PDL_WAIT();
     __shared__ float part[8];
     float a = 0.f;
     for (int i = threadIdx.x; i < R * n; i += 256) a += list[i / n][i % n];
@@ -927,6 +978,7 @@ __global__ void __launch_bounds__(256) sum_list_kernel(int R, int n, const float
 // linear, in one pass (prenet: decoder.py:306-309; query: :359-360).
 __global__ void psine_chain_fwd_kernel(int rows, int cols, const float* __restrict__ X, int xs, const float* __restrict__ w, const float* __restrict__ mask, int ms,
                                        float alpha, const float* __restrict__ addc, int as, float* __restrict__ Y, int ys) {
+    TR_PDL_WAIT();
     TR_EW_LOOP((size_t)rows * cols) {
         const int r = i / cols, c = i % cols;
         float y = sinf(X[(size_t)r * xs + c]) * w[c];
@@ -940,6 +992,7 @@ __global__ void psine_chain_fwd_kernel(int rows, int cols, const float* __restri
 __global__ void __launch_bounds__(256) psine_chain_bwd_kernel(int rows, int cols, const float* __restrict__ X, int xs, const float* __restrict__ w,
                                                               const float* __restrict__ mask, int ms, float alpha, const float* __restrict__ dY, int dys,
                                                               float* __restrict__ dX, int dxs, float* __restrict__ dw) {
+    TR_PDL_WAIT();
     __shared__ float red[16][33];
     const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
@@ -971,6 +1024,7 @@ __global__ void __launch_bounds__(256) psine_chain_bwd_kernel(int rows, int cols
 // gates [B][4H] (pre-activation) + c_prev [B][H] -> act [B][4H] (sigmoid/tanh applied, saved for backward), c [B][H], h [B][H]
 __global__ void lstm_cell_fwd_kernel(int B, int H, const float* __restrict__ G, int gs, const float* __restrict__ Cp, int cps,
                                      float* __restrict__ Act, float* __restrict__ Cn, int cns, float* __restrict__ Hn, int hns) {
+    TR_PDL_WAIT();
     TR_EW_LOOP((size_t)B * H) {
         const int b = i / H, j = i % H;
         const float* g = G + (size_t)b * gs;
@@ -986,6 +1040,7 @@ __global__ void lstm_cell_fwd_kernel(int B, int H, const float* __restrict__ G, 
 __global__ void lstm_cell_bwd_kernel(int B, int H, const float* __restrict__ Act, const float* __restrict__ Cp, int cps, const float* __restrict__ Cn, int cns,
                                      const float* __restrict__ dH, int dhs, const float* __restrict__ dCn, int dcns,
                                      float* __restrict__ dG, int dgs, float* __restrict__ dCp, int dcps) {
+    TR_PDL_WAIT();
     TR_EW_LOOP((size_t)B * H) {
         const int b = i / H, j = i % H;
         const float* a = Act + (size_t)b * 4 * H;
@@ -1005,6 +1060,7 @@ __global__ void lstm_cell_bwd_kernel(int B, int H, const float* __restrict__ Act
 // ---- kernels: Conv1d support (rows (b, l) x channels) ------------------------------------------------------------------
 // col[(b*Lo + lo)][ci*K + kk] = x[(b*L + lo*stride - pad + kk)][ci]  (zero outside [0, L))    — weight layout [co][ci][k]
 __global__ void im2col1d_kernel(int B, int L, int Lo, int C, int K, int stride, int pad, const float* __restrict__ X, int xs, float* __restrict__ col) {
+    TR_PDL_WAIT();
     const size_t total = (size_t)B * Lo * C * K;
     TR_EW_LOOP(total) {
         const int kk = i % K; size_t r = i / K;
@@ -1016,6 +1072,7 @@ __global__ void im2col1d_kernel(int B, int L, int Lo, int C, int K, int stride, 
 }
 // dx[(b*L + l)][ci] += sum_kk dcol[(b*Lo + lo)][ci*K + kk]  over (lo, kk) with lo*stride - pad + kk == l
 __global__ void col2im1d_kernel(int B, int L, int Lo, int C, int K, int stride, int pad, const float* __restrict__ dcol, float* __restrict__ dX, int dxs) {
+    TR_PDL_WAIT();
     TR_EW_LOOP((size_t)B * L * C) {
         const int ci = i % C; size_t r = i / C;
         const int l = r % L; const int b = r / L;
@@ -1032,6 +1089,7 @@ __global__ void col2im1d_kernel(int B, int L, int Lo, int C, int K, int stride, 
 }
 // adaptive_avg_pool1d over rows: y[(b*m + i)][c] = mean of x[(b*L + l)][c] for l in [floor(i L / m), ceil((i+1) L / m))
 __global__ void adaptive_pool_fwd_kernel(int B, int L, int m, int C, const float* __restrict__ X, int xs, float* __restrict__ Y, int ys) {
+    TR_PDL_WAIT();
     TR_EW_LOOP((size_t)B * m * C) {
         const int c = i % C; size_t r = i / C;
         const int j = r % m; const int b = r / m;
@@ -1042,6 +1100,7 @@ __global__ void adaptive_pool_fwd_kernel(int B, int L, int m, int C, const float
     }
 }
 __global__ void adaptive_pool_bwd_kernel(int B, int L, int m, int C, const float* __restrict__ dY, int dys, float* __restrict__ dX, int dxs) {
+    TR_PDL_WAIT();
     TR_EW_LOOP((size_t)B * L * C) {
         const int c = i % C; size_t r = i / C;
         const int l = r % L; const int b = r / L;
@@ -1055,9 +1114,11 @@ __global__ void adaptive_pool_bwd_kernel(int B, int L, int m, int C, const float
 }
 // [B][C][L] <-> rows (b, l) x C
 __global__ void bcl_to_rows_tr_kernel(int B, int C, int L, const float* __restrict__ X, float* __restrict__ Y, int ys) {
+    TR_PDL_WAIT();
     TR_EW_LOOP((size_t)B * C * L) { const int l = i % L; size_t r = i / L; const int c = r % C; const int b = r / C; Y[(size_t)(b * L + l) * ys + c] = X[i]; }
 }
 __global__ void rows_to_bcl_tr_kernel(int B, int C, int L, const float* __restrict__ X, int xs, float* __restrict__ Y) {
+    TR_PDL_WAIT();
     TR_EW_LOOP((size_t)B * C * L) { const int l = i % L; size_t r = i / L; const int c = r % C; const int b = r / C; Y[i] = X[(size_t)(b * L + l) * xs + c]; }
 }
 
@@ -1066,6 +1127,7 @@ __global__ void rows_to_bcl_tr_kernel(int B, int C, int L, const float* __restri
 // One thread per (position, co); the 735-tap patch is re-read through L1 by the 24 threads of a position.
 __global__ void __launch_bounds__(256) stem_fwd_kernel(int B, int T, int H, int W, int Ho, int Wo, const float* __restrict__ X, const float* __restrict__ Wt,
                                                        float* __restrict__ Y) {
+    TR_PDL_WAIT();
     const size_t total = (size_t)B * T * Ho * Wo * 24;
     TR_EW_LOOP(total) {
         const int co = i % 24; size_t r = i / 24;
@@ -1102,6 +1164,7 @@ constexpr int STEM_EW = 51, STEM_PR = 21;
 constexpr size_t STEM_TILED_SMEM = (size_t)(735 * 24 + 2 * 15 * STEM_PR * STEM_EW) * sizeof(float);
 __global__ void __launch_bounds__(192) stem_fwd_tiled_kernel(int B, int T, int H, int W, int Ho, int Wo, const float* __restrict__ X, const float* __restrict__ Wt,
                                                              float* __restrict__ Y) {
+    TR_PDL_WAIT();
     extern __shared__ float4 stem_sm4[];
     float* wts = reinterpret_cast<float*>(stem_sm4);              // [735][24]
     float* ev = wts + 735 * 24;                                      // [(ci*5+kt)][21][51]: input columns 2j - 3
@@ -1166,6 +1229,7 @@ __global__ void __launch_bounds__(192) stem_fwd_tiled_kernel(int B, int T, int H
 // gathered straight from the clip tensor (each thread decodes its taps once), dY rows are broadcast from shared memory.
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(int B, int T, int H, int W, int Ho, int Wo, int pos_per_chunk, const float* __restrict__ X,
                                                          const float* __restrict__ dY, float* __restrict__ part) {
+    TR_PDL_WAIT();
     __shared__ __align__(16) float dys[32][24];
     __shared__ int4 pinfo[32];                                       // per staged position: (b, t, 2 ho - 3, 2 wo - 3)
     const int tid = threadIdx.x;
@@ -1226,6 +1290,7 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(int B, int T, int H, in
 }
 // dst[i] += sum_chunk part[chunk][i]   (fixed order)
 __global__ void sum_chunks_kernel(int n, int chunks, const float* __restrict__ part, float* __restrict__ dst) {
+    TR_PDL_WAIT();
     TR_EW_LOOP((size_t)n) {
         float a = 0.f;
         for (int c = 0; c < chunks; ++c) a += part[(size_t)c * n + i];
@@ -1234,6 +1299,7 @@ __global__ void sum_chunks_kernel(int n, int chunks, const float* __restrict__ p
 }
 // MaxPool 3x3 stride 2 pad 1 over NHWC rows; idx = flat input row of the maximum (first in scan order on ties)
 __global__ void maxpool_fwd_kernel(int N, int H, int W, int C, int Ho, int Wo, const float* __restrict__ X, float* __restrict__ Y, int* __restrict__ idx) {
+    TR_PDL_WAIT();
     TR_EW_LOOP((size_t)N * Ho * Wo * C) {
         const int c = i % C; size_t r = i / C;
         const int wo = r % Wo; r /= Wo;
@@ -1255,6 +1321,7 @@ __global__ void maxpool_fwd_kernel(int N, int H, int W, int C, int Ho, int Wo, c
 }
 // gather form (deterministic): an input position receives dY of every window whose maximum it is
 __global__ void maxpool_bwd_kernel(int N, int H, int W, int C, int Ho, int Wo, const float* __restrict__ dY, const int* __restrict__ idx, float* __restrict__ dX) {
+    TR_PDL_WAIT();
     TR_EW_LOOP((size_t)N * H * W * C) {
         const int c = i % C; size_t r = i / C;
         const int row = (int)r;
@@ -1275,6 +1342,7 @@ __global__ void maxpool_bwd_kernel(int N, int H, int W, int C, int Ho, int Wo, c
 // depthwise 3x3, pad 1, stride s, no bias; weight [C][9]
 __global__ void dw3x3_fwd_kernel(int N, int H, int W, int C, int s, int Ho, int Wo, const float* __restrict__ X, int xs, const float* __restrict__ Wt,
                                  float* __restrict__ Y, int ys) {
+    TR_PDL_WAIT();
     TR_EW_LOOP((size_t)N * Ho * Wo * C) {
         const int c = i % C; size_t r = i / C;
         const int wo = r % Wo; r /= Wo;
@@ -1294,6 +1362,7 @@ __global__ void dw3x3_fwd_kernel(int N, int H, int W, int C, int s, int Ho, int 
 }
 __global__ void dw3x3_dgrad_kernel(int N, int H, int W, int C, int s, int Ho, int Wo, const float* __restrict__ dY, int dys, const float* __restrict__ Wt,
                                    float* __restrict__ dX, int dxs) {
+    TR_PDL_WAIT();
     TR_EW_LOOP((size_t)N * H * W * C) {
         const int c = i % C; size_t r = i / C;
         const int w = r % W; r /= W;
@@ -1320,6 +1389,7 @@ __global__ void dw3x3_dgrad_kernel(int N, int H, int W, int C, int s, int Ho, in
 // dw3x3_wfinish_kernel adds the splits into dW[c][tap]
 __global__ void __launch_bounds__(256) dw3x3_wgrad_kernel(int N, int H, int W, int C, int s, int Ho, int Wo, const float* __restrict__ X, int xs,
                                                           const float* __restrict__ dY, int dys, float* __restrict__ part) {
+    TR_PDL_WAIT();
     __shared__ float red[9][8][33];
     const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
@@ -1358,6 +1428,7 @@ __global__ void __launch_bounds__(256) dw3x3_wgrad_kernel(int N, int H, int W, i
         }
 }
 __global__ void dw3x3_wfinish_kernel(int C, int splits, const float* __restrict__ part, float* __restrict__ dW) {
+    TR_PDL_WAIT();
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;       // one warp per (tap, channel)
     if (i >= 9 * C) return;
     const int tap = i / C, c = i % C;
@@ -1368,12 +1439,14 @@ __global__ void dw3x3_wfinish_kernel(int C, int splits, const float* __restrict_
 }
 // y[:, 2j] = a[:, j], y[:, 2j+1] = b[:, j]   (torch.cat + channel_shuffle(groups=2), shufflenetv2.py:26-40,92-104)
 __global__ void interleave2_fwd_kernel(int rows, int half, const float* __restrict__ A, int as, const float* __restrict__ Bm, int bs, float* __restrict__ Y, int ys) {
+    TR_PDL_WAIT();
     TR_EW_LOOP((size_t)rows * 2 * half) {
         const int c = i % (2 * half); const int r = i / (2 * half);
         Y[(size_t)r * ys + c] = (c & 1) ? Bm[(size_t)r * bs + (c >> 1)] : A[(size_t)r * as + (c >> 1)];
     }
 }
 __global__ void interleave2_bwd_kernel(int rows, int half, const float* __restrict__ dY, int dys, float* __restrict__ dA, int das, float* __restrict__ dB, int dbs) {
+    TR_PDL_WAIT();
     TR_EW_LOOP((size_t)rows * 2 * half) {
         const int c = i % (2 * half); const int r = i / (2 * half);
         const float d = dY[(size_t)r * dys + c];
@@ -1383,6 +1456,7 @@ __global__ void interleave2_bwd_kernel(int rows, int half, const float* __restri
 }
 // F.normalize(p=2, dim=-1, eps=1e-12): y = x / max(||x||, eps); one warp per row; nrm saved
 __global__ void __launch_bounds__(256) l2norm_fwd_kernel(int rows, int cols, const float* __restrict__ X, int xs, float* __restrict__ Y, int ys, float* __restrict__ nrm) {
+    TR_PDL_WAIT();
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (r >= rows) return;
     float s = 0.f;
@@ -1393,6 +1467,7 @@ __global__ void __launch_bounds__(256) l2norm_fwd_kernel(int rows, int cols, con
 }
 __global__ void __launch_bounds__(256) l2norm_bwd_kernel(int rows, int cols, const float* __restrict__ Y, int ys, const float* __restrict__ nrm,
                                                          const float* __restrict__ dY, int dys, float* __restrict__ dX, int dxs) {
+    TR_PDL_WAIT();
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (r >= rows) return;
     float s = 0.f;
@@ -1562,9 +1637,9 @@ struct Engine {
         const int colblocks = (cols + 31) / 32;
         const int splits = std::max(1, std::min(std::min(1024, (148 * 8 + colblocks - 1) / colblocks), rows / 256));
         float* part = scratch((size_t)splits * cols);
-        colreduce_kernel<OP><<<dim3(colblocks, splits), 256, 0, s>>>(rows, cols, X, xs, Y, ys, aux, aux2, eps, part);
+        launch(colreduce_kernel<OP>, dim3(colblocks, splits), 256, 0, s, rows, cols, X, xs, Y, ys, aux, aux2, eps, part);
         ck("column reduce");
-        colfinish_kernel<<<(cols * 32 + 255) / 256, 256, 0, s>>>(cols, splits, part, scale, out, accumulate ? 1 : 0);
+        launch(colfinish_kernel, (cols * 32 + 255) / 256, 256, 0, s, cols, splits, part, scale, out, accumulate ? 1 : 0);
         ck("column reduce finish");
     }
 
@@ -1590,7 +1665,7 @@ struct Engine {
             }
             table_bytes += 2 * half + 16;
             const int N = d.W.rows, K = d.W.cols;
-            sgemm_tn_rows_kernel<<<dim3((K + 63) / 64, (N + 63) / 64), 256, 0, s>>>(N, K, R, tab, tab + R, d.W.g, d.W.rs, d.db);
+            launch(sgemm_tn_rows_kernel, dim3((K + 63) / 64, (N + 63) / 64), 256, 0, s, N, K, R, tab, tab + R, d.W.g, d.W.rs, d.db);
             ck("deferred weight gradient");
         }
         for (auto& kv : deferred_scalar) {
@@ -1603,7 +1678,7 @@ struct Engine {
                 L2S_CUDA(cudaMemcpyAsync(tab, host, bytes, cudaMemcpyHostToDevice, s));
             } else L2S_CUDA(cudaMemcpyAsync(tab, kv.second.data(), bytes, cudaMemcpyHostToDevice, s));
             table_bytes += bytes + 16;
-            sum_list_kernel<<<1, 256, 0, s>>>(R, deferred_scalar_n[kv.first], tab, kv.first);
+            launch(sum_list_kernel, 1, 256, 0, s, R, deferred_scalar_n[kv.first], tab, kv.first);
             ck("deferred scalar gradient");
         }
         // eager: the host pointer tables must outlive the asynchronous copies
@@ -1623,15 +1698,15 @@ struct Engine {
             const int nz = (K + kper - 1) / kper;
             float* part = scratch((size_t)nz * M * N);
             grid.z = nz;
-            if (exact_gemm) sgemm_kernel<TA, TB, true><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, part, N, 0, kper);
-            else sgemm_kernel<TA, TB, false><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, part, N, 0, kper);
+            if (exact_gemm) launch(sgemm_kernel<TA, TB, true>, grid, 256, 0, s, M, N, K, A, lda, B, ldb, part, N, 0, kper);
+            else launch(sgemm_kernel<TA, TB, false>, grid, 256, 0, s, M, N, K, A, lda, B, ldb, part, N, 0, kper);
             ck("sgemm split-K");
-            skinny_nn_sum_kernel<<<ew_blocks((size_t)M * N), 256, 0, s>>>(M, N, nz, part, C, ldc, acc ? 1 : 0);
+            launch(skinny_nn_sum_kernel, ew_blocks((size_t)M * N), 256, 0, s, M, N, nz, part, C, ldc, acc ? 1 : 0);
             ck("sgemm split-K sum");
             return;
         }
-        if (exact_gemm) sgemm_kernel<TA, TB, true><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, acc ? 1 : 0, K);
-        else sgemm_kernel<TA, TB, false><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, acc ? 1 : 0, K);
+        if (exact_gemm) launch(sgemm_kernel<TA, TB, true>, grid, 256, 0, s, M, N, K, A, lda, B, ldb, C, ldc, acc ? 1 : 0, K);
+        else launch(sgemm_kernel<TA, TB, false>, grid, 256, 0, s, M, N, K, A, lda, B, ldb, C, ldc, acc ? 1 : 0, K);
         ck("sgemm");
     }
 
@@ -1642,7 +1717,7 @@ struct Engine {
                           const float* W2, int lw2, const float* b2, float* y, int ly, int accf) {
         const int MT = R <= 8 ? 8 : 16;
         const size_t smem = (size_t)MT * (K1 + K2) * sizeof(float);
-#define L2S_NT(NW_, MT_) skinny_nt_smem_kernel<NW_, MT_><<<(N + 8 * NW_ - 1) / (8 * NW_), 256, smem, s>>>(R, N, K1, x1, lx1, W1, lw1, b1, K2, x2, lx2, W2, lw2, b2, y, ly, accf)
+#define L2S_NT(NW_, MT_) launch(skinny_nt_smem_kernel<NW_, MT_>, (N + 8 * NW_ - 1) / (8 * NW_), 256, smem, s, R, N, K1, x1, lx1, W1, lw1, b1, K2, x2, lx2, W2, lw2, b2, y, ly, accf)
         if (MT == 8) {
             if (N >= 3072) L2S_NT(4, 8); else if (N >= 1536) L2S_NT(2, 8); else L2S_NT(1, 8);
         } else {
@@ -1657,8 +1732,8 @@ struct Engine {
         const int MT = R <= 8 ? 8 : 16;
         const size_t smem = skinny_nn_smem(R, N);
         const dim3 grid((std::max(K1, K2) + 7) / 8, K2 ? 2 : 1);
-        if (MT == 8) skinny_nn_strip_kernel<8><<<grid, NN_THREADS, smem, s>>>(R, N, K1, dy, ldy, W1, lw1, dx1, ldx1, K2, W2, lw2, dx2, ldx2);
-        else skinny_nn_strip_kernel<16><<<grid, NN_THREADS, smem, s>>>(R, N, K1, dy, ldy, W1, lw1, dx1, ldx1, K2, W2, lw2, dx2, ldx2);
+        if (MT == 8) launch(skinny_nn_strip_kernel<8>, grid, NN_THREADS, smem, s, R, N, K1, dy, ldy, W1, lw1, dx1, ldx1, K2, W2, lw2, dx2, ldx2);
+        else launch(skinny_nn_strip_kernel<16>, grid, NN_THREADS, smem, s, R, N, K1, dy, ldy, W1, lw1, dx1, ldx1, K2, W2, lw2, dx2, ldx2);
         ck("skinny_nn strip");
     }
     static size_t skinny_nn_smem(int R, int N) { return (size_t)(R <= 8 ? 8 : 16) * ((N + 255) / 256 * 256) * sizeof(float); }
@@ -1677,13 +1752,13 @@ struct Engine {
             const size_t smem = (size_t)MT * K * sizeof(float);
             if (vec && smem <= (size_t)SKINNY_SMEM_MAX) {
                 launch_skinny_nt(R, N, K, x.v, x.rs, W.v, W.rs, b ? b->v : nullptr, 0, nullptr, 0, nullptr, 0, nullptr, y.v, y.rs, accf);
-            } else if (vec) skinny_nt_kernel<true><<<(N * 32 + 255) / 256, 256, 0, s>>>(R, N, K, x.v, x.rs, W.v, W.rs, b ? b->v : nullptr, y.v, y.rs, accf);
-            else skinny_nt_kernel<false><<<(N * 32 + 255) / 256, 256, 0, s>>>(R, N, K, x.v, x.rs, W.v, W.rs, b ? b->v : nullptr, y.v, y.rs, accf);
+            } else if (vec) launch(skinny_nt_kernel<true>, (N * 32 + 255) / 256, 256, 0, s, R, N, K, x.v, x.rs, W.v, W.rs, b ? b->v : nullptr, y.v, y.rs, accf);
+            else launch(skinny_nt_kernel<false>, (N * 32 + 255) / 256, 256, 0, s, R, N, K, x.v, x.rs, W.v, W.rs, b ? b->v : nullptr, y.v, y.rs, accf);
             if (!(vec && smem <= (size_t)SKINNY_SMEM_MAX)) ck("skinny_nt");
         } else {
             gemm<0, 1>(R, N, K, x.v, x.rs, W.v, W.rs, y.v, y.rs, accumulate);
             if (b) {
-                ew_fwd_kernel<EW_ADDROW><<<ew_blocks(y.numel()), 256, 0, s>>>(R, N, y.v, y.rs, b->v, 0, 0.f, R, y.v, y.rs);   // group = R: one broadcast row
+                launch(ew_fwd_kernel<EW_ADDROW>, ew_blocks(y.numel()), 256, 0, s, R, N, y.v, y.rs, b->v, 0, 0.f, R, y.v, y.rs);   // group = R: one broadcast row
                 ck("bias");
             }
         }
@@ -1704,9 +1779,9 @@ struct Engine {
                 } else if (R <= 16) {
                     const int nslice = 128, nslices = (N + nslice - 1) / nslice;
                     float* part = scratch((size_t)nslices * R * K);
-                    skinny_nn_part_kernel<<<dim3((K + 63) / 64, nslices), 256, 0, s>>>(R, N, K, nslice, y.g, y.rs, W.v, W.rs, part);
+                    launch(skinny_nn_part_kernel, dim3((K + 63) / 64, nslices), 256, 0, s, R, N, K, nslice, y.g, y.rs, W.v, W.rs, part);
                     ck("skinny_nn part");
-                    skinny_nn_sum_kernel<<<ew_blocks((size_t)R * K), 256, 0, s>>>(R, K, nslices, part, x.g, x.rs, 1);
+                    launch(skinny_nn_sum_kernel, ew_blocks((size_t)R * K), 256, 0, s, R, K, nslices, part, x.g, x.rs, 1);
                     ck("skinny_nn sum");
                 } else gemm<0, 0>(R, K, N, y.g, y.rs, W.v, W.rs, x.g, x.rs, true);
             }
@@ -1763,11 +1838,11 @@ struct Engine {
     template <int OP>
     TT ew(const TT& x, const float* aux, int as, float alpha, int group = 1) {
         TT y = make(x.rows, x.cols);
-        ew_fwd_kernel<OP><<<ew_blocks(x.numel()), 256, 0, s>>>(x.rows, x.cols, x.v, x.rs, aux, as, alpha, group, y.v, y.rs);
+        launch(ew_fwd_kernel<OP>, ew_blocks(x.numel()), 256, 0, s, x.rows, x.cols, x.v, x.rs, aux, as, alpha, group, y.v, y.rs);
         ck("elementwise");
         tape.push_back([=]() {
             if (!x.g) return;
-            ew_bwd_kernel<OP><<<ew_blocks(x.numel()), 256, 0, s>>>(x.rows, x.cols, x.v, x.rs, aux, as, alpha, y.g, y.rs, x.g, x.rs);
+            launch(ew_bwd_kernel<OP>, ew_blocks(x.numel()), 256, 0, s, x.rows, x.cols, x.v, x.rs, aux, as, alpha, y.g, y.rs, x.g, x.rs);
             ck("elementwise bwd");
         });
         return y;
@@ -1789,11 +1864,11 @@ struct Engine {
     }
     TT add(const TT& a, const TT& b, const TT* dst = nullptr) {
         TT y = dst ? *dst : make(a.rows, a.cols);
-        ew_fwd_kernel<EW_ADD><<<ew_blocks(a.numel()), 256, 0, s>>>(a.rows, a.cols, a.v, a.rs, b.v, b.rs, 0.f, 1, y.v, y.rs);
+        launch(ew_fwd_kernel<EW_ADD>, ew_blocks(a.numel()), 256, 0, s, a.rows, a.cols, a.v, a.rs, b.v, b.rs, 0.f, 1, y.v, y.rs);
         ck("add");
         tape.push_back([=]() {
             for (const TT* t : {&a, &b})
-                if (t->g) { ew_bwd_kernel<EW_COPY><<<ew_blocks(y.numel()), 256, 0, s>>>(y.rows, y.cols, nullptr, 0, nullptr, 0, 0.f, y.g, y.rs, t->g, t->rs); ck("add bwd"); }
+                if (t->g) { launch(ew_bwd_kernel<EW_COPY>, ew_blocks(y.numel()), 256, 0, s, y.rows, y.cols, nullptr, 0, nullptr, 0, 0.f, y.g, y.rs, t->g, t->rs); ck("add bwd"); }
         });
         return y;
     }
@@ -1801,11 +1876,11 @@ struct Engine {
     // does not depend on the draw, so one captured graph serves every step).  Only b carries a gradient (a = teacher frames).
     TT select(const float* flag, const TT& a, const TT& b) {
         TT y = make(a.rows, a.cols);
-        select_fwd_kernel<<<ew_blocks(a.numel()), 256, 0, s>>>(a.rows, a.cols, flag, a.v, a.rs, b.v, b.rs, y.v, y.rs);
+        launch(select_fwd_kernel, ew_blocks(a.numel()), 256, 0, s, a.rows, a.cols, flag, a.v, a.rs, b.v, b.rs, y.v, y.rs);
         ck("select");
         tape.push_back([=]() {
             if (!b.g) return;
-            select_bwd_kernel<<<ew_blocks(y.numel()), 256, 0, s>>>(y.rows, y.cols, flag, y.g, y.rs, b.g, b.rs);
+            launch(select_bwd_kernel, ew_blocks(y.numel()), 256, 0, s, y.rows, y.cols, flag, y.g, y.rs, b.g, b.rs);
             ck("select bwd");
         });
         return y;
@@ -1813,21 +1888,21 @@ struct Engine {
     // y[(g*group + j)] = x[(g*group + j)] + v[g]     (attention_site broadcast over the T frames of a clip, decoder.py:327)
     TT add_rows(const TT& x, const TT& v, int group) {
         TT y = make(x.rows, x.cols);
-        ew_fwd_kernel<EW_ADDROW><<<ew_blocks(x.numel()), 256, 0, s>>>(x.rows, x.cols, x.v, x.rs, v.v, v.rs, 0.f, group, y.v, y.rs);
+        launch(ew_fwd_kernel<EW_ADDROW>, ew_blocks(x.numel()), 256, 0, s, x.rows, x.cols, x.v, x.rs, v.v, v.rs, 0.f, group, y.v, y.rs);
         ck("add rows");
         tape.push_back([=]() {
-            if (x.g) { ew_bwd_kernel<EW_COPY><<<ew_blocks(y.numel()), 256, 0, s>>>(y.rows, y.cols, nullptr, 0, nullptr, 0, 0.f, y.g, y.rs, x.g, x.rs); ck("add rows bwd"); }
-            if (v.g) { addrow_bwd_kernel<<<ew_blocks((size_t)v.rows * v.cols), 256, 0, s>>>(v.rows, group, v.cols, y.g, y.rs, v.g, v.rs); ck("add rows bwd v"); }
+            if (x.g) { launch(ew_bwd_kernel<EW_COPY>, ew_blocks(y.numel()), 256, 0, s, y.rows, y.cols, nullptr, 0, nullptr, 0, 0.f, y.g, y.rs, x.g, x.rs); ck("add rows bwd"); }
+            if (v.g) { launch(addrow_bwd_kernel, ew_blocks((size_t)v.rows * v.cols), 256, 0, s, v.rows, group, v.cols, y.g, y.rs, v.g, v.rs); ck("add rows bwd v"); }
         });
         return y;
     }
     TT scale_param(const TT& x, const TT& w) {
         TT y = make(x.rows, x.cols);
-        scale_param_kernel<<<ew_blocks(x.numel()), 256, 0, s>>>(x.rows, x.cols, x.v, x.rs, w.v, y.v, y.rs);
+        launch(scale_param_kernel, ew_blocks(x.numel()), 256, 0, s, x.rows, x.cols, x.v, x.rs, w.v, y.v, y.rs);
         ck("scale param");
         tape.push_back([=]() {
-            if (x.g) { scale_param_bwd_kernel<<<ew_blocks(x.numel()), 256, 0, s>>>(x.rows, x.cols, w.v, y.g, y.rs, x.g, x.rs); ck("scale param bwd"); }
-            if (w.g) { dot_all_kernel<<<1, 1024, 0, s>>>(x.rows, x.cols, x.v, x.rs, y.g, y.rs, w.g, 1); ck("scale param dw"); }
+            if (x.g) { launch(scale_param_bwd_kernel, ew_blocks(x.numel()), 256, 0, s, x.rows, x.cols, w.v, y.g, y.rs, x.g, x.rs); ck("scale param bwd"); }
+            if (w.g) { launch(dot_all_kernel, 1, 1024, 0, s, x.rows, x.cols, x.v, x.rs, y.g, y.rs, w.g, 1); ck("scale param dw"); }
         });
         return y;
     }
@@ -1840,7 +1915,7 @@ struct Engine {
         TT y = make(parts[0].rows, cols);
         int c0 = 0;
         for (auto& p : parts) {
-            ew_fwd_kernel<EW_COPY><<<ew_blocks(p.numel()), 256, 0, s>>>(p.rows, p.cols, p.v, p.rs, nullptr, 0, 0.f, 1, y.v + c0, y.rs);
+            launch(ew_fwd_kernel<EW_COPY>, ew_blocks(p.numel()), 256, 0, s, p.rows, p.cols, p.v, p.rs, nullptr, 0, 0.f, 1, y.v + c0, y.rs);
             ck("concat");
             c0 += p.cols;
         }
@@ -1848,7 +1923,7 @@ struct Engine {
         tape.push_back([=]() {
             int c = 0;
             for (auto& p : ps) {
-                if (p.g) { ew_bwd_kernel<EW_COPY><<<ew_blocks(p.numel()), 256, 0, s>>>(p.rows, p.cols, nullptr, 0, nullptr, 0, 0.f, y.g + c, y.rs, p.g, p.rs); ck("concat bwd"); }
+                if (p.g) { launch(ew_bwd_kernel<EW_COPY>, ew_blocks(p.numel()), 256, 0, s, p.rows, p.cols, nullptr, 0, nullptr, 0, 0.f, y.g + c, y.rs, p.g, p.rs); ck("concat bwd"); }
                 c += p.cols;
             }
         });
@@ -1863,12 +1938,12 @@ struct Engine {
         colred<COL_SUM>(R, C, x.v, x.rs, nullptr, 0, nullptr, nullptr, 0.f, 1.f / (float)R, mean, false);
         colred<COL_SQDEV>(R, C, x.v, x.rs, nullptr, 0, mean, nullptr, 0.f, 1.f / (float)R, var, false);       // biased variance, two passes
         TT y = make(R, C);
-        bn_fwd_kernel<<<ew_blocks(x.numel()), 256, 0, s>>>(R, C, x.v, x.rs, mean, var, eps, gamma.v, beta.v, y.v, y.rs);
+        launch(bn_fwd_kernel, ew_blocks(x.numel()), 256, 0, s, R, C, x.v, x.rs, mean, var, eps, gamma.v, beta.v, y.v, y.rs);
         ck("bn fwd");
         if (update_bn_running) {
             auto rm = params->find(name + ".running_mean"), rv = params->find(name + ".running_var");
             if (rm != params->end() && rv != params->end()) {
-                bn_running_kernel<<<(C + 255) / 256, 256, 0, s>>>(C, R, 0.1f, mean, var, rm->second.v, rv->second.v);
+                launch(bn_running_kernel, (C + 255) / 256, 256, 0, s, C, R, 0.1f, mean, var, rm->second.v, rv->second.v);
                 ck("bn running");
             }
         }
@@ -1876,20 +1951,20 @@ struct Engine {
         tape.push_back([=]() {
             colred<COL_BN_DGAMMA>(R, C, x.v, x.rs, y.g, y.rs, mean, var, eps, 1.f, dgamma, false);
             colred<COL_SUM>(R, C, y.g, y.rs, nullptr, 0, nullptr, nullptr, 0.f, 1.f, dbeta, false);
-            if (x.g) { bn_bwd_kernel<<<ew_blocks(x.numel()), 256, 0, s>>>(R, C, x.v, x.rs, mean, var, eps, gamma.v, dgamma, dbeta, y.g, y.rs, x.g, x.rs); ck("bn bwd"); }
-            if (gamma.g) { ew_bwd_kernel<EW_COPY><<<ew_blocks(C), 256, 0, s>>>(1, C, nullptr, 0, nullptr, 0, 0.f, dgamma, C, gamma.g, C); ck("bn dgamma acc"); }
-            if (beta.g) { ew_bwd_kernel<EW_COPY><<<ew_blocks(C), 256, 0, s>>>(1, C, nullptr, 0, nullptr, 0, 0.f, dbeta, C, beta.g, C); ck("bn dbeta acc"); }
+            if (x.g) { launch(bn_bwd_kernel, ew_blocks(x.numel()), 256, 0, s, R, C, x.v, x.rs, mean, var, eps, gamma.v, dgamma, dbeta, y.g, y.rs, x.g, x.rs); ck("bn bwd"); }
+            if (gamma.g) { launch(ew_bwd_kernel<EW_COPY>, ew_blocks(C), 256, 0, s, 1, C, nullptr, 0, nullptr, 0, 0.f, dgamma, C, gamma.g, C); ck("bn dgamma acc"); }
+            if (beta.g) { launch(ew_bwd_kernel<EW_COPY>, ew_blocks(C), 256, 0, s, 1, C, nullptr, 0, nullptr, 0, 0.f, dbeta, C, beta.g, C); ck("bn dbeta acc"); }
         });
         return y;
     }
 
     TT softmax(const TT& x) {
         TT y = make(x.rows, x.cols);
-        softmax_fwd_kernel<<<(x.rows * 32 + 255) / 256, 256, 0, s>>>(x.rows, x.cols, x.v, x.rs, y.v, y.rs);
+        launch(softmax_fwd_kernel, (x.rows * 32 + 255) / 256, 256, 0, s, x.rows, x.cols, x.v, x.rs, y.v, y.rs);
         ck("softmax");
         tape.push_back([=]() {
             if (!x.g) return;
-            softmax_bwd_kernel<<<(x.rows * 32 + 255) / 256, 256, 0, s>>>(x.rows, x.cols, y.v, y.rs, y.g, y.rs, x.g, x.rs);
+            launch(softmax_bwd_kernel, (x.rows * 32 + 255) / 256, 256, 0, s, x.rows, x.cols, y.v, y.rs, y.g, y.rs, x.g, x.rs);
             ck("softmax bwd");
         });
         return y;
@@ -1898,10 +1973,10 @@ struct Engine {
     TT attn_scores(const TT& q, const TT& Km, int T) {
         const int B = q.rows, D = q.cols;
         TT y = make(B, T);
-        attn_scores_kernel<<<(B * T * 32 + 255) / 256, 256, 0, s>>>(B, T, D, q.v, q.rs, Km.v, Km.rs, y.v, y.rs);
+        launch(attn_scores_kernel, (B * T * 32 + 255) / 256, 256, 0, s, B, T, D, q.v, q.rs, Km.v, Km.rs, y.v, y.rs);
         ck("attn scores");
         tape.push_back([=]() {
-            attn_scores_bwd_kernel<<<ew_blocks((size_t)B * D), 256, 0, s>>>(B, T, D, q.v, q.rs, Km.v, Km.rs, y.g, y.rs, q.g, q.rs, Km.g, Km.rs);
+            launch(attn_scores_bwd_kernel, ew_blocks((size_t)B * D), 256, 0, s, B, T, D, q.v, q.rs, Km.v, Km.rs, y.g, y.rs, q.g, q.rs, Km.g, Km.rs);
             ck("attn scores bwd");
         });
         return y;
@@ -1909,10 +1984,10 @@ struct Engine {
     TT attn_context(const TT& a, const TT& V, int T, const TT* dst = nullptr) {
         const int B = a.rows, D = V.cols;
         TT y = dst ? *dst : make(B, D);
-        attn_context_kernel<<<ew_blocks((size_t)B * D), 256, 0, s>>>(B, T, D, a.v, a.rs, V.v, V.rs, y.v, y.rs);
+        launch(attn_context_kernel, ew_blocks((size_t)B * D), 256, 0, s, B, T, D, a.v, a.rs, V.v, V.rs, y.v, y.rs);
         ck("attn context");
         tape.push_back([=]() {
-            attn_context_bwd_kernel<<<(B * T * 32 + 255) / 256, 256, 0, s>>>(B, T, D, a.v, a.rs, V.v, V.rs, y.g, y.rs, a.g, a.rs, V.g, V.rs);
+            launch(attn_context_bwd_kernel, (B * T * 32 + 255) / 256, 256, 0, s, B, T, D, a.v, a.rs, V.v, V.rs, y.g, y.rs, a.g, a.rs, V.g, V.rs);
             ck("attn context bwd");
         });
         return y;
@@ -1929,12 +2004,12 @@ struct Engine {
         const bool vec = !(D & 3) && !(DV & 3) && !(q.rs & 3) && !(Km.rs & 3) && !(V.rs & 3) && !(y.rs & 3) &&
                          !((reinterpret_cast<uintptr_t>(q.v) | reinterpret_cast<uintptr_t>(Km.v) | reinterpret_cast<uintptr_t>(V.v) | reinterpret_cast<uintptr_t>(y.v)) & 15);
         if (!vec) throw L2sError(1, "train: attention operands must be 16-byte aligned with multiples of 4 columns");
-        attn_step_fwd_kernel<<<dim3(B, ATT_SPLIT), 256, 0, s>>>(T, D, DV, w.v, q.v, q.rs, Km.v, Km.rs, mask, alpha, V.v, V.rs, sraw, probs, logits, ls, y.v, y.rs);
+        launch(attn_step_fwd_kernel, dim3(B, ATT_SPLIT), 256, 0, s, T, D, DV, w.v, q.v, q.rs, Km.v, Km.rs, mask, alpha, V.v, V.rs, sraw, probs, logits, ls, y.v, y.rs);
         ck("attention step");
         tape.push_back([=]() {
             float* dwp = nullptr;
             if (w.g) { dwp = scratch(B); deferred_scalar[w.g].push_back(dwp); deferred_scalar_n[w.g] = B; }
-            attn_step_bwd_kernel<<<dim3(B, ATT_SPLIT), 256, 0, s>>>(T, D, DV, w.v, q.v, q.rs, Km.v, Km.rs, mask, alpha, V.v, V.rs, sraw, probs, y.g, y.rs, q.g, q.rs, Km.g, Km.rs,
+            launch(attn_step_bwd_kernel, dim3(B, ATT_SPLIT), 256, 0, s, T, D, DV, w.v, q.v, q.rs, Km.v, Km.rs, mask, alpha, V.v, V.rs, sraw, probs, y.g, y.rs, q.g, q.rs, Km.g, Km.rs,
                                                    V.g, V.rs, dwp);
             ck("attention step bwd");
         });
@@ -1951,10 +2026,10 @@ struct Engine {
         }
         const float alpha = 1.0f / (1.0f - p);
         TT y = make(x.rows, x.cols);
-        psine_chain_fwd_kernel<<<ew_blocks(x.numel()), 256, 0, s>>>(x.rows, x.cols, x.v, x.rs, w.v, mask, ms, alpha, addc, as, y.v, y.rs);
+        launch(psine_chain_fwd_kernel, ew_blocks(x.numel()), 256, 0, s, x.rows, x.cols, x.v, x.rs, w.v, mask, ms, alpha, addc, as, y.v, y.rs);
         ck("psine chain");
         tape.push_back([=]() {
-            psine_chain_bwd_kernel<<<(x.cols + 31) / 32, 256, 0, s>>>(x.rows, x.cols, x.v, x.rs, w.v, mask, ms, alpha, y.g, y.rs, x.g, x.rs, w.g);
+            launch(psine_chain_bwd_kernel, (x.cols + 31) / 32, 256, 0, s, x.rows, x.cols, x.v, x.rs, w.v, mask, ms, alpha, y.g, y.rs, x.g, x.rs, w.g);
             ck("psine chain bwd");
         });
         return y;
@@ -1965,12 +2040,12 @@ struct Engine {
         const int B = gates.rows, H = gates.cols / 4;
         float* act = scratch((size_t)B * 4 * H);
         h = hdst ? *hdst : make(B, H); c = cdst ? *cdst : make(B, H);
-        lstm_cell_fwd_kernel<<<ew_blocks((size_t)B * H), 256, 0, s>>>(B, H, gates.v, gates.rs, cprev.v, cprev.rs, act, c.v, c.rs, h.v, h.rs);
+        launch(lstm_cell_fwd_kernel, ew_blocks((size_t)B * H), 256, 0, s, B, H, gates.v, gates.rs, cprev.v, cprev.rs, act, c.v, c.rs, h.v, h.rs);
         ck("lstm cell");
         TT hh = h, cc = c;
         tape.push_back([=]() {
             // gates.g is overwritten (a gates tensor feeds exactly one cell), then flows on through the tape
-            lstm_cell_bwd_kernel<<<ew_blocks((size_t)B * H), 256, 0, s>>>(B, H, act, cprev.v, cprev.rs, cc.v, cc.rs, hh.g, hh.rs, cc.g, cc.rs, gates.g, gates.rs,
+            launch(lstm_cell_bwd_kernel, ew_blocks((size_t)B * H), 256, 0, s, B, H, act, cprev.v, cprev.rs, cc.v, cc.rs, hh.g, hh.rs, cc.g, cc.rs, gates.g, gates.rs,
                                                                           cprev.g, cprev.rs);
             ck("lstm cell bwd");
         });
@@ -1982,11 +2057,11 @@ struct Engine {
         if (Lout) *Lout = Lo;
         if (K == 1 && stride == 1 && pad == 0) return linear(x, W, b);
         TT col = make(B * Lo, Cin * K);
-        im2col1d_kernel<<<ew_blocks(col.numel()), 256, 0, s>>>(B, L, Lo, Cin, K, stride, pad, x.v, x.rs, col.v);
+        launch(im2col1d_kernel, ew_blocks(col.numel()), 256, 0, s, B, L, Lo, Cin, K, stride, pad, x.v, x.rs, col.v);
         ck("im2col");
         tape.push_back([=]() {
             if (!x.g) return;
-            col2im1d_kernel<<<ew_blocks((size_t)B * L * Cin), 256, 0, s>>>(B, L, Lo, Cin, K, stride, pad, col.g, x.g, x.rs);
+            launch(col2im1d_kernel, ew_blocks((size_t)B * L * Cin), 256, 0, s, B, L, Lo, Cin, K, stride, pad, col.g, x.g, x.rs);
             ck("col2im");
         });
         return linear(col, W, b);
@@ -1997,9 +2072,9 @@ struct Engine {
         const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
         TT y = make(B * T * Ho * Wo, 24);
         if (!(W & 1) && W <= 96 && Wo <= 48)
-            stem_fwd_tiled_kernel<<<B * T * ((Ho + 7) / 8), 192, STEM_TILED_SMEM, s>>>(B, T, H, W, Ho, Wo, video, Wt.v, y.v);
+            launch(stem_fwd_tiled_kernel, B * T * ((Ho + 7) / 8), 192, STEM_TILED_SMEM, s, B, T, H, W, Ho, Wo, video, Wt.v, y.v);
         else
-            stem_fwd_kernel<<<ew_blocks(y.numel()), 256, 0, s>>>(B, T, H, W, Ho, Wo, video, Wt.v, y.v);
+            launch(stem_fwd_kernel, ew_blocks(y.numel()), 256, 0, s, B, T, H, W, Ho, Wo, video, Wt.v, y.v);
         ck("stem conv");
         tape.push_back([=]() {
             if (!Wt.g) return;
@@ -2007,9 +2082,9 @@ struct Engine {
             const int chunks = (int)std::min<size_t>(148 * 4, (npos + 255) / 256);
             const int per = (int)((npos + chunks - 1) / chunks);
             float* part = grads.alloc((size_t)chunks * 24 * 735);
-            stem_wgrad_kernel<<<chunks, 256, 0, s>>>(B, T, H, W, Ho, Wo, per, video, y.g, part);
+            launch(stem_wgrad_kernel, chunks, 256, 0, s, B, T, H, W, Ho, Wo, per, video, y.g, part);
             ck("stem wgrad");
-            sum_chunks_kernel<<<ew_blocks(24 * 735), 256, 0, s>>>(24 * 735, chunks, part, Wt.g);
+            launch(sum_chunks_kernel, ew_blocks(24 * 735), 256, 0, s, 24 * 735, chunks, part, Wt.g);
             ck("stem wgrad sum");
         });
         return y;
@@ -2019,11 +2094,11 @@ struct Engine {
         *Hout = Ho; *Wout = Wo;
         TT y = make(N * Ho * Wo, C);
         int* idx = reinterpret_cast<int*>(scratch(y.numel()));
-        maxpool_fwd_kernel<<<ew_blocks(y.numel()), 256, 0, s>>>(N, H, W, C, Ho, Wo, x.v, y.v, idx);
+        launch(maxpool_fwd_kernel, ew_blocks(y.numel()), 256, 0, s, N, H, W, C, Ho, Wo, x.v, y.v, idx);
         ck("maxpool");
         tape.push_back([=]() {
             if (!x.g) return;
-            maxpool_bwd_kernel<<<ew_blocks(x.numel()), 256, 0, s>>>(N, H, W, C, Ho, Wo, y.g, idx, x.g);
+            launch(maxpool_bwd_kernel, ew_blocks(x.numel()), 256, 0, s, N, H, W, C, Ho, Wo, y.g, idx, x.g);
             ck("maxpool bwd");
         });
         return y;
@@ -2032,17 +2107,17 @@ struct Engine {
         const int C = x.cols, Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
         *Hout = Ho; *Wout = Wo;
         TT y = make(N * Ho * Wo, C);
-        dw3x3_fwd_kernel<<<ew_blocks(y.numel()), 256, 0, s>>>(N, H, W, C, stride, Ho, Wo, x.v, x.rs, Wt.v, y.v, y.rs);
+        launch(dw3x3_fwd_kernel, ew_blocks(y.numel()), 256, 0, s, N, H, W, C, stride, Ho, Wo, x.v, x.rs, Wt.v, y.v, y.rs);
         ck("dw conv");
         tape.push_back([=]() {
-            if (x.g) { dw3x3_dgrad_kernel<<<ew_blocks((size_t)N * H * W * C), 256, 0, s>>>(N, H, W, C, stride, Ho, Wo, y.g, y.rs, Wt.v, x.g, x.rs); ck("dw dgrad"); }
+            if (x.g) { launch(dw3x3_dgrad_kernel, ew_blocks((size_t)N * H * W * C), 256, 0, s, N, H, W, C, stride, Ho, Wo, y.g, y.rs, Wt.v, x.g, x.rs); ck("dw dgrad"); }
             if (Wt.g) {
                 const int rows = N * Ho * Wo, colblocks = (C + 31) / 32;
                 const int splits = std::max(1, std::min(std::min(1024, (148 * 8 + colblocks - 1) / colblocks), rows / 64));
                 float* part = scratch((size_t)splits * 9 * C);
-                dw3x3_wgrad_kernel<<<dim3(colblocks, splits), 256, 0, s>>>(N, H, W, C, stride, Ho, Wo, x.v, x.rs, y.g, y.rs, part);
+                launch(dw3x3_wgrad_kernel, dim3(colblocks, splits), 256, 0, s, N, H, W, C, stride, Ho, Wo, x.v, x.rs, y.g, y.rs, part);
                 ck("dw wgrad");
-                dw3x3_wfinish_kernel<<<(9 * C * 32 + 255) / 256, 256, 0, s>>>(C, splits, part, Wt.g);
+                launch(dw3x3_wfinish_kernel, (9 * C * 32 + 255) / 256, 256, 0, s, C, splits, part, Wt.g);
                 ck("dw wgrad finish");
             }
         });
@@ -2051,10 +2126,10 @@ struct Engine {
     TT interleave2(const TT& a, const TT& b) {
         const int half = a.cols;
         TT y = make(a.rows, 2 * half);
-        interleave2_fwd_kernel<<<ew_blocks(y.numel()), 256, 0, s>>>(a.rows, half, a.v, a.rs, b.v, b.rs, y.v, y.rs);
+        launch(interleave2_fwd_kernel, ew_blocks(y.numel()), 256, 0, s, a.rows, half, a.v, a.rs, b.v, b.rs, y.v, y.rs);
         ck("interleave");
         tape.push_back([=]() {
-            interleave2_bwd_kernel<<<ew_blocks(y.numel()), 256, 0, s>>>(a.rows, half, y.g, y.rs, a.g, a.rs, b.g, b.rs);
+            launch(interleave2_bwd_kernel, ew_blocks(y.numel()), 256, 0, s, a.rows, half, y.g, y.rs, a.g, a.rs, b.g, b.rs);
             ck("interleave bwd");
         });
         return y;
@@ -2062,11 +2137,11 @@ struct Engine {
     TT l2normalize(const TT& x) {
         TT y = make(x.rows, x.cols);
         float* nrm = scratch(x.rows);
-        l2norm_fwd_kernel<<<(x.rows * 32 + 255) / 256, 256, 0, s>>>(x.rows, x.cols, x.v, x.rs, y.v, y.rs, nrm);
+        launch(l2norm_fwd_kernel, (x.rows * 32 + 255) / 256, 256, 0, s, x.rows, x.cols, x.v, x.rs, y.v, y.rs, nrm);
         ck("l2 normalize");
         tape.push_back([=]() {
             if (!x.g) return;
-            l2norm_bwd_kernel<<<(x.rows * 32 + 255) / 256, 256, 0, s>>>(x.rows, x.cols, y.v, y.rs, nrm, y.g, y.rs, x.g, x.rs);
+            launch(l2norm_bwd_kernel, (x.rows * 32 + 255) / 256, 256, 0, s, x.rows, x.cols, y.v, y.rs, nrm, y.g, y.rs, x.g, x.rs);
             ck("l2 normalize bwd");
         });
         return y;
@@ -2074,11 +2149,11 @@ struct Engine {
     TT adaptive_pool(const TT& x, int B, int L, int m) {
         if (L == m) return x;
         TT y = make(B * m, x.cols);
-        adaptive_pool_fwd_kernel<<<ew_blocks(y.numel()), 256, 0, s>>>(B, L, m, x.cols, x.v, x.rs, y.v, y.rs);
+        launch(adaptive_pool_fwd_kernel, ew_blocks(y.numel()), 256, 0, s, B, L, m, x.cols, x.v, x.rs, y.v, y.rs);
         ck("adaptive pool");
         tape.push_back([=]() {
             if (!x.g) return;
-            adaptive_pool_bwd_kernel<<<ew_blocks((size_t)B * L * x.cols), 256, 0, s>>>(B, L, m, x.cols, y.g, y.rs, x.g, x.rs);
+            launch(adaptive_pool_bwd_kernel, ew_blocks((size_t)B * L * x.cols), 256, 0, s, B, L, m, x.cols, y.g, y.rs, x.g, x.rs);
             ck("adaptive pool bwd");
         });
         return y;

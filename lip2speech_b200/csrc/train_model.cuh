@@ -9,16 +9,20 @@ namespace tr {
 
 // out[(b*T + t)][c] = pos[t][c]
 __global__ void tile_pos_kernel(int B, int T, int C, const float* __restrict__ pos, float* __restrict__ out) {
+    TR_PDL_WAIT();
     TR_EW_LOOP((size_t)B * T * C) { const int c = i % C; const int t = (i / C) % T; out[i] = pos[(size_t)t * C + c]; }
 }
 // dst rows (strided view) = src ; backward: src.g += dst.g
 // [B][C][M] keep-mask -> rows (b, m) x C
-__global__ void zero_kernel(float* __restrict__ p, size_t n) { TR_EW_LOOP(n) p[i] = 0.f; }
+__global__ void zero_kernel(float* __restrict__ p, size_t n) {
+    TR_PDL_WAIT(); TR_EW_LOOP(n) p[i] = 0.f; }
 // stop[b*M + i] = per_step[i*B + b] + per_clip[b]   (stop-token logit = W_h . h1_i + (W_c . enc_cell + bias), decoder.py:373)
 __global__ void stop_combine_kernel(int B, int M, const float* __restrict__ step, const float* __restrict__ clip, float* __restrict__ out) {
+    TR_PDL_WAIT();
     TR_EW_LOOP((size_t)B * M) { const int b = i / M, m = i % M; out[i] = step[(size_t)m * B + b] + clip[b]; }
 }
 __global__ void stop_combine_bwd_kernel(int B, int M, const float* __restrict__ g, float* __restrict__ gstep, float* __restrict__ gclip) {
+    TR_PDL_WAIT();
     TR_EW_LOOP((size_t)B * M) { const int m = i / B, b = i % B; gstep[i] += g[(size_t)b * M + m]; }
     TR_EW_LOOP((size_t)B) { float a = 0.f; for (int m = 0; m < M; ++m) a += g[(size_t)i * M + m]; gclip[i] += a; }
 }
@@ -69,12 +73,12 @@ struct DecoderTrain {
     void release() { drop_graphs(); e.release(); io.free_all(); if (cs) cudaStreamDestroy(cs); cs = nullptr; }
 
     static TT assign(Engine& e, const TT& dst_view, const TT& src) {
-        ew_fwd_kernel<EW_COPY><<<ew_blocks(src.numel()), 256, 0, e.s>>>(src.rows, src.cols, src.v, src.rs, nullptr, 0, 0.f, 1, dst_view.v, dst_view.rs);
+        launch(ew_fwd_kernel<EW_COPY>, ew_blocks(src.numel()), 256, 0, e.s, src.rows, src.cols, src.v, src.rs, nullptr, 0, 0.f, 1, dst_view.v, dst_view.rs);
         e.ck("assign");
         Engine* pe = &e;
         e.tape.push_back([=]() {
             if (!src.g || !dst_view.g) return;
-            ew_bwd_kernel<EW_COPY><<<ew_blocks(src.numel()), 256, 0, pe->s>>>(src.rows, src.cols, nullptr, 0, nullptr, 0, 0.f, dst_view.g, dst_view.rs, src.g, src.rs);
+            launch(ew_bwd_kernel<EW_COPY>, ew_blocks(src.numel()), 256, 0, pe->s, src.rows, src.cols, nullptr, 0, nullptr, 0, 0.f, dst_view.g, dst_view.rs, src.g, src.rs);
             pe->ck("assign bwd");
         });
         return dst_view;
@@ -200,7 +204,7 @@ struct DecoderTrain {
         TT enc_cell = lin(e.concat_cols({cf, cb}), P + "E_C.linear_layer", 512);
         TT enc = e.add(e.add_rows(lin(rnn_out, P + "encoder_proj.linear_layer", 512), att_site, T), residual);
         float* pos_tile = e.scratch((size_t)B * T * 512);
-        tile_pos_kernel<<<ew_blocks((size_t)B * T * 512), 256, 0, s>>>(B, T, 512, pos, pos_tile);
+        launch(tile_pos_kernel, ew_blocks((size_t)B * T * 512), 256, 0, s, B, T, 512, pos, pos_tile);
         e.ck("pos tile");
         TT Kmem = e.add_const(e.psine(multihop(enc, P + "K.0."), e.param(P + "K.1.w", 1, 512)), pos_tile, 512);
         TT Vmem = e.add_const(e.psine(multihop(enc, P + "V.0."), e.param(P + "V.1.w", 1, 512)), pos_tile, 512);
@@ -233,10 +237,10 @@ struct DecoderTrain {
         }
         // ---- the M-step loop (decoder.py:343-375) ---------------------------------------------------------------------------
         TT mel_rows = e.make(B * M, 80, false);                     // teacher frames as rows (b, i)
-        bcl_to_rows_tr_kernel<<<ew_blocks((size_t)B * 80 * M), 256, 0, s>>>(B, 80, M, io.mels, mel_rows.v, 80);
+        launch(bcl_to_rows_tr_kernel, ew_blocks((size_t)B * 80 * M), 256, 0, s, B, 80, M, io.mels, mel_rows.v, 80);
         e.ck("mels -> rows");
         TT zeros80 = e.make(B, 80, false);
-        zero_kernel<<<ew_blocks((size_t)B * 80), 256, 0, s>>>(zeros80.v, (size_t)B * 80);
+        launch(zero_kernel, ew_blocks((size_t)B * 80), 256, 0, s, zeros80.v, (size_t)B * 80);
         e.ck("zeros");
         TT bos = e.add_rows(zeros80, e.param(P + "BOS", 1, 80), B);                            // torch.tile(self.BOS, (N,1,1))
         outputs = e.make(B * M, 80);
@@ -246,7 +250,7 @@ struct DecoderTrain {
         TT HH = e.make(M * B, 1024), CC = e.make(M * B, 1024);
         TT hh_prev = e.concat_cols({hf, hb});
         TT cc_prev = e.make(B, 1024, false);
-        zero_kernel<<<ew_blocks((size_t)B * 1024), 256, 0, s>>>(cc_prev.v, (size_t)B * 1024);
+        launch(zero_kernel, ew_blocks((size_t)B * 1024), 256, 0, s, cc_prev.v, (size_t)B * 1024);
         e.ck("zeros");
         TT ys = bos;
         TT temp = e.param(P + "temperature", 1, 1), ctemp = e.param(P + "content.temperature", 1, 1);
@@ -285,11 +289,11 @@ struct DecoderTrain {
             TT Wst_h = Wst.colslice(0, 512), Wst_c = Wst.colslice(512, 512);
             TT per_step = e.linear(HH.colslice(512, 512), Wst_h, nullptr);                     // [M*B, 1], rows (step, clip)
             TT per_clip = e.linear(enc_cell, Wst_c, &bst);                                     // [B, 1]
-            stop_combine_kernel<<<ew_blocks((size_t)B * M), 256, 0, s>>>(B, M, per_step.v, per_clip.v, stops.v);
+            launch(stop_combine_kernel, ew_blocks((size_t)B * M), 256, 0, s, B, M, per_step.v, per_clip.v, stops.v);
             e.ck("stop combine");
             Engine* pe = &e; const int Bc = B, Mc = M; TT st = stops;
             e.tape.push_back([=]() {
-                stop_combine_bwd_kernel<<<ew_blocks((size_t)Bc * Mc), 256, 0, pe->s>>>(Bc, Mc, st.g, per_step.g, per_clip.g);
+                launch(stop_combine_bwd_kernel, ew_blocks((size_t)Bc * Mc), 256, 0, pe->s, Bc, Mc, st.g, per_step.g, per_clip.g);
                 pe->ck("stop combine bwd");
             });
         }
@@ -307,23 +311,23 @@ struct DecoderTrain {
                     if (i != 0) y = e.add(y, x);
                 }
                 TT mrows = e.make(B * M, cout, false);              // keep mask [B,C,M] -> rows (b, m) x C
-                bcl_to_rows_tr_kernel<<<ew_blocks((size_t)B * cout * M), 256, 0, s>>>(B, cout, M, io.post[i], mrows.v, cout);
+                launch(bcl_to_rows_tr_kernel, ew_blocks((size_t)B * cout * M), 256, 0, s, B, cout, M, io.post[i], mrows.v, cout);
                 e.ck("post mask rows");
                 x = e.dropout(y, mrows.v, cout, 0.5f);
             }
             post = e.add(x, outputs);
         }
         // ---- outputs in the caller's layouts (staged) ------------------------------------------------------------------------------
-        rows_to_bcl_tr_kernel<<<ew_blocks((size_t)B * 80 * M), 256, 0, s>>>(B, 80, M, outputs.v, outputs.rs, io.out_mel); e.ck("out mel");
-        rows_to_bcl_tr_kernel<<<ew_blocks((size_t)B * 80 * M), 256, 0, s>>>(B, 80, M, post.v, post.rs, io.out_post); e.ck("out post");
+        launch(rows_to_bcl_tr_kernel, ew_blocks((size_t)B * 80 * M), 256, 0, s, B, 80, M, outputs.v, outputs.rs, io.out_mel); e.ck("out mel");
+        launch(rows_to_bcl_tr_kernel, ew_blocks((size_t)B * 80 * M), 256, 0, s, B, 80, M, post.v, post.rs, io.out_post); e.ck("out post");
         L2S_CUDA(cudaMemcpyAsync(io.out_stop, stops.v, (size_t)B * M * sizeof(float), cudaMemcpyDeviceToDevice, s));
         L2S_CUDA(cudaMemcpyAsync(io.out_cdis, cdis.v, (size_t)B * minT * 501 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
     void backward_body(cudaStream_t s) {
         e.s = s;
         e.begin_backward();
-        bcl_to_rows_tr_kernel<<<ew_blocks((size_t)B * 80 * M), 256, 0, s>>>(B, 80, M, st.g_mel, h.outputs.g, 80); e.ck("g mel");
-        bcl_to_rows_tr_kernel<<<ew_blocks((size_t)B * 80 * M), 256, 0, s>>>(B, 80, M, st.g_post, h.post.g, 80); e.ck("g post");
+        launch(bcl_to_rows_tr_kernel, ew_blocks((size_t)B * 80 * M), 256, 0, s, B, 80, M, st.g_mel, h.outputs.g, 80); e.ck("g mel");
+        launch(bcl_to_rows_tr_kernel, ew_blocks((size_t)B * 80 * M), 256, 0, s, B, 80, M, st.g_post, h.post.g, 80); e.ck("g post");
         L2S_CUDA(cudaMemcpyAsync(h.stops.g, st.g_stop, (size_t)B * M * sizeof(float), cudaMemcpyDeviceToDevice, s));
         L2S_CUDA(cudaMemcpyAsync(h.cdis.g, st.g_cdis, (size_t)B * h.minT * 501 * sizeof(float), cudaMemcpyDeviceToDevice, s));
         e.backward();
