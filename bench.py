@@ -89,13 +89,18 @@ class ClockSampler:
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index):
-        self.index, self.lines, self.proc = index, [], None
+    def __init__(self, rank, world):
+        """One poller for the whole job, on rank 0, over the GPUs of all local ranks: every NVML query takes a driver-wide lock, and
+        eight pollers at 10 Hz next to eight ranks that launch a graph every 25 ms showed up as rank-to-rank jitter at N = 8."""
+        self.index, self.lines, self.proc = ",".join(str(i) for i in range(world)), [], None
+        self.enabled = rank == 0
 
     def start(self):
+        if not self.enabled:
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", self.index], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -262,7 +267,7 @@ def run_train_step(args, rank, local_rank, world):
     for _ in range(max(args.warmup, 3)):
         step(video, spk, mels, gate)
     barrier()
-    sampler = ClockSampler(local_rank); sampler.start()
+    sampler = ClockSampler(rank, world); sampler.start()
     launches0 = be.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for i in range(args.steps):
@@ -343,7 +348,7 @@ def run_train_tail(args, rank, local_rank, world):
     for t in range(max(args.warmup, 3)):
         g.copy_(g0); step(t + 1)
     barrier()
-    sampler = ClockSampler(local_rank); sampler.start()
+    sampler = ClockSampler(rank, world); sampler.start()
     launches0 = be.launch_count()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     for i in range(args.steps):
@@ -476,7 +481,7 @@ def main():
         be.infer(video, wav, g, STEPS_PER_CLIP, prec)
     barrier()
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(rank, world)
     sampler.start()
     launches0 = be.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
