@@ -34,7 +34,7 @@ typedef struct l2s_ctx l2s_ctx;
 #define L2S_PART_SPEAKER 2 /* speaker_encoder.*  (model/modules/audio.py:110-150)          */
 #define L2S_PART_DECODER 4 /* decoder.*          (model/modules/decoder.py:274-444)        */
 
-#define L2S_PRECISION_FP32 0 /* exact fp32 FMA everywhere (parity mode) */
+#define L2S_PRECISION_FP32 0 /* fp32-grade everywhere: 3xTF32 tensor-core products with fp32 accumulation + fp32 FMAs (parity mode) */
 #define L2S_PRECISION_BF16 1 /* bf16 tensor-core stem (config 2 of BASELINE.json); decoder stays fp32 */
 
 int l2s_version(void);
@@ -154,7 +154,7 @@ int l2s_clip_adamw_step(l2s_ctx* ctx, float* p, float* g, float* m, float* v, fl
  * updated in place by the forward pass as nn.BatchNorm*d does in train()).  Pointers stay owned by the caller and must stay
  * valid; re-binding a key replaces it.  An optimizer step therefore needs no re-bind / re-pack. */
 int l2s_train_bind(l2s_ctx* ctx, const char* key, float* param, float* grad, int64_t numel);
-/* The train-mode forward / backward calls below launch ~13 K small kernels per step.  With graphs enabled (the default) the
+/* The train-mode forward / backward calls below launch ~5 K small dependent kernels per step.  With graphs enabled (the default) the
  * second call with the same shapes captures that launch sequence as a CUDA graph and later calls replay it (inputs are staged
  * into library memory first, so caller tensors may move between steps; re-binding a key to different memory drops the graphs).
  * Results are bit-identical either way.  enabled = 0 runs every call eagerly and frees the captured graphs. */

@@ -8,8 +8,8 @@
 // kernels on the tape; `backward()` replays the tape in reverse.  Parameters are NOT copied: the library reads the caller's
 // (PyTorch-owned) fp32 parameter memory and accumulates into the caller's gradient memory (l2s_train_bind), so an optimizer
 // step needs no re-bind / re-pack.  All reductions have a fixed order (no floating-point atomics): results are
-// run-to-run deterministic.  Exact fp32 FMA arithmetic (the GEMMs here are SIMT; the inference path's tcgen05 kernels stay
-// the fast path for inference).
+// run-to-run deterministic.  fp32 FMA arithmetic; the large GEMMs of the decoder run as 3xTF32 tensor-core products with fp32
+// accumulation, those of the video frontend stay on FMAs (sgemm_kernel says why).
 //
 // Speed: a train step is ~5 K small dependent launches (8 clips per GPU: every per-step layer is a few-row GEMM).  The arenas hand
 // out the same addresses for the same shapes, so the forward and the backward launch sequences of a (B, T, M) key are captured
