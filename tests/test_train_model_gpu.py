@@ -214,6 +214,36 @@ def test_graph_replay_is_bit_identical_to_eager(be):
         be.train_set_graphs(True)
 
 
+def test_decoder_train_without_input_gradients(be):
+    """want_input_grads = 0 (the C ABI's switch for a decoder trained on frozen features): the parameter gradients are the
+    same bits, no input-gradient buffers are touched — eager and replayed."""
+    from oracle import train_oracle as TO
+    B, T, M = 3, 29, 5
+    w = _decoder_weights(1234, True)
+    dev, grads = _bind(be, w)
+    visual, face = synth.visual_features(B, T, seed=23)
+    mels = synth.mel_like(B, M, seed=23) * 2 - 5
+    noise = TO.reference_noise(B, T, M, 0.5, with_video=False, generator=torch.Generator().manual_seed(23)).to("cuda")
+    g_out = [torch.randn(B, 80, M, device="cuda"), torch.randn(B, 80, M, device="cuda"), torch.randn(B, M, 1, device="cuda"), None]
+
+    def one_pass(want):
+        for v in grads.values():
+            if v is not None:
+                v.zero_()
+        be.decoder_train_fwd(visual.cuda(), face[:, 0].cuda(), mels.cuda(), noise, want_input_grads=want)
+        gv, gs = be.decoder_train_bwd(*g_out, B, T, want_input_grads=want)
+        torch.cuda.synchronize()
+        return gv, gs, {k: v.clone() for k, v in grads.items() if v is not None}
+
+    gv, gs, ref = one_pass(True)
+    assert gv is not None and gs is not None
+    for attempt in range(3):                     # eager, captured, replayed
+        gv0, gs0, got = one_pass(False)
+        assert gv0 is None and gs0 is None
+        for k in ref:
+            assert torch.equal(got[k], ref[k]), (attempt, k)
+
+
 def test_video_graph_replay_is_bit_identical_to_eager(be):
     B, T = 2, 5
     w = {k: v for k, v in spec.seeded_state_dict(spec.encoder_spec("encoder."), 1234).items()}
