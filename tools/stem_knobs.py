@@ -15,9 +15,11 @@ e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
 e0.record()
 for _ in range(5): be.video_fwd(v, _lib.PRECISION_BF16)
 e1.record(); torch.cuda.synchronize()
-print('skip', os.environ.get('L2S_TC_DEBUG_SKIP'), 'video B=32 ms', round(e0.elapsed_time(e1) / 5, 3), flush=True)
+print('skip', os.environ.get('L2S_TC_DEBUG_SKIP'), 'niter', os.environ.get('L2S_TC_DEBUG_NITER'), 'video B=32 ms', round(e0.elapsed_time(e1) / 5, 3), flush=True)
 """ % ROOT
-for skip in (0, 1, 2, 4, 6, 3, 7, 39):
-    env = dict(os.environ, L2S_TC_DEBUG_SKIP=str(skip))
+import itertools
+cases = [(k, 0) for k in (0, 1, 2, 4, 6, 3, 7, 39)] + [(39, n) for n in (1, 2, 5)] + [(0, n) for n in (1, 2, 5)]
+for skip, niter in cases:
+    env = dict(os.environ, L2S_TC_DEBUG_SKIP=str(skip), L2S_TC_DEBUG_NITER=str(niter))
     r = subprocess.run([sys.executable, "-c", CODE], env=env, capture_output=True, text=True, timeout=300)
     print((r.stdout.strip().splitlines() or ["?"])[-1], r.stderr.strip().splitlines()[-1:] if r.returncode else "")
