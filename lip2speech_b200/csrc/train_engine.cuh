@@ -82,9 +82,12 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const f
                                                     float* __restrict__ C, int ldc, int accumulate, int kper) {
     TR_PDL_WAIT();
     constexpr int BM = 64, BN = 64, BK = 32;
-    constexpr int A_LD = TA == 0 ? BK + 4 : BM + 8, B_LD = TB == 0 ? BN + 8 : BK + 4;
-    __shared__ float As[BM * (BK + 4)];                                // both layouts need 2304 floats
-    __shared__ float Bs[BN * (BK + 4)];
+    // EXACT keeps BOTH tiles k-major with a row stride of 68 floats: a thread then reads its 4 consecutive rows / columns of a k
+    // step as one LDS.128 each (2 shared loads per 16 FMAs); the transposing fill of a k-contiguous operand pays a 4-way conflict.
+    constexpr bool A_KMAJOR = EXACT || TA == 1, B_KMAJOR = EXACT || TB == 0;
+    constexpr int A_LD = EXACT ? BM + 4 : (TA == 0 ? BK + 4 : BM + 8), B_LD = EXACT ? BN + 4 : (TB == 0 ? BN + 8 : BK + 4);
+    __shared__ __align__(16) float As[BM * (BK + 4)];                  // every layout fits in 2304 floats
+    __shared__ __align__(16) float Bs[BN * (BK + 4)];
     static_assert(BM * (BK + 4) == BK * (BM + 8) && BN * (BK + 4) == BK * (BN + 8), "tile layouts");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3, wm = warp & 3, wn = warp >> 2;
@@ -115,15 +118,21 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const f
             }
         }
     };
-    auto a_at = [&](int m, int k) -> float { return TA == 0 ? As[m * A_LD + k] : As[k * A_LD + m]; };
-    auto b_at = [&](int k, int n) -> float { return TB == 0 ? Bs[k * B_LD + n] : Bs[n * B_LD + k]; };
+    auto a_at = [&](int m, int k) -> float { return A_KMAJOR ? As[k * A_LD + m] : As[m * A_LD + k]; };
+    auto b_at = [&](int k, int n) -> float { return B_KMAJOR ? Bs[k * B_LD + n] : Bs[n * B_LD + k]; };
     fetch(kbeg);
     for (int k0 = kbeg; k0 < K; k0 += BK) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int e = tid + i * 256;
-            if (TA == 0) As[(e >> 5) * A_LD + (e & 31)] = ra[i]; else As[(e >> 6) * A_LD + (e & 63)] = ra[i];
-            if (TB == 0) Bs[(e >> 6) * B_LD + (e & 63)] = rb[i]; else Bs[(e >> 5) * B_LD + (e & 31)] = rb[i];
+            {   // (m, k) of element e as fetched; stored at the layout's address
+                const int m = TA == 0 ? e >> 5 : e & 63, k = TA == 0 ? e & 31 : e >> 6;
+                As[A_KMAJOR ? k * A_LD + m : m * A_LD + k] = ra[i];
+            }
+            {
+                const int n = TB == 0 ? e & 63 : e >> 5, k = TB == 0 ? e >> 6 : e & 31;
+                Bs[B_KMAJOR ? k * B_LD + n : n * B_LD + k] = rb[i];
+            }
         }
         __syncthreads();
         if (k0 + BK < K) fetch(k0 + BK);
@@ -131,9 +140,9 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const f
             const int tx = tid & 15, ty = tid >> 4;
 #pragma unroll
             for (int k = 0; k < BK; ++k) {
-                float a[4], b[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { a[i] = a_at(ty + 16 * i, k); b[i] = b_at(k, tx + 16 * i); }
+                const float4 a4 = *reinterpret_cast<const float4*>(As + k * A_LD + 4 * ty);
+                const float4 b4 = *reinterpret_cast<const float4*>(Bs + k * B_LD + 4 * tx);
+                const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -161,13 +170,13 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const f
         __syncthreads();
     }
     // tensor cores: acc[j] = {(r, c), (r, c+1), (r+8, c), (r+8, c+1)}, r = m0 + 16 wm + g, c = n0 + 32 wn + 8 j + 2 t;
-    // EXACT: acc[i][j] = (m0 + ty + 16 i, n0 + tx + 16 j)
+    // EXACT: acc[i][j] = (m0 + 4 ty + i, n0 + 4 tx + j)
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int m = EXACT ? m0 + (tid >> 4) + 16 * j : m0 + wm * 16 + g + 8 * (q >> 1);
-            const int n = EXACT ? n0 + (tid & 15) + 16 * q : n0 + wn * 32 + j * 8 + 2 * t + (q & 1);
+            const int m = EXACT ? m0 + 4 * (tid >> 4) + j : m0 + wm * 16 + g + 8 * (q >> 1);
+            const int n = EXACT ? n0 + 4 * (tid & 15) + q : n0 + wn * 32 + j * 8 + 2 * t + (q & 1);
             if (m < M && n < N) {
                 float* c = C + (size_t)m * ldc + n;
                 *c = accumulate ? *c + acc[j][q] : acc[j][q];
